@@ -1,5 +1,20 @@
-"""dynamicoed.jl_b200 — B200-native batched evaluator for DynamicOED.jl's hot path."""
-from .symbolic import (Differential, Eq, Equation, ODESystem, Num, independent_variable,
+"""dynamicoed.jl_b200 — B200-native batched evaluator for DynamicOED.jl's hot path.
+
+Host-side mirror of the reference's public surface (/root/reference/src/DynamicOED.jl:31-42):
+``OEDSystem``, the six criteria, ``OEDProblem``, ``get_timegrids``, ``get_initial_variables``,
+plus ``OptimizationProblem`` — with objective and gradient evaluated by ``libdynoed_cuda.so``.
+"""
+from .symbolic import (Differential, Eq, Equation, Num, ODESystem, independent_variable,
                        observed_variables, parameters, variables)
-from .augment import OEDSystem, structural_simplify, dae_index_lowering
-from .discretize import Timegrid
+from .augment import OEDSystem, dae_index_lowering, structural_simplify
+from .criteria import (ACriterion, DCriterion, ECriterion, FisherACriterion, FisherDCriterion,
+                       FisherECriterion)
+from .discretize import ComponentVector, Timegrid
+from .problem import (RK4, ConstraintsSystem, OEDProblem, OptimizationProblem, Tsit5,
+                      build_predictor, geq, get_initial_variables, get_timegrids, leq, states)
+
+__all__ = ["OEDSystem", "FisherACriterion", "FisherDCriterion", "FisherECriterion", "ACriterion",
+           "DCriterion", "ECriterion", "OEDProblem", "get_timegrids", "get_initial_variables",
+           "OptimizationProblem", "structural_simplify", "dae_index_lowering", "ODESystem",
+           "variables", "parameters", "observed_variables", "Differential", "Eq", "states",
+           "build_predictor", "ConstraintsSystem", "leq", "geq", "RK4", "Tsit5", "Timegrid"]

@@ -21,7 +21,7 @@ from dataclasses import dataclass, field
 
 import sympy as sp
 
-from .symbolic import (Equation, ODESystem, Num, get_measurement_rate, getbounds,
+from .symbolic import (_derivative, Equation, ODESystem, Num, get_measurement_rate, getbounds,
                        getdefault, is_measured, isinput, istunable)
 
 _SUB = str.maketrans("0123456789", "₀₁₂₃₄₅₆₇₈₉")
@@ -180,9 +180,7 @@ def build_augmented_system(sys: ODESystem, name: str | None = None) -> Augmented
 
 
 def _deriv(v: Num) -> Num:
-    d = Num(f"D({v.name})", "derivative")
-    d.of = v
-    return d
+    return _derivative(v)
 
 
 def OEDSystem(sys: ODESystem, name: str | None = None) -> AugmentedSystem:

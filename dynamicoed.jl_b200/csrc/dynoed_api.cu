@@ -1,0 +1,710 @@
+// dynoed_api.cu — the C ABI of libdynoed_cuda.so (see include/dynoed.h) and the host runtime
+// around the kernel template: model registry, per-problem device tables, scratch ownership,
+// launch configuration, the chunked H2D / compute / D2H pipeline for host buffers, arg-min.
+//
+// There is deliberately no CPU code path in here: every compute entry point launches CUDA
+// kernels or fails with DYNOED_ECUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/dynoed.h"
+#include "dynoed_kernels.cuh"
+#ifdef DYNOED_MODELS_HEADER
+#include DYNOED_MODELS_HEADER
+#else
+#include "generated/models.cuh"
+#endif
+
+namespace dynoed {
+
+static thread_local std::string g_last_error;
+
+struct ModelEntry {
+    const char* name;
+    dynoed_model_info info;
+    cudaError_t (*launch)(int method, bool grad, const EvalParams& P, int grid, int block, size_t smem,
+                          cudaStream_t st);
+    cudaError_t (*attrs)(int method, bool grad, int block, size_t smem, cudaFuncAttributes* fa,
+                         int* blocks_per_sm);
+};
+
+template <class M, class Tab, bool GRAD>
+static cudaError_t launch_one(const EvalParams& P, int grid, int block, size_t smem, cudaStream_t st) {
+    auto kern = oed_eval_kernel<M, Tab, GRAD>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, block, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+template <class M, class Tab, bool GRAD>
+static cudaError_t attrs_one(int block, size_t smem, cudaFuncAttributes* fa, int* bps) {
+    auto kern = oed_eval_kernel<M, Tab, GRAD>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(fa, kern);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, block, smem);
+}
+
+template <class M>
+static cudaError_t launch_model(int method, bool grad, const EvalParams& P, int grid, int block, size_t smem,
+                                cudaStream_t st) {
+    if (method == DYNOED_RK4)
+        return grad ? launch_one<M, TabRK4, true>(P, grid, block, smem, st)
+                    : launch_one<M, TabRK4, false>(P, grid, block, smem, st);
+    return grad ? launch_one<M, TabTsit5, true>(P, grid, block, smem, st)
+                : launch_one<M, TabTsit5, false>(P, grid, block, smem, st);
+}
+
+template <class M>
+static cudaError_t attrs_model(int method, bool grad, int block, size_t smem, cudaFuncAttributes* fa, int* bps) {
+    if (method == DYNOED_RK4)
+        return grad ? attrs_one<M, TabRK4, true>(block, smem, fa, bps) : attrs_one<M, TabRK4, false>(block, smem, fa, bps);
+    return grad ? attrs_one<M, TabTsit5, true>(block, smem, fa, bps) : attrs_one<M, TabTsit5, false>(block, smem, fa, bps);
+}
+
+template <class M>
+static ModelEntry make_entry() {
+    static_assert(M::NX <= kMaxX && M::NX * M::NP <= kMaxG && M::NTH <= kMaxTheta, "model too large");
+    static_assert(M::NCTRL <= kMaxCtrl && M::NOBS <= kMaxObs && M::NIC <= kMaxIC, "model too large");
+    ModelEntry e{};
+    e.name = M::NAME;
+    dynoed_model_info& i = e.info;
+    memset(&i, 0, sizeof(i));
+    i.nx = M::NX; i.np = M::NP; i.n_obs = M::NOBS; i.n_ctrl = M::NCTRL; i.n_ic = M::NIC;
+    i.n_theta = M::NTH; i.nz = M::NZ; i.nF = M::NF;
+    for (int k = 0; k < M::NIC; ++k) i.ic_state[k] = M::ic_state(k);
+    i.flops_primal = M::FLOPS_PRIMAL; i.flops_primal_z = M::FLOPS_PRIMAL_Z;
+    i.flops_adjoint = M::FLOPS_ADJOINT; i.flops_consts = M::FLOPS_CONSTS;
+    for (int k = 0; k < M::NX; ++k) i.x0[k] = M::default_x0()[k];
+    for (int k = 0; k < M::NX * M::NP; ++k) i.G0[k] = M::default_G0()[k];
+    for (int k = 0; k < M::NTH; ++k) i.theta[k] = M::default_theta()[k];
+    e.launch = &launch_model<M>;
+    e.attrs = &attrs_model<M>;
+    return e;
+}
+
+static const std::vector<ModelEntry>& registry() {
+    static const std::vector<ModelEntry> r = [] {
+        std::vector<ModelEntry> v;
+#define DYNOED_REG(M) v.push_back(make_entry<M>());
+        DYNOED_FOR_EACH_MODEL(DYNOED_REG)
+#undef DYNOED_REG
+        return v;
+    }();
+    return r;
+}
+
+static const ModelEntry* find_model(const char* name) {
+    if (!name) return nullptr;
+    for (const auto& e : registry())
+        if (strcmp(e.name, name) == 0) return &e;
+    return nullptr;
+}
+
+constexpr int kSlots = 4;   // pipeline depth of the host-buffer path
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    double *d_designs = nullptr, *d_crit = nullptr, *d_grad = nullptr, *d_fim = nullptr;
+    double* traj = nullptr;
+    size_t traj_bytes = 0;
+    int64_t cap = 0;   // designs
+};
+
+}  // namespace dynoed
+
+using namespace dynoed;
+
+struct dynoed_ctx {
+    int device = 0;
+    const ModelEntry* model = nullptr;
+    int method = DYNOED_RK4;
+    int stages = 4;
+    int criterion = 0;
+    int n_intervals = 0, n_steps = 0, n_var = 0, tile = 128;
+    int sm_count = 0;
+    int bps[2] = {0, 0};   // blocks per SM without / with gradient
+    cudaFuncAttributes fa[2];
+    EvalParams base;       // tables + layout + model data (batch pointers filled per launch)
+    int* d_first_step = nullptr;
+    double* d_step_t = nullptr;
+    double* d_step_h = nullptr;
+    int* d_indicators = nullptr;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    // device-pointer path scratch
+    double* traj = nullptr;
+    size_t traj_bytes = 0;
+    double* part_val = nullptr;
+    long long* part_idx = nullptr;
+    int part_cap = 0;
+    int part_used = 0;
+    double* d_best_val = nullptr;
+    long long* d_best_idx = nullptr;
+    bool have_batch = false;
+    Slot slots[kSlots];
+    int64_t launches = 0;
+    size_t scratch_bytes = 0;
+    std::string err;
+};
+
+static int fail(dynoed_ctx* ctx, int code, const std::string& msg) {
+    g_last_error = msg;
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, DYNOED_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));   \
+    } while (0)
+
+extern "C" {
+
+int dynoed_abi_version(void) { return DYNOED_ABI_VERSION; }
+int dynoed_model_count(void) { return (int)registry().size(); }
+const char* dynoed_model_name(int i) {
+    if (i < 0 || i >= (int)registry().size()) return nullptr;
+    return registry()[i].name;
+}
+int dynoed_model_query(const char* name, dynoed_model_info* out) {
+    const ModelEntry* e = find_model(name);
+    if (!e) return fail(nullptr, DYNOED_ENOMODEL, std::string("unknown model: ") + (name ? name : "(null)"));
+    if (!out) return fail(nullptr, DYNOED_EINVAL, "out is NULL");
+    *out = e->info;
+    return DYNOED_OK;
+}
+
+const char* dynoed_last_error(const dynoed_ctx* ctx) {
+    if (ctx && !ctx->err.empty()) return ctx->err.c_str();
+    return g_last_error.c_str();
+}
+
+static int ensure_partials(dynoed_ctx* ctx, int need) {
+    if (need <= ctx->part_cap) return DYNOED_OK;
+    if (ctx->part_val) cudaFree(ctx->part_val);
+    if (ctx->part_idx) cudaFree(ctx->part_idx);
+    ctx->part_val = nullptr; ctx->part_idx = nullptr;
+    int cap = std::max(need, 4096);
+    CU(cudaMalloc(&ctx->part_val, sizeof(double) * cap));
+    CU(cudaMalloc(&ctx->part_idx, sizeof(long long) * cap));
+    ctx->part_cap = cap;
+    return DYNOED_OK;
+}
+
+static size_t traj_bytes_for(const dynoed_ctx* ctx, int grid) {
+    return (size_t)grid * ctx->n_steps * ctx->model->info.nz * ctx->tile * sizeof(double);
+}
+
+static size_t smem_bytes(const dynoed_ctx* ctx) { return 128 + (size_t)ctx->tile * ctx->n_var * sizeof(double); }
+
+static int grid_for(const dynoed_ctx* ctx, int64_t n, bool grad) {
+    const int64_t ntiles = (n + ctx->tile - 1) / ctx->tile;
+    const int64_t resident = (int64_t)ctx->sm_count * std::max(ctx->bps[grad ? 1 : 0], 1);
+    return (int)std::max<int64_t>(1, std::min(ntiles, resident));
+}
+
+int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
+    dynoed_ctx* ctx = nullptr;
+    if (!d || !out) return fail(nullptr, DYNOED_EINVAL, "desc/out is NULL");
+    if (d->struct_size != sizeof(dynoed_problem_desc))
+        return fail(nullptr, DYNOED_EINVAL, "dynoed_problem_desc.struct_size mismatch (ABI)");
+    const ModelEntry* m = find_model(d->model);
+    if (!m) return fail(nullptr, DYNOED_ENOMODEL, std::string("unknown model: ") + (d->model ? d->model : "(null)"));
+    const dynoed_model_info& mi = m->info;
+    if (d->criterion < 0 || d->criterion > 5) return fail(nullptr, DYNOED_EINVAL, "criterion out of range");
+    if (d->method != DYNOED_RK4 && d->method != DYNOED_TSIT5)
+        return fail(nullptr, DYNOED_EUNSUPPORTED, "unsupported integration method");
+    const int N = d->n_intervals;
+    if (N <= 0 || !d->tgrid || !d->indicators) return fail(nullptr, DYNOED_EINVAL, "empty grid");
+    if ((mi.n_ctrl && !d->ctrl_offsets) || !d->w_offsets) return fail(nullptr, DYNOED_EINVAL, "layout offsets missing");
+    if (d->n_var <= 0 || d->tau_offset < 0 || d->tau_offset >= d->n_var)
+        return fail(nullptr, DYNOED_EINVAL, "bad n_var / tau_offset");
+    if (d->substeps <= 0 && !(d->edge_count && d->step_edges))
+        return fail(nullptr, DYNOED_EINVAL, "need substeps > 0 or explicit step edges");
+    int tile = d->tile ? d->tile : 128;
+    if (tile % 32 != 0 || tile < 32 || tile > kMaxTile) return fail(nullptr, DYNOED_EINVAL, "tile must be 32..128, multiple of 32");
+    const int nvars = mi.n_ctrl + mi.n_obs;
+    // per-variable block lengths from the indicators; all indices must be valid
+    std::vector<int> len(nvars, 0);
+    for (int v = 0; v < nvars; ++v)
+        for (int j = 0; j < N; ++j) {
+            const int k = d->indicators[v * N + j];
+            if (k < 0) return fail(nullptr, DYNOED_EINVAL, "indicator < 0: a merged interval is not covered by a variable grid");
+            len[v] = std::max(len[v], k + 1);
+        }
+    for (int v = 0; v < nvars; ++v) {
+        const int off = v < mi.n_ctrl ? d->ctrl_offsets[v] : d->w_offsets[v - mi.n_ctrl];
+        if (off < 0 || off + len[v] > d->n_var) return fail(nullptr, DYNOED_EINVAL, "design layout exceeds n_var");
+    }
+    if (mi.n_ic && (d->ic_offset < 0 || d->ic_offset + mi.n_ic > d->n_var))
+        return fail(nullptr, DYNOED_EINVAL, "ic_offset out of range");
+    for (int j = 0; j < N; ++j)
+        if (!(d->tgrid[j + 1] > d->tgrid[j])) return fail(nullptr, DYNOED_EINVAL, "tgrid must be strictly increasing");
+
+    ctx = new dynoed_ctx();
+    ctx->device = device;
+    ctx->model = m;
+    ctx->method = d->method;
+    ctx->stages = d->method == DYNOED_RK4 ? TabRK4::S : TabTsit5::S;
+    ctx->criterion = d->criterion;
+    ctx->n_intervals = N;
+    ctx->n_var = d->n_var;
+    ctx->tile = tile;
+
+    // step tables: t and h per step, same arithmetic as the oracle (h = L/m, t = t0 + s*h for
+    // uniform substeps; t = t0 + e_s*L, h = (t0 + e_{s+1}*L) - t for explicit edges)
+    std::vector<int> first(N + 1, 0);
+    std::vector<double> st, sh;
+    {
+        size_t eoff = 0;
+        for (int j = 0; j < N; ++j) {
+            const double t0 = d->tgrid[j], L = d->tgrid[j + 1] - d->tgrid[j];
+            first[j] = (int)st.size();
+            if (d->substeps > 0) {
+                const double h = L / d->substeps;
+                for (int s = 0; s < d->substeps; ++s) { st.push_back(t0 + s * h); sh.push_back(h); }
+            } else {
+                const int ne = d->edge_count[j];
+                if (ne < 2) { delete ctx; return fail(nullptr, DYNOED_EINVAL, "edge_count < 2"); }
+                for (int s = 0; s + 1 < ne; ++s) {
+                    const double ts = t0 + d->step_edges[eoff + s] * L;
+                    st.push_back(ts);
+                    sh.push_back((t0 + d->step_edges[eoff + s + 1] * L) - ts);
+                }
+                eoff += ne;
+            }
+        }
+        first[N] = (int)st.size();
+    }
+    ctx->n_steps = (int)st.size();
+
+    auto bail = [&](int code, const std::string& msg) { dynoed_destroy(ctx); return fail(nullptr, code, msg); };
+#define CUC(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return bail(DYNOED_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+    CUC(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUC(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    CUC(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    CUC(cudaMalloc(&ctx->d_first_step, sizeof(int) * (N + 1)));
+    CUC(cudaMalloc(&ctx->d_step_t, sizeof(double) * st.size()));
+    CUC(cudaMalloc(&ctx->d_step_h, sizeof(double) * st.size()));
+    CUC(cudaMalloc(&ctx->d_indicators, sizeof(int) * nvars * N));
+    CUC(cudaMemcpy(ctx->d_first_step, first.data(), sizeof(int) * (N + 1), cudaMemcpyHostToDevice));
+    CUC(cudaMemcpy(ctx->d_step_t, st.data(), sizeof(double) * st.size(), cudaMemcpyHostToDevice));
+    CUC(cudaMemcpy(ctx->d_step_h, sh.data(), sizeof(double) * st.size(), cudaMemcpyHostToDevice));
+    CUC(cudaMemcpy(ctx->d_indicators, d->indicators, sizeof(int) * nvars * N, cudaMemcpyHostToDevice));
+    CUC(cudaMalloc(&ctx->d_best_val, sizeof(double)));
+    CUC(cudaMalloc(&ctx->d_best_idx, sizeof(long long)));
+
+    EvalParams& P = ctx->base;
+    memset(&P, 0, sizeof(P));
+    P.n_var = d->n_var;
+    P.tile = tile;
+    P.n_intervals = N;
+    P.n_steps = ctx->n_steps;
+    P.first_step = ctx->d_first_step;
+    P.step_t = ctx->d_step_t;
+    P.step_h = ctx->d_step_h;
+    P.indicators = ctx->d_indicators;
+    for (int k = 0; k < mi.n_ctrl; ++k) P.ctrl_off[k] = d->ctrl_offsets[k];
+    for (int k = 0; k < mi.n_obs; ++k) P.w_off[k] = d->w_offsets[k];
+    P.ic_off = d->ic_offset;
+    P.tau_off = d->tau_offset;
+    P.criterion = d->criterion;
+    for (int k = 0; k < mi.n_theta; ++k) P.theta[k] = d->theta ? d->theta[k] : mi.theta[k];
+    for (int k = 0; k < mi.nx; ++k) P.x0[k] = d->x0 ? d->x0[k] : mi.x0[k];
+    for (int k = 0; k < mi.nx * mi.np; ++k) P.G0[k] = d->G0 ? d->G0[k] : mi.G0[k];
+
+    const size_t smem = smem_bytes(ctx);
+    if (smem > (size_t)prop.sharedMemPerBlockOptin)
+        return bail(DYNOED_EINVAL, "tile * n_var does not fit in shared memory; use a smaller tile");
+    for (int g = 0; g < 2; ++g) {
+        CUC(m->attrs(ctx->method, g == 1, tile, smem, &ctx->fa[g], &ctx->bps[g]));
+        if (ctx->bps[g] < 1) return bail(DYNOED_ECUDA, "kernel cannot be resident with this tile size");
+    }
+#undef CUC
+    *out = ctx;
+    return DYNOED_OK;
+}
+
+void dynoed_destroy(dynoed_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    for (auto& s : ctx->slots) {
+        if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+        cudaFree(s.d_designs); cudaFree(s.d_crit); cudaFree(s.d_grad); cudaFree(s.d_fim); cudaFree(s.traj);
+    }
+    cudaFree(ctx->d_first_step); cudaFree(ctx->d_step_t); cudaFree(ctx->d_step_h); cudaFree(ctx->d_indicators);
+    cudaFree(ctx->traj); cudaFree(ctx->part_val); cudaFree(ctx->part_idx);
+    cudaFree(ctx->d_best_val); cudaFree(ctx->d_best_idx);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int dynoed_set_criterion(dynoed_ctx* ctx, int criterion) {
+    if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    if (criterion < 0 || criterion > 5) return fail(ctx, DYNOED_EINVAL, "criterion out of range");
+    ctx->criterion = criterion;
+    ctx->base.criterion = criterion;
+    return DYNOED_OK;
+}
+
+int dynoed_set_stream(dynoed_ctx* ctx, void* s) {
+    if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    ctx->stream = (cudaStream_t)s;   // NULL is the CUDA legacy default stream
+    return DYNOED_OK;
+}
+
+int dynoed_own_stream(dynoed_ctx* ctx) {
+    if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    ctx->stream = ctx->own_stream;
+    return DYNOED_OK;
+}
+
+// 0 = host, 1 = device/managed
+static int ptr_kind(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? 1 : 0;
+}
+
+// launch on device-resident buffers
+static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad,
+                         double* fim, double* xgrid, double* traj, double* part_val, long long* part_idx,
+                         int grid, cudaStream_t st) {
+    EvalParams P = ctx->base;
+    P.designs = designs; P.crit = crit; P.grad = grad; P.fim = fim; P.xgrid = xgrid;
+    P.traj = traj; P.n = n;
+    P.part_val = part_val; P.part_idx = part_idx;
+    P.use_tma = ((reinterpret_cast<uintptr_t>(designs) % 16 == 0) &&
+                 (grad == nullptr || reinterpret_cast<uintptr_t>(grad) % 16 == 0) &&
+                 (((size_t)ctx->tile * ctx->n_var * 8) % 16 == 0)) ? 1 : 0;
+    CU(ctx->model->launch(ctx->method, grad != nullptr, P, grid, ctx->tile, smem_bytes(ctx), st));
+    ctx->launches++;
+    return DYNOED_OK;
+}
+
+static int finish_argmin(dynoed_ctx* ctx, int parts, cudaStream_t st) {
+    argmin_final_kernel<<<1, 256, 0, st>>>(ctx->part_val, ctx->part_idx, parts, ctx->d_best_val, ctx->d_best_idx);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    ctx->have_batch = true;
+    return DYNOED_OK;
+}
+
+static int eval_device(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad, double* fim,
+                       double* xgrid) {
+    const bool g = grad != nullptr;
+    const int grid = grid_for(ctx, n, g);
+    if (g) {
+        const size_t need = traj_bytes_for(ctx, grid);
+        if (need > ctx->traj_bytes) {
+            if (ctx->traj) { CU(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->traj); ctx->traj = nullptr; }
+            const size_t full = traj_bytes_for(ctx, ctx->sm_count * std::max(ctx->bps[1], 1));
+            const size_t want = std::max(need, std::min(full, need * 4));
+            CU(cudaMalloc(&ctx->traj, want));
+            ctx->scratch_bytes += want - ctx->traj_bytes;
+            ctx->traj_bytes = want;
+        }
+    }
+    int rc = ensure_partials(ctx, grid);
+    if (rc) return rc;
+    rc = launch_device(ctx, designs, n, crit, grad, fim, xgrid, ctx->traj, ctx->part_val, ctx->part_idx, grid,
+                       ctx->stream);
+    if (rc) return rc;
+    return finish_argmin(ctx, grid, ctx->stream);
+}
+
+static int ensure_slot(dynoed_ctx* ctx, Slot& s, int64_t cap, bool grad, bool fim) {
+    const int nF = ctx->model->info.nF;
+    if (!s.stream) CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    if (cap > s.cap) {
+        CU(cudaStreamSynchronize(s.stream));
+        cudaFree(s.d_designs); cudaFree(s.d_crit); cudaFree(s.d_grad); cudaFree(s.d_fim);
+        s.d_designs = s.d_crit = s.d_grad = s.d_fim = nullptr;
+        CU(cudaMalloc(&s.d_designs, sizeof(double) * cap * ctx->n_var));
+        CU(cudaMalloc(&s.d_crit, sizeof(double) * cap));
+        CU(cudaMalloc(&s.d_grad, sizeof(double) * cap * ctx->n_var));
+        CU(cudaMalloc(&s.d_fim, sizeof(double) * cap * nF));
+        ctx->scratch_bytes += sizeof(double) * (size_t)(cap - s.cap) * (2 * ctx->n_var + 1 + nF);
+        s.cap = cap;
+    }
+    if (grad) {
+        const int grid = grid_for(ctx, cap, true);
+        const size_t need = traj_bytes_for(ctx, grid);
+        if (need > s.traj_bytes) {
+            CU(cudaStreamSynchronize(s.stream));
+            cudaFree(s.traj); s.traj = nullptr;
+            CU(cudaMalloc(&s.traj, need));
+            ctx->scratch_bytes += need - s.traj_bytes;
+            s.traj_bytes = need;
+        }
+    }
+    (void)fim;
+    return DYNOED_OK;
+}
+
+// host buffers: chunked pipeline, chunk k on stream k % kSlots (H2D -> kernel -> D2H in order on
+// that stream; different chunks overlap copy engines and SMs)
+static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad, double* fim) {
+    const int nF = ctx->model->info.nF;
+    const bool g = grad != nullptr;
+    // chunk: a multiple of the tile, about 1/8 of the batch, at least 16 tiles
+    int64_t chunk = ((n / 8 + ctx->tile - 1) / ctx->tile) * ctx->tile;
+    chunk = std::max<int64_t>(chunk, 16 * ctx->tile);
+    chunk = std::min<int64_t>(chunk, ((n + ctx->tile - 1) / ctx->tile) * ctx->tile);
+    const int64_t nchunks = (n + chunk - 1) / chunk;
+    const int grid_c = grid_for(ctx, chunk, g);
+    int rc = ensure_partials(ctx, (int)(nchunks * grid_c));
+    if (rc) return rc;
+    for (int k = 0; k < kSlots && k < nchunks; ++k) {
+        rc = ensure_slot(ctx, ctx->slots[k], chunk, g, fim != nullptr);
+        if (rc) return rc;
+    }
+    // order after whatever the ctx stream was doing
+    cudaEvent_t ev;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(ev, ctx->stream));
+    for (int k = 0; k < kSlots && k < nchunks; ++k) CU(cudaStreamWaitEvent(ctx->slots[k].stream, ev, 0));
+    for (int64_t c = 0; c < nchunks; ++c) {
+        Slot& s = ctx->slots[c % kSlots];
+        const int64_t off = c * chunk, cnt = std::min(chunk, n - off);
+        CU(cudaMemcpyAsync(s.d_designs, designs + off * ctx->n_var, sizeof(double) * cnt * ctx->n_var,
+                           cudaMemcpyHostToDevice, s.stream));
+        EvalParams P = ctx->base;
+        const int grid = grid_for(ctx, cnt, g);
+        P.designs = s.d_designs; P.crit = s.d_crit; P.grad = g ? s.d_grad : nullptr; P.fim = fim ? s.d_fim : nullptr;
+        P.xgrid = nullptr; P.traj = s.traj; P.n = cnt;
+        P.part_val = ctx->part_val + c * grid_c; P.part_idx = ctx->part_idx + c * grid_c;
+        P.use_tma = (((size_t)ctx->tile * ctx->n_var * 8) % 16 == 0) ? 1 : 0;
+        P.index_base = off;
+        // unused partial slots of this chunk must not win
+        if (grid < grid_c) {
+            CU(cudaMemsetAsync(P.part_idx + grid, 0xff, sizeof(long long) * (grid_c - grid), s.stream));
+        }
+        CU(ctx->model->launch(ctx->method, g, P, grid, ctx->tile, smem_bytes(ctx), s.stream));
+        ctx->launches++;
+        CU(cudaMemcpyAsync(crit + off, s.d_crit, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s.stream));
+        if (g) CU(cudaMemcpyAsync(grad + off * ctx->n_var, s.d_grad, sizeof(double) * cnt * ctx->n_var,
+                                  cudaMemcpyDeviceToHost, s.stream));
+        if (fim) CU(cudaMemcpyAsync(fim + off * nF, s.d_fim, sizeof(double) * cnt * nF, cudaMemcpyDeviceToHost,
+                                    s.stream));
+    }
+    for (int k = 0; k < kSlots && k < nchunks; ++k) {
+        CU(cudaEventRecord(ev, ctx->slots[k].stream));
+        CU(cudaStreamWaitEvent(ctx->stream, ev, 0));
+    }
+    CU(cudaEventDestroy(ev));
+    return finish_argmin(ctx, (int)(nchunks * grid_c), ctx->stream);
+}
+
+static int eval_common(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad, double* fim,
+                       bool allow_host, bool sync) {
+    if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    ctx->err.clear();
+    if (n < 0) return fail(ctx, DYNOED_EINVAL, "n < 0");
+    if (n == 0) { ctx->have_batch = false; return DYNOED_OK; }
+    if (!designs || !crit) return fail(ctx, DYNOED_EINVAL, "designs/crit is NULL");
+    CU(cudaSetDevice(ctx->device));
+    const int kd = ptr_kind(designs);
+    if (ptr_kind(crit) != kd || (grad && ptr_kind(grad) != kd) || (fim && ptr_kind(fim) != kd))
+        return fail(ctx, DYNOED_EINVAL, "designs/crit/grad/fim must all be host or all be device pointers");
+    int rc;
+    if (kd == 1) rc = eval_device(ctx, designs, n, crit, grad, fim, nullptr);
+    else {
+        if (!allow_host) return fail(ctx, DYNOED_EINVAL, "dynoed_eval_batch_async needs device pointers");
+        rc = eval_host(ctx, designs, n, crit, grad, fim);
+    }
+    if (rc) return rc;
+    if (sync) CU(cudaStreamSynchronize(ctx->stream));
+    return DYNOED_OK;
+}
+
+int dynoed_eval_batch(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad, double* fim,
+                      uint32_t flags) {
+    (void)flags;
+    return eval_common(ctx, designs, n, crit, grad, fim, true, true);
+}
+
+int dynoed_eval_batch_async(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad,
+                            double* fim, uint32_t flags) {
+    (void)flags;
+    return eval_common(ctx, designs, n, crit, grad, fim, false, false);
+}
+
+int dynoed_sync(dynoed_ctx* ctx) {
+    if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return DYNOED_OK;
+}
+
+int dynoed_argmin(dynoed_ctx* ctx, int64_t* idx, double* val) {
+    if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    if (!ctx->have_batch) return fail(ctx, DYNOED_EINVAL, "no batch has been evaluated");
+    CU(cudaSetDevice(ctx->device));
+    double v; long long i;
+    CU(cudaMemcpyAsync(&v, ctx->d_best_val, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&i, ctx->d_best_idx, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (idx) *idx = (int64_t)i;
+    if (val) *val = v;
+    return DYNOED_OK;
+}
+
+int dynoed_trajectory(dynoed_ctx* ctx, const double* designs, int64_t n, double* X) {
+    if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    if (!designs || !X || n <= 0) return fail(ctx, DYNOED_EINVAL, "bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    const auto& mi = ctx->model->info;
+    const size_t row = (size_t)(ctx->n_intervals + 1) * (mi.nz + mi.nF);
+    const int kd = ptr_kind(designs);
+    if (ptr_kind(X) != kd) return fail(ctx, DYNOED_EINVAL, "designs/X must both be host or both be device pointers");
+    double *dd = nullptr, *dx = nullptr, *dc = nullptr;
+    CU(cudaMalloc(&dc, sizeof(double) * n));
+    int rc;
+    if (kd == 1) {
+        rc = eval_device(ctx, designs, n, dc, nullptr, nullptr, X);
+        if (!rc) CU(cudaStreamSynchronize(ctx->stream));
+    } else {
+        CU(cudaMalloc(&dd, sizeof(double) * n * ctx->n_var));
+        CU(cudaMalloc(&dx, sizeof(double) * n * row));
+        CU(cudaMemcpyAsync(dd, designs, sizeof(double) * n * ctx->n_var, cudaMemcpyHostToDevice, ctx->stream));
+        rc = eval_device(ctx, dd, n, dc, nullptr, nullptr, dx);
+        if (!rc) {
+            CU(cudaMemcpyAsync(X, dx, sizeof(double) * n * row, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    cudaFree(dd); cudaFree(dx); cudaFree(dc);
+    return rc;
+}
+
+int dynoed_criterion_batch(int device, int criterion, int np, const double* F, const double* tau, int64_t batch,
+                           double* value, double* dcdF) {
+    dynoed_ctx* ctx = nullptr;
+    if (criterion < 0 || criterion > 5) return fail(nullptr, DYNOED_EINVAL, "criterion out of range");
+    if (np < 1 || np > kMaxCritN) return fail(nullptr, DYNOED_EINVAL, "np must be 1..24");
+    if (!F || !value || batch <= 0) return fail(nullptr, DYNOED_EINVAL, "bad arguments");
+    CU(cudaSetDevice(device));
+    const int nF = np * (np + 1) / 2;
+    const int kd = ptr_kind(F);
+    if (ptr_kind(value) != kd || (tau && ptr_kind(tau) != kd) || (dcdF && ptr_kind(dcdF) != kd))
+        return fail(nullptr, DYNOED_EINVAL, "all pointers must be host or all device");
+    const int block = 64;
+    const int grid = (int)((batch + block - 1) / block);
+    if (kd == 1) {
+        criterion_batch_kernel<<<grid, block>>>(F, tau, np, batch, criterion, value, dcdF);
+        CU(cudaGetLastError());
+        CU(cudaDeviceSynchronize());
+        return DYNOED_OK;
+    }
+    double *dF = nullptr, *dt = nullptr, *dv = nullptr, *dL = nullptr;
+    CU(cudaMalloc(&dF, sizeof(double) * batch * nF));
+    CU(cudaMalloc(&dv, sizeof(double) * batch));
+    CU(cudaMemcpy(dF, F, sizeof(double) * batch * nF, cudaMemcpyHostToDevice));
+    if (tau) { CU(cudaMalloc(&dt, sizeof(double) * batch)); CU(cudaMemcpy(dt, tau, sizeof(double) * batch, cudaMemcpyHostToDevice)); }
+    if (dcdF) CU(cudaMalloc(&dL, sizeof(double) * batch * nF));
+    criterion_batch_kernel<<<grid, block>>>(dF, dt, np, batch, criterion, dv, dL);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(value, dv, sizeof(double) * batch, cudaMemcpyDeviceToHost));
+    if (dcdF) CU(cudaMemcpy(dcdF, dL, sizeof(double) * batch * nF, cudaMemcpyDeviceToHost));
+    cudaFree(dF); cudaFree(dt); cudaFree(dv); cudaFree(dL);
+    return DYNOED_OK;
+}
+
+int dynoed_fp64_peak(int device, void* stream, double* tflops, double* ms_out) {
+    dynoed_ctx* ctx = nullptr;
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int block = 256, grid = prop.multiProcessorCount * 8, iters = 4096;
+    double* out = nullptr;
+    CU(cudaMalloc(&out, sizeof(double) * (size_t)grid * block));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(e0, st));
+        fp64_peak_kernel<<<grid, block, 0, st>>>(out, iters, 1.0);
+        CU(cudaEventRecord(e1, st));
+        CU(cudaEventSynchronize(e1));
+        float ms; CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    CU(cudaGetLastError());
+    const double flops = 2.0 * 8 * 16 * (double)iters * grid * block;
+    if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    return DYNOED_OK;
+}
+
+int dynoed_kernel_stats_query(dynoed_ctx* ctx, int with_grad, dynoed_kernel_stats* o) {
+    if (!ctx || !o) return fail(ctx, DYNOED_EINVAL, "ctx/out is NULL");
+    const int g = with_grad ? 1 : 0;
+    const auto& mi = ctx->model->info;
+    memset(o, 0, sizeof(*o));
+    o->regs_per_thread = ctx->fa[g].numRegs;
+    o->static_smem = (int)ctx->fa[g].sharedSizeBytes;
+    o->dynamic_smem = (int)smem_bytes(ctx);
+    o->blocks_per_sm = ctx->bps[g];
+    o->grid = ctx->sm_count * ctx->bps[g];
+    o->block = ctx->tile;
+    o->sm_count = ctx->sm_count;
+    o->launches = ctx->launches;
+    o->scratch_bytes = (int64_t)ctx->scratch_bytes;
+    o->n_steps = ctx->n_steps;
+    o->stages = ctx->stages;
+    // algorithmic flops of the straight-line code the emitter produced (FMA = 2):
+    //   forward step : S primal calls + stage states (2 NZ per non-zero a_ij) + accumulation
+    //                  (2 (NZ + NF) per stage) + h*a / h*b products
+    //   backward step: (S-1) primal_z + S adjoint calls + stage states + kb / lambda / w-bar updates
+    const int S = ctx->stages;
+    int nza = 0;
+    for (int i = 0; i < S; ++i)
+        for (int j = 0; j < i; ++j)
+            nza += (ctx->method == DYNOED_RK4 ? TabRK4::a(i, j) : TabTsit5::a(i, j)) != 0.0;
+    const double fwd = (double)S * mi.flops_primal + 2.0 * mi.nz * nza + 2.0 * (mi.nz + mi.nF) * S + nza + S;
+    const double bwd = (double)(S - 1) * mi.flops_primal_z + (double)S * mi.flops_adjoint + 2.0 * mi.nz * nza /*Z*/ +
+                       (double)S * mi.nz /*hb*lam*/ + 2.0 * mi.nz * nza /*kb*/ + (double)S * mi.nz /*lacc*/ +
+                       2.0 * S * mi.n_obs + nza + S;
+    const double epi = 10.0 * mi.nF;
+    o->flops_per_design_eval = fwd * ctx->n_steps + (double)ctx->n_intervals * mi.flops_consts + epi;
+    o->flops_per_design_grad = (fwd + bwd) * ctx->n_steps + 2.0 * ctx->n_intervals * mi.flops_consts + epi;
+    o->bytes_per_design = 8.0 * (ctx->n_var + 1 + (with_grad ? ctx->n_var : 0) + mi.nF);
+    return DYNOED_OK;
+}
+
+int dynoed_host_alloc(void** p, size_t bytes) {
+    dynoed_ctx* ctx = nullptr;
+    if (!p) return fail(nullptr, DYNOED_EINVAL, "p is NULL");
+    CU(cudaMallocHost(p, bytes));
+    return DYNOED_OK;
+}
+
+int dynoed_host_free(void* p) {
+    dynoed_ctx* ctx = nullptr;
+    CU(cudaFreeHost(p));
+    return DYNOED_OK;
+}
+
+}  // extern "C"

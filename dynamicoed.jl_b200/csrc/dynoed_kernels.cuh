@@ -1,0 +1,780 @@
+// dynoed_kernels.cuh — hand-written sm_100a kernel template for the DynamicOED hot path.
+//
+// One design per lane.  A CTA stages a tile of TILE designs (row-major [TILE][n_var] doubles,
+// the wire layout of /root/reference/src/discretize.jl:110-137) into shared memory with one TMA
+// bulk copy, integrates the sensitivity-augmented system [x; vec(G); F_triu]
+// (/root/reference/src/augment.jl:223-241) over the merged measurement grid with a fixed-step
+// explicit Runge-Kutta method (restart semantics of /root/reference/src/discretize.jl:305-344:
+// piecewise-constant controls/weights per merged interval, no step straddles a grid point),
+// reduces F(t_f) to the criterion  c(F + tau I) + tau  (/root/reference/src/problem.jl:115-120,
+// /root/reference/src/fisher.jl:12-107) and — where the reference pushes ForwardDiff duals
+// through the whole integrator (/root/reference/src/problem.jl:154) — runs ONE discrete-adjoint
+// backward sweep that yields d objective / d (controls, initial conditions, weights, tau).
+// Gradients overwrite the design rows in shared memory in place and leave through one TMA bulk
+// store.  x, G, F, the adjoint and all stage values live in registers; the (x, G) checkpoints of
+// the forward sweep go to a lane-coalesced scratch in global memory (L2/HBM).
+//
+// FP64 throughout (T = Float64, /root/reference/src/augment.jl:132). No tensor cores: the
+// per-design contractions are np x np with np <= ~6.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace dynoed {
+
+constexpr int kMaxCtrl = 8;
+constexpr int kMaxObs = 8;
+constexpr int kMaxIC = 8;
+constexpr int kMaxTheta = 48;
+constexpr int kMaxX = 8;
+constexpr int kMaxG = 64;
+constexpr int kMaxTile = 128;
+
+enum Criterion : int { kFisherA = 0, kFisherD = 1, kFisherE = 2, kA = 3, kD = 4, kE = 5 };
+
+// Everything the kernel needs besides the design batch; passed by value (constant bank).
+struct EvalParams {
+    // batch
+    const double* __restrict__ designs;   // [n][n_var]
+    double* __restrict__ crit;            // [n]            objective c(F + tau I) + tau
+    double* __restrict__ grad;            // [n][n_var]     or nullptr
+    double* __restrict__ fim;             // [n][NF]        or nullptr
+    double* __restrict__ traj;            // scratch: [grid][n_steps][NZ][tile]
+    double* __restrict__ xgrid;           // [n][N+1][NZ+NF] trajectory at grid points or nullptr
+    long long n;
+    long long index_base;                 // added to the design index in arg-min records
+    int n_var;
+    int tile;
+    int use_tma;
+    // grid tables (device memory, uniform reads)
+    int n_intervals;
+    int n_steps;
+    const int* __restrict__ first_step;   // [N+1]
+    const double* __restrict__ step_t;    // [n_steps]
+    const double* __restrict__ step_h;    // [n_steps]
+    const int* __restrict__ indicators;   // [NCTRL+NOBS][N], 0-based index into the variable's own grid
+    // layout
+    int ctrl_off[kMaxCtrl];
+    int w_off[kMaxObs];
+    int ic_off;
+    int tau_off;
+    int criterion;
+    // model data
+    double theta[kMaxTheta];
+    double x0[kMaxX];
+    double G0[kMaxG];
+    // partial arg-min records, one per CTA: (value, global index)
+    double* __restrict__ part_val;
+    long long* __restrict__ part_idx;
+};
+
+// ----------------------------------------------------------------------------------------------
+// Explicit RK tableaus.  Coefficients are returned by constexpr functions so that fully unrolled
+// stage loops constant-fold them.
+// ----------------------------------------------------------------------------------------------
+struct TabRK4 {
+    static constexpr int S = 4;
+    __host__ __device__ static constexpr double a(int i, int j) {
+        constexpr double A[4][4] = {{0, 0, 0, 0}, {0.5, 0, 0, 0}, {0, 0.5, 0, 0}, {0, 0, 1.0, 0}};
+        return A[i][j];
+    }
+    __host__ __device__ static constexpr double b(int i) {
+        constexpr double B[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};
+        return B[i];
+    }
+    __host__ __device__ static constexpr double c(int i) {
+        constexpr double C[4] = {0.0, 0.5, 0.5, 1.0};
+        return C[i];
+    }
+};
+
+// Tsitouras 5(4) — the tableau of OrdinaryDiffEq.Tsit5, the reference's default algorithm
+// (/root/reference/src/problem.jl:25) — stepped with FIXED steps (b7 = 0: six stages).
+struct TabTsit5 {
+    static constexpr int S = 6;
+    __host__ __device__ static constexpr double a(int i, int j) {
+        constexpr double A[6][6] = {
+            {0, 0, 0, 0, 0, 0},
+            {0.161, 0, 0, 0, 0, 0},
+            {-0.008480655492356989, 0.335480655492357, 0, 0, 0, 0},
+            {2.8971530571054935, -6.359448489975075, 4.3622954328695815, 0, 0, 0},
+            {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 0, 0},
+            {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401,
+             -0.028269050394068383, 0}};
+        return A[i][j];
+    }
+    __host__ __device__ static constexpr double b(int i) {
+        constexpr double B[6] = {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742,
+                                 -3.290069515436081, 2.324710524099774};
+        return B[i];
+    }
+    __host__ __device__ static constexpr double c(int i) {
+        constexpr double C[6] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0};
+        return C[i];
+    }
+};
+
+// ----------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA 1-D bulk copies (SASS: UBLKCP / SYNCS)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// Criteria on M = F + tau I (packed upper triangle, column-major: k = j(j+1)/2 + i, i <= j;
+// /root/reference/src/fisher.jl:3-5).  Returns c(M) and Lambda = d c / d M (packed, symmetric).
+// ----------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int tri(int i, int j) { return i <= j ? j * (j + 1) / 2 + i : i * (i + 1) / 2 + j; }
+
+// cyclic Jacobi eigen-decomposition of a small symmetric matrix held in registers
+template <int N>
+__device__ __forceinline__ void jacobi_eig(double (&A)[N][N], double (&V)[N][N], double (&lam)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 24; ++sweep) {
+        double off = 0.0, dia = 0.0;
+#pragma unroll
+        for (int p = 0; p < N; ++p) {
+            dia += A[p][p] * A[p][p];
+#pragma unroll
+            for (int q = p + 1; q < N; ++q) off += A[p][q] * A[p][q];
+        }
+        if (off <= 1e-34 * dia || off == 0.0) break;
+#pragma unroll
+        for (int p = 0; p < N - 1; ++p) {
+#pragma unroll
+            for (int q = p + 1; q < N; ++q) {
+                const double apq = A[p][q];
+                if (apq != 0.0) {
+                    const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+                    const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                    const double cs = 1.0 / sqrt(tt * tt + 1.0);
+                    const double sn = tt * cs;
+#pragma unroll
+                    for (int k = 0; k < N; ++k) {
+                        const double akp = A[k][p], akq = A[k][q];
+                        A[k][p] = cs * akp - sn * akq;
+                        A[k][q] = sn * akp + cs * akq;
+                    }
+#pragma unroll
+                    for (int k = 0; k < N; ++k) {
+                        const double apk = A[p][k], aqk = A[q][k];
+                        A[p][k] = cs * apk - sn * aqk;
+                        A[q][k] = sn * apk + cs * aqk;
+                    }
+#pragma unroll
+                    for (int k = 0; k < N; ++k) {
+                        const double vkp = V[k][p], vkq = V[k][q];
+                        V[k][p] = cs * vkp - sn * vkq;
+                        V[k][q] = sn * vkp + cs * vkq;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) lam[i] = A[i][i];
+}
+
+template <int N>
+__device__ __forceinline__ void criterion_eval(const double (&F)[N * (N + 1) / 2], double tau, int crit,
+                                               double& value, double (&L)[N * (N + 1) / 2]) {
+    constexpr int NF = N * (N + 1) / 2;
+    if constexpr (N == 1) {
+        const double m = F[0] + tau;
+        switch (crit) {
+            case kFisherA: case kFisherD: case kFisherE: value = -m; L[0] = -1.0; break;
+            default: value = 1.0 / m; L[0] = -1.0 / (m * m); break;
+        }
+        return;
+    } else if constexpr (N == 2) {
+        const double a = F[0] + tau, b = F[1], d = F[2] + tau;
+        const double det = fma(a, d, -(b * b));
+        const double tr = a + d;
+        if (crit == kFisherA) { value = -tr; L[0] = -1.0; L[1] = 0.0; L[2] = -1.0; return; }
+        if (crit == kFisherD) { value = -det; L[0] = -d; L[1] = b; L[2] = -a; return; }
+        if (crit == kD) {
+            const double id = 1.0 / det, s = -id * id;
+            value = id; L[0] = s * d; L[1] = -s * b; L[2] = s * a; return;
+        }
+        if (crit == kA) {
+            // tr M^-1 = tr / det ;  d/dM = -M^-2 = -adj(M)^2 / det^2
+            const double id = 1.0 / det, s = -id * id;
+            value = tr * id;
+            L[0] = s * fma(d, d, b * b);
+            L[1] = -s * b * tr;
+            L[2] = s * fma(a, a, b * b);
+            return;
+        }
+        // eigen-based: lambda_min and its unit eigenvector (stable forms)
+        const double mid = 0.5 * tr, hd = 0.5 * (a - d);
+        const double rad = sqrt(fma(hd, hd, b * b));
+        double lmin;
+        if (mid >= 0.0) { const double lmax = mid + rad; lmin = (lmax != 0.0) ? det / lmax : mid - rad; }
+        else lmin = mid - rad;
+        double v0, v1;
+        if (b == 0.0) { v0 = (a <= d) ? 1.0 : 0.0; v1 = 1.0 - v0; }
+        else {
+            // (M - lmin I) v = 0: rows (a - lmin, b) and (b, d - lmin); take the better-conditioned one
+            const double p0 = b, p1 = lmin - a, q0 = lmin - d, q1 = b;
+            const double np2 = fma(p0, p0, p1 * p1), nq2 = fma(q0, q0, q1 * q1);
+            if (np2 >= nq2) { const double r = rsqrt(np2); v0 = p0 * r; v1 = p1 * r; }
+            else { const double r = rsqrt(nq2); v0 = q0 * r; v1 = q1 * r; }
+        }
+        if (crit == kFisherE) { value = -lmin; L[0] = -v0 * v0; L[1] = -v0 * v1; L[2] = -v1 * v1; return; }
+        {   // kE: max_i 1/lambda_i ; for positive definite M this is 1/lambda_min
+            const double lmax = tr - lmin;
+            double lk = lmin, w0 = v0, w1 = v1;
+            if (1.0 / lmax > 1.0 / lmin) { lk = lmax; w0 = -v1; w1 = v0; }
+            const double s = -1.0 / (lk * lk);
+            value = 1.0 / lk; L[0] = s * w0 * w0; L[1] = s * w0 * w1; L[2] = s * w1 * w1;
+        }
+        return;
+    } else {
+        double A[N][N], V[N][N], lam[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+            for (int i = 0; i <= j; ++i) {
+                const double v = F[tri(i, j)] + (i == j ? tau : 0.0);
+                A[i][j] = v; A[j][i] = v;
+            }
+        if (crit == kFisherA) {
+            double tr = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) tr += A[i][i];
+            value = -tr;
+#pragma unroll
+            for (int k = 0; k < NF; ++k) L[k] = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) L[tri(i, i)] = -1.0;
+            return;
+        }
+        jacobi_eig<N>(A, V, lam);
+        double det = 1.0, sinv = 0.0;
+        int kmin = 0, kinvmax = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            det *= lam[i]; sinv += 1.0 / lam[i];
+            if (lam[i] < lam[kmin]) kmin = i;
+            if (1.0 / lam[i] > 1.0 / lam[kinvmax]) kinvmax = i;
+        }
+        double g[N];   // Lambda = V diag(g) V^T
+        switch (crit) {
+            case kFisherD: value = -det;
+#pragma unroll
+                for (int i = 0; i < N; ++i) g[i] = -det / lam[i];
+                break;
+            case kD: value = 1.0 / det;
+#pragma unroll
+                for (int i = 0; i < N; ++i) g[i] = -1.0 / (det * lam[i]);
+                break;
+            case kA: value = sinv;
+#pragma unroll
+                for (int i = 0; i < N; ++i) g[i] = -1.0 / (lam[i] * lam[i]);
+                break;
+            case kFisherE: value = -lam[kmin];
+#pragma unroll
+                for (int i = 0; i < N; ++i) g[i] = (i == kmin) ? -1.0 : 0.0;
+                break;
+            default: value = 1.0 / lam[kinvmax];
+#pragma unroll
+                for (int i = 0; i < N; ++i) g[i] = (i == kinvmax) ? -1.0 / (lam[i] * lam[i]) : 0.0;
+                break;
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+            for (int i = 0; i <= j; ++i) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < N; ++k) s = fma(V[i][k] * g[k], V[j][k], s);
+                L[tri(i, j)] = s;
+            }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// One explicit RK step of the augmented system (forward) and its discrete adjoint (backward)
+// ----------------------------------------------------------------------------------------------
+template <class M, class Tab>
+__device__ __forceinline__ void rk_forward_step(double t, double h, double (&z)[M::NZ], double (&F)[M::NF],
+                                                const double* u, const double* w, const double* th,
+                                                const double* c) {
+    constexpr int S = Tab::S, NZ = M::NZ, NF = M::NF;
+    double k[S][NZ];
+    double zacc[NZ];
+#pragma unroll
+    for (int a = 0; a < NZ; ++a) zacc[a] = z[a];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        double Z[NZ];
+#pragma unroll
+        for (int a = 0; a < NZ; ++a) Z[a] = z[a];
+#pragma unroll
+        for (int j = 0; j < s; ++j) {
+            if (Tab::a(s, j) != 0.0) {
+                const double ha = h * Tab::a(s, j);
+#pragma unroll
+                for (int a = 0; a < NZ; ++a) Z[a] = fma(ha, k[j][a], Z[a]);
+            }
+        }
+        double dF[NF];
+        M::primal(t + Tab::c(s) * h, Z, u, w, th, c, k[s], dF);
+        const double hb = h * Tab::b(s);
+#pragma unroll
+        for (int a = 0; a < NZ; ++a) zacc[a] = fma(hb, k[s][a], zacc[a]);
+#pragma unroll
+        for (int a = 0; a < NF; ++a) F[a] = fma(hb, dF[a], F[a]);
+    }
+#pragma unroll
+    for (int a = 0; a < NZ; ++a) z[a] = zacc[a];
+}
+
+// lam: adjoint of z_{n+1} on entry, of z_n on exit.  ub/wb accumulate d/du and d/dw of the
+// Lambda-weighted objective over this step.
+template <class M, class Tab>
+__device__ __forceinline__ void rk_adjoint_step(double t, double h, const double (&zn)[M::NZ],
+                                                double (&lam)[M::NZ], const double* u, const double* w,
+                                                const double* th, const double* c, const double* L,
+                                                double* ub, double* wb) {
+    constexpr int S = Tab::S, NZ = M::NZ;
+    double Z[S][NZ];
+    {   // recompute the stage states
+        double k[S][NZ];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) Z[s][a] = zn[a];
+#pragma unroll
+            for (int j = 0; j < s; ++j) {
+                if (Tab::a(s, j) != 0.0) {
+                    const double ha = h * Tab::a(s, j);
+#pragma unroll
+                    for (int a = 0; a < NZ; ++a) Z[s][a] = fma(ha, k[j][a], Z[s][a]);
+                }
+            }
+            if (s < S - 1) M::primal_z(t + Tab::c(s) * h, Z[s], u, th, c, k[s]);
+        }
+    }
+    double Zb[S][NZ];
+    double lacc[NZ];
+#pragma unroll
+    for (int a = 0; a < NZ; ++a) lacc[a] = lam[a];
+#pragma unroll
+    for (int s = S - 1; s >= 0; --s) {
+        const double hb = h * Tab::b(s);
+        double kb[NZ];
+#pragma unroll
+        for (int a = 0; a < NZ; ++a) kb[a] = hb * lam[a];
+#pragma unroll
+        for (int j = s + 1; j < S; ++j) {
+            if (Tab::a(j, s) != 0.0) {
+                const double ha = h * Tab::a(j, s);
+#pragma unroll
+                for (int a = 0; a < NZ; ++a) kb[a] = fma(ha, Zb[j][a], kb[a]);
+            }
+        }
+        double qw[M::NOBS];
+        M::adjoint(t + Tab::c(s) * h, Z[s], u, w, th, c, L, kb, hb, Zb[s], ub, qw);
+#pragma unroll
+        for (int i = 0; i < M::NOBS; ++i) wb[i] = fma(hb, qw[i], wb[i]);
+#pragma unroll
+        for (int a = 0; a < NZ; ++a) lacc[a] += Zb[s][a];
+    }
+#pragma unroll
+    for (int a = 0; a < NZ; ++a) lam[a] = lacc[a];
+}
+
+// ----------------------------------------------------------------------------------------------
+// The evaluation kernel
+// ----------------------------------------------------------------------------------------------
+template <class M, class Tab, bool GRAD>
+__global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) {
+    constexpr int NX = M::NX, NP = M::NP, NZ = M::NZ, NF = M::NF, NOBS = M::NOBS, NCTRL = M::NCTRL;
+    constexpr int NCU = NCTRL > 0 ? NCTRL : 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    double* tile_buf = reinterpret_cast<double*>(smem_raw + 128);
+    __shared__ double red_val[kMaxTile / 32];
+    __shared__ long long red_idx[kMaxTile / 32];
+
+    const int tid = threadIdx.x;
+    const int TILE = P.tile;
+    const int n_var = P.n_var;
+    const long long ntiles = (P.n + TILE - 1) / TILE;
+    const int N = P.n_intervals;
+    const double* th = P.theta;
+
+    if (tid == 0 && P.use_tma) mbar_init(bar, 1);
+    __syncthreads();
+    uint32_t phase = 0;
+    double best_val = __longlong_as_double(0x7ff0000000000000LL);   // +inf
+    long long best_idx = -1;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long g0 = tile * TILE;
+        const int count = (int)((P.n - g0 < TILE) ? (P.n - g0) : TILE);
+        const double* src = P.designs + g0 * n_var;
+        const uint32_t bytes = (uint32_t)count * n_var * 8u;
+        const bool tma_ok = P.use_tma && (bytes % 16u == 0);
+        if (tma_ok) {
+            if (tid == 0) {
+                mbar_expect_tx(bar, bytes);
+                tma_load_1d(tile_buf, src, bytes, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+        } else {
+            for (int i = tid; i < count * n_var; i += blockDim.x) tile_buf[i] = src[i];
+            __syncthreads();
+        }
+
+        if (tid < count) {
+            double* row = tile_buf + (size_t)tid * n_var;
+            const long long g = g0 + tid;
+            double z[NZ], F[NF];
+#pragma unroll
+            for (int a = 0; a < NX; ++a) z[a] = P.x0[a];
+#pragma unroll
+            for (int a = 0; a < NX * NP; ++a) z[NX + a] = P.G0[a];
+#pragma unroll
+            for (int a = 0; a < M::NIC; ++a) z[M::ic_state(a)] = row[P.ic_off + a];
+#pragma unroll
+            for (int a = 0; a < NF; ++a) F[a] = 0.0;
+            double* tr = P.traj + ((size_t)blockIdx.x * P.n_steps * NZ) * TILE + tid;
+            double* xg = P.xgrid ? P.xgrid + (size_t)g * (N + 1) * (NZ + NF) : nullptr;
+            if (xg) {
+#pragma unroll
+                for (int a = 0; a < NZ; ++a) xg[a] = z[a];
+#pragma unroll
+                for (int a = 0; a < NF; ++a) xg[NZ + a] = F[a];
+            }
+
+            // ---------------- forward sweep ----------------
+            for (int j = 0; j < N; ++j) {
+                double u[NCU], w[NOBS], c[M::NCONST];
+#pragma unroll
+                for (int k = 0; k < NCTRL; ++k) u[k] = row[P.ctrl_off[k] + __ldg(P.indicators + k * N + j)];
+#pragma unroll
+                for (int i = 0; i < NOBS; ++i) w[i] = row[P.w_off[i] + __ldg(P.indicators + (NCTRL + i) * N + j)];
+                M::consts(u, th, c);
+                const int s0 = __ldg(P.first_step + j), s1 = __ldg(P.first_step + j + 1);
+                for (int s = s0; s < s1; ++s) {
+                    if (GRAD) {
+#pragma unroll
+                        for (int a = 0; a < NZ; ++a) tr[((size_t)s * NZ + a) * TILE] = z[a];
+                    }
+                    rk_forward_step<M, Tab>(__ldg(P.step_t + s), __ldg(P.step_h + s), z, F, u, w, th, c);
+                }
+                if (xg) {
+                    double* o = xg + (size_t)(j + 1) * (NZ + NF);
+#pragma unroll
+                    for (int a = 0; a < NZ; ++a) o[a] = z[a];
+#pragma unroll
+                    for (int a = 0; a < NF; ++a) o[NZ + a] = F[a];
+                }
+            }
+
+            // ---------------- criterion epilogue ----------------
+            const double tau = row[P.tau_off];
+            double value, L[NF];
+            criterion_eval<NP>(F, tau, P.criterion, value, L);
+            const double obj = value + tau;
+            P.crit[g] = obj;
+            if (P.fim) {
+#pragma unroll
+                for (int a = 0; a < NF; ++a) P.fim[g * NF + a] = F[a];
+            }
+            if (obj < best_val) { best_val = obj; best_idx = P.index_base + g; }   // NaN never wins
+
+            // ---------------- backward (discrete adjoint) sweep ----------------
+            if (GRAD) {
+                double lam[NZ];
+#pragma unroll
+                for (int a = 0; a < NZ; ++a) lam[a] = 0.0;
+                double ub[NCU], wb[NOBS];
+                int uk[NCU], wk[NOBS];
+#pragma unroll
+                for (int k = 0; k < NCU; ++k) { ub[k] = 0.0; uk[k] = -1; }
+#pragma unroll
+                for (int i = 0; i < NOBS; ++i) { wb[i] = 0.0; wk[i] = -1; }
+                for (int j = N - 1; j >= 0; --j) {
+                    double u[NCU], w[NOBS], c[M::NCONST];
+#pragma unroll
+                    for (int k = 0; k < NCTRL; ++k) {
+                        const int idx = __ldg(P.indicators + k * N + j);
+                        if (idx != uk[k]) {
+                            if (uk[k] >= 0) row[P.ctrl_off[k] + uk[k]] = ub[k];
+                            ub[k] = 0.0; uk[k] = idx;
+                        }
+                        u[k] = row[P.ctrl_off[k] + idx];
+                    }
+#pragma unroll
+                    for (int i = 0; i < NOBS; ++i) {
+                        const int idx = __ldg(P.indicators + (NCTRL + i) * N + j);
+                        if (idx != wk[i]) {
+                            if (wk[i] >= 0) row[P.w_off[i] + wk[i]] = wb[i];
+                            wb[i] = 0.0; wk[i] = idx;
+                        }
+                        w[i] = row[P.w_off[i] + idx];
+                    }
+                    M::consts(u, th, c);
+                    const int s0 = __ldg(P.first_step + j), s1 = __ldg(P.first_step + j + 1);
+                    for (int s = s1 - 1; s >= s0; --s) {
+                        double zn[NZ];
+#pragma unroll
+                        for (int a = 0; a < NZ; ++a) zn[a] = tr[((size_t)s * NZ + a) * TILE];
+                        rk_adjoint_step<M, Tab>(__ldg(P.step_t + s), __ldg(P.step_h + s), zn, lam, u, w, th, c,
+                                                L, ub, wb);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NCTRL; ++k)
+                    if (uk[k] >= 0) row[P.ctrl_off[k] + uk[k]] = ub[k];
+#pragma unroll
+                for (int i = 0; i < NOBS; ++i)
+                    if (wk[i] >= 0) row[P.w_off[i] + wk[i]] = wb[i];
+#pragma unroll
+                for (int a = 0; a < M::NIC; ++a) row[P.ic_off + a] = lam[M::ic_state(a)];
+                double trL = 1.0;   // d(c(F + tau I) + tau)/d tau = tr Lambda + 1
+#pragma unroll
+                for (int i = 0; i < NP; ++i) trL += L[tri(i, i)];
+                row[P.tau_off] = trL;
+            }
+        }
+
+        if (GRAD) {
+            double* dst = P.grad + g0 * n_var;
+            if (tma_ok) {
+                fence_proxy_async();
+                __syncthreads();
+                if (tid == 0) {
+                    tma_store_1d(dst, tile_buf, bytes);
+                    tma_store_wait_read();
+                }
+                __syncthreads();
+            } else {
+                __syncthreads();
+                for (int i = tid; i < count * n_var; i += blockDim.x) dst[i] = tile_buf[i];
+                __syncthreads();
+            }
+        } else {
+            __syncthreads();
+        }
+    }
+
+    // ---- per-CTA partial arg-min (warp shuffles, then one record per CTA) ----
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, best_val, o);
+        const long long oi = __shfl_down_sync(0xffffffffu, best_idx, o);
+        if (ov < best_val || (ov == best_val && oi >= 0 && (best_idx < 0 || oi < best_idx))) {
+            best_val = ov; best_idx = oi;
+        }
+    }
+    if ((tid & 31) == 0) { red_val[tid >> 5] = best_val; red_idx[tid >> 5] = best_idx; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int wq = 1; wq < (int)((blockDim.x + 31) >> 5); ++wq) {
+            const double ov = red_val[wq];
+            const long long oi = red_idx[wq];
+            if (ov < best_val || (ov == best_val && oi >= 0 && (best_idx < 0 || oi < best_idx))) {
+                best_val = ov; best_idx = oi;
+            }
+        }
+        P.part_val[blockIdx.x] = best_val;
+        P.part_idx[blockIdx.x] = best_idx;
+        if (P.use_tma) tma_store_wait_all();
+    }
+}
+
+// final arg-min over the per-CTA records (one CTA)
+__global__ void argmin_final_kernel(const double* __restrict__ pv, const long long* __restrict__ pi, int m,
+                                    double* __restrict__ out_val, long long* __restrict__ out_idx) {
+    __shared__ double sv[32];
+    __shared__ long long si[32];
+    double bv = __longlong_as_double(0x7ff0000000000000LL);
+    long long bi = -1;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const double v = pv[i];
+        const long long k = pi[i];
+        if (k >= 0 && (v < bv || (v == bv && (bi < 0 || k < bi)))) { bv = v; bi = k; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, bv, o);
+        const long long oi = __shfl_down_sync(0xffffffffu, bi, o);
+        if (oi >= 0 && (ov < bv || (ov == bv && (bi < 0 || oi < bi)))) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int wq = 1; wq < (int)(blockDim.x >> 5); ++wq) {
+            const double ov = sv[wq];
+            const long long oi = si[wq];
+            if (oi >= 0 && (ov < bv || (ov == bv && (bi < 0 || oi < bi)))) { bv = ov; bi = oi; }
+        }
+        *out_val = bv;
+        *out_idx = bi;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Criteria on caller-supplied matrices (host API `criterion(F, tau)`, fisher.jl:12-15): one
+// matrix per thread, runtime n, Jacobi in local memory.  Not a hot path.
+// ----------------------------------------------------------------------------------------------
+constexpr int kMaxCritN = 24;
+
+__global__ void criterion_batch_kernel(const double* __restrict__ Fp, const double* __restrict__ tau, int n,
+                                       long long batch, int crit, double* __restrict__ value,
+                                       double* __restrict__ Lout) {
+    const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (g >= batch) return;
+    const int nF = n * (n + 1) / 2;
+    double A[kMaxCritN * kMaxCritN], V[kMaxCritN * kMaxCritN];
+    const double tv = tau ? tau[g] : 0.0;
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i <= j; ++i) {
+            const double v = Fp[g * nF + tri(i, j)] + (i == j ? tv : 0.0);
+            A[i * n + j] = v; A[j * n + i] = v;
+        }
+    double trc = 0.0;
+    for (int i = 0; i < n; ++i) trc += A[i * n + i];
+    for (int i = 0; i < n * n; ++i) V[i] = 0.0;
+    for (int i = 0; i < n; ++i) V[i * n + i] = 1.0;
+    if (crit != kFisherA) {
+        for (int sweep = 0; sweep < 40; ++sweep) {
+            double off = 0.0, dia = 0.0;
+            for (int p = 0; p < n; ++p) {
+                dia += A[p * n + p] * A[p * n + p];
+                for (int q = p + 1; q < n; ++q) off += A[p * n + q] * A[p * n + q];
+            }
+            if (off <= 1e-34 * dia || off == 0.0) break;
+            for (int p = 0; p < n - 1; ++p)
+                for (int q = p + 1; q < n; ++q) {
+                    const double apq = A[p * n + q];
+                    if (apq == 0.0) continue;
+                    const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+                    const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                    const double cs = 1.0 / sqrt(tt * tt + 1.0), sn = tt * cs;
+                    for (int k = 0; k < n; ++k) {
+                        const double akp = A[k * n + p], akq = A[k * n + q];
+                        A[k * n + p] = cs * akp - sn * akq; A[k * n + q] = sn * akp + cs * akq;
+                    }
+                    for (int k = 0; k < n; ++k) {
+                        const double apk = A[p * n + k], aqk = A[q * n + k];
+                        A[p * n + k] = cs * apk - sn * aqk; A[q * n + k] = sn * apk + cs * aqk;
+                    }
+                    for (int k = 0; k < n; ++k) {
+                        const double vkp = V[k * n + p], vkq = V[k * n + q];
+                        V[k * n + p] = cs * vkp - sn * vkq; V[k * n + q] = sn * vkp + cs * vkq;
+                    }
+                }
+        }
+    }
+    double det = 1.0, sinv = 0.0;
+    int kmin = 0, kinv = 0;
+    for (int i = 0; i < n; ++i) {
+        const double l = A[i * n + i];
+        det *= l; sinv += 1.0 / l;
+        if (l < A[kmin * n + kmin]) kmin = i;
+        if (1.0 / l > 1.0 / A[kinv * n + kinv]) kinv = i;
+    }
+    double val;
+    switch (crit) {
+        case kFisherA: val = -trc; break;
+        case kFisherD: val = -det; break;
+        case kFisherE: val = -A[kmin * n + kmin]; break;
+        case kA: val = sinv; break;
+        case kD: val = 1.0 / det; break;
+        default: val = 1.0 / A[kinv * n + kinv]; break;
+    }
+    value[g] = val;
+    if (Lout) {
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i <= j; ++i) {
+                double s = 0.0;
+                for (int k = 0; k < n; ++k) {
+                    const double l = A[k * n + k];
+                    double gk;
+                    switch (crit) {
+                        case kFisherA: gk = -1.0; break;
+                        case kFisherD: gk = -det / l; break;
+                        case kFisherE: gk = (k == kmin) ? -1.0 : 0.0; break;
+                        case kA: gk = -1.0 / (l * l); break;
+                        case kD: gk = -1.0 / (det * l); break;
+                        default: gk = (k == kinv) ? -1.0 / (l * l) : 0.0; break;
+                    }
+                    s += V[i * n + k] * gk * V[j * n + k];
+                }
+                Lout[g * nF + tri(i, j)] = s;
+            }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// FP64 peak microbenchmark: register-resident DFMA chains (8 independent accumulators per lane).
+// The roofline denominator for this compute-bound path (MEASURED_PEAKS.json has no FP64 entry).
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+}  // namespace dynoed

@@ -1,0 +1,466 @@
+"""CUDA emitter: prints the simplified augmented system into device functions for the
+hand-written sm_100a kernel template (`csrc/dynoed_kernels.cuh`).
+
+Role in the north-star design: "host code builds the simplified RHS and emits its body into a
+hand-written kernel template, compiled once".  The reference gets the same functions from
+ModelingToolkit's code generation (``ODAEProblem``, /root/reference/src/problem.jl:82) and its
+derivatives from ForwardDiff duals (:154); here the host emits
+
+  consts  : sub-expressions that depend only on (controls, parameters) — hoisted out of the
+            integrator's stage loop, recomputed once per merged-grid interval
+  primal  : x' = f,  G' = J G + f_p  (J = df/dx; /root/reference/src/augment.jl:231),
+            F'_triu = sum_i w_i (Q_i^T Q_i)_triu with Q = h_x G (:223-226, :238)
+  adjoint : vector-Jacobian product of the (x, G) right-hand side plus the gradient of the
+            Lambda-weighted Fisher integrand — the stage kernel of the discrete RK adjoint that
+            yields d objective / d(controls, initial conditions, weights) in one backward sweep
+  obs     : Q = h_x G (for the information-gain outputs, /root/reference/src/utilities.jl:19-54)
+
+The matrix structure (J, f_p, h_x as named temporaries; products kept factored) is preserved so
+that nvcc contracts almost everything into DFMA.  Flop counts of the emitted straight-line code
+(FMA = 2, mul/add = 1) are frozen next to the code for the roofline accounting.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+from collections import OrderedDict
+
+import sympy as sp
+from sympy.printing.c import C99CodePrinter
+
+from .augment import SimplifiedOEDSystem, triu_pairs
+from .symbolic import getdefault, is_initial_condition
+
+
+class _Printer(C99CodePrinter):
+    def __init__(self, names):
+        super().__init__({"contract": False})
+        self._names = names
+
+    def _print_Symbol(self, expr):
+        return self._names.get(expr, expr.name)
+
+    def _print_Pow(self, expr):
+        b, e = expr.base, expr.exp
+        if e.is_Integer and 2 <= int(e) <= 4:
+            s = self._print(b)
+            if not (b.is_Symbol or b.is_Number):
+                s = f"({s})"
+            return "*".join([s] * int(e))
+        if e == -1:
+            return f"1.0/({self._print(b)})"
+        if e.is_Integer and -4 <= int(e) <= -2:
+            s = self._print(b)
+            if not (b.is_Symbol or b.is_Number):
+                s = f"({s})"
+            return "1.0/(" + "*".join([s] * int(-e)) + ")"
+        return super()._print_Pow(expr)
+
+    def _print_Integer(self, expr):
+        return f"{int(expr)}.0"
+
+    def _print_Rational(self, expr):
+        return f"({int(expr.p)}.0/{int(expr.q)}.0)"
+
+
+def count_flops(expr) -> int:
+    """mul/add = 1 (an FMA therefore counts 2), division / elementary function = 1."""
+    expr = sp.sympify(expr)
+    n = 0
+    for node in sp.preorder_traversal(expr):
+        if node.is_Add:
+            n += len(node.args) - 1
+        elif node.is_Mul:
+            args = [a for a in node.args if a != -1 and a != 1]
+            n += max(len(args) - 1, 0)
+        elif node.is_Pow:
+            e = node.exp
+            if e.is_Integer:
+                n += abs(int(e)) - 1 + (1 if int(e) < 0 else 0)
+            else:
+                n += 1
+        elif node.is_Function:
+            n += 1
+    return n
+
+
+class _Hoister:
+    """Replaces maximal sub-expressions that depend only on `static` symbols by c[k] symbols."""
+
+    def __init__(self, static):
+        self.static = set(static)
+        self.table = OrderedDict()
+
+    def _is_static(self, e):
+        return len(e.free_symbols) > 0 and e.free_symbols <= self.static
+
+    def _const(self, e):
+        if e.is_Symbol:
+            return e
+        if e.could_extract_minus_sign() and (-e).is_Symbol:
+            return e
+        if e not in self.table:
+            self.table[e] = sp.Symbol(f"hc{len(self.table)}", real=True)
+        return self.table[e]
+
+    def __call__(self, e):
+        e = sp.sympify(e)
+        if e.is_Atom:
+            return e
+        if self._is_static(e):
+            return self._const(e)
+        args = [self(a) for a in e.args]
+        if e.is_Add or e.is_Mul:
+            st = [a for a in args if (a.free_symbols and a.free_symbols <= self.static | set(self.table.values()))
+                  or (a.is_Number and e.is_Add)]
+            dyn = [a for a in args if a not in st]
+            nontrivial = [a for a in st if not a.is_Number]
+            if len(nontrivial) >= 2 or (len(nontrivial) == 1 and len(st) >= 2 and e.is_Add):
+                folded = e.func(*st)
+                folded = folded.xreplace({v: k for k, v in self.table.items()})
+                return e.func(self._const(folded), *dyn)
+        return e.func(*args)
+
+
+def _toposort(defs, inputs):
+    """defs: list of (symbol, expr).  Stable topological order w.r.t. symbol dependencies."""
+    defined = set(inputs)
+    names = {s for s, _ in defs}
+    out, pending = [], list(defs)
+    while pending:
+        rest, progressed = [], False
+        for s, e in pending:
+            deps = {d for d in e.free_symbols if d in names}
+            if deps <= defined:
+                out.append((s, e))
+                defined.add(s)
+                progressed = True
+            else:
+                rest.append((s, e))
+        assert progressed, "cyclic definitions in emitted block"
+        pending = rest
+    return out
+
+
+class _Block:
+    def __init__(self):
+        self.defs = []      # temporaries (symbol, expr)
+        self.outs = []      # (c lvalue string, expr, accumulate?)
+
+    def tmp(self, name, expr):
+        expr = sp.sympify(expr)
+        if expr.is_Number or expr.is_Symbol:
+            return expr
+        if expr.could_extract_minus_sign() and (-expr).is_Symbol:
+            return expr
+        s = sp.Symbol(name, real=True)
+        self.defs.append((s, expr))
+        return s
+
+    def out(self, lvalue, expr, accumulate=False):
+        self.outs.append((lvalue, sp.sympify(expr), accumulate))
+
+    def render(self, printer, inputs, indent="    "):
+        exprs = [e for _, e in self.defs] + [e for _, e, _ in self.outs]
+        repl, red = sp.cse(exprs, symbols=sp.numbered_symbols("v", real=True), order="none")
+        nd = len(self.defs)
+        defs = list(repl) + [(s, red[i]) for i, (s, _) in enumerate(self.defs)]
+        tnames = {s for s, _ in defs}
+        defs = _toposort(defs, inputs)
+        lines, flops = [], 0
+        for s, e in defs:
+            lines.append(f"{indent}const double {s.name} = {printer.doprint(e)};")
+            flops += count_flops(e)
+        for (lv, _, acc), e in zip(self.outs, red[nd:]):
+            lines.append(f"{indent}{lv} {'+=' if acc else '='} {printer.doprint(e)};")
+            flops += count_flops(e) + (1 if acc else 0)
+        return "\n".join(lines), flops
+
+
+def _horner(e, wrt):
+    e = sp.sympify(e)
+    try:
+        if e.is_polynomial(*wrt) and e.free_symbols & set(wrt):
+            return sp.horner(sp.expand(e), wrt=wrt)
+    except Exception:
+        pass
+    return e
+
+
+def emit_model(name: str, s: SimplifiedOEDSystem) -> tuple[str, dict]:
+    nx, np_, n_obs = s.nx, s.np_, s.n_obs
+    nc = len(s.controls)
+    n_ic = len(s.x_ic)
+    n_ord = np_ - n_ic
+    nF = np_ * (np_ + 1) // 2
+    nz = nx + nx * np_
+    t = s.iv
+    theta = [p for p in s.ps if p not in s.controls and p not in s.w and not is_initial_condition(p)]
+    x = list(s.x)
+    G = s.G
+    p_ord = s.p_tunable[:n_ord]
+
+    # --- structured pieces ---------------------------------------------------------------------
+    f = sp.Matrix(s.f)
+    J = f.jacobian(x)
+    fp = f.jacobian(p_ord) if n_ord else sp.zeros(nx, 0)
+    # consistency with the reference-faithful derivation (0 = f_xdot G' + f_x G + f_p, torn)
+    fp_full = sp.Matrix(nx, np_, lambda i, j: fp[i, j] if j < n_ord else 0)
+    chk = (J * G + fp_full - s.dG).applyfunc(sp.expand)
+    assert all(sp.simplify(e) == 0 for e in chk), "structured G' differs from the augmented system"
+    # observation sensitivities Q = Hc G + H0
+    Hc = sp.Matrix(n_obs, nx, lambda i, c: sp.diff(s.Qexpr[i, 0], G[c, 0]))
+    H0 = sp.Matrix(n_obs, np_, lambda i, j: sp.simplify(
+        s.Qexpr[i, j] - sum(Hc[i, c] * G[c, j] for c in range(nx))))
+    assert not any(e.has(*list(G)) for e in list(Hc) + list(H0)), "Q must be affine in G"
+    # check F' against the augmented system
+    wsym = list(s.w)
+    for k, (i, j) in enumerate(triu_pairs(np_)):
+        e = sum(wsym[o] * s.Qexpr[o, i] * s.Qexpr[o, j] for o in range(n_obs)) - s.dF[k]
+        assert sp.simplify(sp.expand(e)) == 0, "structured F' differs from the augmented system"
+
+    # --- C names ---------------------------------------------------------------------------------
+    names = {t: "t"}
+    for i, v in enumerate(x):
+        names[v] = f"z[{i}]"
+    for j in range(np_):
+        for i in range(nx):
+            names[G[i, j]] = f"z[{nx + j * nx + i}]"
+    for k, v in enumerate(theta):
+        names[v] = f"th[{k}]"
+    for k, v in enumerate(s.controls):
+        names[v] = f"u[{k}]"
+    for k, v in enumerate(wsym):
+        names[v] = f"w[{k}]"
+    kb = [sp.Symbol(f"kb{a}", real=True) for a in range(nz)]
+    Ls = [sp.Symbol(f"L{k}", real=True) for k in range(nF)]
+    cq = sp.Symbol("cq", real=True)
+    for a, v in enumerate(kb):
+        names[v] = f"kb[{a}]"
+    for k, v in enumerate(Ls):
+        names[v] = f"L[{k}]"
+    Lfull = sp.zeros(np_, np_)
+    for k, (i, j) in enumerate(triu_pairs(np_)):
+        Lfull[i, j] = Ls[k]
+        Lfull[j, i] = Ls[k]
+
+    hoist = _Hoister(set(theta) | set(s.controls))
+    wrt = x
+    H = lambda e: hoist(_horner(e, wrt))
+
+    # ---------------- primal ---------------------------------------------------------------------
+    def build_primal(with_F: bool):
+        b = _Block()
+        Jt = sp.Matrix(nx, nx, lambda i, c: b.tmp(f"J{i}{c}", H(J[i, c])))
+        fpt = sp.Matrix(nx, max(n_ord, 0), lambda i, j: b.tmp(f"fp{i}{j}", H(fp[i, j]))) \
+            if n_ord else sp.zeros(nx, 0)
+        for i in range(nx):
+            b.out(f"dz[{i}]", H(f[i]))
+        for j in range(np_):
+            for i in range(nx):
+                e = sum(Jt[i, c] * G[c, j] for c in range(nx))
+                if j < n_ord:
+                    e = e + fpt[i, j]
+                b.out(f"dz[{nx + j * nx + i}]", e)
+        if with_F:
+            Hct = sp.Matrix(n_obs, nx, lambda i, c: b.tmp(f"h{i}{c}", H(Hc[i, c])))
+            Qt = sp.Matrix(n_obs, np_, lambda i, j: b.tmp(
+                f"Q{i}{j}", sum(Hct[i, c] * G[c, j] for c in range(nx)) + H(H0[i, j])))
+            wQ = sp.Matrix(n_obs, np_, lambda i, j: b.tmp(f"wQ{i}{j}", wsym[i] * Qt[i, j]))
+            for k, (i, j) in enumerate(triu_pairs(np_)):
+                b.out(f"dF[{k}]", sum(wQ[o, i] * Qt[o, j] for o in range(n_obs)))
+        return b
+
+    # ---------------- adjoint --------------------------------------------------------------------
+    def build_adjoint():
+        b = _Block()
+        kx = kb[:nx]
+        kG = sp.Matrix(nx, np_, lambda i, j: kb[nx + j * nx + i])
+        Jt = sp.Matrix(nx, nx, lambda i, c: b.tmp(f"J{i}{c}", H(J[i, c])))
+        Hct = sp.Matrix(n_obs, nx, lambda i, c: b.tmp(f"h{i}{c}", H(Hc[i, c])))
+        Qt = sp.Matrix(n_obs, np_, lambda i, j: b.tmp(
+            f"Q{i}{j}", sum(Hct[i, c] * G[c, j] for c in range(nx)) + H(H0[i, j])))
+        # r_i = Lambda Q_i^T ; dq_i = Q_i r_i
+        r = sp.Matrix(n_obs, np_, lambda i, j: b.tmp(
+            f"r{i}{j}", sum(Lfull[j, k] * Qt[i, k] for k in range(np_))))
+        for i in range(n_obs):
+            b.out(f"qw[{i}]", sum(Qt[i, j] * r[i, j] for j in range(np_)))
+        cw = [b.tmp(f"cw{i}", 2 * cq * wsym[i]) for i in range(n_obs)]
+        # G-bar = J^T kG + sum_i cw_i Hc[i,:]^T r_i
+        for j in range(np_):
+            for c in range(nx):
+                e = sum(Jt[i, c] * kG[i, j] for i in range(nx))
+                for i in range(n_obs):
+                    if Hc[i, c] != 0:
+                        e = e + (cw[i] * Hct[i, c]) * r[i, j] if Hc[i, c] != 1 else e + cw[i] * r[i, j]
+                b.out(f"zb[{nx + j * nx + c}]", e)
+        # scalar S = kx.f + <W, J> + <kG_ord, fp> + sum_ic m_ic Hc_ic + sum_ij n_ij H0_ij;
+        # x-bar = dS/dx, u-bar = dS/du (W, m, n treated as constants)
+        Wsym = sp.Matrix(nx, nx, lambda i, c: sp.Symbol(f"W{i}{c}", real=True))
+        msym = sp.Matrix(n_obs, nx, lambda i, c: sp.Symbol(f"m{i}{c}", real=True))
+        nsym = sp.Matrix(n_obs, np_, lambda i, j: sp.Symbol(f"n{i}{j}", real=True))
+        S = sum(kx[i] * f[i] for i in range(nx))
+        S += sum(Wsym[i, c] * J[i, c] for i in range(nx) for c in range(nx))
+        S += sum(kG[i, j] * fp[i, j] for i in range(nx) for j in range(n_ord))
+        S += sum(msym[i, c] * Hc[i, c] for i in range(n_obs) for c in range(nx))
+        S += sum(nsym[i, j] * H0[i, j] for i in range(n_obs) for j in range(np_))
+        lin = list(kx) + list(Wsym) + list(kG) + list(msym) + list(nsym)
+        grads = [sp.diff(S, v) for v in x] + [sp.diff(S, v) for v in s.controls]
+        used = set().union(*[g.free_symbols for g in grads]) if grads else set()
+        sub = {}
+        for i in range(nx):
+            for c in range(nx):
+                if Wsym[i, c] in used:
+                    sub[Wsym[i, c]] = b.tmp(f"W{i}{c}", sum(kG[i, j] * G[c, j] for j in range(np_)))
+        for i in range(n_obs):
+            for c in range(nx):
+                if msym[i, c] in used:
+                    sub[msym[i, c]] = b.tmp(f"m{i}{c}", cw[i] * sum(G[c, j] * r[i, j] for j in range(np_)))
+            for j in range(np_):
+                if nsym[i, j] in used:
+                    sub[nsym[i, j]] = b.tmp(f"n{i}{j}", cw[i] * r[i, j])
+
+        def collect_lin(g):
+            g = sp.expand(g)
+            out = 0
+            rest = g
+            for v in lin:
+                co = g.coeff(v)
+                if co != 0:
+                    out = out + v * H(co)
+                    rest = sp.expand(rest - v * co)
+            assert rest == 0, "adjoint scalar must be linear in the adjoint symbols"
+            return out
+        for a in range(nx):
+            b.out(f"zb[{a}]", collect_lin(grads[a]).xreplace(sub))
+        for k in range(nc):
+            b.out(f"ub[{k}]", collect_lin(grads[nx + k]).xreplace(sub), accumulate=True)
+        return b
+
+    def build_obs():
+        b = _Block()
+        for i in range(n_obs):
+            for j in range(np_):
+                b.out(f"Q[{i * np_ + j}]",
+                      sum(H(Hc[i, c]) * G[c, j] for c in range(nx)) + H(H0[i, j]))
+        return b
+
+    blocks = OrderedDict(primal=build_primal(True), primal_z=build_primal(False),
+                         adjoint=build_adjoint(), obs=build_obs())
+    for k, v in enumerate(hoist.table.values()):
+        names[v] = f"c[{k}]"
+    pr = _Printer(names)
+    inputs = set(names.keys()) | {cq}
+    code, flops = {}, {}
+    for key, blk in blocks.items():
+        code[key], flops[key] = blk.render(pr, inputs)
+    cb = _Block()
+    for k, e in enumerate(hoist.table.keys()):
+        cb.out(f"c[{k}]", e)
+    code["consts"], flops["consts"] = cb.render(pr, inputs)
+    n_const = max(len(hoist.table), 1)
+
+    ic_state = [s.x.index(s.aug.x[i - 1]) for i in s.aug.unknown_initial_conditions]
+    x0 = [float(v) for v in s.u0[:nx]]
+    G0 = [float(v) for v in s.u0[nx:nz]]
+    th0 = [float(s.defaults.get(p, getdefault(p, 0.0))) for p in theta]
+    info = dict(name=name, nx=nx, np=np_, n_obs=n_obs, n_ctrl=nc, n_ic=n_ic, n_theta=len(theta),
+                n_const=len(hoist.table), nz=nz, nF=nF, ic_state=ic_state, x0=x0, G0=G0,
+                theta=th0, theta_names=[p.name for p in theta],
+                control_names=[c.name for c in s.controls], w_names=[w.name for w in s.w],
+                ic_names=[p.name for p in s.x_ic], tunable_names=[p.name for p in s.p_tunable],
+                state_names=[v.name for v in s.states], flops=flops)
+
+    def arr(vals, fmt="{!r}"):
+        return ", ".join(fmt.format(v) for v in vals) if vals else "0"
+
+    cname = "Model_" + name
+    src = f"""// GENERATED by dynamicoed.jl_b200/emit.py — do not edit.  Model "{name}".
+// states  : {', '.join(info['state_names'])}
+// tunables: {', '.join(info['tunable_names'])}   controls: {', '.join(info['control_names']) or '-'}
+// theta   : {', '.join(info['theta_names'])}
+// flops (FMA=2): {json.dumps(flops)}
+struct {cname} {{
+    static constexpr int NX = {nx}, NP = {np_}, NOBS = {n_obs}, NCTRL = {nc}, NIC = {n_ic};
+    static constexpr int NTH = {len(theta)}, NCONST = {n_const}, NZ = {nz}, NF = {nF};
+    static constexpr int FLOPS_PRIMAL = {flops['primal']}, FLOPS_PRIMAL_Z = {flops['primal_z']};
+    static constexpr int FLOPS_ADJOINT = {flops['adjoint']}, FLOPS_CONSTS = {flops['consts']};
+    static constexpr const char* NAME = "{name}";
+    __host__ __device__ static constexpr int ic_state(int i) {{
+        constexpr int v[{max(n_ic, 1)}] = {{{arr(ic_state, '{}')}}};
+        return v[i];
+    }}
+    static inline const double* default_x0() {{ static const double v[] = {{{arr(x0)}}}; return v; }}
+    static inline const double* default_G0() {{ static const double v[] = {{{arr(G0)}}}; return v; }}
+    static inline const double* default_theta() {{ static const double v[] = {{{arr(th0)}}}; return v; }}
+
+    __device__ __forceinline__ static void consts(const double* __restrict__ u,
+                                                  const double* __restrict__ th,
+                                                  double* __restrict__ c) {{
+{code['consts']}
+    }}
+    // x' = f, G' = J G + f_p, F'_triu = sum_i w_i (Q_i^T Q_i)_triu
+    __device__ __forceinline__ static void primal(double t, const double* __restrict__ z,
+            const double* __restrict__ u, const double* __restrict__ w,
+            const double* __restrict__ th, const double* __restrict__ c,
+            double* __restrict__ dz, double* __restrict__ dF) {{
+{code['primal']}
+    }}
+    // (x, G) part only — stage recomputation in the backward sweep
+    __device__ __forceinline__ static void primal_z(double t, const double* __restrict__ z,
+            const double* __restrict__ u, const double* __restrict__ th,
+            const double* __restrict__ c, double* __restrict__ dz) {{
+{code['primal_z']}
+    }}
+    // zb = (d g/d z)^T kb + cq * sum_i w_i d(Q_i L Q_i^T)/dz ;  ub += (d g/d u)^T kb ;
+    // qw[i] = Q_i L Q_i^T  (L = packed symmetric d criterion / d F)
+    __device__ __forceinline__ static void adjoint(double t, const double* __restrict__ z,
+            const double* __restrict__ u, const double* __restrict__ w,
+            const double* __restrict__ th, const double* __restrict__ c,
+            const double* __restrict__ L, const double* __restrict__ kb, double cq,
+            double* __restrict__ zb, double* __restrict__ ub, double* __restrict__ qw) {{
+{code['adjoint']}
+    }}
+    // Q = h_x G, row-major [NOBS][NP]
+    __device__ __forceinline__ static void obs(double t, const double* __restrict__ z,
+            const double* __restrict__ u, const double* __restrict__ th,
+            const double* __restrict__ c, double* __restrict__ Q) {{
+{code['obs']}
+    }}
+}};
+"""
+    info["sha"] = hashlib.sha256(src.encode()).hexdigest()[:16]
+    return src, info
+
+
+def emit_builtin(out_dir: str):
+    """Regenerate ``csrc/generated/*`` for the models compiled into libdynoed_cuda.so."""
+    import os
+    from . import models
+    from .augment import OEDSystem, structural_simplify
+    os.makedirs(out_dir, exist_ok=True)
+    infos, includes = [], []
+    for name, ctor in models.BUILTIN.items():
+        sysm = structural_simplify(OEDSystem(ctor()))
+        src, info = emit_model(name, sysm)
+        with open(os.path.join(out_dir, f"model_{name}.cuh"), "w") as fh:
+            fh.write(src)
+        infos.append(info)
+        includes.append(f'#include "model_{name}.cuh"')
+    with open(os.path.join(out_dir, "models.cuh"), "w") as fh:
+        fh.write("// GENERATED by dynamicoed.jl_b200/emit.py — do not edit.\n#pragma once\n")
+        fh.write("\n".join(includes) + "\n")
+        fh.write("#define DYNOED_FOR_EACH_MODEL(X) " +
+                 " ".join(f"X(Model_{i['name']})" for i in infos) + "\n")
+    with open(os.path.join(out_dir, "models.json"), "w") as fh:
+        json.dump(infos, fh, indent=1, ensure_ascii=False)
+    return infos
+
+
+if __name__ == "__main__":
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    infos = emit_builtin(os.path.join(here, "csrc", "generated"))
+    for i in infos:
+        print(i["name"], i["flops"], file=sys.stderr)

@@ -1,0 +1,240 @@
+"""Problem assembly and the optimiser boundary — the drop-in seam of the hot path.
+
+Mirrors /root/reference/src/problem.jl:
+  * ``OEDProblem(sys, criterion; alg, tspan, diffeqoptions)``          (:10-30)
+  * ``states(::OEDProblem)``  symbolic optimisation variables           (:32-66)
+  * ``get_timegrids``, ``get_initial_variables``                        (:68-78, :92-94)
+  * ``build_predictor``  p -> (X, t)                                    (:80-90)
+  * ``OptimizationProblem(prob, AD, u0, p; integer_constraints, constraints)`` (:96-161):
+    objective closure (:112-121), constraints (:123-128), bounds (:131-134), integrality (:137-146)
+
+Where the reference hands Optimization.jl an objective that is differentiated by ForwardDiff,
+this hands the optimiser ``f`` AND ``grad`` closures that call ``libdynoed_cuda.so``; nothing in
+here integrates or differentiates on the CPU.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+import sympy as sp
+
+from . import runtime
+from .augment import SimplifiedOEDSystem, structural_simplify
+from .criteria import AbstractInformationCriterion
+from .discretize import (ComponentVector, Timegrid, design_layout, generate_initial_variables,
+                         generate_variable_bounds)
+from .symbolic import getdefault
+
+_GEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "generated")
+
+
+# --- fixed-step integrators standing in for the OrdinaryDiffEq `alg` argument -------------------
+@dataclass(frozen=True)
+class RK4:
+    """Classic Runge-Kutta 4 with ``substeps`` equal steps per merged-grid interval."""
+    substeps: int = 4
+    method: int = runtime.RK4
+
+
+@dataclass(frozen=True)
+class Tsit5:
+    """The Tsit5 tableau (the reference's default ``alg``, problem.jl:25) with FIXED steps."""
+    substeps: int = 4
+    method: int = runtime.TSIT5
+
+
+def _resolve_model(sys: SimplifiedOEDSystem):
+    """(library path | None, model name, emitter info).  A system whose emitted code equals a
+    compiled-in model uses ``libdynoed_cuda.so``; anything else is emitted and compiled once."""
+    cached = getattr(sys, "_dynoed_model", None)
+    if cached is not None:
+        return cached
+    from .emit import emit_model
+    src, info = emit_model("USERMODEL", sys)
+    found = None
+    for f in sorted(os.listdir(_GEN)):
+        if f.startswith("model_") and f.endswith(".cuh"):
+            name = f[len("model_"):-len(".cuh")]
+            if open(os.path.join(_GEN, f)).read() == src.replace("USERMODEL", name):
+                found = (None, name, dict(info, name=name))
+                break
+    if found is None:
+        from .build import build_user_model
+        import hashlib
+        name = "u" + hashlib.sha256(src.encode()).hexdigest()[:12]
+        src = src.replace("USERMODEL", name)
+        info = dict(info, name=name)
+        found = (build_user_model(src, info), name, info)
+    sys._dynoed_model = found
+    return found
+
+
+class OEDProblem:
+    """problem.jl:10-30."""
+
+    def __init__(self, system, objective: AbstractInformationCriterion, *, alg=None, tspan=None,
+                 diffeqoptions=None, device: int = 0, **kwargs):
+        system = structural_simplify(system)
+        self.system = system
+        self.objective = objective
+        self.timegrid = Timegrid.from_system(system, tspan if tspan is not None else system.tspan)
+        self.alg = alg if alg is not None else Tsit5()
+        self.diffeq_options = dict(diffeqoptions or {})
+        self.device = device
+        self._ctx = None
+
+    @property
+    def layout(self):
+        return design_layout(self.system, self.timegrid)
+
+    def context(self) -> runtime.Context:
+        """The GPU evaluator for this problem (created on first use)."""
+        if self._ctx is None:
+            libpath, name, info = _resolve_model(self.system)
+            lay = self.layout
+            nc = len(self.system.controls)
+            self._ctx = runtime.Context(
+                name, criterion=self.objective.id, method=self.alg.method,
+                tgrid=self.timegrid.tpoints, indicators=self.timegrid.indicators - 1,
+                ctrl_offsets=lay.control_offsets, w_offsets=lay.w_offsets,
+                ic_offset=lay.ic_offset, tau_offset=lay.tau_offset, n_var=lay.n_var,
+                substeps=self.alg.substeps, theta=info["theta"], x0=info["x0"], G0=info["G0"],
+                device=self.device, library_path=libpath)
+        return self._ctx
+
+
+def states(prob: OEDProblem) -> ComponentVector:
+    """Symbolic optimisation variables for constraint building (problem.jl:32-66)."""
+    lay = prob.layout
+    syms = np.empty(lay.n_var, dtype=object)
+    for n, o, l in zip(lay.control_names, lay.control_offsets, lay.control_lengths):
+        for k in range(l):
+            syms[o + k] = sp.Symbol(f"{n}_{k+1}", real=True)
+    for i, n in enumerate(lay.ic_names):
+        syms[lay.ic_offset + i] = sp.Symbol(n, real=True)
+    for n, o, l in zip(lay.w_names, lay.w_offsets, lay.w_lengths):
+        for k in range(l):
+            syms[o + k] = sp.Symbol(f"{n}_{k+1}", real=True)
+    syms[lay.tau_offset] = sp.Symbol("τ", real=True)
+    cv = ComponentVector.__new__(ComponentVector)
+    object.__setattr__(cv, "data", syms)
+    object.__setattr__(cv, "axes", lay.axes())
+    return cv
+
+
+def get_timegrids(prob: OEDProblem) -> dict:
+    """problem.jl:68-78: {variable name: list of (t0, t1)} sorted by name."""
+    g = prob.timegrid
+    return {k: list(v) for k, v in sorted(zip(g.variables, g.timegrids))}
+
+
+def get_initial_variables(prob: OEDProblem) -> ComponentVector:
+    return generate_initial_variables(prob.system, prob.timegrid)
+
+
+def build_predictor(prob: OEDProblem):
+    """problem.jl:80-90: returns p -> (X, t) with X [n_aug, N+1] at the merged-grid points."""
+    ctx = prob.context()
+    t = prob.timegrid.tpoints
+
+    def predictor(p):
+        X = ctx.trajectory(np.asarray(p, dtype=np.float64))[0]
+        return X.T.copy(), t.copy()
+    return predictor
+
+
+# --- constraints (ModelingToolkit.ConstraintsSystem stand-in) -----------------------------------
+@dataclass
+class Constraint:
+    """lhs - rhs  with bounds  lcons <= expr <= ucons."""
+    expr: sp.Expr
+    lb: float
+    ub: float
+
+
+def leq(a, b) -> Constraint:
+    """a ≲ b  ->  a - b in (-inf, 0]"""
+    return Constraint(sp.sympify(a) - sp.sympify(b), -np.inf, 0.0)
+
+
+def geq(a, b) -> Constraint:
+    """a ≳ b  ->  a - b in [0, inf)"""
+    return Constraint(sp.sympify(a) - sp.sympify(b), 0.0, np.inf)
+
+
+@dataclass
+class ConstraintsSystem:
+    constraints: list
+    variables: object = None
+    name: str = "constraint_set"
+
+
+@dataclass
+class OptimizationFunction:
+    f: object
+    grad: object
+    cons: object = None
+    cons_j: object = None
+    syms: list = field(default_factory=list)
+
+
+@dataclass
+class OptimizationProblemT:
+    f: OptimizationFunction
+    u0: np.ndarray
+    p: object
+    lb: np.ndarray
+    ub: np.ndarray
+    int: np.ndarray
+    lcons: object
+    ucons: object
+    oed: OEDProblem = None
+
+
+def OptimizationProblem(prob: OEDProblem, AD=None, u0=None, p=None, *, integer_constraints=False,
+                        constraints=None, variable_type=np.float64, **kwargs) -> OptimizationProblemT:
+    """problem.jl:96-161.  ``AD`` is accepted for signature compatibility and ignored: the
+    gradient comes from the GPU adjoint sweep, not from an AD backend."""
+    u0v = get_initial_variables(prob) if u0 is None else u0
+    u0a = np.asarray(u0v, dtype=variable_type).copy()
+    ctx = prob.context()
+    n_var = ctx.n_var
+
+    def objective(u, _p=None):
+        c, _, _ = ctx.evaluate(np.asarray(u, dtype=np.float64).reshape(1, n_var), grad=False, fim=False)
+        return float(c[0])
+
+    def gradient(G, u, _p=None):
+        _, g, _ = ctx.evaluate(np.asarray(u, dtype=np.float64).reshape(1, n_var), grad=True, fim=False)
+        if G is not None:
+            G[:] = g[0]
+            return G
+        return g[0]
+
+    cons = cons_j = lcons = ucons = None
+    if isinstance(constraints, ConstraintsSystem):
+        syms = list(states(prob).data)
+        exprs = [c.expr for c in constraints.constraints]
+        fn = sp.lambdify(syms, exprs, "numpy")
+        jn = sp.lambdify(syms, sp.Matrix(exprs).jacobian(syms), "numpy")
+        cons = lambda u, _p=None: np.asarray(fn(*u), dtype=np.float64)
+        cons_j = lambda u, _p=None: np.asarray(jn(*u), dtype=np.float64)
+        lcons = np.array([c.lb for c in constraints.constraints])
+        ucons = np.array([c.ub for c in constraints.constraints])
+
+    lb = np.asarray(generate_variable_bounds(prob.system, prob.timegrid, True), dtype=variable_type)
+    ub = np.asarray(generate_variable_bounds(prob.system, prob.timegrid, False), dtype=variable_type)
+    assert np.all(lb <= u0a) and np.all(u0a <= ub), \
+        "The initial variables are not within the bounds. Please check the input!"
+    lay = prob.layout
+    integrality = np.zeros(n_var, dtype=bool)
+    if integer_constraints:
+        for o, l in zip(lay.w_offsets, lay.w_lengths):
+            integrality[o:o + l] = True                       # measurements are always integer
+        for c, o, l in zip(prob.system.controls, lay.control_offsets, lay.control_lengths):
+            integrality[o:o + l] = bool(c.meta.get("integer", False))
+    syms = [v.name for v in list(prob.system.x_ic) + list(prob.system.controls) + list(prob.system.w)]
+    opt_f = OptimizationFunction(objective, gradient, cons, cons_j, syms)
+    return OptimizationProblemT(opt_f, u0a, p, lb, ub, integrality, lcons, ucons, prob)

@@ -1,0 +1,262 @@
+"""ctypes binding of ``libdynoed_cuda.so`` (C ABI in ``include/dynoed.h``).
+
+This is the only way the package computes anything: there is no CPU fallback.  If the shared
+library has not been built (``python -c "import __graft_entry__ as g; g.build()"``) importing
+this module raises; if no CUDA device is present every compute call raises `DynoedError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdynoed_cuda.so")
+
+RK4, TSIT5 = 0, 1
+METHODS = {"rk4": RK4, "RK4": RK4, "tsit5": TSIT5, "Tsit5": TSIT5}
+
+
+class DynoedError(RuntimeError):
+    pass
+
+
+class ModelInfo(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("np", C.c_int32), ("n_obs", C.c_int32), ("n_ctrl", C.c_int32),
+                ("n_ic", C.c_int32), ("n_theta", C.c_int32), ("nz", C.c_int32), ("nF", C.c_int32),
+                ("ic_state", C.c_int32 * 8),
+                ("flops_primal", C.c_int32), ("flops_primal_z", C.c_int32),
+                ("flops_adjoint", C.c_int32), ("flops_consts", C.c_int32),
+                ("x0", C.c_double * 8), ("G0", C.c_double * 64), ("theta", C.c_double * 48)]
+
+
+class ProblemDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("model", C.c_char_p), ("criterion", C.c_int32),
+                ("method", C.c_int32), ("n_intervals", C.c_int32),
+                ("tgrid", C.POINTER(C.c_double)), ("substeps", C.c_int32),
+                ("edge_count", C.POINTER(C.c_int32)), ("step_edges", C.POINTER(C.c_double)),
+                ("indicators", C.POINTER(C.c_int32)), ("ctrl_offsets", C.POINTER(C.c_int32)),
+                ("w_offsets", C.POINTER(C.c_int32)), ("ic_offset", C.c_int32),
+                ("tau_offset", C.c_int32), ("n_var", C.c_int32),
+                ("theta", C.POINTER(C.c_double)), ("x0", C.POINTER(C.c_double)),
+                ("G0", C.POINTER(C.c_double)), ("tile", C.c_int32), ("max_batch_hint", C.c_int32)]
+
+
+class KernelStats(C.Structure):
+    _fields_ = [("regs_per_thread", C.c_int32), ("static_smem", C.c_int32),
+                ("dynamic_smem", C.c_int32), ("blocks_per_sm", C.c_int32), ("grid", C.c_int32),
+                ("block", C.c_int32), ("sm_count", C.c_int32), ("launches", C.c_int64),
+                ("scratch_bytes", C.c_int64), ("n_steps", C.c_int32), ("stages", C.c_int32),
+                ("flops_per_design_eval", C.c_double), ("flops_per_design_grad", C.c_double),
+                ("bytes_per_design", C.c_double)]
+
+
+EXPORTS = ["dynoed_abi_version", "dynoed_model_count", "dynoed_model_name", "dynoed_model_query",
+           "dynoed_create", "dynoed_destroy", "dynoed_set_criterion", "dynoed_set_stream",
+           "dynoed_own_stream",
+           "dynoed_eval_batch", "dynoed_eval_batch_async", "dynoed_sync", "dynoed_argmin",
+           "dynoed_trajectory", "dynoed_criterion_batch", "dynoed_fp64_peak",
+           "dynoed_kernel_stats_query", "dynoed_host_alloc", "dynoed_host_free",
+           "dynoed_last_error"]
+
+_libs = {}
+
+
+def lib(path: str | None = None):
+    """The configured CDLL for ``path`` (default: the in-tree ``libdynoed_cuda.so``)."""
+    path = path or LIB_PATH
+    if path not in _libs:
+        if not os.path.exists(path):
+            raise DynoedError(f"{path} is missing: build it with __graft_entry__.build(); "
+                              "there is no CPU fallback")
+        L = C.CDLL(path)
+        vp, dp, i64 = C.c_void_p, C.c_void_p, C.c_int64
+        L.dynoed_abi_version.restype = C.c_int
+        L.dynoed_model_count.restype = C.c_int
+        L.dynoed_model_name.restype = C.c_char_p
+        L.dynoed_model_name.argtypes = [C.c_int]
+        L.dynoed_model_query.argtypes = [C.c_char_p, C.POINTER(ModelInfo)]
+        L.dynoed_create.argtypes = [C.POINTER(ProblemDesc), C.c_int, C.POINTER(vp)]
+        L.dynoed_destroy.argtypes = [vp]
+        L.dynoed_destroy.restype = None
+        L.dynoed_set_criterion.argtypes = [vp, C.c_int]
+        L.dynoed_set_stream.argtypes = [vp, vp]
+        L.dynoed_own_stream.argtypes = [vp]
+        L.dynoed_eval_batch.argtypes = [vp, dp, i64, dp, dp, dp, C.c_uint32]
+        L.dynoed_eval_batch_async.argtypes = [vp, dp, i64, dp, dp, dp, C.c_uint32]
+        L.dynoed_sync.argtypes = [vp]
+        L.dynoed_argmin.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+        L.dynoed_trajectory.argtypes = [vp, dp, i64, dp]
+        L.dynoed_criterion_batch.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, i64, dp, dp]
+        L.dynoed_fp64_peak.argtypes = [C.c_int, vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.dynoed_kernel_stats_query.argtypes = [vp, C.c_int, C.POINTER(KernelStats)]
+        L.dynoed_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+        L.dynoed_host_free.argtypes = [vp]
+        L.dynoed_last_error.restype = C.c_char_p
+        L.dynoed_last_error.argtypes = [vp]
+        if L.dynoed_abi_version() != 1:
+            raise DynoedError("libdynoed_cuda.so ABI version mismatch")
+        _libs[path] = L
+    return _libs[path]
+
+
+def _check(rc, ctx=None, L=None):
+    if rc != 0:
+        msg = (L or lib()).dynoed_last_error(ctx)
+        raise DynoedError(f"dynoed error {rc}: {msg.decode() if msg else '?'}")
+
+
+def model_names(path=None):
+    L = lib(path)
+    return [L.dynoed_model_name(i).decode() for i in range(L.dynoed_model_count())]
+
+
+def model_info(name: str, path=None) -> ModelInfo:
+    mi = ModelInfo()
+    _check(lib(path).dynoed_model_query(name.encode(), C.byref(mi)), None, lib(path))
+    return mi
+
+
+def _ptr(a):
+    """Device pointer of a torch CUDA tensor, host pointer of a numpy array / torch CPU tensor."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        assert a.is_contiguous() and str(a.dtype) == "torch.float64"
+        return a.data_ptr()
+    if isinstance(a, int):
+        return a
+    raise TypeError(type(a))
+
+
+class Context:
+    """One OED problem bound to one GPU (wraps ``dynoed_ctx``)."""
+
+    def __init__(self, model: str, *, criterion: int, method: int, tgrid, indicators, ctrl_offsets,
+                 w_offsets, ic_offset: int, tau_offset: int, n_var: int, substeps: int = 4,
+                 step_edges=None, theta=None, x0=None, G0=None, device: int = 0, tile: int = 0,
+                 library_path: str | None = None):
+        L = self._L = lib(library_path)
+        self._keep = []
+
+        def arr(x, dt):
+            if x is None:
+                return None
+            a = np.ascontiguousarray(np.asarray(x, dtype=dt))
+            self._keep.append(a)
+            return a.ctypes.data_as(C.POINTER(C.c_double if dt == np.float64 else C.c_int32))
+        tgrid = np.asarray(tgrid, dtype=np.float64)
+        d = ProblemDesc()
+        d.struct_size = C.sizeof(ProblemDesc)
+        d.model = model.encode()
+        d.criterion = int(criterion)
+        d.method = int(method)
+        d.n_intervals = len(tgrid) - 1
+        d.tgrid = arr(tgrid, np.float64)
+        if step_edges is not None:
+            d.substeps = 0
+            d.edge_count = arr([len(e) for e in step_edges], np.int32)
+            d.step_edges = arr(np.concatenate([np.asarray(e, dtype=np.float64) for e in step_edges]),
+                               np.float64)
+        else:
+            d.substeps = int(substeps)
+        d.indicators = arr(np.asarray(indicators, dtype=np.int32).reshape(-1), np.int32)
+        d.ctrl_offsets = arr(list(ctrl_offsets) or [0], np.int32)
+        d.w_offsets = arr(list(w_offsets), np.int32)
+        d.ic_offset = int(ic_offset)
+        d.tau_offset = int(tau_offset)
+        d.n_var = int(n_var)
+        d.theta = arr(theta, np.float64)
+        d.x0 = arr(x0, np.float64)
+        d.G0 = arr(G0, np.float64)
+        d.tile = int(tile)
+        self.n_var = int(n_var)
+        self.n_intervals = d.n_intervals
+        self.info = model_info(model, library_path)
+        self.device = device
+        h = C.c_void_p()
+        _check(L.dynoed_create(C.byref(d), device, C.byref(h)), None, L)
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.dynoed_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_criterion(self, criterion: int):
+        _check(self._L.dynoed_set_criterion(self._h, int(criterion)), self._h, self._L)
+
+    def set_stream(self, stream_ptr: int):
+        """Run on the given cudaStream_t (0 = legacy default stream, e.g. torch's default)."""
+        _check(self._L.dynoed_set_stream(self._h, C.c_void_p(int(stream_ptr))), self._h, self._L)
+
+    def own_stream(self):
+        _check(self._L.dynoed_own_stream(self._h), self._h, self._L)
+
+    def eval_batch(self, designs, crit, grad=None, fim=None, n=None, async_=False):
+        """designs [n, n_var], crit [n], grad [n, n_var] | None, fim [n, nF] | None — numpy arrays
+        (host path) or torch CUDA tensors (device path), float64, contiguous."""
+        n = int(designs.shape[0]) if n is None else int(n)
+        fn = self._L.dynoed_eval_batch_async if async_ else self._L.dynoed_eval_batch
+        _check(fn(self._h, _ptr(designs), n, _ptr(crit), _ptr(grad), _ptr(fim), 0), self._h, self._L)
+
+    def sync(self):
+        _check(self._L.dynoed_sync(self._h), self._h, self._L)
+
+    def argmin(self):
+        i, v = C.c_int64(), C.c_double()
+        _check(self._L.dynoed_argmin(self._h, C.byref(i), C.byref(v)), self._h, self._L)
+        return int(i.value), float(v.value)
+
+    def trajectory(self, designs):
+        designs = np.ascontiguousarray(np.atleast_2d(designs), dtype=np.float64)
+        n = designs.shape[0]
+        X = np.empty((n, self.n_intervals + 1, self.info.nz + self.info.nF))
+        _check(self._L.dynoed_trajectory(self._h, _ptr(designs), n, _ptr(X)), self._h, self._L)
+        return X
+
+    def kernel_stats(self, with_grad=True) -> dict:
+        ks = KernelStats()
+        _check(self._L.dynoed_kernel_stats_query(self._h, int(with_grad), C.byref(ks)), self._h, self._L)
+        return {k: getattr(ks, k) for k, _ in KernelStats._fields_}
+
+    # convenience: host numpy in, numpy out
+    def evaluate(self, designs, grad=True, fim=True):
+        designs = np.ascontiguousarray(np.atleast_2d(designs), dtype=np.float64)
+        n = designs.shape[0]
+        crit = np.empty(n)
+        g = np.empty((n, self.n_var)) if grad else None
+        f = np.empty((n, self.info.nF)) if fim else None
+        self.eval_batch(designs, crit, g, f)
+        return crit, g, f
+
+
+def criterion_batch(criterion: int, F_packed, tau=None, with_gradient=False, device: int = 0):
+    """c(Symmetric(F + tau I)) for a batch of packed symmetric matrices — on the GPU."""
+    F_packed = np.ascontiguousarray(np.atleast_2d(F_packed), dtype=np.float64)
+    b, nF = F_packed.shape
+    n = int(round((np.sqrt(8 * nF + 1) - 1) / 2))
+    assert n * (n + 1) // 2 == nF
+    t = None if tau is None else np.ascontiguousarray(np.broadcast_to(np.asarray(tau, dtype=np.float64), (b,)))
+    val = np.empty(b)
+    dL = np.empty((b, nF)) if with_gradient else None
+    _check(lib().dynoed_criterion_batch(device, int(criterion), n, _ptr(F_packed), _ptr(t), b,
+                                        _ptr(val), _ptr(dL)))
+    return (val, dL) if with_gradient else val
+
+
+def fp64_peak(device: int = 0, stream_ptr=None):
+    t, ms = C.c_double(), C.c_double()
+    _check(lib().dynoed_fp64_peak(device, C.c_void_p(stream_ptr) if stream_ptr else None,
+                                  C.byref(t), C.byref(ms)))
+    return float(t.value), float(ms.value)

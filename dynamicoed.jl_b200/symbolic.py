@@ -27,12 +27,18 @@ class Num(sp.Symbol):
     integer, measurement_function, fisher_state, unweighted_information_gain, variable_ic
     """
 
-    def __new__(cls, name, kind="parameter", **meta):
+    def __new__(cls, name, kind="parameter", uid=None, **meta):
         obj = sp.Symbol.__xnew__(cls, name, real=True)
         obj.role = kind
         obj.meta = dict(meta)
         obj.order = next(_counter)
+        # identity = (name, declaration): two models may both declare a "p[1]" with different
+        # metadata; they must not compare equal (sympy caches expressions by equality).
+        obj.uid = uid if uid is not None else obj.order
         return obj
+
+    def _hashable_content(self):
+        return super()._hashable_content() + (self.uid,)
 
     # sympy re-creates atoms through __getnewargs_ex__ on pickling only; identity is kept in
     # subs/xreplace, so metadata survives every manipulation used in this package.
@@ -99,9 +105,13 @@ class Differential:
 
     def __call__(self, x):
         assert isinstance(x, Num), "Differential applies to a declared variable"
-        d = Num(f"D({x.name})", "derivative")
-        d.of = x
-        return d
+        return _derivative(x)
+
+
+def _derivative(x: "Num") -> "Num":
+    d = Num(f"D({x.name})", "derivative", uid=("D", x.uid))
+    d.of = x
+    return d
 
 
 @dataclass(frozen=True)
@@ -214,6 +224,4 @@ class ODESystem:
         return self.states
 
     def derivative_of(self, x: Num) -> Num:
-        d = Num(f"D({x.name})", "derivative")
-        d.of = x
-        return d
+        return _derivative(x)

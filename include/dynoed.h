@@ -1,0 +1,146 @@
+/* dynoed.h — C ABI of libdynoed_cuda.so: the B200-native batched evaluator for DynamicOED.jl's
+ * hot path (sensitivity-augmented integration over the measurement grid -> OED criterion and
+ * its gradient, for many candidate designs at once).
+ *
+ * There is no FFI in the reference (pure Julia).  Each entry point below names the reference
+ * interface it stands in for; INTEGRATION.md shows the Julia `ccall` binding a maintainer adds.
+ *
+ * Conventions
+ *   - plain C, no torch/CUDA types in signatures; every function returns 0 on success or a
+ *     negative DYNOED_E* code; the message is available from dynoed_last_error().
+ *   - the caller owns every buffer it passes.  `designs`, `crit`, `grad`, `fim` may be host
+ *     pointers (pageable or pinned) or device pointers; all pointers of one call must be of the
+ *     same kind (detected with cudaPointerGetAttributes).
+ *   - NaN/Inf in outputs are data, not errors.
+ *   - a ctx is bound to one device and is not re-entrant: one ctx per host thread / stream.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     DYNOED_ECUDA.
+ */
+#ifndef DYNOED_H
+#define DYNOED_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DYNOED_ABI_VERSION 1
+
+#define DYNOED_OK 0
+#define DYNOED_EINVAL (-1)  /* bad argument / inconsistent descriptor */
+#define DYNOED_ECUDA (-2)   /* CUDA runtime error (incl. "no device") */
+#define DYNOED_ENOMODEL (-3)
+#define DYNOED_EUNSUPPORTED (-4)
+
+/* criteria — /root/reference/src/fisher.jl:26-107, evaluated on Symmetric(F + tau I) (:12-15) */
+#define DYNOED_FISHER_A 0 /* -tr F          fisher.jl:28-30  */
+#define DYNOED_FISHER_D 1 /* -det F         fisher.jl:43-45  */
+#define DYNOED_FISHER_E 2 /* -lambda_min F  fisher.jl:58-60  */
+#define DYNOED_A 3        /* tr F^-1        fisher.jl:73-76  */
+#define DYNOED_D 4        /* 1/det F        fisher.jl:89-91  */
+#define DYNOED_E 5        /* max 1/lambda   fisher.jl:104-107 */
+
+/* fixed-step integrators (the reference passes `alg` to OrdinaryDiffEq.solve,
+ * /root/reference/src/problem.jl:25, /root/reference/src/discretize.jl:314-317) */
+#define DYNOED_RK4 0
+#define DYNOED_TSIT5 1 /* Tsit5 tableau, fixed step */
+
+typedef struct dynoed_ctx dynoed_ctx;
+
+/* Static facts about a compiled-in model (the emitted augmented system of
+ * /root/reference/src/augment.jl:128-244 after structural_simplify). */
+typedef struct dynoed_model_info {
+    int32_t nx, np, n_obs, n_ctrl, n_ic, n_theta, nz, nF;
+    int32_t ic_state[8];       /* 0-based state index of each unknown initial condition */
+    int32_t flops_primal, flops_primal_z, flops_adjoint, flops_consts; /* per RHS call, FMA = 2 */
+    double x0[8];
+    double G0[64];             /* column-major nx x np */
+    double theta[48];          /* default parameter values (non-control, non-weight) */
+} dynoed_model_info;
+
+/* One OED problem = model + merged time grid + design-vector layout + criterion + integrator.
+ * Replaces what OEDProblem / Timegrid / OEDRemake hold on the Julia side
+ * (/root/reference/src/problem.jl:10-30, /root/reference/src/discretize.jl:32-83, :229-265). */
+typedef struct dynoed_problem_desc {
+    uint32_t struct_size;      /* = sizeof(dynoed_problem_desc) */
+    const char* model;         /* name of a compiled-in model */
+    int32_t criterion;         /* DYNOED_FISHER_A ... */
+    int32_t method;            /* DYNOED_RK4 | DYNOED_TSIT5 */
+    int32_t n_intervals;       /* N: merged grid intervals (Timegrid.timespans) */
+    const double* tgrid;       /* [N+1] merged grid points */
+    int32_t substeps;          /* uniform substeps per merged interval (>0), or 0 with step_edges */
+    const int32_t* edge_count; /* [N] number of substep edges per interval (graded grids) or NULL */
+    const double* step_edges;  /* concatenated relative edges in [0,1] per interval, or NULL */
+    const int32_t* indicators; /* [(n_ctrl+n_obs)][N], 0-based (Timegrid.indicators - 1) */
+    const int32_t* ctrl_offsets; /* [n_ctrl] offset of each control's block in a design row */
+    const int32_t* w_offsets;    /* [n_obs]  offset of each weight block */
+    int32_t ic_offset;         /* offset of the initial-condition block (n_ic scalars) */
+    int32_t tau_offset;        /* offset of the regularisation variable */
+    int32_t n_var;             /* design-vector length */
+    const double* theta;       /* [n_theta] parameter values or NULL for the model defaults */
+    const double* x0;          /* [nx] or NULL */
+    const double* G0;          /* [nx*np] or NULL */
+    int32_t tile;              /* designs per CTA (0 = default 128; multiple of 32, <= 128) */
+    int32_t max_batch_hint;    /* 0 or expected designs per call (sizes scratch eagerly) */
+} dynoed_problem_desc;
+
+typedef struct dynoed_kernel_stats {
+    int32_t regs_per_thread, static_smem, dynamic_smem, blocks_per_sm, grid, block, sm_count;
+    int64_t launches;          /* kernels launched by this ctx so far */
+    int64_t scratch_bytes;
+    int32_t n_steps, stages;
+    double flops_per_design_eval, flops_per_design_grad; /* algorithmic, FMA = 2 */
+    double bytes_per_design;   /* algorithmic HBM bytes: n_var in + (1 + n_var + nF) out */
+} dynoed_kernel_stats;
+
+int dynoed_abi_version(void);
+int dynoed_model_count(void);
+const char* dynoed_model_name(int i);
+int dynoed_model_query(const char* name, dynoed_model_info* out);
+
+/* OEDProblem(sys, criterion; alg, tspan) + build_predictor (problem.jl:23-30, :80-90) */
+int dynoed_create(const dynoed_problem_desc* desc, int device, dynoed_ctx** out);
+void dynoed_destroy(dynoed_ctx* ctx);
+int dynoed_set_criterion(dynoed_ctx* ctx, int criterion);
+/* run on a caller-owned CUDA stream (cudaStream_t as void*; NULL = the legacy default stream);
+ * dynoed_own_stream() goes back to the stream the ctx created for itself */
+int dynoed_set_stream(dynoed_ctx* ctx, void* cuda_stream);
+int dynoed_own_stream(dynoed_ctx* ctx);
+
+/* The objective closure and its ForwardDiff gradient (problem.jl:112-121, :154), batched:
+ *   crit[k]  = c(F_k(t_f) + tau_k I) + tau_k
+ *   grad[k]  = d crit[k] / d designs[k]   (same layout as designs; NULL = objective only)
+ *   fim[k]   = packed upper triangle of F_k(t_f) (fisher.jl:3-5 order; NULL = skip)
+ * designs: [n][n_var] row-major in the layout of discretize.jl:110-137.  Blocking. */
+int dynoed_eval_batch(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad,
+                      double* fim, uint32_t flags);
+/* device pointers only; enqueues on the ctx stream and returns */
+int dynoed_eval_batch_async(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit,
+                            double* grad, double* fim, uint32_t flags);
+int dynoed_sync(dynoed_ctx* ctx);
+/* arg-min of the criterion over the most recent batch (multistart selection) */
+int dynoed_argmin(dynoed_ctx* ctx, int64_t* idx, double* val);
+
+/* the predictor p -> (X, t) of build_predictor (problem.jl:80-90) at the merged-grid points:
+ * X[k] is [N+1][nz+nF] row-major (state order [x; vec(G); F_triu], augment.jl:240) */
+int dynoed_trajectory(dynoed_ctx* ctx, const double* designs, int64_t n, double* X);
+
+/* criterion(F, tau) on caller-supplied packed symmetric matrices (fisher.jl:12-15):
+ * value[k] = c(Symmetric(F_k + tau_k I)); dcdF (optional) = packed d c / d F.  np <= 24. */
+int dynoed_criterion_batch(int device, int criterion, int np, const double* F_packed,
+                           const double* tau, int64_t batch, double* value, double* dcdF);
+
+/* register-resident DFMA-chain microbenchmark: the FP64 roofline denominator (TFLOP/s, FMA=2) */
+int dynoed_fp64_peak(int device, void* cuda_stream, double* tflops, double* ms);
+
+int dynoed_kernel_stats_query(dynoed_ctx* ctx, int with_grad, dynoed_kernel_stats* out);
+int dynoed_host_alloc(void** p, size_t bytes); /* pinned host memory for the e2e path */
+int dynoed_host_free(void* p);
+const char* dynoed_last_error(const dynoed_ctx* ctx); /* ctx may be NULL: last global error */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYNOED_H */
