@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — OED criterion+gradient evaluations per second on batched Lotka-Volterra.
+
+  python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+  python bench.py --impl reference --gpus N ...          # the reference path's CPU restatement
+
+A "step" is one pass of the hot path over one batch of 65,536 synthetic random relaxed designs
+per GPU (BASELINE.json config 3): integrate the sensitivity-augmented LV-fishing
+system (classic RK4, 4 substeps per merged interval, 30 intervals), reduce to the FisherD
+objective c(F + tau I) + tau and its full gradient w.r.t. all 71 design variables, arg-min.
+
+Prints ONE JSON line (rank 0).  value = device-resident throughput; e2e = the same metric through
+the public host-buffer call (pinned host memory, H2D + D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_PER_GPU = 65536
+SUBSTEPS = 4
+NBUF = 6        # rotating buffer sets: 6 x (37 MB in + 39 MB out) = 458 MB > 126 MB L2
+METRIC = "OED criterion+gradient evals/sec, batched Lotka-Volterra"
+UNIT = "designs/s"
+
+
+def make_designs(n, n_var, seed):
+    rng = np.random.Generator(np.random.Philox(seed))
+    d = rng.random((n, n_var))
+    d[:, -1] = 1e-3 + (1 - 1e-3) * d[:, -1]       # tau ~ U[1e-3, 1)
+    return d
+
+
+def workload_config(n_gpus):
+    return {"workload": "lv_fishing: 65,536 random relaxed designs per GPU, FisherD criterion + "
+                        "full gradient (71 vars), RK4 m=4 x 30 intervals, arg-min",
+            "designs_per_gpu": N_PER_GPU, "total_designs": N_PER_GPU * n_gpus, "n_var": 71,
+            "integrator": "RK4 fixed step, 4 substeps/interval (120 steps)",
+            "criterion": "FisherDCriterion", "parallelism": f"design-sharded x{n_gpus}",
+            "l2": f"{NBUF} rotating input/output buffer sets (>126 MB L2) + 327 MB trajectory scratch"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        load = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(pw)}
+
+
+def cpu_oracle(method="rk4"):
+    from dynamicoed.jl_b200 import models
+    from oracle.cpp_oracle import CppOracle, max_threads
+    from oracle.oed_oracle import FISHER_D, Oracle
+    o = Oracle(models.lotka_volterra_fishing(), FISHER_D, method, SUBSTEPS)
+    return CppOracle("lv_fishing", o), max_threads()
+
+
+def time_cpu(orc, threads, designs, seconds):
+    """designs/s of the CPU restatement on a bounded sample (about `seconds` of CPU work)."""
+    n0 = 64 * threads
+    t = time.perf_counter()
+    orc.evaluate(designs[:n0], grad=True, threads=threads)
+    dt = max(time.perf_counter() - t, 1e-6)
+    n = int(min(len(designs), max(n0, n0 * seconds / dt)))
+    t = time.perf_counter()
+    orc.evaluate(designs[:n], grad=True, threads=threads)
+    dt = time.perf_counter() - t
+    return n / dt, n, dt
+
+
+def run_reference(args):
+    """The reference arm: the reference path's own CPU implementation is Julia and cannot run here
+    (no Julia in the image); this times its CPU restatement (oracle/oed_oracle.cpp: forward-mode
+    duals through the fixed-step integrator, chunk 12, like ForwardDiff) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    orc, threads = cpu_oracle()
+    designs = make_designs(N_PER_GPU, 71, 20262)
+    sample = int(os.environ.get("DYNOED_REF_SAMPLE", 2048 * max(1, threads // 8)))
+    for _ in range(min(args.warmup, 2)):
+        orc.evaluate(designs[:sample], grad=True, threads=threads)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        lo = (k * sample) % (N_PER_GPU - sample + 1)
+        orc.evaluate(designs[lo:lo + sample], grad=True, threads=threads)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{sample} designs per step x {args.steps} steps of the same "
+                                       "workload (criterion + full forward-mode gradient)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import dynamicoed.jl_b200 as D
+    from dynamicoed.jl_b200 import models, runtime
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    prob = D.OEDProblem(D.OEDSystem(models.lotka_volterra_fishing()), D.FisherDCriterion(),
+                        alg=D.RK4(SUBSTEPS), device=local)
+    ctx = prob.context()
+    n, n_var = N_PER_GPU, ctx.n_var
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    # ---- device-resident inputs (distinct per rank and per buffer set) ----
+    d_in, d_crit, d_grad, d_fim = [], [], [], []
+    for b in range(NBUF):
+        h = make_designs(n, n_var, 20262 + 1000 * rank + b)
+        d_in.append(torch.from_numpy(h).to(dev))
+        d_crit.append(torch.empty(n, dtype=torch.float64, device=dev))
+        d_grad.append(torch.empty((n, n_var), dtype=torch.float64, device=dev))
+        d_fim.append(torch.empty((n, 3), dtype=torch.float64, device=dev))
+    rec_val = torch.empty(1, dtype=torch.float64, device=dev)
+    rec_idx = torch.empty(1, dtype=torch.int64, device=dev)
+    gat_val = [torch.empty(1, dtype=torch.float64, device=dev) for _ in range(world)]
+    gat_idx = [torch.empty(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    best = torch.empty(2, dtype=torch.float64, device=dev)
+
+    def step(k):
+        b = k % NBUF
+        ctx.eval_batch(d_in[b], d_crit[b], d_grad[b], d_fim[b], async_=True)
+        if world > 1:   # gather the per-rank (min, index) records and arg-min them, on device
+            ctx.argmin_async(rec_val, rec_idx)
+            dist.all_gather(gat_val, rec_val)
+            dist.all_gather(gat_idx, rec_idx)
+            v = torch.cat(gat_val)
+            j = torch.argmin(v)
+            best[0] = v[j]
+            best[1] = torch.cat(gat_idx)[j].double() + j.double() * n
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peak_burst, _ = runtime.fp64_peak(local, stream.cuda_stream)
+    for k in range(args.warmup):
+        step(k)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.12)
+    ctx.set_profiling(True)
+    launches0 = ctx.kernel_stats(True)["launches"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for k in range(args.steps):
+        step(k)
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    kernel_ms, kcount = ctx.kernel_time()
+    launches = ctx.kernel_stats(True)["launches"] - launches0 + (3 * args.steps if world > 1 else 0)
+    ctx.set_profiling(False)
+    if world > 1:
+        tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_total = float(tmax)
+    # keep the GPU under the same load long enough for nvidia-smi to see it (not timed)
+    t_probe = time.perf_counter()
+    k = 0
+    while sampler and time.perf_counter() - t_probe < 1.0:
+        step(k); k += 1
+        if k % 50 == 0:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    peak_after, _ = runtime.fp64_peak(local, stream.cuda_stream)
+
+    # ---- e2e: public host-buffer call, pinned host memory, H2D + D2H inside the timed region ----
+    ctx.own_stream()
+    hp = torch.from_numpy(make_designs(n, n_var, 777 + rank)).pin_memory()
+    hc = torch.empty(n, dtype=torch.float64).pin_memory()
+    hg = torch.empty((n, n_var), dtype=torch.float64).pin_memory()
+    hf = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+    e2e_steps = max(3, min(args.steps, 50))
+    for _ in range(3):
+        ctx.eval_batch(hp.numpy(), hc.numpy(), hg.numpy(), hf.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.eval_batch(hp.numpy(), hc.numpy(), hg.numpy(), hf.numpy())
+        _ = float(hc[0])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tmax = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_s = float(tmax)
+    e2e_value = n * world * e2e_steps / e2e_s
+
+    if rank == 0:
+        ks = ctx.kernel_stats(True)
+        flops = ks["flops_per_design_grad"] * n
+        achieved = flops / (kernel_ms * 1e-3) / 1e12 if kernel_ms > 0 else None
+        peak = max(peak_burst, peak_after)
+        hbm_peak, hbm_src = 6650.0, "fallback"
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+            hbm_src = "measured"
+        except Exception:
+            pass
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        line = {"metric": METRIC, "value": n * world * args.steps / (ms_total * 1e-3), "unit": UNIT,
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(world),
+                "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                             "frac": achieved / peak if achieved else None, "traffic": traffic,
+                             "peak_source": "DFMA-chain microbenchmark in this run (of measured; "
+                                            "nominal 148x64x2x1.965 GHz = 37.2)",
+                             "kernel": "oed_eval_kernel<Model_lv_fishing,TabRK4,grad>",
+                             "kernel_ms": kernel_ms, "kernel_launches_timed": kcount,
+                             "flops_per_design": ks["flops_per_design_grad"],
+                             "regs": ks["regs_per_thread"], "blocks_per_sm": ks["blocks_per_sm"],
+                             "hbm": {"achieved_gbs": ks["bytes_per_design"] * n / (kernel_ms * 1e-3) / 1e9
+                                     if kernel_ms > 0 else None,
+                                     "peak_gbs": hbm_peak, "peak_source": hbm_src,
+                                     "algorithmic_bytes_per_design": ks["bytes_per_design"]}},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * n_var * 8,
+                        "d2h_bytes_per_step": n * (1 + n_var + 3) * 8, "steps": e2e_steps,
+                        "host_memory": "pinned"},
+                "gpu_launches": int(launches), "clocks": clocks}
+        if not args.no_cpu_baseline:
+            orc, threads = cpu_oracle()
+            v, ns, dt = time_cpu(orc, threads, make_designs(N_PER_GPU, 71, 20262), 12.0)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{ns} of the 65,536 designs, criterion + full "
+                                              f"forward-mode gradient, {dt:.1f} s"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -153,6 +153,12 @@ struct dynoed_ctx {
     Slot slots[kSlots];
     int64_t launches = 0;
     size_t scratch_bytes = 0;
+    // optional per-launch timing of the evaluation kernel (device-pointer path)
+    bool profiling = false;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+    double kernel_ms_sum = 0.0;
+    int64_t kernel_ms_count = 0;
+    bool ev_pending = false;
     std::string err;
 };
 
@@ -354,6 +360,7 @@ void dynoed_destroy(dynoed_ctx* ctx) {
     cudaFree(ctx->d_first_step); cudaFree(ctx->d_step_t); cudaFree(ctx->d_step_h); cudaFree(ctx->d_indicators);
     cudaFree(ctx->traj); cudaFree(ctx->part_val); cudaFree(ctx->part_idx);
     cudaFree(ctx->d_best_val); cudaFree(ctx->d_best_idx);
+    if (ctx->ev_k0) { cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -396,7 +403,18 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
     P.use_tma = ((reinterpret_cast<uintptr_t>(designs) % 16 == 0) &&
                  (grad == nullptr || reinterpret_cast<uintptr_t>(grad) % 16 == 0) &&
                  (((size_t)ctx->tile * ctx->n_var * 8) % 16 == 0)) ? 1 : 0;
+    if (ctx->profiling) {
+        if (ctx->ev_pending) {   // fold the previous launch's duration into the running sum
+            CU(cudaEventSynchronize(ctx->ev_k1));
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1));
+            ctx->kernel_ms_sum += ms; ctx->kernel_ms_count++;
+            ctx->ev_pending = false;
+        }
+        CU(cudaEventRecord(ctx->ev_k0, st));
+    }
     CU(ctx->model->launch(ctx->method, grad != nullptr, P, grid, ctx->tile, smem_bytes(ctx), st));
+    if (ctx->profiling) { CU(cudaEventRecord(ctx->ev_k1, st)); ctx->ev_pending = true; }
     ctx->launches++;
     return DYNOED_OK;
 }
@@ -566,6 +584,38 @@ int dynoed_argmin(dynoed_ctx* ctx, int64_t* idx, double* val) {
     CU(cudaStreamSynchronize(ctx->stream));
     if (idx) *idx = (int64_t)i;
     if (val) *val = v;
+    return DYNOED_OK;
+}
+
+int dynoed_argmin_async(dynoed_ctx* ctx, double* d_val, int64_t* d_idx) {
+    if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    if (!ctx->have_batch) return fail(ctx, DYNOED_EINVAL, "no batch has been evaluated");
+    if (!d_val || !d_idx) return fail(ctx, DYNOED_EINVAL, "destination is NULL");
+    CU(cudaMemcpyAsync(d_val, ctx->d_best_val, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_idx, ctx->d_best_idx, sizeof(long long), cudaMemcpyDeviceToDevice, ctx->stream));
+    return DYNOED_OK;
+}
+
+int dynoed_set_profiling(dynoed_ctx* ctx, int on) {
+    if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    CU(cudaSetDevice(ctx->device));
+    if (on && !ctx->ev_k0) { CU(cudaEventCreate(&ctx->ev_k0)); CU(cudaEventCreate(&ctx->ev_k1)); }
+    ctx->profiling = on != 0;
+    ctx->kernel_ms_sum = 0.0; ctx->kernel_ms_count = 0; ctx->ev_pending = false;
+    return DYNOED_OK;
+}
+
+int dynoed_kernel_time(dynoed_ctx* ctx, double* mean_ms, int64_t* count) {
+    if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    if (ctx->ev_pending) {
+        CU(cudaEventSynchronize(ctx->ev_k1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1));
+        ctx->kernel_ms_sum += ms; ctx->kernel_ms_count++;
+        ctx->ev_pending = false;
+    }
+    if (mean_ms) *mean_ms = ctx->kernel_ms_count ? ctx->kernel_ms_sum / ctx->kernel_ms_count : 0.0;
+    if (count) *count = ctx->kernel_ms_count;
     return DYNOED_OK;
 }
 

@@ -172,6 +172,11 @@ class ComponentVector:
             return float(self.data[sl]) if isinstance(sl, int) else self.data[sl]
         raise AttributeError(key)
 
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            return self.__getattr__(key)
+        return np.asarray(self)[key]
+
     def __setattr__(self, key, value):
         sl = self.axes[key]
         if isinstance(sl, dict):

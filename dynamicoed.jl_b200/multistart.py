@@ -1,0 +1,92 @@
+"""Multi-GPU multistart sweep: the design batch is sharded over ranks (one process per GPU), each
+rank evaluates its contiguous block through ``libdynoed_cuda.so`` with NO data-path collective,
+and NCCL (``torch.distributed``) is used only to gather the per-rank (min value, global index)
+records, pick the global arg-min and broadcast the winner's design and gradient row
+(BASELINE.json config 5).
+
+The reference has no counterpart (single-threaded Julia; the optimiser calls the objective one
+design at a time, /root/reference/src/problem.jl:112-121).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous blocks of ceil(n/world) designs per rank."""
+    per = math.ceil(n / world) if world > 0 else n
+    lo = min(rank * per, n)
+    return lo, min(lo + per, n)
+
+
+def global_argmin(local_val: float, local_idx: int, device, group=None):
+    """all_gather of one (value, index) record per rank -> (value, index, owner rank).
+    NaN never wins; ties go to the smallest global index."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rec = torch.tensor([local_val if local_val == local_val else float("inf"), float(local_idx)],
+                       dtype=torch.float64, device=device)
+    if world == 1:
+        return float(rec[0]), int(local_idx), 0
+    out = [torch.empty_like(rec) for _ in range(world)]
+    dist.all_gather(out, rec, group=group)
+    recs = torch.stack(out).cpu()
+    best, owner = None, -1
+    for r in range(world):
+        v, i = float(recs[r, 0]), int(recs[r, 1])
+        if i < 0:
+            continue
+        if best is None or v < best[0] or (v == best[0] and i < best[1]):
+            best, owner = (v, i), r
+    if best is None:
+        return float("inf"), -1, -1
+    return best[0], best[1], owner
+
+
+def sweep(evaluate, designs_local: torch.Tensor, index_base: int, group=None, gather_crit=False):
+    """One multistart sweep on this rank's shard.
+
+    evaluate(designs_local) -> (crit [n_local], grad [n_local, n_var], (local argmin idx, value))
+    Returns dict(value, index, owner, design, grad[, crit_all on rank 0]).
+    """
+    crit, grad, (li, lv) = evaluate(designs_local)
+    dev = designs_local.device
+    gi = index_base + li if li >= 0 else -1
+    val, idx, owner = global_argmin(lv, gi, dev, group)
+    n_var = designs_local.shape[1]
+    row = torch.zeros(2, n_var, dtype=torch.float64, device=dev)
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if owner == rank and idx >= 0:
+        row[0] = designs_local[idx - index_base]
+        row[1] = grad[idx - index_base]
+    if dist.is_initialized() and dist.get_world_size(group) > 1 and owner >= 0:
+        dist.broadcast(row, src=owner, group=group)
+    out = dict(value=val, index=idx, owner=owner, design=row[0], grad=row[1])
+    if gather_crit and dist.is_initialized() and dist.get_world_size(group) > 1:
+        world = dist.get_world_size(group)
+        sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([crit.numel()], dtype=torch.int64, device=dev), group=group)
+        mx = int(max(int(s) for s in sizes))
+        pad = torch.full((mx,), float("nan"), dtype=torch.float64, device=dev)
+        pad[:crit.numel()] = crit
+        bufs = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(bufs, pad, group=group)
+        out["crit_all"] = torch.cat([b[:int(s)] for b, s in zip(bufs, sizes)])
+    elif gather_crit:
+        out["crit_all"] = crit
+    return out
+
+
+def gpu_evaluator(ctx):
+    """evaluate() closure over a `runtime.Context` for CUDA tensors (device-pointer path)."""
+    def evaluate(designs_local: torch.Tensor):
+        n = designs_local.shape[0]
+        crit = torch.empty(n, dtype=torch.float64, device=designs_local.device)
+        grad = torch.empty_like(designs_local)
+        if n > 0:
+            ctx.eval_batch(designs_local, crit, grad)
+            return crit, grad, ctx.argmin()
+        return crit, grad, (-1, float("inf"))
+    return evaluate

@@ -56,6 +56,7 @@ EXPORTS = ["dynoed_abi_version", "dynoed_model_count", "dynoed_model_name", "dyn
            "dynoed_create", "dynoed_destroy", "dynoed_set_criterion", "dynoed_set_stream",
            "dynoed_own_stream",
            "dynoed_eval_batch", "dynoed_eval_batch_async", "dynoed_sync", "dynoed_argmin",
+           "dynoed_argmin_async", "dynoed_set_profiling", "dynoed_kernel_time",
            "dynoed_trajectory", "dynoed_criterion_batch", "dynoed_fp64_peak",
            "dynoed_kernel_stats_query", "dynoed_host_alloc", "dynoed_host_free",
            "dynoed_last_error"]
@@ -87,6 +88,9 @@ def lib(path: str | None = None):
         L.dynoed_eval_batch_async.argtypes = [vp, dp, i64, dp, dp, dp, C.c_uint32]
         L.dynoed_sync.argtypes = [vp]
         L.dynoed_argmin.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+        L.dynoed_argmin_async.argtypes = [vp, dp, dp]
+        L.dynoed_set_profiling.argtypes = [vp, C.c_int]
+        L.dynoed_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         L.dynoed_trajectory.argtypes = [vp, dp, i64, dp]
         L.dynoed_criterion_batch.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, i64, dp, dp]
         L.dynoed_fp64_peak.argtypes = [C.c_int, vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -217,6 +221,18 @@ class Context:
         i, v = C.c_int64(), C.c_double()
         _check(self._L.dynoed_argmin(self._h, C.byref(i), C.byref(v)), self._h, self._L)
         return int(i.value), float(v.value)
+
+    def argmin_async(self, d_val, d_idx):
+        """Copy the (value, index) record into 1-element CUDA tensors (float64 / int64)."""
+        _check(self._L.dynoed_argmin_async(self._h, d_val.data_ptr(), d_idx.data_ptr()), self._h, self._L)
+
+    def set_profiling(self, on: bool):
+        _check(self._L.dynoed_set_profiling(self._h, int(bool(on))), self._h, self._L)
+
+    def kernel_time(self):
+        ms, cnt = C.c_double(), C.c_int64()
+        _check(self._L.dynoed_kernel_time(self._h, C.byref(ms), C.byref(cnt)), self._h, self._L)
+        return float(ms.value), int(cnt.value)
 
     def trajectory(self, designs):
         designs = np.ascontiguousarray(np.atleast_2d(designs), dtype=np.float64)

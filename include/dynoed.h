@@ -123,6 +123,10 @@ int dynoed_sync(dynoed_ctx* ctx);
 /* arg-min of the criterion over the most recent batch (multistart selection) */
 int dynoed_argmin(dynoed_ctx* ctx, int64_t* idx, double* val);
 
+/* same record copied into caller-owned DEVICE memory on the ctx stream (no host sync): feeds the
+ * NCCL all-gather of per-rank (min, index) records in the multi-GPU sweep */
+int dynoed_argmin_async(dynoed_ctx* ctx, double* d_val, int64_t* d_idx);
+
 /* the predictor p -> (X, t) of build_predictor (problem.jl:80-90) at the merged-grid points:
  * X[k] is [N+1][nz+nF] row-major (state order [x; vec(G); F_triu], augment.jl:240) */
 int dynoed_trajectory(dynoed_ctx* ctx, const double* designs, int64_t n, double* X);
@@ -135,6 +139,9 @@ int dynoed_criterion_batch(int device, int criterion, int np, const double* F_pa
 /* register-resident DFMA-chain microbenchmark: the FP64 roofline denominator (TFLOP/s, FMA=2) */
 int dynoed_fp64_peak(int device, void* cuda_stream, double* tflops, double* ms);
 
+/* CUDA-event timing of the evaluation kernel itself (device-pointer path), for the roofline */
+int dynoed_set_profiling(dynoed_ctx* ctx, int on);
+int dynoed_kernel_time(dynoed_ctx* ctx, double* mean_ms, int64_t* count);
 int dynoed_kernel_stats_query(dynoed_ctx* ctx, int with_grad, dynoed_kernel_stats* out);
 int dynoed_host_alloc(void** p, size_t bytes); /* pinned host memory for the e2e path */
 int dynoed_host_free(void* p);

@@ -1,0 +1,278 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracles, the committed
+golden fixtures and the reference's own goldens.  Tolerance: relative 1e-10 on F entries,
+criterion values and gradients (BASELINE.json north_star); gradients are compared relative to
+the largest gradient entry of the design (FisherE/D conditioning note)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import dynamicoed.jl_b200 as D
+from dynamicoed.jl_b200 import models, runtime
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+RTOL = 1e-10
+CRITS = [D.FisherACriterion, D.FisherDCriterion, D.FisherECriterion, D.ACriterion, D.DCriterion,
+         D.ECriterion]
+CASES = {"one_d": models.one_d, "readme": models.readme, "lv_fishing": models.lotka_volterra_fishing,
+         "lv_ic": models.lotka_volterra_ic}
+ALGS = {"rk4": D.RK4, "tsit5": D.Tsit5}
+
+
+def rel(a, b):
+    return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-300))
+
+
+def rel_rows(a, b):
+    den = np.maximum(np.max(np.abs(b), axis=1), 1e-300)
+    return float(np.max(np.max(np.abs(a - b), axis=1) / den))
+
+
+def random_designs(name, n_var, n, seed):
+    rng = np.random.Generator(np.random.Philox(seed))
+    d = rng.random((n, n_var))
+    d[:, -1] = 1e-3 + (1 - 1e-3) * d[:, -1]
+    if name == "lv_ic":
+        d[:, 0] = 0.1 + 0.9 * d[:, 0]
+    return d
+
+
+def make_problem(name, crit_cls, method="rk4", m=4, **kw):
+    return D.OEDProblem(D.OEDSystem(CASES[name]()), crit_cls(), alg=ALGS[method](m), **kw)
+
+
+@pytest.fixture(scope="module")
+def oracles():
+    from oracle.cpp_oracle import CppOracle
+    from oracle.oed_oracle import Oracle
+    cache = {}
+
+    def get(name, crit, method, m):
+        key = (name, method, m)
+        if key not in cache:
+            o = Oracle(CASES[name](), 0, method, m)
+            cache[key] = CppOracle(name, o)
+        cache[key].set_criterion(crit)
+        return cache[key]
+    return get
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("method", ["rk4", "tsit5"])
+def test_golden_fixtures(name, method, built_library):
+    z = np.load(os.path.join(GOLD, f"{name}_{method}_m4.npz"))
+    for crit, cls in enumerate(CRITS):
+        ctx = make_problem(name, cls, method).context()
+        c, g, F = ctx.evaluate(z["designs"])
+        assert rel(c, z[f"crit{crit}"]) < RTOL
+        assert rel(F, z["F"]) < RTOL
+        assert rel_rows(g, z[f"grad{crit}"]) < RTOL, (name, method, crit)
+    X = ctx.trajectory(z["designs"][2])[0].T
+    assert np.allclose(X, z["X0"], rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("method,m", [("rk4", 4), ("rk4", 1), ("tsit5", 2)])
+def test_random_designs_vs_cpp_oracle(name, method, m, oracles, built_library):
+    n = 2048 if name == "lv_fishing" else 512
+    for crit, cls in enumerate(CRITS):
+        ctx = make_problem(name, cls, method, m).context()
+        des = random_designs(name, ctx.n_var, n, 20260 + crit)
+        c, g, F = ctx.evaluate(des)
+        oc, og, oF = oracles(name, crit, method, m).evaluate(des, grad=True)
+        assert rel(c, oc) < RTOL and rel(F, oF) < RTOL
+        assert rel_rows(g, og) < RTOL, (name, method, m, crit, rel_rows(g, og))
+        i, v = ctx.argmin()
+        assert i == int(np.argmin(c)) and v == c[i]
+
+
+def test_ragged_and_empty_batches(oracles, built_library):
+    ctx = make_problem("lv_fishing", D.DCriterion).context()
+    orc = oracles("lv_fishing", 4, "rk4", 4)
+    des = random_designs("lv_fishing", 71, 1000, 5)
+    full = ctx.evaluate(des)
+    for n in (1, 2, 31, 127, 128, 129, 257, 1000):
+        c, g, F = ctx.evaluate(des[:n])
+        assert np.array_equal(c, full[0][:n]) and np.array_equal(g, full[1][:n])
+        assert np.array_equal(F, full[2][:n])
+    oc, og, oF = orc.evaluate(des[:129], grad=True)
+    assert rel(full[0][:129], oc) < RTOL and rel_rows(full[1][:129], og) < RTOL
+    # empty batch: OK, nothing written
+    ctx.eval_batch(np.zeros((0, 71)), np.zeros(0), np.zeros((0, 71)), None, n=0)
+    with pytest.raises(runtime.DynoedError):
+        ctx.argmin()
+    # objective only / no fim
+    c2, g2, f2 = ctx.evaluate(des[:300], grad=False, fim=False)
+    assert g2 is None and f2 is None and np.array_equal(c2, full[0][:300])
+
+
+def test_host_and_device_paths_agree_bitwise(built_library):
+    import torch
+    ctx = make_problem("lv_fishing", D.FisherDCriterion).context()
+    des = random_designs("lv_fishing", 71, 20000, 6)
+    c, g, F = ctx.evaluate(des)                                   # host path (chunked pipeline)
+    d = torch.from_numpy(des).cuda()
+    dc = torch.empty(len(des), dtype=torch.float64, device="cuda")
+    dg = torch.empty_like(d)
+    dF = torch.empty((len(des), 3), dtype=torch.float64, device="cuda")
+    ctx.eval_batch(d, dc, dg, dF)                                 # device path (one launch)
+    assert np.array_equal(dc.cpu().numpy(), c) and np.array_equal(dg.cpu().numpy(), g)
+    assert np.array_equal(dF.cpu().numpy(), F)
+    assert ctx.argmin()[0] == int(np.argmin(c))
+    # unaligned device pointer -> non-TMA staging path, same numbers
+    buf = torch.empty(len(des) * 71 + 1, dtype=torch.float64, device="cuda")
+    d2 = buf[1:].view(len(des), 71)
+    d2.copy_(d)
+    ctx.eval_batch(d2, dc, dg, dF)
+    assert np.array_equal(dc.cpu().numpy(), c) and np.array_equal(dg.cpu().numpy(), g)
+    # mixing host and device pointers is an error, not a crash
+    with pytest.raises(runtime.DynoedError):
+        ctx.eval_batch(d, c, None, None)
+
+
+def test_criteria_kat_on_gpu(built_library):
+    """/root/reference/test/criteria.jl:14-30 through dynoed_criterion_batch."""
+    F = np.array([[5.68145, -0.148312, 2.00382, 5.1841, 3.57814],
+                  [-0.148312, 2.17276, -1.18576, 1.57651, -3.95544],
+                  [2.00382, -1.18576, 3.8703, -0.14832, 2.69545],
+                  [5.1841, 1.57651, -0.14832, 10.9617, 0.0774284],
+                  [3.57814, -3.95544, 2.69545, 0.0774284, 24.8495]])
+    res = [-47.53571, -2180.4107236837117, -1.0326129713287733, 2.103928493261123,
+           0.0004586291881332073, 0.9684170427504832]
+    for cls, r in zip(CRITS, res):
+        assert np.isclose(cls()(F, 0.0), r, rtol=1.5e-8, atol=0)
+        assert np.isclose(cls()(F), r, rtol=1.5e-8, atol=0)
+    from oracle.oed_oracle import criterion, criterion_matrix_gradient
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 3, 4, 6, 8, 12):
+        A = rng.standard_normal((n, n + 3))
+        M = A @ A.T
+        for crit, cls in enumerate(CRITS):
+            assert np.isclose(cls()(M, 0.25), criterion(crit, M, 0.25), rtol=1e-11)
+            L = cls().gradient(M, 0.25)
+            Lo = criterion_matrix_gradient(crit, M, 0.25)
+            assert np.max(np.abs(L - Lo)) <= 1e-9 * np.max(np.abs(Lo))
+
+
+def test_full_size_properties(oracles, built_library):
+    """BASELINE.json config 3 size (65,536 designs): linearity of F in w, determinism, arg-min,
+    and spot parity on a 4,096-design subset."""
+    import torch
+    n = 65536
+    ctx = make_problem("lv_fishing", D.FisherDCriterion).context()
+    des = random_designs("lv_fishing", 71, n, 20262)
+    d = torch.from_numpy(des).cuda()
+    outs = []
+    for rep in range(2):
+        c = torch.empty(n, dtype=torch.float64, device="cuda")
+        g = torch.empty_like(d)
+        F = torch.empty((n, 3), dtype=torch.float64, device="cuda")
+        ctx.eval_batch(d, c, g, F)
+        outs.append((c.cpu().numpy(), g.cpu().numpy(), F.cpu().numpy()))
+    assert all(np.array_equal(a, b) for a, b in zip(*outs))           # deterministic
+    c, g, F = outs[0]
+    assert ctx.argmin() == (int(np.argmin(c)), float(c.min()))
+    # linearity: same controls, w3 = 0.25 w1 + 0.5 w2  =>  F3 = 0.25 F1 + 0.5 F2
+    half = n // 2
+    d1, d2 = des[:half].copy(), des[:half].copy()
+    d2[:, 10:70] = des[half:, 10:70]
+    d3 = d1.copy()
+    d3[:, 10:70] = 0.25 * d1[:, 10:70] + 0.5 * d2[:, 10:70]
+    Fs = [ctx.evaluate(x, grad=False)[2] for x in (d1, d2, d3)]
+    assert rel(Fs[2], 0.25 * Fs[0] + 0.5 * Fs[1]) < 1e-13
+    # d obj / d tau = tr(Lambda) + 1 and FisherD: Lambda = -adj(M) => -(F11 + F22 + 2 tau) + 1
+    assert rel(g[:, 70], -(F[:, 0] + F[:, 2] + 2 * des[:, 70]) + 1) < 1e-13
+    idx = np.random.default_rng(0).choice(n, 4096, replace=False)
+    oc, og, oF = oracles("lv_fishing", 1, "rk4", 4).evaluate(des[idx], grad=True)
+    assert rel(c[idx], oc) < RTOL and rel(F[idx], oF) < RTOL and rel_rows(g[idx], og) < RTOL
+
+
+def test_set_criterion_and_predictor(oracles, built_library):
+    prob = make_problem("lv_fishing", D.FisherACriterion)
+    ctx = prob.context()
+    des = random_designs("lv_fishing", 71, 64, 8)
+    for crit in range(6):
+        ctx.set_criterion(crit)
+        c, g, _ = ctx.evaluate(des)
+        oc, og, _ = oracles("lv_fishing", crit, "rk4", 4).evaluate(des, grad=True)
+        assert rel(c, oc) < RTOL and rel_rows(g, og) < RTOL
+    X, t = D.build_predictor(prob)(des[0])
+    assert X.shape == (9, 31) and np.array_equal(t, prob.timegrid.tpoints)
+    Xo = oracles("lv_fishing", 0, "rk4", 4).trajectory(des[0])
+    assert np.allclose(X, Xo, rtol=1e-11, atol=1e-13)
+
+
+def test_user_model_is_emitted_and_compiled_once(built_library):
+    """A system that is not compiled in: emitted, built with nvcc, loaded, parity-checked."""
+    from dynamicoed.jl_b200.symbolic import (Differential, Eq, ODESystem, independent_variable,
+                                             observed_variables, parameters, variables)
+    from oracle.oed_oracle import Oracle
+    t = independent_variable("t")
+    a, b = variables("a b", [1.0, 0.5])
+    k = parameters("k[1] k[2]", [0.7, 1.3], tunable=True)
+    v = parameters("v", 0.0, input=True, measurement_rate=0.5, bounds=(0.0, 1.0))
+    obs = observed_variables("o[1] o[2]", measurement_rate=0.25)
+    Dt = Differential(t)
+    import sympy as sp
+    sysm = ODESystem([Eq(Dt(a), -k[0] * a * b + v), Eq(Dt(b), k[0] * a * b - k[1] * b * sp.exp(-a))],
+                     t, tspan=(0.0, 2.0), observed=[Eq(obs[0], a * b), Eq(obs[1], b)], name="user")
+    prob = D.OEDProblem(D.OEDSystem(sysm), D.ACriterion(), alg=D.RK4(3))
+    ctx = prob.context()
+    des = random_designs("user", ctx.n_var, 200, 4)
+    c, g, F = ctx.evaluate(des)
+    oc, og, oF = Oracle(sysm, 3, "rk4", 3).evaluate(des, grad=True)
+    assert rel(c, oc) < RTOL and rel(F, oF) < RTOL and rel_rows(g, og) < RTOL
+
+
+def _solve(opt_prob, u0=None):
+    from scipy.optimize import NonlinearConstraint, minimize
+    f = opt_prob.f
+    cons = []
+    if f.cons is not None:
+        cons = [NonlinearConstraint(f.cons, opt_prob.lcons, opt_prob.ucons, jac=f.cons_j)]
+    u0 = opt_prob.u0 if u0 is None else u0
+    return minimize(f.f, u0, jac=lambda u: f.grad(None, u), bounds=list(zip(opt_prob.lb, opt_prob.ub)),
+                    constraints=cons, method="SLSQP", options=dict(ftol=1e-13, maxiter=400))
+
+
+def test_reference_1d_optimum_through_the_boundary(built_library):
+    """/root/reference/test/references/1D.jl:29-66 with SLSQP standing in for Ipopt: objective and
+    gradient come from the GPU through OptimizationProblem's f / grad hooks."""
+    for i, cls in enumerate(CRITS):
+        prob = D.OEDProblem(D.structural_simplify(D.OEDSystem(models.one_d())), cls())
+        v = D.states(prob)
+        dts = {k: np.array([b - a for a, b in g]) for k, g in D.get_timegrids(prob).items()}
+        cons = D.ConstraintsSystem([D.geq(0.2 - 0.5 * sum(dts["w₁"] * v.measurements["w₁"]), 0)])
+        op = D.OptimizationProblem(prob, None, constraints=cons, integer_constraints=False)
+        u0 = op.u0.copy()
+        u0[:10] = 0.3
+        r = _solve(op, u0)
+        assert np.allclose(r.x[:10], [0, 0, 0, 1, 1, 1, 1, 0, 0, 0], atol=2e-3), (cls, r.x)
+        want = -1.2823515846720533e-02 if i < 3 else 2.0
+        assert abs(r.fun - want) <= 1e-2 + 1e-1 * abs(want)
+
+
+def test_reference_lv_optimum_through_the_boundary(built_library):
+    """/root/reference/test/references/LotkaVolterra.jl:8-155: u* = [0.62, 0, ...], w1*, w2* = last
+    4 of 30, objective -4.85 (atol 1e-2)."""
+    prob = D.OEDProblem(D.structural_simplify(D.OEDSystem(models.lotka_volterra_fishing())),
+                        D.FisherACriterion())
+    v = D.states(prob)
+    dts = {k: np.array([b - a for a, b in g]) for k, g in D.get_timegrids(prob).items()}
+    cons = D.ConstraintsSystem([
+        D.geq(0.2 - 0.5 * sum(dts["w₁"] * v.measurements["w₁"]), 0),
+        D.geq(0.2 - 0.5 * sum(dts["w₁"] * v.measurements["w₂"]), 0),
+        D.geq(1.0, sum(dts["u"] * v.controls["u"]))])
+    op = D.OptimizationProblem(prob, None, constraints=cons, integer_constraints=False)
+    assert len(op.u0) == 71 and not op.int.any()
+    r = _solve(op)
+    assert abs(r.fun - (-4.85)) < 1e-2
+    assert np.allclose(r.x[:10], [0.62] + [0] * 9, atol=1e-2)
+    w_ref = np.array([0.0] * 26 + [1.0] * 4)
+    assert np.allclose(r.x[10:40], w_ref, atol=1e-2) and np.allclose(r.x[40:70], w_ref, atol=1e-2)
+    opi = D.OptimizationProblem(D.OEDProblem(D.OEDSystem(models.lotka_volterra_fishing(True)),
+                                             D.DCriterion()), None, integer_constraints=True)
+    assert opi.int[:10].all() and opi.int[10:70].all() and not opi.int[70]

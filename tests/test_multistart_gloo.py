@@ -1,0 +1,69 @@
+"""N>1 host logic (sharding, (min, index) gather, winner broadcast) with world_size=2 over gloo
+on CPU.  The evaluator is injected: here the CPU oracle stands in for the GPU library."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from dynamicoed.jl_b200 import models
+from dynamicoed.jl_b200.multistart import shard_bounds
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 64, 65536, 1048576 + 3):
+        for w in (1, 2, 4, 8):
+            parts = [shard_bounds(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(parts[:-1], parts[1:]))
+            assert max(hi - lo for lo, hi in parts) - min(hi - lo for lo, hi in parts) <= \
+                max(1, -(-n // w))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dynamicoed.jl_b200.multistart import sweep
+    from oracle.cpp_oracle import CppOracle
+    from oracle.oed_oracle import Oracle, FISHER_D
+    o = Oracle(models.lotka_volterra_fishing(), FISHER_D, "rk4", 2)
+    c = CppOracle("lv_fishing", o)
+    rng = np.random.Generator(np.random.Philox(99))
+    n = 301                                     # ragged: 151 + 150
+    des = rng.random((n, 71))
+    lo, hi = shard_bounds(n, rank, world)
+
+    def evaluate(d):
+        cr, g, _ = c.evaluate(d.numpy(), grad=True, threads=2)
+        k = int(np.argmin(cr))
+        return torch.from_numpy(cr), torch.from_numpy(g), (k, float(cr[k]))
+    out = sweep(evaluate, torch.from_numpy(des[lo:hi]), lo, gather_crit=True)
+    cr_all, g_all, _ = c.evaluate(des, grad=True, threads=2)
+    k = int(np.argmin(cr_all))
+    ok = (out["index"] == k and out["value"] == cr_all[k] and
+          np.array_equal(out["design"].numpy(), des[k]) and
+          np.array_equal(out["grad"].numpy(), g_all[k]) and
+          np.array_equal(out["crit_all"].numpy(), cr_all) and out["owner"] == (0 if k < hi - lo or rank == 0 and k < hi else out["owner"]))
+    q.put((rank, bool(ok), out["index"], k))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_sweep_matches_single_process():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _, _ in res), res
