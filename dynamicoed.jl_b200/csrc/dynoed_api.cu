@@ -734,9 +734,10 @@ int dynoed_kernel_stats_query(dynoed_ctx* ctx, int with_grad, dynoed_kernel_stat
         for (int j = 0; j < i; ++j)
             nza += (ctx->method == DYNOED_RK4 ? TabRK4::a(i, j) : TabTsit5::a(i, j)) != 0.0;
     const double fwd = (double)S * mi.flops_primal + 2.0 * mi.nz * nza + 2.0 * (mi.nz + mi.nF) * S + nza + S;
-    const double bwd = (double)(S - 1) * mi.flops_primal_z + (double)S * mi.flops_adjoint + 2.0 * mi.nz * nza /*Z*/ +
-                       (double)S * mi.nz /*hb*lam*/ + 2.0 * mi.nz * nza /*kb*/ + (double)S * mi.nz /*lacc*/ +
-                       2.0 * S * mi.n_obs + nza + S;
+    //   backward step: (S-1) primal_z + S adjoint calls + stage states (2 NZ per a_ij) + kb'
+    //                  (2 NZ per a_ij) + lambda / u-bar / w-bar accumulation (2 per entry and stage)
+    const double bwd = (double)(S - 1) * mi.flops_primal_z + (double)S * mi.flops_adjoint + 2.0 * mi.nz * nza +
+                       2.0 * mi.nz * nza + 2.0 * S * (mi.nz + mi.n_obs + mi.n_ctrl) + 2.0 * nza + S;
     const double epi = 10.0 * mi.nF;
     o->flops_per_design_eval = fwd * ctx->n_steps + (double)ctx->n_intervals * mi.flops_consts + epi;
     o->flops_per_design_grad = (fwd + bwd) * ctx->n_steps + 2.0 * ctx->n_intervals * mi.flops_consts + epi;

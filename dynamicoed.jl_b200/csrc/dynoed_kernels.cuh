@@ -255,9 +255,9 @@ __device__ __forceinline__ void criterion_eval(const double (&F)[N * (N + 1) / 2
         // eigen-based: lambda_min and its unit eigenvector (stable forms)
         const double mid = 0.5 * tr, hd = 0.5 * (a - d);
         const double rad = sqrt(fma(hd, hd, b * b));
-        double lmin;
-        if (mid >= 0.0) { const double lmax = mid + rad; lmin = (lmax != 0.0) ? det / lmax : mid - rad; }
-        else lmin = mid - rad;
+        double lmin, lmax;
+        if (mid >= 0.0) { lmax = mid + rad; lmin = (lmax != 0.0) ? det / lmax : mid - rad; }
+        else { lmin = mid - rad; lmax = det / lmin; }
         double v0, v1;
         if (b == 0.0) { v0 = (a <= d) ? 1.0 : 0.0; v1 = 1.0 - v0; }
         else {
@@ -268,10 +268,9 @@ __device__ __forceinline__ void criterion_eval(const double (&F)[N * (N + 1) / 2
             else { const double r = rsqrt(nq2); v0 = q0 * r; v1 = q1 * r; }
         }
         if (crit == kFisherE) { value = -lmin; L[0] = -v0 * v0; L[1] = -v0 * v1; L[2] = -v1 * v1; return; }
-        {   // kE: max_i 1/lambda_i ; for positive definite M this is 1/lambda_min
-            const double lmax = tr - lmin;
+        {   // kE: max_i 1/lambda_i = 1/lambda_min unless the matrix is indefinite
             double lk = lmin, w0 = v0, w1 = v1;
-            if (1.0 / lmax > 1.0 / lmin) { lk = lmax; w0 = -v1; w1 = v0; }
+            if (lmin < 0.0 && lmax > 0.0) { lk = lmax; w0 = -v1; w1 = v0; }
             const double s = -1.0 / (lk * lk);
             value = 1.0 / lk; L[0] = s * w0 * w0; L[1] = s * w0 * w1; L[2] = s * w1 * w1;
         }
@@ -378,13 +377,17 @@ __device__ __forceinline__ void rk_forward_step(double t, double h, double (&z)[
 }
 
 // lam: adjoint of z_{n+1} on entry, of z_n on exit.  ub/wb accumulate d/du and d/dw of the
-// Lambda-weighted objective over this step.
+// Lambda-weighted objective over this step.  The stage adjoints are carried UNSCALED
+// (zb'_s = zb_s / (h b_s)), which removes the h*b_s*lam products from the dependency chain:
+//   kb'_s = lam + sum_{j>s} (h a_js b_j / b_s) zb'_j ,   zb'_s = g_z(Z_s)^T kb'_s + q_z(Z_s) ,
+//   lam_n = lam + sum_s h b_s zb'_s ,  ub += h b_s g_u^T kb'_s ,  wb_i += h b_s q_i(Z_s).
 template <class M, class Tab>
 __device__ __forceinline__ void rk_adjoint_step(double t, double h, const double (&zn)[M::NZ],
-                                                double (&lam)[M::NZ], const double* u, const double* w,
+                                                double (&lam)[M::NZ], const double* u, const double* cw,
                                                 const double* th, const double* c, const double* L,
                                                 double* ub, double* wb) {
     constexpr int S = Tab::S, NZ = M::NZ;
+    constexpr int NCU = M::NCTRL > 0 ? M::NCTRL : 1;
     double Z[S][NZ];
     {   // recompute the stage states
         double k[S][NZ];
@@ -409,24 +412,27 @@ __device__ __forceinline__ void rk_adjoint_step(double t, double h, const double
     for (int a = 0; a < NZ; ++a) lacc[a] = lam[a];
 #pragma unroll
     for (int s = S - 1; s >= 0; --s) {
+        static_assert(Tab::b(0) != 0.0, "unscaled stage adjoints need b_s != 0");
         const double hb = h * Tab::b(s);
         double kb[NZ];
 #pragma unroll
-        for (int a = 0; a < NZ; ++a) kb[a] = hb * lam[a];
+        for (int a = 0; a < NZ; ++a) kb[a] = lam[a];
 #pragma unroll
         for (int j = s + 1; j < S; ++j) {
             if (Tab::a(j, s) != 0.0) {
-                const double ha = h * Tab::a(j, s);
+                const double r = h * (Tab::a(j, s) * Tab::b(j) / Tab::b(s));
 #pragma unroll
-                for (int a = 0; a < NZ; ++a) kb[a] = fma(ha, Zb[j][a], kb[a]);
+                for (int a = 0; a < NZ; ++a) kb[a] = fma(r, Zb[j][a], kb[a]);
             }
         }
-        double qw[M::NOBS];
-        M::adjoint(t + Tab::c(s) * h, Z[s], u, w, th, c, L, kb, hb, Zb[s], ub, qw);
+        double qw[M::NOBS], us[NCU];
+        M::adjoint(t + Tab::c(s) * h, Z[s], u, cw, th, c, L, kb, Zb[s], us, qw);
 #pragma unroll
         for (int i = 0; i < M::NOBS; ++i) wb[i] = fma(hb, qw[i], wb[i]);
 #pragma unroll
-        for (int a = 0; a < NZ; ++a) lacc[a] += Zb[s][a];
+        for (int k = 0; k < M::NCTRL; ++k) ub[k] = fma(hb, us[k], ub[k]);
+#pragma unroll
+        for (int a = 0; a < NZ; ++a) lacc[a] = fma(hb, Zb[s][a], lacc[a]);
     }
 #pragma unroll
     for (int a = 0; a < NZ; ++a) lam[a] = lacc[a];
@@ -545,8 +551,13 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
                 for (int k = 0; k < NCU; ++k) { ub[k] = 0.0; uk[k] = -1; }
 #pragma unroll
                 for (int i = 0; i < NOBS; ++i) { wb[i] = 0.0; wk[i] = -1; }
+                // (x, G) checkpoint of the step about to be processed; the next one (s - 1) is
+                // requested one full step ahead so that its L2/HBM latency hides behind the math
+                double zn[NZ];
+#pragma unroll
+                for (int a = 0; a < NZ; ++a) zn[a] = tr[((size_t)(P.n_steps - 1) * NZ + a) * TILE];
                 for (int j = N - 1; j >= 0; --j) {
-                    double u[NCU], w[NOBS], c[M::NCONST];
+                    double u[NCU], cw[NOBS], c[M::NCONST];
 #pragma unroll
                     for (int k = 0; k < NCTRL; ++k) {
                         const int idx = __ldg(P.indicators + k * N + j);
@@ -563,16 +574,19 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
                             if (wk[i] >= 0) row[P.w_off[i] + wk[i]] = wb[i];
                             wb[i] = 0.0; wk[i] = idx;
                         }
-                        w[i] = row[P.w_off[i] + idx];
+                        cw[i] = 2.0 * row[P.w_off[i] + idx];
                     }
                     M::consts(u, th, c);
                     const int s0 = __ldg(P.first_step + j), s1 = __ldg(P.first_step + j + 1);
                     for (int s = s1 - 1; s >= s0; --s) {
-                        double zn[NZ];
+                        double znext[NZ];
+                        const int sp = s > 0 ? s - 1 : 0;
 #pragma unroll
-                        for (int a = 0; a < NZ; ++a) zn[a] = tr[((size_t)s * NZ + a) * TILE];
-                        rk_adjoint_step<M, Tab>(__ldg(P.step_t + s), __ldg(P.step_h + s), zn, lam, u, w, th, c,
+                        for (int a = 0; a < NZ; ++a) znext[a] = tr[((size_t)sp * NZ + a) * TILE];
+                        rk_adjoint_step<M, Tab>(__ldg(P.step_t + s), __ldg(P.step_h + s), zn, lam, u, cw, th, c,
                                                 L, ub, wb);
+#pragma unroll
+                        for (int a = 0; a < NZ; ++a) zn[a] = znext[a];
                     }
                 }
 #pragma unroll

@@ -160,7 +160,10 @@ class ComponentVector:
     reference uses: ``u.controls.u``, ``u.measurements.w₁``, ``u.regularization``)."""
 
     def __init__(self, data, axes):
-        object.__setattr__(self, "data", np.asarray(data, dtype=np.float64))
+        data = np.asarray(data)
+        if data.dtype != object:
+            data = np.asarray(data, dtype=np.float64)
+        object.__setattr__(self, "data", data)
         object.__setattr__(self, "axes", axes)
 
     def __getattr__(self, key):
@@ -169,7 +172,9 @@ class ComponentVector:
             sl = axes[key]
             if isinstance(sl, dict):
                 return ComponentVector(self.data, sl)
-            return float(self.data[sl]) if isinstance(sl, int) else self.data[sl]
+            if isinstance(sl, int):
+                return self.data[sl] if self.data.dtype == object else float(self.data[sl])
+            return self.data[sl]
         raise AttributeError(key)
 
     def __getitem__(self, key):

@@ -234,11 +234,13 @@ def emit_model(name: str, s: SimplifiedOEDSystem) -> tuple[str, dict]:
         names[v] = f"w[{k}]"
     kb = [sp.Symbol(f"kb{a}", real=True) for a in range(nz)]
     Ls = [sp.Symbol(f"L{k}", real=True) for k in range(nF)]
-    cq = sp.Symbol("cq", real=True)
+    cws = [sp.Symbol(f"cw{i}", real=True) for i in range(n_obs)]   # cw_i = 2 w_i (caller)
     for a, v in enumerate(kb):
         names[v] = f"kb[{a}]"
     for k, v in enumerate(Ls):
         names[v] = f"L[{k}]"
+    for k, v in enumerate(cws):
+        names[v] = f"cw[{k}]"
     Lfull = sp.zeros(np_, np_)
     for k, (i, j) in enumerate(triu_pairs(np_)):
         Lfull[i, j] = Ls[k]
@@ -285,7 +287,7 @@ def emit_model(name: str, s: SimplifiedOEDSystem) -> tuple[str, dict]:
             f"r{i}{j}", sum(Lfull[j, k] * Qt[i, k] for k in range(np_))))
         for i in range(n_obs):
             b.out(f"qw[{i}]", sum(Qt[i, j] * r[i, j] for j in range(np_)))
-        cw = [b.tmp(f"cw{i}", 2 * cq * wsym[i]) for i in range(n_obs)]
+        cw = cws
         # G-bar = J^T kG + sum_i cw_i Hc[i,:]^T r_i
         for j in range(np_):
             for c in range(nx):
@@ -334,7 +336,7 @@ def emit_model(name: str, s: SimplifiedOEDSystem) -> tuple[str, dict]:
         for a in range(nx):
             b.out(f"zb[{a}]", collect_lin(grads[a]).xreplace(sub))
         for k in range(nc):
-            b.out(f"ub[{k}]", collect_lin(grads[nx + k]).xreplace(sub), accumulate=True)
+            b.out(f"ub[{k}]", collect_lin(grads[nx + k]).xreplace(sub))
         return b
 
     def build_obs():
@@ -350,7 +352,7 @@ def emit_model(name: str, s: SimplifiedOEDSystem) -> tuple[str, dict]:
     for k, v in enumerate(hoist.table.values()):
         names[v] = f"c[{k}]"
     pr = _Printer(names)
-    inputs = set(names.keys()) | {cq}
+    inputs = set(names.keys())
     code, flops = {}, {}
     for key, blk in blocks.items():
         code[key], flops[key] = blk.render(pr, inputs)
@@ -412,12 +414,12 @@ struct {cname} {{
             const double* __restrict__ c, double* __restrict__ dz) {{
 {code['primal_z']}
     }}
-    // zb = (d g/d z)^T kb + cq * sum_i w_i d(Q_i L Q_i^T)/dz ;  ub += (d g/d u)^T kb ;
-    // qw[i] = Q_i L Q_i^T  (L = packed symmetric d criterion / d F)
+    // zb = (d g/d z)^T kb + sum_i (cw_i / 2) d(Q_i L Q_i^T)/dz   (caller passes cw_i = 2 w_i) ;
+    // ub = (d g/d u)^T kb ;  qw[i] = Q_i L Q_i^T  (L = packed symmetric d criterion / d F)
     __device__ __forceinline__ static void adjoint(double t, const double* __restrict__ z,
-            const double* __restrict__ u, const double* __restrict__ w,
+            const double* __restrict__ u, const double* __restrict__ cw,
             const double* __restrict__ th, const double* __restrict__ c,
-            const double* __restrict__ L, const double* __restrict__ kb, double cq,
+            const double* __restrict__ L, const double* __restrict__ kb,
             double* __restrict__ zb, double* __restrict__ ub, double* __restrict__ qw) {{
 {code['adjoint']}
     }}
