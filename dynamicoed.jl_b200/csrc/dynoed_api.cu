@@ -132,6 +132,7 @@ struct dynoed_ctx {
     int n_intervals = 0, n_steps = 0, n_var = 0, tile = 128;
     int sm_count = 0;
     int bps[2] = {0, 0};   // blocks per SM without / with gradient
+    size_t smem_floor = 0; // dynamic shared memory padding that caps the resident CTAs per SM
     cudaFuncAttributes fa[2];
     EvalParams base;       // tables + layout + model data (batch pointers filled per launch)
     int* d_first_step = nullptr;
@@ -149,6 +150,7 @@ struct dynoed_ctx {
     int part_used = 0;
     double* d_best_val = nullptr;
     long long* d_best_idx = nullptr;
+    unsigned int* d_ticket = nullptr;
     bool have_batch = false;
     Slot slots[kSlots];
     int64_t launches = 0;
@@ -212,7 +214,9 @@ static size_t traj_bytes_for(const dynoed_ctx* ctx, int grid) {
     return (size_t)grid * ctx->n_steps * ctx->model->info.nz * ctx->tile * sizeof(double);
 }
 
-static size_t smem_bytes(const dynoed_ctx* ctx) { return 128 + (size_t)ctx->tile * ctx->n_var * sizeof(double); }
+static size_t smem_bytes(const dynoed_ctx* ctx) {
+    return std::max(ctx->smem_floor, 128 + (size_t)ctx->tile * ctx->n_var * sizeof(double));
+}
 
 static int grid_for(const dynoed_ctx* ctx, int64_t n, bool grad) {
     const int64_t ntiles = (n + ctx->tile - 1) / ctx->tile;
@@ -317,6 +321,8 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     CUC(cudaMemcpy(ctx->d_indicators, d->indicators, sizeof(int) * nvars * N, cudaMemcpyHostToDevice));
     CUC(cudaMalloc(&ctx->d_best_val, sizeof(double)));
     CUC(cudaMalloc(&ctx->d_best_idx, sizeof(long long)));
+    CUC(cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)));
+    CUC(cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int)));
 
     EvalParams& P = ctx->base;
     memset(&P, 0, sizeof(P));
@@ -337,6 +343,11 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     for (int k = 0; k < mi.nx; ++k) P.x0[k] = d->x0 ? d->x0[k] : mi.x0[k];
     for (int k = 0; k < mi.nx * mi.np; ++k) P.G0[k] = d->G0 ? d->G0[k] : mi.G0[k];
 
+    if (const char* cap = getenv("DYNOED_MAX_CTAS_PER_SM")) {   // tuning knob (occupancy experiments)
+        const int k = atoi(cap);
+        if (k > 0) ctx->smem_floor = ((size_t)prop.sharedMemPerMultiprocessor / k - 1024) & ~(size_t)127;
+        if (ctx->smem_floor > (size_t)prop.sharedMemPerBlockOptin - 2048) ctx->smem_floor = prop.sharedMemPerBlockOptin - 2048;
+    }
     const size_t smem = smem_bytes(ctx);
     if (smem > (size_t)prop.sharedMemPerBlockOptin)
         return bail(DYNOED_EINVAL, "tile * n_var does not fit in shared memory; use a smaller tile");
@@ -359,7 +370,7 @@ void dynoed_destroy(dynoed_ctx* ctx) {
     }
     cudaFree(ctx->d_first_step); cudaFree(ctx->d_step_t); cudaFree(ctx->d_step_h); cudaFree(ctx->d_indicators);
     cudaFree(ctx->traj); cudaFree(ctx->part_val); cudaFree(ctx->part_idx);
-    cudaFree(ctx->d_best_val); cudaFree(ctx->d_best_idx);
+    cudaFree(ctx->d_best_val); cudaFree(ctx->d_best_idx); cudaFree(ctx->d_ticket);
     if (ctx->ev_k0) { cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -400,6 +411,8 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
     P.designs = designs; P.crit = crit; P.grad = grad; P.fim = fim; P.xgrid = xgrid;
     P.traj = traj; P.n = n;
     P.part_val = part_val; P.part_idx = part_idx;
+    P.part_base = 0; P.n_parts = grid; P.ticket_target = (unsigned int)grid;
+    P.ticket = ctx->d_ticket; P.best_val = ctx->d_best_val; P.best_idx = ctx->d_best_idx;
     P.use_tma = ((reinterpret_cast<uintptr_t>(designs) % 16 == 0) &&
                  (grad == nullptr || reinterpret_cast<uintptr_t>(grad) % 16 == 0) &&
                  (((size_t)ctx->tile * ctx->n_var * 8) % 16 == 0)) ? 1 : 0;
@@ -416,14 +429,6 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
     CU(ctx->model->launch(ctx->method, grad != nullptr, P, grid, ctx->tile, smem_bytes(ctx), st));
     if (ctx->profiling) { CU(cudaEventRecord(ctx->ev_k1, st)); ctx->ev_pending = true; }
     ctx->launches++;
-    return DYNOED_OK;
-}
-
-static int finish_argmin(dynoed_ctx* ctx, int parts, cudaStream_t st) {
-    argmin_final_kernel<<<1, 256, 0, st>>>(ctx->part_val, ctx->part_idx, parts, ctx->d_best_val, ctx->d_best_idx);
-    CU(cudaGetLastError());
-    ctx->launches++;
-    ctx->have_batch = true;
     return DYNOED_OK;
 }
 
@@ -447,7 +452,8 @@ static int eval_device(dynoed_ctx* ctx, const double* designs, int64_t n, double
     rc = launch_device(ctx, designs, n, crit, grad, fim, xgrid, ctx->traj, ctx->part_val, ctx->part_idx, grid,
                        ctx->stream);
     if (rc) return rc;
-    return finish_argmin(ctx, grid, ctx->stream);
+    ctx->have_batch = true;
+    return DYNOED_OK;
 }
 
 static int ensure_slot(dynoed_ctx* ctx, Slot& s, int64_t cap, bool grad, bool fim) {
@@ -490,7 +496,9 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
     chunk = std::min<int64_t>(chunk, ((n + ctx->tile - 1) / ctx->tile) * ctx->tile);
     const int64_t nchunks = (n + chunk - 1) / chunk;
     const int grid_c = grid_for(ctx, chunk, g);
-    int rc = ensure_partials(ctx, (int)(nchunks * grid_c));
+    int total_parts = 0;
+    for (int64_t c = 0; c < nchunks; ++c) total_parts += grid_for(ctx, std::min(chunk, n - c * chunk), g);
+    int rc = ensure_partials(ctx, total_parts);
     if (rc) return rc;
     for (int k = 0; k < kSlots && k < nchunks; ++k) {
         rc = ensure_slot(ctx, ctx->slots[k], chunk, g, fim != nullptr);
@@ -501,6 +509,7 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
     CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(cudaEventRecord(ev, ctx->stream));
     for (int k = 0; k < kSlots && k < nchunks; ++k) CU(cudaStreamWaitEvent(ctx->slots[k].stream, ev, 0));
+    int part_base = 0;
     for (int64_t c = 0; c < nchunks; ++c) {
         Slot& s = ctx->slots[c % kSlots];
         const int64_t off = c * chunk, cnt = std::min(chunk, n - off);
@@ -510,13 +519,12 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         const int grid = grid_for(ctx, cnt, g);
         P.designs = s.d_designs; P.crit = s.d_crit; P.grad = g ? s.d_grad : nullptr; P.fim = fim ? s.d_fim : nullptr;
         P.xgrid = nullptr; P.traj = s.traj; P.n = cnt;
-        P.part_val = ctx->part_val + c * grid_c; P.part_idx = ctx->part_idx + c * grid_c;
+        P.part_val = ctx->part_val; P.part_idx = ctx->part_idx;
+        P.part_base = part_base; P.n_parts = total_parts; P.ticket_target = (unsigned int)total_parts;
+        P.ticket = ctx->d_ticket; P.best_val = ctx->d_best_val; P.best_idx = ctx->d_best_idx;
+        part_base += grid;
         P.use_tma = (((size_t)ctx->tile * ctx->n_var * 8) % 16 == 0) ? 1 : 0;
         P.index_base = off;
-        // unused partial slots of this chunk must not win
-        if (grid < grid_c) {
-            CU(cudaMemsetAsync(P.part_idx + grid, 0xff, sizeof(long long) * (grid_c - grid), s.stream));
-        }
         CU(ctx->model->launch(ctx->method, g, P, grid, ctx->tile, smem_bytes(ctx), s.stream));
         ctx->launches++;
         CU(cudaMemcpyAsync(crit + off, s.d_crit, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s.stream));
@@ -530,7 +538,9 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         CU(cudaStreamWaitEvent(ctx->stream, ev, 0));
     }
     CU(cudaEventDestroy(ev));
-    return finish_argmin(ctx, (int)(nchunks * grid_c), ctx->stream);
+    (void)grid_c;
+    ctx->have_batch = true;
+    return DYNOED_OK;
 }
 
 static int eval_common(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad, double* fim,
@@ -704,6 +714,39 @@ int dynoed_fp64_peak(int device, void* stream, double* tflops, double* ms_out) {
     const double flops = 2.0 * 8 * 16 * (double)iters * grid * block;
     if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
     if (ms_out) *ms_out = best;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    return DYNOED_OK;
+}
+
+// instruction throughput of FP64 operand patterns, in Ginstr/s per GPU (thread-level instructions)
+int dynoed_fp64_microbench(int device, int variant, double* ginstr_per_s) {
+    dynoed_ctx* ctx = nullptr;
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    const int block = 256, grid = prop.multiProcessorCount * 8, iters = 2048;
+    double* out = nullptr;
+    CU(cudaMalloc(&out, sizeof(double) * (size_t)grid * block));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU(cudaEventRecord(e0, 0));
+        switch (variant) {
+            case 1: fp64_variant_kernel<1><<<grid, block>>>(out, iters, 1.0, 0.999999); break;
+            case 2: fp64_variant_kernel<2><<<grid, block>>>(out, iters, 1.0, 0.999999); break;
+            case 3: fp64_variant_kernel<3><<<grid, block>>>(out, iters, 1.0, 0.999999); break;
+            case 4: fp64_variant_kernel<4><<<grid, block>>>(out, iters, 1.0, 0.999999); break;
+            case 5: fp64_variant_kernel<5><<<grid, block>>>(out, iters, 1.0, 0.999999); break;
+            default: fp64_peak_kernel<<<grid, block>>>(out, iters, 1.0); break;
+        }
+        CU(cudaEventRecord(e1, 0));
+        CU(cudaEventSynchronize(e1));
+        float ms; CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    CU(cudaGetLastError());
+    if (ginstr_per_s) *ginstr_per_s = 8.0 * 16 * (double)iters * grid * block / (best * 1e-3) / 1e9;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
     return DYNOED_OK;
 }

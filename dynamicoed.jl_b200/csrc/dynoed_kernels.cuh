@@ -63,9 +63,16 @@ struct EvalParams {
     double theta[kMaxTheta];
     double x0[kMaxX];
     double G0[kMaxG];
-    // partial arg-min records, one per CTA: (value, global index)
+    // arg-min: one (value, global index) record per CTA; the last CTA to finish (ticket) reduces
+    // all n_parts records of the batch into best_val / best_idx
     double* __restrict__ part_val;
     long long* __restrict__ part_idx;
+    int part_base;                        // first record slot of this launch
+    int n_parts;                          // records of the whole batch (all launches of the call)
+    unsigned int ticket_target;           // CTAs of the whole batch
+    unsigned int* __restrict__ ticket;
+    double* __restrict__ best_val;
+    long long* __restrict__ best_idx;
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -159,6 +166,15 @@ __device__ __forceinline__ void tma_store_wait_read() {
 }
 __device__ __forceinline__ void tma_store_wait_all() {
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+// trajectory checkpoint load that the compiler may not sink towards its use (issued where written)
+__device__ __forceinline__ double ld_pinned(const double* p) {
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -551,11 +567,13 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
                 for (int k = 0; k < NCU; ++k) { ub[k] = 0.0; uk[k] = -1; }
 #pragma unroll
                 for (int i = 0; i < NOBS; ++i) { wb[i] = 0.0; wk[i] = -1; }
-                // (x, G) checkpoint of the step about to be processed; the next one (s - 1) is
-                // requested one full step ahead so that its L2/HBM latency hides behind the math
+                // (x, G) checkpoint and (t, h) of the step about to be processed.  The next step's
+                // (s - 1) are requested at the top of the current step, and the checkpoint three
+                // steps ahead is pulled from HBM into L2, so that neither latency is exposed.
                 double zn[NZ];
 #pragma unroll
                 for (int a = 0; a < NZ; ++a) zn[a] = tr[((size_t)(P.n_steps - 1) * NZ + a) * TILE];
+                double tcur = __ldg(P.step_t + P.n_steps - 1), hcur = __ldg(P.step_h + P.n_steps - 1);
                 for (int j = N - 1; j >= 0; --j) {
                     double u[NCU], cw[NOBS], c[M::NCONST];
 #pragma unroll
@@ -582,11 +600,16 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
                         double znext[NZ];
                         const int sp = s > 0 ? s - 1 : 0;
 #pragma unroll
-                        for (int a = 0; a < NZ; ++a) znext[a] = tr[((size_t)sp * NZ + a) * TILE];
-                        rk_adjoint_step<M, Tab>(__ldg(P.step_t + s), __ldg(P.step_h + s), zn, lam, u, cw, th, c,
-                                                L, ub, wb);
+                        for (int a = 0; a < NZ; ++a) znext[a] = ld_pinned(tr + ((size_t)sp * NZ + a) * TILE);
+                        const double tnext = __ldg(P.step_t + sp), hnext = __ldg(P.step_h + sp);
+                        if (s >= 3) {
+#pragma unroll
+                            for (int a = 0; a < NZ; ++a) prefetch_l2(tr + ((size_t)(s - 3) * NZ + a) * TILE);
+                        }
+                        rk_adjoint_step<M, Tab>(tcur, hcur, zn, lam, u, cw, th, c, L, ub, wb);
 #pragma unroll
                         for (int a = 0; a < NZ; ++a) zn[a] = znext[a];
+                        tcur = tnext; hcur = hnext;
                     }
                 }
 #pragma unroll
@@ -635,6 +658,7 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
     }
     if ((tid & 31) == 0) { red_val[tid >> 5] = best_val; red_idx[tid >> 5] = best_idx; }
     __syncthreads();
+    __shared__ int is_last;
     if (tid == 0) {
         for (int wq = 1; wq < (int)((blockDim.x + 31) >> 5); ++wq) {
             const double ov = red_val[wq];
@@ -643,40 +667,42 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
                 best_val = ov; best_idx = oi;
             }
         }
-        P.part_val[blockIdx.x] = best_val;
-        P.part_idx[blockIdx.x] = best_idx;
+        P.part_val[P.part_base + blockIdx.x] = best_val;
+        P.part_idx[P.part_base + blockIdx.x] = best_idx;
         if (P.use_tma) tma_store_wait_all();
+        __threadfence();
+        const unsigned int t = atomicAdd(P.ticket, 1u);
+        is_last = (t == P.ticket_target - 1u);
     }
-}
-
-// final arg-min over the per-CTA records (one CTA)
-__global__ void argmin_final_kernel(const double* __restrict__ pv, const long long* __restrict__ pi, int m,
-                                    double* __restrict__ out_val, long long* __restrict__ out_idx) {
-    __shared__ double sv[32];
-    __shared__ long long si[32];
-    double bv = __longlong_as_double(0x7ff0000000000000LL);
-    long long bi = -1;
-    for (int i = threadIdx.x; i < m; i += blockDim.x) {
-        const double v = pv[i];
-        const long long k = pi[i];
-        if (k >= 0 && (v < bv || (v == bv && (bi < 0 || k < bi)))) { bv = v; bi = k; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_down_sync(0xffffffffu, bv, o);
-        const long long oi = __shfl_down_sync(0xffffffffu, bi, o);
-        if (oi >= 0 && (ov < bv || (ov == bv && (bi < 0 || oi < bi)))) { bv = ov; bi = oi; }
-    }
-    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int wq = 1; wq < (int)(blockDim.x >> 5); ++wq) {
-            const double ov = sv[wq];
-            const long long oi = si[wq];
+    if (is_last) {   // the last CTA of the batch reduces every record (no extra launch)
+        __threadfence();
+        double bv = __longlong_as_double(0x7ff0000000000000LL);
+        long long bi = -1;
+        for (int i = tid; i < P.n_parts; i += blockDim.x) {
+            const double v = __ldcg(P.part_val + i);
+            const long long k = __ldcg(P.part_idx + i);
+            if (k >= 0 && (v < bv || (v == bv && (bi < 0 || k < bi)))) { bv = v; bi = k; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, bv, o);
+            const long long oi = __shfl_down_sync(0xffffffffu, bi, o);
             if (oi >= 0 && (ov < bv || (ov == bv && (bi < 0 || oi < bi)))) { bv = ov; bi = oi; }
         }
-        *out_val = bv;
-        *out_idx = bi;
+        __syncthreads();
+        if ((tid & 31) == 0) { red_val[tid >> 5] = bv; red_idx[tid >> 5] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int wq = 1; wq < (int)((blockDim.x + 31) >> 5); ++wq) {
+                const double ov = red_val[wq];
+                const long long oi = red_idx[wq];
+                if (oi >= 0 && (ov < bv || (ov == bv && (bi < 0 || oi < bi)))) { bv = ov; bi = oi; }
+            }
+            *P.best_val = bv;
+            *P.best_idx = bi;
+            *P.ticket = 0u;
+        }
     }
 }
 
@@ -789,6 +815,37 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
         }
     }
     out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+
+// Operand-pattern variants of the DFMA chain (what a real right-hand side looks like):
+//   1: d = fma(a, b, c) with three distinct REGISTER operands per chain
+//   2: d = fma(a, b, a)  (two distinct registers)     3: d = a * b (DMUL, two registers)
+//   4: d = a + b (DADD)                                5: d = fma(a, U, c) with U a uniform/param operand
+template <int V>
+__global__ void __launch_bounds__(256) fp64_variant_kernel(double* out, int iters, double seed, double up) {
+    double a[8], b[8], c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        a[i] = seed + threadIdx.x + i; b[i] = 0.999999 + 1e-9 * (threadIdx.x + i); c[i] = 1e-9 * (i + 1 + threadIdx.x);
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (V == 1) a[i] = fma(a[i], b[i], c[i]);
+                else if (V == 2) a[i] = fma(a[i], b[i], a[i]);
+                else if (V == 3) a[i] = a[i] * b[i];
+                else if (V == 4) a[i] = a[i] + c[i];
+                else a[i] = fma(a[i], up, c[i]);
+            }
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+    out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = s;
 }
 
 }  // namespace dynoed

@@ -57,7 +57,7 @@ EXPORTS = ["dynoed_abi_version", "dynoed_model_count", "dynoed_model_name", "dyn
            "dynoed_own_stream",
            "dynoed_eval_batch", "dynoed_eval_batch_async", "dynoed_sync", "dynoed_argmin",
            "dynoed_argmin_async", "dynoed_set_profiling", "dynoed_kernel_time",
-           "dynoed_trajectory", "dynoed_criterion_batch", "dynoed_fp64_peak",
+           "dynoed_trajectory", "dynoed_criterion_batch", "dynoed_fp64_peak", "dynoed_fp64_microbench",
            "dynoed_kernel_stats_query", "dynoed_host_alloc", "dynoed_host_free",
            "dynoed_last_error"]
 
@@ -94,6 +94,7 @@ def lib(path: str | None = None):
         L.dynoed_trajectory.argtypes = [vp, dp, i64, dp]
         L.dynoed_criterion_batch.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, i64, dp, dp]
         L.dynoed_fp64_peak.argtypes = [C.c_int, vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.dynoed_fp64_microbench.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
         L.dynoed_kernel_stats_query.argtypes = [vp, C.c_int, C.POINTER(KernelStats)]
         L.dynoed_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
         L.dynoed_host_free.argtypes = [vp]
@@ -276,3 +277,10 @@ def fp64_peak(device: int = 0, stream_ptr=None):
     _check(lib().dynoed_fp64_peak(device, C.c_void_p(stream_ptr) if stream_ptr else None,
                                   C.byref(t), C.byref(ms)))
     return float(t.value), float(ms.value)
+
+
+def fp64_microbench(variant: int, device: int = 0) -> float:
+    """Thread-level FP64 instructions per second (in 1e9) for an operand pattern (see dynoed.h)."""
+    g = C.c_double()
+    _check(lib().dynoed_fp64_microbench(device, int(variant), C.byref(g)))
+    return float(g.value)

@@ -139,6 +139,10 @@ int dynoed_criterion_batch(int device, int criterion, int np, const double* F_pa
 /* register-resident DFMA-chain microbenchmark: the FP64 roofline denominator (TFLOP/s, FMA=2) */
 int dynoed_fp64_peak(int device, void* cuda_stream, double* tflops, double* ms);
 
+/* FP64 instruction throughput (thread-level Ginstr/s) for operand patterns: 0 DFMA reg*const+const,
+ * 1 DFMA three registers, 2 DFMA two registers, 3 DMUL, 4 DADD, 5 DFMA reg*uniform+reg */
+int dynoed_fp64_microbench(int device, int variant, double* ginstr_per_s);
+
 /* CUDA-event timing of the evaluation kernel itself (device-pointer path), for the roofline */
 int dynoed_set_profiling(dynoed_ctx* ctx, int on);
 int dynoed_kernel_time(dynoed_ctx* ctx, double* mean_ms, int64_t* count);
