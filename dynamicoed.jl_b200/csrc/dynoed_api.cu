@@ -28,24 +28,24 @@ static thread_local std::string g_last_error;
 struct ModelEntry {
     const char* name;
     dynoed_model_info info;
-    cudaError_t (*launch)(int method, bool grad, const EvalParams& P, int grid, int block, size_t smem,
+    cudaError_t (*launch)(int method, bool grad, bool ucoef, const EvalParams& P, int grid, int block, size_t smem,
                           cudaStream_t st);
-    cudaError_t (*attrs)(int method, bool grad, int block, size_t smem, cudaFuncAttributes* fa,
+    cudaError_t (*attrs)(int method, bool grad, bool ucoef, int block, size_t smem, cudaFuncAttributes* fa,
                          int* blocks_per_sm);
 };
 
-template <class M, class Tab, bool GRAD>
+template <class M, class Tab, bool GRAD, bool UC>
 static cudaError_t launch_one(const EvalParams& P, int grid, int block, size_t smem, cudaStream_t st) {
-    auto kern = oed_eval_kernel<M, Tab, GRAD>;
+    auto kern = oed_eval_kernel<M, Tab, GRAD, UC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, block, smem, st>>>(P);
     return cudaGetLastError();
 }
 
-template <class M, class Tab, bool GRAD>
+template <class M, class Tab, bool GRAD, bool UC>
 static cudaError_t attrs_one(int block, size_t smem, cudaFuncAttributes* fa, int* bps) {
-    auto kern = oed_eval_kernel<M, Tab, GRAD>;
+    auto kern = oed_eval_kernel<M, Tab, GRAD, UC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(fa, kern);
@@ -53,21 +53,35 @@ static cudaError_t attrs_one(int block, size_t smem, cudaFuncAttributes* fa, int
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, block, smem);
 }
 
-template <class M>
-static cudaError_t launch_model(int method, bool grad, const EvalParams& P, int grid, int block, size_t smem,
-                                cudaStream_t st) {
-    if (method == DYNOED_RK4)
-        return grad ? launch_one<M, TabRK4, true>(P, grid, block, smem, st)
-                    : launch_one<M, TabRK4, false>(P, grid, block, smem, st);
-    return grad ? launch_one<M, TabTsit5, true>(P, grid, block, smem, st)
-                : launch_one<M, TabTsit5, false>(P, grid, block, smem, st);
+template <class M, class Tab>
+static cudaError_t launch_tab(bool grad, bool uc, const EvalParams& P, int grid, int block, size_t smem,
+                              cudaStream_t st) {
+    if (grad) return uc ? launch_one<M, Tab, true, true>(P, grid, block, smem, st)
+                        : launch_one<M, Tab, true, false>(P, grid, block, smem, st);
+    return uc ? launch_one<M, Tab, false, true>(P, grid, block, smem, st)
+              : launch_one<M, Tab, false, false>(P, grid, block, smem, st);
 }
 
 template <class M>
-static cudaError_t attrs_model(int method, bool grad, int block, size_t smem, cudaFuncAttributes* fa, int* bps) {
-    if (method == DYNOED_RK4)
-        return grad ? attrs_one<M, TabRK4, true>(block, smem, fa, bps) : attrs_one<M, TabRK4, false>(block, smem, fa, bps);
-    return grad ? attrs_one<M, TabTsit5, true>(block, smem, fa, bps) : attrs_one<M, TabTsit5, false>(block, smem, fa, bps);
+static cudaError_t launch_model(int method, bool grad, bool uc, const EvalParams& P, int grid, int block,
+                                size_t smem, cudaStream_t st) {
+    if (method == DYNOED_RK4) return launch_tab<M, TabRK4>(grad, uc, P, grid, block, smem, st);
+    return launch_tab<M, TabTsit5>(grad, uc, P, grid, block, smem, st);
+}
+
+template <class M, class Tab>
+static cudaError_t attrs_tab(bool grad, bool uc, int block, size_t smem, cudaFuncAttributes* fa, int* bps) {
+    if (grad) return uc ? attrs_one<M, Tab, true, true>(block, smem, fa, bps)
+                        : attrs_one<M, Tab, true, false>(block, smem, fa, bps);
+    return uc ? attrs_one<M, Tab, false, true>(block, smem, fa, bps)
+              : attrs_one<M, Tab, false, false>(block, smem, fa, bps);
+}
+
+template <class M>
+static cudaError_t attrs_model(int method, bool grad, bool uc, int block, size_t smem, cudaFuncAttributes* fa,
+                               int* bps) {
+    if (method == DYNOED_RK4) return attrs_tab<M, TabRK4>(grad, uc, block, smem, fa, bps);
+    return attrs_tab<M, TabTsit5>(grad, uc, block, smem, fa, bps);
 }
 
 template <class M>
@@ -131,6 +145,7 @@ struct dynoed_ctx {
     int criterion = 0;
     int n_intervals = 0, n_steps = 0, n_var = 0, tile = 128;
     int sm_count = 0;
+    bool ucoef = false;    // step coefficients served from the constant bank (uniform registers)
     int bps[2] = {0, 0};   // blocks per SM without / with gradient
     size_t smem_floor = 0; // dynamic shared memory padding that caps the resident CTAs per SM
     cudaFuncAttributes fa[2];
@@ -298,6 +313,21 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
         first[N] = (int)st.size();
     }
     ctx->n_steps = (int)st.size();
+    // uniform-coefficient path: uniform substeps, N <= 256 and at most kMaxCoefSets distinct h
+    std::vector<double> hsets;
+    std::vector<unsigned char> iset(kMaxUIntervals, 0);
+    bool ucoef = d->substeps > 0 && N <= kMaxUIntervals && !getenv("DYNOED_NO_UCOEF");
+    for (int j = 0; ucoef && j < N; ++j) {
+        const double h = sh[first[j]];
+        size_t k = 0;
+        while (k < hsets.size() && memcmp(&hsets[k], &h, sizeof(double)) != 0) ++k;
+        if (k == hsets.size()) {
+            if ((int)hsets.size() == kMaxCoefSets) { ucoef = false; break; }
+            hsets.push_back(h);
+        }
+        iset[j] = (unsigned char)k;
+    }
+    ctx->ucoef = ucoef;
 
     auto bail = [&](int code, const std::string& msg) { dynoed_destroy(ctx); return fail(nullptr, code, msg); };
 #define CUC(call)                                                                                  \
@@ -342,6 +372,13 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     for (int k = 0; k < mi.n_theta; ++k) P.theta[k] = d->theta ? d->theta[k] : mi.theta[k];
     for (int k = 0; k < mi.nx; ++k) P.x0[k] = d->x0 ? d->x0[k] : mi.x0[k];
     for (int k = 0; k < mi.nx * mi.np; ++k) P.G0[k] = d->G0 ? d->G0[k] : mi.G0[k];
+    if (ctx->ucoef) {
+        memcpy(P.iset, iset.data(), kMaxUIntervals);
+        for (size_t k = 0; k < hsets.size(); ++k) {
+            if (d->method == DYNOED_RK4) fill_coef<TabRK4>(hsets[k], P.coef + k * kCoefStride);
+            else fill_coef<TabTsit5>(hsets[k], P.coef + k * kCoefStride);
+        }
+    }
 
     if (const char* cap = getenv("DYNOED_MAX_CTAS_PER_SM")) {   // tuning knob (occupancy experiments)
         const int k = atoi(cap);
@@ -352,7 +389,7 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     if (smem > (size_t)prop.sharedMemPerBlockOptin)
         return bail(DYNOED_EINVAL, "tile * n_var does not fit in shared memory; use a smaller tile");
     for (int g = 0; g < 2; ++g) {
-        CUC(m->attrs(ctx->method, g == 1, tile, smem, &ctx->fa[g], &ctx->bps[g]));
+        CUC(m->attrs(ctx->method, g == 1, ctx->ucoef, tile, smem, &ctx->fa[g], &ctx->bps[g]));
         if (ctx->bps[g] < 1) return bail(DYNOED_ECUDA, "kernel cannot be resident with this tile size");
     }
 #undef CUC
@@ -426,7 +463,7 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
         }
         CU(cudaEventRecord(ctx->ev_k0, st));
     }
-    CU(ctx->model->launch(ctx->method, grad != nullptr, P, grid, ctx->tile, smem_bytes(ctx), st));
+    CU(ctx->model->launch(ctx->method, grad != nullptr, ctx->ucoef, P, grid, ctx->tile, smem_bytes(ctx), st));
     if (ctx->profiling) { CU(cudaEventRecord(ctx->ev_k1, st)); ctx->ev_pending = true; }
     ctx->launches++;
     return DYNOED_OK;
@@ -525,7 +562,7 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         part_base += grid;
         P.use_tma = (((size_t)ctx->tile * ctx->n_var * 8) % 16 == 0) ? 1 : 0;
         P.index_base = off;
-        CU(ctx->model->launch(ctx->method, g, P, grid, ctx->tile, smem_bytes(ctx), s.stream));
+        CU(ctx->model->launch(ctx->method, g, ctx->ucoef, P, grid, ctx->tile, smem_bytes(ctx), s.stream));
         ctx->launches++;
         CU(cudaMemcpyAsync(crit + off, s.d_crit, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s.stream));
         if (g) CU(cudaMemcpyAsync(grad + off * ctx->n_var, s.d_grad, sizeof(double) * cnt * ctx->n_var,

@@ -29,6 +29,18 @@ constexpr int kMaxTheta = 48;
 constexpr int kMaxX = 8;
 constexpr int kMaxG = 64;
 constexpr int kMaxTile = 128;
+// Uniform step coefficients: per distinct step size h one row [h, h*b_s, h*a_sj, h*a_js*b_j/b_s]
+// lives in the kernel-parameter constant bank, so that the Runge-Kutta combinations read them as
+// uniform-register operands (a DFMA with three distinct vector-register sources issues at 64% of
+// the FP64 rate on sm_100a; register*uniform+register issues at full rate — see DESIGN.md).
+constexpr int kCoefS = 6;                                   // max stages
+constexpr int kCoefStride = 1 + kCoefS + 2 * kCoefS * kCoefS;   // 79
+constexpr int kMaxCoefSets = 8;
+constexpr int kMaxUIntervals = 256;
+__host__ __device__ constexpr int coef_h() { return 0; }
+__host__ __device__ constexpr int coef_hb(int s) { return 1 + s; }
+__host__ __device__ constexpr int coef_ha(int s, int j) { return 1 + kCoefS + s * kCoefS + j; }
+__host__ __device__ constexpr int coef_hr(int j, int s) { return 1 + kCoefS + kCoefS * kCoefS + j * kCoefS + s; }
 
 enum Criterion : int { kFisherA = 0, kFisherD = 1, kFisherE = 2, kA = 3, kD = 4, kE = 5 };
 
@@ -73,7 +85,26 @@ struct EvalParams {
     unsigned int* __restrict__ ticket;
     double* __restrict__ best_val;
     long long* __restrict__ best_idx;
+    // uniform step coefficients (UCOEF kernels): row index per merged interval + the rows
+    unsigned char iset[kMaxUIntervals];
+    double coef[kMaxCoefSets * kCoefStride];
 };
+
+// fills one coefficient row; the SAME arithmetic runs on the host (dynoed_create) and, for grids
+// that do not qualify for the uniform path, per step on the device
+template <class Tab>
+__host__ __device__ __forceinline__ void fill_coef(double h, double* cf) {
+    cf[coef_h()] = h;
+#pragma unroll
+    for (int s = 0; s < Tab::S; ++s) {
+        cf[coef_hb(s)] = h * Tab::b(s);
+#pragma unroll
+        for (int j = 0; j < Tab::S; ++j) {
+            cf[coef_ha(s, j)] = (j < s && Tab::a(s, j) != 0.0) ? h * Tab::a(s, j) : 0.0;
+            cf[coef_hr(j, s)] = (j > s && Tab::a(j, s) != 0.0) ? h * (Tab::a(j, s) * Tab::b(j) / Tab::b(s)) : 0.0;
+        }
+    }
+}
 
 // ----------------------------------------------------------------------------------------------
 // Explicit RK tableaus.  Coefficients are returned by constexpr functions so that fully unrolled
@@ -359,9 +390,9 @@ __device__ __forceinline__ void criterion_eval(const double (&F)[N * (N + 1) / 2
 // One explicit RK step of the augmented system (forward) and its discrete adjoint (backward)
 // ----------------------------------------------------------------------------------------------
 template <class M, class Tab>
-__device__ __forceinline__ void rk_forward_step(double t, double h, double (&z)[M::NZ], double (&F)[M::NF],
-                                                const double* u, const double* w, const double* th,
-                                                const double* c) {
+__device__ __forceinline__ void rk_forward_step(double t, const double* __restrict__ cf, double (&z)[M::NZ],
+                                                double (&F)[M::NF], const double* u, const double* w,
+                                                const double* th, const double* c) {
     constexpr int S = Tab::S, NZ = M::NZ, NF = M::NF;
     double k[S][NZ];
     double zacc[NZ];
@@ -375,14 +406,14 @@ __device__ __forceinline__ void rk_forward_step(double t, double h, double (&z)[
 #pragma unroll
         for (int j = 0; j < s; ++j) {
             if (Tab::a(s, j) != 0.0) {
-                const double ha = h * Tab::a(s, j);
+                const double ha = cf[coef_ha(s, j)];
 #pragma unroll
                 for (int a = 0; a < NZ; ++a) Z[a] = fma(ha, k[j][a], Z[a]);
             }
         }
         double dF[NF];
-        M::primal(t + Tab::c(s) * h, Z, u, w, th, c, k[s], dF);
-        const double hb = h * Tab::b(s);
+        M::primal(t + Tab::c(s) * cf[coef_h()], Z, u, w, th, c, k[s], dF);
+        const double hb = cf[coef_hb(s)];
 #pragma unroll
         for (int a = 0; a < NZ; ++a) zacc[a] = fma(hb, k[s][a], zacc[a]);
 #pragma unroll
@@ -398,12 +429,13 @@ __device__ __forceinline__ void rk_forward_step(double t, double h, double (&z)[
 //   kb'_s = lam + sum_{j>s} (h a_js b_j / b_s) zb'_j ,   zb'_s = g_z(Z_s)^T kb'_s + q_z(Z_s) ,
 //   lam_n = lam + sum_s h b_s zb'_s ,  ub += h b_s g_u^T kb'_s ,  wb_i += h b_s q_i(Z_s).
 template <class M, class Tab>
-__device__ __forceinline__ void rk_adjoint_step(double t, double h, const double (&zn)[M::NZ],
+__device__ __forceinline__ void rk_adjoint_step(double t, const double* __restrict__ cf, const double (&zn)[M::NZ],
                                                 double (&lam)[M::NZ], const double* u, const double* cw,
                                                 const double* th, const double* c, const double* L,
                                                 double* ub, double* wb) {
     constexpr int S = Tab::S, NZ = M::NZ;
     constexpr int NCU = M::NCTRL > 0 ? M::NCTRL : 1;
+    const double h = cf[coef_h()];
     double Z[S][NZ];
     {   // recompute the stage states
         double k[S][NZ];
@@ -414,7 +446,7 @@ __device__ __forceinline__ void rk_adjoint_step(double t, double h, const double
 #pragma unroll
             for (int j = 0; j < s; ++j) {
                 if (Tab::a(s, j) != 0.0) {
-                    const double ha = h * Tab::a(s, j);
+                    const double ha = cf[coef_ha(s, j)];
 #pragma unroll
                     for (int a = 0; a < NZ; ++a) Z[s][a] = fma(ha, k[j][a], Z[s][a]);
                 }
@@ -429,14 +461,14 @@ __device__ __forceinline__ void rk_adjoint_step(double t, double h, const double
 #pragma unroll
     for (int s = S - 1; s >= 0; --s) {
         static_assert(Tab::b(0) != 0.0, "unscaled stage adjoints need b_s != 0");
-        const double hb = h * Tab::b(s);
+        const double hb = cf[coef_hb(s)];
         double kb[NZ];
 #pragma unroll
         for (int a = 0; a < NZ; ++a) kb[a] = lam[a];
 #pragma unroll
         for (int j = s + 1; j < S; ++j) {
             if (Tab::a(j, s) != 0.0) {
-                const double r = h * (Tab::a(j, s) * Tab::b(j) / Tab::b(s));
+                const double r = cf[coef_hr(j, s)];
 #pragma unroll
                 for (int a = 0; a < NZ; ++a) kb[a] = fma(r, Zb[j][a], kb[a]);
             }
@@ -457,7 +489,7 @@ __device__ __forceinline__ void rk_adjoint_step(double t, double h, const double
 // ----------------------------------------------------------------------------------------------
 // The evaluation kernel
 // ----------------------------------------------------------------------------------------------
-template <class M, class Tab, bool GRAD>
+template <class M, class Tab, bool GRAD, bool UCOEF>
 __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) {
     constexpr int NX = M::NX, NP = M::NP, NZ = M::NZ, NF = M::NF, NOBS = M::NOBS, NCTRL = M::NCTRL;
     constexpr int NCU = NCTRL > 0 ? NCTRL : 1;
@@ -528,12 +560,19 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
                 for (int i = 0; i < NOBS; ++i) w[i] = row[P.w_off[i] + __ldg(P.indicators + (NCTRL + i) * N + j)];
                 M::consts(u, th, c);
                 const int s0 = __ldg(P.first_step + j), s1 = __ldg(P.first_step + j + 1);
+                const double* cfu = P.coef + (UCOEF ? (int)P.iset[j] * kCoefStride : 0);
                 for (int s = s0; s < s1; ++s) {
                     if (GRAD) {
 #pragma unroll
                         for (int a = 0; a < NZ; ++a) tr[((size_t)s * NZ + a) * TILE] = z[a];
                     }
-                    rk_forward_step<M, Tab>(__ldg(P.step_t + s), __ldg(P.step_h + s), z, F, u, w, th, c);
+                    if (UCOEF) {
+                        rk_forward_step<M, Tab>(__ldg(P.step_t + s), cfu, z, F, u, w, th, c);
+                    } else {
+                        double cfl[kCoefStride];
+                        fill_coef<Tab>(__ldg(P.step_h + s), cfl);
+                        rk_forward_step<M, Tab>(__ldg(P.step_t + s), cfl, z, F, u, w, th, c);
+                    }
                 }
                 if (xg) {
                     double* o = xg + (size_t)(j + 1) * (NZ + NF);
@@ -596,6 +635,7 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
                     }
                     M::consts(u, th, c);
                     const int s0 = __ldg(P.first_step + j), s1 = __ldg(P.first_step + j + 1);
+                    const double* cfu = P.coef + (UCOEF ? (int)P.iset[j] * kCoefStride : 0);
                     for (int s = s1 - 1; s >= s0; --s) {
                         double znext[NZ];
                         const int sp = s > 0 ? s - 1 : 0;
@@ -606,7 +646,13 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
 #pragma unroll
                             for (int a = 0; a < NZ; ++a) prefetch_l2(tr + ((size_t)(s - 3) * NZ + a) * TILE);
                         }
-                        rk_adjoint_step<M, Tab>(tcur, hcur, zn, lam, u, cw, th, c, L, ub, wb);
+                        if (UCOEF) {
+                            rk_adjoint_step<M, Tab>(tcur, cfu, zn, lam, u, cw, th, c, L, ub, wb);
+                        } else {
+                            double cfl[kCoefStride];
+                            fill_coef<Tab>(hcur, cfl);
+                            rk_adjoint_step<M, Tab>(tcur, cfl, zn, lam, u, cw, th, c, L, ub, wb);
+                        }
 #pragma unroll
                         for (int a = 0; a < NZ; ++a) zn[a] = znext[a];
                         tcur = tnext; hcur = hnext;
