@@ -226,7 +226,7 @@ static int ensure_partials(dynoed_ctx* ctx, int need) {
 }
 
 static size_t traj_bytes_for(const dynoed_ctx* ctx, int grid) {
-    return (size_t)grid * ctx->n_steps * ctx->model->info.nz * ctx->tile * sizeof(double);
+    return (size_t)grid * ctx->n_steps * ctx->model->info.nz * kMaxTile * sizeof(double);
 }
 
 static size_t smem_bytes(const dynoed_ctx* ctx) {
@@ -287,17 +287,30 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     ctx->n_var = d->n_var;
     ctx->tile = tile;
 
-    // step tables: t and h per step, same arithmetic as the oracle (h = L/m, t = t0 + s*h for
-    // uniform substeps; t = t0 + e_s*L, h = (t0 + e_{s+1}*L) - t for explicit edges)
+    // step tables: t and h per step, same arithmetic as the oracle.  Uniform substeps: h = L/m per
+    // merged interval — unless the merged grid is uniform up to rounding (all L_j/m within 64 ulp
+    // of hbar = (t_N - t_0)/(N m)); then every step uses the single constant dt = hbar, as a
+    // fixed-dt integrator run would (grid points such as k/10 are rounded decimals, and their
+    // differences scatter over a few ulp).  Explicit edges: t = t0 + e_s*L, h = (t0 + e_{s+1}*L) - t.
     std::vector<int> first(N + 1, 0);
     std::vector<double> st, sh;
+    bool single_h = false;
     {
+        double hbar = 0.0;
+        if (d->substeps > 0) {
+            hbar = (d->tgrid[N] - d->tgrid[0]) / ((double)N * d->substeps);
+            single_h = true;
+            for (int j = 0; j < N; ++j) {
+                const double h = (d->tgrid[j + 1] - d->tgrid[j]) / d->substeps;
+                if (!(std::fabs(h - hbar) <= 64.0 * 2.220446049250313e-16 * hbar)) { single_h = false; break; }
+            }
+        }
         size_t eoff = 0;
         for (int j = 0; j < N; ++j) {
             const double t0 = d->tgrid[j], L = d->tgrid[j + 1] - d->tgrid[j];
             first[j] = (int)st.size();
             if (d->substeps > 0) {
-                const double h = L / d->substeps;
+                const double h = single_h ? hbar : L / d->substeps;
                 for (int s = 0; s < d->substeps; ++s) { st.push_back(t0 + s * h); sh.push_back(h); }
             } else {
                 const int ne = d->edge_count[j];
@@ -313,21 +326,9 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
         first[N] = (int)st.size();
     }
     ctx->n_steps = (int)st.size();
-    // uniform-coefficient path: uniform substeps, N <= 256 and at most kMaxCoefSets distinct h
-    std::vector<double> hsets;
-    std::vector<unsigned char> iset(kMaxUIntervals, 0);
-    bool ucoef = d->substeps > 0 && N <= kMaxUIntervals && !getenv("DYNOED_NO_UCOEF");
-    for (int j = 0; ucoef && j < N; ++j) {
-        const double h = sh[first[j]];
-        size_t k = 0;
-        while (k < hsets.size() && memcmp(&hsets[k], &h, sizeof(double)) != 0) ++k;
-        if (k == hsets.size()) {
-            if ((int)hsets.size() == kMaxCoefSets) { ucoef = false; break; }
-            hsets.push_back(h);
-        }
-        iset[j] = (unsigned char)k;
-    }
-    ctx->ucoef = ucoef;
+    // one step size for the whole grid => the Runge-Kutta factors h*a, h*b are kernel-parameter
+    // constants with compile-time addresses (constant-bank operands of the DFMAs)
+    ctx->ucoef = single_h && !getenv("DYNOED_NO_UCOEF");
 
     auto bail = [&](int code, const std::string& msg) { dynoed_destroy(ctx); return fail(nullptr, code, msg); };
 #define CUC(call)                                                                                  \
@@ -373,11 +374,8 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     for (int k = 0; k < mi.nx; ++k) P.x0[k] = d->x0 ? d->x0[k] : mi.x0[k];
     for (int k = 0; k < mi.nx * mi.np; ++k) P.G0[k] = d->G0 ? d->G0[k] : mi.G0[k];
     if (ctx->ucoef) {
-        memcpy(P.iset, iset.data(), kMaxUIntervals);
-        for (size_t k = 0; k < hsets.size(); ++k) {
-            if (d->method == DYNOED_RK4) fill_coef<TabRK4>(hsets[k], P.coef + k * kCoefStride);
-            else fill_coef<TabTsit5>(hsets[k], P.coef + k * kCoefStride);
-        }
+        if (d->method == DYNOED_RK4) fill_coef<TabRK4>(sh[0], P.coef);
+        else fill_coef<TabTsit5>(sh[0], P.coef);
     }
 
     if (const char* cap = getenv("DYNOED_MAX_CTAS_PER_SM")) {   // tuning knob (occupancy experiments)

@@ -29,14 +29,12 @@ constexpr int kMaxTheta = 48;
 constexpr int kMaxX = 8;
 constexpr int kMaxG = 64;
 constexpr int kMaxTile = 128;
-// Uniform step coefficients: per distinct step size h one row [h, h*b_s, h*a_sj, h*a_js*b_j/b_s]
-// lives in the kernel-parameter constant bank, so that the Runge-Kutta combinations read them as
-// uniform-register operands (a DFMA with three distinct vector-register sources issues at 64% of
-// the FP64 rate on sm_100a; register*uniform+register issues at full rate — see DESIGN.md).
+// Step coefficients of a uniform grid: one row [h, h*b_s, h*a_sj, h*a_js*b_j/b_s] in the kernel-
+// parameter constant bank, so that the Runge-Kutta combinations read them as constant operands (a
+// DFMA with three distinct vector-register sources issues at 65% of the FP64 rate on sm_100a;
+// register*constant+register issues at full rate — see DESIGN.md).
 constexpr int kCoefS = 6;                                   // max stages
 constexpr int kCoefStride = 1 + kCoefS + 2 * kCoefS * kCoefS;   // 79
-constexpr int kMaxCoefSets = 8;
-constexpr int kMaxUIntervals = 256;
 __host__ __device__ constexpr int coef_h() { return 0; }
 __host__ __device__ constexpr int coef_hb(int s) { return 1 + s; }
 __host__ __device__ constexpr int coef_ha(int s, int j) { return 1 + kCoefS + s * kCoefS + j; }
@@ -85,9 +83,8 @@ struct EvalParams {
     unsigned int* __restrict__ ticket;
     double* __restrict__ best_val;
     long long* __restrict__ best_idx;
-    // uniform step coefficients (UCOEF kernels): row index per merged interval + the rows
-    unsigned char iset[kMaxUIntervals];
-    double coef[kMaxCoefSets * kCoefStride];
+    // Runge-Kutta factors of the single step size of a uniform grid (UCOEF kernels)
+    double coef[kCoefStride];
 };
 
 // fills one coefficient row; the SAME arithmetic runs on the host (dynoed_create) and, for grids
@@ -487,6 +484,65 @@ __device__ __forceinline__ void rk_adjoint_step(double t, const double* __restri
 }
 
 // ----------------------------------------------------------------------------------------------
+// The substeps of one merged interval.  UC: the grid has ONE step size and the Runge-Kutta factors
+// h*a, h*b are read from EvalParams::coef at compile-time addresses (constant-bank operands: a
+// DFMA with three vector-register sources issues at 2/3 rate on sm_100a, register * constant +
+// register at full rate); otherwise they are computed per step from step_h.
+// ----------------------------------------------------------------------------------------------
+template <class M, class Tab, bool GRAD, bool UC>
+__device__ __forceinline__ void forward_interval(const EvalParams& P, int s0, int s1, double* __restrict__ tr,
+                                                 double (&z)[M::NZ], double (&F)[M::NF], const double* u,
+                                                 const double* w, const double* th, const double* c) {
+    constexpr int NZ = M::NZ;
+    for (int s = s0; s < s1; ++s) {
+        if (GRAD) {
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) tr[((size_t)s * NZ + a) * kMaxTile] = z[a];
+        }
+        if (UC) {
+            rk_forward_step<M, Tab>(__ldg(P.step_t + s), P.coef, z, F, u, w, th, c);
+        } else {
+            double cfl[kCoefStride];
+            fill_coef<Tab>(__ldg(P.step_h + s), cfl);
+            rk_forward_step<M, Tab>(__ldg(P.step_t + s), cfl, z, F, u, w, th, c);
+        }
+    }
+}
+
+// zn / tcur / hcur: (x, G) checkpoint and (t, h) of the step about to be processed.  The next
+// step's are requested at the top of the current step, and the checkpoint three steps ahead is
+// pulled from HBM into L2, so that neither latency is exposed.
+template <class M, class Tab, bool UC>
+__device__ __forceinline__ void backward_interval(const EvalParams& P, int s0, int s1, const double* __restrict__ tr,
+                                                  double (&zn)[M::NZ], double& tcur, double& hcur,
+                                                  double (&lam)[M::NZ], const double* u, const double* cw,
+                                                  const double* th, const double* c, const double* L,
+                                                  double* ub, double* wb) {
+    constexpr int NZ = M::NZ;
+    for (int s = s1 - 1; s >= s0; --s) {
+        double znext[NZ];
+        const int sp = s > 0 ? s - 1 : 0;
+#pragma unroll
+        for (int a = 0; a < NZ; ++a) znext[a] = ld_pinned(tr + ((size_t)sp * NZ + a) * kMaxTile);
+        const double tnext = __ldg(P.step_t + sp), hnext = __ldg(P.step_h + sp);
+        if (s >= 3) {
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) prefetch_l2(tr + ((size_t)(s - 3) * NZ + a) * kMaxTile);
+        }
+        if (UC) {
+            rk_adjoint_step<M, Tab>(tcur, P.coef, zn, lam, u, cw, th, c, L, ub, wb);
+        } else {
+            double cfl[kCoefStride];
+            fill_coef<Tab>(hcur, cfl);
+            rk_adjoint_step<M, Tab>(tcur, cfl, zn, lam, u, cw, th, c, L, ub, wb);
+        }
+#pragma unroll
+        for (int a = 0; a < NZ; ++a) zn[a] = znext[a];
+        tcur = tnext; hcur = hnext;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
 // The evaluation kernel
 // ----------------------------------------------------------------------------------------------
 template <class M, class Tab, bool GRAD, bool UCOEF>
@@ -530,7 +586,11 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
             __syncthreads();
         }
 
-        if (tid < count) {
+        // All lanes of the CTA run the sweeps (lanes past `count` integrate whatever their shared-
+        // memory row holds and store nothing): the interval/step loops stay warp-uniform, so loop
+        // counters, table reads and the Runge-Kutta coefficient row live in uniform registers.
+        const bool active = tid < count;
+        {
             double* row = tile_buf + (size_t)tid * n_var;
             const long long g = g0 + tid;
             double z[NZ], F[NF];
@@ -542,8 +602,8 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
             for (int a = 0; a < M::NIC; ++a) z[M::ic_state(a)] = row[P.ic_off + a];
 #pragma unroll
             for (int a = 0; a < NF; ++a) F[a] = 0.0;
-            double* tr = P.traj + ((size_t)blockIdx.x * P.n_steps * NZ) * TILE + tid;
-            double* xg = P.xgrid ? P.xgrid + (size_t)g * (N + 1) * (NZ + NF) : nullptr;
+            double* tr = P.traj + ((size_t)blockIdx.x * P.n_steps * NZ) * kMaxTile + tid;
+            double* xg = (P.xgrid && active) ? P.xgrid + (size_t)g * (N + 1) * (NZ + NF) : nullptr;
             if (xg) {
 #pragma unroll
                 for (int a = 0; a < NZ; ++a) xg[a] = z[a];
@@ -560,20 +620,9 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
                 for (int i = 0; i < NOBS; ++i) w[i] = row[P.w_off[i] + __ldg(P.indicators + (NCTRL + i) * N + j)];
                 M::consts(u, th, c);
                 const int s0 = __ldg(P.first_step + j), s1 = __ldg(P.first_step + j + 1);
-                const double* cfu = P.coef + (UCOEF ? (int)P.iset[j] * kCoefStride : 0);
-                for (int s = s0; s < s1; ++s) {
-                    if (GRAD) {
-#pragma unroll
-                        for (int a = 0; a < NZ; ++a) tr[((size_t)s * NZ + a) * TILE] = z[a];
-                    }
-                    if (UCOEF) {
-                        rk_forward_step<M, Tab>(__ldg(P.step_t + s), cfu, z, F, u, w, th, c);
-                    } else {
-                        double cfl[kCoefStride];
-                        fill_coef<Tab>(__ldg(P.step_h + s), cfl);
-                        rk_forward_step<M, Tab>(__ldg(P.step_t + s), cfl, z, F, u, w, th, c);
-                    }
-                }
+                // one instantiation per coefficient row: the row offset is then a compile-time
+                // constant and every h*a / h*b factor is a constant-bank operand of its DFMA
+                forward_interval<M, Tab, GRAD, UCOEF>(P, s0, s1, tr, z, F, u, w, th, c);
                 if (xg) {
                     double* o = xg + (size_t)(j + 1) * (NZ + NF);
 #pragma unroll
@@ -588,12 +637,12 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
             double value, L[NF];
             criterion_eval<NP>(F, tau, P.criterion, value, L);
             const double obj = value + tau;
-            P.crit[g] = obj;
-            if (P.fim) {
+            if (active) P.crit[g] = obj;
+            if (P.fim && active) {
 #pragma unroll
                 for (int a = 0; a < NF; ++a) P.fim[g * NF + a] = F[a];
             }
-            if (obj < best_val) { best_val = obj; best_idx = P.index_base + g; }   // NaN never wins
+            if (active && obj < best_val) { best_val = obj; best_idx = P.index_base + g; }   // NaN never wins
 
             // ---------------- backward (discrete adjoint) sweep ----------------
             if (GRAD) {
@@ -611,7 +660,7 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
                 // steps ahead is pulled from HBM into L2, so that neither latency is exposed.
                 double zn[NZ];
 #pragma unroll
-                for (int a = 0; a < NZ; ++a) zn[a] = tr[((size_t)(P.n_steps - 1) * NZ + a) * TILE];
+                for (int a = 0; a < NZ; ++a) zn[a] = tr[((size_t)(P.n_steps - 1) * NZ + a) * kMaxTile];
                 double tcur = __ldg(P.step_t + P.n_steps - 1), hcur = __ldg(P.step_h + P.n_steps - 1);
                 for (int j = N - 1; j >= 0; --j) {
                     double u[NCU], cw[NOBS], c[M::NCONST];
@@ -635,28 +684,7 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
                     }
                     M::consts(u, th, c);
                     const int s0 = __ldg(P.first_step + j), s1 = __ldg(P.first_step + j + 1);
-                    const double* cfu = P.coef + (UCOEF ? (int)P.iset[j] * kCoefStride : 0);
-                    for (int s = s1 - 1; s >= s0; --s) {
-                        double znext[NZ];
-                        const int sp = s > 0 ? s - 1 : 0;
-#pragma unroll
-                        for (int a = 0; a < NZ; ++a) znext[a] = ld_pinned(tr + ((size_t)sp * NZ + a) * TILE);
-                        const double tnext = __ldg(P.step_t + sp), hnext = __ldg(P.step_h + sp);
-                        if (s >= 3) {
-#pragma unroll
-                            for (int a = 0; a < NZ; ++a) prefetch_l2(tr + ((size_t)(s - 3) * NZ + a) * TILE);
-                        }
-                        if (UCOEF) {
-                            rk_adjoint_step<M, Tab>(tcur, cfu, zn, lam, u, cw, th, c, L, ub, wb);
-                        } else {
-                            double cfl[kCoefStride];
-                            fill_coef<Tab>(hcur, cfl);
-                            rk_adjoint_step<M, Tab>(tcur, cfl, zn, lam, u, cw, th, c, L, ub, wb);
-                        }
-#pragma unroll
-                        for (int a = 0; a < NZ; ++a) zn[a] = znext[a];
-                        tcur = tnext; hcur = hnext;
-                    }
+                    backward_interval<M, Tab, UCOEF>(P, s0, s1, tr, zn, tcur, hcur, lam, u, cw, th, c, L, ub, wb);
                 }
 #pragma unroll
                 for (int k = 0; k < NCTRL; ++k)

@@ -49,14 +49,31 @@ def lib():
     return _lib
 
 
+def uniform_step(tgrid, substeps):
+    """The single step size of a grid that is uniform up to rounding, else None.
+
+    Grid points such as k/10 are rounded decimals, so L_j/m scatters over a few ulp; a fixed-dt
+    integrator run (`solve(...; adaptive=false, dt=dt)`) steps with ONE dt.  Rule (shared with
+    dynoed_create): hbar = (t_N - t_0)/(N m); if every L_j/m is within 64 ulp of hbar, all steps
+    use hbar."""
+    N = len(tgrid) - 1
+    hbar = (float(tgrid[N]) - float(tgrid[0])) / (float(N) * substeps)
+    for j in range(N):
+        h = (float(tgrid[j + 1]) - float(tgrid[j])) / substeps
+        if not abs(h - hbar) <= 64.0 * 2.220446049250313e-16 * hbar:
+            return None
+    return hbar
+
+
 def step_table(tgrid, substeps=None, edges=None):
     """(first_step[N+1], step_t, step_h) with the arithmetic the GPU library uses
     (dynamicoed.jl_b200/csrc/dynoed_api.cu, dynoed_create)."""
     first, st, sh = [0], [], []
+    hbar = uniform_step(tgrid, substeps) if edges is None else None
     for j in range(len(tgrid) - 1):
         t0, L = float(tgrid[j]), float(tgrid[j + 1]) - float(tgrid[j])
         if edges is None:
-            h = L / substeps
+            h = hbar if hbar is not None else L / substeps
             for s in range(substeps):
                 st.append(t0 + s * h)
                 sh.append(h)

@@ -468,6 +468,10 @@ class Oracle:
         tab = tableau(self.method) if self.method in ("rk4", "tsit5") else None
         nc = len(self.controls)
         traj = [list(z)] if save else None
+        hbar = None
+        if self.uniform is not None:        # single dt on a grid that is uniform up to rounding
+            from .cpp_oracle import uniform_step
+            hbar = uniform_step(self.grid.tpoints, self.uniform)
         for j, (t0, t1) in enumerate(self.grid.timespans):
             u = [col[lay.control_offsets[c] + int(self.grid.indicators[c, j]) - 1]
                  for c in range(nc)]
@@ -477,7 +481,7 @@ class Oracle:
             L = t1 - t0
             for s in range(len(e) - 1):
                 if self.uniform is not None:
-                    h = L / self.uniform
+                    h = hbar if hbar is not None else L / self.uniform
                     ts = t0 + s * h
                 else:
                     ts = t0 + e[s] * L
