@@ -28,19 +28,24 @@ static thread_local std::string g_last_error;
 struct ModelEntry {
     const char* name;
     dynoed_model_info info;
-    cudaError_t (*launch)(int method, bool grad, bool ucoef, const EvalParams& P, int grid, int block, size_t smem,
-                          cudaStream_t st);
+    cudaError_t (*launch)(int method, bool grad, bool ucoef, bool pdl, const EvalParams& P, int grid, int block,
+                          size_t smem, cudaStream_t st);
     cudaError_t (*attrs)(int method, bool grad, bool ucoef, int block, size_t smem, cudaFuncAttributes* fa,
                          int* blocks_per_sm);
 };
 
 template <class M, class Tab, bool GRAD, bool UC>
-static cudaError_t launch_one(const EvalParams& P, int grid, int block, size_t smem, cudaStream_t st) {
+static cudaError_t launch_one(bool pdl, const EvalParams& P, int grid, int block, size_t smem, cudaStream_t st) {
     auto kern = oed_eval_kernel<M, Tab, GRAD, UC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, block, smem, st>>>(P);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, P);
 }
 
 template <class M, class Tab, bool GRAD, bool UC>
@@ -54,19 +59,19 @@ static cudaError_t attrs_one(int block, size_t smem, cudaFuncAttributes* fa, int
 }
 
 template <class M, class Tab>
-static cudaError_t launch_tab(bool grad, bool uc, const EvalParams& P, int grid, int block, size_t smem,
+static cudaError_t launch_tab(bool grad, bool uc, bool pdl, const EvalParams& P, int grid, int block, size_t smem,
                               cudaStream_t st) {
-    if (grad) return uc ? launch_one<M, Tab, true, true>(P, grid, block, smem, st)
-                        : launch_one<M, Tab, true, false>(P, grid, block, smem, st);
-    return uc ? launch_one<M, Tab, false, true>(P, grid, block, smem, st)
-              : launch_one<M, Tab, false, false>(P, grid, block, smem, st);
+    if (grad) return uc ? launch_one<M, Tab, true, true>(pdl, P, grid, block, smem, st)
+                        : launch_one<M, Tab, true, false>(pdl, P, grid, block, smem, st);
+    return uc ? launch_one<M, Tab, false, true>(pdl, P, grid, block, smem, st)
+              : launch_one<M, Tab, false, false>(pdl, P, grid, block, smem, st);
 }
 
 template <class M>
-static cudaError_t launch_model(int method, bool grad, bool uc, const EvalParams& P, int grid, int block,
+static cudaError_t launch_model(int method, bool grad, bool uc, bool pdl, const EvalParams& P, int grid, int block,
                                 size_t smem, cudaStream_t st) {
-    if (method == DYNOED_RK4) return launch_tab<M, TabRK4>(grad, uc, P, grid, block, smem, st);
-    return launch_tab<M, TabTsit5>(grad, uc, P, grid, block, smem, st);
+    if (method == DYNOED_RK4) return launch_tab<M, TabRK4>(grad, uc, pdl, P, grid, block, smem, st);
+    return launch_tab<M, TabTsit5>(grad, uc, pdl, P, grid, block, smem, st);
 }
 
 template <class M, class Tab>
@@ -156,19 +161,31 @@ struct dynoed_ctx {
     int* d_indicators = nullptr;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
-    // device-pointer path scratch
-    double* traj = nullptr;
-    size_t traj_bytes = 0;
-    double* part_val = nullptr;
-    long long* part_idx = nullptr;
-    int part_cap = 0;
-    int part_used = 0;
-    double* d_best_val = nullptr;
-    long long* d_best_idx = nullptr;
-    unsigned int* d_ticket = nullptr;
+    // device-pointer path scratch, double-buffered by launch parity: consecutive device-path
+    // launches may overlap (programmatic dependent launch), so launch k and k+1 never share
+    // checkpoint scratch, arg-min records, ticket or result slot
+    double* traj[2] = {nullptr, nullptr};
+    size_t traj_bytes[2] = {0, 0};
+    double* part_val[2] = {nullptr, nullptr};
+    long long* part_idx[2] = {nullptr, nullptr};
+    int part_cap[2] = {0, 0};
+    double* d_best_val = nullptr;      // [2]
+    long long* d_best_idx = nullptr;   // [2]
+    unsigned int* d_ticket = nullptr;  // [2]
+    int parity = 0;                    // scratch set of the NEXT device-path launch
+    int last_parity = 0;               // scratch set that holds the most recent batch's arg-min
+    struct Prev {                      // the previous device-path launch (overlap eligibility)
+        bool valid = false, grad = false, full = false;
+        cudaStream_t stream = nullptr;
+        const char *in0 = nullptr, *in1 = nullptr;
+        const char* out0[3] = {nullptr, nullptr, nullptr};
+        const char* out1[3] = {nullptr, nullptr, nullptr};
+    } prev;
+    bool pdl_enabled = true;
     bool have_batch = false;
     Slot slots[kSlots];
     int64_t launches = 0;
+    int64_t pdl_launches = 0;
     size_t scratch_bytes = 0;
     // optional per-launch timing of the evaluation kernel (device-pointer path)
     bool profiling = false;
@@ -213,15 +230,16 @@ const char* dynoed_last_error(const dynoed_ctx* ctx) {
     return g_last_error.c_str();
 }
 
-static int ensure_partials(dynoed_ctx* ctx, int need) {
-    if (need <= ctx->part_cap) return DYNOED_OK;
-    if (ctx->part_val) cudaFree(ctx->part_val);
-    if (ctx->part_idx) cudaFree(ctx->part_idx);
-    ctx->part_val = nullptr; ctx->part_idx = nullptr;
+static int ensure_partials(dynoed_ctx* ctx, int need, int par) {
+    if (need <= ctx->part_cap[par]) return DYNOED_OK;
+    CU(cudaDeviceSynchronize());
+    if (ctx->part_val[par]) cudaFree(ctx->part_val[par]);
+    if (ctx->part_idx[par]) cudaFree(ctx->part_idx[par]);
+    ctx->part_val[par] = nullptr; ctx->part_idx[par] = nullptr;
     int cap = std::max(need, 4096);
-    CU(cudaMalloc(&ctx->part_val, sizeof(double) * cap));
-    CU(cudaMalloc(&ctx->part_idx, sizeof(long long) * cap));
-    ctx->part_cap = cap;
+    CU(cudaMalloc(&ctx->part_val[par], sizeof(double) * cap));
+    CU(cudaMalloc(&ctx->part_idx[par], sizeof(long long) * cap));
+    ctx->part_cap[par] = cap;
     return DYNOED_OK;
 }
 
@@ -350,10 +368,11 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     CUC(cudaMemcpy(ctx->d_step_t, st.data(), sizeof(double) * st.size(), cudaMemcpyHostToDevice));
     CUC(cudaMemcpy(ctx->d_step_h, sh.data(), sizeof(double) * st.size(), cudaMemcpyHostToDevice));
     CUC(cudaMemcpy(ctx->d_indicators, d->indicators, sizeof(int) * nvars * N, cudaMemcpyHostToDevice));
-    CUC(cudaMalloc(&ctx->d_best_val, sizeof(double)));
-    CUC(cudaMalloc(&ctx->d_best_idx, sizeof(long long)));
-    CUC(cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)));
-    CUC(cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int)));
+    CUC(cudaMalloc(&ctx->d_best_val, 2 * sizeof(double)));
+    CUC(cudaMalloc(&ctx->d_best_idx, 2 * sizeof(long long)));
+    CUC(cudaMalloc(&ctx->d_ticket, 2 * sizeof(unsigned int)));
+    CUC(cudaMemset(ctx->d_ticket, 0, 2 * sizeof(unsigned int)));
+    ctx->pdl_enabled = !getenv("DYNOED_NO_PDL");
 
     EvalParams& P = ctx->base;
     memset(&P, 0, sizeof(P));
@@ -404,7 +423,7 @@ void dynoed_destroy(dynoed_ctx* ctx) {
         cudaFree(s.d_designs); cudaFree(s.d_crit); cudaFree(s.d_grad); cudaFree(s.d_fim); cudaFree(s.traj);
     }
     cudaFree(ctx->d_first_step); cudaFree(ctx->d_step_t); cudaFree(ctx->d_step_h); cudaFree(ctx->d_indicators);
-    cudaFree(ctx->traj); cudaFree(ctx->part_val); cudaFree(ctx->part_idx);
+    for (int q = 0; q < 2; ++q) { cudaFree(ctx->traj[q]); cudaFree(ctx->part_val[q]); cudaFree(ctx->part_idx[q]); }
     cudaFree(ctx->d_best_val); cudaFree(ctx->d_best_idx); cudaFree(ctx->d_ticket);
     if (ctx->ev_k0) { cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -438,19 +457,44 @@ static int ptr_kind(const void* p) {
     return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? 1 : 0;
 }
 
+static bool ranges_overlap(const char* a0, const char* a1, const char* b0, const char* b1) {
+    return a0 && b0 && a0 < b1 && b0 < a1;
+}
+
 // launch on device-resident buffers
 static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad,
-                         double* fim, double* xgrid, double* traj, double* part_val, long long* part_idx,
-                         int grid, cudaStream_t st) {
+                         double* fim, double* xgrid, int par, int grid, cudaStream_t st) {
+    const auto& mi = ctx->model->info;
     EvalParams P = ctx->base;
     P.designs = designs; P.crit = crit; P.grad = grad; P.fim = fim; P.xgrid = xgrid;
-    P.traj = traj; P.n = n;
-    P.part_val = part_val; P.part_idx = part_idx;
+    P.traj = ctx->traj[par]; P.n = n;
+    P.part_val = ctx->part_val[par]; P.part_idx = ctx->part_idx[par];
     P.part_base = 0; P.n_parts = grid; P.ticket_target = (unsigned int)grid;
-    P.ticket = ctx->d_ticket; P.best_val = ctx->d_best_val; P.best_idx = ctx->d_best_idx;
+    P.ticket = ctx->d_ticket + par; P.best_val = ctx->d_best_val + par; P.best_idx = ctx->d_best_idx + par;
     P.use_tma = ((reinterpret_cast<uintptr_t>(designs) % 16 == 0) &&
                  (grad == nullptr || reinterpret_cast<uintptr_t>(grad) % 16 == 0) &&
                  (((size_t)ctx->tile * ctx->n_var * 8) % 16 == 0)) ? 1 : 0;
+    // May this launch start while the previous one drains?  Only if both fill the whole GPU with
+    // the same kernel (then launch k+1 cannot start before launch k-1 has left the SMs, and two
+    // scratch sets suffice), on the same stream, and their buffers are disjoint.
+    dynoed_ctx::Prev cur;
+    cur.valid = xgrid == nullptr;
+    cur.grad = grad != nullptr;
+    cur.full = grid == ctx->sm_count * std::max(ctx->bps[cur.grad ? 1 : 0], 1);
+    cur.stream = st;
+    cur.in0 = (const char*)designs; cur.in1 = cur.in0 + sizeof(double) * n * ctx->n_var;
+    cur.out0[0] = (const char*)crit; cur.out1[0] = cur.out0[0] + sizeof(double) * n;
+    cur.out0[1] = (const char*)grad; cur.out1[1] = grad ? cur.out0[1] + sizeof(double) * n * ctx->n_var : nullptr;
+    cur.out0[2] = (const char*)fim; cur.out1[2] = fim ? cur.out0[2] + sizeof(double) * n * mi.nF : nullptr;
+    const dynoed_ctx::Prev& pv = ctx->prev;
+    bool pdl = ctx->pdl_enabled && !ctx->profiling && cur.valid && pv.valid && cur.full && pv.full &&
+               cur.grad == pv.grad && cur.stream == pv.stream;
+    for (int a = 0; pdl && a < 3; ++a) {
+        if (ranges_overlap(cur.in0, cur.in1, pv.out0[a], pv.out1[a])) pdl = false;      // RAW
+        if (ranges_overlap(cur.out0[a], cur.out1[a], pv.in0, pv.in1)) pdl = false;      // WAR
+        for (int b = 0; pdl && b < 3; ++b)
+            if (ranges_overlap(cur.out0[a], cur.out1[a], pv.out0[b], pv.out1[b])) pdl = false;   // WAW
+    }
     if (ctx->profiling) {
         if (ctx->ev_pending) {   // fold the previous launch's duration into the running sum
             CU(cudaEventSynchronize(ctx->ev_k1));
@@ -461,9 +505,11 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
         }
         CU(cudaEventRecord(ctx->ev_k0, st));
     }
-    CU(ctx->model->launch(ctx->method, grad != nullptr, ctx->ucoef, P, grid, ctx->tile, smem_bytes(ctx), st));
+    CU(ctx->model->launch(ctx->method, grad != nullptr, ctx->ucoef, pdl, P, grid, ctx->tile, smem_bytes(ctx), st));
     if (ctx->profiling) { CU(cudaEventRecord(ctx->ev_k1, st)); ctx->ev_pending = true; }
+    ctx->prev = cur;
     ctx->launches++;
+    ctx->pdl_launches += pdl ? 1 : 0;
     return DYNOED_OK;
 }
 
@@ -471,22 +517,24 @@ static int eval_device(dynoed_ctx* ctx, const double* designs, int64_t n, double
                        double* xgrid) {
     const bool g = grad != nullptr;
     const int grid = grid_for(ctx, n, g);
+    const int par = ctx->parity;
     if (g) {
         const size_t need = traj_bytes_for(ctx, grid);
-        if (need > ctx->traj_bytes) {
-            if (ctx->traj) { CU(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->traj); ctx->traj = nullptr; }
+        if (need > ctx->traj_bytes[par]) {
+            if (ctx->traj[par]) { CU(cudaDeviceSynchronize()); cudaFree(ctx->traj[par]); ctx->traj[par] = nullptr; }
             const size_t full = traj_bytes_for(ctx, ctx->sm_count * std::max(ctx->bps[1], 1));
             const size_t want = std::max(need, std::min(full, need * 4));
-            CU(cudaMalloc(&ctx->traj, want));
-            ctx->scratch_bytes += want - ctx->traj_bytes;
-            ctx->traj_bytes = want;
+            CU(cudaMalloc(&ctx->traj[par], want));
+            ctx->scratch_bytes += want - ctx->traj_bytes[par];
+            ctx->traj_bytes[par] = want;
         }
     }
-    int rc = ensure_partials(ctx, grid);
+    int rc = ensure_partials(ctx, grid, par);
     if (rc) return rc;
-    rc = launch_device(ctx, designs, n, crit, grad, fim, xgrid, ctx->traj, ctx->part_val, ctx->part_idx, grid,
-                       ctx->stream);
+    rc = launch_device(ctx, designs, n, crit, grad, fim, xgrid, par, grid, ctx->stream);
     if (rc) return rc;
+    ctx->last_parity = par;
+    ctx->parity = par ^ 1;
     ctx->have_batch = true;
     return DYNOED_OK;
 }
@@ -533,7 +581,9 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
     const int grid_c = grid_for(ctx, chunk, g);
     int total_parts = 0;
     for (int64_t c = 0; c < nchunks; ++c) total_parts += grid_for(ctx, std::min(chunk, n - c * chunk), g);
-    int rc = ensure_partials(ctx, total_parts);
+    const int par = ctx->parity;
+    ctx->prev.valid = false;    // host-path launches run on their own streams: no overlap bookkeeping
+    int rc = ensure_partials(ctx, total_parts, par);
     if (rc) return rc;
     for (int k = 0; k < kSlots && k < nchunks; ++k) {
         rc = ensure_slot(ctx, ctx->slots[k], chunk, g, fim != nullptr);
@@ -554,13 +604,13 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         const int grid = grid_for(ctx, cnt, g);
         P.designs = s.d_designs; P.crit = s.d_crit; P.grad = g ? s.d_grad : nullptr; P.fim = fim ? s.d_fim : nullptr;
         P.xgrid = nullptr; P.traj = s.traj; P.n = cnt;
-        P.part_val = ctx->part_val; P.part_idx = ctx->part_idx;
+        P.part_val = ctx->part_val[par]; P.part_idx = ctx->part_idx[par];
         P.part_base = part_base; P.n_parts = total_parts; P.ticket_target = (unsigned int)total_parts;
-        P.ticket = ctx->d_ticket; P.best_val = ctx->d_best_val; P.best_idx = ctx->d_best_idx;
+        P.ticket = ctx->d_ticket + par; P.best_val = ctx->d_best_val + par; P.best_idx = ctx->d_best_idx + par;
         part_base += grid;
         P.use_tma = (((size_t)ctx->tile * ctx->n_var * 8) % 16 == 0) ? 1 : 0;
         P.index_base = off;
-        CU(ctx->model->launch(ctx->method, g, ctx->ucoef, P, grid, ctx->tile, smem_bytes(ctx), s.stream));
+        CU(ctx->model->launch(ctx->method, g, ctx->ucoef, false, P, grid, ctx->tile, smem_bytes(ctx), s.stream));
         ctx->launches++;
         CU(cudaMemcpyAsync(crit + off, s.d_crit, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s.stream));
         if (g) CU(cudaMemcpyAsync(grad + off * ctx->n_var, s.d_grad, sizeof(double) * cnt * ctx->n_var,
@@ -574,6 +624,8 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
     }
     CU(cudaEventDestroy(ev));
     (void)grid_c;
+    ctx->last_parity = par;
+    ctx->parity = par ^ 1;
     ctx->have_batch = true;
     return DYNOED_OK;
 }
@@ -624,8 +676,8 @@ int dynoed_argmin(dynoed_ctx* ctx, int64_t* idx, double* val) {
     if (!ctx->have_batch) return fail(ctx, DYNOED_EINVAL, "no batch has been evaluated");
     CU(cudaSetDevice(ctx->device));
     double v; long long i;
-    CU(cudaMemcpyAsync(&v, ctx->d_best_val, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(&i, ctx->d_best_idx, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&v, ctx->d_best_val + ctx->last_parity, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&i, ctx->d_best_idx + ctx->last_parity, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     if (idx) *idx = (int64_t)i;
     if (val) *val = v;
@@ -636,8 +688,8 @@ int dynoed_argmin_async(dynoed_ctx* ctx, double* d_val, int64_t* d_idx) {
     if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
     if (!ctx->have_batch) return fail(ctx, DYNOED_EINVAL, "no batch has been evaluated");
     if (!d_val || !d_idx) return fail(ctx, DYNOED_EINVAL, "destination is NULL");
-    CU(cudaMemcpyAsync(d_val, ctx->d_best_val, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(d_idx, ctx->d_best_idx, sizeof(long long), cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_val, ctx->d_best_val + ctx->last_parity, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_idx, ctx->d_best_idx + ctx->last_parity, sizeof(long long), cudaMemcpyDeviceToDevice, ctx->stream));
     return DYNOED_OK;
 }
 
@@ -799,6 +851,7 @@ int dynoed_kernel_stats_query(dynoed_ctx* ctx, int with_grad, dynoed_kernel_stat
     o->block = ctx->tile;
     o->sm_count = ctx->sm_count;
     o->launches = ctx->launches;
+    o->overlapped_launches = ctx->pdl_launches;
     o->scratch_bytes = (int64_t)ctx->scratch_bytes;
     o->n_steps = ctx->n_steps;
     o->stages = ctx->stages;

@@ -562,6 +562,10 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
     const int N = P.n_intervals;
     const double* th = P.theta;
 
+    // Programmatic dependent launch: the next batch's launch (same stream, disjoint buffers and
+    // the other scratch parity — see launch_device) may start filling SMs as this grid's CTAs
+    // drain, which hides the partial last wave.  No-op when the next launch is an ordinary one.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0 && P.use_tma) mbar_init(bar, 1);
     __syncthreads();
     uint32_t phase = 0;

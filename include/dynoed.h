@@ -93,6 +93,7 @@ typedef struct dynoed_kernel_stats {
     int32_t n_steps, stages;
     double flops_per_design_eval, flops_per_design_grad; /* algorithmic, FMA = 2 */
     double bytes_per_design;   /* algorithmic HBM bytes: n_var in + (1 + n_var + nF) out */
+    int64_t overlapped_launches; /* launches allowed to start while their predecessor drained */
 } dynoed_kernel_stats;
 
 int dynoed_abi_version(void);

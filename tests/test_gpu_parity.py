@@ -276,3 +276,42 @@ def test_reference_lv_optimum_through_the_boundary(built_library):
     opi = D.OptimizationProblem(D.OEDProblem(D.OEDSystem(models.lotka_volterra_fishing(True)),
                                              D.DCriterion()), None, integer_constraints=True)
     assert opi.int[:10].all() and opi.int[10:70].all() and not opi.int[70]
+
+
+def test_overlapped_back_to_back_launches_match_isolated_ones(built_library):
+    """Consecutive full-GPU launches on disjoint buffers may overlap their tails (programmatic
+    dependent launch, two scratch sets).  Every batch must still equal its isolated evaluation
+    bit for bit, the arg-min must be the last batch's, and launches that reuse a buffer of their
+    predecessor must NOT be overlapped."""
+    import torch
+    ctx = make_problem("lv_fishing", D.FisherDCriterion).context()
+    ks = ctx.kernel_stats(True)
+    n = ks["grid"] * ks["block"] + 5000                  # 1.09 waves: a real partial last wave
+    K = 5
+    ins = [torch.from_numpy(random_designs("lv_fishing", 71, n, 100 + k)).cuda() for k in range(K)]
+    ref = []
+    for k in range(K):                                   # isolated: a sync between launches
+        c = torch.empty(n, dtype=torch.float64, device="cuda"); g = torch.empty_like(ins[k])
+        f = torch.empty((n, 3), dtype=torch.float64, device="cuda")
+        ctx.eval_batch(ins[k], c, g, f)
+        ref.append((c.clone(), g.clone(), f.clone(), ctx.argmin()))
+    over0 = ctx.kernel_stats(True)["overlapped_launches"]
+    outs = [(torch.empty(n, dtype=torch.float64, device="cuda"), torch.empty_like(ins[k]),
+             torch.empty((n, 3), dtype=torch.float64, device="cuda")) for k in range(K)]
+    for rep in range(3):
+        for k in range(K):
+            ctx.eval_batch(ins[k], *outs[k], async_=True)
+    ctx.sync()
+    assert ctx.kernel_stats(True)["overlapped_launches"] - over0 == 3 * K
+    for k in range(K):
+        for a, b in zip(outs[k], ref[k][:3]):
+            assert torch.equal(a, b)
+    assert ctx.argmin() == ref[K - 1][3]
+    # same output buffers twice in a row: stream order must be kept, so no overlap
+    over1 = ctx.kernel_stats(True)["overlapped_launches"]
+    ctx.eval_batch(ins[0], *outs[0], async_=True)
+    ctx.eval_batch(ins[1], *outs[0], async_=True)
+    ctx.sync()
+    assert ctx.kernel_stats(True)["overlapped_launches"] == over1 + 1   # only the first of the two
+    for a, b in zip(outs[0], ref[1][:3]):
+        assert torch.equal(a, b)
