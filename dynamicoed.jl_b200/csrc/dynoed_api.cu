@@ -15,6 +15,7 @@
 
 #include "../../include/dynoed.h"
 #include "dynoed_kernels.cuh"
+#include "dynoed_rosenbrock.cuh"
 #ifdef DYNOED_MODELS_HEADER
 #include DYNOED_MODELS_HEADER
 #else
@@ -67,11 +68,35 @@ static cudaError_t launch_tab(bool grad, bool uc, bool pdl, const EvalParams& P,
               : launch_one<M, Tab, false, false>(pdl, P, grid, block, smem, st);
 }
 
+template <class M, class RT, bool GRAD>
+static cudaError_t launch_ros(const EvalParams& P, int grid, int block, size_t smem, cudaStream_t st) {
+    auto kern = ros_eval_kernel<M, RT, GRAD>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, block, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+template <class M, class RT, bool GRAD>
+static cudaError_t attrs_ros(int block, size_t smem, cudaFuncAttributes* fa, int* bps) {
+    auto kern = ros_eval_kernel<M, RT, GRAD>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(fa, kern);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, block, smem);
+}
+
 template <class M>
 static cudaError_t launch_model(int method, bool grad, bool uc, bool pdl, const EvalParams& P, int grid, int block,
                                 size_t smem, cudaStream_t st) {
     if (method == DYNOED_RK4) return launch_tab<M, TabRK4>(grad, uc, pdl, P, grid, block, smem, st);
-    return launch_tab<M, TabTsit5>(grad, uc, pdl, P, grid, block, smem, st);
+    if (method == DYNOED_TSIT5) return launch_tab<M, TabTsit5>(grad, uc, pdl, P, grid, block, smem, st);
+    if (method == DYNOED_ROS2)
+        return grad ? launch_ros<M, TabROS2, true>(P, grid, block, smem, st)
+                    : launch_ros<M, TabROS2, false>(P, grid, block, smem, st);
+    return grad ? launch_ros<M, TabROS3P, true>(P, grid, block, smem, st)
+                : launch_ros<M, TabROS3P, false>(P, grid, block, smem, st);
 }
 
 template <class M, class Tab>
@@ -86,7 +111,10 @@ template <class M>
 static cudaError_t attrs_model(int method, bool grad, bool uc, int block, size_t smem, cudaFuncAttributes* fa,
                                int* bps) {
     if (method == DYNOED_RK4) return attrs_tab<M, TabRK4>(grad, uc, block, smem, fa, bps);
-    return attrs_tab<M, TabTsit5>(grad, uc, block, smem, fa, bps);
+    if (method == DYNOED_TSIT5) return attrs_tab<M, TabTsit5>(grad, uc, block, smem, fa, bps);
+    if (method == DYNOED_ROS2)
+        return grad ? attrs_ros<M, TabROS2, true>(block, smem, fa, bps) : attrs_ros<M, TabROS2, false>(block, smem, fa, bps);
+    return grad ? attrs_ros<M, TabROS3P, true>(block, smem, fa, bps) : attrs_ros<M, TabROS3P, false>(block, smem, fa, bps);
 }
 
 template <class M>
@@ -100,6 +128,7 @@ static ModelEntry make_entry() {
     i.nx = M::NX; i.np = M::NP; i.n_obs = M::NOBS; i.n_ctrl = M::NCTRL; i.n_ic = M::NIC;
     i.n_theta = M::NTH; i.nz = M::NZ; i.nF = M::NF;
     for (int k = 0; k < M::NIC; ++k) i.ic_state[k] = M::ic_state(k);
+    i.autonomous = M::AUTONOMOUS ? 1 : 0;
     i.flops_primal = M::FLOPS_PRIMAL; i.flops_primal_z = M::FLOPS_PRIMAL_Z;
     i.flops_adjoint = M::FLOPS_ADJOINT; i.flops_consts = M::FLOPS_CONSTS;
     for (int k = 0; k < M::NX; ++k) i.x0[k] = M::default_x0()[k];
@@ -151,6 +180,7 @@ struct dynoed_ctx {
     int n_intervals = 0, n_steps = 0, n_var = 0, tile = 128;
     int sm_count = 0;
     bool ucoef = false;    // step coefficients served from the constant bank (uniform registers)
+    bool rosenbrock = false;
     int bps[2] = {0, 0};   // blocks per SM without / with gradient
     size_t smem_floor = 0; // dynamic shared memory padding that caps the resident CTAs per SM
     cudaFuncAttributes fa[2];
@@ -182,6 +212,7 @@ struct dynoed_ctx {
         const char* out1[3] = {nullptr, nullptr, nullptr};
     } prev;
     bool pdl_enabled = true;
+    int host_chunks = 8;               // pipeline granularity of the host-buffer path
     bool have_batch = false;
     Slot slots[kSlots];
     int64_t launches = 0;
@@ -243,8 +274,13 @@ static int ensure_partials(dynoed_ctx* ctx, int need, int par) {
     return DYNOED_OK;
 }
 
+// per-CTA scratch of a gradient launch: (x, G) checkpoints of every step (explicit RK adjoint) or
+// the per-interval unweighted quadratures (Rosenbrock)
 static size_t traj_bytes_for(const dynoed_ctx* ctx, int grid) {
-    return (size_t)grid * ctx->n_steps * ctx->model->info.nz * kMaxTile * sizeof(double);
+    const auto& mi = ctx->model->info;
+    const size_t per_lane = ctx->rosenbrock ? (size_t)ctx->n_intervals * mi.n_obs * mi.nF
+                                            : (size_t)ctx->n_steps * mi.nz;
+    return (size_t)grid * per_lane * kMaxTile * sizeof(double);
 }
 
 static size_t smem_bytes(const dynoed_ctx* ctx) {
@@ -266,8 +302,11 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     if (!m) return fail(nullptr, DYNOED_ENOMODEL, std::string("unknown model: ") + (d->model ? d->model : "(null)"));
     const dynoed_model_info& mi = m->info;
     if (d->criterion < 0 || d->criterion > 5) return fail(nullptr, DYNOED_EINVAL, "criterion out of range");
-    if (d->method != DYNOED_RK4 && d->method != DYNOED_TSIT5)
+    if (d->method < DYNOED_RK4 || d->method > DYNOED_ROS3P)
         return fail(nullptr, DYNOED_EUNSUPPORTED, "unsupported integration method");
+    const bool rosenbrock = d->method == DYNOED_ROS2 || d->method == DYNOED_ROS3P;
+    if (rosenbrock && !mi.autonomous)
+        return fail(nullptr, DYNOED_EUNSUPPORTED, "the Rosenbrock integrators need an autonomous right-hand side");
     const int N = d->n_intervals;
     if (N <= 0 || !d->tgrid || !d->indicators) return fail(nullptr, DYNOED_EINVAL, "empty grid");
     if ((mi.n_ctrl && !d->ctrl_offsets) || !d->w_offsets) return fail(nullptr, DYNOED_EINVAL, "layout offsets missing");
@@ -299,7 +338,9 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     ctx->device = device;
     ctx->model = m;
     ctx->method = d->method;
-    ctx->stages = d->method == DYNOED_RK4 ? TabRK4::S : TabTsit5::S;
+    ctx->stages = d->method == DYNOED_RK4 ? TabRK4::S : d->method == DYNOED_TSIT5 ? TabTsit5::S
+                : d->method == DYNOED_ROS2 ? TabROS2::S : TabROS3P::S;
+    ctx->rosenbrock = rosenbrock;
     ctx->criterion = d->criterion;
     ctx->n_intervals = N;
     ctx->n_var = d->n_var;
@@ -346,7 +387,7 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     ctx->n_steps = (int)st.size();
     // one step size for the whole grid => the Runge-Kutta factors h*a, h*b are kernel-parameter
     // constants with compile-time addresses (constant-bank operands of the DFMAs)
-    ctx->ucoef = single_h && !getenv("DYNOED_NO_UCOEF");
+    ctx->ucoef = single_h && !rosenbrock && !getenv("DYNOED_NO_UCOEF");
 
     auto bail = [&](int code, const std::string& msg) { dynoed_destroy(ctx); return fail(nullptr, code, msg); };
 #define CUC(call)                                                                                  \
@@ -373,6 +414,7 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     CUC(cudaMalloc(&ctx->d_ticket, 2 * sizeof(unsigned int)));
     CUC(cudaMemset(ctx->d_ticket, 0, 2 * sizeof(unsigned int)));
     ctx->pdl_enabled = !getenv("DYNOED_NO_PDL");
+    if (const char* hc = getenv("DYNOED_HOST_CHUNKS")) ctx->host_chunks = std::max(1, atoi(hc));
 
     EvalParams& P = ctx->base;
     memset(&P, 0, sizeof(P));
@@ -573,8 +615,8 @@ static int ensure_slot(dynoed_ctx* ctx, Slot& s, int64_t cap, bool grad, bool fi
 static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad, double* fim) {
     const int nF = ctx->model->info.nF;
     const bool g = grad != nullptr;
-    // chunk: a multiple of the tile, about 1/8 of the batch, at least 16 tiles
-    int64_t chunk = ((n / 8 + ctx->tile - 1) / ctx->tile) * ctx->tile;
+    // chunk: a multiple of the tile, about 1/host_chunks of the batch, at least 16 tiles
+    int64_t chunk = ((n / ctx->host_chunks + ctx->tile - 1) / ctx->tile) * ctx->tile;
     chunk = std::max<int64_t>(chunk, 16 * ctx->tile);
     chunk = std::min<int64_t>(chunk, ((n + ctx->tile - 1) / ctx->tile) * ctx->tile);
     const int64_t nchunks = (n + chunk - 1) / chunk;
@@ -637,6 +679,10 @@ static int eval_common(dynoed_ctx* ctx, const double* designs, int64_t n, double
     if (n < 0) return fail(ctx, DYNOED_EINVAL, "n < 0");
     if (n == 0) { ctx->have_batch = false; return DYNOED_OK; }
     if (!designs || !crit) return fail(ctx, DYNOED_EINVAL, "designs/crit is NULL");
+    if (grad && ctx->rosenbrock && ctx->model->info.n_ctrl > 0)
+        return fail(ctx, DYNOED_EUNSUPPORTED,
+                    "the Rosenbrock integrators do not differentiate with respect to controls; "
+                    "pass grad = NULL or use an explicit method");
     CU(cudaSetDevice(ctx->device));
     const int kd = ptr_kind(designs);
     if (ptr_kind(crit) != kd || (grad && ptr_kind(grad) != kd) || (fim && ptr_kind(fim) != kd))
@@ -870,6 +916,11 @@ int dynoed_kernel_stats_query(dynoed_ctx* ctx, int with_grad, dynoed_kernel_stat
     const double bwd = (double)(S - 1) * mi.flops_primal_z + (double)S * mi.flops_adjoint + 2.0 * mi.nz * nza +
                        2.0 * mi.nz * nza + 2.0 * S * (mi.nz + mi.n_obs + mi.n_ctrl) + 2.0 * nza + S;
     const double epi = 10.0 * mi.nF;
+    if (ctx->rosenbrock) {   // no frozen flop count for the Rosenbrock kernels (not a roofline-reported path)
+        o->flops_per_design_eval = o->flops_per_design_grad = 0.0;
+        o->bytes_per_design = 8.0 * (ctx->n_var + 1 + (with_grad ? ctx->n_var : 0) + mi.nF);
+        return DYNOED_OK;
+    }
     o->flops_per_design_eval = fwd * ctx->n_steps + (double)ctx->n_intervals * mi.flops_consts + epi;
     o->flops_per_design_grad = (fwd + bwd) * ctx->n_steps + 2.0 * ctx->n_intervals * mi.flops_consts + epi;
     o->bytes_per_design = 8.0 * (ctx->n_var + 1 + (with_grad ? ctx->n_var : 0) + mi.nF);

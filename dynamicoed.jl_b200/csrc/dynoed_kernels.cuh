@@ -484,6 +484,72 @@ __device__ __forceinline__ void rk_adjoint_step(double t, const double* __restri
 }
 
 // ----------------------------------------------------------------------------------------------
+// Per-CTA partial arg-min (warp shuffles, then one record per CTA); the last CTA of the batch
+// (atomic ticket) reduces every record, so multistart selection needs no second launch.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void argmin_tail(const EvalParams& P, double best_val, long long best_idx) {
+    __shared__ double red_val[kMaxTile / 32];
+    __shared__ long long red_idx[kMaxTile / 32];
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, best_val, o);
+        const long long oi = __shfl_down_sync(0xffffffffu, best_idx, o);
+        if (ov < best_val || (ov == best_val && oi >= 0 && (best_idx < 0 || oi < best_idx))) {
+            best_val = ov; best_idx = oi;
+        }
+    }
+    if ((tid & 31) == 0) { red_val[tid >> 5] = best_val; red_idx[tid >> 5] = best_idx; }
+    __syncthreads();
+    __shared__ int is_last;
+    if (tid == 0) {
+        for (int wq = 1; wq < (int)((blockDim.x + 31) >> 5); ++wq) {
+            const double ov = red_val[wq];
+            const long long oi = red_idx[wq];
+            if (ov < best_val || (ov == best_val && oi >= 0 && (best_idx < 0 || oi < best_idx))) {
+                best_val = ov; best_idx = oi;
+            }
+        }
+        P.part_val[P.part_base + blockIdx.x] = best_val;
+        P.part_idx[P.part_base + blockIdx.x] = best_idx;
+        if (P.use_tma) tma_store_wait_all();
+        __threadfence();
+        const unsigned int t = atomicAdd(P.ticket, 1u);
+        is_last = (t == P.ticket_target - 1u);
+    }
+    __syncthreads();
+    if (is_last) {   // the last CTA of the batch reduces every record (no extra launch)
+        __threadfence();
+        double bv = __longlong_as_double(0x7ff0000000000000LL);
+        long long bi = -1;
+        for (int i = tid; i < P.n_parts; i += blockDim.x) {
+            const double v = __ldcg(P.part_val + i);
+            const long long k = __ldcg(P.part_idx + i);
+            if (k >= 0 && (v < bv || (v == bv && (bi < 0 || k < bi)))) { bv = v; bi = k; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, bv, o);
+            const long long oi = __shfl_down_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (ov < bv || (ov == bv && (bi < 0 || oi < bi)))) { bv = ov; bi = oi; }
+        }
+        __syncthreads();
+        if ((tid & 31) == 0) { red_val[tid >> 5] = bv; red_idx[tid >> 5] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int wq = 1; wq < (int)((blockDim.x + 31) >> 5); ++wq) {
+                const double ov = red_val[wq];
+                const long long oi = red_idx[wq];
+                if (oi >= 0 && (ov < bv || (ov == bv && (bi < 0 || oi < bi)))) { bv = ov; bi = oi; }
+            }
+            *P.best_val = bv;
+            *P.best_idx = bi;
+            *P.ticket = 0u;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
 // The substeps of one merged interval.  UC: the grid has ONE step size and the Runge-Kutta factors
 // h*a, h*b are read from EvalParams::coef at compile-time addresses (constant-bank operands: a
 // DFMA with three vector-register sources issues at 2/3 rate on sm_100a, register * constant +
@@ -552,9 +618,6 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     double* tile_buf = reinterpret_cast<double*>(smem_raw + 128);
-    __shared__ double red_val[kMaxTile / 32];
-    __shared__ long long red_idx[kMaxTile / 32];
-
     const int tid = threadIdx.x;
     const int TILE = P.tile;
     const int n_var = P.n_var;
@@ -725,63 +788,7 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
         }
     }
 
-    // ---- per-CTA partial arg-min (warp shuffles, then one record per CTA) ----
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_down_sync(0xffffffffu, best_val, o);
-        const long long oi = __shfl_down_sync(0xffffffffu, best_idx, o);
-        if (ov < best_val || (ov == best_val && oi >= 0 && (best_idx < 0 || oi < best_idx))) {
-            best_val = ov; best_idx = oi;
-        }
-    }
-    if ((tid & 31) == 0) { red_val[tid >> 5] = best_val; red_idx[tid >> 5] = best_idx; }
-    __syncthreads();
-    __shared__ int is_last;
-    if (tid == 0) {
-        for (int wq = 1; wq < (int)((blockDim.x + 31) >> 5); ++wq) {
-            const double ov = red_val[wq];
-            const long long oi = red_idx[wq];
-            if (ov < best_val || (ov == best_val && oi >= 0 && (best_idx < 0 || oi < best_idx))) {
-                best_val = ov; best_idx = oi;
-            }
-        }
-        P.part_val[P.part_base + blockIdx.x] = best_val;
-        P.part_idx[P.part_base + blockIdx.x] = best_idx;
-        if (P.use_tma) tma_store_wait_all();
-        __threadfence();
-        const unsigned int t = atomicAdd(P.ticket, 1u);
-        is_last = (t == P.ticket_target - 1u);
-    }
-    __syncthreads();
-    if (is_last) {   // the last CTA of the batch reduces every record (no extra launch)
-        __threadfence();
-        double bv = __longlong_as_double(0x7ff0000000000000LL);
-        long long bi = -1;
-        for (int i = tid; i < P.n_parts; i += blockDim.x) {
-            const double v = __ldcg(P.part_val + i);
-            const long long k = __ldcg(P.part_idx + i);
-            if (k >= 0 && (v < bv || (v == bv && (bi < 0 || k < bi)))) { bv = v; bi = k; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_down_sync(0xffffffffu, bv, o);
-            const long long oi = __shfl_down_sync(0xffffffffu, bi, o);
-            if (oi >= 0 && (ov < bv || (ov == bv && (bi < 0 || oi < bi)))) { bv = ov; bi = oi; }
-        }
-        __syncthreads();
-        if ((tid & 31) == 0) { red_val[tid >> 5] = bv; red_idx[tid >> 5] = bi; }
-        __syncthreads();
-        if (tid == 0) {
-            for (int wq = 1; wq < (int)((blockDim.x + 31) >> 5); ++wq) {
-                const double ov = red_val[wq];
-                const long long oi = red_idx[wq];
-                if (oi >= 0 && (ov < bv || (ov == bv && (bi < 0 || oi < bi)))) { bv = ov; bi = oi; }
-            }
-            *P.best_val = bv;
-            *P.best_idx = bi;
-            *P.ticket = 0u;
-        }
-    }
+    argmin_tail(P, best_val, best_idx);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -1,0 +1,429 @@
+// dynoed_rosenbrock.cuh — fixed-grid Rosenbrock integration of the sensitivity-augmented system
+// for the stiff / DAE configuration (BASELINE.json config 4; the reference runs Rodas5 on the torn
+// system, /root/reference/test/references/Rober.jl:23-31, /root/reference/src/problem.jl:82).
+//
+// State per design lane: y = [x; vec(G); P] with P_i = int (h_x[i,:]G)^T (h_x[i,:]G) dt the
+// UNWEIGHTED per-observation quadratures of one merged interval; F += w_i P_i at the interval end
+// (F is linear in w because nothing depends on F, /root/reference/src/augment.jl:223-226), and
+// the per-interval P_i are exactly what d objective / d w needs.
+//
+// One step (Hairer/Wanner IV.7, implementation form without Jacobian-vector products):
+//     (1/(h gamma) I - J_y(y_n)) U_i = g(y_n + sum_{j<i} a_ij U_j) + sum_{j<i} (c_ij / h) U_j
+//     y_{n+1} = y_n + sum_i m_i U_i
+// J_y is block lower triangular with the SAME diagonal block f_x for x and for every column of G
+// and a zero diagonal block for P: one nx x nx LU per step (partial
+// pivoting, registers) serves all 1 + np right-hand sides; the off-diagonal products
+// d(J G_j + f_p,j)/dx . U_x and dq/dy . U are emitted symbolically (Model::ros_ling / ros_linp).
+// The reference factors the dense n_aug x n_aug matrix instead.
+//
+// Gradient: d/dw and d/dtau need no extra integration; d/d(unknown initial conditions) is carried
+// as forward-mode dual parts through the whole scheme (the way the reference's ForwardDiff does,
+// /root/reference/src/problem.jl:154), one dual direction per unknown initial condition.
+// Controls as design variables are not differentiated by this integrator (DYNOED_EUNSUPPORTED).
+#pragma once
+#include <type_traits>
+
+#include "dynoed_kernels.cuh"
+
+namespace dynoed {
+
+// ----------------------------------------------------------------------------------------------
+// forward-mode dual number with K directions
+// ----------------------------------------------------------------------------------------------
+template <int K>
+struct Dual {
+    double v;
+    double d[K];
+    __device__ __forceinline__ Dual() {}
+    __device__ __forceinline__ Dual(double x) : v(x) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) d[i] = 0.0;
+    }
+};
+#define DYNOED_DUAL_LOOP _Pragma("unroll") for (int i = 0; i < K; ++i)
+template <int K> __device__ __forceinline__ Dual<K> operator+(const Dual<K>& a, const Dual<K>& b) { Dual<K> r; r.v = a.v + b.v; DYNOED_DUAL_LOOP r.d[i] = a.d[i] + b.d[i]; return r; }
+template <int K> __device__ __forceinline__ Dual<K> operator-(const Dual<K>& a, const Dual<K>& b) { Dual<K> r; r.v = a.v - b.v; DYNOED_DUAL_LOOP r.d[i] = a.d[i] - b.d[i]; return r; }
+template <int K> __device__ __forceinline__ Dual<K> operator-(const Dual<K>& a) { Dual<K> r; r.v = -a.v; DYNOED_DUAL_LOOP r.d[i] = -a.d[i]; return r; }
+template <int K> __device__ __forceinline__ Dual<K> operator*(const Dual<K>& a, const Dual<K>& b) { Dual<K> r; r.v = a.v * b.v; DYNOED_DUAL_LOOP r.d[i] = fma(a.d[i], b.v, a.v * b.d[i]); return r; }
+template <int K> __device__ __forceinline__ Dual<K> operator/(const Dual<K>& a, const Dual<K>& b) { Dual<K> r; const double ib = 1.0 / b.v; r.v = a.v * ib; DYNOED_DUAL_LOOP r.d[i] = (a.d[i] - r.v * b.d[i]) * ib; return r; }
+template <int K> __device__ __forceinline__ Dual<K> operator+(const Dual<K>& a, double b) { Dual<K> r = a; r.v += b; return r; }
+template <int K> __device__ __forceinline__ Dual<K> operator+(double b, const Dual<K>& a) { Dual<K> r = a; r.v += b; return r; }
+template <int K> __device__ __forceinline__ Dual<K> operator-(const Dual<K>& a, double b) { Dual<K> r = a; r.v -= b; return r; }
+template <int K> __device__ __forceinline__ Dual<K> operator-(double b, const Dual<K>& a) { Dual<K> r; r.v = b - a.v; DYNOED_DUAL_LOOP r.d[i] = -a.d[i]; return r; }
+template <int K> __device__ __forceinline__ Dual<K> operator*(const Dual<K>& a, double b) { Dual<K> r; r.v = a.v * b; DYNOED_DUAL_LOOP r.d[i] = a.d[i] * b; return r; }
+template <int K> __device__ __forceinline__ Dual<K> operator*(double b, const Dual<K>& a) { return a * b; }
+template <int K> __device__ __forceinline__ Dual<K> operator/(const Dual<K>& a, double b) { return a * (1.0 / b); }
+template <int K> __device__ __forceinline__ Dual<K> operator/(double a, const Dual<K>& b) { Dual<K> r; r.v = a / b.v; const double s = -r.v / b.v; DYNOED_DUAL_LOOP r.d[i] = s * b.d[i]; return r; }
+template <int K> __device__ __forceinline__ Dual<K> sqrt(const Dual<K>& a) { Dual<K> r; r.v = ::sqrt(a.v); const double s = 0.5 / r.v; DYNOED_DUAL_LOOP r.d[i] = s * a.d[i]; return r; }
+template <int K> __device__ __forceinline__ Dual<K> exp(const Dual<K>& a) { Dual<K> r; r.v = ::exp(a.v); DYNOED_DUAL_LOOP r.d[i] = r.v * a.d[i]; return r; }
+template <int K> __device__ __forceinline__ Dual<K> log(const Dual<K>& a) { Dual<K> r; r.v = ::log(a.v); const double s = 1.0 / a.v; DYNOED_DUAL_LOOP r.d[i] = s * a.d[i]; return r; }
+template <int K> __device__ __forceinline__ Dual<K> sin(const Dual<K>& a) { Dual<K> r; r.v = ::sin(a.v); const double s = ::cos(a.v); DYNOED_DUAL_LOOP r.d[i] = s * a.d[i]; return r; }
+template <int K> __device__ __forceinline__ Dual<K> cos(const Dual<K>& a) { Dual<K> r; r.v = ::cos(a.v); const double s = -::sin(a.v); DYNOED_DUAL_LOOP r.d[i] = s * a.d[i]; return r; }
+template <int K> __device__ __forceinline__ Dual<K> pow(const Dual<K>& a, double e) { Dual<K> r; r.v = ::pow(a.v, e); const double s = e * ::pow(a.v, e - 1.0); DYNOED_DUAL_LOOP r.d[i] = s * a.d[i]; return r; }
+#undef DYNOED_DUAL_LOOP
+__device__ __forceinline__ double value_of(double x) { return x; }
+template <int K> __device__ __forceinline__ double value_of(const Dual<K>& x) { return x.v; }
+__device__ __forceinline__ double dual_part(double, int) { return 0.0; }
+template <int K> __device__ __forceinline__ double dual_part(const Dual<K>& x, int k) { return x.d[k]; }
+
+// ----------------------------------------------------------------------------------------------
+// Rosenbrock tableaus in implementation form (gamma, a_ij, c_ij, m_i)
+// ----------------------------------------------------------------------------------------------
+// ROS2 (Verwer, Spee, Blom, Hundsdorfer 1999): 2 stages, order 2, L-stable, gamma = 1 + 1/sqrt(2):
+//   (I - gamma h J) k1 = f(y),  (I - gamma h J) k2 = f(y + h k1) - 2 k1,  y+ = y + 1.5 h k1 + 0.5 h k2
+// with U_i = gamma h k_i.
+struct TabROS2 {
+    static constexpr int S = 2;
+    static constexpr double gamma = 1.7071067811865475244;
+    __host__ __device__ static constexpr double a(int i, int j) { return (i == 1 && j == 0) ? 1.0 / gamma : 0.0; }
+    __host__ __device__ static constexpr double c(int i, int j) { return (i == 1 && j == 0) ? -2.0 / gamma : 0.0; }
+    __host__ __device__ static constexpr double m(int i) { return i == 0 ? 1.5 / gamma : 0.5 / gamma; }
+    __host__ __device__ static constexpr bool same_stage_state(int i) { return false; }
+};
+// ROS3P (Lang, Verwer 2001): 3 stages, order 3, A-stable (R(inf) = 0.73), two function evaluations
+// (stages 2 and 3 share their stage state).
+struct TabROS3P {
+    static constexpr int S = 3;
+    static constexpr double gamma = 7.886751345948129e-01;
+    __host__ __device__ static constexpr double a(int i, int j) {
+        return (i == 1 && j == 0) ? 1.267949192431123 : (i == 2 && j == 0) ? 1.267949192431123 : 0.0;
+    }
+    __host__ __device__ static constexpr double c(int i, int j) {
+        return (i == 1 && j == 0) ? -1.607695154586736
+             : (i == 2 && j == 0) ? -3.464101615137755
+             : (i == 2 && j == 1) ? -1.732050807568877 : 0.0;
+    }
+    __host__ __device__ static constexpr double m(int i) {
+        return i == 0 ? 2.0 : i == 1 ? 5.773502691896258e-01 : 4.226497308103742e-01;
+    }
+    __host__ __device__ static constexpr bool same_stage_state(int i) { return i == 2; }
+};
+
+// ----------------------------------------------------------------------------------------------
+// LU with partial pivoting of a small matrix held in registers.  Row exchanges are done with
+// compare-and-swap over statically indexed rows (no dynamic register indexing => no local memory);
+// the right-hand sides are permuted the same way at solve time.
+// ----------------------------------------------------------------------------------------------
+template <class T, int N>
+struct SmallLU {
+    T a[N][N];
+    int piv[N];   // piv[k] = row exchanged with row k at elimination step k
+
+    __device__ __forceinline__ void factor() {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            int p = k;
+            double best = fabs(value_of(a[k][k]));
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) {
+                const double v = fabs(value_of(a[i][k]));
+                if (v > best) { best = v; p = i; }
+            }
+            piv[k] = p;
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) {
+                if (p == i) {   // exchange the active part only: earlier multipliers stay put, which
+                                // is what the interleaved swap/eliminate order of solve() assumes
+#pragma unroll
+                    for (int j = k; j < N; ++j) { const T t = a[k][j]; a[k][j] = a[i][j]; a[i][j] = t; }
+                }
+            }
+            const T inv = 1.0 / a[k][k];
+            a[k][k] = inv;   // the diagonal keeps 1 / pivot
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) {
+                const T l = a[i][k] * inv;
+                a[i][k] = l;
+#pragma unroll
+                for (int j = k + 1; j < N; ++j) a[i][j] = a[i][j] - l * a[k][j];
+            }
+        }
+    }
+    __device__ __forceinline__ void solve(T (&b)[N]) const {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) {
+                if (piv[k] == i) { const T t = b[k]; b[k] = b[i]; b[i] = t; }
+            }
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) b[i] = b[i] - a[i][k] * b[k];
+        }
+#pragma unroll
+        for (int k = N - 1; k >= 0; --k) {
+            T s = b[k];
+#pragma unroll
+            for (int j = k + 1; j < N; ++j) s = s - a[k][j] * b[j];
+            b[k] = s * a[k][k];
+        }
+    }
+};
+
+// ----------------------------------------------------------------------------------------------
+// One Rosenbrock step on y = [z (x, G); Pq (unweighted quadratures)]
+// ----------------------------------------------------------------------------------------------
+template <class M, class RT, class T>
+__device__ __forceinline__ void rosenbrock_step(double t, double h, T (&z)[M::NZ], T (&Pq)[M::NOBS * M::NF],
+                                                const double* u, const double* th, const double* c) {
+    constexpr int S = RT::S, NX = M::NX, NP = M::NP, NZ = M::NZ, NQ = M::NOBS * M::NF;
+    const double c0 = 1.0 / (h * RT::gamma);
+    const double ih = 1.0 / h;
+    SmallLU<T, NX> lu;
+    {
+        T A[NX * NX];
+        M::template ros_jac<T>(t, z, u, th, c, A);
+#pragma unroll
+        for (int i = 0; i < NX; ++i)
+#pragma unroll
+            for (int j = 0; j < NX; ++j) lu.a[i][j] = (i == j ? c0 : 0.0) - A[i * NX + j];
+    }
+    lu.factor();
+    T Uz[S][NZ], Uq[S][NQ];
+    T gz[NZ], gq[NQ];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        if (!RT::same_stage_state(s)) {
+            T Z[NZ];
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) Z[a] = z[a];
+#pragma unroll
+            for (int j = 0; j < s; ++j) {
+                if (RT::a(s, j) != 0.0) {
+#pragma unroll
+                    for (int a = 0; a < NZ; ++a) Z[a] = Z[a] + RT::a(s, j) * Uz[j][a];
+                }
+            }
+            M::template ros_f<T>(t, Z, u, th, c, gz, gq);
+        }
+        T rz[NZ], rq[NQ];
+#pragma unroll
+        for (int a = 0; a < NZ; ++a) rz[a] = gz[a];
+#pragma unroll
+        for (int a = 0; a < NQ; ++a) rq[a] = gq[a];
+#pragma unroll
+        for (int j = 0; j < s; ++j) {
+            if (RT::c(s, j) != 0.0) {
+                const double cj = RT::c(s, j) * ih;
+#pragma unroll
+                for (int a = 0; a < NZ; ++a) rz[a] = rz[a] + cj * Uz[j][a];
+#pragma unroll
+                for (int a = 0; a < NQ; ++a) rq[a] = rq[a] + cj * Uq[j][a];
+            }
+        }
+        // x block
+        T bx[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) bx[i] = rz[i];
+        lu.solve(bx);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) Uz[s][i] = bx[i];
+        // G columns: (c0 I - f_x) U_Gj = r_Gj + B_j U_x
+        T BU[NX * NP];
+        M::template ros_ling<T>(t, z, u, th, c, Uz[s], BU);
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            T bg[NX];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) bg[i] = rz[NX + j * NX + i] + BU[j * NX + i];
+            lu.solve(bg);
+#pragma unroll
+            for (int i = 0; i < NX; ++i) Uz[s][NX + j * NX + i] = bg[i];
+        }
+        // quadrature rows: c0 U_P = r_P + dq/dy . U
+        T dPU[NQ];
+        M::template ros_linp<T>(t, z, u, th, c, Uz[s], dPU);
+        const double ic0 = h * RT::gamma;
+#pragma unroll
+        for (int a = 0; a < NQ; ++a) Uq[s][a] = (rq[a] + dPU[a]) * ic0;
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+#pragma unroll
+        for (int a = 0; a < NZ; ++a) z[a] = z[a] + RT::m(s) * Uz[s][a];
+#pragma unroll
+        for (int a = 0; a < NQ; ++a) Pq[a] = Pq[a] + RT::m(s) * Uq[s][a];
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// The Rosenbrock evaluation kernel: same tile staging (TMA), epilogue and arg-min as
+// oed_eval_kernel; forward sweep only (see the header comment for the gradient).
+// P.traj is used as the per-interval quadrature scratch [grid][N][NOBS*NF][kMaxTile].
+// ----------------------------------------------------------------------------------------------
+template <class M, class RT, bool GRAD>
+__global__ void __launch_bounds__(kMaxTile) ros_eval_kernel(const EvalParams P) {
+    constexpr int NX = M::NX, NP = M::NP, NZ = M::NZ, NF = M::NF, NOBS = M::NOBS, NCTRL = M::NCTRL;
+    constexpr int NCU = NCTRL > 0 ? NCTRL : 1, NQ = NOBS * NF;
+    constexpr int KD = (GRAD && M::NIC > 0) ? M::NIC : 1;
+    using T = typename std::conditional<(GRAD && M::NIC > 0), Dual<KD>, double>::type;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    double* tile_buf = reinterpret_cast<double*>(smem_raw + 128);
+
+    const int tid = threadIdx.x;
+    const int TILE = P.tile;
+    const int n_var = P.n_var;
+    const long long ntiles = (P.n + TILE - 1) / TILE;
+    const int N = P.n_intervals;
+    const double* th = P.theta;
+
+    if (tid == 0 && P.use_tma) mbar_init(bar, 1);
+    __syncthreads();
+    uint32_t phase = 0;
+    double best_val = __longlong_as_double(0x7ff0000000000000LL);
+    long long best_idx = -1;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long g0 = tile * TILE;
+        const int count = (int)((P.n - g0 < TILE) ? (P.n - g0) : TILE);
+        const double* src = P.designs + g0 * n_var;
+        const uint32_t bytes = (uint32_t)count * n_var * 8u;
+        const bool tma_ok = P.use_tma && (bytes % 16u == 0);
+        if (tma_ok) {
+            if (tid == 0) {
+                mbar_expect_tx(bar, bytes);
+                tma_load_1d(tile_buf, src, bytes, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+        } else {
+            for (int i = tid; i < count * n_var; i += blockDim.x) tile_buf[i] = src[i];
+            __syncthreads();
+        }
+
+        if (tid < count) {
+            double* row = tile_buf + (size_t)tid * n_var;
+            const long long g = g0 + tid;
+            T z[NZ], F[NF];
+#pragma unroll
+            for (int a = 0; a < NX; ++a) z[a] = T(P.x0[a]);
+#pragma unroll
+            for (int a = 0; a < NX * NP; ++a) z[NX + a] = T(P.G0[a]);
+            if constexpr (M::NIC > 0) {
+#pragma unroll
+                for (int a = 0; a < M::NIC; ++a) {
+                    T v(row[P.ic_off + a]);
+                    if constexpr (GRAD) v.d[a] = 1.0;
+                    z[M::ic_state(a)] = v;
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < NF; ++a) F[a] = T(0.0);
+            double* pq = P.traj + ((size_t)blockIdx.x * N * NQ) * kMaxTile + tid;
+            double* xg = P.xgrid ? P.xgrid + (size_t)g * (N + 1) * (NZ + NF) : nullptr;
+            if (xg) {
+#pragma unroll
+                for (int a = 0; a < NZ; ++a) xg[a] = value_of(z[a]);
+#pragma unroll
+                for (int a = 0; a < NF; ++a) xg[NZ + a] = 0.0;
+            }
+            for (int j = 0; j < N; ++j) {
+                double u[NCU], w[NOBS], c[M::NCONST];
+#pragma unroll
+                for (int k = 0; k < NCTRL; ++k) u[k] = row[P.ctrl_off[k] + __ldg(P.indicators + k * N + j)];
+#pragma unroll
+                for (int i = 0; i < NOBS; ++i) w[i] = row[P.w_off[i] + __ldg(P.indicators + (NCTRL + i) * N + j)];
+                M::consts(u, th, c);
+                T Pq[NQ];
+#pragma unroll
+                for (int a = 0; a < NQ; ++a) Pq[a] = T(0.0);
+                const int s0 = __ldg(P.first_step + j), s1 = __ldg(P.first_step + j + 1);
+                for (int s = s0; s < s1; ++s)
+                    rosenbrock_step<M, RT, T>(__ldg(P.step_t + s), __ldg(P.step_h + s), z, Pq, u, th, c);
+#pragma unroll
+                for (int i = 0; i < NOBS; ++i)
+#pragma unroll
+                    for (int k = 0; k < NF; ++k) F[k] = F[k] + w[i] * Pq[i * NF + k];
+                if (GRAD) {
+#pragma unroll
+                    for (int a = 0; a < NQ; ++a) pq[((size_t)j * NQ + a) * kMaxTile] = value_of(Pq[a]);
+                }
+                if (xg) {
+                    double* o = xg + (size_t)(j + 1) * (NZ + NF);
+#pragma unroll
+                    for (int a = 0; a < NZ; ++a) o[a] = value_of(z[a]);
+#pragma unroll
+                    for (int a = 0; a < NF; ++a) o[NZ + a] = value_of(F[a]);
+                }
+            }
+
+            // ---- criterion epilogue ----
+            const double tau = row[P.tau_off];
+            double Fv[NF], value, L[NF];
+#pragma unroll
+            for (int a = 0; a < NF; ++a) Fv[a] = value_of(F[a]);
+            criterion_eval<NP>(Fv, tau, P.criterion, value, L);
+            const double obj = value + tau;
+            P.crit[g] = obj;
+            if (P.fim) {
+#pragma unroll
+                for (int a = 0; a < NF; ++a) P.fim[g * NF + a] = Fv[a];
+            }
+            if (obj < best_val) { best_val = obj; best_idx = P.index_base + g; }
+
+            // ---- gradient: <Lambda, .> with the symmetric pairing (off-diagonals count twice) ----
+            if (GRAD) {
+                double Ls[NF];
+#pragma unroll
+                for (int jj = 0; jj < NP; ++jj)
+#pragma unroll
+                    for (int ii = 0; ii <= jj; ++ii) Ls[tri(ii, jj)] = (ii == jj ? 1.0 : 2.0) * L[tri(ii, jj)];
+                double wb[NOBS];
+                int wk[NOBS];
+#pragma unroll
+                for (int i = 0; i < NOBS; ++i) { wb[i] = 0.0; wk[i] = -1; }
+                for (int j = 0; j < N; ++j) {
+#pragma unroll
+                    for (int i = 0; i < NOBS; ++i) {
+                        const int idx = __ldg(P.indicators + (NCTRL + i) * N + j);
+                        if (idx != wk[i]) {
+                            if (wk[i] >= 0) row[P.w_off[i] + wk[i]] = wb[i];
+                            wb[i] = 0.0; wk[i] = idx;
+                        }
+                        double s = 0.0;
+#pragma unroll
+                        for (int k = 0; k < NF; ++k) s = fma(Ls[k], pq[((size_t)j * NQ + i * NF + k) * kMaxTile], s);
+                        wb[i] += s;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NOBS; ++i)
+                    if (wk[i] >= 0) row[P.w_off[i] + wk[i]] = wb[i];
+#pragma unroll
+                for (int a = 0; a < M::NIC; ++a) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NF; ++k) s = fma(Ls[k], dual_part(F[k], a), s);
+                    row[P.ic_off + a] = s;
+                }
+                // controls are not differentiated by the Rosenbrock integrator (rejected on the host)
+                double trL = 1.0;
+#pragma unroll
+                for (int i = 0; i < NP; ++i) trL += L[tri(i, i)];
+                row[P.tau_off] = trL;
+            }
+        }
+
+        if (GRAD) {
+            double* dst = P.grad + g0 * n_var;
+            if (tma_ok) {
+                fence_proxy_async();
+                __syncthreads();
+                if (tid == 0) {
+                    tma_store_1d(dst, tile_buf, bytes);
+                    tma_store_wait_read();
+                }
+                __syncthreads();
+            } else {
+                __syncthreads();
+                for (int i = tid; i < count * n_var; i += blockDim.x) dst[i] = tile_buf[i];
+                __syncthreads();
+            }
+        } else {
+            __syncthreads();
+        }
+    }
+    argmin_tail(P, best_val, best_idx);
+}
+
+}  // namespace dynoed

@@ -160,7 +160,7 @@ class _Block:
     def out(self, lvalue, expr, accumulate=False):
         self.outs.append((lvalue, sp.sympify(expr), accumulate))
 
-    def render(self, printer, inputs, indent="    "):
+    def render(self, printer, inputs, indent="    ", scalar="double"):
         exprs = [e for _, e in self.defs] + [e for _, e, _ in self.outs]
         repl, red = sp.cse(exprs, symbols=sp.numbered_symbols("v", real=True), order="none")
         nd = len(self.defs)
@@ -169,7 +169,7 @@ class _Block:
         defs = _toposort(defs, inputs)
         lines, flops = [], 0
         for s, e in defs:
-            lines.append(f"{indent}const double {s.name} = {printer.doprint(e)};")
+            lines.append(f"{indent}const {scalar} {s.name} = {printer.doprint(e)};")
             flops += count_flops(e)
         for (lv, _, acc), e in zip(self.outs, red[nd:]):
             lines.append(f"{indent}{lv} {'+=' if acc else '='} {printer.doprint(e)};")
@@ -347,20 +347,84 @@ def emit_model(name: str, s: SimplifiedOEDSystem) -> tuple[str, dict]:
                       sum(H(Hc[i, c]) * G[c, j] for c in range(nx)) + H(H0[i, j]))
         return b
 
+    # ---------------- Rosenbrock pieces (stiff / DAE configuration) ---------------------------
+    # The Rosenbrock step works on y = [x; vec(G); P] with P the UNWEIGHTED per-observation
+    # quadratures (F = sum_i w_i P_i is linear in w because nothing depends on F).  The Jacobian of
+    # the augmented system is block lower triangular with the SAME diagonal block f_x for x and
+    # for every column of G, so one nx x nx LU per step serves all
+    # 1 + np right-hand sides; what remains are the off-diagonal products emitted here:
+    #   ros_f    : g(y)  = [f; J G + f_p] and the quadrature integrands q_i = (Q_i^T Q_i)_triu
+    #   ros_jac  : A     = f_x(x)
+    #   ros_ling : B_j U_x = d(J G_j + f_p,j)/dx . U_x          (needs second derivatives of f)
+    #   ros_linp : dq_i/dy . U                                   (x- and G-directions)
+    Usym = [sp.Symbol(f"U{a}", real=True) for a in range(nz)]
+    for a, v in enumerate(Usym):
+        names[v] = f"U[{a}]"
+
+    def build_ros_f():
+        b = _Block()
+        Jt = sp.Matrix(nx, nx, lambda i, c: b.tmp(f"J{i}{c}", H(J[i, c])))
+        fpt = sp.Matrix(nx, max(n_ord, 0), lambda i, j: b.tmp(f"fp{i}{j}", H(fp[i, j]))) \
+            if n_ord else sp.zeros(nx, 0)
+        for i in range(nx):
+            b.out(f"dz[{i}]", H(f[i]))
+        for j in range(np_):
+            for i in range(nx):
+                e = sum(Jt[i, c] * G[c, j] for c in range(nx))
+                if j < n_ord:
+                    e = e + fpt[i, j]
+                b.out(f"dz[{nx + j * nx + i}]", e)
+        Hct = sp.Matrix(n_obs, nx, lambda i, c: b.tmp(f"h{i}{c}", H(Hc[i, c])))
+        Qt = sp.Matrix(n_obs, np_, lambda i, j: b.tmp(
+            f"Q{i}{j}", sum(Hct[i, c] * G[c, j] for c in range(nx)) + H(H0[i, j])))
+        for o in range(n_obs):
+            for k, (i, j) in enumerate(triu_pairs(np_)):
+                b.out(f"dP[{o * nF + k}]", Qt[o, i] * Qt[o, j])
+        return b
+
+    def build_ros_jac():
+        b = _Block()
+        for i in range(nx):
+            for c in range(nx):
+                b.out(f"A[{i * nx + c}]", H(J[i, c]))
+        return b
+
+    def build_ros_ling():
+        b = _Block()
+        for j in range(np_):
+            for i in range(nx):
+                gij = sum(J[i, c] * G[c, j] for c in range(nx)) + (fp[i, j] if j < n_ord else 0)
+                e = sum(H(sp.diff(gij, x[c])) * Usym[c] for c in range(nx))
+                b.out(f"BU[{j * nx + i}]", e)
+        return b
+
+    def build_ros_linp():
+        b = _Block()
+        zs = x + [G[i, j] for j in range(np_) for i in range(nx)]
+        for o in range(n_obs):
+            for k, (i, j) in enumerate(triu_pairs(np_)):
+                q = s.Qexpr[o, i] * s.Qexpr[o, j]
+                e = sum(H(sp.diff(q, zs[a])) * Usym[a] for a in range(nz))
+                b.out(f"dPU[{o * nF + k}]", e)
+        return b
+
     blocks = OrderedDict(primal=build_primal(True), primal_z=build_primal(False),
-                         adjoint=build_adjoint(), obs=build_obs())
+                         adjoint=build_adjoint(), obs=build_obs(), ros_f=build_ros_f(),
+                         ros_jac=build_ros_jac(), ros_ling=build_ros_ling(),
+                         ros_linp=build_ros_linp())
     for k, v in enumerate(hoist.table.values()):
         names[v] = f"c[{k}]"
     pr = _Printer(names)
     inputs = set(names.keys())
     code, flops = {}, {}
     for key, blk in blocks.items():
-        code[key], flops[key] = blk.render(pr, inputs)
+        code[key], flops[key] = blk.render(pr, inputs, scalar="T" if key.startswith("ros_") else "double")
     cb = _Block()
     for k, e in enumerate(hoist.table.keys()):
         cb.out(f"c[{k}]", e)
     code["consts"], flops["consts"] = cb.render(pr, inputs)
     n_const = max(len(hoist.table), 1)
+    autonomous = not any(sp.sympify(e).has(t) for e in list(f) + list(s.Qexpr))
 
     ic_state = [s.x.index(s.aug.x[i - 1]) for i in s.aug.unknown_initial_conditions]
     x0 = [float(v) for v in s.u0[:nx]]
@@ -428,6 +492,36 @@ struct {cname} {{
             const double* __restrict__ u, const double* __restrict__ th,
             const double* __restrict__ c, double* __restrict__ Q) {{
 {code['obs']}
+    }}
+    // ---- Rosenbrock pieces; T = double or a forward-mode dual number ------------------------
+    static constexpr bool AUTONOMOUS = {'true' if autonomous else 'false'};
+    // g(y) = [f; J G + f_p] and the unweighted quadrature integrands q_i = (Q_i^T Q_i)_triu
+    template <class T>
+    __device__ __forceinline__ static void ros_f(double t, const T* __restrict__ z,
+            const double* __restrict__ u, const double* __restrict__ th,
+            const double* __restrict__ c, T* __restrict__ dz, T* __restrict__ dP) {{
+{code['ros_f']}
+    }}
+    // A = f_x(x), row-major [NX][NX]
+    template <class T>
+    __device__ __forceinline__ static void ros_jac(double t, const T* __restrict__ z,
+            const double* __restrict__ u, const double* __restrict__ th,
+            const double* __restrict__ c, T* __restrict__ A) {{
+{code['ros_jac']}
+    }}
+    // BU[j*NX+i] = d(J G_j + f_p,j)_i/dx . U_x   (off-diagonal block of the augmented Jacobian)
+    template <class T>
+    __device__ __forceinline__ static void ros_ling(double t, const T* __restrict__ z,
+            const double* __restrict__ u, const double* __restrict__ th,
+            const double* __restrict__ c, const T* __restrict__ U, T* __restrict__ BU) {{
+{code['ros_ling']}
+    }}
+    // dPU = dq/dy . U  (rows of the quadratures)
+    template <class T>
+    __device__ __forceinline__ static void ros_linp(double t, const T* __restrict__ z,
+            const double* __restrict__ u, const double* __restrict__ th,
+            const double* __restrict__ c, const T* __restrict__ U, T* __restrict__ dPU) {{
+{code['ros_linp']}
     }}
 }};
 """

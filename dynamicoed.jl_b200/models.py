@@ -80,6 +80,31 @@ def robertson():
     return ODESystem(eqs, t, tspan=(0.0, 100.0), observed=[Eq(obs, y1)], name="roberdae")
 
 
+def chem6():
+    """The builder-defined stiff instance of BASELINE.json config 4 ("stiff chemical kinetics with
+    unknown initial conditions, ~6 states, 12 sensitivities, FisherE, Rosenbrock"): it is NOT in
+    the reference (sizes table).  Robertson's autocatalytic core
+    (/root/reference/test/references/Rober.jl:9-21: A -> B, B + C -> A + C, 2B -> B + C) feeding a
+    slow cycle C + D -> E -> F -> D.  The two unknown initial conditions A(0), D(0) are the
+    LEADING states (quirk Q3, /root/reference/src/augment.jl:186); observed: E and C."""
+    t = independent_variable("t")
+    A = variables("A", 1.0, tunable=True, bounds=(0.5, 1.5))
+    Dd = variables("D", 0.5, tunable=True, bounds=(0.1, 1.0))
+    B, Cc, E, Fs = variables("B C E Fs", [0.0, 0.0, 0.0, 0.0])
+    k1, k2, k3, k4, k5, k6 = parameters("k₁ k₂ k₃ k₄ k₅ k₆", [0.04, 3e7, 1e4, 50.0, 2.0, 0.5],
+                                        tunable=False)
+    obs = observed_variables("obs[1] obs[2]", measurement_rate=10)
+    D = Differential(t)
+    eqs = [Eq(D(A), -k1 * A + k3 * B * Cc),
+           Eq(D(Dd), -k4 * Cc * Dd + k6 * Fs),
+           Eq(D(B), k1 * A - k3 * B * Cc - k2 * B ** 2),
+           Eq(D(Cc), k2 * B ** 2 - k4 * Cc * Dd),
+           Eq(D(E), k4 * Cc * Dd - k5 * E),
+           Eq(D(Fs), k5 * E - k6 * Fs)]
+    return ODESystem(eqs, t, tspan=(0.0, 50.0), observed=[Eq(obs[0], E), Eq(obs[1], Cc)],
+                     name="chem6")
+
+
 def mtk_simple(n_obs: int = 1, control: bool = False):
     """/root/reference/test/mtk_extensions.jl:6-21 and /root/reference/test/discretize.jl:6-46 —
     x' = p x (+ c), y1 = x (rate 1.0), y2 = sqrt(x) (rate 0.3), c rate 0.1, on (0,2)."""
@@ -101,4 +126,5 @@ BUILTIN = {
     "lv_fishing": lotka_volterra_fishing,
     "lv_ic": lotka_volterra_ic,
     "robertson": robertson,
+    "chem6": chem6,
 }

@@ -45,6 +45,34 @@ class Tsit5:
     method: int = runtime.TSIT5
 
 
+@dataclass(frozen=True)
+class ROS2:
+    """Fixed-grid Rosenbrock method ROS2 (2 stages, order 2, L-stable) for the stiff / DAE
+    configuration — stands where the reference passes ``Rodas5()``
+    (/root/reference/test/references/Rober.jl:29).  ``substeps`` equal steps per merged interval,
+    or ``edges``: one array of relative substep edges in [0, 1] per merged interval (graded grid)."""
+    substeps: int = 4
+    edges: tuple | None = None
+    method: int = runtime.ROS2
+
+
+@dataclass(frozen=True)
+class ROS3P:
+    """Fixed-grid Rosenbrock method ROS3P (3 stages, order 3, A-stable); see `ROS2`."""
+    substeps: int = 4
+    edges: tuple | None = None
+    method: int = runtime.ROS3P
+
+
+def graded_edges(n_intervals: int, n_first: int, t_min_rel: float, substeps: int) -> tuple:
+    """Substep edges for a stiff start-up transient: ``n_first`` geometrically spaced steps from
+    ``t_min_rel`` (relative to the first interval) up to its end, ``substeps`` equal steps in every
+    later interval (Robertson)."""
+    first = np.concatenate([[0.0], np.geomspace(t_min_rel, 1.0, n_first)])
+    rest = np.arange(substeps + 1, dtype=np.float64) / substeps
+    return tuple([first] + [rest] * (n_intervals - 1))
+
+
 def _resolve_model(sys: SimplifiedOEDSystem):
     """(library path | None, model name, emitter info).  A system whose emitted code equals a
     compiled-in model uses ``libdynoed_cuda.so``; anything else is emitted and compiled once."""
@@ -100,7 +128,8 @@ class OEDProblem:
                 tgrid=self.timegrid.tpoints, indicators=self.timegrid.indicators - 1,
                 ctrl_offsets=lay.control_offsets, w_offsets=lay.w_offsets,
                 ic_offset=lay.ic_offset, tau_offset=lay.tau_offset, n_var=lay.n_var,
-                substeps=self.alg.substeps, theta=info["theta"], x0=info["x0"], G0=info["G0"],
+                substeps=self.alg.substeps, step_edges=getattr(self.alg, "edges", None),
+                theta=info["theta"], x0=info["x0"], G0=info["G0"],
                 device=self.device, library_path=libpath)
         return self._ctx
 

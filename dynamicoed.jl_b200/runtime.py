@@ -14,8 +14,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdynoed_cuda.so")
 
-RK4, TSIT5 = 0, 1
-METHODS = {"rk4": RK4, "RK4": RK4, "tsit5": TSIT5, "Tsit5": TSIT5}
+RK4, TSIT5, ROS2, ROS3P = 0, 1, 2, 3
+METHODS = {"rk4": RK4, "RK4": RK4, "tsit5": TSIT5, "Tsit5": TSIT5, "ros2": ROS2, "ROS2": ROS2,
+           "ros3p": ROS3P, "ROS3P": ROS3P}
 
 
 class DynoedError(RuntimeError):
@@ -25,7 +26,7 @@ class DynoedError(RuntimeError):
 class ModelInfo(C.Structure):
     _fields_ = [("nx", C.c_int32), ("np", C.c_int32), ("n_obs", C.c_int32), ("n_ctrl", C.c_int32),
                 ("n_ic", C.c_int32), ("n_theta", C.c_int32), ("nz", C.c_int32), ("nF", C.c_int32),
-                ("ic_state", C.c_int32 * 8),
+                ("autonomous", C.c_int32), ("ic_state", C.c_int32 * 8),
                 ("flops_primal", C.c_int32), ("flops_primal_z", C.c_int32),
                 ("flops_adjoint", C.c_int32), ("flops_consts", C.c_int32),
                 ("x0", C.c_double * 8), ("G0", C.c_double * 64), ("theta", C.c_double * 48)]

@@ -46,6 +46,11 @@ extern "C" {
  * /root/reference/src/problem.jl:25, /root/reference/src/discretize.jl:314-317) */
 #define DYNOED_RK4 0
 #define DYNOED_TSIT5 1 /* Tsit5 tableau, fixed step */
+/* fixed-grid Rosenbrock methods for the stiff / DAE configuration (the reference uses Rodas5,
+ * /root/reference/test/references/Rober.jl:29); autonomous models only; gradients with respect to
+ * weights, tau and unknown initial conditions (not controls) */
+#define DYNOED_ROS2 2  /* 2 stages, order 2, L-stable */
+#define DYNOED_ROS3P 3 /* 3 stages, order 3, A-stable */
 
 typedef struct dynoed_ctx dynoed_ctx;
 
@@ -53,6 +58,7 @@ typedef struct dynoed_ctx dynoed_ctx;
  * /root/reference/src/augment.jl:128-244 after structural_simplify). */
 typedef struct dynoed_model_info {
     int32_t nx, np, n_obs, n_ctrl, n_ic, n_theta, nz, nF;
+    int32_t autonomous;        /* 1 if the right-hand side does not depend on t explicitly */
     int32_t ic_state[8];       /* 0-based state index of each unknown initial condition */
     int32_t flops_primal, flops_primal_z, flops_adjoint, flops_consts; /* per RHS call, FMA = 2 */
     double x0[8];
@@ -67,7 +73,7 @@ typedef struct dynoed_problem_desc {
     uint32_t struct_size;      /* = sizeof(dynoed_problem_desc) */
     const char* model;         /* name of a compiled-in model */
     int32_t criterion;         /* DYNOED_FISHER_A ... */
-    int32_t method;            /* DYNOED_RK4 | DYNOED_TSIT5 */
+    int32_t method;            /* DYNOED_RK4 | DYNOED_TSIT5 | DYNOED_ROS2 | DYNOED_ROS3P */
     int32_t n_intervals;       /* N: merged grid intervals (Timegrid.timespans) */
     const double* tgrid;       /* [N+1] merged grid points */
     int32_t substeps;          /* uniform substeps per merged interval (>0), or 0 with step_edges */

@@ -13,7 +13,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(_HERE, "_build", "liboed_oracle.so")
-MODEL_IDS = {"one_d": 0, "readme": 1, "lv_fishing": 2, "lv_ic": 3, "robertson": 4}
+MODEL_IDS = {"one_d": 0, "readme": 1, "lv_fishing": 2, "lv_ic": 3, "robertson": 4, "chem6": 5}
 
 
 class _Desc(C.Structure):
@@ -109,7 +109,7 @@ class CppOracle:
             G0=np.ascontiguousarray(o.G0.T.reshape(-1), dtype=np.float64))   # column-major
         d = _Desc()
         d.model, d.crit = self.model, o.crit
-        d.method = {"rk4": 0, "tsit5": 1}[o.method]
+        d.method = {"rk4": 0, "tsit5": 1, "ros2": 2, "ros3p": 3}[o.method]
         d.N, d.n_var, d.n_steps = o.N, o.n_var, len(st)
         a = self._a
         d.tgrid, d.first_step, d.step_t, d.step_h = (a["tgrid"].ctypes.data, a["first"].ctypes.data,

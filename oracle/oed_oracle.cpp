@@ -16,7 +16,10 @@
 //     whole integrator in chunks of 12 directions (ForwardDiff's default chunk size for n > 12;
 //     AutoForwardDiff at /root/reference/src/problem.jl:154)
 // Integrator: FIXED-step classic RK4 or the Tsit5 tableau (parity is only meaningful on a fixed
-// tableau/grid).  PARITY PIN: cross-checked against oracle/oed_oracle.py (which
+// tableau/grid), or a fixed-grid Rosenbrock method (ROS2 / ROS3P) for the stiff
+// configuration, applied the way the reference applies Rodas5: to the FLAT augmented system
+// [x; vec(G); F] with its DENSE Jacobian (obtained here by nested dual numbers, one directional
+// derivative per column, so no hand-written second derivatives) and a dense pivoted LU per step.  PARITY PIN: cross-checked against oracle/oed_oracle.py (which
 // derives its Jacobians symbolically) in tests/test_oracle.py; integration results against the
 // reference itself are unpinned beyond the reference's own 1e-2 test tolerances (no Julia here).
 //
@@ -44,12 +47,35 @@ template <int N> inline Dual<N> operator+(const Dual<N>& a, const Dual<N>& b) { 
 template <int N> inline Dual<N> operator-(const Dual<N>& a, const Dual<N>& b) { Dual<N> r; r.v = a.v - b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] - b.d[i]; return r; }
 template <int N> inline Dual<N> operator-(const Dual<N>& a) { Dual<N> r; r.v = -a.v; for (int i = 0; i < N; ++i) r.d[i] = -a.d[i]; return r; }
 template <int N> inline Dual<N> operator*(const Dual<N>& a, const Dual<N>& b) { Dual<N> r; r.v = a.v * b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * b.v + b.d[i] * a.v; return r; }
+template <int N> inline Dual<N> operator/(const Dual<N>& a, const Dual<N>& b) { Dual<N> r; r.v = a.v / b.v; for (int i = 0; i < N; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) / b.v; return r; }
 template <int N> inline Dual<N> operator*(double a, const Dual<N>& b) { Dual<N> r; r.v = a * b.v; for (int i = 0; i < N; ++i) r.d[i] = a * b.d[i]; return r; }
 template <int N> inline Dual<N> operator*(const Dual<N>& b, double a) { return a * b; }
 template <int N> inline Dual<N> operator+(const Dual<N>& a, double b) { Dual<N> r = a; r.v += b; return r; }
 template <int N> inline Dual<N> operator+(double b, const Dual<N>& a) { return a + b; }
 template <int N> inline Dual<N> operator-(const Dual<N>& a, double b) { Dual<N> r = a; r.v -= b; return r; }
 template <int N> inline Dual<N> operator-(double b, const Dual<N>& a) { return -a + b; }
+// ---------------------------------------------------------------------------------------------
+// one-direction dual number over an arbitrary base type (double or Dual<N>): nesting it around
+// the gradient duals gives Jacobian-vector products of the right-hand side for the Rosenbrock
+// methods without any hand-written second derivative
+// ---------------------------------------------------------------------------------------------
+template <class B>
+struct Du {
+    B v, d;
+    Du() : v(0.0), d(0.0) {}
+    Du(double x) : v(x), d(0.0) {}
+    Du(const B& a, const B& b) : v(a), d(b) {}
+};
+template <class B> inline Du<B> operator+(const Du<B>& a, const Du<B>& b) { return Du<B>(a.v + b.v, a.d + b.d); }
+template <class B> inline Du<B> operator-(const Du<B>& a, const Du<B>& b) { return Du<B>(a.v - b.v, a.d - b.d); }
+template <class B> inline Du<B> operator-(const Du<B>& a) { return Du<B>(-a.v, -a.d); }
+template <class B> inline Du<B> operator*(const Du<B>& a, const Du<B>& b) { return Du<B>(a.v * b.v, a.d * b.v + a.v * b.d); }
+template <class B> inline Du<B> operator*(double a, const Du<B>& b) { return Du<B>(a * b.v, a * b.d); }
+template <class B> inline Du<B> operator*(const Du<B>& b, double a) { return a * b; }
+template <class B> inline Du<B> operator+(const Du<B>& a, double b) { return Du<B>(a.v + b, a.d); }
+template <class B> inline Du<B> operator+(double b, const Du<B>& a) { return a + b; }
+template <class B> inline Du<B> operator-(const Du<B>& a, double b) { return Du<B>(a.v - b, a.d); }
+template <class B> inline Du<B> operator-(double b, const Du<B>& a) { return -a + b; }
 inline double value_of(double x) { return x; }
 template <int N> inline double value_of(const Dual<N>& x) { return x.v; }
 
@@ -131,6 +157,34 @@ struct Robertson {
     static constexpr int ic_state(int) { return 0; }
 };
 
+// Stiff 6-species kinetics with two unknown initial conditions (builder-defined instance of
+// BASELINE.json config 4; dynamicoed.jl_b200/models.py::chem6).  States (A, D, B, C, E, Fs);
+// theta = (k1..k6); tunables = (A(0), D(0)); obs (E, C)
+struct Chem6 {
+    static constexpr int NX = 6, NXA = 0, NPO = 0, NIC = 2, NOBS = 2, NCTRL = 0, NTH = 6;
+    template <class T> static void eval(double, const T* x, const T*, const double* th, const T*, T* f, T (*Jd)[NX], T (*)[1], T (*)[1], T (*Hd)[NX], T (*)[1]) {
+        const double k1 = th[0], k2 = th[1], k3 = th[2], k4 = th[3], k5 = th[4], k6 = th[5];
+        const T A = x[0], D = x[1], B = x[2], C = x[3], E = x[4], Fs = x[5];
+        f[0] = -k1 * A + k3 * (B * C);
+        f[1] = -k4 * (C * D) + k6 * Fs;
+        f[2] = k1 * A - k3 * (B * C) - k2 * (B * B);
+        f[3] = k2 * (B * B) - k4 * (C * D);
+        f[4] = k4 * (C * D) - k5 * E;
+        f[5] = k5 * E - k6 * Fs;
+        for (int i = 0; i < NX; ++i) for (int j = 0; j < NX; ++j) Jd[i][j] = T(0.0);
+        Jd[0][0] = T(-k1); Jd[0][2] = k3 * C; Jd[0][3] = k3 * B;
+        Jd[1][1] = -k4 * C; Jd[1][3] = -k4 * D; Jd[1][5] = T(k6);
+        Jd[2][0] = T(k1); Jd[2][2] = -k3 * C - (2.0 * k2) * B; Jd[2][3] = -k3 * B;
+        Jd[3][1] = -k4 * C; Jd[3][2] = (2.0 * k2) * B; Jd[3][3] = -k4 * D;
+        Jd[4][1] = k4 * C; Jd[4][3] = k4 * D; Jd[4][4] = T(-k5);
+        Jd[5][4] = T(k5); Jd[5][5] = T(-k6);
+        for (int o = 0; o < NOBS; ++o) for (int j = 0; j < NX; ++j) Hd[o][j] = T(0.0);
+        Hd[0][4] = T(1.0); Hd[1][3] = T(1.0);
+    }
+    template <class T> static void torn(double, const T*, const double*, T*, T (*)[NX], T (*)[1]) {}
+    static constexpr int ic_state(int i) { return i; }
+};
+
 struct Grid {
     int N, n_var, method, crit;
     const double* tgrid;
@@ -200,6 +254,87 @@ static const double TS_A[6][6] = {
 static const double TS_B[6] = {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774};
 static const double TS_C[6] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0};
 
+// ---------------------------------------------------------------------------------------------
+// Rosenbrock methods in implementation form (Hairer/Wanner IV.7):
+//   (1/(h gamma) I - J) U_i = g(y + sum_{j<i} a_ij U_j) + sum_{j<i} (c_ij/h) U_j,  y+ = y + sum m_i U_i
+// method 2: ROS2 (Verwer et al. 1999), method 3: ROS3P (Lang/Verwer 2001)
+// ---------------------------------------------------------------------------------------------
+struct RosTab { int S; double gamma; double a[3][3]; double c[3][3]; double m[3]; };
+static const double ROS2_G = 1.7071067811865475244;
+static const RosTab ROS2_TAB = {2, ROS2_G, {{0, 0, 0}, {1.0 / ROS2_G, 0, 0}, {0, 0, 0}},
+                                {{0, 0, 0}, {-2.0 / ROS2_G, 0, 0}, {0, 0, 0}}, {1.5 / ROS2_G, 0.5 / ROS2_G, 0}};
+static const RosTab ROS3P_TAB = {3, 7.886751345948129e-01,
+                                 {{0, 0, 0}, {1.267949192431123, 0, 0}, {1.267949192431123, 0, 0}},
+                                 {{0, 0, 0}, {-1.607695154586736, 0, 0}, {-3.464101615137755, -1.732050807568877, 0}},
+                                 {2.0, 5.773502691896258e-01, 4.226497308103742e-01}};
+
+inline double scalar_value(double x) { return x; }
+template <int N> inline double scalar_value(const Dual<N>& x) { return x.v; }
+inline double div_t(double a, double b) { return a / b; }
+template <int N> inline Dual<N> div_t(const Dual<N>& a, const Dual<N>& b) { return a / b; }
+
+template <class M, class T>
+void rosenbrock_step(const RosTab& tab, double t, double h, T* y, const T* u, const T* w, const double* th) {
+    constexpr int NX = M::NX, NP = M::NPO + M::NIC;
+    constexpr int NA = NX + NX * NP + NP * (NP + 1) / 2;
+    constexpr int NOBS = M::NOBS, NC1 = M::NCTRL > 0 ? M::NCTRL : 1;
+    // dense Jacobian of the flat augmented system, column by column: J e_c = d/d eps g(y + eps e_c)
+    T W[NA][NA];
+    {
+        Du<T> yd[NA], ud[NC1], wd[NOBS], gd[NA];
+        for (int k = 0; k < M::NCTRL; ++k) ud[k] = Du<T>(u[k], T(0.0));
+        for (int o = 0; o < NOBS; ++o) wd[o] = Du<T>(w[o], T(0.0));
+        for (int c = 0; c < NA; ++c) {
+            for (int a = 0; a < NA; ++a) yd[a] = Du<T>(y[a], T(a == c ? 1.0 : 0.0));
+            rhs<M, Du<T>>(t, yd, ud, wd, th, gd);
+            for (int a = 0; a < NA; ++a) W[a][c] = -gd[a].d;
+        }
+        const double c0 = 1.0 / (h * tab.gamma);
+        for (int a = 0; a < NA; ++a) W[a][a] = W[a][a] + c0;
+    }
+    // LU with partial pivoting (pivot chosen on the value part)
+    int perm[NA];
+    for (int k = 0; k < NA; ++k) {
+        int p = k;
+        double best = std::fabs(scalar_value(W[k][k]));
+        for (int i = k + 1; i < NA; ++i) {
+            const double v = std::fabs(scalar_value(W[i][k]));
+            if (v > best) { best = v; p = i; }
+        }
+        perm[k] = p;
+        if (p != k) for (int j = k; j < NA; ++j) std::swap(W[k][j], W[p][j]);   // active part only: the
+        // multipliers of earlier columns stay put, matching the interleaved swap/eliminate solve below
+        for (int i = k + 1; i < NA; ++i) {
+            W[i][k] = div_t(W[i][k], W[k][k]);
+            for (int j = k + 1; j < NA; ++j) W[i][j] = W[i][j] - W[i][k] * W[k][j];
+        }
+    }
+    T U[3][NA], Y[NA], g[NA], r[NA];
+    for (int s = 0; s < tab.S; ++s) {
+        for (int a = 0; a < NA; ++a) Y[a] = y[a];
+        for (int j = 0; j < s; ++j)
+            if (tab.a[s][j] != 0.0)
+                for (int a = 0; a < NA; ++a) Y[a] = Y[a] + tab.a[s][j] * U[j][a];
+        rhs<M, T>(t, Y, u, w, th, g);
+        for (int a = 0; a < NA; ++a) r[a] = g[a];
+        for (int j = 0; j < s; ++j)
+            if (tab.c[s][j] != 0.0)
+                for (int a = 0; a < NA; ++a) r[a] = r[a] + (tab.c[s][j] / h) * U[j][a];
+        for (int k = 0; k < NA; ++k) {
+            if (perm[k] != k) std::swap(r[k], r[perm[k]]);
+            for (int i = k + 1; i < NA; ++i) r[i] = r[i] - W[i][k] * r[k];
+        }
+        for (int k = NA - 1; k >= 0; --k) {
+            T sum = r[k];
+            for (int j = k + 1; j < NA; ++j) sum = sum - W[k][j] * r[j];
+            r[k] = div_t(sum, W[k][k]);
+        }
+        for (int a = 0; a < NA; ++a) U[s][a] = r[a];
+    }
+    for (int s = 0; s < tab.S; ++s)
+        for (int a = 0; a < NA; ++a) y[a] = y[a] + tab.m[s] * U[s][a];
+}
+
 template <class M, class T>
 void integrate(const Grid& g, const T* design, T* z) {
     constexpr int NX = M::NX, NP = M::NPO + M::NIC, NOBS = M::NOBS, NCTRL = M::NCTRL;
@@ -217,6 +352,10 @@ void integrate(const Grid& g, const T* design, T* z) {
         for (int o = 0; o < NOBS; ++o) w[o] = design[g.w_off[o] + g.ind[(NCTRL + o) * g.N + j]];
         for (int s = g.first_step[j]; s < g.first_step[j + 1]; ++s) {
             const double t = g.step_t[s], h = g.step_h[s];
+            if (g.method >= 2) {
+                rosenbrock_step<M, T>(g.method == 2 ? ROS2_TAB : ROS3P_TAB, t, h, z, u, w, g.theta);
+                continue;
+            }
             for (int st = 0; st < S; ++st) {
                 for (int a = 0; a < NA; ++a) zs[a] = z[a];
                 for (int q = 0; q < st; ++q) {
@@ -366,7 +505,7 @@ void traj_one(const Grid& g, const double* design, double* X) {
 extern "C" {
 
 struct oracle_desc {
-    int32_t model;       // 0 one_d, 1 readme, 2 lv_fishing, 3 lv_ic, 4 robertson
+    int32_t model;       // 0 one_d, 1 readme, 2 lv_fishing, 3 lv_ic, 4 robertson, 5 chem6
     int32_t crit, method, N, n_var, n_steps;
     const double* tgrid; const int32_t* first_step; const double* step_t; const double* step_h;
     const int32_t* ind; const int32_t* ctrl_off; const int32_t* w_off; int32_t ic_off, tau_off;
@@ -390,6 +529,7 @@ int oracle_eval_batch(const oracle_desc* d, const double* designs, int64_t n, do
         case 2: eval_batch<LVFishing>(g, designs, n, crit, grad, fim, threads); break;
         case 3: eval_batch<LVIC>(g, designs, n, crit, grad, fim, threads); break;
         case 4: eval_batch<Robertson>(g, designs, n, crit, grad, fim, threads); break;
+        case 5: eval_batch<Chem6>(g, designs, n, crit, grad, fim, threads); break;
         default: return -1;
     }
     return 0;
@@ -403,6 +543,7 @@ int oracle_trajectory(const oracle_desc* d, const double* design, double* X) {
         case 2: traj_one<LVFishing>(g, design, X); break;
         case 3: traj_one<LVIC>(g, design, X); break;
         case 4: traj_one<Robertson>(g, design, X); break;
+        case 5: traj_one<Chem6>(g, design, X); break;
         default: return -1;
     }
     return 0;

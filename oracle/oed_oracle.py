@@ -252,7 +252,8 @@ class Oracle:
 
     sys       : un-augmented ``ODESystem`` (the oracle augments it itself, numerically)
     criterion : 0..5 (FisherA, FisherD, FisherE, A, D, E)
-    method    : "rk4" | "tsit5" (explicit, fixed step) | "ros2" (fixed-grid Rosenbrock)
+    method    : "rk4" | "tsit5" (explicit, fixed step) | "ros2" | "ros3p" (fixed-grid Rosenbrock,
+                values only in this oracle)
     substeps  : int (uniform per merged interval) or list of per-interval substep *edge arrays*
                 (relative positions in [0,1], first 0 and last 1) for graded grids
     theta     : optional dict {parameter name: value} overriding defaults
@@ -441,7 +442,10 @@ class Oracle:
         return out
 
     def _step_ros2(self, t, z, h, u, w):
-        from . import rosenbrock_oracle   # pragma: no cover  (added with the stiff config)
+        from . import rosenbrock_oracle
+        if any(isinstance(v, Jet) for v in z):
+            raise NotImplementedError("the numpy oracle's Rosenbrock step carries values only; "
+                                      "gradients of the stiff configuration come from the C++ oracle")
         return rosenbrock_oracle.step(self, t, z, h, u, w)
 
     # -- sequential solve (discretize.jl:305-344) ------------------------------------------------

@@ -315,3 +315,77 @@ def test_overlapped_back_to_back_launches_match_isolated_ones(built_library):
     assert ctx.kernel_stats(True)["overlapped_launches"] == over1 + 1   # only the first of the two
     for a, b in zip(outs[0], ref[1][:3]):
         assert torch.equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------
+# stiff configuration (BASELINE.json config 4): fixed-grid Rosenbrock kernels
+# ---------------------------------------------------------------------------------------------
+ROS = {"ros2": D.ROS2, "ros3p": D.ROS3P}
+STIFF = {"robertson": (models.robertson, D.DCriterion, 4), "chem6": (models.chem6, D.FisherECriterion, 2)}
+
+
+def stiff_designs(name, n_var, n, seed):
+    rng = np.random.Generator(np.random.Philox(seed))
+    d = rng.random((n, n_var))
+    d[:, -1] = 1e-3 + 0.9 * d[:, -1]
+    if name == "chem6":                      # unknown initial conditions within their bounds
+        d[:, 0] = 0.5 + d[:, 0]
+        d[:, 1] = 0.1 + 0.9 * d[:, 1]
+    return d
+
+
+@pytest.mark.parametrize("name", list(STIFF))
+@pytest.mark.parametrize("method", ["ros2", "ros3p"])
+def test_rosenbrock_kernels_vs_cpp_oracle(name, method, built_library):
+    """GPU (block-triangular solves with one nx x nx LU per step, symbolic second derivatives,
+    dual parts for the unknown initial conditions) vs the C++ oracle (flat dense Jacobian by nested
+    duals): F, objective and the full gradient to relative 1e-10, on a graded grid."""
+    from oracle.cpp_oracle import CppOracle
+    from oracle.oed_oracle import Oracle
+    ctor, crit_cls, crit_id = STIFF[name]
+    edges = D.graded_edges(10, 30, 1e-6, 6)
+    prob = D.OEDProblem(D.OEDSystem(ctor()), crit_cls(), alg=ROS[method](edges=edges))
+    ctx = prob.context()
+    orc = CppOracle(name, Oracle(ctor(), crit_id, method, list(edges)))
+    des = stiff_designs(name, ctx.n_var, 300, 11)
+    c, g, F = ctx.evaluate(des)
+    oc, og, oF = orc.evaluate(des, grad=True)
+    assert rel(F, oF) < RTOL
+    # eigenvalue criteria of a small-lambda_min F inherit the ABSOLUTE error of F (|d lambda| <=
+    # ||dF||): the objective is compared relative to max(|objective|, ||F||_max) per design
+    den = np.maximum(np.abs(oc), np.max(np.abs(oF), axis=1))
+    assert float(np.max(np.abs(c - oc) / den)) < RTOL
+    assert rel_rows(g, og) < RTOL
+    assert ctx.argmin()[0] == int(np.argmin(oc))
+    # criterion only, device buffers, predictor at the grid points
+    c2, _, _ = ctx.evaluate(des[:77], grad=False, fim=False)     # plain-double kernel (no dual parts)
+    assert float(np.max(np.abs(c2 - c[:77]) / den[:77])) < RTOL
+    X = ctx.trajectory(des[5])[0]
+    assert rel(X.T, orc.trajectory(des[5])) < RTOL
+
+
+def test_robertson_reference_golden_through_the_boundary(built_library):
+    """test/references/Rober.jl:50-66 — DCriterion, measurements on the last 3 of 10 intervals:
+    objective 0 +- 1e-2 (here 1/(F + tau) + tau with F = 740.6)."""
+    edges = D.graded_edges(10, 160, 1e-6, 40)
+    prob = D.OEDProblem(D.structural_simplify(D.dae_index_lowering(D.OEDSystem(models.robertson()))),
+                        D.DCriterion(), alg=D.ROS3P(edges=edges))
+    u = np.asarray(D.get_initial_variables(prob), dtype=np.float64)
+    u[7:10] = 1.0
+    u[-1] = 1e-3
+    c, g, F = prob.context().evaluate(u[None])
+    assert abs(F[0, 0] - 740.59) / 740.59 < 1e-4
+    assert abs(c[0]) < 1e-2
+
+
+def test_rosenbrock_rejects_control_gradients_and_time_dependence(built_library):
+    from oracle.cpp_oracle import CppOracle
+    from oracle.oed_oracle import Oracle
+    prob = D.OEDProblem(D.OEDSystem(models.lotka_volterra_fishing()), D.FisherDCriterion(), alg=D.ROS2(4))
+    ctx = prob.context()
+    des = random_designs("lv_fishing", 71, 64, 3)
+    with pytest.raises(runtime.DynoedError):
+        ctx.evaluate(des)                                      # gradient w.r.t. controls: unsupported
+    c, _, F = ctx.evaluate(des, grad=False)                    # the objective itself is fine
+    oc, _, oF = CppOracle("lv_fishing", Oracle(models.lotka_volterra_fishing(), 1, "ros2", 4)).evaluate(des, grad=False)
+    assert rel(F, oF) < RTOL and rel(c, oc) < RTOL

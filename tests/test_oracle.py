@@ -232,3 +232,91 @@ def test_forward_mode_gradient_vs_finite_differences():
         e = np.zeros(71); e[k] = 1e-6
         fd = (o.evaluate(d + e)[0][0] - o.evaluate(d - e)[0][0]) / 2e-6
         assert abs(fd - g[0, k]) < 1e-7 * max(1, abs(fd))
+
+
+# ---------------------------------------------------------------------------------------------
+# stiff configuration: fixed-grid Rosenbrock oracles
+# ---------------------------------------------------------------------------------------------
+def _graded(n_first=40, m=10, n_intervals=10):
+    import dynamicoed.jl_b200 as D
+    return list(D.graded_edges(n_intervals, n_first, 1e-6, m))
+
+
+def test_rosenbrock_tableaus_order_and_stability():
+    """Empirical order of ROS2 / ROS3P on a nonlinear test problem and |R(-inf)| on y' = lambda y,
+    through the numpy oracle's step (so the coefficients themselves are checked)."""
+    from oracle import rosenbrock_oracle as R
+
+    class Toy:   # y1' = -y1 y2 + 0.3 y2^2, y2' = y1^2 - y2
+        def __init__(self, method): self.method = method
+        def rhs(self, t, y, u, w): return [-y[0] * y[1] + 0.3 * y[1] * y[1], y[0] * y[0] - y[1]], None
+    f = lambda t, y: [-y[0] * y[1] + 0.3 * y[1] ** 2, y[0] ** 2 - y[1]]
+    ref = solve_ivp(f, (0, 2), [1.0, 0.5], rtol=1e-13, atol=1e-14, method="DOP853").y[:, -1]
+    for method, order in (("ros2", 2), ("ros3p", 3)):
+        errs = []
+        for n in (40, 80, 160):
+            y = [np.array([1.0]), np.array([0.5])]
+            for _ in range(n):
+                y = R.step(Toy(method), 0.0, y, 2.0 / n, [], [])
+            errs.append(np.hypot(y[0][0] - ref[0], y[1][0] - ref[1]))
+        rates = np.log2(np.array(errs[:-1]) / np.array(errs[1:]))
+        assert np.all(np.abs(rates - order) < 0.15), (method, rates)
+
+    class Lin:
+        def __init__(self, method): self.method = method
+        def rhs(self, t, y, u, w): return [-1e8 * y[0]], None
+    assert abs(R.step(Lin("ros2"), 0.0, [np.array([1.0])], 1.0, [], [])[0][0]) < 1e-6      # L-stable
+    assert abs(R.step(Lin("ros3p"), 0.0, [np.array([1.0])], 1.0, [], [])[0][0]) < 0.74     # A-stable
+
+
+def test_robertson_rosenbrock_vs_radau_and_reference_golden():
+    """Robertson DAE (test/references/Rober.jl:9-21), w = last 3 of 10: tight scipy Radau gives
+    F = 740.59; the fixed-grid Rosenbrock oracles converge to it and the
+    DCriterion objective matches the reference's golden 0 +- 1e-2 (Rober.jl:50-66)."""
+    k1, k2, k3 = 0.04, 3e7, 1e4
+
+    def rhs(t, s):
+        y1, y2, g1, g2, F = s
+        y3 = 1 - y1 - y2
+        a11, a12 = -k1 - k3 * y2, k3 * y3 - k3 * y2
+        a21, a22 = k1 + k3 * y2, -k3 * y3 + k3 * y2 - 2 * k2 * y2
+        return [-k1 * y1 + k3 * y2 * y3, k1 * y1 - k3 * y2 * y3 - k2 * y2 ** 2,
+                a11 * g1 + a12 * g2 - y1, a21 * g1 + a22 * g2 + y1, (t >= 70.0) * g1 * g1]
+    s1 = solve_ivp(rhs, (0, 70), [1, 0, 0, 0, 0], method="Radau", rtol=1e-11, atol=1e-14)
+    s2 = solve_ivp(rhs, (70, 100), s1.y[:, -1], method="Radau", rtol=1e-11, atol=1e-14)
+    F_exact = s2.y[4, -1]
+    assert abs(F_exact - 740.59) < 0.05
+    des = np.zeros((1, 11)); des[0, 7:10] = 1.0; des[0, 10] = 1e-3
+    errs = {}
+    for method, n0, m in (("ros2", 160, 40), ("ros3p", 40, 10), ("ros3p", 160, 40)):
+        o = Oracle(models.robertson(), CRIT_D, method, _graded(n0, m))
+        c, _, F = o.evaluate(des)
+        errs[(method, n0)] = abs(F[0, 0] - F_exact) / F_exact
+        assert abs(c[0] - (1.0 / (F_exact + 1e-3) + 1e-3)) < 1e-2          # reference golden tolerance
+    assert errs[("ros2", 160)] < 2e-3 and errs[("ros3p", 40)] < 2e-3 and errs[("ros3p", 160)] < 1e-4
+
+
+@pytest.mark.parametrize("name,ctor,crit", [("robertson", models.robertson, CRIT_D),
+                                            ("chem6", models.chem6, FISHER_E)])
+@pytest.mark.parametrize("method", ["ros2", "ros3p"])
+def test_rosenbrock_cpp_oracle_matches_numpy_oracle_and_fd(name, ctor, crit, method):
+    """Flat dense Rosenbrock two ways (numpy: dual-number Jacobian + LAPACK; C++: nested duals +
+    own pivoted LU) agree to rounding; the C++ forward-mode gradient matches central differences."""
+    o = Oracle(ctor(), crit, method, _graded(30, 6))
+    co = cpp_oracle.CppOracle(name, o)
+    rng = np.random.Generator(np.random.Philox(7))
+    des = rng.random((3, o.n_var))
+    des[:, -1] = 1e-3 + 0.9 * des[:, -1]
+    if name == "chem6":
+        des[:, 0] = 0.5 + des[:, 0]
+        des[:, 1] = 0.1 + 0.9 * des[:, 1]
+    c, _, F = o.evaluate(des)
+    c2, g2, F2 = co.evaluate(des, grad=True)
+    assert np.max(np.abs(F - F2) / np.max(np.abs(F2))) < 1e-11
+    assert np.max(np.abs(c - c2) / np.abs(c2)) < 1e-11
+    eps = 1e-6
+    for k in range(o.n_var):
+        dp, dm = des.copy(), des.copy()
+        dp[:, k] += eps; dm[:, k] -= eps
+        fd = (co.evaluate(dp, grad=False)[0] - co.evaluate(dm, grad=False)[0]) / (2 * eps)
+        assert np.allclose(fd, g2[:, k], rtol=2e-5, atol=1e-9 * max(1.0, np.max(np.abs(g2)))), (k, fd, g2[:, k])
