@@ -158,6 +158,7 @@ static const ModelEntry* find_model(const char* name) {
 }
 
 constexpr int kSlots = 4;   // pipeline depth of the host-buffer path
+constexpr int kRing = 64;   // arg-min records kept for deferred (batched) multi-GPU gathers
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -199,8 +200,9 @@ struct dynoed_ctx {
     double* part_val[2] = {nullptr, nullptr};
     long long* part_idx[2] = {nullptr, nullptr};
     int part_cap[2] = {0, 0};
-    double* d_best_val = nullptr;      // [2]
-    long long* d_best_idx = nullptr;   // [2]
+    long long* d_best = nullptr;       // [2 parities][2]: {criterion value (double bits), design index}
+    long long* d_ring = nullptr;       // [kRing][2]: the same record for the last kRing batches
+    int64_t batch_seq = 0;             // batches evaluated so far (ring slot = seq % kRing)
     unsigned int* d_ticket = nullptr;  // [2]
     int parity = 0;                    // scratch set of the NEXT device-path launch
     int last_parity = 0;               // scratch set that holds the most recent batch's arg-min
@@ -409,8 +411,9 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     CUC(cudaMemcpy(ctx->d_step_t, st.data(), sizeof(double) * st.size(), cudaMemcpyHostToDevice));
     CUC(cudaMemcpy(ctx->d_step_h, sh.data(), sizeof(double) * st.size(), cudaMemcpyHostToDevice));
     CUC(cudaMemcpy(ctx->d_indicators, d->indicators, sizeof(int) * nvars * N, cudaMemcpyHostToDevice));
-    CUC(cudaMalloc(&ctx->d_best_val, 2 * sizeof(double)));
-    CUC(cudaMalloc(&ctx->d_best_idx, 2 * sizeof(long long)));
+    CUC(cudaMalloc(&ctx->d_best, 4 * sizeof(long long)));
+    CUC(cudaMalloc(&ctx->d_ring, 2 * kRing * sizeof(long long)));
+    CUC(cudaMemset(ctx->d_ring, 0xff, 2 * kRing * sizeof(long long)));
     CUC(cudaMalloc(&ctx->d_ticket, 2 * sizeof(unsigned int)));
     CUC(cudaMemset(ctx->d_ticket, 0, 2 * sizeof(unsigned int)));
     ctx->pdl_enabled = !getenv("DYNOED_NO_PDL");
@@ -466,7 +469,7 @@ void dynoed_destroy(dynoed_ctx* ctx) {
     }
     cudaFree(ctx->d_first_step); cudaFree(ctx->d_step_t); cudaFree(ctx->d_step_h); cudaFree(ctx->d_indicators);
     for (int q = 0; q < 2; ++q) { cudaFree(ctx->traj[q]); cudaFree(ctx->part_val[q]); cudaFree(ctx->part_idx[q]); }
-    cudaFree(ctx->d_best_val); cudaFree(ctx->d_best_idx); cudaFree(ctx->d_ticket);
+    cudaFree(ctx->d_best); cudaFree(ctx->d_ring); cudaFree(ctx->d_ticket);
     if (ctx->ev_k0) { cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -512,7 +515,8 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
     P.traj = ctx->traj[par]; P.n = n;
     P.part_val = ctx->part_val[par]; P.part_idx = ctx->part_idx[par];
     P.part_base = 0; P.n_parts = grid; P.ticket_target = (unsigned int)grid;
-    P.ticket = ctx->d_ticket + par; P.best_val = ctx->d_best_val + par; P.best_idx = ctx->d_best_idx + par;
+    P.ticket = ctx->d_ticket + par; P.best_val = reinterpret_cast<double*>(ctx->d_best + 2 * par); P.best_idx = ctx->d_best + 2 * par + 1;
+    P.ring_rec = ctx->d_ring + 2 * (ctx->batch_seq % kRing);
     P.use_tma = ((reinterpret_cast<uintptr_t>(designs) % 16 == 0) &&
                  (grad == nullptr || reinterpret_cast<uintptr_t>(grad) % 16 == 0) &&
                  (((size_t)ctx->tile * ctx->n_var * 8) % 16 == 0)) ? 1 : 0;
@@ -577,6 +581,7 @@ static int eval_device(dynoed_ctx* ctx, const double* designs, int64_t n, double
     if (rc) return rc;
     ctx->last_parity = par;
     ctx->parity = par ^ 1;
+    ctx->batch_seq++;
     ctx->have_batch = true;
     return DYNOED_OK;
 }
@@ -648,7 +653,8 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         P.xgrid = nullptr; P.traj = s.traj; P.n = cnt;
         P.part_val = ctx->part_val[par]; P.part_idx = ctx->part_idx[par];
         P.part_base = part_base; P.n_parts = total_parts; P.ticket_target = (unsigned int)total_parts;
-        P.ticket = ctx->d_ticket + par; P.best_val = ctx->d_best_val + par; P.best_idx = ctx->d_best_idx + par;
+        P.ticket = ctx->d_ticket + par; P.best_val = reinterpret_cast<double*>(ctx->d_best + 2 * par); P.best_idx = ctx->d_best + 2 * par + 1;
+        P.ring_rec = ctx->d_ring + 2 * (ctx->batch_seq % kRing);
         part_base += grid;
         P.use_tma = (((size_t)ctx->tile * ctx->n_var * 8) % 16 == 0) ? 1 : 0;
         P.index_base = off;
@@ -668,6 +674,7 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
     (void)grid_c;
     ctx->last_parity = par;
     ctx->parity = par ^ 1;
+    ctx->batch_seq++;
     ctx->have_batch = true;
     return DYNOED_OK;
 }
@@ -722,9 +729,11 @@ int dynoed_argmin(dynoed_ctx* ctx, int64_t* idx, double* val) {
     if (!ctx->have_batch) return fail(ctx, DYNOED_EINVAL, "no batch has been evaluated");
     CU(cudaSetDevice(ctx->device));
     double v; long long i;
-    CU(cudaMemcpyAsync(&v, ctx->d_best_val + ctx->last_parity, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(&i, ctx->d_best_idx + ctx->last_parity, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    long long rec[2];
+    CU(cudaMemcpyAsync(rec, ctx->d_best + 2 * ctx->last_parity, sizeof(rec), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    memcpy(&v, &rec[0], sizeof(double));
+    i = rec[1];
     if (idx) *idx = (int64_t)i;
     if (val) *val = v;
     return DYNOED_OK;
@@ -734,8 +743,46 @@ int dynoed_argmin_async(dynoed_ctx* ctx, double* d_val, int64_t* d_idx) {
     if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
     if (!ctx->have_batch) return fail(ctx, DYNOED_EINVAL, "no batch has been evaluated");
     if (!d_val || !d_idx) return fail(ctx, DYNOED_EINVAL, "destination is NULL");
-    CU(cudaMemcpyAsync(d_val, ctx->d_best_val + ctx->last_parity, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(d_idx, ctx->d_best_idx + ctx->last_parity, sizeof(long long), cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_val, ctx->d_best + 2 * ctx->last_parity, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_idx, ctx->d_best + 2 * ctx->last_parity + 1, sizeof(long long), cudaMemcpyDeviceToDevice, ctx->stream));
+    return DYNOED_OK;
+}
+
+int dynoed_argmin_record_async(dynoed_ctx* ctx, void* d_record) {
+    if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    if (!ctx->have_batch) return fail(ctx, DYNOED_EINVAL, "no batch has been evaluated");
+    if (!d_record) return fail(ctx, DYNOED_EINVAL, "destination is NULL");
+    CU(cudaMemcpyAsync(d_record, ctx->d_best + 2 * ctx->last_parity, 2 * sizeof(long long),
+                       cudaMemcpyDeviceToDevice, ctx->stream));
+    return DYNOED_OK;
+}
+
+int dynoed_argmin_history_async(dynoed_ctx* ctx, int count, void* d_records) {
+    if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    if (count < 1 || count > kRing || (int64_t)count > ctx->batch_seq)
+        return fail(ctx, DYNOED_EINVAL, "count must be 1..64 and not exceed the batches evaluated so far");
+    if (!d_records) return fail(ctx, DYNOED_EINVAL, "destination is NULL");
+    const int64_t first = ctx->batch_seq - count;          // oldest batch wanted
+    const int s0 = (int)(first % kRing);
+    const int n0 = std::min(count, kRing - s0);            // up to the end of the ring, then wrap
+    char* dst = reinterpret_cast<char*>(d_records);
+    CU(cudaMemcpyAsync(dst, ctx->d_ring + 2 * s0, (size_t)n0 * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (n0 < count)
+        CU(cudaMemcpyAsync(dst + (size_t)n0 * 16, ctx->d_ring, (size_t)(count - n0) * 16, cudaMemcpyDeviceToDevice,
+                           ctx->stream));
+    return DYNOED_OK;
+}
+
+int dynoed_argmin_gathered(dynoed_ctx* ctx, const void* d_records, int world, int groups, int64_t shard_size,
+                           void* d_out) {
+    if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    if (!d_records || !d_out || world < 1 || world > 1024 || groups < 1 || groups > 65535)
+        return fail(ctx, DYNOED_EINVAL, "bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    argmin_records_kernel<<<groups, 32, 0, ctx->stream>>>(reinterpret_cast<const long long*>(d_records), world, groups,
+                                                          (long long)shard_size, reinterpret_cast<long long*>(d_out));
+    CU(cudaGetLastError());
+    ctx->launches++;
     return DYNOED_OK;
 }
 

@@ -83,6 +83,7 @@ struct EvalParams {
     unsigned int* __restrict__ ticket;
     double* __restrict__ best_val;
     long long* __restrict__ best_idx;
+    long long* __restrict__ ring_rec;     // history slot of this batch: {value bits, index} (or nullptr)
     // Runge-Kutta factors of the single step size of a uniform grid (UCOEF kernels)
     double coef[kCoefStride];
 };
@@ -544,6 +545,7 @@ __device__ __forceinline__ void argmin_tail(const EvalParams& P, double best_val
             }
             *P.best_val = bv;
             *P.best_idx = bi;
+            if (P.ring_rec) { P.ring_rec[0] = __double_as_longlong(bv); P.ring_rec[1] = bi; }
             *P.ticket = 0u;
         }
     }
@@ -789,6 +791,38 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
     }
 
     argmin_tail(P, best_val, best_idx);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Multi-GPU multistart: arg-min over the per-rank {value, local index} records that an NCCL
+// all-gather collected, for `groups` batches at once (one warp per batch).
+// out[g] = {value bits, global index = rank * shard + local, owner}.
+// NaN never wins; ties go to the smallest global index.
+// ----------------------------------------------------------------------------------------------
+__global__ void argmin_records_kernel(const long long* __restrict__ rec, int world, int groups, long long shard,
+                                      long long* __restrict__ out) {
+    // rec: [world][groups][2]; one block (one warp) per group (= per gathered batch)
+    const int g = blockIdx.x;
+    double bv = __longlong_as_double(0x7ff0000000000000LL);
+    long long bi = -1;
+    for (int r = threadIdx.x; r < world; r += 32) {
+        const long long* q = rec + ((size_t)r * groups + g) * 2;
+        const double v = __longlong_as_double(q[0]);
+        const long long li = q[1];
+        const long long gi = li >= 0 ? (long long)r * shard + li : -1;
+        if (gi >= 0 && (v < bv || (v == bv && (bi < 0 || gi < bi)))) { bv = v; bi = gi; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, bv, o);
+        const long long oi = __shfl_down_sync(0xffffffffu, bi, o);
+        if (oi >= 0 && (ov < bv || (ov == bv && (bi < 0 || oi < bi)))) { bv = ov; bi = oi; }
+    }
+    if (threadIdx.x == 0) {
+        out[3 * g + 0] = __double_as_longlong(bv);
+        out[3 * g + 1] = bi;
+        out[3 * g + 2] = bi >= 0 ? bi / shard : -1;
+    }
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -57,7 +57,9 @@ EXPORTS = ["dynoed_abi_version", "dynoed_model_count", "dynoed_model_name", "dyn
            "dynoed_create", "dynoed_destroy", "dynoed_set_criterion", "dynoed_set_stream",
            "dynoed_own_stream",
            "dynoed_eval_batch", "dynoed_eval_batch_async", "dynoed_sync", "dynoed_argmin",
-           "dynoed_argmin_async", "dynoed_set_profiling", "dynoed_kernel_time",
+           "dynoed_argmin_async", "dynoed_argmin_record_async", "dynoed_argmin_history_async",
+           "dynoed_argmin_gathered",
+           "dynoed_set_profiling", "dynoed_kernel_time",
            "dynoed_trajectory", "dynoed_criterion_batch", "dynoed_fp64_peak", "dynoed_fp64_microbench",
            "dynoed_kernel_stats_query", "dynoed_host_alloc", "dynoed_host_free",
            "dynoed_last_error"]
@@ -90,6 +92,9 @@ def lib(path: str | None = None):
         L.dynoed_sync.argtypes = [vp]
         L.dynoed_argmin.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
         L.dynoed_argmin_async.argtypes = [vp, dp, dp]
+        L.dynoed_argmin_record_async.argtypes = [vp, dp]
+        L.dynoed_argmin_history_async.argtypes = [vp, C.c_int, dp]
+        L.dynoed_argmin_gathered.argtypes = [vp, dp, C.c_int, C.c_int, i64, dp]
         L.dynoed_set_profiling.argtypes = [vp, C.c_int]
         L.dynoed_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         L.dynoed_trajectory.argtypes = [vp, dp, i64, dp]
@@ -227,6 +232,20 @@ class Context:
     def argmin_async(self, d_val, d_idx):
         """Copy the (value, index) record into 1-element CUDA tensors (float64 / int64)."""
         _check(self._L.dynoed_argmin_async(self._h, d_val.data_ptr(), d_idx.data_ptr()), self._h, self._L)
+
+    def argmin_record_async(self, d_record):
+        """Copy the 16-byte {value, local index} record into a 2-element int64 CUDA tensor."""
+        _check(self._L.dynoed_argmin_record_async(self._h, d_record.data_ptr()), self._h, self._L)
+
+    def argmin_history_async(self, count: int, d_records):
+        """Records of the last `count` batches (oldest first) into a [count, 2] int64 CUDA tensor."""
+        _check(self._L.dynoed_argmin_history_async(self._h, int(count), d_records.data_ptr()), self._h, self._L)
+
+    def argmin_gathered(self, d_records, world: int, shard_size: int, d_out, groups: int = 1):
+        """Arg-min over all-gathered records ([world, groups, 2] int64 CUDA tensor) into d_out
+        ([groups, 3] int64: value bits, global index, owner rank), on the ctx stream."""
+        _check(self._L.dynoed_argmin_gathered(self._h, d_records.data_ptr(), int(world), int(groups),
+                                              int(shard_size), d_out.data_ptr()), self._h, self._L)
 
     def set_profiling(self, on: bool):
         _check(self._L.dynoed_set_profiling(self._h, int(bool(on))), self._h, self._L)

@@ -134,6 +134,18 @@ int dynoed_argmin(dynoed_ctx* ctx, int64_t* idx, double* val);
  * NCCL all-gather of per-rank (min, index) records in the multi-GPU sweep */
 int dynoed_argmin_async(dynoed_ctx* ctx, double* d_val, int64_t* d_idx);
 
+/* the same record as ONE 16-byte device-to-device copy: {double value, int64 local index} */
+int dynoed_argmin_record_async(dynoed_ctx* ctx, void* d_record);
+/* the records of the last `count` batches (oldest first, count <= 64) as [count][2] x 8 bytes,
+ * copied on the ctx stream: lets a multi-GPU sweep gather several batches with ONE collective, so
+ * that consecutive evaluation launches stay back to back (and overlap their tails) */
+int dynoed_argmin_history_async(dynoed_ctx* ctx, int count, void* d_records);
+/* arg-min over gathered records ([world][groups][2] x 8 bytes, rank-major) on the ctx stream:
+ * d_out[groups][3] x 8 bytes = {double value, int64 global index = rank * shard_size + local,
+ * int64 owner rank}.  NaN never wins, ties go to the smallest global index.  (BASELINE config 5.) */
+int dynoed_argmin_gathered(dynoed_ctx* ctx, const void* d_records, int world, int groups,
+                           int64_t shard_size, void* d_out);
+
 /* the predictor p -> (X, t) of build_predictor (problem.jl:80-90) at the merged-grid points:
  * X[k] is [N+1][nz+nF] row-major (state order [x; vec(G); F_triu], augment.jl:240) */
 int dynoed_trajectory(dynoed_ctx* ctx, const double* designs, int64_t n, double* X);

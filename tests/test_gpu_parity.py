@@ -389,3 +389,45 @@ def test_rosenbrock_rejects_control_gradients_and_time_dependence(built_library)
     c, _, F = ctx.evaluate(des, grad=False)                    # the objective itself is fine
     oc, _, oF = CppOracle("lv_fishing", Oracle(models.lotka_volterra_fishing(), 1, "ros2", 4)).evaluate(des, grad=False)
     assert rel(F, oF) < RTOL and rel(c, oc) < RTOL
+
+
+def test_argmin_record_and_gathered_reduction(built_library):
+    """The multi-GPU sweep gathers one 16-byte {value, local index} record per rank (NCCL) and
+    reduces them with one small kernel; here the ranks' records are fabricated on one GPU."""
+    import torch
+    ctx = make_problem("lv_fishing", D.FisherDCriterion).context()
+    des = random_designs("lv_fishing", 71, 4096, 21)
+    c, _, _ = ctx.evaluate(des, grad=False, fim=False)
+    rec = torch.empty(2, dtype=torch.int64, device="cuda")
+    ctx.argmin_record_async(rec)
+    ctx.sync()
+    assert int(rec[1]) == int(np.argmin(c)) and float(rec[:1].view(torch.float64)[0]) == float(np.min(c))
+    world, shard = 5, 4096
+    vals = np.array([0.5, -2.0, np.nan, -2.0, 1.0])
+    idxs = np.array([7, 100, 3, 5, -1])
+    gat = torch.from_numpy(np.stack([vals.view(np.int64), idxs], axis=1).copy()).cuda()
+    out = torch.empty(3, dtype=torch.int64, device="cuda")
+    ctx.argmin_gathered(gat, world, shard, out)
+    ctx.sync()
+    o = out.cpu().numpy()
+    assert o[:1].view(np.float64)[0] == -2.0 and o[1] == 1 * shard + 100 and o[2] == 1   # tie -> smaller global index
+    # history ring: the records of the last few batches, oldest first, also across the ring's wrap
+    mins = []
+    for k in range(70):
+        sub = des[37 * k % 3000: 37 * k % 3000 + 512]
+        ck, _, _ = ctx.evaluate(sub, grad=False, fim=False)
+        mins.append((float(np.min(ck)), int(np.argmin(ck))))
+    hist = torch.empty((6, 2), dtype=torch.int64, device="cuda")
+    ctx.argmin_history_async(6, hist)
+    ctx.sync()
+    h = hist.cpu().numpy()
+    for row, (v, i) in zip(h, mins[-6:]):
+        assert row[:1].view(np.float64)[0] == v and row[1] == i
+    # two "ranks" x 6 gathered batches in one reduction
+    g2 = torch.stack([hist, hist]).contiguous()
+    out2 = torch.empty((6, 3), dtype=torch.int64, device="cuda")
+    ctx.argmin_gathered(g2, 2, 512, out2, groups=6)
+    ctx.sync()
+    o2 = out2.cpu().numpy()
+    for row, (v, i) in zip(o2, mins[-6:]):
+        assert row[:1].view(np.float64)[0] == v and row[1] == i and row[2] == 0
