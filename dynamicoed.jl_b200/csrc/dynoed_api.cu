@@ -33,6 +33,7 @@ struct ModelEntry {
                           size_t smem, cudaStream_t st);
     cudaError_t (*attrs)(int method, bool grad, bool ucoef, int block, size_t smem, cudaFuncAttributes* fa,
                          int* blocks_per_sm);
+    cudaError_t (*info_gain)(const EvalParams& P, const double* X, double* Pout, double* Piout, cudaStream_t st);
 };
 
 template <class M, class Tab, bool GRAD, bool UC>
@@ -118,6 +119,14 @@ static cudaError_t attrs_model(int method, bool grad, bool uc, int block, size_t
 }
 
 template <class M>
+static cudaError_t info_gain_model(const EvalParams& P, const double* X, double* Pout, double* Piout,
+                                   cudaStream_t st) {
+    const long long total = P.n * (P.n_intervals + 1);
+    info_gain_kernel<M><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(P, X, Pout, Piout);
+    return cudaGetLastError();
+}
+
+template <class M>
 static ModelEntry make_entry() {
     static_assert(M::NX <= kMaxX && M::NX * M::NP <= kMaxG && M::NTH <= kMaxTheta, "model too large");
     static_assert(M::NCTRL <= kMaxCtrl && M::NOBS <= kMaxObs && M::NIC <= kMaxIC, "model too large");
@@ -136,6 +145,7 @@ static ModelEntry make_entry() {
     for (int k = 0; k < M::NTH; ++k) i.theta[k] = M::default_theta()[k];
     e.launch = &launch_model<M>;
     e.attrs = &attrs_model<M>;
+    e.info_gain = &info_gain_model<M>;
     return e;
 }
 
@@ -835,6 +845,52 @@ int dynoed_trajectory(dynoed_ctx* ctx, const double* designs, int64_t n, double*
     }
     cudaFree(dd); cudaFree(dx); cudaFree(dc);
     return rc;
+}
+
+int dynoed_information_gain(dynoed_ctx* ctx, const double* designs, int64_t n, double* F, double* Pl, double* Pi) {
+    if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    if (!designs || n <= 0 || (!Pl && !Pi && !F)) return fail(ctx, DYNOED_EINVAL, "bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    const auto& mi = ctx->model->info;
+    const int N = ctx->n_intervals;
+    const size_t xrow = (size_t)(N + 1) * (mi.nz + mi.nF);
+    const size_t prow = (size_t)(N + 1) * mi.n_obs * mi.np * mi.np;
+    const int kd = ptr_kind(designs);
+    if ((F && ptr_kind(F) != kd) || (Pl && ptr_kind(Pl) != kd) || (Pi && ptr_kind(Pi) != kd))
+        return fail(ctx, DYNOED_EINVAL, "all pointers must be host or all device");
+    double *dd = nullptr, *dx = nullptr, *dc = nullptr, *dP = nullptr, *dPi = nullptr, *dF = nullptr;
+    int rc = DYNOED_OK;
+    auto cleanup = [&]() { cudaFree(dd); cudaFree(dx); cudaFree(dc); cudaFree(dF); if (kd == 0) { cudaFree(dP); cudaFree(dPi); } };
+#define CUI(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); \
+        return fail(ctx, DYNOED_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+    CUI(cudaMalloc(&dx, sizeof(double) * n * xrow));
+    CUI(cudaMalloc(&dc, sizeof(double) * n));
+    CUI(cudaMalloc(&dF, sizeof(double) * n * mi.nF));
+    const double* ddes = designs;
+    if (kd == 0) {
+        CUI(cudaMalloc(&dd, sizeof(double) * n * ctx->n_var));
+        CUI(cudaMemcpyAsync(dd, designs, sizeof(double) * n * ctx->n_var, cudaMemcpyHostToDevice, ctx->stream));
+        ddes = dd;
+        if (Pl) CUI(cudaMalloc(&dP, sizeof(double) * n * prow));
+        if (Pi) CUI(cudaMalloc(&dPi, sizeof(double) * n * prow));
+    } else { dP = Pl; dPi = Pi; }
+    rc = eval_device(ctx, ddes, n, dc, nullptr, dF, dx);     // trajectory at the grid points + F(t_f)
+    if (rc) { cleanup(); return rc; }
+    EvalParams P = ctx->base;
+    P.designs = ddes; P.n = n;
+    CUI(ctx->model->info_gain(P, dx, dP, dPi, ctx->stream));
+    ctx->launches++;
+    if (kd == 0) {
+        if (F) CUI(cudaMemcpyAsync(F, dF, sizeof(double) * n * mi.nF, cudaMemcpyDeviceToHost, ctx->stream));
+        if (Pl) CUI(cudaMemcpyAsync(Pl, dP, sizeof(double) * n * prow, cudaMemcpyDeviceToHost, ctx->stream));
+        if (Pi) CUI(cudaMemcpyAsync(Pi, dPi, sizeof(double) * n * prow, cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (F) {
+        CUI(cudaMemcpyAsync(F, dF, sizeof(double) * n * mi.nF, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    CUI(cudaStreamSynchronize(ctx->stream));
+#undef CUI
+    cleanup();
+    return DYNOED_OK;
 }
 
 int dynoed_criterion_batch(int device, int criterion, int np, const double* F, const double* tau, int64_t batch,

@@ -826,6 +826,95 @@ __global__ void argmin_records_kernel(const long long* __restrict__ rec, int wor
 }
 
 // ----------------------------------------------------------------------------------------------
+// Local information gain (/root/reference/src/utilities.jl:47-70): at every merged-grid point t_j
+// and for every observed function i,  P_i(t_j) = Q_i^T Q_i  with Q = h_x G  (np x np, rank one) and
+// Pi_i(t_j) = F^-1 P_i F^-1  with F = F(t_f) (no regularisation, as in the reference).
+// One thread per (design, grid point); X is the trajectory the evaluation kernel wrote
+// ([n][N+1][NZ+NF]).  F^-1 by Gauss-Jordan with partial pivoting in registers; a singular F
+// yields Inf/NaN (data, not an error).
+// ----------------------------------------------------------------------------------------------
+template <class M>
+__global__ void info_gain_kernel(const EvalParams P, const double* __restrict__ X, double* __restrict__ Pout,
+                                 double* __restrict__ Piout) {
+    constexpr int NX = M::NX, NP = M::NP, NZ = M::NZ, NF = M::NF, NOBS = M::NOBS, NCTRL = M::NCTRL;
+    constexpr int NCU = NCTRL > 0 ? NCTRL : 1;
+    const int N = P.n_intervals;
+    const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (gid >= P.n * (N + 1)) return;
+    const long long g = gid / (N + 1);
+    const int j = (int)(gid % (N + 1));
+    const double* xs = X + ((size_t)g * (N + 1) + j) * (NZ + NF);
+    const double* xf = X + ((size_t)g * (N + 1) + N) * (NZ + NF) + NZ;
+    double z[NZ];
+#pragma unroll
+    for (int a = 0; a < NZ; ++a) z[a] = xs[a];
+    const int jj = j < N ? j : N - 1;    // controls are piecewise constant: interval starting at t_j
+    double u[NCU], c[M::NCONST], Q[NOBS * NP];
+#pragma unroll
+    for (int k = 0; k < NCTRL; ++k)
+        u[k] = P.designs[g * P.n_var + P.ctrl_off[k] + __ldg(P.indicators + k * N + jj)];
+    M::consts(u, P.theta, c);
+    const double t = j < N ? __ldg(P.step_t + __ldg(P.first_step + j)) : 0.0;
+    M::obs(t, z, u, P.theta, c, Q);
+    // F^-1
+    double A[NP][NP], B[NP][NP];
+#pragma unroll
+    for (int a = 0; a < NP; ++a)
+#pragma unroll
+        for (int b = 0; b < NP; ++b) { A[a][b] = xf[tri(a, b)]; B[a][b] = a == b ? 1.0 : 0.0; }
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        int p = k;
+        double best = fabs(A[k][k]);
+#pragma unroll
+        for (int i = k + 1; i < NP; ++i)
+            if (fabs(A[i][k]) > best) { best = fabs(A[i][k]); p = i; }
+#pragma unroll
+        for (int i = k + 1; i < NP; ++i) {
+            if (p == i) {
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    double tmp = A[k][q]; A[k][q] = A[i][q]; A[i][q] = tmp;
+                    tmp = B[k][q]; B[k][q] = B[i][q]; B[i][q] = tmp;
+                }
+            }
+        }
+        const double inv = 1.0 / A[k][k];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) { A[k][q] *= inv; B[k][q] *= inv; }
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            if (i != k) {
+                const double l = A[i][k];
+#pragma unroll
+                for (int q = 0; q < NP; ++q) { A[i][q] = fma(-l, A[k][q], A[i][q]); B[i][q] = fma(-l, B[k][q], B[i][q]); }
+            }
+        }
+    }
+    double* po = Pout ? Pout + (size_t)gid * NOBS * NP * NP : nullptr;
+    double* pio = Piout ? Piout + (size_t)gid * NOBS * NP * NP : nullptr;
+#pragma unroll
+    for (int i = 0; i < NOBS; ++i) {
+        double v[NP];   // F^-1 Q_i^T  (F^-1 symmetric) => Pi_i = v v^T
+#pragma unroll
+        for (int a = 0; a < NP; ++a) {
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < NP; ++b) s = fma(B[a][b], Q[i * NP + b], s);
+            v[a] = s;
+        }
+#pragma unroll
+        for (int a = 0; a < NP; ++a)
+#pragma unroll
+            for (int b = 0; b < NP; ++b) {
+                if (po) po[(i * NP + a) * NP + b] = Q[i * NP + a] * Q[i * NP + b];
+                if (pio) pio[(i * NP + a) * NP + b] = v[a] * v[b];
+            }
+    }
+    (void)NX;
+}
+
+// ----------------------------------------------------------------------------------------------
 // Criteria on caller-supplied matrices (host API `criterion(F, tau)`, fisher.jl:12-15): one
 // matrix per thread, runtime n, Jacobi in local memory.  Not a hot path.
 // ----------------------------------------------------------------------------------------------

@@ -60,7 +60,7 @@ EXPORTS = ["dynoed_abi_version", "dynoed_model_count", "dynoed_model_name", "dyn
            "dynoed_argmin_async", "dynoed_argmin_record_async", "dynoed_argmin_history_async",
            "dynoed_argmin_gathered",
            "dynoed_set_profiling", "dynoed_kernel_time",
-           "dynoed_trajectory", "dynoed_criterion_batch", "dynoed_fp64_peak", "dynoed_fp64_microbench",
+           "dynoed_trajectory", "dynoed_information_gain", "dynoed_criterion_batch", "dynoed_fp64_peak", "dynoed_fp64_microbench",
            "dynoed_kernel_stats_query", "dynoed_host_alloc", "dynoed_host_free",
            "dynoed_last_error"]
 
@@ -98,6 +98,7 @@ def lib(path: str | None = None):
         L.dynoed_set_profiling.argtypes = [vp, C.c_int]
         L.dynoed_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         L.dynoed_trajectory.argtypes = [vp, dp, i64, dp]
+        L.dynoed_information_gain.argtypes = [vp, dp, i64, dp, dp, dp]
         L.dynoed_criterion_batch.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, i64, dp, dp]
         L.dynoed_fp64_peak.argtypes = [C.c_int, vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.dynoed_fp64_microbench.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
@@ -261,6 +262,17 @@ class Context:
         X = np.empty((n, self.n_intervals + 1, self.info.nz + self.info.nF))
         _check(self._L.dynoed_trajectory(self._h, _ptr(designs), n, _ptr(X)), self._h, self._L)
         return X
+
+    def information_gain(self, designs):
+        """(F [n, nF], P [n, N+1, n_obs, np, np], Pi same shape) — utilities.jl:47-70 at the grid points."""
+        designs = np.ascontiguousarray(np.atleast_2d(designs), dtype=np.float64)
+        n, mi = designs.shape[0], self.info
+        F = np.empty((n, mi.nF))
+        P = np.empty((n, self.n_intervals + 1, mi.n_obs, mi.np, mi.np))
+        Pi = np.empty_like(P)
+        _check(self._L.dynoed_information_gain(self._h, _ptr(designs), n, _ptr(F), _ptr(P), _ptr(Pi)),
+               self._h, self._L)
+        return F, P, Pi
 
     def kernel_stats(self, with_grad=True) -> dict:
         ks = KernelStats()

@@ -150,6 +150,14 @@ int dynoed_argmin_gathered(dynoed_ctx* ctx, const void* d_records, int world, in
  * X[k] is [N+1][nz+nF] row-major (state order [x; vec(G); F_triu], augment.jl:240) */
 int dynoed_trajectory(dynoed_ctx* ctx, const double* designs, int64_t n, double* X);
 
+/* compute_information_gain (/root/reference/src/utilities.jl:47-70) at the merged-grid points:
+ *   F  [n][nF]                       packed F(t_f)
+ *   P  [n][N+1][n_obs][np][np]       local information gain  P_i(t_j) = Q_i^T Q_i,  Q = h_x G
+ *   Pi [n][N+1][n_obs][np][np]       F^-1 P_i(t_j) F^-1
+ * any of F / P / Pi may be NULL.  Blocking; host or device pointers (all of one kind). */
+int dynoed_information_gain(dynoed_ctx* ctx, const double* designs, int64_t n, double* F, double* P,
+                            double* Pi);
+
 /* criterion(F, tau) on caller-supplied packed symmetric matrices (fisher.jl:12-15):
  * value[k] = c(Symmetric(F_k + tau_k I)); dcdF (optional) = packed d c / d F.  np <= 24. */
 int dynoed_criterion_batch(int device, int criterion, int np, const double* F_packed,

@@ -431,3 +431,34 @@ def test_argmin_record_and_gathered_reduction(built_library):
     o2 = out2.cpu().numpy()
     for row, (v, i) in zip(o2, mins[-6:]):
         assert row[:1].view(np.float64)[0] == v and row[1] == i and row[2] == 0
+
+
+@pytest.mark.parametrize("name", ["lv_fishing", "readme", "lv_ic"])
+def test_information_gain_matches_oracle(name, oracles, built_library):
+    """compute_information_gain (/root/reference/src/utilities.jl:47-70) at the merged-grid points:
+    P_i(t_j) = Q_i^T Q_i with Q = h_x G from the oracle's trajectory, Pi = F^-1 P F^-1."""
+    from oracle.oed_oracle import symmetric_from_vector
+    ctx = make_problem(name, D.FisherACriterion).context()
+    orc = oracles(name, 0, "rk4", 4)
+    o = orc.o                                            # the numpy oracle (for Q = h_x G)
+    des = random_designs(name, ctx.n_var, 5, 31)
+    F, P, Pi = ctx.information_gain(des)
+    nx, np_, nobs, N = o.nxd, o.np_, o.n_obs, o.N
+    nc = len(o.controls)
+    for d in range(len(des)):
+        X = orc.trajectory(des[d])                       # [n_aug, N+1]
+        Ff = symmetric_from_vector(X[nx + nx * np_:, -1])
+        assert rel(F[d], X[nx + nx * np_:, -1]) < RTOL
+        Finv = np.linalg.inv(Ff)
+        for j in range(N + 1):
+            jj = min(j, N - 1)
+            u = [np.array([des[d, o.layout.control_offsets[c] + int(o.grid.indicators[c, jj]) - 1]])
+                 for c in range(nc)]
+            z = [np.array([v]) for v in X[:, j]]
+            _, Q = o.rhs(o.grid.tpoints[jj], z, u, [np.array([0.0])] * nobs)
+            Q = np.array([[float(np.asarray(q).reshape(-1)[0]) for q in row] for row in Q])   # [nobs, np]
+            for i in range(nobs):
+                Pref = np.outer(Q[i], Q[i])
+                assert np.max(np.abs(P[d, j, i] - Pref)) <= RTOL * max(np.max(np.abs(Pref)), 1e-300)
+                Piref = Finv @ Pref @ Finv
+                assert np.max(np.abs(Pi[d, j, i] - Piref)) <= 1e-8 * max(np.max(np.abs(Piref)), 1e-300)
