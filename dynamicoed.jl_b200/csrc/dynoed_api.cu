@@ -190,6 +190,8 @@ struct dynoed_ctx {
     int criterion = 0;
     int n_intervals = 0, n_steps = 0, n_var = 0, tile = 128;
     int sm_count = 0;
+    size_t smem_optin = 0, smem_per_sm = 0;
+    int w_len[kMaxObs] = {0};   // length of each measurement-weight block of the design vector
     bool ucoef = false;    // step coefficients served from the constant bank (uniform registers)
     bool rosenbrock = false;
     int bps[2] = {0, 0};   // blocks per SM without / with gradient
@@ -341,6 +343,7 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
         const int off = v < mi.n_ctrl ? d->ctrl_offsets[v] : d->w_offsets[v - mi.n_ctrl];
         if (off < 0 || off + len[v] > d->n_var) return fail(nullptr, DYNOED_EINVAL, "design layout exceeds n_var");
     }
+    std::vector<int> w_len_tmp(len.begin() + mi.n_ctrl, len.end());
     if (mi.n_ic && (d->ic_offset < 0 || d->ic_offset + mi.n_ic > d->n_var))
         return fail(nullptr, DYNOED_EINVAL, "ic_offset out of range");
     for (int j = 0; j < N; ++j)
@@ -357,6 +360,7 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     ctx->n_intervals = N;
     ctx->n_var = d->n_var;
     ctx->tile = tile;
+    for (int i = 0; i < mi.n_obs; ++i) ctx->w_len[i] = w_len_tmp[i];
 
     // step tables: t and h per step, same arithmetic as the oracle.  Uniform substeps: h = L/m per
     // merged interval — unless the merged grid is uniform up to rounding (all L_j/m within 64 ulp
@@ -411,6 +415,8 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     cudaDeviceProp prop;
     CUC(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    ctx->smem_per_sm = prop.sharedMemPerMultiprocessor;
     CUC(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     CUC(cudaMalloc(&ctx->d_first_step, sizeof(int) * (N + 1)));
@@ -889,6 +895,90 @@ int dynoed_information_gain(dynoed_ctx* ctx, const double* designs, int64_t n, d
     }
     CUI(cudaStreamSynchronize(ctx->stream));
 #undef CUI
+    cleanup();
+    return DYNOED_OK;
+}
+
+int dynoed_fim_basis(dynoed_ctx* ctx, const double* design, double* basis) {
+    if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    if (!design || !basis) return fail(ctx, DYNOED_EINVAL, "bad arguments");
+    if (ptr_kind(design) != 0 || ptr_kind(basis) != 0) return fail(ctx, DYNOED_EINVAL, "host pointers expected");
+    const auto& mi = ctx->model->info;
+    const int nv = ctx->n_var, nF = mi.nF;
+    // one unit-weight design per weight column; every other weight zero, controls / ICs as given
+    std::vector<int> cols;
+    for (int i = 0; i < mi.n_obs; ++i)
+        for (int k = 0; k < ctx->w_len[i]; ++k) cols.push_back(ctx->base.w_off[i] + k);
+    std::vector<double> batch(cols.size() * (size_t)nv), crit(cols.size()), fim(cols.size() * (size_t)nF);
+    for (size_t r = 0; r < cols.size(); ++r) {
+        double* row = batch.data() + r * nv;
+        memcpy(row, design, sizeof(double) * nv);
+        for (int c : cols) row[c] = 0.0;
+        row[cols[r]] = 1.0;
+    }
+    int rc = eval_common(ctx, batch.data(), (int64_t)cols.size(), crit.data(), nullptr, fim.data(), true, true);
+    if (rc) return rc;
+    memset(basis, 0, sizeof(double) * (size_t)nv * nF);
+    for (size_t r = 0; r < cols.size(); ++r) memcpy(basis + (size_t)cols[r] * nF, fim.data() + r * nF, sizeof(double) * nF);
+    return DYNOED_OK;
+}
+
+int dynoed_eval_fixed_controls(dynoed_ctx* ctx, const double* basis, const double* designs, int64_t n, double* crit,
+                               double* grad, double* fim) {
+    if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    if (!basis || !designs || !crit || n <= 0) return fail(ctx, DYNOED_EINVAL, "bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    const auto& mi = ctx->model->info;
+    const int nv = ctx->n_var, nF = mi.nF;
+    const int kd = ptr_kind(designs);
+    if (ptr_kind(crit) != kd || (grad && ptr_kind(grad) != kd) || (fim && ptr_kind(fim) != kd))
+        return fail(ctx, DYNOED_EINVAL, "designs/crit/grad/fim must all be host or all be device pointers");
+    if (mi.np > 6) return fail(ctx, DYNOED_EUNSUPPORTED, "np > 6");
+    cudaStream_t st = ctx->stream;
+    double *db = nullptr, *dd = nullptr, *dc = nullptr, *dg = nullptr, *df = nullptr;
+    auto cleanup = [&]() { cudaFree(db); cudaFree(dd); cudaFree(dc); cudaFree(dg); cudaFree(df); };
+#define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); \
+        return fail(ctx, DYNOED_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+    const double* bdev = basis;
+    if (ptr_kind(basis) == 0) {
+        CUF(cudaMalloc(&db, sizeof(double) * nv * nF));
+        CUF(cudaMemcpyAsync(db, basis, sizeof(double) * nv * nF, cudaMemcpyHostToDevice, st));
+        bdev = db;
+    }
+    const double* ddes = designs; double *dcr = crit, *dgr = grad, *dfi = fim;
+    if (kd == 0) {
+        CUF(cudaMalloc(&dd, sizeof(double) * n * nv)); CUF(cudaMalloc(&dc, sizeof(double) * n));
+        if (grad) CUF(cudaMalloc(&dg, sizeof(double) * n * nv));
+        if (fim) CUF(cudaMalloc(&df, sizeof(double) * n * nF));
+        CUF(cudaMemcpyAsync(dd, designs, sizeof(double) * n * nv, cudaMemcpyHostToDevice, st));
+        ddes = dd; dcr = dc; dgr = dg; dfi = df;
+    }
+    const int block = 256;
+    const size_t smem = 128 + sizeof(double) * ((size_t)kFcTile * nv + (size_t)nv * nF);
+    if (smem > ctx->smem_optin) { cleanup(); return fail(ctx, DYNOED_EUNSUPPORTED, "design rows too long for the fixed-controls kernel"); }
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, ctx->smem_per_sm / (smem + 1024)));
+    const int64_t ntiles = (n + kFcTile - 1) / kFcTile;
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * per_sm);
+    const int use_tma = (reinterpret_cast<uintptr_t>(ddes) % 16 == 0 && (!dgr || reinterpret_cast<uintptr_t>(dgr) % 16 == 0) &&
+                         ((size_t)kFcTile * nv * 8) % 16 == 0) ? 1 : 0;
+    switch (mi.np) {
+#define DYNOED_FC(NPV) case NPV: { auto kern = fixed_controls_kernel<NPV>; \
+        CUF(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<grid, block, smem, st>>>(ddes, bdev, n, nv, ctx->base.tau_off, ctx->criterion, use_tma, dcr, dgr, dfi); } break;
+        DYNOED_FC(1) DYNOED_FC(2) DYNOED_FC(3) DYNOED_FC(4) DYNOED_FC(5) DYNOED_FC(6)
+#undef DYNOED_FC
+    }
+    CUF(cudaGetLastError());
+    ctx->launches++;
+    if (kd == 0) {
+        CUF(cudaMemcpyAsync(crit, dc, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+        if (grad) CUF(cudaMemcpyAsync(grad, dg, sizeof(double) * n * nv, cudaMemcpyDeviceToHost, st));
+        if (fim) CUF(cudaMemcpyAsync(fim, df, sizeof(double) * n * nF, cudaMemcpyDeviceToHost, st));
+        CUF(cudaStreamSynchronize(st));
+    } else if (db) {
+        CUF(cudaStreamSynchronize(st));
+    }
+#undef CUF
     cleanup();
     return DYNOED_OK;
 }

@@ -915,6 +915,115 @@ __global__ void info_gain_kernel(const EvalParams P, const double* __restrict__ 
 }
 
 // ----------------------------------------------------------------------------------------------
+// Fixed-controls shortcut (the integer / branch-and-bound batch mode): with
+// controls and initial conditions frozen, F(t_f) = sum_k w_k B_k is LINEAR in the measurement
+// weights (/root/reference/src/augment.jl:223-226: nothing depends on F), so a whole batch of
+// measurement designs needs no integration at all:  F = designs[n][n_var] x basis[n_var][NF]
+// (basis rows are zero for non-weight columns), then the criterion and
+// d objective / d w_k = <Lambda, B_k>.  Pure HBM streaming: tiles of 64 rows staged by TMA bulk
+// copies, one warp per design row, gradients written over the rows in shared memory and stored
+// by one TMA bulk copy; basis in shared memory.  HBM roofline: 8 (2 n_var + 1) bytes per design.
+// ----------------------------------------------------------------------------------------------
+constexpr int kFcTile = 64;   // design rows per TMA-staged tile of the fixed-controls kernel
+
+template <int NP>
+__global__ void __launch_bounds__(256) fixed_controls_kernel(const double* __restrict__ designs,
+                                                             const double* __restrict__ basis, long long n,
+                                                             int n_var, int tau_off, int criterion, int use_tma,
+                                                             double* __restrict__ crit, double* __restrict__ grad,
+                                                             double* __restrict__ fim) {
+    constexpr int NF = NP * (NP + 1) / 2;
+    extern __shared__ __align__(128) unsigned char fc_smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(fc_smem);
+    double* tile_buf = reinterpret_cast<double*>(fc_smem + 128);            // [kFcTile][n_var]
+    double* sb = tile_buf + (size_t)kFcTile * n_var;                         // [n_var][NF]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    for (int i = tid; i < n_var * NF; i += blockDim.x) sb[i] = basis[i];
+    if (tid == 0 && use_tma) mbar_init(bar, 1);
+    __syncthreads();
+    uint32_t phase = 0;
+    const long long ntiles = (n + kFcTile - 1) / kFcTile;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long g0 = tile * kFcTile;
+        const int count = (int)((n - g0 < kFcTile) ? (n - g0) : kFcTile);
+        const uint32_t bytes = (uint32_t)count * n_var * 8u;
+        const bool tma_ok = use_tma && (bytes % 16u == 0);
+        if (tma_ok) {
+            if (tid == 0) {
+                mbar_expect_tx(bar, bytes);
+                tma_load_1d(tile_buf, designs + g0 * n_var, bytes, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+        } else {
+            for (int i = tid; i < count * n_var; i += blockDim.x) tile_buf[i] = designs[g0 * n_var + i];
+            __syncthreads();
+        }
+        for (int r = warp; r < count; r += nwarp) {      // one warp per design row
+            double* row = tile_buf + (size_t)r * n_var;
+            double F[NF];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) F[f] = 0.0;
+            for (int k = lane; k < n_var; k += 32) {
+                const double v = row[k];
+#pragma unroll
+                for (int f = 0; f < NF; ++f) F[f] = fma(v, sb[k * NF + f], F[f]);
+            }
+#pragma unroll
+            for (int f = 0; f < NF; ++f)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) F[f] += __shfl_xor_sync(0xffffffffu, F[f], o);
+            const double tau = row[tau_off];
+            double value, L[NF];
+            criterion_eval<NP>(F, tau, criterion, value, L);
+            if (lane == 0) {
+                crit[g0 + r] = value + tau;
+                if (fim) {
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) fim[(g0 + r) * NF + f] = F[f];
+                }
+            }
+            if (grad) {
+                double Ls[NF], trL = 1.0;
+#pragma unroll
+                for (int j = 0; j < NP; ++j)
+#pragma unroll
+                    for (int i = 0; i <= j; ++i) {
+                        Ls[tri(i, j)] = (i == j ? 1.0 : 2.0) * L[tri(i, j)];
+                        if (i == j) trL += L[tri(i, j)];
+                    }
+                __syncwarp();                              // every lane has read tau before it is overwritten
+                for (int k = lane; k < n_var; k += 32) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) s = fma(Ls[f], sb[k * NF + f], s);
+                    row[k] = k == tau_off ? trL : s;       // gradients overwrite the row in place
+                }
+            }
+        }
+        if (grad) {
+            double* dst = grad + g0 * n_var;
+            if (tma_ok) {
+                fence_proxy_async();
+                __syncthreads();
+                if (tid == 0) {
+                    tma_store_1d(dst, tile_buf, bytes);
+                    tma_store_wait_read();
+                }
+                __syncthreads();
+            } else {
+                __syncthreads();
+                for (int i = tid; i < count * n_var; i += blockDim.x) dst[i] = tile_buf[i];
+                __syncthreads();
+            }
+        } else {
+            __syncthreads();
+        }
+    }
+    if (tid == 0 && use_tma) tma_store_wait_all();
+}
+
+// ----------------------------------------------------------------------------------------------
 // Criteria on caller-supplied matrices (host API `criterion(F, tau)`, fisher.jl:12-15): one
 // matrix per thread, runtime n, Jacobi in local memory.  Not a hot path.
 // ----------------------------------------------------------------------------------------------

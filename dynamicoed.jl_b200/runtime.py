@@ -60,7 +60,8 @@ EXPORTS = ["dynoed_abi_version", "dynoed_model_count", "dynoed_model_name", "dyn
            "dynoed_argmin_async", "dynoed_argmin_record_async", "dynoed_argmin_history_async",
            "dynoed_argmin_gathered",
            "dynoed_set_profiling", "dynoed_kernel_time",
-           "dynoed_trajectory", "dynoed_information_gain", "dynoed_criterion_batch", "dynoed_fp64_peak", "dynoed_fp64_microbench",
+           "dynoed_trajectory", "dynoed_information_gain", "dynoed_fim_basis",
+           "dynoed_eval_fixed_controls", "dynoed_criterion_batch", "dynoed_fp64_peak", "dynoed_fp64_microbench",
            "dynoed_kernel_stats_query", "dynoed_host_alloc", "dynoed_host_free",
            "dynoed_last_error"]
 
@@ -99,6 +100,8 @@ def lib(path: str | None = None):
         L.dynoed_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         L.dynoed_trajectory.argtypes = [vp, dp, i64, dp]
         L.dynoed_information_gain.argtypes = [vp, dp, i64, dp, dp, dp]
+        L.dynoed_fim_basis.argtypes = [vp, dp, dp]
+        L.dynoed_eval_fixed_controls.argtypes = [vp, dp, dp, i64, dp, dp, dp]
         L.dynoed_criterion_batch.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, i64, dp, dp]
         L.dynoed_fp64_peak.argtypes = [C.c_int, vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.dynoed_fp64_microbench.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
@@ -273,6 +276,20 @@ class Context:
         _check(self._L.dynoed_information_gain(self._h, _ptr(designs), n, _ptr(F), _ptr(P), _ptr(Pi)),
                self._h, self._L)
         return F, P, Pi
+
+    def fim_basis(self, design):
+        """basis [n_var, nF]: F(t_f) per unit measurement weight, controls / ICs taken from `design`."""
+        design = np.ascontiguousarray(np.asarray(design, dtype=np.float64).reshape(self.n_var))
+        basis = np.empty((self.n_var, self.info.nF))
+        _check(self._L.dynoed_fim_basis(self._h, _ptr(design), _ptr(basis)), self._h, self._L)
+        return basis
+
+    def eval_fixed_controls(self, basis, designs, crit, grad=None, fim=None, n=None):
+        """Objective / gradient / F for measurement designs that share the controls of `basis`
+        (numpy arrays or torch CUDA tensors, like `eval_batch`)."""
+        n = int(designs.shape[0]) if n is None else int(n)
+        _check(self._L.dynoed_eval_fixed_controls(self._h, _ptr(basis), _ptr(designs), n, _ptr(crit),
+                                                  _ptr(grad), _ptr(fim)), self._h, self._L)
 
     def kernel_stats(self, with_grad=True) -> dict:
         ks = KernelStats()

@@ -158,6 +158,16 @@ int dynoed_trajectory(dynoed_ctx* ctx, const double* designs, int64_t n, double*
 int dynoed_information_gain(dynoed_ctx* ctx, const double* designs, int64_t n, double* F, double* P,
                             double* Pi);
 
+/* Fixed-controls shortcut for batches of MEASUREMENT designs (integer / branch-and-bound mode,
+ * /root/reference/src/problem.jl:137-146; F is linear in w, /root/reference/src/augment.jl:223-226):
+ * dynoed_fim_basis integrates once per weight column with the controls / initial conditions of
+ * `design` (host, one row) and returns basis[n_var][nF] (zero rows for non-weight columns);
+ * dynoed_eval_fixed_controls then evaluates  F = designs x basis, the objective and its gradient
+ * w.r.t. weights and tau (control / IC entries of grad are 0) with one HBM-streaming kernel. */
+int dynoed_fim_basis(dynoed_ctx* ctx, const double* design, double* basis);
+int dynoed_eval_fixed_controls(dynoed_ctx* ctx, const double* basis, const double* designs, int64_t n,
+                               double* crit, double* grad, double* fim);
+
 /* criterion(F, tau) on caller-supplied packed symmetric matrices (fisher.jl:12-15):
  * value[k] = c(Symmetric(F_k + tau_k I)); dcdF (optional) = packed d c / d F.  np <= 24. */
 int dynoed_criterion_batch(int device, int criterion, int np, const double* F_packed,

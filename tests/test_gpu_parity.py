@@ -462,3 +462,31 @@ def test_information_gain_matches_oracle(name, oracles, built_library):
                 assert np.max(np.abs(P[d, j, i] - Pref)) <= RTOL * max(np.max(np.abs(Pref)), 1e-300)
                 Piref = Finv @ Pref @ Finv
                 assert np.max(np.abs(Pi[d, j, i] - Piref)) <= 1e-8 * max(np.max(np.abs(Piref)), 1e-300)
+
+
+def test_fixed_controls_shortcut_matches_full_evaluation(oracles, built_library):
+    """Integer / branch-and-bound batch mode (problem.jl:137-146): with the controls frozen, F is
+    linear in the weights, so F = designs x basis.  The shortcut must reproduce the full
+    integration (objective, F, d/dw, d/dtau) for {0,1} and relaxed measurement designs."""
+    import torch
+    for crit_cls in (D.FisherDCriterion, D.ACriterion, D.FisherECriterion):
+        ctx = make_problem("lv_fishing", crit_cls).context()
+        rng = np.random.Generator(np.random.Philox(41))
+        base = random_designs("lv_fishing", 71, 1, 5)[0]
+        basis = ctx.fim_basis(base)
+        assert np.all(basis[:10] == 0.0) and np.all(basis[70] == 0.0) and np.all(np.any(basis[10:70] != 0.0, axis=1))
+        n = 3000
+        des = np.tile(base, (n, 1))
+        des[:, 10:70] = rng.random((n, 60))
+        des[: n // 2, 10:70] = (des[: n // 2, 10:70] > 0.7).astype(np.float64)      # integer designs
+        des[:, 70] = 1e-3 + 0.9 * rng.random(n)
+        c, g, F = ctx.evaluate(des)                                                # full integration
+        c2, g2, F2 = np.empty(n), np.empty((n, 71)), np.empty((n, 3))
+        ctx.eval_fixed_controls(basis, des, c2, g2, F2)                            # host buffers
+        assert rel(F2, F) < RTOL and rel(c2, c) < RTOL
+        assert rel_rows(g2[:, 10:], g[:, 10:]) < RTOL and np.all(g2[:, :10] == 0.0)
+        d = torch.from_numpy(des).cuda()                                           # device buffers
+        dc = torch.empty(n, dtype=torch.float64, device="cuda"); dg = torch.empty_like(d)
+        ctx.eval_fixed_controls(torch.from_numpy(basis).cuda(), d, dc, dg, None)
+        ctx.sync()
+        assert np.array_equal(dc.cpu().numpy(), c2) and np.array_equal(dg.cpu().numpy(), g2)
