@@ -251,7 +251,7 @@ __device__ __forceinline__ void rosenbrock_step(double t, double h, T (&z)[M::NZ
 // P.traj is used as the per-interval quadrature scratch [grid][N][NOBS*NF][kMaxTile].
 // ----------------------------------------------------------------------------------------------
 template <class M, class RT, bool GRAD>
-__global__ void __launch_bounds__(kMaxTile) ros_eval_kernel(const EvalParams P) {
+__global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams P) {
     constexpr int NX = M::NX, NP = M::NP, NZ = M::NZ, NF = M::NF, NOBS = M::NOBS, NCTRL = M::NCTRL;
     constexpr int NCU = NCTRL > 0 ? NCTRL : 1, NQ = NOBS * NF;
     constexpr int KD = (GRAD && M::NIC > 0) ? M::NIC : 1;
