@@ -34,8 +34,9 @@ def build_library(out_path: str, models_dir: str | None = None, force: bool = Fa
                   verbose: bool = False) -> str:
     """Compile csrc/dynoed_api.cu against ``<models_dir>/models.cuh`` into ``out_path``."""
     models_dir = models_dir or os.path.join(CSRC, "generated")
-    srcs = [os.path.join(CSRC, "dynoed_api.cu"), os.path.join(CSRC, "dynoed_kernels.cuh"),
-            os.path.join(_HERE, "..", "include", "dynoed.h")]
+    srcs = [os.path.join(CSRC, "dynoed_api.cu")]
+    srcs += [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cuh")]
+    srcs += [os.path.join(_HERE, "..", "include", "dynoed.h")]
     srcs += [os.path.join(models_dir, f) for f in sorted(os.listdir(models_dir)) if f.endswith(".cuh")]
     if not force and _newer(out_path, srcs):
         return out_path

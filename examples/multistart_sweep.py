@@ -61,21 +61,24 @@ def main():
         li = j * args.chunk + int(rec[j, 1])
         return float(vals[j]), li
 
-    sweep(); torch.cuda.synchronize()             # warm-up (scratch allocation)
+    def whole():
+        t0 = time.perf_counter()
+        lv, li = sweep()
+        t_eval = time.perf_counter() - t0
+        val, idx, owner = multistart.global_argmin(lv, lo + li, dev)
+        row = torch.zeros(2, n_var, dtype=torch.float64, device=dev)
+        if owner == rank:
+            row[0], row[1] = designs[idx - lo], grad[idx - lo]
+        if world > 1:
+            dist.broadcast(row, src=owner)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, t_eval, val, idx, owner, row
+
+    whole()                                       # warm-up: scratch allocation, lazy module loads, NCCL
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    lv, li = sweep()
-    t_eval = time.perf_counter() - t0
-    val, idx, owner = multistart.global_argmin(lv, lo + li, dev)
-    row = torch.zeros(2, n_var, dtype=torch.float64, device=dev)
-    if owner == rank:
-        row[0], row[1] = designs[idx - lo], grad[idx - lo]
-    if world > 1:
-        dist.broadcast(row, src=owner)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    dt, t_eval, val, idx, owner, row = whole()
     if world > 1:
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
