@@ -167,6 +167,29 @@ static const ModelEntry* find_model(const char* name) {
     return nullptr;
 }
 
+// Serial number of the last evaluation launch this library put on a stream (any context).  A
+// launch may only overlap its predecessor if that predecessor is the SAME context's previous
+// launch (whose buffers it was checked against); foreign kernels in between are harmless because
+// they do not trigger programmatic completion early.
+static std::mutex g_stream_mu;
+static std::vector<std::pair<cudaStream_t, uint64_t>> g_stream_serial;
+static uint64_t g_serial = 0;
+static uint64_t stream_last_serial(cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_stream_mu);
+    for (auto& e : g_stream_serial)
+        if (e.first == st) return e.second;
+    return 0;
+}
+static uint64_t stream_new_serial(cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_stream_mu);
+    const uint64_t v = ++g_serial;
+    for (auto& e : g_stream_serial)
+        if (e.first == st) { e.second = v; return v; }
+    if (g_stream_serial.size() > 256) g_stream_serial.clear();
+    g_stream_serial.emplace_back(st, v);
+    return v;
+}
+
 constexpr int kSlots = 4;   // pipeline depth of the host-buffer path
 constexpr int kRing = 64;   // arg-min records kept for deferred (batched) multi-GPU gathers
 
@@ -220,6 +243,7 @@ struct dynoed_ctx {
     int last_parity = 0;               // scratch set that holds the most recent batch's arg-min
     struct Prev {                      // the previous device-path launch (overlap eligibility)
         bool valid = false, grad = false, full = false;
+        uint64_t serial = 0;
         cudaStream_t stream = nullptr;
         const char *in0 = nullptr, *in1 = nullptr;
         const char* out0[3] = {nullptr, nullptr, nullptr};
@@ -550,7 +574,7 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
     cur.out0[2] = (const char*)fim; cur.out1[2] = fim ? cur.out0[2] + sizeof(double) * n * mi.nF : nullptr;
     const dynoed_ctx::Prev& pv = ctx->prev;
     bool pdl = ctx->pdl_enabled && !ctx->profiling && cur.valid && pv.valid && cur.full && pv.full &&
-               cur.grad == pv.grad && cur.stream == pv.stream;
+               cur.grad == pv.grad && cur.stream == pv.stream && stream_last_serial(st) == pv.serial;
     for (int a = 0; pdl && a < 3; ++a) {
         if (ranges_overlap(cur.in0, cur.in1, pv.out0[a], pv.out1[a])) pdl = false;      // RAW
         if (ranges_overlap(cur.out0[a], cur.out1[a], pv.in0, pv.in1)) pdl = false;      // WAR
@@ -569,6 +593,7 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
     }
     CU(ctx->model->launch(ctx->method, grad != nullptr, ctx->ucoef, pdl, P, grid, ctx->tile, smem_bytes(ctx), st));
     if (ctx->profiling) { CU(cudaEventRecord(ctx->ev_k1, st)); ctx->ev_pending = true; }
+    cur.serial = stream_new_serial(st);
     ctx->prev = cur;
     ctx->launches++;
     ctx->pdl_launches += pdl ? 1 : 0;
@@ -1064,6 +1089,8 @@ int dynoed_fp64_microbench(int device, int variant, double* ginstr_per_s) {
             case 3: fp64_variant_kernel<3><<<grid, block>>>(out, iters, 1.0, 0.999999); break;
             case 4: fp64_variant_kernel<4><<<grid, block>>>(out, iters, 1.0, 0.999999); break;
             case 5: fp64_variant_kernel<5><<<grid, block>>>(out, iters, 1.0, 0.999999); break;
+            case 6: fp64_variant_kernel<6><<<grid, block>>>(out, iters, 1.0, 0.999999); break;
+            case 7: fp64_variant_kernel<7><<<grid, block>>>(out, iters, 1.0, 0.999999); break;
             default: fp64_peak_kernel<<<grid, block>>>(out, iters, 1.0); break;
         }
         CU(cudaEventRecord(e1, 0));

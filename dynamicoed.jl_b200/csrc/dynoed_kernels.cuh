@@ -1139,6 +1139,8 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
 //   1: d = fma(a, b, c) with three distinct REGISTER operands per chain
 //   2: d = fma(a, b, a)  (two distinct registers)     3: d = a * b (DMUL, two registers)
 //   4: d = a + b (DADD)                                5: d = fma(a, U, c) with U a uniform/param operand
+//   6: d = fma(B, c, d) with ONE register B shared by all chains (operand-reuse cache)
+//   7: d = fma(b, C, d) with C alternating between two registers
 template <int V>
 __global__ void __launch_bounds__(256) fp64_variant_kernel(double* out, int iters, double seed, double up) {
     double a[8], b[8], c[8];
@@ -1155,7 +1157,9 @@ __global__ void __launch_bounds__(256) fp64_variant_kernel(double* out, int iter
                 else if (V == 2) a[i] = fma(a[i], b[i], a[i]);
                 else if (V == 3) a[i] = a[i] * b[i];
                 else if (V == 4) a[i] = a[i] + c[i];
-                else a[i] = fma(a[i], up, c[i]);
+                else if (V == 5) a[i] = fma(a[i], up, c[i]);
+                else if (V == 6) a[i] = fma(b[0], c[i], a[i]);          // multiplicand shared by consecutive DFMAs
+                else a[i] = fma(b[i], c[i & 1], a[i]);                  // V == 7: second factor from 2 registers
             }
         }
     }

@@ -490,3 +490,28 @@ def test_fixed_controls_shortcut_matches_full_evaluation(oracles, built_library)
         ctx.eval_fixed_controls(torch.from_numpy(basis).cuda(), d, dc, dg, None)
         ctx.sync()
         assert np.array_equal(dc.cpu().numpy(), c2) and np.array_equal(dg.cpu().numpy(), g2)
+
+
+def test_two_contexts_sharing_a_stream_do_not_overlap(built_library):
+    """A launch may only overlap the SAME context's previous launch (the one its buffers were
+    checked against): two contexts alternating on one stream must stay strictly ordered."""
+    import torch
+    a = make_problem("lv_fishing", D.FisherDCriterion).context()
+    b = make_problem("lv_fishing", D.FisherACriterion).context()
+    st = torch.cuda.current_stream().cuda_stream
+    a.set_stream(st); b.set_stream(st)
+    ks = a.kernel_stats(True)
+    n = ks["grid"] * ks["block"]
+    d1 = torch.from_numpy(random_designs("lv_fishing", 71, n, 1)).cuda()
+    ga = [torch.empty_like(d1) for _ in range(2)]
+    gb = [torch.empty_like(d1) for _ in range(2)]
+    ca = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(2)]
+    cb = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(2)]
+    for k in range(4):                                   # rotating buffers: only the stream check can say no
+        a.eval_batch(d1, ca[k % 2], ga[k % 2], None, async_=True)
+        b.eval_batch(ga[k % 2], cb[k % 2], gb[k % 2], None, async_=True)   # b consumes a's output
+    torch.cuda.synchronize()
+    assert a.kernel_stats(True)["overlapped_launches"] == 0 and b.kernel_stats(True)["overlapped_launches"] == 0
+    cb_ref = torch.empty_like(cb[1]); gb_ref = torch.empty_like(gb[1])
+    b.eval_batch(ga[1].clone(), cb_ref, gb_ref, None)
+    assert torch.equal(cb[1].nan_to_num(), cb_ref.nan_to_num()) and torch.equal(gb[1].nan_to_num(), gb_ref.nan_to_num())
