@@ -978,7 +978,7 @@ int dynoed_eval_fixed_controls(dynoed_ctx* ctx, const double* basis, const doubl
         CUF(cudaMemcpyAsync(dd, designs, sizeof(double) * n * nv, cudaMemcpyHostToDevice, st));
         ddes = dd; dcr = dc; dgr = dg; dfi = df;
     }
-    const int block = 256;
+    const int block = kFcTile;
     const size_t smem = 128 + sizeof(double) * ((size_t)kFcTile * nv + (size_t)nv * nF);
     if (smem > ctx->smem_optin) { cleanup(); return fail(ctx, DYNOED_EUNSUPPORTED, "design rows too long for the fixed-controls kernel"); }
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, ctx->smem_per_sm / (smem + 1024)));

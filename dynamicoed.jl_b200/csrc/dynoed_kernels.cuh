@@ -920,24 +920,26 @@ __global__ void info_gain_kernel(const EvalParams P, const double* __restrict__ 
 // weights (/root/reference/src/augment.jl:223-226: nothing depends on F), so a whole batch of
 // measurement designs needs no integration at all:  F = designs[n][n_var] x basis[n_var][NF]
 // (basis rows are zero for non-weight columns), then the criterion and
-// d objective / d w_k = <Lambda, B_k>.  Pure HBM streaming: tiles of 64 rows staged by TMA bulk
-// copies, one warp per design row, gradients written over the rows in shared memory and stored
-// by one TMA bulk copy; basis in shared memory.  HBM roofline: 8 (2 n_var + 1) bytes per design.
+// d objective / d w_k = <Lambda, B_k>.  Pure HBM streaming, same tile mechanics as the evaluation
+// kernel: 128 rows staged by one TMA bulk load, one design row per lane (bank-conflict free for
+// odd n_var), gradients written over the rows in place and stored by one TMA bulk copy; the
+// basis sits in shared memory and is read as a broadcast.  Several CTAs per SM overlap each
+// other's load / arithmetic / store phases.  HBM roofline: 8 (2 n_var + 1) bytes per design.
 // ----------------------------------------------------------------------------------------------
-constexpr int kFcTile = 64;   // design rows per TMA-staged tile of the fixed-controls kernel
+constexpr int kFcTile = 128;   // design rows per TMA-staged tile of the fixed-controls kernel
 
 template <int NP>
-__global__ void __launch_bounds__(256) fixed_controls_kernel(const double* __restrict__ designs,
-                                                             const double* __restrict__ basis, long long n,
-                                                             int n_var, int tau_off, int criterion, int use_tma,
-                                                             double* __restrict__ crit, double* __restrict__ grad,
-                                                             double* __restrict__ fim) {
+__global__ void __launch_bounds__(kFcTile) fixed_controls_kernel(const double* __restrict__ designs,
+                                                                 const double* __restrict__ basis, long long n,
+                                                                 int n_var, int tau_off, int criterion, int use_tma,
+                                                                 double* __restrict__ crit, double* __restrict__ grad,
+                                                                 double* __restrict__ fim) {
     constexpr int NF = NP * (NP + 1) / 2;
     extern __shared__ __align__(128) unsigned char fc_smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(fc_smem);
     double* tile_buf = reinterpret_cast<double*>(fc_smem + 128);            // [kFcTile][n_var]
     double* sb = tile_buf + (size_t)kFcTile * n_var;                         // [n_var][NF]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const int tid = threadIdx.x;
     for (int i = tid; i < n_var * NF; i += blockDim.x) sb[i] = basis[i];
     if (tid == 0 && use_tma) mbar_init(bar, 1);
     __syncthreads();
@@ -959,29 +961,23 @@ __global__ void __launch_bounds__(256) fixed_controls_kernel(const double* __res
             for (int i = tid; i < count * n_var; i += blockDim.x) tile_buf[i] = designs[g0 * n_var + i];
             __syncthreads();
         }
-        for (int r = warp; r < count; r += nwarp) {      // one warp per design row
-            double* row = tile_buf + (size_t)r * n_var;
+        if (tid < count) {                                 // one design row per lane (as in oed_eval_kernel)
+            double* row = tile_buf + (size_t)tid * n_var;
             double F[NF];
 #pragma unroll
             for (int f = 0; f < NF; ++f) F[f] = 0.0;
-            for (int k = lane; k < n_var; k += 32) {
+            for (int k = 0; k < n_var; ++k) {
                 const double v = row[k];
 #pragma unroll
                 for (int f = 0; f < NF; ++f) F[f] = fma(v, sb[k * NF + f], F[f]);
             }
-#pragma unroll
-            for (int f = 0; f < NF; ++f)
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) F[f] += __shfl_xor_sync(0xffffffffu, F[f], o);
             const double tau = row[tau_off];
             double value, L[NF];
             criterion_eval<NP>(F, tau, criterion, value, L);
-            if (lane == 0) {
-                crit[g0 + r] = value + tau;
-                if (fim) {
+            crit[g0 + tid] = value + tau;
+            if (fim) {
 #pragma unroll
-                    for (int f = 0; f < NF; ++f) fim[(g0 + r) * NF + f] = F[f];
-                }
+                for (int f = 0; f < NF; ++f) fim[(g0 + tid) * NF + f] = F[f];
             }
             if (grad) {
                 double Ls[NF], trL = 1.0;
@@ -992,13 +988,13 @@ __global__ void __launch_bounds__(256) fixed_controls_kernel(const double* __res
                         Ls[tri(i, j)] = (i == j ? 1.0 : 2.0) * L[tri(i, j)];
                         if (i == j) trL += L[tri(i, j)];
                     }
-                __syncwarp();                              // every lane has read tau before it is overwritten
-                for (int k = lane; k < n_var; k += 32) {
+                for (int k = 0; k < n_var; ++k) {
                     double s = 0.0;
 #pragma unroll
                     for (int f = 0; f < NF; ++f) s = fma(Ls[f], sb[k * NF + f], s);
-                    row[k] = k == tau_off ? trL : s;       // gradients overwrite the row in place
+                    row[k] = s;                            // gradients overwrite the row in place
                 }
+                row[tau_off] = trL;
             }
         }
         if (grad) {
