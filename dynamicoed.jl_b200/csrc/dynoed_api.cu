@@ -525,13 +525,18 @@ int dynoed_set_criterion(dynoed_ctx* ctx, int criterion) {
 
 int dynoed_set_stream(dynoed_ctx* ctx, void* s) {
     if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    // the ctx's scratch is ordered by its stream: drain the old one before work moves to another
+    if (ctx->stream != (cudaStream_t)s) { CU(cudaSetDevice(ctx->device)); CU(cudaStreamSynchronize(ctx->stream)); }
     ctx->stream = (cudaStream_t)s;   // NULL is the CUDA legacy default stream
+    ctx->prev.valid = false;
     return DYNOED_OK;
 }
 
 int dynoed_own_stream(dynoed_ctx* ctx) {
     if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    if (ctx->stream != ctx->own_stream) { CU(cudaSetDevice(ctx->device)); CU(cudaStreamSynchronize(ctx->stream)); }
     ctx->stream = ctx->own_stream;
+    ctx->prev.valid = false;
     return DYNOED_OK;
 }
 

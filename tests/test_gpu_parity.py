@@ -515,3 +515,32 @@ def test_two_contexts_sharing_a_stream_do_not_overlap(built_library):
     cb_ref = torch.empty_like(cb[1]); gb_ref = torch.empty_like(gb[1])
     b.eval_batch(ga[1].clone(), cb_ref, gb_ref, None)
     assert torch.equal(cb[1].nan_to_num(), cb_ref.nan_to_num()) and torch.equal(gb[1].nan_to_num(), gb_ref.nan_to_num())
+
+
+def test_nan_and_extreme_designs_are_data_not_errors(oracles, built_library):
+    """NaN / Inf in a design row poison that row only (no error, no effect on neighbours); NaN never
+    wins the arg-min; weights outside [0, 1] and tau = eps() (the reference's lower bound,
+    discretize.jl:168) evaluate like any other number and match the oracle."""
+    ctx = make_problem("lv_fishing", D.ACriterion).context()
+    orc = oracles("lv_fishing", 3, "rk4", 4)
+    des = random_designs("lv_fishing", 71, 700, 77)
+    clean = ctx.evaluate(des)
+    bad = des.copy()
+    bad[3, 20] = np.nan            # a weight
+    bad[130, 2] = np.inf           # a control
+    bad[699, 70] = np.nan          # tau
+    c, g, F = ctx.evaluate(bad)
+    ok = np.ones(700, dtype=bool); ok[[3, 130, 699]] = False
+    assert np.array_equal(c[ok], clean[0][ok]) and np.array_equal(g[ok], clean[1][ok])
+    assert np.isnan(c[3]) and not np.isfinite(c[130]) and np.isnan(c[699])
+    i, v = ctx.argmin()
+    assert ok[i] and v == np.min(c[ok])
+    ext = des[:64].copy()
+    ext[:, 10:70] = 3.0 * ext[:, 10:70] - 1.0          # weights in [-1, 2)
+    ext[:, 70] = np.finfo(float).eps
+    ext[0, 10:70] = 0.0                                 # F = 0, M = eps I: 1/eps-sized criteria
+    c, g, F = ctx.evaluate(ext)
+    oc, og, oF = orc.evaluate(ext, grad=True)
+    assert rel(F, oF) < RTOL
+    assert float(np.max(np.abs(c - oc) / np.abs(oc))) < 1e-9
+    assert rel_rows(g[1:], og[1:]) < 1e-8               # cond(F + eps I) amplifies rounding
