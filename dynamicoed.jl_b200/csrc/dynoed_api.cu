@@ -26,6 +26,9 @@ namespace dynoed {
 
 static thread_local std::string g_last_error;
 
+// method + kFwdOnly selects the forward-only gradient kernel of an explicit tableau (DYNOED_GRAD_NO_CONTROLS)
+constexpr int kFwdOnly = 16;
+
 struct ModelEntry {
     const char* name;
     dynoed_model_info info;
@@ -69,18 +72,18 @@ static cudaError_t launch_tab(bool grad, bool uc, bool pdl, const EvalParams& P,
               : launch_one<M, Tab, false, false>(pdl, P, grid, block, smem, st);
 }
 
-template <class M, class RT, bool GRAD>
+template <class M, class Stepper, bool GRAD>
 static cudaError_t launch_ros(const EvalParams& P, int grid, int block, size_t smem, cudaStream_t st) {
-    auto kern = ros_eval_kernel<M, RT, GRAD>;
+    auto kern = ros_eval_kernel<M, Stepper, GRAD>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, block, smem, st>>>(P);
     return cudaGetLastError();
 }
 
-template <class M, class RT, bool GRAD>
+template <class M, class Stepper, bool GRAD>
 static cudaError_t attrs_ros(int block, size_t smem, cudaFuncAttributes* fa, int* bps) {
-    auto kern = ros_eval_kernel<M, RT, GRAD>;
+    auto kern = ros_eval_kernel<M, Stepper, GRAD>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(fa, kern);
@@ -94,10 +97,14 @@ static cudaError_t launch_model(int method, bool grad, bool uc, bool pdl, const 
     if (method == DYNOED_RK4) return launch_tab<M, TabRK4>(grad, uc, pdl, P, grid, block, smem, st);
     if (method == DYNOED_TSIT5) return launch_tab<M, TabTsit5>(grad, uc, pdl, P, grid, block, smem, st);
     if (method == DYNOED_ROS2)
-        return grad ? launch_ros<M, TabROS2, true>(P, grid, block, smem, st)
-                    : launch_ros<M, TabROS2, false>(P, grid, block, smem, st);
-    return grad ? launch_ros<M, TabROS3P, true>(P, grid, block, smem, st)
-                : launch_ros<M, TabROS3P, false>(P, grid, block, smem, st);
+        return grad ? launch_ros<M, RosenbrockStepper<TabROS2>, true>(P, grid, block, smem, st)
+                    : launch_ros<M, RosenbrockStepper<TabROS2>, false>(P, grid, block, smem, st);
+    if (method == DYNOED_ROS3P)
+        return grad ? launch_ros<M, RosenbrockStepper<TabROS3P>, true>(P, grid, block, smem, st)
+                    : launch_ros<M, RosenbrockStepper<TabROS3P>, false>(P, grid, block, smem, st);
+    // forward-only gradient mode of the explicit tableaus (kFwdOnly + method)
+    if (method == kFwdOnly + DYNOED_RK4) return launch_ros<M, ExplicitStepper<TabRK4>, true>(P, grid, block, smem, st);
+    return launch_ros<M, ExplicitStepper<TabTsit5>, true>(P, grid, block, smem, st);
 }
 
 template <class M, class Tab>
@@ -114,8 +121,13 @@ static cudaError_t attrs_model(int method, bool grad, bool uc, int block, size_t
     if (method == DYNOED_RK4) return attrs_tab<M, TabRK4>(grad, uc, block, smem, fa, bps);
     if (method == DYNOED_TSIT5) return attrs_tab<M, TabTsit5>(grad, uc, block, smem, fa, bps);
     if (method == DYNOED_ROS2)
-        return grad ? attrs_ros<M, TabROS2, true>(block, smem, fa, bps) : attrs_ros<M, TabROS2, false>(block, smem, fa, bps);
-    return grad ? attrs_ros<M, TabROS3P, true>(block, smem, fa, bps) : attrs_ros<M, TabROS3P, false>(block, smem, fa, bps);
+        return grad ? attrs_ros<M, RosenbrockStepper<TabROS2>, true>(block, smem, fa, bps)
+                    : attrs_ros<M, RosenbrockStepper<TabROS2>, false>(block, smem, fa, bps);
+    if (method == DYNOED_ROS3P)
+        return grad ? attrs_ros<M, RosenbrockStepper<TabROS3P>, true>(block, smem, fa, bps)
+                    : attrs_ros<M, RosenbrockStepper<TabROS3P>, false>(block, smem, fa, bps);
+    if (method == kFwdOnly + DYNOED_RK4) return attrs_ros<M, ExplicitStepper<TabRK4>, true>(block, smem, fa, bps);
+    return attrs_ros<M, ExplicitStepper<TabTsit5>, true>(block, smem, fa, bps);
 }
 
 template <class M>
@@ -139,7 +151,7 @@ static ModelEntry make_entry() {
     for (int k = 0; k < M::NIC; ++k) i.ic_state[k] = M::ic_state(k);
     i.autonomous = M::AUTONOMOUS ? 1 : 0;
     i.flops_primal = M::FLOPS_PRIMAL; i.flops_primal_z = M::FLOPS_PRIMAL_Z;
-    i.flops_adjoint = M::FLOPS_ADJOINT; i.flops_consts = M::FLOPS_CONSTS;
+    i.flops_adjoint = M::FLOPS_ADJOINT; i.flops_consts = M::FLOPS_CONSTS; i.flops_ros_f = M::FLOPS_ROS_F;
     for (int k = 0; k < M::NX; ++k) i.x0[k] = M::default_x0()[k];
     for (int k = 0; k < M::NX * M::NP; ++k) i.G0[k] = M::default_G0()[k];
     for (int k = 0; k < M::NTH; ++k) i.theta[k] = M::default_theta()[k];
@@ -217,9 +229,9 @@ struct dynoed_ctx {
     int w_len[kMaxObs] = {0};   // length of each measurement-weight block of the design vector
     bool ucoef = false;    // step coefficients served from the constant bank (uniform registers)
     bool rosenbrock = false;
-    int bps[2] = {0, 0};   // blocks per SM without / with gradient
+    int bps[3] = {0, 0, 0};   // blocks per SM: objective only / gradient / forward-only gradient (explicit RK)
     size_t smem_floor = 0; // dynamic shared memory padding that caps the resident CTAs per SM
-    cudaFuncAttributes fa[2];
+    cudaFuncAttributes fa[3];
     EvalParams base;       // tables + layout + model data (batch pointers filled per launch)
     int* d_first_step = nullptr;
     double* d_step_t = nullptr;
@@ -239,10 +251,12 @@ struct dynoed_ctx {
     long long* d_ring = nullptr;       // [kRing][2]: the same record for the last kRing batches
     int64_t batch_seq = 0;             // batches evaluated so far (ring slot = seq % kRing)
     unsigned int* d_ticket = nullptr;  // [2]
+    int kidx_req = 1;                  // gradient kernel requested by the current call (1 adjoint/Rosenbrock, 2 forward-only)
     int parity = 0;                    // scratch set of the NEXT device-path launch
     int last_parity = 0;               // scratch set that holds the most recent batch's arg-min
     struct Prev {                      // the previous device-path launch (overlap eligibility)
-        bool valid = false, grad = false, full = false;
+        bool valid = false, full = false;
+        int kidx = 0;
         uint64_t serial = 0;
         cudaStream_t stream = nullptr;
         const char *in0 = nullptr, *in1 = nullptr;
@@ -314,20 +328,26 @@ static int ensure_partials(dynoed_ctx* ctx, int need, int par) {
 
 // per-CTA scratch of a gradient launch: (x, G) checkpoints of every step (explicit RK adjoint) or
 // the per-interval unweighted quadratures (Rosenbrock)
-static size_t traj_bytes_for(const dynoed_ctx* ctx, int grid) {
+static size_t traj_bytes_for(const dynoed_ctx* ctx, int grid, int kidx = 1) {
     const auto& mi = ctx->model->info;
-    const size_t per_lane = ctx->rosenbrock ? (size_t)ctx->n_intervals * mi.n_obs * mi.nF
-                                            : (size_t)ctx->n_steps * mi.nz;
+    const size_t per_lane = (ctx->rosenbrock || kidx == 2) ? (size_t)ctx->n_intervals * mi.n_obs * mi.nF
+                                                           : (size_t)ctx->n_steps * mi.nz;
     return (size_t)grid * per_lane * kMaxTile * sizeof(double);
+}
+
+// 0: objective only, 1: gradient (adjoint sweep, or the Rosenbrock kernel), 2: forward-only gradient
+static int kernel_index(const dynoed_ctx* ctx, bool grad, uint32_t flags) {
+    if (!grad) return 0;
+    return ((flags & DYNOED_GRAD_NO_CONTROLS) && !ctx->rosenbrock) ? 2 : 1;
 }
 
 static size_t smem_bytes(const dynoed_ctx* ctx) {
     return std::max(ctx->smem_floor, 128 + (size_t)ctx->tile * ctx->n_var * sizeof(double));
 }
 
-static int grid_for(const dynoed_ctx* ctx, int64_t n, bool grad) {
+static int grid_for(const dynoed_ctx* ctx, int64_t n, int kidx) {
     const int64_t ntiles = (n + ctx->tile - 1) / ctx->tile;
-    const int64_t resident = (int64_t)ctx->sm_count * std::max(ctx->bps[grad ? 1 : 0], 1);
+    const int64_t resident = (int64_t)ctx->sm_count * std::max(ctx->bps[kidx], 1);
     return (int)std::max<int64_t>(1, std::min(ntiles, resident));
 }
 
@@ -490,8 +510,10 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     const size_t smem = smem_bytes(ctx);
     if (smem > (size_t)prop.sharedMemPerBlockOptin)
         return bail(DYNOED_EINVAL, "tile * n_var does not fit in shared memory; use a smaller tile");
-    for (int g = 0; g < 2; ++g) {
-        CUC(m->attrs(ctx->method, g == 1, ctx->ucoef, tile, smem, &ctx->fa[g], &ctx->bps[g]));
+    for (int g = 0; g < 3; ++g) {
+        if (g == 2 && rosenbrock) { ctx->fa[2] = ctx->fa[1]; ctx->bps[2] = ctx->bps[1]; break; }
+        CUC(m->attrs(g == 2 ? kFwdOnly + ctx->method : ctx->method, g >= 1, ctx->ucoef, tile, smem, &ctx->fa[g],
+                     &ctx->bps[g]));
         if (ctx->bps[g] < 1) return bail(DYNOED_ECUDA, "kernel cannot be resident with this tile size");
     }
 #undef CUC
@@ -570,8 +592,8 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
     // scratch sets suffice), on the same stream, and their buffers are disjoint.
     dynoed_ctx::Prev cur;
     cur.valid = xgrid == nullptr;
-    cur.grad = grad != nullptr;
-    cur.full = grid == ctx->sm_count * std::max(ctx->bps[cur.grad ? 1 : 0], 1);
+    cur.kidx = grad ? ctx->kidx_req : 0;
+    cur.full = grid == ctx->sm_count * std::max(ctx->bps[cur.kidx], 1);
     cur.stream = st;
     cur.in0 = (const char*)designs; cur.in1 = cur.in0 + sizeof(double) * n * ctx->n_var;
     cur.out0[0] = (const char*)crit; cur.out1[0] = cur.out0[0] + sizeof(double) * n;
@@ -579,7 +601,8 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
     cur.out0[2] = (const char*)fim; cur.out1[2] = fim ? cur.out0[2] + sizeof(double) * n * mi.nF : nullptr;
     const dynoed_ctx::Prev& pv = ctx->prev;
     bool pdl = ctx->pdl_enabled && !ctx->profiling && cur.valid && pv.valid && cur.full && pv.full &&
-               cur.grad == pv.grad && cur.stream == pv.stream && stream_last_serial(st) == pv.serial;
+               cur.kidx == pv.kidx && cur.kidx < 2 && !ctx->rosenbrock &&   // only oed_eval_kernel triggers early
+               cur.stream == pv.stream && stream_last_serial(st) == pv.serial;
     for (int a = 0; pdl && a < 3; ++a) {
         if (ranges_overlap(cur.in0, cur.in1, pv.out0[a], pv.out1[a])) pdl = false;      // RAW
         if (ranges_overlap(cur.out0[a], cur.out1[a], pv.in0, pv.in1)) pdl = false;      // WAR
@@ -596,7 +619,8 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
         }
         CU(cudaEventRecord(ctx->ev_k0, st));
     }
-    CU(ctx->model->launch(ctx->method, grad != nullptr, ctx->ucoef, pdl, P, grid, ctx->tile, smem_bytes(ctx), st));
+    CU(ctx->model->launch(cur.kidx == 2 ? kFwdOnly + ctx->method : ctx->method, grad != nullptr, ctx->ucoef, pdl, P, grid,
+                          ctx->tile, smem_bytes(ctx), st));
     if (ctx->profiling) { CU(cudaEventRecord(ctx->ev_k1, st)); ctx->ev_pending = true; }
     cur.serial = stream_new_serial(st);
     ctx->prev = cur;
@@ -608,13 +632,14 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
 static int eval_device(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad, double* fim,
                        double* xgrid) {
     const bool g = grad != nullptr;
-    const int grid = grid_for(ctx, n, g);
+    const int kidx = g ? ctx->kidx_req : 0;
+    const int grid = grid_for(ctx, n, kidx);
     const int par = ctx->parity;
     if (g) {
-        const size_t need = traj_bytes_for(ctx, grid);
+        const size_t need = traj_bytes_for(ctx, grid, kidx);
         if (need > ctx->traj_bytes[par]) {
             if (ctx->traj[par]) { CU(cudaDeviceSynchronize()); cudaFree(ctx->traj[par]); ctx->traj[par] = nullptr; }
-            const size_t full = traj_bytes_for(ctx, ctx->sm_count * std::max(ctx->bps[1], 1));
+            const size_t full = traj_bytes_for(ctx, ctx->sm_count * std::max(ctx->bps[kidx], 1), kidx);
             const size_t want = std::max(need, std::min(full, need * 4));
             CU(cudaMalloc(&ctx->traj[par], want));
             ctx->scratch_bytes += want - ctx->traj_bytes[par];
@@ -632,7 +657,8 @@ static int eval_device(dynoed_ctx* ctx, const double* designs, int64_t n, double
     return DYNOED_OK;
 }
 
-static int ensure_slot(dynoed_ctx* ctx, Slot& s, int64_t cap, bool grad, bool fim) {
+static int ensure_slot(dynoed_ctx* ctx, Slot& s, int64_t cap, int kidx, bool fim) {
+    const bool grad = kidx > 0;
     const int nF = ctx->model->info.nF;
     if (!s.stream) CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     if (cap > s.cap) {
@@ -647,8 +673,8 @@ static int ensure_slot(dynoed_ctx* ctx, Slot& s, int64_t cap, bool grad, bool fi
         s.cap = cap;
     }
     if (grad) {
-        const int grid = grid_for(ctx, cap, true);
-        const size_t need = traj_bytes_for(ctx, grid);
+        const int grid = grid_for(ctx, cap, kidx);
+        const size_t need = traj_bytes_for(ctx, grid, kidx);
         if (need > s.traj_bytes) {
             CU(cudaStreamSynchronize(s.stream));
             cudaFree(s.traj); s.traj = nullptr;
@@ -691,13 +717,14 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
     int64_t chunk = 0;
     for (int64_t c = 0; c < nchunks; ++c) chunk = std::max(chunk, bounds[c + 1] - bounds[c]);
     int total_parts = 0;
-    for (int64_t c = 0; c < nchunks; ++c) total_parts += grid_for(ctx, bounds[c + 1] - bounds[c], g);
+    const int kidx = g ? ctx->kidx_req : 0;
+    for (int64_t c = 0; c < nchunks; ++c) total_parts += grid_for(ctx, bounds[c + 1] - bounds[c], kidx);
     const int par = ctx->parity;
     ctx->prev.valid = false;    // host-path launches run on their own streams: no overlap bookkeeping
     int rc = ensure_partials(ctx, total_parts, par);
     if (rc) return rc;
     for (int k = 0; k < kSlots && k < nchunks; ++k) {
-        rc = ensure_slot(ctx, ctx->slots[k], chunk, g, fim != nullptr);
+        rc = ensure_slot(ctx, ctx->slots[k], chunk, kidx, fim != nullptr);
         if (rc) return rc;
     }
     // order after whatever the ctx stream was doing
@@ -712,7 +739,7 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         CU(cudaMemcpyAsync(s.d_designs, designs + off * ctx->n_var, sizeof(double) * cnt * ctx->n_var,
                            cudaMemcpyHostToDevice, s.stream));
         EvalParams P = ctx->base;
-        const int grid = grid_for(ctx, cnt, g);
+        const int grid = grid_for(ctx, cnt, kidx);
         P.designs = s.d_designs; P.crit = s.d_crit; P.grad = g ? s.d_grad : nullptr; P.fim = fim ? s.d_fim : nullptr;
         P.xgrid = nullptr; P.traj = s.traj; P.n = cnt;
         P.part_val = ctx->part_val[par]; P.part_idx = ctx->part_idx[par];
@@ -722,7 +749,8 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         part_base += grid;
         P.use_tma = (((size_t)ctx->tile * ctx->n_var * 8) % 16 == 0) ? 1 : 0;
         P.index_base = off;
-        CU(ctx->model->launch(ctx->method, g, ctx->ucoef, false, P, grid, ctx->tile, smem_bytes(ctx), s.stream));
+        CU(ctx->model->launch(kidx == 2 ? kFwdOnly + ctx->method : ctx->method, g, ctx->ucoef, false, P, grid, ctx->tile,
+                              smem_bytes(ctx), s.stream));
         ctx->launches++;
         CU(cudaMemcpyAsync(crit + off, s.d_crit, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s.stream));
         if (g) CU(cudaMemcpyAsync(grad + off * ctx->n_var, s.d_grad, sizeof(double) * cnt * ctx->n_var,
@@ -743,16 +771,17 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
 }
 
 static int eval_common(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad, double* fim,
-                       bool allow_host, bool sync) {
+                       bool allow_host, bool sync, uint32_t flags = 0) {
     if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
     ctx->err.clear();
     if (n < 0) return fail(ctx, DYNOED_EINVAL, "n < 0");
     if (n == 0) { ctx->have_batch = false; return DYNOED_OK; }
     if (!designs || !crit) return fail(ctx, DYNOED_EINVAL, "designs/crit is NULL");
-    if (grad && ctx->rosenbrock && ctx->model->info.n_ctrl > 0)
+    if (grad && ctx->rosenbrock && ctx->model->info.n_ctrl > 0 && !(flags & DYNOED_GRAD_NO_CONTROLS))
         return fail(ctx, DYNOED_EUNSUPPORTED,
-                    "the Rosenbrock integrators do not differentiate with respect to controls; "
-                    "pass grad = NULL or use an explicit method");
+                    "the Rosenbrock integrators do not differentiate with respect to controls; pass "
+                    "DYNOED_GRAD_NO_CONTROLS (control entries become NaN), grad = NULL, or use an explicit method");
+    ctx->kidx_req = kernel_index(ctx, grad != nullptr, flags);
     CU(cudaSetDevice(ctx->device));
     const int kd = ptr_kind(designs);
     if (ptr_kind(crit) != kd || (grad && ptr_kind(grad) != kd) || (fim && ptr_kind(fim) != kd))
@@ -770,14 +799,12 @@ static int eval_common(dynoed_ctx* ctx, const double* designs, int64_t n, double
 
 int dynoed_eval_batch(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad, double* fim,
                       uint32_t flags) {
-    (void)flags;
-    return eval_common(ctx, designs, n, crit, grad, fim, true, true);
+    return eval_common(ctx, designs, n, crit, grad, fim, true, true, flags);
 }
 
 int dynoed_eval_batch_async(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad,
                             double* fim, uint32_t flags) {
-    (void)flags;
-    return eval_common(ctx, designs, n, crit, grad, fim, false, false);
+    return eval_common(ctx, designs, n, crit, grad, fim, false, false, flags);
 }
 
 int dynoed_sync(dynoed_ctx* ctx) {
@@ -1128,7 +1155,7 @@ int dynoed_fp64_microbench(int device, int variant, double* ginstr_per_s) {
 
 int dynoed_kernel_stats_query(dynoed_ctx* ctx, int with_grad, dynoed_kernel_stats* o) {
     if (!ctx || !o) return fail(ctx, DYNOED_EINVAL, "ctx/out is NULL");
-    const int g = with_grad ? 1 : 0;
+    const int g = with_grad == 2 ? 2 : with_grad ? 1 : 0;
     const auto& mi = ctx->model->info;
     memset(o, 0, sizeof(*o));
     o->regs_per_thread = ctx->fa[g].numRegs;
@@ -1165,6 +1192,12 @@ int dynoed_kernel_stats_query(dynoed_ctx* ctx, int with_grad, dynoed_kernel_stat
     }
     o->flops_per_design_eval = fwd * ctx->n_steps + (double)ctx->n_intervals * mi.flops_consts + epi;
     o->flops_per_design_grad = (fwd + bwd) * ctx->n_steps + 2.0 * ctx->n_intervals * mi.flops_consts + epi;
+    if (g == 2) {   // forward-only gradient: unweighted per-observation quadratures, F += w P per interval,
+                    // d/dw = <Lambda, P> in the epilogue
+        const int nq = mi.n_obs * mi.nF;
+        const double f2 = (double)S * mi.flops_ros_f + 2.0 * mi.nz * nza + 2.0 * (mi.nz + nq) * S + nza + S;
+        o->flops_per_design_grad = f2 * ctx->n_steps + (double)ctx->n_intervals * (mi.flops_consts + 4.0 * nq) + epi;
+    }
     o->bytes_per_design = 8.0 * (ctx->n_var + 1 + (with_grad ? ctx->n_var : 0) + mi.nF);
     return DYNOED_OK;
 }

@@ -246,11 +246,61 @@ __device__ __forceinline__ void rosenbrock_step(double t, double h, T (&z)[M::NZ
 }
 
 // ----------------------------------------------------------------------------------------------
-// The Rosenbrock evaluation kernel: same tile staging (TMA), epilogue and arg-min as
-// oed_eval_kernel; forward sweep only (see the header comment for the gradient).
+// Steppers for the forward-only kernel below: Rosenbrock (stiff configuration) or an explicit
+// Runge-Kutta tableau on the same state y = [z; Pq] (the "criterion + d/dw + d/dtau" mode of the
+// explicit integrators: no backward sweep, controls are not differentiated).
+// ----------------------------------------------------------------------------------------------
+template <class RT>
+struct RosenbrockStepper {
+    template <class M, class T>
+    __device__ __forceinline__ static void step(double t, double h, T (&z)[M::NZ], T (&Pq)[M::NOBS * M::NF],
+                                                const double* u, const double* th, const double* c) {
+        rosenbrock_step<M, RT, T>(t, h, z, Pq, u, th, c);
+    }
+};
+
+template <class Tab>
+struct ExplicitStepper {
+    template <class M, class T>
+    __device__ __forceinline__ static void step(double t, double h, T (&z)[M::NZ], T (&Pq)[M::NOBS * M::NF],
+                                                const double* u, const double* th, const double* c) {
+        constexpr int S = Tab::S, NZ = M::NZ, NQ = M::NOBS * M::NF;
+        T k[S][NZ], zacc[NZ];
+#pragma unroll
+        for (int a = 0; a < NZ; ++a) zacc[a] = z[a];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            T Z[NZ];
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) Z[a] = z[a];
+#pragma unroll
+            for (int j = 0; j < s; ++j) {
+                if (Tab::a(s, j) != 0.0) {
+                    const double ha = h * Tab::a(s, j);
+#pragma unroll
+                    for (int a = 0; a < NZ; ++a) Z[a] = Z[a] + ha * k[j][a];
+                }
+            }
+            T dq[NQ];
+            M::template ros_f<T>(t + Tab::c(s) * h, Z, u, th, c, k[s], dq);
+            const double hb = h * Tab::b(s);
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) zacc[a] = zacc[a] + hb * k[s][a];
+#pragma unroll
+            for (int a = 0; a < NQ; ++a) Pq[a] = Pq[a] + hb * dq[a];
+        }
+#pragma unroll
+        for (int a = 0; a < NZ; ++a) z[a] = zacc[a];
+    }
+};
+
+// ----------------------------------------------------------------------------------------------
+// The forward-only evaluation kernel (Rosenbrock, or explicit RK without control gradients): same
+// tile staging (TMA), epilogue and arg-min as oed_eval_kernel; no backward sweep (see the header
+// comment for the gradient).  Control entries of the gradient are NaN ("not computed").
 // P.traj is used as the per-interval quadrature scratch [grid][N][NOBS*NF][kMaxTile].
 // ----------------------------------------------------------------------------------------------
-template <class M, class RT, bool GRAD>
+template <class M, class Stepper, bool GRAD>
 __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams P) {
     constexpr int NX = M::NX, NP = M::NP, NZ = M::NZ, NF = M::NF, NOBS = M::NOBS, NCTRL = M::NCTRL;
     constexpr int NCU = NCTRL > 0 ? NCTRL : 1, NQ = NOBS * NF;
@@ -329,7 +379,7 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams 
                 for (int a = 0; a < NQ; ++a) Pq[a] = T(0.0);
                 const int s0 = __ldg(P.first_step + j), s1 = __ldg(P.first_step + j + 1);
                 for (int s = s0; s < s1; ++s)
-                    rosenbrock_step<M, RT, T>(__ldg(P.step_t + s), __ldg(P.step_h + s), z, Pq, u, th, c);
+                    Stepper::template step<M, T>(__ldg(P.step_t + s), __ldg(P.step_h + s), z, Pq, u, th, c);
 #pragma unroll
                 for (int i = 0; i < NOBS; ++i)
 #pragma unroll
@@ -396,7 +446,14 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams 
                     for (int k = 0; k < NF; ++k) s = fma(Ls[k], dual_part(F[k], a), s);
                     row[P.ic_off + a] = s;
                 }
-                // controls are not differentiated by the Rosenbrock integrator (rejected on the host)
+                // controls are not differentiated by this kernel: their entries say so
+                for (int k = 0; k < NCTRL; ++k) {
+                    int last = -1;
+                    for (int j = 0; j < N; ++j) {
+                        const int idx = __ldg(P.indicators + k * N + j);
+                        if (idx != last) { row[P.ctrl_off[k] + idx] = __longlong_as_double(0x7ff8000000000000LL); last = idx; }
+                    }
+                }
                 double trL = 1.0;
 #pragma unroll
                 for (int i = 0; i < NP; ++i) trL += L[tri(i, i)];

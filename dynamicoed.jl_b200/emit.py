@@ -451,6 +451,7 @@ struct {cname} {{
     static constexpr int NTH = {len(theta)}, NCONST = {n_const}, NZ = {nz}, NF = {nF};
     static constexpr int FLOPS_PRIMAL = {flops['primal']}, FLOPS_PRIMAL_Z = {flops['primal_z']};
     static constexpr int FLOPS_ADJOINT = {flops['adjoint']}, FLOPS_CONSTS = {flops['consts']};
+    static constexpr int FLOPS_ROS_F = {flops['ros_f']};
     static constexpr const char* NAME = "{name}";
     __host__ __device__ static constexpr int ic_state(int i) {{
         constexpr int v[{max(n_ic, 1)}] = {{{arr(ic_state, '{}')}}};

@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdynoed_cuda.so")
 
 RK4, TSIT5, ROS2, ROS3P = 0, 1, 2, 3
+GRAD_NO_CONTROLS = 1    # eval flag: weights / tau / IC gradient only (forward sweep), control entries NaN
 METHODS = {"rk4": RK4, "RK4": RK4, "tsit5": TSIT5, "Tsit5": TSIT5, "ros2": ROS2, "ROS2": ROS2,
            "ros3p": ROS3P, "ROS3P": ROS3P}
 
@@ -28,7 +29,7 @@ class ModelInfo(C.Structure):
                 ("n_ic", C.c_int32), ("n_theta", C.c_int32), ("nz", C.c_int32), ("nF", C.c_int32),
                 ("autonomous", C.c_int32), ("ic_state", C.c_int32 * 8),
                 ("flops_primal", C.c_int32), ("flops_primal_z", C.c_int32),
-                ("flops_adjoint", C.c_int32), ("flops_consts", C.c_int32),
+                ("flops_adjoint", C.c_int32), ("flops_consts", C.c_int32), ("flops_ros_f", C.c_int32),
                 ("x0", C.c_double * 8), ("G0", C.c_double * 64), ("theta", C.c_double * 48)]
 
 
@@ -218,12 +219,12 @@ class Context:
     def own_stream(self):
         _check(self._L.dynoed_own_stream(self._h), self._h, self._L)
 
-    def eval_batch(self, designs, crit, grad=None, fim=None, n=None, async_=False):
+    def eval_batch(self, designs, crit, grad=None, fim=None, n=None, async_=False, flags=0):
         """designs [n, n_var], crit [n], grad [n, n_var] | None, fim [n, nF] | None — numpy arrays
         (host path) or torch CUDA tensors (device path), float64, contiguous."""
         n = int(designs.shape[0]) if n is None else int(n)
         fn = self._L.dynoed_eval_batch_async if async_ else self._L.dynoed_eval_batch
-        _check(fn(self._h, _ptr(designs), n, _ptr(crit), _ptr(grad), _ptr(fim), 0), self._h, self._L)
+        _check(fn(self._h, _ptr(designs), n, _ptr(crit), _ptr(grad), _ptr(fim), int(flags)), self._h, self._L)
 
     def sync(self):
         _check(self._L.dynoed_sync(self._h), self._h, self._L)
@@ -293,17 +294,17 @@ class Context:
 
     def kernel_stats(self, with_grad=True) -> dict:
         ks = KernelStats()
-        _check(self._L.dynoed_kernel_stats_query(self._h, int(with_grad), C.byref(ks)), self._h, self._L)
+        _check(self._L.dynoed_kernel_stats_query(self._h, int(with_grad), C.byref(ks)), self._h, self._L)   # 2: NO_CONTROLS kernel
         return {k: getattr(ks, k) for k, _ in KernelStats._fields_}
 
     # convenience: host numpy in, numpy out
-    def evaluate(self, designs, grad=True, fim=True):
+    def evaluate(self, designs, grad=True, fim=True, flags=0):
         designs = np.ascontiguousarray(np.atleast_2d(designs), dtype=np.float64)
         n = designs.shape[0]
         crit = np.empty(n)
         g = np.empty((n, self.n_var)) if grad else None
         f = np.empty((n, self.info.nF)) if fim else None
-        self.eval_batch(designs, crit, g, f)
+        self.eval_batch(designs, crit, g, f, flags=flags)
         return crit, g, f
 
 

@@ -52,6 +52,11 @@ extern "C" {
 #define DYNOED_ROS2 2  /* 2 stages, order 2, L-stable */
 #define DYNOED_ROS3P 3 /* 3 stages, order 3, A-stable */
 
+/* flags of dynoed_eval_batch[_async] */
+#define DYNOED_GRAD_NO_CONTROLS 1u /* gradient w.r.t. weights, tau and unknown initial conditions only:
+                                    * forward sweep with per-interval quadratures, no adjoint sweep;
+                                    * control entries of grad are NaN ("not computed") */
+
 typedef struct dynoed_ctx dynoed_ctx;
 
 /* Static facts about a compiled-in model (the emitted augmented system of
@@ -60,7 +65,7 @@ typedef struct dynoed_model_info {
     int32_t nx, np, n_obs, n_ctrl, n_ic, n_theta, nz, nF;
     int32_t autonomous;        /* 1 if the right-hand side does not depend on t explicitly */
     int32_t ic_state[8];       /* 0-based state index of each unknown initial condition */
-    int32_t flops_primal, flops_primal_z, flops_adjoint, flops_consts; /* per RHS call, FMA = 2 */
+    int32_t flops_primal, flops_primal_z, flops_adjoint, flops_consts, flops_ros_f; /* per call, FMA = 2 */
     double x0[8];
     double G0[64];             /* column-major nx x np */
     double theta[48];          /* default parameter values (non-control, non-weight) */
@@ -183,6 +188,7 @@ int dynoed_fp64_microbench(int device, int variant, double* ginstr_per_s);
 /* CUDA-event timing of the evaluation kernel itself (device-pointer path), for the roofline */
 int dynoed_set_profiling(dynoed_ctx* ctx, int on);
 int dynoed_kernel_time(dynoed_ctx* ctx, double* mean_ms, int64_t* count);
+/* with_grad: 0 objective only, 1 gradient, 2 gradient with DYNOED_GRAD_NO_CONTROLS */
 int dynoed_kernel_stats_query(dynoed_ctx* ctx, int with_grad, dynoed_kernel_stats* out);
 int dynoed_host_alloc(void** p, size_t bytes); /* pinned host memory for the e2e path */
 int dynoed_host_free(void* p);

@@ -544,3 +544,24 @@ def test_nan_and_extreme_designs_are_data_not_errors(oracles, built_library):
     assert rel(F, oF) < RTOL
     assert float(np.max(np.abs(c - oc) / np.abs(oc))) < 1e-9
     assert rel_rows(g[1:], og[1:]) < 1e-8               # cond(F + eps I) amplifies rounding
+
+
+@pytest.mark.parametrize("name,method", [("lv_fishing", "rk4"), ("lv_fishing", "tsit5"), ("lv_ic", "rk4"),
+                                          ("readme", "tsit5")])
+def test_forward_only_gradient_mode(name, method, oracles, built_library):
+    """DYNOED_GRAD_NO_CONTROLS: criterion + d/dw + d/dtau (+ d/dx0 by dual parts) from a forward sweep
+    with per-interval quadratures; control entries are NaN; everything else equals the adjoint
+    gradient / the oracle."""
+    ctx = make_problem(name, D.DCriterion, method).context()
+    orc = oracles(name, 4, method, 4)
+    des = random_designs(name, ctx.n_var, 2500, 13)
+    c, g, F = ctx.evaluate(des, flags=runtime.GRAD_NO_CONTROLS)
+    oc, og, oF = orc.evaluate(des, grad=True)
+    nc = ctx.info.n_ctrl
+    lay = make_problem(name, D.DCriterion, method).layout
+    ctrl_cols = [o + k for o, l in zip(lay.control_offsets, lay.control_lengths) for k in range(l)] if nc else []
+    keep = [k for k in range(ctx.n_var) if k not in ctrl_cols]
+    assert rel(F, oF) < RTOL and rel(c, oc) < RTOL
+    assert np.all(np.isnan(g[:, ctrl_cols]))
+    assert rel_rows(g[:, keep], og[:, keep]) < RTOL
+    assert ctx.argmin()[0] == int(np.argmin(oc))
