@@ -259,6 +259,28 @@ def main():
     torch.cuda.synchronize()
     kernel_ms_iso, kcount = ctx.kernel_time()
     ctx.set_profiling(False)
+    # sub-metrics of SURVEY.md 8d on the same buffers (rank-local, not part of `value`):
+    # objective only, and objective + d/dw + d/dtau from the forward-only gradient kernel
+    sub = {}
+    for key, kw in (("criterion_only", dict(grad=False)), ("criterion_dw_dtau", dict(grad=True, flags=runtime.GRAD_NO_CONTROLS))):
+        def one(k):
+            ctx.eval_batch(d_in[k % NBUF], d_crit[k % NBUF], d_grad[k % NBUF] if kw["grad"] else None, d_fim[k % NBUF],
+                           async_=True, flags=kw.get("flags", 0))
+        for k in range(3):
+            one(k)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = min(args.steps, 100)
+        s0.record(stream)
+        for k in range(reps):
+            one(k)
+        s1.record(stream)
+        torch.cuda.synchronize()
+        ksx = ctx.kernel_stats(0 if not kw["grad"] else 2)
+        fl = ksx["flops_per_design_eval"] if not kw["grad"] else ksx["flops_per_design_grad"]
+        msx = s0.elapsed_time(s1) / reps
+        sub[key] = {"designs_per_s_per_gpu": n / msx * 1e3, "ms_per_step": msx, "flops_per_design": fl,
+                    "tflops": fl * n / msx / 1e9}
     if world > 1:
         tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -340,7 +362,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * n_var * 8,
                         "d2h_bytes_per_step": n * (1 + n_var + 3) * 8, "steps": e2e_steps,
                         "host_memory": "pinned"},
-                "gpu_launches": int(launches), "clocks": clocks}
+                "gpu_launches": int(launches), "clocks": clocks, "sub_metrics": sub}
         if not args.no_cpu_baseline:
             orc, threads = cpu_oracle()
             v, ns, dt = time_cpu(orc, threads, make_designs(4 * N_PER_GPU, 71, 20262), 12.0)

@@ -39,9 +39,9 @@ struct ModelEntry {
     cudaError_t (*info_gain)(const EvalParams& P, const double* X, double* Pout, double* Piout, cudaStream_t st);
 };
 
-template <class M, class Tab, bool GRAD, bool UC>
-static cudaError_t launch_one(bool pdl, const EvalParams& P, int grid, int block, size_t smem, cudaStream_t st) {
-    auto kern = oed_eval_kernel<M, Tab, GRAD, UC>;
+template <class K>
+static cudaError_t launch_kernel(K kern, bool pdl, const EvalParams& P, int grid, int block, size_t smem,
+                                 cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
@@ -51,6 +51,11 @@ static cudaError_t launch_one(bool pdl, const EvalParams& P, int grid, int block
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, P);
+}
+
+template <class M, class Tab, bool GRAD, bool UC>
+static cudaError_t launch_one(bool pdl, const EvalParams& P, int grid, int block, size_t smem, cudaStream_t st) {
+    return launch_kernel(oed_eval_kernel<M, Tab, GRAD, UC>, pdl, P, grid, block, smem, st);
 }
 
 template <class M, class Tab, bool GRAD, bool UC>
@@ -73,12 +78,8 @@ static cudaError_t launch_tab(bool grad, bool uc, bool pdl, const EvalParams& P,
 }
 
 template <class M, class Stepper, bool GRAD>
-static cudaError_t launch_ros(const EvalParams& P, int grid, int block, size_t smem, cudaStream_t st) {
-    auto kern = ros_eval_kernel<M, Stepper, GRAD>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, block, smem, st>>>(P);
-    return cudaGetLastError();
+static cudaError_t launch_ros(bool pdl, const EvalParams& P, int grid, int block, size_t smem, cudaStream_t st) {
+    return launch_kernel(ros_eval_kernel<M, Stepper, GRAD>, pdl, P, grid, block, smem, st);
 }
 
 template <class M, class Stepper, bool GRAD>
@@ -97,14 +98,14 @@ static cudaError_t launch_model(int method, bool grad, bool uc, bool pdl, const 
     if (method == DYNOED_RK4) return launch_tab<M, TabRK4>(grad, uc, pdl, P, grid, block, smem, st);
     if (method == DYNOED_TSIT5) return launch_tab<M, TabTsit5>(grad, uc, pdl, P, grid, block, smem, st);
     if (method == DYNOED_ROS2)
-        return grad ? launch_ros<M, RosenbrockStepper<TabROS2>, true>(P, grid, block, smem, st)
-                    : launch_ros<M, RosenbrockStepper<TabROS2>, false>(P, grid, block, smem, st);
+        return grad ? launch_ros<M, RosenbrockStepper<TabROS2>, true>(pdl, P, grid, block, smem, st)
+                    : launch_ros<M, RosenbrockStepper<TabROS2>, false>(pdl, P, grid, block, smem, st);
     if (method == DYNOED_ROS3P)
-        return grad ? launch_ros<M, RosenbrockStepper<TabROS3P>, true>(P, grid, block, smem, st)
-                    : launch_ros<M, RosenbrockStepper<TabROS3P>, false>(P, grid, block, smem, st);
+        return grad ? launch_ros<M, RosenbrockStepper<TabROS3P>, true>(pdl, P, grid, block, smem, st)
+                    : launch_ros<M, RosenbrockStepper<TabROS3P>, false>(pdl, P, grid, block, smem, st);
     // forward-only gradient mode of the explicit tableaus (kFwdOnly + method)
-    if (method == kFwdOnly + DYNOED_RK4) return launch_ros<M, ExplicitStepper<TabRK4>, true>(P, grid, block, smem, st);
-    return launch_ros<M, ExplicitStepper<TabTsit5>, true>(P, grid, block, smem, st);
+    if (method == kFwdOnly + DYNOED_RK4) return launch_ros<M, ExplicitStepper<TabRK4>, true>(pdl, P, grid, block, smem, st);
+    return launch_ros<M, ExplicitStepper<TabTsit5>, true>(pdl, P, grid, block, smem, st);
 }
 
 template <class M, class Tab>
@@ -601,8 +602,7 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
     cur.out0[2] = (const char*)fim; cur.out1[2] = fim ? cur.out0[2] + sizeof(double) * n * mi.nF : nullptr;
     const dynoed_ctx::Prev& pv = ctx->prev;
     bool pdl = ctx->pdl_enabled && !ctx->profiling && cur.valid && pv.valid && cur.full && pv.full &&
-               cur.kidx == pv.kidx && cur.kidx < 2 && !ctx->rosenbrock &&   // only oed_eval_kernel triggers early
-               cur.stream == pv.stream && stream_last_serial(st) == pv.serial;
+               cur.kidx == pv.kidx && cur.stream == pv.stream && stream_last_serial(st) == pv.serial;
     for (int a = 0; pdl && a < 3; ++a) {
         if (ranges_overlap(cur.in0, cur.in1, pv.out0[a], pv.out1[a])) pdl = false;      // RAW
         if (ranges_overlap(cur.out0[a], cur.out1[a], pv.in0, pv.in1)) pdl = false;      // WAR

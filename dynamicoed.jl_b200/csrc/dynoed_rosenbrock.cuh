@@ -317,6 +317,7 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams 
     const int N = P.n_intervals;
     const double* th = P.theta;
 
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see oed_eval_kernel / launch_device
     if (tid == 0 && P.use_tma) mbar_init(bar, 1);
     __syncthreads();
     uint32_t phase = 0;
