@@ -96,3 +96,24 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 for pat in (r"(from|import)\s+oracle", r"liboed_oracle", r"oed_oracle", r"oracle/"):
                     assert not re.search(pat, src), (pat, os.path.join(dirpath, f))
+
+
+def test_header_is_valid_c_and_matches_the_ctypes_mirror(tmp_path):
+    """include/dynoed.h must compile as plain C (the Julia `ccall` / cgo-style consumers see a C
+    ABI), and the struct sizes the ctypes mirror assumes must equal the compiler's."""
+    import ctypes
+    import shutil
+    import subprocess
+    from dynamicoed.jl_b200 import runtime
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "t.c"
+    src.write_text('#include "dynoed.h"\n#include <stdio.h>\nint main(void){printf("%zu %zu %zu\\n",'
+                   'sizeof(dynoed_model_info), sizeof(dynoed_problem_desc), sizeof(dynoed_kernel_stats));return 0;}\n')
+    exe = tmp_path / "t"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", inc, str(src), "-o", str(exe)], check=True)
+    sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [ctypes.sizeof(runtime.ModelInfo), ctypes.sizeof(runtime.ProblemDesc),
+                     ctypes.sizeof(runtime.KernelStats)]

@@ -565,3 +565,35 @@ def test_forward_only_gradient_mode(name, method, oracles, built_library):
     assert np.all(np.isnan(g[:, ctrl_cols]))
     assert rel_rows(g[:, keep], og[:, keep]) < RTOL
     assert ctx.argmin()[0] == int(np.argmin(oc))
+
+
+def test_stiff_full_size_properties(built_library):
+    """Robertson (config 4) at batch size 65,536 through device buffers: determinism, F linear in
+    the weights with the SAME basis for every design (no controls / ICs => x, G do not depend on
+    the design), d/dtau = tr(Lambda) + 1, arg-min, and the fixed-controls shortcut reproducing the
+    Rosenbrock integration."""
+    import torch
+    n = 65536
+    edges = D.graded_edges(10, 40, 1e-6, 10)
+    prob = D.OEDProblem(D.OEDSystem(models.robertson()), D.DCriterion(), alg=D.ROS3P(edges=edges))
+    ctx = prob.context()
+    des = stiff_designs("robertson", ctx.n_var, n, 5)
+    d = torch.from_numpy(des).cuda()
+    runs = []
+    for _ in range(2):
+        c = torch.empty(n, dtype=torch.float64, device="cuda"); g = torch.empty_like(d)
+        F = torch.empty((n, 1), dtype=torch.float64, device="cuda")
+        ctx.eval_batch(d, c, g, F)
+        runs.append((c.cpu().numpy(), g.cpu().numpy(), F.cpu().numpy()))
+    assert all(np.array_equal(a, b) for a, b in zip(*runs))
+    c, g, F = runs[0]
+    assert ctx.argmin() == (int(np.argmin(c)), float(c.min()))
+    basis = ctx.fim_basis(des[0])                          # [n_var, 1]; the same for every design here
+    assert rel(F[:, 0], des @ basis[:, 0]) < 1e-12
+    M = F[:, 0] + des[:, 10]
+    assert rel(c, 1.0 / M + des[:, 10]) < 1e-13            # DCriterion, np = 1
+    assert rel(g[:, 10], -1.0 / M ** 2 + 1.0) < 1e-12
+    assert rel_rows(g[:, :10], (-1.0 / M ** 2)[:, None] * basis[None, :10, 0]) < 1e-11
+    c2, g2 = np.empty(n), np.empty((n, 11))
+    ctx.eval_fixed_controls(basis, des, c2, g2, None)
+    assert rel(c2, c) < 1e-12 and rel_rows(g2, g) < 1e-11
