@@ -727,6 +727,17 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         rc = ensure_slot(ctx, ctx->slots[k], chunk, kidx, fim != nullptr);
         if (rc) return rc;
     }
+    // Pinned (page-locked, mapped) result arrays: the kernel stores crit / fim straight into host
+    // memory (posted PCIe writes, 8 + 8 nF bytes per design), which removes two of the three
+    // device-to-host copies per chunk; the gradient still travels as one bulk copy.
+    auto mapped = [](const void* p) -> double* {
+        if (!p || getenv("DYNOED_NO_ZEROCOPY")) return nullptr;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        return a.type == cudaMemoryTypeHost ? static_cast<double*>(a.devicePointer) : nullptr;
+    };
+    double* crit_map = mapped(crit);
+    double* fim_map = mapped(fim);
     // order after whatever the ctx stream was doing
     cudaEvent_t ev;
     CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -740,7 +751,8 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
                            cudaMemcpyHostToDevice, s.stream));
         EvalParams P = ctx->base;
         const int grid = grid_for(ctx, cnt, kidx);
-        P.designs = s.d_designs; P.crit = s.d_crit; P.grad = g ? s.d_grad : nullptr; P.fim = fim ? s.d_fim : nullptr;
+        P.designs = s.d_designs; P.crit = crit_map ? crit_map + off : s.d_crit; P.grad = g ? s.d_grad : nullptr;
+        P.fim = !fim ? nullptr : fim_map ? fim_map + off * nF : s.d_fim;
         P.xgrid = nullptr; P.traj = s.traj; P.n = cnt;
         P.part_val = ctx->part_val[par]; P.part_idx = ctx->part_idx[par];
         P.part_base = part_base; P.n_parts = total_parts; P.ticket_target = (unsigned int)total_parts;
@@ -752,11 +764,11 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         CU(ctx->model->launch(kidx == 2 ? kFwdOnly + ctx->method : ctx->method, g, ctx->ucoef, false, P, grid, ctx->tile,
                               smem_bytes(ctx), s.stream));
         ctx->launches++;
-        CU(cudaMemcpyAsync(crit + off, s.d_crit, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s.stream));
+        if (!crit_map) CU(cudaMemcpyAsync(crit + off, s.d_crit, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s.stream));
         if (g) CU(cudaMemcpyAsync(grad + off * ctx->n_var, s.d_grad, sizeof(double) * cnt * ctx->n_var,
                                   cudaMemcpyDeviceToHost, s.stream));
-        if (fim) CU(cudaMemcpyAsync(fim + off * nF, s.d_fim, sizeof(double) * cnt * nF, cudaMemcpyDeviceToHost,
-                                    s.stream));
+        if (fim && !fim_map) CU(cudaMemcpyAsync(fim + off * nF, s.d_fim, sizeof(double) * cnt * nF, cudaMemcpyDeviceToHost,
+                                                s.stream));
     }
     for (int k = 0; k < kSlots && k < nchunks; ++k) {
         CU(cudaEventRecord(ev, ctx->slots[k].stream));

@@ -597,3 +597,19 @@ def test_stiff_full_size_properties(built_library):
     c2, g2 = np.empty(n), np.empty((n, 11))
     ctx.eval_fixed_controls(basis, des, c2, g2, None)
     assert rel(c2, c) < 1e-12 and rel_rows(g2, g) < 1e-11
+
+
+def test_pinned_host_buffers_take_the_zero_copy_result_path(built_library):
+    """Page-locked result arrays: crit / fim are stored by the kernel straight into host memory;
+    numbers must equal the pageable (copy) path bit for bit."""
+    import torch
+    ctx = make_problem("lv_fishing", D.FisherDCriterion).context()
+    des = random_designs("lv_fishing", 71, 20000, 8)
+    c, g, F = ctx.evaluate(des)                                    # pageable numpy arrays
+    hp = torch.from_numpy(des).pin_memory()
+    hc = torch.full((len(des),), float("nan"), dtype=torch.float64).pin_memory()
+    hg = torch.empty((len(des), 71), dtype=torch.float64).pin_memory()
+    hf = torch.full((len(des), 3), float("nan"), dtype=torch.float64).pin_memory()
+    ctx.eval_batch(hp.numpy(), hc.numpy(), hg.numpy(), hf.numpy())
+    assert np.array_equal(hc.numpy(), c) and np.array_equal(hg.numpy(), g) and np.array_equal(hf.numpy(), F)
+    assert ctx.argmin()[0] == int(np.argmin(c))
