@@ -231,16 +231,28 @@ def OptimizationProblem(prob: OEDProblem, AD=None, u0=None, p=None, *, integer_c
     ctx = prob.context()
     n_var = ctx.n_var
 
+    # Ipopt asks for f(u) and grad f(u) at the same point in separate callbacks: evaluate both in
+    # ONE launch (the gradient kernel also returns the objective) and serve the second from a
+    # one-entry cache keyed by the design's bytes.
+    cache = {"key": None, "c": None, "g": None}
+
+    def _both(u):
+        u = np.ascontiguousarray(np.asarray(u, dtype=np.float64).reshape(1, n_var))
+        key = u.tobytes()
+        if cache["key"] != key:
+            c, g, _ = ctx.evaluate(u, grad=True, fim=False)
+            cache.update(key=key, c=float(c[0]), g=g[0].copy())
+        return cache
+
     def objective(u, _p=None):
-        c, _, _ = ctx.evaluate(np.asarray(u, dtype=np.float64).reshape(1, n_var), grad=False, fim=False)
-        return float(c[0])
+        return _both(u)["c"]
 
     def gradient(G, u, _p=None):
-        _, g, _ = ctx.evaluate(np.asarray(u, dtype=np.float64).reshape(1, n_var), grad=True, fim=False)
+        g = _both(u)["g"]
         if G is not None:
-            G[:] = g[0]
+            G[:] = g
             return G
-        return g[0]
+        return g.copy()
 
     cons = cons_j = lcons = ucons = None
     if isinstance(constraints, ConstraintsSystem):

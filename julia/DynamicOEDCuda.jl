@@ -168,16 +168,19 @@ function Optimization.OptimizationProblem(prob::OEDProblem, backend::CudaBackend
     ctx = DynoedContext(prob, backend)
     buf = zeros(ctx.n_var, 1); c1 = zeros(1); g1 = zeros(ctx.n_var, 1)
 
-    objective = (u, _) -> begin
-        buf[:, 1] .= u
-        eval_batch!(ctx, buf, c1)[1]
-    end
-    gradient! = (G, u, _) -> begin
-        buf[:, 1] .= u
-        eval_batch!(ctx, buf, c1; grad = g1)
-        G .= view(g1, :, 1)
+    # Ipopt asks for f(u) and grad f(u) at the same point in separate callbacks: one launch serves
+    # both (the gradient kernel also returns the objective); `last` is a one-entry cache.
+    last = fill(NaN, ctx.n_var)
+    both! = u -> begin
+        if !(last == u)                       # NaN-initialised => first call always evaluates
+            buf[:, 1] .= u
+            eval_batch!(ctx, buf, c1; grad = g1)
+            last .= u
+        end
         nothing
     end
+    objective = (u, _) -> (both!(u); c1[1])
+    gradient! = (G, u, _) -> (both!(u); G .= view(g1, :, 1); nothing)
 
     if isa(constraints, ConstraintsSystem)          # src/problem.jl:123-128
         (_, cons), cons_lb, cons_ub = ModelingToolkit.generate_function(constraints, expression = Val{false})
