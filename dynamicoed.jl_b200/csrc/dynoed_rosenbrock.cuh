@@ -17,8 +17,8 @@
 // The reference factors the dense n_aug x n_aug matrix instead.
 //
 // Gradient: d/dw and d/dtau need no extra integration; d/d(unknown initial conditions) is carried
-// as forward-mode dual parts through the whole scheme (the way the reference's ForwardDiff does,
-// /root/reference/src/problem.jl:154), one dual direction per unknown initial condition.
+// as a forward-mode dual part through the whole scheme (the way the reference's ForwardDiff does,
+// /root/reference/src/problem.jl:154), one integration pass per unknown initial condition.
 // Controls as design variables are not differentiated by this integrator (DYNOED_EUNSUPPORTED).
 #pragma once
 #include <type_traits>
@@ -304,8 +304,13 @@ template <class M, class Stepper, bool GRAD>
 __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams P) {
     constexpr int NX = M::NX, NP = M::NP, NZ = M::NZ, NF = M::NF, NOBS = M::NOBS, NCTRL = M::NCTRL;
     constexpr int NCU = NCTRL > 0 ? NCTRL : 1, NQ = NOBS * NF;
-    constexpr int KD = (GRAD && M::NIC > 0) ? M::NIC : 1;
-    using T = typename std::conditional<(GRAD && M::NIC > 0), Dual<KD>, double>::type;
+    // unknown initial conditions: ONE dual direction per integration pass (NIC passes).  Carrying all
+    // directions at once (Dual<NIC>) is 1 + NIC units of arithmetic instead of 2 NIC, but its register
+    // footprint spills 3.6-4.9 KB per lane for models of chem6's size (2.3-2.9 KB this way) and
+    // measured 1.1x (ROS2) to 1.4x (ROS3P) slower on B200.
+    constexpr bool DUAL = GRAD && M::NIC > 0;
+    constexpr int NDIR = DUAL ? M::NIC : 1;
+    using T = typename std::conditional<DUAL, Dual<1>, double>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     double* tile_buf = reinterpret_cast<double*>(smem_raw + 128);
@@ -345,80 +350,92 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams 
         if (tid < count) {
             double* row = tile_buf + (size_t)tid * n_var;
             const long long g = g0 + tid;
-            T z[NZ], F[NF];
-#pragma unroll
-            for (int a = 0; a < NX; ++a) z[a] = T(P.x0[a]);
-#pragma unroll
-            for (int a = 0; a < NX * NP; ++a) z[NX + a] = T(P.G0[a]);
-            if constexpr (M::NIC > 0) {
-#pragma unroll
-                for (int a = 0; a < M::NIC; ++a) {
-                    T v(row[P.ic_off + a]);
-                    if constexpr (GRAD) v.d[a] = 1.0;
-                    z[M::ic_state(a)] = v;
-                }
-            }
-#pragma unroll
-            for (int a = 0; a < NF; ++a) F[a] = T(0.0);
             double* pq = P.traj + ((size_t)blockIdx.x * N * NQ) * kMaxTile + tid;
-            double* xg = P.xgrid ? P.xgrid + (size_t)g * (N + 1) * (NZ + NF) : nullptr;
-            if (xg) {
+            double Ls[NF], L[NF], icg[M::NIC > 0 ? M::NIC : 1];
+            for (int dir = 0; dir < NDIR; ++dir) {
+                T z[NZ], F[NF];
 #pragma unroll
-                for (int a = 0; a < NZ; ++a) xg[a] = value_of(z[a]);
+                for (int a = 0; a < NX; ++a) z[a] = T(P.x0[a]);
 #pragma unroll
-                for (int a = 0; a < NF; ++a) xg[NZ + a] = 0.0;
-            }
-            for (int j = 0; j < N; ++j) {
-                double u[NCU], w[NOBS], c[M::NCONST];
+                for (int a = 0; a < NX * NP; ++a) z[NX + a] = T(P.G0[a]);
+                if constexpr (M::NIC > 0) {
 #pragma unroll
-                for (int k = 0; k < NCTRL; ++k) u[k] = row[P.ctrl_off[k] + __ldg(P.indicators + k * N + j)];
-#pragma unroll
-                for (int i = 0; i < NOBS; ++i) w[i] = row[P.w_off[i] + __ldg(P.indicators + (NCTRL + i) * N + j)];
-                M::consts(u, th, c);
-                T Pq[NQ];
-#pragma unroll
-                for (int a = 0; a < NQ; ++a) Pq[a] = T(0.0);
-                const int s0 = __ldg(P.first_step + j), s1 = __ldg(P.first_step + j + 1);
-                for (int s = s0; s < s1; ++s)
-                    Stepper::template step<M, T>(__ldg(P.step_t + s), __ldg(P.step_h + s), z, Pq, u, th, c);
-#pragma unroll
-                for (int i = 0; i < NOBS; ++i)
-#pragma unroll
-                    for (int k = 0; k < NF; ++k) F[k] = F[k] + w[i] * Pq[i * NF + k];
-                if (GRAD) {
-#pragma unroll
-                    for (int a = 0; a < NQ; ++a) pq[((size_t)j * NQ + a) * kMaxTile] = value_of(Pq[a]);
+                    for (int a = 0; a < M::NIC; ++a) {
+                        T v(row[P.ic_off + a]);
+                        if constexpr (GRAD) v.d[0] = (a == dir) ? 1.0 : 0.0;
+                        z[M::ic_state(a)] = v;
+                    }
                 }
+#pragma unroll
+                for (int a = 0; a < NF; ++a) F[a] = T(0.0);
+                double* xg = (P.xgrid && dir == 0) ? P.xgrid + (size_t)g * (N + 1) * (NZ + NF) : nullptr;
                 if (xg) {
-                    double* o = xg + (size_t)(j + 1) * (NZ + NF);
 #pragma unroll
-                    for (int a = 0; a < NZ; ++a) o[a] = value_of(z[a]);
+                    for (int a = 0; a < NZ; ++a) xg[a] = value_of(z[a]);
 #pragma unroll
-                    for (int a = 0; a < NF; ++a) o[NZ + a] = value_of(F[a]);
+                    for (int a = 0; a < NF; ++a) xg[NZ + a] = 0.0;
+                }
+                for (int j = 0; j < N; ++j) {
+                    double u[NCU], w[NOBS], c[M::NCONST];
+#pragma unroll
+                    for (int k = 0; k < NCTRL; ++k) u[k] = row[P.ctrl_off[k] + __ldg(P.indicators + k * N + j)];
+#pragma unroll
+                    for (int i = 0; i < NOBS; ++i) w[i] = row[P.w_off[i] + __ldg(P.indicators + (NCTRL + i) * N + j)];
+                    M::consts(u, th, c);
+                    T Pq[NQ];
+#pragma unroll
+                    for (int a = 0; a < NQ; ++a) Pq[a] = T(0.0);
+                    const int s0 = __ldg(P.first_step + j), s1 = __ldg(P.first_step + j + 1);
+                    for (int s = s0; s < s1; ++s)
+                        Stepper::template step<M, T>(__ldg(P.step_t + s), __ldg(P.step_h + s), z, Pq, u, th, c);
+#pragma unroll
+                    for (int i = 0; i < NOBS; ++i)
+#pragma unroll
+                        for (int k = 0; k < NF; ++k) F[k] = F[k] + w[i] * Pq[i * NF + k];
+                    if (GRAD && dir == 0) {
+#pragma unroll
+                        for (int a = 0; a < NQ; ++a) pq[((size_t)j * NQ + a) * kMaxTile] = value_of(Pq[a]);
+                    }
+                    if (xg) {
+                        double* o = xg + (size_t)(j + 1) * (NZ + NF);
+#pragma unroll
+                        for (int a = 0; a < NZ; ++a) o[a] = value_of(z[a]);
+#pragma unroll
+                        for (int a = 0; a < NF; ++a) o[NZ + a] = value_of(F[a]);
+                    }
+                }
+
+                if (dir == 0) {
+                    // ---- criterion epilogue ----
+                    const double tau = row[P.tau_off];
+                    double Fv[NF], value;
+#pragma unroll
+                    for (int a = 0; a < NF; ++a) Fv[a] = value_of(F[a]);
+                    criterion_eval<NP>(Fv, tau, P.criterion, value, L);
+                    const double obj = value + tau;
+                    P.crit[g] = obj;
+                    if (P.fim) {
+#pragma unroll
+                        for (int a = 0; a < NF; ++a) P.fim[g * NF + a] = Fv[a];
+                    }
+                    if (obj < best_val) { best_val = obj; best_idx = P.index_base + g; }
+#pragma unroll
+                    for (int jj = 0; jj < NP; ++jj)
+#pragma unroll
+                        for (int ii = 0; ii <= jj; ++ii) Ls[tri(ii, jj)] = (ii == jj ? 1.0 : 2.0) * L[tri(ii, jj)];
+                }
+                if constexpr (DUAL) {   // <Lambda, dF/dx0_dir> with the symmetric pairing
+                    double sd = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NF; ++k) sd = fma(Ls[k], dual_part(F[k], 0), sd);
+#pragma unroll
+                    for (int a = 0; a < M::NIC; ++a)
+                        if (a == dir) icg[a] = sd;          // static indexing keeps icg in registers
                 }
             }
-
-            // ---- criterion epilogue ----
-            const double tau = row[P.tau_off];
-            double Fv[NF], value, L[NF];
-#pragma unroll
-            for (int a = 0; a < NF; ++a) Fv[a] = value_of(F[a]);
-            criterion_eval<NP>(Fv, tau, P.criterion, value, L);
-            const double obj = value + tau;
-            P.crit[g] = obj;
-            if (P.fim) {
-#pragma unroll
-                for (int a = 0; a < NF; ++a) P.fim[g * NF + a] = Fv[a];
-            }
-            if (obj < best_val) { best_val = obj; best_idx = P.index_base + g; }
 
             // ---- gradient: <Lambda, .> with the symmetric pairing (off-diagonals count twice) ----
             if (GRAD) {
-                double Ls[NF];
-#pragma unroll
-                for (int jj = 0; jj < NP; ++jj)
-#pragma unroll
-                    for (int ii = 0; ii <= jj; ++ii) Ls[tri(ii, jj)] = (ii == jj ? 1.0 : 2.0) * L[tri(ii, jj)];
                 double wb[NOBS];
                 int wk[NOBS];
 #pragma unroll
@@ -441,12 +458,7 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams 
                 for (int i = 0; i < NOBS; ++i)
                     if (wk[i] >= 0) row[P.w_off[i] + wk[i]] = wb[i];
 #pragma unroll
-                for (int a = 0; a < M::NIC; ++a) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int k = 0; k < NF; ++k) s = fma(Ls[k], dual_part(F[k], a), s);
-                    row[P.ic_off + a] = s;
-                }
+                for (int a = 0; a < M::NIC; ++a) row[P.ic_off + a] = icg[a];
                 // controls are not differentiated by this kernel: their entries say so
                 for (int k = 0; k < NCTRL; ++k) {
                     int last = -1;
