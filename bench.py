@@ -363,7 +363,7 @@ def main():
                         "d2h_bytes_per_step": n * (1 + n_var + 3) * 8, "steps": e2e_steps,
                         "host_memory": "pinned"},
                 "gpu_launches": int(launches), "clocks": clocks, "sub_metrics": sub}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only
             orc, threads = cpu_oracle()
             v, ns, dt = time_cpu(orc, threads, make_designs(4 * N_PER_GPU, 71, 20262), 12.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
