@@ -613,3 +613,31 @@ def test_pinned_host_buffers_take_the_zero_copy_result_path(built_library):
     ctx.eval_batch(hp.numpy(), hc.numpy(), hg.numpy(), hf.numpy())
     assert np.array_equal(hc.numpy(), c) and np.array_equal(hg.numpy(), g) and np.array_equal(hf.numpy(), F)
     assert ctx.argmin()[0] == int(np.argmin(c))
+
+
+def test_plain_c_consumer_of_the_abi(tmp_path, built_library):
+    """examples/c_abi_demo.c — no Python between the caller and libdynoed_cuda.so: the grid and the
+    layout are written out by hand in C.  Its numbers must equal the Python host's, and design 0 is
+    the reference test's LV optimum (F = [1.2025, 0.3721, 2.6536])."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    libdir = os.path.dirname(runtime.LIB_PATH)
+    exe = str(tmp_path / "c_abi_demo")
+    subprocess.run([cc, "-std=c99", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_abi_demo.c"),
+                    "-o", exe, "-L", libdir, "-ldynoed_cuda", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    rows = [[float(x) for x in ln.split()[3::2][:1]] + [float(v) for v in ln.split()[5:8]] +
+            [float(ln.split()[9]), float(ln.split()[11]), float(ln.split()[13])] for ln in out[:4]]
+    des = np.zeros((4, 71))
+    des[0, 0] = 0.62; des[0, 36:40] = 1.0; des[0, 66:70] = 1.0; des[0, 70] = 1.0
+    for j in range(1, 4):
+        des[j] = [((j * 37 + k * 11) % 17) / 17.0 for k in range(71)]
+        des[j, 70] = 0.1 * j
+    c, g, F = make_problem("lv_fishing", D.FisherDCriterion).context().evaluate(des)
+    for j, r in enumerate(rows):
+        assert r[0] == c[j] and r[1:4] == list(F[j]) and r[4:] == [g[j, 0], g[j, 39], g[j, 70]]
+    assert np.allclose(F[0], [1.20249794, 0.37211035, 2.6535698], rtol=2e-6)     # RK4 m=4 vs exact: 6e-8
+    assert out[4].split()[1] == str(int(np.argmin(c)))
