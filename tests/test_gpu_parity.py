@@ -641,3 +641,41 @@ def test_plain_c_consumer_of_the_abi(tmp_path, built_library):
         assert r[0] == c[j] and r[1:4] == list(F[j]) and r[4:] == [g[j, 0], g[j, 39], g[j, 70]]
     assert np.allclose(F[0], [1.20249794, 0.37211035, 2.6535698], rtol=2e-6)     # RK4 m=4 vs exact: 6e-8
     assert out[4].split()[1] == str(int(np.argmin(c)))
+
+
+@pytest.mark.parametrize("crit_cls", CRITS)
+def test_four_parameter_model_exercises_the_register_jacobi_path(crit_cls, built_library):
+    """np = 4 (three rate constants + one unknown initial condition): the in-kernel criteria use the
+    cyclic-Jacobi eigen-decomposition in registers instead of the np <= 2 closed forms.  All six
+    criteria and their gradients (controls, IC, weights, tau) against the numpy oracle, for the
+    adjoint kernel and the forward-only kernel."""
+    from dynamicoed.jl_b200.symbolic import (Differential, Eq, ODESystem, independent_variable,
+                                             observed_variables, parameters, variables)
+    from oracle.oed_oracle import Oracle
+    t = independent_variable("t")
+    a = variables("a", 1.0, tunable=True, bounds=(0.5, 1.5))           # unknown IC on the leading state
+    b, c3 = variables("b c", [0.5, 0.2])
+    k = parameters("k[1] k[2] k[3]", [0.7, 1.3, 0.4], tunable=True)
+    v = parameters("v", 0.0, input=True, measurement_rate=0.5, bounds=(0.0, 1.0))
+    obs = observed_variables("o[1] o[2] o[3]", measurement_rate=0.25)
+    Dt = Differential(t)
+    sysm = ODESystem([Eq(Dt(a), -k[0] * a * b + v), Eq(Dt(b), k[0] * a * b - k[1] * b * c3),
+                      Eq(Dt(c3), k[1] * b * c3 - k[2] * c3 + 0.1 * a)],
+                     t, tspan=(0.0, 2.0), observed=[Eq(obs[0], a), Eq(obs[1], b * c3), Eq(obs[2], c3)], name="np4")
+    prob = D.OEDProblem(D.OEDSystem(sysm), crit_cls(), alg=D.RK4(2))
+    ctx = prob.context()
+    assert ctx.info.np == 4 and ctx.info.nF == 10 and ctx.info.n_ic == 1
+    rng = np.random.Generator(np.random.Philox(9))
+    des = rng.random((160, ctx.n_var))
+    des[:, -1] = 1e-2 + 0.9 * des[:, -1]
+    des[:, prob.layout.ic_offset] = 0.5 + des[:, prob.layout.ic_offset]
+    des[:, prob.layout.w_offsets[0]:prob.layout.tau_offset] = 0.2 + 0.8 * des[:, prob.layout.w_offsets[0]:prob.layout.tau_offset]
+    c, g, F = ctx.evaluate(des)
+    oc, og, oF = Oracle(sysm, crit_cls().id, "rk4", 2).evaluate(des, grad=True)
+    den = np.maximum(np.abs(oc), 1e-300)
+    assert rel(F, oF) < RTOL and float(np.max(np.abs(c - oc) / den)) < 1e-9
+    assert rel_rows(g, og) < 1e-8                       # eigen-criteria: cond(F + tau I) amplifies rounding
+    c2, g2, _ = ctx.evaluate(des, flags=runtime.GRAD_NO_CONTROLS)
+    lay = prob.layout
+    keep = [k_ for k_ in range(ctx.n_var) if not (lay.control_offsets[0] <= k_ < lay.control_offsets[0] + lay.control_lengths[0])]
+    assert float(np.max(np.abs(c2 - oc) / den)) < 1e-9 and rel_rows(g2[:, keep], og[:, keep]) < 1e-8
