@@ -72,7 +72,14 @@ def build_default(force: bool = False, regenerate: bool = True, verbose: bool = 
 def build_user_model(src: str, info: dict, cache_dir: str | None = None) -> str:
     """Compile a library that contains exactly one emitted model; returns the .so path."""
     cache_dir = cache_dir or os.path.join(_HERE, "_user_models")
-    key = hashlib.sha256(src.encode()).hexdigest()[:16]
+    h = hashlib.sha256(src.encode())
+    # the kernel template and the ABI are part of the key: a cached library built against older
+    # headers must never be loaded by a newer host
+    for f in sorted(os.listdir(CSRC)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(CSRC, f), "rb").read())
+    h.update(open(os.path.join(_HERE, "..", "include", "dynoed.h"), "rb").read())
+    key = h.hexdigest()[:16]
     d = os.path.join(cache_dir, key)
     out = os.path.join(d, f"libdynoed_{key}.so")
     if os.path.exists(out):
