@@ -1152,6 +1152,8 @@ int dynoed_fp64_microbench(int device, int variant, double* ginstr_per_s) {
             case 5: fp64_variant_kernel<5><<<grid, block>>>(out, iters, 1.0, 0.999999); break;
             case 6: fp64_variant_kernel<6><<<grid, block>>>(out, iters, 1.0, 0.999999); break;
             case 7: fp64_variant_kernel<7><<<grid, block>>>(out, iters, 1.0, 0.999999); break;
+            case 8: dmma_probe_kernel<0><<<grid, block>>>(out, iters, 1.0); break;
+            case 9: dmma_probe_kernel<1><<<grid, block>>>(out, iters, 1.0); break;
             default: fp64_peak_kernel<<<grid, block>>>(out, iters, 1.0); break;
         }
         CU(cudaEventRecord(e1, 0));
@@ -1160,7 +1162,12 @@ int dynoed_fp64_microbench(int device, int variant, double* ginstr_per_s) {
         if (rep > 0) best = std::min(best, ms);
     }
     CU(cudaGetLastError());
-    if (ginstr_per_s) *ginstr_per_s = 8.0 * 16 * (double)iters * grid * block / (best * 1e-3) / 1e9;
+    // variants 0..7: 8 chains x 16 FP64 instructions per iteration and thread; 8: 16 DMMA (each
+    // 8x8x4 = 256 FMA per warp = 8 per thread); 9: 16 DMMA + 32 DFMA per iteration and thread
+    double per_iter = 8.0 * 16;
+    if (variant == 8) per_iter = 16.0 * 8;            // thread-level FMA equivalents
+    if (variant == 9) per_iter = 16.0 * 8 + 32.0;
+    if (ginstr_per_s) *ginstr_per_s = per_iter * (double)iters * grid * block / (best * 1e-3) / 1e9;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
     return DYNOED_OK;
 }

@@ -1165,4 +1165,35 @@ __global__ void __launch_bounds__(256) fp64_variant_kernel(double* out, int iter
     out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = s;
 }
 
+// FP64 tensor-core probe: chains of mma.sync.m8n8k4.f64 (SASS DMMA), optionally interleaved with
+// DFMA chains, to see whether the two share one pipe on sm_100a (variants 8, 9 of the microbench).
+//   MIX = 0: DMMA only     MIX = 1: DMMA + as many DFMA chains
+template <int MIX>
+__global__ void __launch_bounds__(256) dmma_probe_kernel(double* out, int iters, double seed) {
+    double a = seed + threadIdx.x * 1e-3, b = 0.999 + threadIdx.x * 1e-6;
+    double c0[4] = {1e-9, 2e-9, 3e-9, 4e-9}, c1[4] = {5e-9, 6e-9, 7e-9, 8e-9};   // 4 accumulator pairs
+    double f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = seed + i + threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c0[q]), "+d"(c1[q]) : "d"(a), "d"(b));
+            if (MIX) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = fma(f[i], 0.999999, 1e-9);
+            }
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s += c0[q] + c1[q];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += f[i];
+    out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace dynoed

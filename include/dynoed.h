@@ -182,7 +182,9 @@ int dynoed_criterion_batch(int device, int criterion, int np, const double* F_pa
 int dynoed_fp64_peak(int device, void* cuda_stream, double* tflops, double* ms);
 
 /* FP64 instruction throughput (thread-level Ginstr/s) for operand patterns: 0 DFMA reg*const+const,
- * 1 DFMA three registers, 2 DFMA two registers, 3 DMUL, 4 DADD, 5 DFMA reg*uniform+reg */
+ * 1 DFMA three registers, 2 DFMA two registers, 3 DMUL, 4 DADD, 5 DFMA reg*uniform+reg,
+ * 6 DFMA with a shared multiplicand (operand reuse), 7 DFMA second factor from two registers,
+ * 8 DMMA m8n8k4 chains, 9 DMMA + DFMA mix (8, 9 in thread-level FMA equivalents) */
 int dynoed_fp64_microbench(int device, int variant, double* ginstr_per_s);
 
 /* CUDA-event timing of the evaluation kernel itself (device-pointer path), for the roofline */

@@ -8,7 +8,7 @@ from dynamicoed.jl_b200 import models, runtime
 if "--micro" in sys.argv:
     pk = runtime.fp64_peak()[0]
     print("fp64 peak TF", pk)
-    for v, name in enumerate(["DFMA r*c+c", "DFMA r*r+r (3 regs)", "DFMA r*r+same (2 regs)", "DMUL r*r", "DADD r+r", "DFMA r*U+r", "DFMA B*r+r (B shared)", "DFMA r*C+r (C of 2 regs)"]):
+    for v, name in enumerate(["DFMA r*c+c", "DFMA r*r+r (3 regs)", "DFMA r*r+same (2 regs)", "DMUL r*r", "DADD r+r", "DFMA r*U+r", "DFMA B*r+r (B shared)", "DFMA r*C+r (C of 2 regs)", "DMMA m8n8k4 (FMA equiv.)", "DMMA + DFMA mix (FMA equiv.)"]):
         g = runtime.fp64_microbench(v)
         print(f"variant {v} {name:28s} {g:9.1f} Ginstr/s  = {g/ (pk*1e3/2):.3f} of DFMA-chain rate")
 method = D.Tsit5(4) if "--tsit5" in sys.argv else D.RK4(4)
