@@ -525,7 +525,8 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
 void dynoed_destroy(dynoed_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    cudaDeviceSynchronize();   // launches may still be running on a caller-owned stream: scratch is freed below
+    cudaGetLastError();
     for (auto& s : ctx->slots) {
         if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
         cudaFree(s.d_designs); cudaFree(s.d_crit); cudaFree(s.d_grad); cudaFree(s.d_fim); cudaFree(s.traj);
