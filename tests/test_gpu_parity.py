@@ -679,3 +679,28 @@ def test_four_parameter_model_exercises_the_register_jacobi_path(crit_cls, built
     lay = prob.layout
     keep = [k_ for k_ in range(ctx.n_var) if not (lay.control_offsets[0] <= k_ < lay.control_offsets[0] + lay.control_lengths[0])]
     assert float(np.max(np.abs(c2 - oc) / den)) < 1e-9 and rel_rows(g2[:, keep], og[:, keep]) < 1e-8
+
+
+@pytest.mark.parametrize("crit_cls", CRITS)
+def test_reference_integer_optimum_by_exhaustive_batch(crit_cls, built_library):
+    """test/references/1D.jl:68-107 ("Integer": Juniper + Ipopt): x' = p x, 10 measurement decisions,
+    0.05 sum(w) <= 0.2.  The batch evaluator makes branch-and-bound unnecessary at this size: ALL
+    feasible {0,1}^10 designs are evaluated in one call (full integration and the fixed-controls
+    shortcut) and the arg-min is the reference's optimum w* = [0,0,0,1,1,1,1,0,0,0], objective
+    -1.2823515846720533e-2 (Fisher*) or 2.0 (A/D/E) within the reference's tolerances."""
+    import itertools
+    prob = D.OEDProblem(D.OEDSystem(models.one_d()), crit_cls(), alg=D.Tsit5(8))
+    ctx = prob.context()
+    W = np.array([w for w in itertools.product((0.0, 1.0), repeat=10) if 0.05 * sum(w) <= 0.2 + 1e-12])
+    des = np.concatenate([W, np.ones((len(W), 1))], axis=1)          # tau at its upper bound
+    c, g, F = ctx.evaluate(des)
+    best = int(np.argmin(c))
+    assert ctx.argmin()[0] == best
+    assert np.array_equal(W[best], [0, 0, 0, 1, 1, 1, 1, 0, 0, 0])
+    golden = -1.2823515846720533e-2 if crit_cls().id <= 2 else 2.0
+    assert np.isclose(c[best], golden, atol=1e-2, rtol=1e-1)
+    assert abs(F[best, 0] - 0.012813544228654607) < 1e-9              # exact int_0.3^0.7 t^2 e^{-4t} dt
+    basis = ctx.fim_basis(des[0])                                     # no controls: one basis for all
+    c2 = np.empty(len(W))
+    ctx.eval_fixed_controls(basis, des, c2, None, None)
+    assert int(np.argmin(c2)) == best and rel(c2, c) < 1e-12
