@@ -15,6 +15,10 @@
  *   - a ctx is bound to one device and is not re-entrant: one ctx per host thread / stream.
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
  *     DYNOED_ECUDA.
+ *   - stream order is kept: whatever is enqueued on the ctx stream after an evaluation sees its
+ *     results.  Two consecutive dynoed_eval_batch_async calls of one ctx on DISJOINT buffers may
+ *     overlap on the device (the second starts while the first drains); calls that share a
+ *     buffer, or that come from different contexts, never do.
  */
 #ifndef DYNOED_H
 #define DYNOED_H
