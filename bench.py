@@ -395,7 +395,7 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks, "sub_metrics": sub}
         if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only
             orc, threads = cpu_oracle()
-            v, ns, dt = time_cpu(orc, threads, make_designs(4 * N_PER_GPU, 71, 20262), 12.0)
+            v, ns, dt = time_cpu(orc, threads, make_designs(4 * N_PER_GPU, 71, 20262), 20.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{ns} designs of the same workload (same generator), "
                                               f"criterion + full forward-mode gradient, {dt:.1f} s"}
