@@ -103,6 +103,9 @@ static cudaError_t launch_model(int method, bool grad, bool uc, bool pdl, const 
     if (method == DYNOED_ROS3P)
         return grad ? launch_ros<M, RosenbrockStepper<TabROS3P>, true>(pdl, P, grid, block, smem, st)
                     : launch_ros<M, RosenbrockStepper<TabROS3P>, false>(pdl, P, grid, block, smem, st);
+    if (method == DYNOED_RODAS3)
+        return grad ? launch_ros<M, RosenbrockStepper<TabRODAS3>, true>(pdl, P, grid, block, smem, st)
+                    : launch_ros<M, RosenbrockStepper<TabRODAS3>, false>(pdl, P, grid, block, smem, st);
     // forward-only gradient mode of the explicit tableaus (kFwdOnly + method)
     if (method == kFwdOnly + DYNOED_RK4) return launch_ros<M, ExplicitStepper<TabRK4>, true>(pdl, P, grid, block, smem, st);
     return launch_ros<M, ExplicitStepper<TabTsit5>, true>(pdl, P, grid, block, smem, st);
@@ -127,6 +130,9 @@ static cudaError_t attrs_model(int method, bool grad, bool uc, int block, size_t
     if (method == DYNOED_ROS3P)
         return grad ? attrs_ros<M, RosenbrockStepper<TabROS3P>, true>(block, smem, fa, bps)
                     : attrs_ros<M, RosenbrockStepper<TabROS3P>, false>(block, smem, fa, bps);
+    if (method == DYNOED_RODAS3)
+        return grad ? attrs_ros<M, RosenbrockStepper<TabRODAS3>, true>(block, smem, fa, bps)
+                    : attrs_ros<M, RosenbrockStepper<TabRODAS3>, false>(block, smem, fa, bps);
     if (method == kFwdOnly + DYNOED_RK4) return attrs_ros<M, ExplicitStepper<TabRK4>, true>(block, smem, fa, bps);
     return attrs_ros<M, ExplicitStepper<TabTsit5>, true>(block, smem, fa, bps);
 }
@@ -361,9 +367,9 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     if (!m) return fail(nullptr, DYNOED_ENOMODEL, std::string("unknown model: ") + (d->model ? d->model : "(null)"));
     const dynoed_model_info& mi = m->info;
     if (d->criterion < 0 || d->criterion > 5) return fail(nullptr, DYNOED_EINVAL, "criterion out of range");
-    if (d->method < DYNOED_RK4 || d->method > DYNOED_ROS3P)
+    if (d->method < DYNOED_RK4 || d->method > DYNOED_RODAS3)
         return fail(nullptr, DYNOED_EUNSUPPORTED, "unsupported integration method");
-    const bool rosenbrock = d->method == DYNOED_ROS2 || d->method == DYNOED_ROS3P;
+    const bool rosenbrock = d->method == DYNOED_ROS2 || d->method == DYNOED_ROS3P || d->method == DYNOED_RODAS3;
     if (rosenbrock && !mi.autonomous)
         return fail(nullptr, DYNOED_EUNSUPPORTED, "the Rosenbrock integrators need an autonomous right-hand side");
     const int N = d->n_intervals;
@@ -399,7 +405,7 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     ctx->model = m;
     ctx->method = d->method;
     ctx->stages = d->method == DYNOED_RK4 ? TabRK4::S : d->method == DYNOED_TSIT5 ? TabTsit5::S
-                : d->method == DYNOED_ROS2 ? TabROS2::S : TabROS3P::S;
+                : d->method == DYNOED_ROS2 ? TabROS2::S : d->method == DYNOED_ROS3P ? TabROS3P::S : TabRODAS3::S;
     ctx->rosenbrock = rosenbrock;
     ctx->criterion = d->criterion;
     ctx->n_intervals = N;

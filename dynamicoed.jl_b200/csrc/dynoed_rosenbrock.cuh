@@ -78,7 +78,7 @@ struct TabROS2 {
     __host__ __device__ static constexpr double a(int i, int j) { return (i == 1 && j == 0) ? 1.0 / gamma : 0.0; }
     __host__ __device__ static constexpr double c(int i, int j) { return (i == 1 && j == 0) ? -2.0 / gamma : 0.0; }
     __host__ __device__ static constexpr double m(int i) { return i == 0 ? 1.5 / gamma : 0.5 / gamma; }
-    __host__ __device__ static constexpr bool same_stage_state(int i) { return false; }
+    __host__ __device__ static constexpr bool same_stage_state(int) { return false; }
 };
 // ROS3P (Lang, Verwer 2001): 3 stages, order 3, A-stable (R(inf) = 0.73), two function evaluations
 // (stages 2 and 3 share their stage state).
@@ -97,6 +97,23 @@ struct TabROS3P {
         return i == 0 ? 2.0 : i == 1 ? 5.773502691896258e-01 : 4.226497308103742e-01;
     }
     __host__ __device__ static constexpr bool same_stage_state(int i) { return i == 2; }
+};
+
+// RODAS3 (Sandu, Verwer, Blom, Spee, Carmichael, Potra 1997): 4 stages, order 3, stiffly accurate
+// and L-stable (R(inf) = 0), three function evaluations (stages 1 and 2 share their stage state).
+struct TabRODAS3 {
+    static constexpr int S = 4;
+    static constexpr double gamma = 0.5;
+    __host__ __device__ static constexpr double a(int i, int j) {
+        return (i == 2 && j == 0) ? 2.0 : (i == 3 && j == 0) ? 2.0 : (i == 3 && j == 2) ? 1.0 : 0.0;
+    }
+    __host__ __device__ static constexpr double c(int i, int j) {
+        return (i == 1 && j == 0) ? 4.0
+             : (i == 2 && j == 0) ? 1.0 : (i == 2 && j == 1) ? -1.0
+             : (i == 3 && j == 0) ? 1.0 : (i == 3 && j == 1) ? -1.0 : (i == 3 && j == 2) ? -8.0 / 3.0 : 0.0;
+    }
+    __host__ __device__ static constexpr double m(int i) { return i == 0 ? 2.0 : i == 1 ? 0.0 : 1.0; }
+    __host__ __device__ static constexpr bool same_stage_state(int i) { return i == 1; }
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -238,10 +255,12 @@ __device__ __forceinline__ void rosenbrock_step(double t, double h, T (&z)[M::NZ
     }
 #pragma unroll
     for (int s = 0; s < S; ++s) {
+        if (RT::m(s) != 0.0) {
 #pragma unroll
-        for (int a = 0; a < NZ; ++a) z[a] = z[a] + RT::m(s) * Uz[s][a];
+            for (int a = 0; a < NZ; ++a) z[a] = z[a] + RT::m(s) * Uz[s][a];
 #pragma unroll
-        for (int a = 0; a < NQ; ++a) Pq[a] = Pq[a] + RT::m(s) * Uq[s][a];
+            for (int a = 0; a < NQ; ++a) Pq[a] = Pq[a] + RT::m(s) * Uq[s][a];
+        }
     }
 }
 

@@ -64,6 +64,14 @@ class ROS3P:
     method: int = runtime.ROS3P
 
 
+@dataclass(frozen=True)
+class RODAS3:
+    """Fixed-grid Rosenbrock method RODAS3 (4 stages, order 3, stiffly accurate, L-stable); see `ROS2`."""
+    substeps: int = 4
+    edges: tuple | None = None
+    method: int = runtime.RODAS3
+
+
 def graded_edges(n_intervals: int, n_first: int, t_min_rel: float, substeps: int) -> tuple:
     """Substep edges for a stiff start-up transient: ``n_first`` geometrically spaced steps from
     ``t_min_rel`` (relative to the first interval) up to its end, ``substeps`` equal steps in every

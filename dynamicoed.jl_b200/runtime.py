@@ -14,10 +14,10 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdynoed_cuda.so")
 
-RK4, TSIT5, ROS2, ROS3P = 0, 1, 2, 3
+RK4, TSIT5, ROS2, ROS3P, RODAS3 = 0, 1, 2, 3, 4
 GRAD_NO_CONTROLS = 1    # eval flag: weights / tau / IC gradient only (forward sweep), control entries NaN
 METHODS = {"rk4": RK4, "RK4": RK4, "tsit5": TSIT5, "Tsit5": TSIT5, "ros2": ROS2, "ROS2": ROS2,
-           "ros3p": ROS3P, "ROS3P": ROS3P}
+           "ros3p": ROS3P, "ROS3P": ROS3P, "rodas3": RODAS3, "RODAS3": RODAS3}
 
 
 class DynoedError(RuntimeError):

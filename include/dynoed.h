@@ -55,6 +55,7 @@ extern "C" {
  * weights, tau and unknown initial conditions (not controls) */
 #define DYNOED_ROS2 2  /* 2 stages, order 2, L-stable */
 #define DYNOED_ROS3P 3 /* 3 stages, order 3, A-stable */
+#define DYNOED_RODAS3 4 /* 4 stages, order 3, stiffly accurate, L-stable */
 
 /* flags of dynoed_eval_batch[_async] */
 #define DYNOED_GRAD_NO_CONTROLS 1u /* gradient w.r.t. weights, tau and unknown initial conditions only:
@@ -82,7 +83,7 @@ typedef struct dynoed_problem_desc {
     uint32_t struct_size;      /* = sizeof(dynoed_problem_desc) */
     const char* model;         /* name of a compiled-in model */
     int32_t criterion;         /* DYNOED_FISHER_A ... */
-    int32_t method;            /* DYNOED_RK4 | DYNOED_TSIT5 | DYNOED_ROS2 | DYNOED_ROS3P */
+    int32_t method;            /* DYNOED_RK4 | DYNOED_TSIT5 | DYNOED_ROS2 | DYNOED_ROS3P | DYNOED_RODAS3 */
     int32_t n_intervals;       /* N: merged grid intervals (Timegrid.timespans) */
     const double* tgrid;       /* [N+1] merged grid points */
     int32_t substeps;          /* uniform substeps per merged interval (>0), or 0 with step_edges */

@@ -33,7 +33,7 @@ dynoed_library(path::AbstractString) = (LIB[] = String(path))
 
 # ---- mirrors of include/dynoed.h -------------------------------------------------------------
 const DYNOED_OK = Cint(0)
-const METHODS = Dict(:rk4 => Cint(0), :tsit5 => Cint(1), :ros2 => Cint(2), :ros3p => Cint(3))
+const METHODS = Dict(:rk4 => Cint(0), :tsit5 => Cint(1), :ros2 => Cint(2), :ros3p => Cint(3), :rodas3 => Cint(4))
 
 criterion_id(::FisherACriterion) = Cint(0)
 criterion_id(::FisherDCriterion) = Cint(1)

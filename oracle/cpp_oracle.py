@@ -109,7 +109,7 @@ class CppOracle:
             G0=np.ascontiguousarray(o.G0.T.reshape(-1), dtype=np.float64))   # column-major
         d = _Desc()
         d.model, d.crit = self.model, o.crit
-        d.method = {"rk4": 0, "tsit5": 1, "ros2": 2, "ros3p": 3}[o.method]
+        d.method = {"rk4": 0, "tsit5": 1, "ros2": 2, "ros3p": 3, "rodas3": 4}[o.method]
         d.N, d.n_var, d.n_steps = o.N, o.n_var, len(st)
         a = self._a
         d.tgrid, d.first_step, d.step_t, d.step_h = (a["tgrid"].ctypes.data, a["first"].ctypes.data,

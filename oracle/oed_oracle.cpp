@@ -257,16 +257,19 @@ static const double TS_C[6] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0};
 // ---------------------------------------------------------------------------------------------
 // Rosenbrock methods in implementation form (Hairer/Wanner IV.7):
 //   (1/(h gamma) I - J) U_i = g(y + sum_{j<i} a_ij U_j) + sum_{j<i} (c_ij/h) U_j,  y+ = y + sum m_i U_i
-// method 2: ROS2 (Verwer et al. 1999), method 3: ROS3P (Lang/Verwer 2001)
+// method 2: ROS2 (Verwer et al. 1999), method 3: ROS3P (Lang/Verwer 2001), method 4: RODAS3 (Sandu et al. 1997)
 // ---------------------------------------------------------------------------------------------
-struct RosTab { int S; double gamma; double a[3][3]; double c[3][3]; double m[3]; };
+struct RosTab { int S; double gamma; double a[4][4]; double c[4][4]; double m[4]; };
 static const double ROS2_G = 1.7071067811865475244;
-static const RosTab ROS2_TAB = {2, ROS2_G, {{0, 0, 0}, {1.0 / ROS2_G, 0, 0}, {0, 0, 0}},
-                                {{0, 0, 0}, {-2.0 / ROS2_G, 0, 0}, {0, 0, 0}}, {1.5 / ROS2_G, 0.5 / ROS2_G, 0}};
+static const RosTab ROS2_TAB = {2, ROS2_G, {{0}, {1.0 / ROS2_G}, {0}, {0}},
+                                {{0}, {-2.0 / ROS2_G}, {0}, {0}}, {1.5 / ROS2_G, 0.5 / ROS2_G, 0, 0}};
 static const RosTab ROS3P_TAB = {3, 7.886751345948129e-01,
-                                 {{0, 0, 0}, {1.267949192431123, 0, 0}, {1.267949192431123, 0, 0}},
-                                 {{0, 0, 0}, {-1.607695154586736, 0, 0}, {-3.464101615137755, -1.732050807568877, 0}},
-                                 {2.0, 5.773502691896258e-01, 4.226497308103742e-01}};
+                                 {{0}, {1.267949192431123}, {1.267949192431123}, {0}},
+                                 {{0}, {-1.607695154586736}, {-3.464101615137755, -1.732050807568877}, {0}},
+                                 {2.0, 5.773502691896258e-01, 4.226497308103742e-01, 0}};
+// RODAS3 (Sandu et al. 1997): 4 stages, order 3, stiffly accurate, L-stable
+static const RosTab RODAS3_TAB = {4, 0.5, {{0}, {0}, {2.0}, {2.0, 0, 1.0}},
+                                  {{0}, {4.0}, {1.0, -1.0}, {1.0, -1.0, -8.0 / 3.0}}, {2.0, 0.0, 1.0, 1.0}};
 
 inline double scalar_value(double x) { return x; }
 template <int N> inline double scalar_value(const Dual<N>& x) { return x.v; }
@@ -309,7 +312,7 @@ void rosenbrock_step(const RosTab& tab, double t, double h, T* y, const T* u, co
             for (int j = k + 1; j < NA; ++j) W[i][j] = W[i][j] - W[i][k] * W[k][j];
         }
     }
-    T U[3][NA], Y[NA], g[NA], r[NA];
+    T U[4][NA], Y[NA], g[NA], r[NA];
     for (int s = 0; s < tab.S; ++s) {
         for (int a = 0; a < NA; ++a) Y[a] = y[a];
         for (int j = 0; j < s; ++j)
@@ -353,7 +356,7 @@ void integrate(const Grid& g, const T* design, T* z) {
         for (int s = g.first_step[j]; s < g.first_step[j + 1]; ++s) {
             const double t = g.step_t[s], h = g.step_h[s];
             if (g.method >= 2) {
-                rosenbrock_step<M, T>(g.method == 2 ? ROS2_TAB : ROS3P_TAB, t, h, z, u, w, g.theta);
+                rosenbrock_step<M, T>(g.method == 2 ? ROS2_TAB : g.method == 3 ? ROS3P_TAB : RODAS3_TAB, t, h, z, u, w, g.theta);
                 continue;
             }
             for (int st = 0; st < S; ++st) {

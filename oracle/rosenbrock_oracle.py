@@ -11,7 +11,7 @@ oracle's nested-dual implementation.
 
 Implementation form (Hairer/Wanner IV.7):
     (1/(h gamma) I - J) U_i = g(y + sum_{j<i} a_ij U_j) + sum_{j<i} (c_ij/h) U_j ,  y+ = y + sum m_i U_i
-ROS2: Verwer, Spee, Blom, Hundsdorfer (1999); ROS3P: Lang, Verwer (2001).
+ROS2: Verwer, Spee, Blom, Hundsdorfer (1999); ROS3P: Lang, Verwer (2001); RODAS3: Sandu et al. (1997).
 """
 from __future__ import annotations
 
@@ -24,6 +24,9 @@ TABLEAUS = {
               [[0, 0, 0], [1.267949192431123, 0, 0], [1.267949192431123, 0, 0]],
               [[0, 0, 0], [-1.607695154586736, 0, 0], [-3.464101615137755, -1.732050807568877, 0]],
               [2.0, 5.773502691896258e-01, 4.226497308103742e-01]),
+    "rodas3": (0.5, [[0, 0, 0, 0], [0, 0, 0, 0], [2.0, 0, 0, 0], [2.0, 0, 1.0, 0]],
+               [[0, 0, 0, 0], [4.0, 0, 0, 0], [1.0, -1.0, 0, 0], [1.0, -1.0, -8.0 / 3.0, 0]],
+               [2.0, 0.0, 1.0, 1.0]),
 }
 
 

@@ -320,7 +320,7 @@ def test_overlapped_back_to_back_launches_match_isolated_ones(built_library):
 # ---------------------------------------------------------------------------------------------
 # stiff configuration (BASELINE.json config 4): fixed-grid Rosenbrock kernels
 # ---------------------------------------------------------------------------------------------
-ROS = {"ros2": D.ROS2, "ros3p": D.ROS3P}
+ROS = {"ros2": D.ROS2, "ros3p": D.ROS3P, "rodas3": D.RODAS3}
 STIFF = {"robertson": (models.robertson, D.DCriterion, 4), "chem6": (models.chem6, D.FisherECriterion, 2)}
 
 
@@ -335,7 +335,7 @@ def stiff_designs(name, n_var, n, seed):
 
 
 @pytest.mark.parametrize("name", list(STIFF))
-@pytest.mark.parametrize("method", ["ros2", "ros3p"])
+@pytest.mark.parametrize("method", ["ros2", "ros3p", "rodas3"])
 def test_rosenbrock_kernels_vs_cpp_oracle(name, method, built_library):
     """GPU (block-triangular solves with one nx x nx LU per step, symbolic second derivatives,
     dual parts for the unknown initial conditions) vs the C++ oracle (flat dense Jacobian by nested

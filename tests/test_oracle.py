@@ -252,7 +252,7 @@ def test_rosenbrock_tableaus_order_and_stability():
         def rhs(self, t, y, u, w): return [-y[0] * y[1] + 0.3 * y[1] * y[1], y[0] * y[0] - y[1]], None
     f = lambda t, y: [-y[0] * y[1] + 0.3 * y[1] ** 2, y[0] ** 2 - y[1]]
     ref = solve_ivp(f, (0, 2), [1.0, 0.5], rtol=1e-13, atol=1e-14, method="DOP853").y[:, -1]
-    for method, order in (("ros2", 2), ("ros3p", 3)):
+    for method, order in (("ros2", 2), ("ros3p", 3), ("rodas3", 3)):
         errs = []
         for n in (40, 80, 160):
             y = [np.array([1.0]), np.array([0.5])]
@@ -267,6 +267,7 @@ def test_rosenbrock_tableaus_order_and_stability():
         def rhs(self, t, y, u, w): return [-1e8 * y[0]], None
     assert abs(R.step(Lin("ros2"), 0.0, [np.array([1.0])], 1.0, [], [])[0][0]) < 1e-6      # L-stable
     assert abs(R.step(Lin("ros3p"), 0.0, [np.array([1.0])], 1.0, [], [])[0][0]) < 0.74     # A-stable
+    assert abs(R.step(Lin("rodas3"), 0.0, [np.array([1.0])], 1.0, [], [])[0][0]) < 1e-6    # L-stable
 
 
 def test_robertson_rosenbrock_vs_radau_and_reference_golden():
@@ -288,17 +289,18 @@ def test_robertson_rosenbrock_vs_radau_and_reference_golden():
     assert abs(F_exact - 740.59) < 0.05
     des = np.zeros((1, 11)); des[0, 7:10] = 1.0; des[0, 10] = 1e-3
     errs = {}
-    for method, n0, m in (("ros2", 160, 40), ("ros3p", 40, 10), ("ros3p", 160, 40)):
+    for method, n0, m in (("ros2", 160, 40), ("ros3p", 40, 10), ("ros3p", 160, 40), ("rodas3", 40, 10)):
         o = Oracle(models.robertson(), CRIT_D, method, _graded(n0, m))
         c, _, F = o.evaluate(des)
         errs[(method, n0)] = abs(F[0, 0] - F_exact) / F_exact
         assert abs(c[0] - (1.0 / (F_exact + 1e-3) + 1e-3)) < 1e-2          # reference golden tolerance
     assert errs[("ros2", 160)] < 2e-3 and errs[("ros3p", 40)] < 2e-3 and errs[("ros3p", 160)] < 1e-4
+    assert errs[("rodas3", 40)] < 2e-3
 
 
 @pytest.mark.parametrize("name,ctor,crit", [("robertson", models.robertson, CRIT_D),
                                             ("chem6", models.chem6, FISHER_E)])
-@pytest.mark.parametrize("method", ["ros2", "ros3p"])
+@pytest.mark.parametrize("method", ["ros2", "ros3p", "rodas3"])
 def test_rosenbrock_cpp_oracle_matches_numpy_oracle_and_fd(name, ctor, crit, method):
     """Flat dense Rosenbrock two ways (numpy: dual-number Jacobian + LAPACK; C++: nested duals +
     own pivoted LU) agree to rounding; the C++ forward-mode gradient matches central differences."""
