@@ -379,7 +379,11 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
         return fail(nullptr, DYNOED_EINVAL, "bad n_var / tau_offset");
     if (d->substeps <= 0 && !(d->edge_count && d->step_edges))
         return fail(nullptr, DYNOED_EINVAL, "need substeps > 0 or explicit step edges");
+    // designs per CTA: 128 unless the caller says otherwise; long design vectors (many intervals /
+    // variables) fall back to the largest multiple of 32 whose rows fit the 227 KB of shared memory
     int tile = d->tile ? d->tile : 128;
+    if (!d->tile)
+        while (tile > 32 && 128 + (size_t)tile * d->n_var * sizeof(double) > (size_t)227 * 1024) tile -= 32;
     if (tile % 32 != 0 || tile < 32 || tile > kMaxTile) return fail(nullptr, DYNOED_EINVAL, "tile must be 32..128, multiple of 32");
     const int nvars = mi.n_ctrl + mi.n_obs;
     // per-variable block lengths from the indicators; all indices must be valid

@@ -704,3 +704,25 @@ def test_reference_integer_optimum_by_exhaustive_batch(crit_cls, built_library):
     c2 = np.empty(len(W))
     ctx.eval_fixed_controls(basis, des, c2, None, None)
     assert int(np.argmin(c2)) == best and rel(c2, c) < 1e-12
+
+
+def test_long_design_vectors_pick_a_smaller_tile(oracles, built_library):
+    """README model with measurement_rate 1/400: n_var = 401 (> 128 rows x 227 KB of shared memory),
+    so the default tile drops below 128; results still match the oracle, TMA staging included."""
+    from dynamicoed.jl_b200.symbolic import (Differential, Eq, ODESystem, independent_variable,
+                                             observed_variables, parameters, variables)
+    from oracle.oed_oracle import Oracle
+    t = independent_variable("t")
+    x = variables("x", 1.0)
+    p = parameters("p[1]", -2.0, tunable=True)
+    obs = observed_variables("obs", measurement_rate=400)
+    sysm = ODESystem([Eq(Differential(t)(x), p * x)], t, tspan=(0.0, 1.0), observed=[Eq(obs, x ** 2)],
+                     name="simple_system")
+    prob = D.OEDProblem(D.OEDSystem(sysm), D.ACriterion(), alg=D.RK4(1))
+    ctx = prob.context()
+    assert ctx.n_var == 401 and ctx.kernel_stats(True)["block"] == 64
+    rng = np.random.Generator(np.random.Philox(3))
+    des = rng.random((333, 401)); des[:, -1] = 0.05 + 0.9 * des[:, -1]
+    c, g, F = ctx.evaluate(des)
+    oc, og, oF = Oracle(sysm, 3, "rk4", 1).evaluate(des, grad=True)
+    assert rel(c, oc) < RTOL and rel(F, oF) < RTOL and rel_rows(g, og) < RTOL
