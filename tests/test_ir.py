@@ -42,3 +42,14 @@ def test_ir_of_lv_fishing_reads_like_the_reference_declaration():
     assert len(u) == 1 and u[0]["measurement_rate"] == 0.3 and u[0]["bounds"] == [0.0, 1.0]
     assert [p["name"] for p in d["parameters"] if p["tunable"] and not p["input"]] == ["c[1]", "c[2]"]
     assert d["equations"][0]["lhs"] == "D(x0)" and [o["measurement_rate"] for o in d["observed"]] == [0.1, 0.1]
+
+
+def test_build_from_ir_resolves_builtin_models_without_recompiling(tmp_path, built_library):
+    """`python -m dynamicoed.jl_b200.ir build model.json` — the Julia host's hand-over: an exported
+    built-in model maps back onto libdynoed_cuda.so (identical emitted source), no nvcc run."""
+    from dynamicoed.jl_b200 import runtime
+    path = tmp_path / "lv.json"
+    path.write_text(json.dumps(ir.system_to_ir(models.lotka_volterra_fishing()), ensure_ascii=False))
+    out = ir.build_from_ir(str(path))
+    assert out["model"] == "lv_fishing" and out["library"] == runtime.LIB_PATH
+    assert (out["nx"], out["np"], out["n_obs"], out["n_ctrl"], out["n_ic"]) == (2, 2, 2, 1, 0)
