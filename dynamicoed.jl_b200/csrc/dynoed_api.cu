@@ -271,6 +271,7 @@ struct dynoed_ctx {
         const char* out1[3] = {nullptr, nullptr, nullptr};
     } prev;
     bool pdl_enabled = true;
+    bool zero_copy = true;             // store crit / fim straight into page-locked host arrays
     int host_chunks = 8;               // equal chunks; 0 (DYNOED_HOST_CHUNKS=0) selects the ramped schedule
     bool have_batch = false;
     Slot slots[kSlots];
@@ -488,6 +489,7 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     CUC(cudaMalloc(&ctx->d_ticket, 2 * sizeof(unsigned int)));
     CUC(cudaMemset(ctx->d_ticket, 0, 2 * sizeof(unsigned int)));
     ctx->pdl_enabled = !getenv("DYNOED_NO_PDL");
+    ctx->zero_copy = !getenv("DYNOED_NO_ZEROCOPY");
     if (const char* hc = getenv("DYNOED_HOST_CHUNKS")) ctx->host_chunks = std::max(0, atoi(hc));
 
     EvalParams& P = ctx->base;
@@ -741,8 +743,8 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
     // Pinned (page-locked, mapped) result arrays: the kernel stores crit / fim straight into host
     // memory (posted PCIe writes, 8 + 8 nF bytes per design), which removes two of the three
     // device-to-host copies per chunk; the gradient still travels as one bulk copy.
-    auto mapped = [](const void* p) -> double* {
-        if (!p || getenv("DYNOED_NO_ZEROCOPY")) return nullptr;
+    auto mapped = [ctx](const void* p) -> double* {
+        if (!p || !ctx->zero_copy) return nullptr;
         cudaPointerAttributes a;
         if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
         return a.type == cudaMemoryTypeHost ? static_cast<double*>(a.devicePointer) : nullptr;
