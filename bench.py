@@ -349,11 +349,11 @@ def main():
     if rank == 0:
         ks = ctx.kernel_stats(True)
         flops = ks["flops_per_design_grad"] * n
-        # N=1: the evaluation kernel is the only launch of the timed region, so its average launch
-        # duration over the region IS region time / launches (consecutive launches overlap their
-        # tails, see "overlapped_launches").  N>1: the region also holds the NCCL record gather, so
-        # the isolated per-launch duration is used.
-        kernel_ms = ms_total / args.steps if world == 1 else kernel_ms_iso
+        # The evaluation kernel is the only launch of the timed region at N = 1, so its average launch
+        # duration over the region IS region time / launches (consecutive launches overlap their tails,
+        # see "overlapped_launches").  At N > 1 the region also holds one NCCL record gather and one
+        # reduction kernel per 8 steps; region time / steps is then a slightly pessimistic kernel time.
+        kernel_ms = ms_total / args.steps
         achieved = flops / (kernel_ms * 1e-3) / 1e12 if kernel_ms > 0 else None
         peak = max(peak_burst, peak_after)
         hbm_peak, hbm_src = 6650.0, "fallback"
