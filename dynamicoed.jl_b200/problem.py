@@ -287,3 +287,36 @@ def OptimizationProblem(prob: OEDProblem, AD=None, u0=None, p=None, *, integer_c
     syms = [v.name for v in list(prob.system.x_ic) + list(prob.system.controls) + list(prob.system.w)]
     opt_f = OptimizationFunction(objective, gradient, cons, cons_j, syms)
     return OptimizationProblemT(opt_f, u0a, p, lb, ub, integrality, lcons, ucons, prob)
+
+
+@dataclass
+class OptimizationSolution:
+    u: np.ndarray
+    objective: float
+    success: bool
+    message: str
+    iterations: int
+    evaluations: int
+
+
+def solve(opt_prob: OptimizationProblemT, method: str = "SLSQP", **options) -> OptimizationSolution:
+    """Stand-in for ``solve(optimization_problem, Ipopt.Optimizer())`` (/root/reference/README.md:62):
+    hands the GPU objective / gradient closures, bounds and constraints to a scipy NLP solver
+    (Ipopt itself is not in this image).  Relaxed problems only; for ``integer_constraints`` use
+    the batch evaluator (exhaustive / branch-and-bound over `Context.eval_fixed_controls`)."""
+    from scipy.optimize import NonlinearConstraint, minimize
+    f = opt_prob.f
+    cons = []
+    if f.cons is not None:
+        cons = [NonlinearConstraint(f.cons, opt_prob.lcons, opt_prob.ucons, jac=f.cons_j)]
+    calls = [0]
+
+    def fun(u):
+        calls[0] += 1
+        return f.f(u)
+    opts = dict(ftol=1e-12, maxiter=500) if method == "SLSQP" else {}
+    opts.update(options)
+    r = minimize(fun, opt_prob.u0, jac=lambda u: f.grad(None, u), method=method,
+                 bounds=list(zip(opt_prob.lb, opt_prob.ub)), constraints=cons, options=opts)
+    return OptimizationSolution(np.asarray(r.x), float(r.fun), bool(r.success), str(r.message),
+                                int(getattr(r, "nit", 0)), calls[0])

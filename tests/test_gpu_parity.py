@@ -726,3 +726,17 @@ def test_long_design_vectors_pick_a_smaller_tile(oracles, built_library):
     c, g, F = ctx.evaluate(des)
     oc, og, oF = Oracle(sysm, 3, "rk4", 1).evaluate(des, grad=True)
     assert rel(c, oc) < RTOL and rel(F, oF) < RTOL and rel_rows(g, og) < RTOL
+
+
+def test_readme_example_runs_end_to_end(built_library):
+    """examples/readme_example.py — the reference's README (README.md:25-63) with D.solve standing in
+    for Ipopt: at most 3 of 10 measurements of x^2; FisherA puts them where (2 x G)^2 is largest."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "readme_example.py")],
+                         capture_output=True, text=True, check=True, timeout=300).stdout
+    assert "success True" in out
+    w = np.array([float(v) for v in out.split("w*  = [")[1].split("]")[0].split()])
+    assert abs(w.sum() - 3.0) < 1e-6 and np.all(w > -1e-9) and np.all(w < 1 + 1e-9)
+    # the integrand 4 t^2 e^{-8t} peaks at t = 0.25: intervals 2, 3, 4 (0-based 1..3) carry the weight
+    assert np.allclose(np.sort(np.argsort(-w)[:3]), [1, 2, 3])
