@@ -15,3 +15,9 @@ print("host path %.1f ms (pageable), device path %.2f ms" % (th * 1e3, td * 1e3)
 print("equal:", np.array_equal(dc.cpu().numpy(), c), np.array_equal(dg.cpu().numpy(), g), np.array_equal(dF.cpu().numpy(), F))
 print("argmin", ctx.argmin(), int(np.argmin(c)), "scratch MB", ctx.kernel_stats(True)["scratch_bytes"] / 1e6,
       "GPU mem used MB", torch.cuda.mem_get_info()[1] / 1e6 - torch.cuda.mem_get_info()[0] / 1e6)
+hp = torch.from_numpy(des).pin_memory(); hc = torch.empty(n, dtype=torch.float64).pin_memory()
+hg = torch.empty((n, 71), dtype=torch.float64).pin_memory(); hf = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+ctx.eval_batch(hp.numpy(), hc.numpy(), hg.numpy(), hf.numpy())
+t = time.perf_counter()
+for _ in range(3): ctx.eval_batch(hp.numpy(), hc.numpy(), hg.numpy(), hf.numpy())
+print("host path pinned %.1f ms; equal: %s" % ((time.perf_counter() - t) / 3 * 1e3, np.array_equal(hg.numpy(), g)))
