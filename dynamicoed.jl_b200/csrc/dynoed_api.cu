@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -218,7 +219,25 @@ struct Slot {
     double* traj = nullptr;
     size_t traj_bytes = 0;
     int64_t cap = 0;   // designs
+    // page-locked staging for PAGEABLE caller arrays (ordinary malloc / numpy / Julia arrays)
+    double *h_designs = nullptr, *h_crit = nullptr, *h_grad = nullptr, *h_fim = nullptr;
+    int64_t hcap = 0;
+    cudaEvent_t done = nullptr;
 };
+
+// memcpy split over a few host threads: one core moves ~10 GB/s, a PCIe Gen5 link wants ~50
+static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int nt = (int)std::min<size_t>(std::min<unsigned>(8u, std::max(1u, hw / 2)), bytes / (1u << 20));
+    if (nt <= 1) { memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> th;
+    const size_t per = ((bytes / nt) + 63) & ~(size_t)63;
+    for (int t = 0; t < nt; ++t) {
+        const size_t lo = std::min(bytes, (size_t)t * per), hi = std::min(bytes, lo + per);
+        if (hi > lo) th.emplace_back([=] { memcpy((char*)dst + lo, (const char*)src + lo, hi - lo); });
+    }
+    for (auto& x : th) x.join();
+}
 
 }  // namespace dynoed
 
@@ -272,6 +291,7 @@ struct dynoed_ctx {
     } prev;
     bool pdl_enabled = true;
     bool zero_copy = true;             // store crit / fim straight into page-locked host arrays
+    bool host_staging = true;          // pageable caller arrays go through page-locked staging
     int host_chunks = 8;               // equal chunks; 0 (DYNOED_HOST_CHUNKS=0) selects the ramped schedule
     bool have_batch = false;
     Slot slots[kSlots];
@@ -490,6 +510,7 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     CUC(cudaMemset(ctx->d_ticket, 0, 2 * sizeof(unsigned int)));
     ctx->pdl_enabled = !getenv("DYNOED_NO_PDL");
     ctx->zero_copy = !getenv("DYNOED_NO_ZEROCOPY");
+    ctx->host_staging = !getenv("DYNOED_NO_STAGING");
     if (const char* hc = getenv("DYNOED_HOST_CHUNKS")) ctx->host_chunks = std::max(0, atoi(hc));
 
     EvalParams& P = ctx->base;
@@ -542,6 +563,8 @@ void dynoed_destroy(dynoed_ctx* ctx) {
     for (auto& s : ctx->slots) {
         if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
         cudaFree(s.d_designs); cudaFree(s.d_crit); cudaFree(s.d_grad); cudaFree(s.d_fim); cudaFree(s.traj);
+        cudaFreeHost(s.h_designs); cudaFreeHost(s.h_crit); cudaFreeHost(s.h_grad); cudaFreeHost(s.h_fim);
+        if (s.done) cudaEventDestroy(s.done);
     }
     cudaFree(ctx->d_first_step); cudaFree(ctx->d_step_t); cudaFree(ctx->d_step_h); cudaFree(ctx->d_indicators);
     for (int q = 0; q < 2; ++q) { cudaFree(ctx->traj[q]); cudaFree(ctx->part_val[q]); cudaFree(ctx->part_idx[q]); }
@@ -700,6 +723,30 @@ static int ensure_slot(dynoed_ctx* ctx, Slot& s, int64_t cap, int kidx, bool fim
     return DYNOED_OK;
 }
 
+static int ensure_staging(dynoed_ctx* ctx, Slot& s, int64_t cap) {
+    const int nF = ctx->model->info.nF;
+    if (!s.done) CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    if (cap > s.hcap) {
+        CU(cudaStreamSynchronize(s.stream));
+        cudaFreeHost(s.h_designs); cudaFreeHost(s.h_crit); cudaFreeHost(s.h_grad); cudaFreeHost(s.h_fim);
+        s.h_designs = s.h_crit = s.h_grad = s.h_fim = nullptr;
+        CU(cudaMallocHost(&s.h_designs, sizeof(double) * cap * ctx->n_var));
+        CU(cudaMallocHost(&s.h_crit, sizeof(double) * cap));
+        CU(cudaMallocHost(&s.h_grad, sizeof(double) * cap * ctx->n_var));
+        CU(cudaMallocHost(&s.h_fim, sizeof(double) * cap * nF));
+        s.hcap = cap;
+    }
+    return DYNOED_OK;
+}
+
+// is this host pointer ordinary pageable memory (not page-locked / registered)?
+static bool is_pageable(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
 // host buffers: chunked pipeline, chunk k on stream k % kSlots (H2D -> kernel -> D2H in order on
 // that stream; different chunks overlap copy engines and SMs)
 static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad, double* fim) {
@@ -715,6 +762,7 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
     if (ctx->host_chunks > 0 || ntiles < 64) {
         const int64_t k = ctx->host_chunks > 0 ? ctx->host_chunks : 8;
         int64_t chunk = std::max<int64_t>(((ntiles + k - 1) / k), std::min<int64_t>(16, ntiles)) * tile;
+        chunk = std::min<int64_t>(chunk, 65536);   // bounds the per-slot device and staging buffers for huge batches
         for (int64_t o = chunk; o < n; o += chunk) bounds.push_back(o);
     } else {
         static const int ramp[10] = {1, 1, 2, 4, 8, 8, 4, 2, 1, 1};
@@ -751,6 +799,27 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
     };
     double* crit_map = mapped(crit);
     double* fim_map = mapped(fim);
+    // Pageable caller arrays: the driver would stage them through a small bounce buffer at a few
+    // GB/s.  Instead every chunk goes through page-locked staging owned by its slot, filled and
+    // drained by multi-threaded memcpy while the other slots' copies and kernels are in flight.
+    const bool staged = ctx->host_staging &&
+                        (is_pageable(designs) || is_pageable(crit) || is_pageable(grad) || is_pageable(fim));
+    if (staged) {
+        crit_map = fim_map = nullptr;
+        for (int k = 0; k < kSlots && k < nchunks; ++k) {
+            rc = ensure_staging(ctx, ctx->slots[k], chunk);
+            if (rc) return rc;
+        }
+    }
+    auto drain = [&](int64_t c) -> int {     // chunk c has landed in its slot's staging: hand it to the caller
+        Slot& s = ctx->slots[c % kSlots];
+        const int64_t off = bounds[c], cnt = bounds[c + 1] - bounds[c];
+        CU(cudaEventSynchronize(s.done));
+        memcpy(crit + off, s.h_crit, sizeof(double) * cnt);
+        if (g) parallel_memcpy(grad + off * ctx->n_var, s.h_grad, sizeof(double) * cnt * ctx->n_var);
+        if (fim) memcpy(fim + off * nF, s.h_fim, sizeof(double) * cnt * nF);
+        return DYNOED_OK;
+    };
     // order after whatever the ctx stream was doing
     cudaEvent_t ev;
     CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -760,8 +829,13 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
     for (int64_t c = 0; c < nchunks; ++c) {
         Slot& s = ctx->slots[c % kSlots];
         const int64_t off = bounds[c], cnt = bounds[c + 1] - bounds[c];
-        CU(cudaMemcpyAsync(s.d_designs, designs + off * ctx->n_var, sizeof(double) * cnt * ctx->n_var,
-                           cudaMemcpyHostToDevice, s.stream));
+        const double* h_src = designs + off * ctx->n_var;
+        if (staged) {
+            if (c >= kSlots) { rc = drain(c - kSlots); if (rc) return rc; }   // frees this slot's staging
+            parallel_memcpy(s.h_designs, h_src, sizeof(double) * cnt * ctx->n_var);
+            h_src = s.h_designs;
+        }
+        CU(cudaMemcpyAsync(s.d_designs, h_src, sizeof(double) * cnt * ctx->n_var, cudaMemcpyHostToDevice, s.stream));
         EvalParams P = ctx->base;
         const int grid = grid_for(ctx, cnt, kidx);
         P.designs = s.d_designs; P.crit = crit_map ? crit_map + off : s.d_crit; P.grad = g ? s.d_grad : nullptr;
@@ -777,12 +851,16 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         CU(ctx->model->launch(kidx == 2 ? kFwdOnly + ctx->method : ctx->method, g, ctx->ucoef, false, P, grid, ctx->tile,
                               smem_bytes(ctx), s.stream));
         ctx->launches++;
-        if (!crit_map) CU(cudaMemcpyAsync(crit + off, s.d_crit, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s.stream));
-        if (g) CU(cudaMemcpyAsync(grad + off * ctx->n_var, s.d_grad, sizeof(double) * cnt * ctx->n_var,
-                                  cudaMemcpyDeviceToHost, s.stream));
-        if (fim && !fim_map) CU(cudaMemcpyAsync(fim + off * nF, s.d_fim, sizeof(double) * cnt * nF, cudaMemcpyDeviceToHost,
-                                                s.stream));
+        double* o_crit = staged ? s.h_crit : crit + off;
+        double* o_grad = staged ? s.h_grad : (g ? grad + off * ctx->n_var : nullptr);
+        double* o_fim = staged ? s.h_fim : (fim ? fim + off * nF : nullptr);
+        if (!crit_map) CU(cudaMemcpyAsync(o_crit, s.d_crit, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s.stream));
+        if (g) CU(cudaMemcpyAsync(o_grad, s.d_grad, sizeof(double) * cnt * ctx->n_var, cudaMemcpyDeviceToHost, s.stream));
+        if (fim && !fim_map) CU(cudaMemcpyAsync(o_fim, s.d_fim, sizeof(double) * cnt * nF, cudaMemcpyDeviceToHost, s.stream));
+        if (staged) CU(cudaEventRecord(s.done, s.stream));
     }
+    if (staged)
+        for (int64_t c = std::max<int64_t>(0, nchunks - kSlots); c < nchunks; ++c) { rc = drain(c); if (rc) return rc; }
     for (int k = 0; k < kSlots && k < nchunks; ++k) {
         CU(cudaEventRecord(ev, ctx->slots[k].stream));
         CU(cudaStreamWaitEvent(ctx->stream, ev, 0));

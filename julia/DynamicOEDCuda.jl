@@ -157,7 +157,7 @@ end
 
 Page-locked host memory from `dynoed_host_alloc`, wrapped as a Julia matrix (freed by a finalizer).
 Ordinary Julia arrays are pageable: the library accepts them, but large batches then move at a few
-GB/s instead of the PCIe rate (1 M LV designs: 330 ms pageable vs 15 ms pinned on B200).  Use this
+GB/s instead of the PCIe rate (1 M LV designs: 71 ms pageable vs 15 ms pinned on B200).  Use this
 for the `designs` / `crit` / `grad` buffers of batched sweeps.
 """
 function pinned_matrix(rows::Integer, cols::Integer)

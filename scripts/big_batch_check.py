@@ -7,6 +7,7 @@ from dynamicoed.jl_b200 import models
 n = 1 << 20
 ctx = D.OEDProblem(D.OEDSystem(models.lotka_volterra_fishing()), D.FisherDCriterion(), alg=D.RK4(4)).context()
 rng = np.random.Generator(np.random.Philox(1)); des = rng.random((n, 71)); des[:, -1] = 1e-3 + 0.99 * des[:, -1]
+c, g, F = ctx.evaluate(des)        # first call allocates slots / staging
 t = time.perf_counter(); c, g, F = ctx.evaluate(des); th = time.perf_counter() - t
 d = torch.from_numpy(des).cuda(); dc = torch.empty(n, dtype=torch.float64, device="cuda"); dg = torch.empty_like(d)
 dF = torch.empty((n, 3), dtype=torch.float64, device="cuda")
