@@ -296,6 +296,15 @@ def main():
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
     peak_after, _ = runtime.fp64_peak(local, stream.cuda_stream)
+    # sustained FP64 peak: the same DFMA-chain microbenchmark back to back for ~1.5 s (this kernel
+    # class runs into the 1 kW power cap, clocks settle below the burst clock)
+    peak_sustained = None
+    if rank == 0:
+        t_s = time.perf_counter()
+        vals = []
+        while time.perf_counter() - t_s < 1.5:
+            vals.append(runtime.fp64_peak(local, stream.cuda_stream)[0])
+        peak_sustained = float(np.median(vals[len(vals) // 2:]))
 
     # ---- e2e: public host-buffer call, pinned host memory, H2D + D2H inside the timed region ----
     # Every step is one blocking dynoed_eval_batch on HOST buffers (its own H2D of 37 MB of designs,
@@ -374,8 +383,10 @@ def main():
                 "config": workload_config(world),
                 "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": achieved / peak if achieved else None, "traffic": traffic,
-                             "peak_source": "DFMA-chain microbenchmark in this run (of measured; "
+                             "peak_source": "DFMA-chain microbenchmark in this run, burst (of measured; "
                                             "nominal 148x64x2x1.965 GHz = 37.2)",
+                             "peak_sustained": peak_sustained,
+                             "frac_of_sustained_peak": achieved / peak_sustained if achieved and peak_sustained else None,
                              "kernel": "oed_eval_kernel<Model_lv_fishing,TabRK4,grad>",
                              "kernel_ms": kernel_ms, "kernel_ms_isolated": kernel_ms_iso,
                              "kernel_launches_timed": args.steps, "overlapped_launches": int(overlapped),
