@@ -200,7 +200,7 @@ def main():
     # multi-GPU: NCCL only gathers the per-rank (min, index) records.  GATHER batches share one
     # collective (records come from the library's history ring), so that the evaluation launches
     # in between stay back to back and overlap their tails exactly as at N=1.
-    GATHER = 8
+    GATHER = 16
     rec = torch.empty((GATHER, 2), dtype=torch.int64, device=dev)          # {value bits, local index}
     gat = torch.empty((world, GATHER, 2), dtype=torch.int64, device=dev)
     best = torch.empty((GATHER, 3), dtype=torch.int64, device=dev)         # {value bits, global index, owner}
@@ -361,7 +361,7 @@ def main():
         # The evaluation kernel is the only launch of the timed region at N = 1, so its average launch
         # duration over the region IS region time / launches (consecutive launches overlap their tails,
         # see "overlapped_launches").  At N > 1 the region also holds one NCCL record gather and one
-        # reduction kernel per 8 steps; region time / steps is then a slightly pessimistic kernel time.
+        # reduction kernel per 16 steps; region time / steps is then a slightly pessimistic kernel time.
         kernel_ms = ms_total / args.steps
         achieved = flops / (kernel_ms * 1e-3) / 1e12 if kernel_ms > 0 else None
         peak = max(peak_burst, peak_after)
