@@ -50,5 +50,34 @@ def main():
             print(name, method, des.shape)
 
 
+STIFF = {"robertson": (models.robertson, 4, "ros3p"), "chem6": (models.chem6, 2, "rodas3")}
+
+
+def stiff_edges():
+    import dynamicoed.jl_b200 as D
+    return D.graded_edges(10, 30, 1e-6, 6)
+
+
+def main_stiff():
+    """Stiff configuration: values from BOTH oracles (numpy flat-dense Rosenbrock, C++ nested duals),
+    gradients from the C++ oracle; the two value sets must agree before anything is written."""
+    from oracle.cpp_oracle import CppOracle
+    for name, (ctor, crit, method) in STIFF.items():
+        o = Oracle(ctor(), crit, method, list(stiff_edges()))
+        rng = np.random.Generator(np.random.Philox(20264))
+        des = rng.random((10, o.n_var))
+        des[:, -1] = 1e-3 + 0.9 * des[:, -1]
+        if name == "chem6":
+            des[:, 0] = 0.5 + des[:, 0]
+            des[:, 1] = 0.1 + 0.9 * des[:, 1]
+        c_py, _, F_py = o.evaluate(des, grad=False)
+        c, g, F = CppOracle(name, o).evaluate(des, grad=True)
+        assert np.max(np.abs(F - F_py)) <= 1e-11 * np.max(np.abs(F)) and np.allclose(c, c_py, rtol=1e-9, atol=0)
+        np.savez_compressed(os.path.join(HERE, f"{name}_{method}_graded.npz"), designs=des, crit=c, grad=g, F=F,
+                            criterion=crit)
+        print(name, method, des.shape)
+
+
 if __name__ == "__main__":
     main()
+    main_stiff()

@@ -740,3 +740,16 @@ def test_readme_example_runs_end_to_end(built_library):
     assert abs(w.sum() - 3.0) < 1e-6 and np.all(w > -1e-9) and np.all(w < 1 + 1e-9)
     # the integrand 4 t^2 e^{-8t} peaks at t = 0.25: intervals 2, 3, 4 (0-based 1..3) carry the weight
     assert np.allclose(np.sort(np.argsort(-w)[:3]), [1, 2, 3])
+
+
+@pytest.mark.parametrize("name,method,crit_cls", [("robertson", "ros3p", D.DCriterion), ("chem6", "rodas3", D.FisherECriterion)])
+def test_stiff_golden_fixtures(name, method, crit_cls, built_library):
+    """Committed fixtures of the stiff configuration (tests/golden/make_golden.py::main_stiff): no
+    oracle at run time."""
+    z = np.load(os.path.join(GOLD, f"{name}_{method}_graded.npz"))
+    edges = D.graded_edges(10, 30, 1e-6, 6)
+    ctx = D.OEDProblem(D.OEDSystem(STIFF[name][0]()), crit_cls(), alg=ROS[method](edges=edges)).context()
+    c, g, F = ctx.evaluate(z["designs"])
+    den = np.maximum(np.abs(z["crit"]), np.max(np.abs(z["F"]), axis=1))
+    assert rel(F, z["F"]) < RTOL and float(np.max(np.abs(c - z["crit"]) / den)) < RTOL
+    assert rel_rows(g, z["grad"]) < RTOL

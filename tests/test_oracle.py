@@ -322,3 +322,15 @@ def test_rosenbrock_cpp_oracle_matches_numpy_oracle_and_fd(name, ctor, crit, met
         dp[:, k] += eps; dm[:, k] -= eps
         fd = (co.evaluate(dp, grad=False)[0] - co.evaluate(dm, grad=False)[0]) / (2 * eps)
         assert np.allclose(fd, g2[:, k], rtol=2e-5, atol=1e-9 * max(1.0, np.max(np.abs(g2)))), (k, fd, g2[:, k])
+
+
+@pytest.mark.parametrize("name,method", [("robertson", "ros3p"), ("chem6", "rodas3")])
+def test_stiff_golden_fixtures_match_the_cpp_oracle(name, method):
+    """The committed stiff fixtures are reproducible from the oracle (guards against drift)."""
+    import os
+    import dynamicoed.jl_b200 as D
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{name}_{method}_graded.npz"))
+    ctor = {"robertson": models.robertson, "chem6": models.chem6}[name]
+    o = Oracle(ctor(), int(z["criterion"]), method, list(D.graded_edges(10, 30, 1e-6, 6)))
+    c, g, F = cpp_oracle.CppOracle(name, o).evaluate(z["designs"], grad=True)
+    assert np.array_equal(c, z["crit"]) and np.array_equal(g, z["grad"]) and np.array_equal(F, z["F"])
