@@ -29,6 +29,8 @@ static thread_local std::string g_last_error;
 
 // method + kFwdOnly selects the forward-only gradient kernel of an explicit tableau (DYNOED_GRAD_NO_CONTROLS)
 constexpr int kFwdOnly = 16;
+// method | kCtrlGrad: Rosenbrock gradient kernel that also differentiates with respect to control values
+constexpr int kCtrlGrad = 32;
 
 struct ModelEntry {
     const char* name;
@@ -78,14 +80,15 @@ static cudaError_t launch_tab(bool grad, bool uc, bool pdl, const EvalParams& P,
               : launch_one<M, Tab, false, false>(pdl, P, grid, block, smem, st);
 }
 
-template <class M, class Stepper, bool GRAD>
+// CG: differentiate with respect to control values too (one dual pass each; Rosenbrock steppers)
+template <class M, class Stepper, bool GRAD, bool CG = false>
 static cudaError_t launch_ros(bool pdl, const EvalParams& P, int grid, int block, size_t smem, cudaStream_t st) {
-    return launch_kernel(ros_eval_kernel<M, Stepper, GRAD>, pdl, P, grid, block, smem, st);
+    return launch_kernel(ros_eval_kernel<M, Stepper, GRAD, CG>, pdl, P, grid, block, smem, st);
 }
 
-template <class M, class Stepper, bool GRAD>
+template <class M, class Stepper, bool GRAD, bool CG = false>
 static cudaError_t attrs_ros(int block, size_t smem, cudaFuncAttributes* fa, int* bps) {
-    auto kern = ros_eval_kernel<M, Stepper, GRAD>;
+    auto kern = ros_eval_kernel<M, Stepper, GRAD, CG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(fa, kern);
@@ -96,17 +99,22 @@ static cudaError_t attrs_ros(int block, size_t smem, cudaFuncAttributes* fa, int
 template <class M>
 static cudaError_t launch_model(int method, bool grad, bool uc, bool pdl, const EvalParams& P, int grid, int block,
                                 size_t smem, cudaStream_t st) {
+    const bool cg = (method & kCtrlGrad) != 0;
+    method &= ~kCtrlGrad;
     if (method == DYNOED_RK4) return launch_tab<M, TabRK4>(grad, uc, pdl, P, grid, block, smem, st);
     if (method == DYNOED_TSIT5) return launch_tab<M, TabTsit5>(grad, uc, pdl, P, grid, block, smem, st);
     if (method == DYNOED_ROS2)
-        return grad ? launch_ros<M, RosenbrockStepper<TabROS2>, true>(pdl, P, grid, block, smem, st)
-                    : launch_ros<M, RosenbrockStepper<TabROS2>, false>(pdl, P, grid, block, smem, st);
+        return !grad ? launch_ros<M, RosenbrockStepper<TabROS2>, false>(pdl, P, grid, block, smem, st)
+               : cg ? launch_ros<M, RosenbrockStepper<TabROS2>, true, (M::NCTRL > 0)>(pdl, P, grid, block, smem, st)
+                    : launch_ros<M, RosenbrockStepper<TabROS2>, true>(pdl, P, grid, block, smem, st);
     if (method == DYNOED_ROS3P)
-        return grad ? launch_ros<M, RosenbrockStepper<TabROS3P>, true>(pdl, P, grid, block, smem, st)
-                    : launch_ros<M, RosenbrockStepper<TabROS3P>, false>(pdl, P, grid, block, smem, st);
+        return !grad ? launch_ros<M, RosenbrockStepper<TabROS3P>, false>(pdl, P, grid, block, smem, st)
+               : cg ? launch_ros<M, RosenbrockStepper<TabROS3P>, true, (M::NCTRL > 0)>(pdl, P, grid, block, smem, st)
+                    : launch_ros<M, RosenbrockStepper<TabROS3P>, true>(pdl, P, grid, block, smem, st);
     if (method == DYNOED_RODAS3)
-        return grad ? launch_ros<M, RosenbrockStepper<TabRODAS3>, true>(pdl, P, grid, block, smem, st)
-                    : launch_ros<M, RosenbrockStepper<TabRODAS3>, false>(pdl, P, grid, block, smem, st);
+        return !grad ? launch_ros<M, RosenbrockStepper<TabRODAS3>, false>(pdl, P, grid, block, smem, st)
+               : cg ? launch_ros<M, RosenbrockStepper<TabRODAS3>, true, (M::NCTRL > 0)>(pdl, P, grid, block, smem, st)
+                    : launch_ros<M, RosenbrockStepper<TabRODAS3>, true>(pdl, P, grid, block, smem, st);
     // forward-only gradient mode of the explicit tableaus (kFwdOnly + method)
     if (method == kFwdOnly + DYNOED_RK4) return launch_ros<M, ExplicitStepper<TabRK4>, true>(pdl, P, grid, block, smem, st);
     return launch_ros<M, ExplicitStepper<TabTsit5>, true>(pdl, P, grid, block, smem, st);
@@ -123,17 +131,22 @@ static cudaError_t attrs_tab(bool grad, bool uc, int block, size_t smem, cudaFun
 template <class M>
 static cudaError_t attrs_model(int method, bool grad, bool uc, int block, size_t smem, cudaFuncAttributes* fa,
                                int* bps) {
+    const bool cg = (method & kCtrlGrad) != 0;
+    method &= ~kCtrlGrad;
     if (method == DYNOED_RK4) return attrs_tab<M, TabRK4>(grad, uc, block, smem, fa, bps);
     if (method == DYNOED_TSIT5) return attrs_tab<M, TabTsit5>(grad, uc, block, smem, fa, bps);
     if (method == DYNOED_ROS2)
-        return grad ? attrs_ros<M, RosenbrockStepper<TabROS2>, true>(block, smem, fa, bps)
-                    : attrs_ros<M, RosenbrockStepper<TabROS2>, false>(block, smem, fa, bps);
+        return !grad ? attrs_ros<M, RosenbrockStepper<TabROS2>, false>(block, smem, fa, bps)
+               : cg ? attrs_ros<M, RosenbrockStepper<TabROS2>, true, (M::NCTRL > 0)>(block, smem, fa, bps)
+                    : attrs_ros<M, RosenbrockStepper<TabROS2>, true>(block, smem, fa, bps);
     if (method == DYNOED_ROS3P)
-        return grad ? attrs_ros<M, RosenbrockStepper<TabROS3P>, true>(block, smem, fa, bps)
-                    : attrs_ros<M, RosenbrockStepper<TabROS3P>, false>(block, smem, fa, bps);
+        return !grad ? attrs_ros<M, RosenbrockStepper<TabROS3P>, false>(block, smem, fa, bps)
+               : cg ? attrs_ros<M, RosenbrockStepper<TabROS3P>, true, (M::NCTRL > 0)>(block, smem, fa, bps)
+                    : attrs_ros<M, RosenbrockStepper<TabROS3P>, true>(block, smem, fa, bps);
     if (method == DYNOED_RODAS3)
-        return grad ? attrs_ros<M, RosenbrockStepper<TabRODAS3>, true>(block, smem, fa, bps)
-                    : attrs_ros<M, RosenbrockStepper<TabRODAS3>, false>(block, smem, fa, bps);
+        return !grad ? attrs_ros<M, RosenbrockStepper<TabRODAS3>, false>(block, smem, fa, bps)
+               : cg ? attrs_ros<M, RosenbrockStepper<TabRODAS3>, true, (M::NCTRL > 0)>(block, smem, fa, bps)
+                    : attrs_ros<M, RosenbrockStepper<TabRODAS3>, true>(block, smem, fa, bps);
     if (method == kFwdOnly + DYNOED_RK4) return attrs_ros<M, ExplicitStepper<TabRK4>, true>(block, smem, fa, bps);
     return attrs_ros<M, ExplicitStepper<TabTsit5>, true>(block, smem, fa, bps);
 }
@@ -358,15 +371,23 @@ static int ensure_partials(dynoed_ctx* ctx, int need, int par) {
 // the per-interval unweighted quadratures (Rosenbrock)
 static size_t traj_bytes_for(const dynoed_ctx* ctx, int grid, int kidx = 1) {
     const auto& mi = ctx->model->info;
-    const size_t per_lane = (ctx->rosenbrock || kidx == 2) ? (size_t)ctx->n_intervals * mi.n_obs * mi.nF
-                                                           : (size_t)ctx->n_steps * mi.nz;
+    const size_t per_lane = (ctx->rosenbrock || kidx == 2)
+                                ? (size_t)ctx->n_intervals * mi.n_obs * mi.nF + ctx->base.n_ctrl_values
+                                : (size_t)ctx->n_steps * mi.nz;
     return (size_t)grid * per_lane * kMaxTile * sizeof(double);
 }
 
 // 0: objective only, 1: gradient (adjoint sweep, or the Rosenbrock kernel), 2: forward-only gradient
 static int kernel_index(const dynoed_ctx* ctx, bool grad, uint32_t flags) {
+    (void)ctx;
     if (!grad) return 0;
-    return ((flags & DYNOED_GRAD_NO_CONTROLS) && !ctx->rosenbrock) ? 2 : 1;
+    return (flags & DYNOED_GRAD_NO_CONTROLS) ? 2 : 1;
+}
+
+// the method code the model's launch / attrs dispatch understands, per kernel index
+static int method_code(const dynoed_ctx* ctx, int kidx) {
+    if (ctx->rosenbrock) return (kidx == 1 && ctx->model->info.n_ctrl > 0) ? (ctx->method | kCtrlGrad) : ctx->method;
+    return kidx == 2 ? kFwdOnly + ctx->method : ctx->method;
 }
 
 static size_t smem_bytes(const dynoed_ctx* ctx) {
@@ -523,7 +544,7 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     P.step_t = ctx->d_step_t;
     P.step_h = ctx->d_step_h;
     P.indicators = ctx->d_indicators;
-    for (int k = 0; k < mi.n_ctrl; ++k) P.ctrl_off[k] = d->ctrl_offsets[k];
+    for (int k = 0; k < mi.n_ctrl; ++k) { P.ctrl_off[k] = d->ctrl_offsets[k]; P.ctrl_len[k] = len[k]; P.n_ctrl_values += len[k]; }
     for (int k = 0; k < mi.n_obs; ++k) P.w_off[k] = d->w_offsets[k];
     P.ic_off = d->ic_offset;
     P.tau_off = d->tau_offset;
@@ -545,9 +566,7 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     if (smem > (size_t)prop.sharedMemPerBlockOptin)
         return bail(DYNOED_EINVAL, "tile * n_var does not fit in shared memory; use a smaller tile");
     for (int g = 0; g < 3; ++g) {
-        if (g == 2 && rosenbrock) { ctx->fa[2] = ctx->fa[1]; ctx->bps[2] = ctx->bps[1]; break; }
-        CUC(m->attrs(g == 2 ? kFwdOnly + ctx->method : ctx->method, g >= 1, ctx->ucoef, tile, smem, &ctx->fa[g],
-                     &ctx->bps[g]));
+        CUC(m->attrs(method_code(ctx, g), g >= 1, ctx->ucoef, tile, smem, &ctx->fa[g], &ctx->bps[g]));
         if (ctx->bps[g] < 1) return bail(DYNOED_ECUDA, "kernel cannot be resident with this tile size");
     }
 #undef CUC
@@ -655,8 +674,7 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
         }
         CU(cudaEventRecord(ctx->ev_k0, st));
     }
-    CU(ctx->model->launch(cur.kidx == 2 ? kFwdOnly + ctx->method : ctx->method, grad != nullptr, ctx->ucoef, pdl, P, grid,
-                          ctx->tile, smem_bytes(ctx), st));
+    CU(ctx->model->launch(method_code(ctx, cur.kidx), grad != nullptr, ctx->ucoef, pdl, P, grid, ctx->tile, smem_bytes(ctx), st));
     if (ctx->profiling) { CU(cudaEventRecord(ctx->ev_k1, st)); ctx->ev_pending = true; }
     cur.serial = stream_new_serial(st);
     ctx->prev = cur;
@@ -848,8 +866,7 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         part_base += grid;
         P.use_tma = (((size_t)ctx->tile * ctx->n_var * 8) % 16 == 0) ? 1 : 0;
         P.index_base = off;
-        CU(ctx->model->launch(kidx == 2 ? kFwdOnly + ctx->method : ctx->method, g, ctx->ucoef, false, P, grid, ctx->tile,
-                              smem_bytes(ctx), s.stream));
+        CU(ctx->model->launch(method_code(ctx, kidx), g, ctx->ucoef, false, P, grid, ctx->tile, smem_bytes(ctx), s.stream));
         ctx->launches++;
         double* o_crit = staged ? s.h_crit : crit + off;
         double* o_grad = staged ? s.h_grad : (g ? grad + off * ctx->n_var : nullptr);
@@ -880,10 +897,6 @@ static int eval_common(dynoed_ctx* ctx, const double* designs, int64_t n, double
     if (n < 0) return fail(ctx, DYNOED_EINVAL, "n < 0");
     if (n == 0) { ctx->have_batch = false; return DYNOED_OK; }
     if (!designs || !crit) return fail(ctx, DYNOED_EINVAL, "designs/crit is NULL");
-    if (grad && ctx->rosenbrock && ctx->model->info.n_ctrl > 0 && !(flags & DYNOED_GRAD_NO_CONTROLS))
-        return fail(ctx, DYNOED_EUNSUPPORTED,
-                    "the Rosenbrock integrators do not differentiate with respect to controls; pass "
-                    "DYNOED_GRAD_NO_CONTROLS (control entries become NaN), grad = NULL, or use an explicit method");
     ctx->kidx_req = kernel_index(ctx, grad != nullptr, flags);
     CU(cudaSetDevice(ctx->device));
     const int kd = ptr_kind(designs);

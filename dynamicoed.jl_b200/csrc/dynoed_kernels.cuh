@@ -65,6 +65,8 @@ struct EvalParams {
     const int* __restrict__ indicators;   // [NCTRL+NOBS][N], 0-based index into the variable's own grid
     // layout
     int ctrl_off[kMaxCtrl];
+    int ctrl_len[kMaxCtrl];               // values per control block of the design vector
+    int n_ctrl_values;                    // their sum
     int w_off[kMaxObs];
     int ic_off;
     int tau_off;

@@ -16,10 +16,11 @@
 // d(J G_j + f_p,j)/dx . U_x and dq/dy . U are emitted symbolically (Model::ros_ling / ros_linp).
 // The reference factors the dense n_aug x n_aug matrix instead.
 //
-// Gradient: d/dw and d/dtau need no extra integration; d/d(unknown initial conditions) is carried
-// as a forward-mode dual part through the whole scheme (the way the reference's ForwardDiff does,
-// /root/reference/src/problem.jl:154), one integration pass per unknown initial condition.
-// Controls as design variables are not differentiated by this integrator (DYNOED_EUNSUPPORTED).
+// Gradient: d/dw and d/dtau need no extra integration; d/d(unknown initial conditions) and
+// d/d(control values) are carried as a forward-mode dual part through the whole scheme (the way
+// the reference's ForwardDiff does, /root/reference/src/problem.jl:154), one integration pass per
+// unknown initial condition / control value (controls: Rosenbrock only — the explicit tableaus have
+// the adjoint sweep of oed_eval_kernel; with DYNOED_GRAD_NO_CONTROLS their entries are NaN).
 #pragma once
 #include <type_traits>
 
@@ -181,7 +182,7 @@ struct SmallLU {
 // ----------------------------------------------------------------------------------------------
 template <class M, class RT, class T>
 __device__ __forceinline__ void rosenbrock_step(double t, double h, T (&z)[M::NZ], T (&Pq)[M::NOBS * M::NF],
-                                                const double* u, const double* th, const double* c) {
+                                                const T* u, const double* th, const T* c) {
     constexpr int S = RT::S, NX = M::NX, NP = M::NP, NZ = M::NZ, NQ = M::NOBS * M::NF;
     const double c0 = 1.0 / (h * RT::gamma);
     const double ih = 1.0 / h;
@@ -273,7 +274,7 @@ template <class RT>
 struct RosenbrockStepper {
     template <class M, class T>
     __device__ __forceinline__ static void step(double t, double h, T (&z)[M::NZ], T (&Pq)[M::NOBS * M::NF],
-                                                const double* u, const double* th, const double* c) {
+                                                const T* u, const double* th, const T* c) {
         rosenbrock_step<M, RT, T>(t, h, z, Pq, u, th, c);
     }
 };
@@ -282,7 +283,7 @@ template <class Tab>
 struct ExplicitStepper {
     template <class M, class T>
     __device__ __forceinline__ static void step(double t, double h, T (&z)[M::NZ], T (&Pq)[M::NOBS * M::NF],
-                                                const double* u, const double* th, const double* c) {
+                                                const T* u, const double* th, const T* c) {
         constexpr int S = Tab::S, NZ = M::NZ, NQ = M::NOBS * M::NF;
         T k[S][NZ], zacc[NZ];
 #pragma unroll
@@ -319,7 +320,7 @@ struct ExplicitStepper {
 // comment for the gradient).  Control entries of the gradient are NaN ("not computed").
 // P.traj is used as the per-interval quadrature scratch [grid][N][NOBS*NF][kMaxTile].
 // ----------------------------------------------------------------------------------------------
-template <class M, class Stepper, bool GRAD>
+template <class M, class Stepper, bool GRAD, bool CTRLGRAD>
 __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams P) {
     constexpr int NX = M::NX, NP = M::NP, NZ = M::NZ, NF = M::NF, NOBS = M::NOBS, NCTRL = M::NCTRL;
     constexpr int NCU = NCTRL > 0 ? NCTRL : 1, NQ = NOBS * NF;
@@ -327,8 +328,9 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams 
     // directions at once (Dual<NIC>) is 1 + NIC units of arithmetic instead of 2 NIC, but its register
     // footprint spills 3.6-4.9 KB per lane for models of chem6's size (2.3-2.9 KB this way) and
     // measured 1.1x (ROS2) to 1.4x (ROS3P) slower on B200.
-    constexpr bool DUAL = GRAD && M::NIC > 0;
-    constexpr int NDIR = DUAL ? M::NIC : 1;
+    // CTRLGRAD (Rosenbrock with controls): one more pass per control VALUE of the design vector.
+    constexpr bool CG = GRAD && CTRLGRAD && M::NCTRL > 0;
+    constexpr bool DUAL = GRAD && (M::NIC > 0 || CG);
     using T = typename std::conditional<DUAL, Dual<1>, double>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -369,9 +371,24 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams 
         if (tid < count) {
             double* row = tile_buf + (size_t)tid * n_var;
             const long long g = g0 + tid;
-            double* pq = P.traj + ((size_t)blockIdx.x * N * NQ) * kMaxTile + tid;
+            // per-lane scratch: [N][NQ] interval quadratures, then one slot per control value
+            double* pq = P.traj + ((size_t)blockIdx.x * (N * NQ + P.n_ctrl_values)) * kMaxTile + tid;
+            double* cg = pq + (size_t)N * NQ * kMaxTile;
             double Ls[NF], L[NF], icg[M::NIC > 0 ? M::NIC : 1];
-            for (int dir = 0; dir < NDIR; ++dir) {
+            const int ndir = DUAL ? M::NIC + (CG ? P.n_ctrl_values : 0) : 1;
+            // direction -> (control k, entry idx) for dir >= NIC: controls are laid out block after block
+            for (int dir = 0; dir < (ndir > 0 ? ndir : 1); ++dir) {
+                int dk = -1, didx = -1;
+                if (CG && dir >= M::NIC) {
+                    int rest = dir - M::NIC;
+#pragma unroll
+                    for (int k = 0; k < NCTRL; ++k) {
+                        if (dk < 0) {
+                            if (rest < P.ctrl_len[k]) { dk = k; didx = rest; }
+                            else rest -= P.ctrl_len[k];
+                        }
+                    }
+                }
                 T z[NZ], F[NF];
 #pragma unroll
                 for (int a = 0; a < NX; ++a) z[a] = T(P.x0[a]);
@@ -395,12 +412,17 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams 
                     for (int a = 0; a < NF; ++a) xg[NZ + a] = 0.0;
                 }
                 for (int j = 0; j < N; ++j) {
-                    double u[NCU], w[NOBS], c[M::NCONST];
+                    T u[NCU], c[M::NCONST];
+                    double w[NOBS];
 #pragma unroll
-                    for (int k = 0; k < NCTRL; ++k) u[k] = row[P.ctrl_off[k] + __ldg(P.indicators + k * N + j)];
+                    for (int k = 0; k < NCTRL; ++k) {
+                        const int idx = __ldg(P.indicators + k * N + j);
+                        u[k] = T(row[P.ctrl_off[k] + idx]);
+                        if constexpr (CG) u[k].d[0] = (k == dk && idx == didx) ? 1.0 : 0.0;
+                    }
 #pragma unroll
                     for (int i = 0; i < NOBS; ++i) w[i] = row[P.w_off[i] + __ldg(P.indicators + (NCTRL + i) * N + j)];
-                    M::consts(u, th, c);
+                    M::template consts_t<T>(u, th, c);
                     T Pq[NQ];
 #pragma unroll
                     for (int a = 0; a < NQ; ++a) Pq[a] = T(0.0);
@@ -443,13 +465,14 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams 
 #pragma unroll
                         for (int ii = 0; ii <= jj; ++ii) Ls[tri(ii, jj)] = (ii == jj ? 1.0 : 2.0) * L[tri(ii, jj)];
                 }
-                if constexpr (DUAL) {   // <Lambda, dF/dx0_dir> with the symmetric pairing
+                if constexpr (DUAL) {   // <Lambda, dF/d(direction)> with the symmetric pairing
                     double sd = 0.0;
 #pragma unroll
                     for (int k = 0; k < NF; ++k) sd = fma(Ls[k], dual_part(F[k], 0), sd);
 #pragma unroll
                     for (int a = 0; a < M::NIC; ++a)
                         if (a == dir) icg[a] = sd;          // static indexing keeps icg in registers
+                    if (CG && dir >= M::NIC) cg[(size_t)(dir - M::NIC) * kMaxTile] = sd;
                 }
             }
 
@@ -478,13 +501,14 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams 
                     if (wk[i] >= 0) row[P.w_off[i] + wk[i]] = wb[i];
 #pragma unroll
                 for (int a = 0; a < M::NIC; ++a) row[P.ic_off + a] = icg[a];
-                // controls are not differentiated by this kernel: their entries say so
-                for (int k = 0; k < NCTRL; ++k) {
-                    int last = -1;
-                    for (int j = 0; j < N; ++j) {
-                        const int idx = __ldg(P.indicators + k * N + j);
-                        if (idx != last) { row[P.ctrl_off[k] + idx] = __longlong_as_double(0x7ff8000000000000LL); last = idx; }
-                    }
+                // controls: one dual pass per value (CTRLGRAD), otherwise "not computed" (NaN)
+                {
+                    int d = 0;
+#pragma unroll
+                    for (int k = 0; k < NCTRL; ++k)
+                        for (int idx = 0; idx < P.ctrl_len[k]; ++idx, ++d)
+                            row[P.ctrl_off[k] + idx] = CG ? cg[(size_t)d * kMaxTile]
+                                                          : __longlong_as_double(0x7ff8000000000000LL);
                 }
                 double trL = 1.0;
 #pragma unroll

@@ -423,6 +423,7 @@ def emit_model(name: str, s: SimplifiedOEDSystem) -> tuple[str, dict]:
     for k, e in enumerate(hoist.table.keys()):
         cb.out(f"c[{k}]", e)
     code["consts"], flops["consts"] = cb.render(pr, inputs)
+    code["consts_t"], _ = cb.render(pr, inputs, scalar="T")
     n_const = max(len(hoist.table), 1)
     autonomous = not any(sp.sympify(e).has(t) for e in list(f) + list(s.Qexpr))
 
@@ -496,32 +497,39 @@ struct {cname} {{
     }}
     // ---- Rosenbrock pieces; T = double or a forward-mode dual number ------------------------
     static constexpr bool AUTONOMOUS = {'true' if autonomous else 'false'};
+    // the hoisted (control, parameter) sub-expressions for a dual-number control
+    template <class T>
+    __device__ __forceinline__ static void consts_t(const T* __restrict__ u,
+                                                    const double* __restrict__ th,
+                                                    T* __restrict__ c) {{
+{code['consts_t']}
+    }}
     // g(y) = [f; J G + f_p] and the unweighted quadrature integrands q_i = (Q_i^T Q_i)_triu
     template <class T>
     __device__ __forceinline__ static void ros_f(double t, const T* __restrict__ z,
-            const double* __restrict__ u, const double* __restrict__ th,
-            const double* __restrict__ c, T* __restrict__ dz, T* __restrict__ dP) {{
+            const T* __restrict__ u, const double* __restrict__ th,
+            const T* __restrict__ c, T* __restrict__ dz, T* __restrict__ dP) {{
 {code['ros_f']}
     }}
     // A = f_x(x), row-major [NX][NX]
     template <class T>
     __device__ __forceinline__ static void ros_jac(double t, const T* __restrict__ z,
-            const double* __restrict__ u, const double* __restrict__ th,
-            const double* __restrict__ c, T* __restrict__ A) {{
+            const T* __restrict__ u, const double* __restrict__ th,
+            const T* __restrict__ c, T* __restrict__ A) {{
 {code['ros_jac']}
     }}
     // BU[j*NX+i] = d(J G_j + f_p,j)_i/dx . U_x   (off-diagonal block of the augmented Jacobian)
     template <class T>
     __device__ __forceinline__ static void ros_ling(double t, const T* __restrict__ z,
-            const double* __restrict__ u, const double* __restrict__ th,
-            const double* __restrict__ c, const T* __restrict__ U, T* __restrict__ BU) {{
+            const T* __restrict__ u, const double* __restrict__ th,
+            const T* __restrict__ c, const T* __restrict__ U, T* __restrict__ BU) {{
 {code['ros_ling']}
     }}
     // dPU = dq/dy . U  (rows of the quadratures)
     template <class T>
     __device__ __forceinline__ static void ros_linp(double t, const T* __restrict__ z,
-            const double* __restrict__ u, const double* __restrict__ th,
-            const double* __restrict__ c, const T* __restrict__ U, T* __restrict__ dPU) {{
+            const T* __restrict__ u, const double* __restrict__ th,
+            const T* __restrict__ c, const T* __restrict__ U, T* __restrict__ dPU) {{
 {code['ros_linp']}
     }}
 }};

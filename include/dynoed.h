@@ -51,15 +51,17 @@ extern "C" {
 #define DYNOED_RK4 0
 #define DYNOED_TSIT5 1 /* Tsit5 tableau, fixed step */
 /* fixed-grid Rosenbrock methods for the stiff / DAE configuration (the reference uses Rodas5,
- * /root/reference/test/references/Rober.jl:29); autonomous models only; gradients with respect to
- * weights, tau and unknown initial conditions (not controls) */
+ * /root/reference/test/references/Rober.jl:29); autonomous models only.  Gradients: weights and tau
+ * from per-interval quadratures; unknown initial conditions and control values by one forward-mode
+ * dual pass each (there is no adjoint sweep for these schemes) */
 #define DYNOED_ROS2 2  /* 2 stages, order 2, L-stable */
 #define DYNOED_ROS3P 3 /* 3 stages, order 3, A-stable */
 #define DYNOED_RODAS3 4 /* 4 stages, order 3, stiffly accurate, L-stable */
 
 /* flags of dynoed_eval_batch[_async] */
 #define DYNOED_GRAD_NO_CONTROLS 1u /* gradient w.r.t. weights, tau and unknown initial conditions only:
-                                    * forward sweep with per-interval quadratures, no adjoint sweep;
+                                    * forward sweep with per-interval quadratures, no adjoint sweep
+                                    * (explicit tableaus) / no control passes (Rosenbrock);
                                     * control entries of grad are NaN ("not computed") */
 
 typedef struct dynoed_ctx dynoed_ctx;

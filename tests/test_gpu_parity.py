@@ -378,17 +378,23 @@ def test_robertson_reference_golden_through_the_boundary(built_library):
     assert abs(c[0]) < 1e-2
 
 
-def test_rosenbrock_rejects_control_gradients_and_time_dependence(built_library):
+@pytest.mark.parametrize("method", ["ros2", "rodas3"])
+def test_rosenbrock_with_controls_full_gradient(method, built_library):
+    """LV-fishing under a Rosenbrock integrator: the control gradient comes from one dual pass per
+    control value (no adjoint sweep exists for the Rosenbrock schemes); with DYNOED_GRAD_NO_CONTROLS
+    the control entries are NaN and the rest is unchanged."""
     from oracle.cpp_oracle import CppOracle
     from oracle.oed_oracle import Oracle
-    prob = D.OEDProblem(D.OEDSystem(models.lotka_volterra_fishing()), D.FisherDCriterion(), alg=D.ROS2(4))
+    prob = D.OEDProblem(D.OEDSystem(models.lotka_volterra_fishing()), D.FisherDCriterion(), alg=ROS[method](4))
     ctx = prob.context()
-    des = random_designs("lv_fishing", 71, 64, 3)
-    with pytest.raises(runtime.DynoedError):
-        ctx.evaluate(des)                                      # gradient w.r.t. controls: unsupported
-    c, _, F = ctx.evaluate(des, grad=False)                    # the objective itself is fine
-    oc, _, oF = CppOracle("lv_fishing", Oracle(models.lotka_volterra_fishing(), 1, "ros2", 4)).evaluate(des, grad=False)
-    assert rel(F, oF) < RTOL and rel(c, oc) < RTOL
+    des = random_designs("lv_fishing", 71, 200, 3)
+    c, g, F = ctx.evaluate(des)
+    oc, og, oF = CppOracle("lv_fishing", Oracle(models.lotka_volterra_fishing(), 1, method, 4)).evaluate(des, grad=True)
+    assert rel(F, oF) < RTOL and rel(c, oc) < RTOL and rel_rows(g, og) < RTOL
+    c2, g2, _ = ctx.evaluate(des, flags=runtime.GRAD_NO_CONTROLS)
+    assert np.all(np.isnan(g2[:, :10])) and rel(c2, oc) < RTOL and rel_rows(g2[:, 10:], og[:, 10:]) < RTOL
+    c3, _, F3 = ctx.evaluate(des, grad=False)
+    assert rel(F3, oF) < RTOL and rel(c3, oc) < RTOL
 
 
 def test_argmin_record_and_gathered_reduction(built_library):
