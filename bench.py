@@ -388,6 +388,32 @@ def main():
     e2e_single = e2e_run(1)
     e2e_value = e2e_run(E2E_THREADS)
 
+    # one host thread, two calls in flight (dynoed_eval_batch_host_async / dynoed_wait)
+    def e2e_pipelined():
+        c0 = sets[0][0]
+        ids = [None] * len(sets)
+        barrier()
+        t0 = time.perf_counter()
+        acc = 0.0
+        for k in range(e2e_steps):
+            b = k % len(sets)
+            _, hp, hc, hg, hf = sets[b]
+            if ids[b] is not None:
+                c0.wait(ids[b])
+                acc += float(hc[0])
+            ids[b] = c0.eval_batch_host_async(hp.numpy(), hc.numpy(), hg.numpy(), hf.numpy())
+        for b, i in enumerate(ids):
+            if i is not None:
+                c0.wait(i)
+                acc += float(sets[b][2][0])
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tmax = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dt = float(tmax)
+        return n * world * e2e_steps / dt
+    e2e_piped = e2e_pipelined()
+
     if rank == 0:
         ks = ctx.kernel_stats(True)
         flops = ks["flops_per_design_grad"] * n
@@ -434,6 +460,7 @@ def main():
                         "d2h_bytes_per_step": n * (1 + n_var + 3) * 8, "steps": e2e_steps,
                         "host_memory": "pinned", "host_threads": E2E_THREADS,
                         "value_single_host_thread": e2e_single,
+                        "value_single_host_thread_pipelined": e2e_piped,
                         "note": "blocking dynoed_eval_batch calls on host buffers, alternate steps on two "
                                 "host threads (one ctx each); PCIe-bound"},
                 "gpu_launches": int(launches), "clocks": clocks, "sub_metrics": sub}

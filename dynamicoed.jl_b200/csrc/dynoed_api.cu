@@ -302,6 +302,11 @@ struct dynoed_ctx {
         const char* out0[3] = {nullptr, nullptr, nullptr};
         const char* out1[3] = {nullptr, nullptr, nullptr};
     } prev;
+    // pipelined host calls (dynoed_eval_batch_host_async): completion event per scratch parity
+    cudaEvent_t call_done[2] = {nullptr, nullptr};
+    int64_t call_of_parity[2] = {-1, -1};   // id of the last host call that used each parity
+    int64_t host_seq = 0;                   // host calls enqueued so far (ids are 1-based)
+    bool stream_dirty = true;               // work other than host calls was put on ctx->stream since the last host call
     bool pdl_enabled = true;
     bool zero_copy = true;             // store crit / fim straight into page-locked host arrays
     bool host_staging = true;          // pageable caller arrays go through page-locked staging
@@ -586,7 +591,7 @@ void dynoed_destroy(dynoed_ctx* ctx) {
         if (s.done) cudaEventDestroy(s.done);
     }
     cudaFree(ctx->d_first_step); cudaFree(ctx->d_step_t); cudaFree(ctx->d_step_h); cudaFree(ctx->d_indicators);
-    for (int q = 0; q < 2; ++q) { cudaFree(ctx->traj[q]); cudaFree(ctx->part_val[q]); cudaFree(ctx->part_idx[q]); }
+    for (int q = 0; q < 2; ++q) { cudaFree(ctx->traj[q]); cudaFree(ctx->part_val[q]); cudaFree(ctx->part_idx[q]); if (ctx->call_done[q]) cudaEventDestroy(ctx->call_done[q]); }
     cudaFree(ctx->d_best); cudaFree(ctx->d_ring); cudaFree(ctx->d_ticket);
     if (ctx->ev_k0) { cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -678,6 +683,7 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
     if (ctx->profiling) { CU(cudaEventRecord(ctx->ev_k1, st)); ctx->ev_pending = true; }
     cur.serial = stream_new_serial(st);
     ctx->prev = cur;
+    ctx->stream_dirty = true;
     ctx->launches++;
     ctx->pdl_launches += pdl ? 1 : 0;
     return DYNOED_OK;
@@ -767,7 +773,8 @@ static bool is_pageable(const void* p) {
 
 // host buffers: chunked pipeline, chunk k on stream k % kSlots (H2D -> kernel -> D2H in order on
 // that stream; different chunks overlap copy engines and SMs)
-static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad, double* fim) {
+static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad, double* fim,
+                     bool pipelined = false) {
     const int nF = ctx->model->info.nF;
     const bool g = grad != nullptr;
     // Chunk schedule: host_chunks equal chunks (default 8).  Measured on B200 / PCIe Gen5: 4..16 equal
@@ -838,11 +845,22 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         if (fim) memcpy(fim + off * nF, s.h_fim, sizeof(double) * cnt * nF);
         return DYNOED_OK;
     };
-    // order after whatever the ctx stream was doing
     cudaEvent_t ev;
     CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CU(cudaEventRecord(ev, ctx->stream));
-    for (int k = 0; k < kSlots && k < nchunks; ++k) CU(cudaStreamWaitEvent(ctx->slots[k].stream, ev, 0));
+    for (int q = 0; q < 2; ++q)
+        if (!ctx->call_done[q]) CU(cudaEventCreateWithFlags(&ctx->call_done[q], cudaEventDisableTiming));
+    if (pipelined && !ctx->stream_dirty && !staged) {
+        // Pipelined host call: do NOT order after the previous host call (its D2H should overlap this
+        // call's H2D; chunk c of both calls shares slot c % kSlots, whose stream keeps them in order).
+        // Only the call that used the same scratch parity (two calls back) must have finished.
+        if (ctx->call_of_parity[par] >= 0)
+            for (int k = 0; k < kSlots && k < nchunks; ++k)
+                CU(cudaStreamWaitEvent(ctx->slots[k].stream, ctx->call_done[par], 0));
+    } else {
+        // order after whatever the ctx stream was doing
+        CU(cudaEventRecord(ev, ctx->stream));
+        for (int k = 0; k < kSlots && k < nchunks; ++k) CU(cudaStreamWaitEvent(ctx->slots[k].stream, ev, 0));
+    }
     int part_base = 0;
     for (int64_t c = 0; c < nchunks; ++c) {
         Slot& s = ctx->slots[c % kSlots];
@@ -883,6 +901,10 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         CU(cudaStreamWaitEvent(ctx->stream, ev, 0));
     }
     CU(cudaEventDestroy(ev));
+    CU(cudaEventRecord(ctx->call_done[par], ctx->stream));   // fires when every chunk of THIS call has landed
+    ctx->host_seq++;
+    ctx->call_of_parity[par] = ctx->host_seq;
+    ctx->stream_dirty = false;
     ctx->last_parity = par;
     ctx->parity = par ^ 1;
     ctx->batch_seq++;
@@ -891,7 +913,7 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
 }
 
 static int eval_common(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad, double* fim,
-                       bool allow_host, bool sync, uint32_t flags = 0) {
+                       bool allow_host, bool sync, uint32_t flags = 0, bool pipelined = false) {
     if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
     ctx->err.clear();
     if (n < 0) return fail(ctx, DYNOED_EINVAL, "n < 0");
@@ -906,7 +928,7 @@ static int eval_common(dynoed_ctx* ctx, const double* designs, int64_t n, double
     if (kd == 1) rc = eval_device(ctx, designs, n, crit, grad, fim, nullptr);
     else {
         if (!allow_host) return fail(ctx, DYNOED_EINVAL, "dynoed_eval_batch_async needs device pointers");
-        rc = eval_host(ctx, designs, n, crit, grad, fim);
+        rc = eval_host(ctx, designs, n, crit, grad, fim, pipelined);
     }
     if (rc) return rc;
     if (sync) CU(cudaStreamSynchronize(ctx->stream));
@@ -921,6 +943,31 @@ int dynoed_eval_batch(dynoed_ctx* ctx, const double* designs, int64_t n, double*
 int dynoed_eval_batch_async(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad,
                             double* fim, uint32_t flags) {
     return eval_common(ctx, designs, n, crit, grad, fim, false, false, flags);
+}
+
+int dynoed_eval_batch_host_async(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad,
+                                 double* fim, uint32_t flags, int64_t* call_id) {
+    if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    if (n <= 0 || !designs || !crit) return fail(ctx, DYNOED_EINVAL, "bad arguments");
+    if (ptr_kind(designs) != 0) return fail(ctx, DYNOED_EINVAL, "dynoed_eval_batch_host_async takes host pointers");
+    const int rc = eval_common(ctx, designs, n, crit, grad, fim, true, false, flags, true);
+    if (rc) return rc;
+    if (call_id) *call_id = ctx->host_seq;
+    return DYNOED_OK;
+}
+
+int dynoed_wait(dynoed_ctx* ctx, int64_t call_id) {
+    if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    if (call_id < 1 || call_id > ctx->host_seq) return fail(ctx, DYNOED_EINVAL, "unknown call id");
+    CU(cudaSetDevice(ctx->device));
+    // the event of the parity this call used (re-recorded by the call two later, which is ordered after it)
+    for (int q = 0; q < 2; ++q)
+        if (ctx->call_of_parity[q] >= call_id && ((ctx->call_of_parity[q] - call_id) % 2 == 0)) {
+            CU(cudaEventSynchronize(ctx->call_done[q]));
+            return DYNOED_OK;
+        }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return DYNOED_OK;
 }
 
 int dynoed_sync(dynoed_ctx* ctx) {

@@ -57,7 +57,8 @@ class KernelStats(C.Structure):
 EXPORTS = ["dynoed_abi_version", "dynoed_model_count", "dynoed_model_name", "dynoed_model_query",
            "dynoed_create", "dynoed_destroy", "dynoed_set_criterion", "dynoed_set_stream",
            "dynoed_own_stream",
-           "dynoed_eval_batch", "dynoed_eval_batch_async", "dynoed_sync", "dynoed_argmin",
+           "dynoed_eval_batch", "dynoed_eval_batch_async", "dynoed_eval_batch_host_async", "dynoed_wait",
+           "dynoed_sync", "dynoed_argmin",
            "dynoed_argmin_async", "dynoed_argmin_record_async", "dynoed_argmin_history_async",
            "dynoed_argmin_gathered",
            "dynoed_set_profiling", "dynoed_kernel_time",
@@ -91,6 +92,8 @@ def lib(path: str | None = None):
         L.dynoed_own_stream.argtypes = [vp]
         L.dynoed_eval_batch.argtypes = [vp, dp, i64, dp, dp, dp, C.c_uint32]
         L.dynoed_eval_batch_async.argtypes = [vp, dp, i64, dp, dp, dp, C.c_uint32]
+        L.dynoed_eval_batch_host_async.argtypes = [vp, dp, i64, dp, dp, dp, C.c_uint32, C.POINTER(C.c_int64)]
+        L.dynoed_wait.argtypes = [vp, i64]
         L.dynoed_sync.argtypes = [vp]
         L.dynoed_argmin.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
         L.dynoed_argmin_async.argtypes = [vp, dp, dp]
@@ -225,6 +228,16 @@ class Context:
         n = int(designs.shape[0]) if n is None else int(n)
         fn = self._L.dynoed_eval_batch_async if async_ else self._L.dynoed_eval_batch
         _check(fn(self._h, _ptr(designs), n, _ptr(crit), _ptr(grad), _ptr(fim), int(flags)), self._h, self._L)
+
+    def eval_batch_host_async(self, designs, crit, grad=None, fim=None, flags=0) -> int:
+        """Pipelined host-buffer evaluation (page-locked numpy arrays): returns a call id for `wait`."""
+        cid = C.c_int64()
+        _check(self._L.dynoed_eval_batch_host_async(self._h, _ptr(designs), int(designs.shape[0]), _ptr(crit),
+                                                    _ptr(grad), _ptr(fim), int(flags), C.byref(cid)), self._h, self._L)
+        return int(cid.value)
+
+    def wait(self, call_id: int):
+        _check(self._L.dynoed_wait(self._h, int(call_id)), self._h, self._L)
 
     def sync(self):
         _check(self._L.dynoed_sync(self._h), self._h, self._L)

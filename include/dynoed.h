@@ -139,6 +139,15 @@ int dynoed_eval_batch(dynoed_ctx* ctx, const double* designs, int64_t n, double*
 int dynoed_eval_batch_async(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit,
                             double* grad, double* fim, uint32_t flags);
 int dynoed_sync(dynoed_ctx* ctx);
+/* Pipelined HOST-buffer evaluation for a single host thread: enqueues the chunked H2D / kernel / D2H
+ * pipeline and returns at once with a call id; dynoed_wait(ctx, id) blocks until that call's results
+ * are in the caller's arrays.  Consecutive calls overlap (one call's D2H under the next call's H2D),
+ * which a sequence of blocking dynoed_eval_batch calls cannot do.  Use page-locked arrays
+ * (dynoed_host_alloc) that stay valid and untouched until the wait; pageable arrays are accepted but
+ * are staged synchronously (the call has completed when it returns).  At most two calls in flight. */
+int dynoed_eval_batch_host_async(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit,
+                                 double* grad, double* fim, uint32_t flags, int64_t* call_id);
+int dynoed_wait(dynoed_ctx* ctx, int64_t call_id);
 /* arg-min of the criterion over the most recent batch (multistart selection) */
 int dynoed_argmin(dynoed_ctx* ctx, int64_t* idx, double* val);
 

@@ -28,3 +28,22 @@ for T in (1, 2, 3):
     dt = (time.perf_counter() - t) / steps
     print(f"threads {T}: {dt*1e3:.3f} ms/step {n/dt/1e6:.1f} Mdesigns/s", flush=True)
     for s in sets: s[0].close()
+# single host thread, pipelined host calls (two in flight)
+ctx, _, _, _, _ = mk()
+bufs = [mk()[1:] for _ in range(2)]
+ids = [None, None]
+for k in range(4):
+    hp, hc, hg, hf = bufs[k % 2]
+    if ids[k % 2] is not None: ctx.wait(ids[k % 2])
+    ids[k % 2] = ctx.eval_batch_host_async(hp.numpy(), hc.numpy(), hg.numpy(), hf.numpy())
+for i in ids: ctx.wait(i)
+ids = [None, None]; steps = 60
+t = time.perf_counter()
+for k in range(steps):
+    hp, hc, hg, hf = bufs[k % 2]
+    if ids[k % 2] is not None:
+        ctx.wait(ids[k % 2]); _ = float(hc[0])
+    ids[k % 2] = ctx.eval_batch_host_async(hp.numpy(), hc.numpy(), hg.numpy(), hf.numpy())
+for i in ids: ctx.wait(i)
+dt = (time.perf_counter() - t) / steps
+print(f"1 thread, pipelined host calls: {dt*1e3:.3f} ms/step {n/dt/1e6:.1f} Mdesigns/s", flush=True)

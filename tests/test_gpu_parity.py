@@ -759,3 +759,41 @@ def test_stiff_golden_fixtures(name, method, crit_cls, built_library):
     den = np.maximum(np.abs(z["crit"]), np.max(np.abs(z["F"]), axis=1))
     assert rel(F, z["F"]) < RTOL and float(np.max(np.abs(c - z["crit"]) / den)) < RTOL
     assert rel_rows(g, z["grad"]) < RTOL
+
+
+def test_pipelined_host_calls_match_blocking_ones(built_library):
+    """dynoed_eval_batch_host_async / dynoed_wait: a single host thread keeps two host-buffer calls in
+    flight (page-locked arrays); every call's results equal the blocking call's bit for bit, in any
+    interleaving with device-path launches."""
+    import torch
+    ctx = make_problem("lv_fishing", D.FisherDCriterion).context()
+    n, K = 30000, 6
+    des = [random_designs("lv_fishing", 71, n, 50 + k) for k in range(K)]
+    ref = [ctx.evaluate(d) for d in des]
+    sets = [(torch.empty((n, 71), dtype=torch.float64).pin_memory(), torch.empty(n, dtype=torch.float64).pin_memory(),
+             torch.empty((n, 71), dtype=torch.float64).pin_memory(), torch.empty((n, 3), dtype=torch.float64).pin_memory())
+            for _ in range(2)]
+    ids = [None, None]
+    for k in range(K + 1):
+        b = k % 2
+        if k >= 2 or (k >= 1 and False):
+            pass
+        if ids[b] is not None:                       # the call that used this buffer set two steps ago
+            ctx.wait(ids[b])
+            hp, hc, hg, hf = sets[b]
+            c, g, F = ref[k - 2]
+            assert np.array_equal(hc.numpy(), c) and np.array_equal(hg.numpy(), g) and np.array_equal(hf.numpy(), F)
+        if k < K:
+            hp, hc, hg, hf = sets[b]
+            hp.numpy()[:] = des[k]
+            hc.fill_(float("nan")); hg.fill_(float("nan"))
+            ids[b] = ctx.eval_batch_host_async(hp.numpy(), hc.numpy(), hg.numpy(), hf.numpy())
+            if k == 3:                               # a device-path launch in between must not break ordering
+                d = torch.from_numpy(des[0]).cuda(); dc = torch.empty(n, dtype=torch.float64, device="cuda")
+                ctx.eval_batch(d, dc, None, None)
+                assert np.array_equal(dc.cpu().numpy(), ref[0][0])
+    ctx.wait(ids[(K - 1) % 2])
+    hp, hc, hg, hf = sets[(K - 1) % 2]
+    assert np.array_equal(hc.numpy(), ref[K - 1][0]) and np.array_equal(hg.numpy(), ref[K - 1][1])
+    with pytest.raises(runtime.DynoedError):
+        ctx.wait(10 ** 6)
