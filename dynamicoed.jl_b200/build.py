@@ -41,6 +41,7 @@ def build_library(out_path: str, models_dir: str | None = None, force: bool = Fa
     if not force and _newer(out_path, srcs):
         return out_path
     cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+    cmd += [f"-D{d}" for d in os.environ.get("DYNOED_NVCC_DEFINES", "").split() if d]
     if os.path.abspath(models_dir) != os.path.abspath(os.path.join(CSRC, "generated")):
         cmd += [f'-DDYNOED_MODELS_HEADER="{os.path.join(os.path.abspath(models_dir), "models.cuh")}"']
     cmd += ["-o", out_path, srcs[0]]

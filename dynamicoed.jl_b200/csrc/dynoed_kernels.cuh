@@ -595,10 +595,12 @@ __device__ __forceinline__ void backward_interval(const EvalParams& P, int s0, i
 #pragma unroll
         for (int a = 0; a < NZ; ++a) znext[a] = ld_pinned(tr + ((size_t)sp * NZ + a) * kMaxTile);
         const double tnext = __ldg(P.step_t + sp), hnext = __ldg(P.step_h + sp);
+#ifndef DYNOED_NO_L2_PREFETCH
         if (s >= 3) {
 #pragma unroll
             for (int a = 0; a < NZ; ++a) prefetch_l2(tr + ((size_t)(s - 3) * NZ + a) * kMaxTile);
         }
+#endif
         if (UC) {
             rk_adjoint_step<M, Tab>(tcur, P.coef, zn, lam, u, cw, th, c, L, ub, wb);
         } else {
