@@ -294,26 +294,29 @@ def main():
         msx = s0.elapsed_time(s1) / reps
         sub[key] = {"designs_per_s_per_gpu": n / msx * 1e3, "ms_per_step": msx, "flops_per_design": fl,
                     "tflops": fl * n / msx / 1e9}
-    # the reference's default tableau (Tsit5, /root/reference/src/problem.jl:25) on the same batch
+    # other integrator settings on the same batch: the reference's default tableau (Tsit5,
+    # /root/reference/src/problem.jl:25) and RK4 with m = 1 and m = 16 substeps
     if rank == 0:
-        ctx5 = D.OEDProblem(D.OEDSystem(models.lotka_volterra_fishing()), D.FisherDCriterion(),
-                            alg=D.Tsit5(SUBSTEPS), device=local).context()
-        ctx5.set_stream(stream.cuda_stream)
-        for k in range(3):
-            ctx5.eval_batch(d_in[k % NBUF], d_crit[k % NBUF], d_grad[k % NBUF], d_fim[k % NBUF], async_=True)
-        torch.cuda.synchronize()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = min(args.steps, 60)
-        s0.record(stream)
-        for k in range(reps):
-            ctx5.eval_batch(d_in[k % NBUF], d_crit[k % NBUF], d_grad[k % NBUF], d_fim[k % NBUF], async_=True)
-        s1.record(stream)
-        torch.cuda.synchronize()
-        ms5 = s0.elapsed_time(s1) / reps
-        fl5 = ctx5.kernel_stats(1)["flops_per_design_grad"]
-        sub["tsit5_tableau_full_gradient"] = {"designs_per_s_per_gpu": n / ms5 * 1e3, "ms_per_step": ms5,
-                                              "flops_per_design": fl5, "tflops": fl5 * n / ms5 / 1e9}
-        ctx5.close()
+        for key, alg in (("tsit5_tableau_full_gradient", D.Tsit5(SUBSTEPS)),
+                         ("rk4_m1_full_gradient", D.RK4(1)), ("rk4_m16_full_gradient", D.RK4(16))):
+            ctxa = D.OEDProblem(D.OEDSystem(models.lotka_volterra_fishing()), D.FisherDCriterion(),
+                                alg=alg, device=local).context()
+            ctxa.set_stream(stream.cuda_stream)
+            for k in range(3):
+                ctxa.eval_batch(d_in[k % NBUF], d_crit[k % NBUF], d_grad[k % NBUF], d_fim[k % NBUF], async_=True)
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = min(args.steps, 40)
+            s0.record(stream)
+            for k in range(reps):
+                ctxa.eval_batch(d_in[k % NBUF], d_crit[k % NBUF], d_grad[k % NBUF], d_fim[k % NBUF], async_=True)
+            s1.record(stream)
+            torch.cuda.synchronize()
+            msa = s0.elapsed_time(s1) / reps
+            fla = ctxa.kernel_stats(1)["flops_per_design_grad"]
+            sub[key] = {"designs_per_s_per_gpu": n / msa * 1e3, "ms_per_step": msa,
+                        "flops_per_design": fla, "tflops": fla * n / msa / 1e9}
+            ctxa.close()
     if world > 1:
         tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
