@@ -290,6 +290,10 @@ struct dynoed_ctx {
     long long* d_ring = nullptr;       // [kRing][2]: the same record for the last kRing batches
     int64_t batch_seq = 0;             // batches evaluated so far (ring slot = seq % kRing)
     unsigned int* d_ticket = nullptr;  // [2]
+    struct HessScratch {               // dynoed_hessian_batch: perturbed batch + staging, grown on demand
+        double *pert = nullptr, *pcrit = nullptr, *pgrad = nullptr, *x = nullptr, *c = nullptr, *g = nullptr, *H = nullptr;
+        int64_t cap = 0;               // designs per chunk the buffers hold
+    } hs;
     int kidx_req = 1;                  // gradient kernel requested by the current call (1 adjoint/Rosenbrock, 2 forward-only)
     int parity = 0;                    // scratch set of the NEXT device-path launch
     int last_parity = 0;               // scratch set that holds the most recent batch's arg-min
@@ -593,6 +597,7 @@ void dynoed_destroy(dynoed_ctx* ctx) {
     cudaFree(ctx->d_first_step); cudaFree(ctx->d_step_t); cudaFree(ctx->d_step_h); cudaFree(ctx->d_indicators);
     for (int q = 0; q < 2; ++q) { cudaFree(ctx->traj[q]); cudaFree(ctx->part_val[q]); cudaFree(ctx->part_idx[q]); if (ctx->call_done[q]) cudaEventDestroy(ctx->call_done[q]); }
     cudaFree(ctx->d_best); cudaFree(ctx->d_ring); cudaFree(ctx->d_ticket);
+    cudaFree(ctx->hs.pert); cudaFree(ctx->hs.pcrit); cudaFree(ctx->hs.pgrad); cudaFree(ctx->hs.x); cudaFree(ctx->hs.c); cudaFree(ctx->hs.g); cudaFree(ctx->hs.H);
     if (ctx->ev_k0) { cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -1133,6 +1138,65 @@ int dynoed_information_gain(dynoed_ctx* ctx, const double* designs, int64_t n, d
     CUI(cudaStreamSynchronize(ctx->stream));
 #undef CUI
     cleanup();
+    return DYNOED_OK;
+}
+
+// Hessians of the objective for n points: central differences of the exact gradient, all
+// n (2 n_var + 1) perturbed designs evaluated as ordinary batches of the gradient kernel.
+int dynoed_hessian_batch(dynoed_ctx* ctx, const double* designs, int64_t n, double rel_step, double* crit,
+                         double* grad, double* hess) {
+    if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    if (!designs || !hess || n <= 0) return fail(ctx, DYNOED_EINVAL, "bad arguments");
+    if (!(rel_step >= 0.0) || rel_step > 0.1) return fail(ctx, DYNOED_EINVAL, "rel_step must lie in [0, 0.1] (0 = default)");
+    CU(cudaSetDevice(ctx->device));
+    const int kd = ptr_kind(designs);
+    if (ptr_kind(hess) != kd || (crit && ptr_kind(crit) != kd) || (grad && ptr_kind(grad) != kd))
+        return fail(ctx, DYNOED_EINVAL, "designs/crit/grad/hess must all be host or all be device pointers");
+    const int nv = ctx->n_var;
+    const int64_t R = 2 * (int64_t)nv + 1;
+    const double rel = rel_step > 0.0 ? rel_step : 6.0554544523933395e-06;   // cbrt(2^-52)
+    const int64_t chunk = std::min<int64_t>(n, std::max<int64_t>(1, 131072 / R));
+    auto& hs = ctx->hs;
+    if (chunk > hs.cap) {
+        CU(cudaDeviceSynchronize());
+        cudaFree(hs.pert); cudaFree(hs.pcrit); cudaFree(hs.pgrad); cudaFree(hs.x); cudaFree(hs.c); cudaFree(hs.g); cudaFree(hs.H);
+        hs = dynoed_ctx::HessScratch();
+        CU(cudaMalloc(&hs.pert, sizeof(double) * chunk * R * nv));
+        CU(cudaMalloc(&hs.pcrit, sizeof(double) * chunk * R));
+        CU(cudaMalloc(&hs.pgrad, sizeof(double) * chunk * R * nv));
+        CU(cudaMalloc(&hs.x, sizeof(double) * chunk * nv));
+        CU(cudaMalloc(&hs.c, sizeof(double) * chunk));
+        CU(cudaMalloc(&hs.g, sizeof(double) * chunk * nv));
+        CU(cudaMalloc(&hs.H, sizeof(double) * chunk * nv * nv));
+        hs.cap = chunk;
+    }
+    cudaStream_t st = ctx->stream;
+    ctx->kidx_req = 1;
+    ctx->prev.valid = false;
+    for (int64_t o = 0; o < n; o += chunk) {
+        const int64_t m = std::min(chunk, n - o);
+        const double* xd = designs + o * nv;
+        double *cd = crit ? crit + o : nullptr, *gd = grad ? grad + o * nv : nullptr, *Hd = hess + o * nv * nv;
+        if (kd == 0) {
+            CU(cudaMemcpyAsync(hs.x, xd, sizeof(double) * m * nv, cudaMemcpyHostToDevice, st));
+            xd = hs.x; cd = crit ? hs.c : nullptr; gd = grad ? hs.g : nullptr; Hd = hs.H;
+        }
+        const int64_t tot_p = m * R * nv, tot_h = m * nv * (int64_t)nv;
+        fd_perturb_kernel<<<(int)std::min<int64_t>((tot_p + 255) / 256, 4096), 256, 0, st>>>(xd, m, nv, rel, hs.pert);
+        CU(cudaGetLastError());
+        int rc = eval_device(ctx, hs.pert, m * R, hs.pcrit, hs.pgrad, nullptr, nullptr);
+        if (rc) return rc;
+        fd_hessian_kernel<<<(int)std::min<int64_t>((tot_h + 255) / 256, 4096), 256, 0, st>>>(hs.pert, hs.pcrit, hs.pgrad, m, nv, cd, gd, Hd);
+        CU(cudaGetLastError());
+        ctx->launches += 2;
+        ctx->prev.valid = false;      // the scratch is reused by the next chunk: no overlap across it
+        if (kd == 0) {
+            if (crit) CU(cudaMemcpyAsync(crit + o, hs.c, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+            if (grad) CU(cudaMemcpyAsync(grad + o * nv, hs.g, sizeof(double) * m * nv, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(hess + o * nv * nv, hs.H, sizeof(double) * m * nv * nv, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CU(cudaStreamSynchronize(st));
     return DYNOED_OK;
 }
 

@@ -1024,6 +1024,58 @@ __global__ void __launch_bounds__(kFcTile) fixed_controls_kernel(const double* _
 }
 
 // ----------------------------------------------------------------------------------------------
+// Hessian of the objective by central differences of the EXACT gradient: the 2 n_var + 1 perturbed
+// designs of one point are just another batch for the evaluation kernel (the reference gets
+// Hessians from nested ForwardDiff duals when Ipopt runs without hessian_approximation =
+// "limited-memory", /root/reference/README.md:63, /root/reference/src/problem.jl:154).
+// Row layout per design: rows 0..nv-1 = x + h_i e_i, rows nv..2nv-1 = x - h_i e_i, row 2nv = x.
+// ----------------------------------------------------------------------------------------------
+__global__ void fd_perturb_kernel(const double* __restrict__ x, long long n, int nv, double rel,
+                                  double* __restrict__ out) {
+    const long long R = 2LL * nv + 1;
+    const long long total = n * R * nv;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(g % nv);
+        const long long r = (g / nv) % R;
+        const long long d = g / (R * nv);
+        double v = x[d * nv + j];
+        const double h = rel * fmax(1.0, fabs(v));
+        if (r == j) v += h;
+        else if (r == j + nv) v -= h;
+        out[g] = v;
+    }
+}
+
+// H_ij = ((g_j(x + h_i e_i) - g_j(x - h_i e_i)) / (2 h_i) + (i <-> j)) / 2 with the steps read back from
+// the perturbed designs (so the divisor is the step actually taken); also copies objective and
+// gradient of the centre row.
+__global__ void fd_hessian_kernel(const double* __restrict__ pert, const double* __restrict__ pcrit,
+                                  const double* __restrict__ pgrad, long long n, int nv,
+                                  double* __restrict__ crit, double* __restrict__ grad,
+                                  double* __restrict__ H) {
+    const long long R = 2LL * nv + 1;
+    const long long total = n * nv * nv;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(g % nv);
+        const int i = (int)((g / nv) % nv);
+        const long long d = g / ((long long)nv * nv);
+        const double* pd = pert + d * R * nv;
+        const double* gd = pgrad + d * R * nv;
+        const double di = pd[(long long)i * nv + i] - pd[(long long)(nv + i) * nv + i];
+        const double dj = pd[(long long)j * nv + j] - pd[(long long)(nv + j) * nv + j];
+        const double a = (gd[(long long)i * nv + j] - gd[(long long)(nv + i) * nv + j]) / di;
+        const double b = (gd[(long long)j * nv + i] - gd[(long long)(nv + j) * nv + i]) / dj;
+        H[g] = 0.5 * (a + b);
+        if (i == 0) {
+            if (grad) grad[d * nv + j] = gd[2LL * nv * nv + j];
+            if (j == 0 && crit) crit[d] = pcrit[d * R + 2 * nv];
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
 // Criteria on caller-supplied matrices (host API `criterion(F, tau)`, fisher.jl:12-15): one
 // matrix per thread, runtime n, Jacobi in local memory.  Not a hot path.
 // ----------------------------------------------------------------------------------------------

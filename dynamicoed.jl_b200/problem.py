@@ -215,6 +215,7 @@ class OptimizationFunction:
     cons: object = None
     cons_j: object = None
     syms: list = field(default_factory=list)
+    hess: object = None
 
 
 @dataclass
@@ -262,6 +263,17 @@ def OptimizationProblem(prob: OEDProblem, AD=None, u0=None, p=None, *, integer_c
             return G
         return g.copy()
 
+    def hessian(H, u, _p=None):
+        """Hessian of the objective: central differences of the exact gradient, 2 n_var + 1 designs
+        in one launch (`dynoed_hessian_batch`); also refreshes the f / grad cache at u."""
+        u = np.ascontiguousarray(np.asarray(u, dtype=np.float64).reshape(1, n_var))
+        c, g, Hm = ctx.hessian(u[0])
+        cache.update(key=u.tobytes(), c=float(c), g=g.copy())
+        if H is not None:
+            H[:] = Hm
+            return H
+        return Hm
+
     cons = cons_j = lcons = ucons = None
     if isinstance(constraints, ConstraintsSystem):
         syms = list(states(prob).data)
@@ -285,7 +297,7 @@ def OptimizationProblem(prob: OEDProblem, AD=None, u0=None, p=None, *, integer_c
         for c, o, l in zip(prob.system.controls, lay.control_offsets, lay.control_lengths):
             integrality[o:o + l] = bool(c.meta.get("integer", False))
     syms = [v.name for v in list(prob.system.x_ic) + list(prob.system.controls) + list(prob.system.w)]
-    opt_f = OptimizationFunction(objective, gradient, cons, cons_j, syms)
+    opt_f = OptimizationFunction(objective, gradient, cons, cons_j, syms, hessian)
     return OptimizationProblemT(opt_f, u0a, p, lb, ub, integrality, lcons, ucons, prob)
 
 
@@ -316,7 +328,10 @@ def solve(opt_prob: OptimizationProblemT, method: str = "SLSQP", **options) -> O
         return f.f(u)
     opts = dict(ftol=1e-12, maxiter=500) if method == "SLSQP" else {}
     opts.update(options)
+    extra = {}
+    if method == "trust-constr" and f.hess is not None:   # exact-Hessian mode (Ipopt's default)
+        extra["hess"] = lambda u: f.hess(None, u)
     r = minimize(fun, opt_prob.u0, jac=lambda u: f.grad(None, u), method=method,
-                 bounds=list(zip(opt_prob.lb, opt_prob.ub)), constraints=cons, options=opts)
+                 bounds=list(zip(opt_prob.lb, opt_prob.ub)), constraints=cons, options=opts, **extra)
     return OptimizationSolution(np.asarray(r.x), float(r.fun), bool(r.success), str(r.message),
                                 int(getattr(r, "nit", 0)), calls[0])

@@ -62,7 +62,7 @@ EXPORTS = ["dynoed_abi_version", "dynoed_model_count", "dynoed_model_name", "dyn
            "dynoed_argmin_async", "dynoed_argmin_record_async", "dynoed_argmin_history_async",
            "dynoed_argmin_gathered",
            "dynoed_set_profiling", "dynoed_kernel_time",
-           "dynoed_trajectory", "dynoed_information_gain", "dynoed_fim_basis",
+           "dynoed_trajectory", "dynoed_information_gain", "dynoed_fim_basis", "dynoed_hessian_batch",
            "dynoed_eval_fixed_controls", "dynoed_criterion_batch", "dynoed_fp64_peak", "dynoed_fp64_microbench",
            "dynoed_kernel_stats_query", "dynoed_host_alloc", "dynoed_host_free",
            "dynoed_last_error"]
@@ -105,6 +105,7 @@ def lib(path: str | None = None):
         L.dynoed_trajectory.argtypes = [vp, dp, i64, dp]
         L.dynoed_information_gain.argtypes = [vp, dp, i64, dp, dp, dp]
         L.dynoed_fim_basis.argtypes = [vp, dp, dp]
+        L.dynoed_hessian_batch.argtypes = [vp, dp, C.c_int64, C.c_double, dp, dp, dp]
         L.dynoed_eval_fixed_controls.argtypes = [vp, dp, dp, i64, dp, dp, dp]
         L.dynoed_criterion_batch.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, i64, dp, dp]
         L.dynoed_fp64_peak.argtypes = [C.c_int, vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -297,6 +298,21 @@ class Context:
         basis = np.empty((self.n_var, self.info.nF))
         _check(self._L.dynoed_fim_basis(self._h, _ptr(design), _ptr(basis)), self._h, self._L)
         return basis
+
+    def hessian_batch(self, designs, hess, crit=None, grad=None, rel_step=0.0, n=None):
+        """Hessians of the objective (central differences of the exact gradient, evaluated as batches
+        of the gradient kernel); numpy arrays or torch CUDA tensors, like `eval_batch`."""
+        n = int(designs.shape[0]) if n is None else int(n)
+        _check(self._L.dynoed_hessian_batch(self._h, _ptr(designs), n, float(rel_step), _ptr(crit),
+                                            _ptr(grad), _ptr(hess)), self._h, self._L)
+
+    def hessian(self, design, rel_step=0.0):
+        """(objective, gradient, Hessian) at one or more host designs."""
+        d = np.ascontiguousarray(np.atleast_2d(design), dtype=np.float64)
+        n = d.shape[0]
+        c, g, H = np.empty(n), np.empty((n, self.n_var)), np.empty((n, self.n_var, self.n_var))
+        self.hessian_batch(d, H, c, g, rel_step)
+        return (c[0], g[0], H[0]) if np.ndim(design) == 1 else (c, g, H)
 
     def eval_fixed_controls(self, basis, designs, crit, grad=None, fim=None, n=None):
         """Objective / gradient / F for measurement designs that share the controls of `basis`

@@ -179,6 +179,18 @@ int dynoed_trajectory(dynoed_ctx* ctx, const double* designs, int64_t n, double*
 int dynoed_information_gain(dynoed_ctx* ctx, const double* designs, int64_t n, double* F, double* P,
                             double* Pi);
 
+/* Hessians of the objective at n points, hess[n][n_var][n_var] (symmetric, row-major), by central
+ * differences of the exact gradient: the 2 n_var + 1 perturbed designs of every point are evaluated
+ * as ordinary batches of the gradient kernel (one launch for up to 131072 / (2 n_var + 1) points),
+ * step h_i = rel_step * max(1, |x_i|) (rel_step = 0: cbrt(eps) = 6.06e-6; error ~ 1e-10 relative to
+ * the gradient's scale).  crit[n] / grad[n][n_var] (either may be NULL) receive objective and
+ * gradient at the points themselves.  Replaces the nested-ForwardDiff Hessian Optimization.jl
+ * builds when Ipopt runs WITHOUT hessian_approximation = "limited-memory"
+ * (/root/reference/README.md:63, /root/reference/src/problem.jl:154).  Blocking; host or device
+ * pointers (all of one kind); overwrites the arg-min record of the previous batch. */
+int dynoed_hessian_batch(dynoed_ctx* ctx, const double* designs, int64_t n, double rel_step, double* crit,
+                         double* grad, double* hess);
+
 /* Fixed-controls shortcut for batches of MEASUREMENT designs (integer / branch-and-bound mode,
  * /root/reference/src/problem.jl:137-146; F is linear in w, /root/reference/src/augment.jl:223-226):
  * dynoed_fim_basis integrates once per weight column with the controls / initial conditions of

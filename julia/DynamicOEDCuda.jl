@@ -13,7 +13,7 @@
 #   using DynamicOED, DynamicOEDCuda, Optimization, OptimizationMOI, Ipopt
 #   prob = OEDProblem(structural_simplify(OEDSystem(sys)), FisherDCriterion())
 #   optp = OptimizationProblem(prob, CudaBackend(model = "lv_fishing", alg = :rk4, substeps = 4))
-#   res  = solve(optp, Ipopt.Optimizer(); hessian_approximation = "limited-memory")
+#   res  = solve(optp, Ipopt.Optimizer())      # exact Hessian from the GPU; "limited-memory" works too
 module DynamicOEDCuda
 
 using DynamicOED
@@ -25,7 +25,7 @@ using ModelingToolkit
 using Optimization
 using SciMLBase
 
-export CudaBackend, DynoedContext, eval_batch!, eval_batch_async!, wait_call, argmin_design, dynoed_library,
+export CudaBackend, DynoedContext, eval_batch!, hessian!, eval_batch_async!, wait_call, argmin_design, dynoed_library,
        pinned_matrix
 
 const LIB = Ref{String}(get(ENV, "DYNOED_CUDA_LIB", "libdynoed_cuda.so"))
@@ -154,6 +154,26 @@ function eval_batch!(ctx::DynoedContext, designs::Matrix{Float64}, crit::Vector{
 end
 
 """
+    hessian!(ctx, H, u; crit = nothing, grad = nothing, rel_step = 0.0) -> H
+
+Hessian of the objective at `u` (`n_var` vector, or an `n_var x n` matrix with `H` of size
+`n_var x n_var x n`): central differences of the exact gradient, the `2 n_var + 1` perturbed designs
+of every point evaluated as one batch of the gradient kernel (`dynoed_hessian_batch`).
+"""
+function hessian!(ctx::DynoedContext, H::Array{Float64}, u::Array{Float64};
+        crit::Union{Nothing, Vector{Float64}} = nothing, grad::Union{Nothing, Array{Float64}} = nothing,
+        rel_step::Float64 = 0.0)
+    n = size(u, 2)
+    @assert size(u, 1) == ctx.n_var && length(H) == ctx.n_var^2 * n
+    rc = ccall((:dynoed_hessian_batch, LIB[]), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Cdouble, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        ctx.handle, u, n, rel_step, crit === nothing ? C_NULL : pointer(crit),
+        grad === nothing ? C_NULL : pointer(grad), H)
+    check(rc, ctx.handle)
+    H
+end
+
+"""
     pinned_matrix(rows, cols) -> Matrix{Float64}
 
 Page-locked host memory from `dynoed_host_alloc`, wrapped as a Julia matrix (freed by a finalizer).
@@ -237,9 +257,20 @@ function Optimization.OptimizationProblem(prob::OEDProblem, backend::CudaBackend
     end
     syms = Symbol.(vcat(get_initial_conditions(prob.system), get_control_parameters(prob.system),
         get_measurement_function(prob.system)))
-    # No AD type is passed: objective and gradient are supplied; Hessians are not, so the solver
-    # must run with hessian_approximation = "limited-memory" (as docs/src/examples/1D.md:89 does).
-    opt_f = OptimizationFunction(objective; grad = gradient!, syms = syms, cons = cons)
+    # Objective, gradient AND Hessian come from the GPU, so `solve(opt_prob, Ipopt.Optimizer())` works
+    # with Ipopt's default exact Hessian as in the reference's tests (test/references/1D.jl:30) as well
+    # as with hessian_approximation = "limited-memory" (docs/src/examples/1D.md:89).  The AD type only
+    # serves what is NOT supplied: Jacobian / Hessians of the pure-Julia constraint function `cons`.
+    hbuf = Matrix{Float64}(undef, ctx.n_var, ctx.n_var)
+    hessian_cb! = (H, u, _) -> begin
+        buf[:, 1] .= u
+        hessian!(ctx, hbuf, buf; crit = c1, grad = g1)     # refreshes the f / grad cache too
+        last .= u
+        H .= hbuf
+        nothing
+    end
+    opt_f = OptimizationFunction(objective, Optimization.AutoForwardDiff(); grad = gradient!,
+        hess = hessian_cb!, syms = syms, cons = cons)
     OptimizationProblem(opt_f, u0, p; lb = lb, ub = ub, int = integrality, lcons = cons_lb, ucons = cons_ub)
 end
 

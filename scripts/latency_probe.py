@@ -23,3 +23,8 @@ for name, ctor, crit, alg in (("readme", models.readme, D.FisherACriterion, D.Ts
         u[0, 0] = 0.3 + 1e-3 * k
         opt.f.f(u[0]); opt.f.grad(None, u[0])
     print(f"{name:10s} optimizer callbacks f + grad: {(time.perf_counter()-t)/200*1e6:7.1f} us per iterate", flush=True)
+    H = np.empty((1, ctx.n_var, ctx.n_var)); c1 = np.empty(1); g1 = np.empty((1, ctx.n_var))
+    for _ in range(10): ctx.hessian_batch(u, H, c1, g1)
+    t = time.perf_counter()
+    for _ in range(200): ctx.hessian_batch(u, H, c1, g1)
+    print(f"{name:10s} Hessian ({2 * ctx.n_var + 1} designs, one launch): {(time.perf_counter()-t)/200*1e6:7.1f} us per call", flush=True)

@@ -797,3 +797,118 @@ def test_pipelined_host_calls_match_blocking_ones(built_library):
     assert np.array_equal(hc.numpy(), ref[K - 1][0]) and np.array_equal(hg.numpy(), ref[K - 1][1])
     with pytest.raises(runtime.DynoedError):
         ctx.wait(10 ** 6)
+
+
+# ---- Hessians (dynoed_hessian_batch): what Ipopt's exact-Hessian mode asks Optimization.jl for ----
+def _fd_hessian_of(gradfun, x, rel_step):
+    """The same central-difference formula, on the CPU, from any gradient function."""
+    nv = x.size
+    h = rel_step * np.maximum(1.0, np.abs(x))
+    P = np.vstack([x + np.diag(h), x - np.diag(h)])
+    G = gradfun(P)
+    den = (P[np.arange(nv), np.arange(nv)] - P[nv + np.arange(nv), np.arange(nv)])[:, None]
+    A = (G[:nv] - G[nv:]) / den
+    return 0.5 * (A + A.T)
+
+
+def _phi_second(crit, M, A, B):
+    """d^2 phi(M)[A, B] for the criteria that are smooth functions of det / inverse."""
+    Mi = np.linalg.inv(M)
+    tA, tB, tAB = np.trace(Mi @ A), np.trace(Mi @ B), np.trace(Mi @ A @ Mi @ B)
+    d = np.linalg.det(M)
+    if crit == 0:
+        return 0.0                                    # -tr M
+    if crit == 1:
+        return -d * (tA * tB - tAB)                   # -det M
+    if crit == 3:
+        return 2.0 * np.trace(Mi @ A @ Mi @ B @ Mi)   # tr M^-1
+    if crit == 4:
+        return (tA * tB + tAB) / d                    # 1 / det M
+    raise ValueError(crit)
+
+
+@pytest.mark.parametrize("crit", [0, 1, 3, 4])
+def test_hessian_weight_block_vs_closed_form(crit, oracles, built_library):
+    # F is linear in the weights (augment.jl:223-226): the (w, tau) block of the Hessian is
+    # d^2 phi(F + tau I)[B_a, B_b] with B_k = dF/dw_k from the ORACLE (tau direction: I)
+    ctx = make_problem("lv_fishing", CRITS[crit]).context()
+    orc = oracles("lv_fishing", crit, "rk4", 4)
+    x = random_designs("lv_fishing", 71, 1, 77)[0]
+    x[-1] = 0.3
+    c, g, H = ctx.hessian(x)
+    oc, og, oF = orc.evaluate(x[None], grad=True)
+    assert rel(np.array([c]), oc) < RTOL and rel_rows(g[None], og) < RTOL
+    assert np.array_equal(H, H.T)
+    wcols = np.arange(10, 70)
+    units = np.tile(x, (60, 1)); units[:, 10:70] = np.eye(60)
+    _, _, Bp = orc.evaluate(units, grad=False)
+    sym = lambda p: np.array([[p[0], p[1]], [p[1], p[2]]])
+    dirs = [sym(b) for b in Bp] + [np.eye(2)]
+    M = sym(oF[0]) + x[-1] * np.eye(2)
+    cols = list(wcols) + [70]
+    Hw = np.array([[_phi_second(crit, M, A, B) for B in dirs] for A in dirs])
+    scale = max(np.abs(Hw).max(), np.abs(og).max())
+    assert np.abs(H[np.ix_(cols, cols)] - Hw).max() < 2e-8 * scale, np.abs(H[np.ix_(cols, cols)] - Hw).max() / scale
+
+
+@pytest.mark.parametrize("name,crit", [("lv_fishing", 1), ("lv_fishing", 5), ("lv_ic", 3), ("readme", 3)])
+def test_hessian_full_vs_oracle_differences(name, crit, oracles, built_library):
+    ctx = make_problem(name, CRITS[crit]).context()
+    orc = oracles(name, crit, "rk4", 4)
+    xs = random_designs(name, ctx.n_var, 3, 91 + crit)
+    rs = 6.0554544523933395e-06
+    c, g, H = ctx.hessian(xs)                                   # three points: one batch of 3 (2 nv + 1) rows
+    oc, og, _ = orc.evaluate(xs, grad=True)
+    assert rel(c, oc) < RTOL and rel_rows(g, og) < RTOL
+    for k in range(3):
+        Ho = _fd_hessian_of(lambda P: orc.evaluate(P, grad=True)[1], xs[k], rs)
+        scale = max(np.abs(Ho).max(), np.abs(og[k]).max())
+        assert np.abs(H[k] - Ho).max() < 1e-7 * scale, (name, crit, np.abs(H[k] - Ho).max() / scale)
+        assert np.array_equal(H[k], H[k].T)
+    # truncation error: a 10x larger step moves the result by O(h^2)
+    _, _, H10 = ctx.hessian(xs[0], rel_step=10 * rs)
+    assert np.abs(H10 - H[0]).max() < 1e-5 * max(np.abs(H[0]).max(), 1.0)
+
+
+def test_hessian_device_pointers_chunks_and_errors(built_library):
+    import torch
+    ctx = make_problem("lv_fishing", D.FisherDCriterion).context()
+    nv = ctx.n_var
+    n = 1000                                                     # > 131072 / 143 = 916: two chunks
+    xs = random_designs("lv_fishing", nv, n, 5)
+    c, g, H = ctx.hessian(xs)
+    d = torch.from_numpy(xs).cuda()
+    Hd = torch.empty((n, nv, nv), dtype=torch.float64, device="cuda")
+    cd = torch.empty(n, dtype=torch.float64, device="cuda")
+    ctx.hessian_batch(d, Hd, cd, None)
+    assert np.array_equal(Hd.cpu().numpy(), H) and np.array_equal(cd.cpu().numpy(), c)
+    c1, g1, H1 = ctx.hessian(xs[917])
+    assert np.array_equal(H1, H[917]) and np.array_equal(g1, g[917]) and c1 == c[917]
+    c0, g0, _ = ctx.evaluate(xs)
+    assert np.array_equal(c0, c) and np.array_equal(g0, g)
+    with pytest.raises(runtime.DynoedError):
+        ctx.hessian_batch(xs, Hd)                                # host designs, device Hessian
+    with pytest.raises(runtime.DynoedError):
+        ctx.hessian(xs[0], rel_step=0.5)
+
+
+def test_exact_hessian_solve_reaches_the_reference_optimum(built_library):
+    # /root/reference/test/references/LotkaVolterra.jl:8-155 solved the way the reference's tests do
+    # — `solve(opt_prob, Ipopt.Optimizer())`, i.e. with exact Hessians — here scipy trust-constr
+    # with the GPU Hessian in Ipopt's place
+    prob = D.OEDProblem(D.structural_simplify(D.OEDSystem(models.lotka_volterra_fishing())),
+                        D.FisherACriterion())
+    v = D.states(prob)
+    dts = {k: np.array([b - a for a, b in g]) for k, g in D.get_timegrids(prob).items()}
+    cons = D.ConstraintsSystem([
+        D.geq(0.2 - 0.5 * sum(dts["w₁"] * v.measurements["w₁"]), 0),
+        D.geq(0.2 - 0.5 * sum(dts["w₁"] * v.measurements["w₂"]), 0),
+        D.geq(1.0, sum(dts["u"] * v.controls["u"]))])
+    op = D.OptimizationProblem(prob, None, constraints=cons, integer_constraints=False)
+    r = D.solve(op, method="trust-constr", gtol=1e-9, xtol=1e-12, maxiter=500)
+    assert abs(r.objective - (-4.85)) < 1e-2, r.objective
+    assert np.allclose(r.u[:10], [0.62] + [0] * 9, atol=1e-2), r.u[:10]
+    w_ref = np.array([0.0] * 26 + [1.0] * 4)
+    assert np.allclose(r.u[10:40], w_ref, atol=1e-2) and np.allclose(r.u[40:70], w_ref, atol=1e-2)
+    H = op.f.hess(None, r.u)
+    assert H.shape == (71, 71) and np.array_equal(H, H.T) and np.abs(H[:10, :10]).max() > 0
