@@ -31,6 +31,9 @@ static thread_local std::string g_last_error;
 constexpr int kFwdOnly = 16;
 // method | kCtrlGrad: Rosenbrock gradient kernel that also differentiates with respect to control values
 constexpr int kCtrlGrad = 32;
+// method | kDirPar: direction-parallel gradient kernel for small batches (dir_eval_kernel)
+constexpr int kDirPar = 64;
+constexpr int kDirBlock = 32;
 
 struct ModelEntry {
     const char* name;
@@ -96,9 +99,24 @@ static cudaError_t attrs_ros(int block, size_t smem, cudaFuncAttributes* fa, int
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, block, smem);
 }
 
+template <class M, class Stepper>
+static cudaError_t launch_dir(const EvalParams& P, int grid, cudaStream_t st) {
+    dir_eval_kernel<M, Stepper><<<grid, kDirBlock, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
 template <class M>
 static cudaError_t launch_model(int method, bool grad, bool uc, bool pdl, const EvalParams& P, int grid, int block,
                                 size_t smem, cudaStream_t st) {
+    if (method & kDirPar) {
+        switch (method & 15) {
+            case DYNOED_RK4: return launch_dir<M, ExplicitStepper<TabRK4>>(P, grid, st);
+            case DYNOED_TSIT5: return launch_dir<M, ExplicitStepper<TabTsit5>>(P, grid, st);
+            case DYNOED_ROS2: return launch_dir<M, RosenbrockStepper<TabROS2>>(P, grid, st);
+            case DYNOED_ROS3P: return launch_dir<M, RosenbrockStepper<TabROS3P>>(P, grid, st);
+            default: return launch_dir<M, RosenbrockStepper<TabRODAS3>>(P, grid, st);
+        }
+    }
     const bool cg = (method & kCtrlGrad) != 0;
     method &= ~kCtrlGrad;
     if (method == DYNOED_RK4) return launch_tab<M, TabRK4>(grad, uc, pdl, P, grid, block, smem, st);
@@ -294,6 +312,10 @@ struct dynoed_ctx {
         double *pert = nullptr, *pcrit = nullptr, *pgrad = nullptr, *x = nullptr, *c = nullptr, *g = nullptr, *H = nullptr;
         int64_t cap = 0;               // designs per chunk the buffers hold
     } hs;
+    bool dir_ok = false;               // direction-parallel kernel usable for small gradient batches
+    int dir_nl = 1;                    // its lanes per design: 1 + unknown ICs + control values
+    int64_t dir_max_lanes = 0;
+    int64_t call_n = 0;                // designs of the call being served
     int kidx_req = 1;                  // gradient kernel requested by the current call (1 adjoint/Rosenbrock, 2 forward-only)
     int parity = 0;                    // scratch set of the NEXT device-path launch
     int last_parity = 0;               // scratch set that holds the most recent batch's arg-min
@@ -319,6 +341,7 @@ struct dynoed_ctx {
     Slot slots[kSlots];
     int64_t launches = 0;
     int64_t pdl_launches = 0;
+    int64_t dir_launches = 0;
     size_t scratch_bytes = 0;
     // optional per-launch timing of the evaluation kernel (device-pointer path)
     bool profiling = false;
@@ -403,11 +426,28 @@ static size_t smem_bytes(const dynoed_ctx* ctx) {
     return std::max(ctx->smem_floor, 128 + (size_t)ctx->tile * ctx->n_var * sizeof(double));
 }
 
+// Small gradient batches (the optimiser callback, finite-difference Hessians) are bound by the
+// sequential depth of one design, not by arithmetic: they run on the direction-parallel kernel
+// (1 + n_dir lanes per design, forward sweep only) while its lanes stay below three warps per SM.
+static bool dir_eligible(const dynoed_ctx* ctx, int64_t n, int kidx) {
+    // decided on the size of the whole CALL (a chunk of a large host batch must not switch kernels)
+    return kidx == 1 && ctx->dir_ok && n > 0 && std::max(n, ctx->call_n) * ctx->dir_nl <= ctx->dir_max_lanes;
+}
+
 static int grid_for(const dynoed_ctx* ctx, int64_t n, int kidx) {
+    if (dir_eligible(ctx, n, kidx)) return (int)((n * ctx->dir_nl + kDirBlock - 1) / kDirBlock);
     const int64_t ntiles = (n + ctx->tile - 1) / ctx->tile;
     const int64_t resident = (int64_t)ctx->sm_count * std::max(ctx->bps[kidx], 1);
     return (int)std::max<int64_t>(1, std::min(ntiles, resident));
 }
+
+// scratch of one gradient launch of n designs
+static size_t traj_need(const dynoed_ctx* ctx, int64_t n, int kidx) {
+    if (dir_eligible(ctx, n, kidx))
+        return sizeof(double) * (size_t)n * ctx->n_intervals * ctx->model->info.n_obs * ctx->model->info.nF;
+    return traj_bytes_for(ctx, grid_for(ctx, n, kidx), kidx);
+}
+
 
 int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     dynoed_ctx* ctx = nullptr;
@@ -539,6 +579,16 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     CUC(cudaMalloc(&ctx->d_ticket, 2 * sizeof(unsigned int)));
     CUC(cudaMemset(ctx->d_ticket, 0, 2 * sizeof(unsigned int)));
     ctx->pdl_enabled = !getenv("DYNOED_NO_PDL");
+    {   // direction-parallel small-batch kernel: its quadrature scratch must fit what a launch owns anyway
+        int nvals = 0;
+        for (int k = 0; k < mi.n_ctrl; ++k) nvals += len[k];
+        ctx->dir_nl = 1 + mi.n_ic + nvals;
+        // measured on B200 (scripts/small_batch_probe.py): ahead of the adjoint kernel up to ~3 warps per SM
+        ctx->dir_max_lanes = (int64_t)prop.multiProcessorCount * 3 * kDirBlock;
+        if (const char* dl = getenv("DYNOED_DIRPAR_MAX_LANES")) ctx->dir_max_lanes = std::max(0, atoi(dl));
+        ctx->dir_ok = !getenv("DYNOED_NO_DIRPAR") && ctx->dir_nl > 1 &&
+                      (rosenbrock || (size_t)N * mi.n_obs * mi.nF <= (size_t)ctx->n_steps * mi.nz);
+    }
     ctx->zero_copy = !getenv("DYNOED_NO_ZEROCOPY");
     ctx->host_staging = !getenv("DYNOED_NO_STAGING");
     if (const char* hc = getenv("DYNOED_HOST_CHUNKS")) ctx->host_chunks = std::max(0, atoi(hc));
@@ -659,7 +709,9 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
     dynoed_ctx::Prev cur;
     cur.valid = xgrid == nullptr;
     cur.kidx = grad ? ctx->kidx_req : 0;
-    cur.full = grid == ctx->sm_count * std::max(ctx->bps[cur.kidx], 1);
+    const bool dirpar = grad && !xgrid && dir_eligible(ctx, n, cur.kidx);
+    if (dirpar) P.use_tma = 0;
+    cur.full = !dirpar && grid == ctx->sm_count * std::max(ctx->bps[cur.kidx], 1);
     cur.stream = st;
     cur.in0 = (const char*)designs; cur.in1 = cur.in0 + sizeof(double) * n * ctx->n_var;
     cur.out0[0] = (const char*)crit; cur.out1[0] = cur.out0[0] + sizeof(double) * n;
@@ -684,13 +736,15 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
         }
         CU(cudaEventRecord(ctx->ev_k0, st));
     }
-    CU(ctx->model->launch(method_code(ctx, cur.kidx), grad != nullptr, ctx->ucoef, pdl, P, grid, ctx->tile, smem_bytes(ctx), st));
+    CU(ctx->model->launch(method_code(ctx, cur.kidx) | (dirpar ? kDirPar : 0), grad != nullptr, ctx->ucoef, pdl, P, grid,
+                          ctx->tile, smem_bytes(ctx), st));
     if (ctx->profiling) { CU(cudaEventRecord(ctx->ev_k1, st)); ctx->ev_pending = true; }
     cur.serial = stream_new_serial(st);
     ctx->prev = cur;
     ctx->stream_dirty = true;
     ctx->launches++;
     ctx->pdl_launches += pdl ? 1 : 0;
+    ctx->dir_launches += dirpar ? 1 : 0;
     return DYNOED_OK;
 }
 
@@ -698,10 +752,11 @@ static int eval_device(dynoed_ctx* ctx, const double* designs, int64_t n, double
                        double* xgrid) {
     const bool g = grad != nullptr;
     const int kidx = g ? ctx->kidx_req : 0;
+    ctx->call_n = n;
     const int grid = grid_for(ctx, n, kidx);
     const int par = ctx->parity;
     if (g) {
-        const size_t need = traj_bytes_for(ctx, grid, kidx);
+        const size_t need = traj_need(ctx, n, kidx);
         if (need > ctx->traj_bytes[par]) {
             if (ctx->traj[par]) { CU(cudaDeviceSynchronize()); cudaFree(ctx->traj[par]); ctx->traj[par] = nullptr; }
             const size_t full = traj_bytes_for(ctx, ctx->sm_count * std::max(ctx->bps[kidx], 1), kidx);
@@ -738,8 +793,7 @@ static int ensure_slot(dynoed_ctx* ctx, Slot& s, int64_t cap, int kidx, bool fim
         s.cap = cap;
     }
     if (grad) {
-        const int grid = grid_for(ctx, cap, kidx);
-        const size_t need = traj_bytes_for(ctx, grid, kidx);
+        const size_t need = traj_need(ctx, cap, kidx);
         if (need > s.traj_bytes) {
             CU(cudaStreamSynchronize(s.stream));
             cudaFree(s.traj); s.traj = nullptr;
@@ -782,6 +836,7 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
                      bool pipelined = false) {
     const int nF = ctx->model->info.nF;
     const bool g = grad != nullptr;
+    ctx->call_n = n;
     // Chunk schedule: host_chunks equal chunks (default 8).  Measured on B200 / PCIe Gen5: 4..16 equal
     // chunks and a ramped schedule (small chunks at both ends: 1,1,2,4,8,8,4,2,1,1 thirty-seconds,
     // DYNOED_HOST_CHUNKS=0) all land within 5 % of each other at 71-75 % of the rate of two
@@ -887,10 +942,13 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         P.ticket = ctx->d_ticket + par; P.best_val = reinterpret_cast<double*>(ctx->d_best + 2 * par); P.best_idx = ctx->d_best + 2 * par + 1;
         P.ring_rec = ctx->d_ring + 2 * (ctx->batch_seq % kRing);
         part_base += grid;
-        P.use_tma = (((size_t)ctx->tile * ctx->n_var * 8) % 16 == 0) ? 1 : 0;
+        const bool dirpar = g && dir_eligible(ctx, cnt, kidx);
+        P.use_tma = (!dirpar && ((size_t)ctx->tile * ctx->n_var * 8) % 16 == 0) ? 1 : 0;
         P.index_base = off;
-        CU(ctx->model->launch(method_code(ctx, kidx), g, ctx->ucoef, false, P, grid, ctx->tile, smem_bytes(ctx), s.stream));
+        CU(ctx->model->launch(method_code(ctx, kidx) | (dirpar ? kDirPar : 0), g, ctx->ucoef, false, P, grid, ctx->tile,
+                              smem_bytes(ctx), s.stream));
         ctx->launches++;
+        ctx->dir_launches += dirpar ? 1 : 0;
         double* o_crit = staged ? s.h_crit : crit + off;
         double* o_grad = staged ? s.h_grad : (g ? grad + off * ctx->n_var : nullptr);
         double* o_fim = staged ? s.h_fim : (fim ? fim + off * nF : nullptr);
@@ -1401,6 +1459,9 @@ int dynoed_kernel_stats_query(dynoed_ctx* ctx, int with_grad, dynoed_kernel_stat
     o->sm_count = ctx->sm_count;
     o->launches = ctx->launches;
     o->overlapped_launches = ctx->pdl_launches;
+    o->small_batch_launches = ctx->dir_launches;
+    o->small_batch_max = ctx->dir_ok ? (int32_t)(ctx->dir_max_lanes / ctx->dir_nl) : 0;
+    o->reserved_ = 0;
     o->scratch_bytes = (int64_t)ctx->scratch_bytes;
     o->n_steps = ctx->n_steps;
     o->stages = ctx->stages;

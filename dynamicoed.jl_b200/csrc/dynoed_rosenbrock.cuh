@@ -539,4 +539,142 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams 
     argmin_tail(P, best_val, best_idx);
 }
 
+// ----------------------------------------------------------------------------------------------
+// Direction-parallel gradient kernel for SMALL batches — the optimiser callback (one design per
+// call, /root/reference/src/problem.jl:115-120 and its ForwardDiff gradient :154) and the
+// 2 n_var + 1 designs of a finite-difference Hessian.  A batch that cannot fill the GPU is bound by
+// the sequential depth of one design (forward sweep + adjoint sweep), not by arithmetic, so the
+// work of ONE design is spread over 1 + n_dir lanes: lane 0 integrates the plain system and keeps
+// the per-interval quadratures (objective, F, d/dw, d/dtau); lane 1 + k carries a forward-mode dual
+// part for direction k (an unknown initial condition or one control value) through the same sweep
+// and writes that single gradient entry.  No backward sweep, no checkpoints; every lane of a warp
+// runs the same instruction stream (the base lane is a dual lane with a zero seed).  Designs are
+// read and gradients written straight from/to global memory (a few KB per call).
+// P.traj is used as [n][N][NOBS*NF] quadrature scratch of the base lanes.
+// ----------------------------------------------------------------------------------------------
+template <class M, class Stepper>
+__global__ void __launch_bounds__(32, 1) dir_eval_kernel(const EvalParams P) {
+    constexpr int NX = M::NX, NP = M::NP, NZ = M::NZ, NF = M::NF, NOBS = M::NOBS, NCTRL = M::NCTRL;
+    constexpr int NCU = NCTRL > 0 ? NCTRL : 1, NQ = NOBS * NF;
+    using T = Dual<1>;
+    const int n_var = P.n_var, N = P.n_intervals;
+    const int nl = 1 + M::NIC + P.n_ctrl_values;          // lanes per design
+    const long long lane = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long g = lane / nl;
+    const int dir = (int)(lane - g * nl) - 1;             // -1: base lane
+    const double* th = P.theta;
+    double best_val = __longlong_as_double(0x7ff0000000000000LL);
+    long long best_idx = -1;
+
+    if (g < P.n) {
+        const double* row = P.designs + g * n_var;
+        double* grow = P.grad + g * n_var;
+        int dk = -1, didx = -1;                           // direction -> (control k, entry idx)
+        if (dir >= M::NIC) {
+            int rest = dir - M::NIC;
+#pragma unroll
+            for (int k = 0; k < NCTRL; ++k) {
+                if (dk < 0) {
+                    if (rest < P.ctrl_len[k]) { dk = k; didx = rest; }
+                    else rest -= P.ctrl_len[k];
+                }
+            }
+        }
+        T z[NZ], F[NF];
+#pragma unroll
+        for (int a = 0; a < NX; ++a) z[a] = T(P.x0[a]);
+#pragma unroll
+        for (int a = 0; a < NX * NP; ++a) z[NX + a] = T(P.G0[a]);
+        if constexpr (M::NIC > 0) {
+#pragma unroll
+            for (int a = 0; a < M::NIC; ++a) {
+                T v(__ldg(row + P.ic_off + a));
+                v.d[0] = (a == dir) ? 1.0 : 0.0;
+                z[M::ic_state(a)] = v;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < NF; ++a) F[a] = T(0.0);
+        double* pq = P.traj + (size_t)g * N * NQ;
+        for (int j = 0; j < N; ++j) {
+            T u[NCU], c[M::NCONST];
+            double w[NOBS];
+#pragma unroll
+            for (int k = 0; k < NCTRL; ++k) {
+                const int idx = __ldg(P.indicators + k * N + j);
+                u[k] = T(__ldg(row + P.ctrl_off[k] + idx));
+                u[k].d[0] = (k == dk && idx == didx) ? 1.0 : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < NOBS; ++i) w[i] = __ldg(row + P.w_off[i] + __ldg(P.indicators + (NCTRL + i) * N + j));
+            M::template consts_t<T>(u, th, c);
+            T Pq[NQ];
+#pragma unroll
+            for (int a = 0; a < NQ; ++a) Pq[a] = T(0.0);
+            const int s0 = __ldg(P.first_step + j), s1 = __ldg(P.first_step + j + 1);
+            for (int s = s0; s < s1; ++s)
+                Stepper::template step<M, T>(__ldg(P.step_t + s), __ldg(P.step_h + s), z, Pq, u, th, c);
+#pragma unroll
+            for (int i = 0; i < NOBS; ++i)
+#pragma unroll
+                for (int k = 0; k < NF; ++k) F[k] = F[k] + w[i] * Pq[i * NF + k];
+            if (dir < 0) {
+#pragma unroll
+                for (int a = 0; a < NQ; ++a) pq[(size_t)j * NQ + a] = Pq[a].v;
+            }
+        }
+        // every lane evaluates the criterion on its own (identical) F: no exchange between lanes
+        const double tau = __ldg(row + P.tau_off);
+        double Fv[NF], L[NF], Ls[NF], value;
+#pragma unroll
+        for (int a = 0; a < NF; ++a) Fv[a] = F[a].v;
+        criterion_eval<NP>(Fv, tau, P.criterion, value, L);
+#pragma unroll
+        for (int jj = 0; jj < NP; ++jj)
+#pragma unroll
+            for (int ii = 0; ii <= jj; ++ii) Ls[tri(ii, jj)] = (ii == jj ? 1.0 : 2.0) * L[tri(ii, jj)];
+        if (dir >= 0) {
+            double sd = 0.0;
+#pragma unroll
+            for (int k = 0; k < NF; ++k) sd = fma(Ls[k], F[k].d[0], sd);
+            if (dir < M::NIC) grow[P.ic_off + dir] = sd;
+            else grow[P.ctrl_off[dk] + didx] = sd;
+        } else {
+            const double obj = value + tau;
+            P.crit[g] = obj;
+            if (P.fim) {
+#pragma unroll
+                for (int a = 0; a < NF; ++a) P.fim[g * NF + a] = Fv[a];
+            }
+            if (obj < best_val) { best_val = obj; best_idx = P.index_base + g; }   // NaN never wins
+            double wb[NOBS];
+            int wk[NOBS];
+#pragma unroll
+            for (int i = 0; i < NOBS; ++i) { wb[i] = 0.0; wk[i] = -1; }
+            for (int j = 0; j < N; ++j) {
+#pragma unroll
+                for (int i = 0; i < NOBS; ++i) {
+                    const int idx = __ldg(P.indicators + (NCTRL + i) * N + j);
+                    if (idx != wk[i]) {
+                        if (wk[i] >= 0) grow[P.w_off[i] + wk[i]] = wb[i];
+                        wb[i] = 0.0; wk[i] = idx;
+                    }
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NF; ++k) sacc = fma(Ls[k], pq[(size_t)j * NQ + i * NF + k], sacc);
+                    wb[i] += sacc;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NOBS; ++i)
+                if (wk[i] >= 0) grow[P.w_off[i] + wk[i]] = wb[i];
+            double trL = 1.0;
+#pragma unroll
+            for (int i = 0; i < NP; ++i) trL += L[tri(i, i)];
+            grow[P.tau_off] = trL;
+        }
+    }
+    argmin_tail(P, best_val, best_idx);
+}
+
 }  // namespace dynoed
