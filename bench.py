@@ -317,6 +317,24 @@ def main():
             sub[key] = {"designs_per_s_per_gpu": n / msa * 1e3, "ms_per_step": msa,
                         "flops_per_design": fla, "tflops": fla * n / msa / 1e9}
             ctxa.close()
+    # BASELINE config 2: ONE design, objective + gradient (+ Hessian) through the blocking host call —
+    # the optimiser callback (wall clock per call; numpy arrays, i.e. pageable memory)
+    if rank == 0:
+        torch.cuda.synchronize()
+        u1 = np.random.default_rng(2).random((1, n_var))
+        c1, g1, H1 = np.empty(1), np.empty((1, n_var)), np.empty((1, n_var, n_var))
+        lat = {}
+        for key, call in (("objective_gradient_us", lambda: ctx.eval_batch(u1, c1, g1, None)),
+                          ("objective_only_us", lambda: ctx.eval_batch(u1, c1, None, None)),
+                          ("hessian_us", lambda: ctx.hessian_batch(u1, H1, c1, g1))):
+            for _ in range(10):
+                call()
+            t0 = time.perf_counter()
+            for _ in range(100):
+                call()
+            lat[key] = (time.perf_counter() - t0) / 100 * 1e6
+        lat["hessian_designs_per_call"] = 2 * n_var + 1
+        sub["single_design_host_call"] = lat
     if world > 1:
         tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)

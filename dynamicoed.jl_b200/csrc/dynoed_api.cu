@@ -34,6 +34,8 @@ constexpr int kCtrlGrad = 32;
 // method | kDirPar: direction-parallel gradient kernel for small batches (dir_eval_kernel)
 constexpr int kDirPar = 64;
 constexpr int kDirBlock = 32;
+// host calls of at most this many designs let the kernel read / write page-locked host memory directly
+constexpr int64_t kSmallZeroCopy = 16;
 
 struct ModelEntry {
     const char* name;
@@ -100,8 +102,15 @@ static cudaError_t attrs_ros(int block, size_t smem, cudaFuncAttributes* fa, int
 }
 
 template <class M, class Stepper>
-static cudaError_t launch_dir(const EvalParams& P, int grid, cudaStream_t st) {
-    dir_eval_kernel<M, Stepper><<<grid, kDirBlock, 0, st>>>(P);
+static cudaError_t launch_dir(const EvalParams& P0, int grid, cudaStream_t st) {
+    // the design rows of one CTA's lanes are staged in shared memory when they fit the default 48 KB
+    EvalParams P = P0;
+    const int nl = 1 + M::NIC + P.n_ctrl_values;
+    const size_t rows = (size_t)(kDirBlock + nl - 1) / nl + 1;
+    size_t smem = rows * P.n_var * sizeof(double);
+    P.tile = smem <= 48 * 1024 ? (int)rows : 0;
+    if (P.tile == 0) smem = 0;
+    dir_eval_kernel<M, Stepper><<<grid, kDirBlock, smem, st>>>(P);
     return cudaGetLastError();
 }
 
@@ -921,6 +930,25 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         CU(cudaEventRecord(ev, ctx->stream));
         for (int k = 0; k < kSlots && k < nchunks; ++k) CU(cudaStreamWaitEvent(ctx->slots[k].stream, ev, 0));
     }
+    // A call of a handful of designs (the optimiser callback) is all latency: skip the three or four
+    // small DMA transfers — the direction-parallel kernel stages the rows from page-locked host
+    // memory itself (one coalesced read) and stores its results there (posted writes).
+    bool small_zc = false;
+    double *zc_in = nullptr, *zc_crit = nullptr, *zc_grad = nullptr, *zc_fim = nullptr;
+    if (g && nchunks == 1 && n <= kSmallZeroCopy && ctx->zero_copy && !pipelined && dir_eligible(ctx, n, kidx) &&
+        ((size_t)(kDirBlock + ctx->dir_nl - 1) / ctx->dir_nl + 1) * ctx->n_var * sizeof(double) <= 48 * 1024) {
+        Slot& s0 = ctx->slots[0];
+        auto dev = [](const void* p) -> double* {
+            cudaPointerAttributes a;
+            if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            return a.type == cudaMemoryTypeHost ? static_cast<double*>(a.devicePointer) : nullptr;
+        };
+        zc_in = dev(staged ? s0.h_designs : designs);
+        zc_crit = dev(staged ? s0.h_crit : crit);
+        zc_grad = dev(staged ? s0.h_grad : grad);
+        zc_fim = fim ? dev(staged ? s0.h_fim : fim) : nullptr;
+        small_zc = zc_in && zc_crit && zc_grad && (!fim || zc_fim);
+    }
     int part_base = 0;
     for (int64_t c = 0; c < nchunks; ++c) {
         Slot& s = ctx->slots[c % kSlots];
@@ -928,14 +956,19 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         const double* h_src = designs + off * ctx->n_var;
         if (staged) {
             if (c >= kSlots) { rc = drain(c - kSlots); if (rc) return rc; }   // frees this slot's staging
-            parallel_memcpy(s.h_designs, h_src, sizeof(double) * cnt * ctx->n_var);
+            if (small_zc) memcpy(s.h_designs, h_src, sizeof(double) * cnt * ctx->n_var);
+            else parallel_memcpy(s.h_designs, h_src, sizeof(double) * cnt * ctx->n_var);
             h_src = s.h_designs;
         }
-        CU(cudaMemcpyAsync(s.d_designs, h_src, sizeof(double) * cnt * ctx->n_var, cudaMemcpyHostToDevice, s.stream));
+        if (!small_zc)
+            CU(cudaMemcpyAsync(s.d_designs, h_src, sizeof(double) * cnt * ctx->n_var, cudaMemcpyHostToDevice, s.stream));
         EvalParams P = ctx->base;
         const int grid = grid_for(ctx, cnt, kidx);
         P.designs = s.d_designs; P.crit = crit_map ? crit_map + off : s.d_crit; P.grad = g ? s.d_grad : nullptr;
         P.fim = !fim ? nullptr : fim_map ? fim_map + off * nF : s.d_fim;
+        if (small_zc) {   // the kernel reads the rows from, and stores every result into, page-locked host memory
+            P.designs = zc_in; P.crit = zc_crit; P.grad = zc_grad; P.fim = fim ? zc_fim : nullptr;
+        }
         P.xgrid = nullptr; P.traj = s.traj; P.n = cnt;
         P.part_val = ctx->part_val[par]; P.part_idx = ctx->part_idx[par];
         P.part_base = part_base; P.n_parts = total_parts; P.ticket_target = (unsigned int)total_parts;
@@ -952,9 +985,9 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         double* o_crit = staged ? s.h_crit : crit + off;
         double* o_grad = staged ? s.h_grad : (g ? grad + off * ctx->n_var : nullptr);
         double* o_fim = staged ? s.h_fim : (fim ? fim + off * nF : nullptr);
-        if (!crit_map) CU(cudaMemcpyAsync(o_crit, s.d_crit, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s.stream));
-        if (g) CU(cudaMemcpyAsync(o_grad, s.d_grad, sizeof(double) * cnt * ctx->n_var, cudaMemcpyDeviceToHost, s.stream));
-        if (fim && !fim_map) CU(cudaMemcpyAsync(o_fim, s.d_fim, sizeof(double) * cnt * nF, cudaMemcpyDeviceToHost, s.stream));
+        if (!crit_map && !small_zc) CU(cudaMemcpyAsync(o_crit, s.d_crit, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s.stream));
+        if (g && !small_zc) CU(cudaMemcpyAsync(o_grad, s.d_grad, sizeof(double) * cnt * ctx->n_var, cudaMemcpyDeviceToHost, s.stream));
+        if (fim && !fim_map && !small_zc) CU(cudaMemcpyAsync(o_fim, s.d_fim, sizeof(double) * cnt * nF, cudaMemcpyDeviceToHost, s.stream));
         if (staged) CU(cudaEventRecord(s.done, s.stream));
     }
     if (staged)

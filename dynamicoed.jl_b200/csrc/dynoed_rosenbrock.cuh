@@ -566,8 +566,21 @@ __global__ void __launch_bounds__(32, 1) dir_eval_kernel(const EvalParams P) {
     double best_val = __longlong_as_double(0x7ff0000000000000LL);
     long long best_idx = -1;
 
+    // P.tile > 0: the design rows of this CTA's lanes are staged in shared memory first (one
+    // coalesced read — the rows may live in mapped host memory, see eval_host's small-call path)
+    extern __shared__ __align__(16) double dir_rows[];
+    const long long d_first = (blockIdx.x * (long long)blockDim.x) / nl;
+    if (P.tile > 0) {
+        long long d_last = (blockIdx.x * (long long)blockDim.x + blockDim.x - 1) / nl;
+        if (d_last > P.n - 1) d_last = P.n - 1;
+        const long long cnt = (d_last - d_first + 1) * n_var;
+        const double* src = P.designs + d_first * n_var;
+        for (long long i = threadIdx.x; i < cnt; i += blockDim.x) dir_rows[i] = src[i];
+        __syncthreads();
+    }
+
     if (g < P.n) {
-        const double* row = P.designs + g * n_var;
+        const double* row = P.tile > 0 ? dir_rows + (g - d_first) * n_var : P.designs + g * n_var;
         double* grow = P.grad + g * n_var;
         int dk = -1, didx = -1;                           // direction -> (control k, entry idx)
         if (dir >= M::NIC) {
@@ -588,7 +601,7 @@ __global__ void __launch_bounds__(32, 1) dir_eval_kernel(const EvalParams P) {
         if constexpr (M::NIC > 0) {
 #pragma unroll
             for (int a = 0; a < M::NIC; ++a) {
-                T v(__ldg(row + P.ic_off + a));
+                T v(row[P.ic_off + a]);
                 v.d[0] = (a == dir) ? 1.0 : 0.0;
                 z[M::ic_state(a)] = v;
             }
@@ -602,11 +615,11 @@ __global__ void __launch_bounds__(32, 1) dir_eval_kernel(const EvalParams P) {
 #pragma unroll
             for (int k = 0; k < NCTRL; ++k) {
                 const int idx = __ldg(P.indicators + k * N + j);
-                u[k] = T(__ldg(row + P.ctrl_off[k] + idx));
+                u[k] = T(row[P.ctrl_off[k] + idx]);
                 u[k].d[0] = (k == dk && idx == didx) ? 1.0 : 0.0;
             }
 #pragma unroll
-            for (int i = 0; i < NOBS; ++i) w[i] = __ldg(row + P.w_off[i] + __ldg(P.indicators + (NCTRL + i) * N + j));
+            for (int i = 0; i < NOBS; ++i) w[i] = row[P.w_off[i] + __ldg(P.indicators + (NCTRL + i) * N + j)];
             M::template consts_t<T>(u, th, c);
             T Pq[NQ];
 #pragma unroll
@@ -624,7 +637,7 @@ __global__ void __launch_bounds__(32, 1) dir_eval_kernel(const EvalParams P) {
             }
         }
         // every lane evaluates the criterion on its own (identical) F: no exchange between lanes
-        const double tau = __ldg(row + P.tau_off);
+        const double tau = row[P.tau_off];
         double Fv[NF], L[NF], Ls[NF], value;
 #pragma unroll
         for (int a = 0; a < NF; ++a) Fv[a] = F[a].v;
