@@ -107,7 +107,8 @@ static cudaError_t launch_dir(const EvalParams& P0, int grid, cudaStream_t st) {
     EvalParams P = P0;
     const int nl = 1 + M::NIC + P.n_ctrl_values;
     const size_t rows = (size_t)(kDirBlock + nl - 1) / nl + 1;
-    size_t smem = rows * P.n_var * sizeof(double);
+    size_t smem = rows * (P.n_var + (size_t)P.n_intervals * M::NOBS * M::NF) * sizeof(double) +
+                  sizeof(int) * ((size_t)(M::NCTRL + M::NOBS) * P.n_intervals + P.n_intervals + 1);
     P.tile = smem <= 48 * 1024 ? (int)rows : 0;
     if (P.tile == 0) smem = 0;
     dir_eval_kernel<M, Stepper><<<grid, kDirBlock, smem, st>>>(P);
@@ -575,8 +576,11 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     CUC(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     CUC(cudaMalloc(&ctx->d_first_step, sizeof(int) * (N + 1)));
-    CUC(cudaMalloc(&ctx->d_step_t, sizeof(double) * st.size()));
-    CUC(cudaMalloc(&ctx->d_step_h, sizeof(double) * st.size()));
+    // one padding entry: the small-batch kernel fetches (t, h) of step s + 1 while it computes step s
+    CUC(cudaMalloc(&ctx->d_step_t, sizeof(double) * (st.size() + 1)));
+    CUC(cudaMalloc(&ctx->d_step_h, sizeof(double) * (st.size() + 1)));
+    CUC(cudaMemset(ctx->d_step_t, 0, sizeof(double) * (st.size() + 1)));
+    CUC(cudaMemset(ctx->d_step_h, 0, sizeof(double) * (st.size() + 1)));
     CUC(cudaMalloc(&ctx->d_indicators, sizeof(int) * nvars * N));
     CUC(cudaMemcpy(ctx->d_first_step, first.data(), sizeof(int) * (N + 1), cudaMemcpyHostToDevice));
     CUC(cudaMemcpy(ctx->d_step_t, st.data(), sizeof(double) * st.size(), cudaMemcpyHostToDevice));
@@ -936,7 +940,9 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
     bool small_zc = false;
     double *zc_in = nullptr, *zc_crit = nullptr, *zc_grad = nullptr, *zc_fim = nullptr;
     if (g && nchunks == 1 && n <= kSmallZeroCopy && ctx->zero_copy && !pipelined && dir_eligible(ctx, n, kidx) &&
-        ((size_t)(kDirBlock + ctx->dir_nl - 1) / ctx->dir_nl + 1) * ctx->n_var * sizeof(double) <= 48 * 1024) {
+        ((size_t)(kDirBlock + ctx->dir_nl - 1) / ctx->dir_nl + 1) *
+                (ctx->n_var + (size_t)ctx->n_intervals * ctx->model->info.n_obs * ctx->model->info.nF) * sizeof(double) +
+                sizeof(int) * ((size_t)(ctx->model->info.n_ctrl + ctx->model->info.n_obs + 1) * ctx->n_intervals + 1) <= 48 * 1024) {
         Slot& s0 = ctx->slots[0];
         auto dev = [](const void* p) -> double* {
             cudaPointerAttributes a;

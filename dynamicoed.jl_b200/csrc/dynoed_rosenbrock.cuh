@@ -570,12 +570,21 @@ __global__ void __launch_bounds__(32, 1) dir_eval_kernel(const EvalParams P) {
     // coalesced read — the rows may live in mapped host memory, see eval_host's small-call path)
     extern __shared__ __align__(16) double dir_rows[];
     const long long d_first = (blockIdx.x * (long long)blockDim.x) / nl;
+    // ... and so are the interval tables (indicator matrix, first step of every interval): a lone
+    // warp has nothing to hide a global load behind
+    const int* ind = P.indicators;
+    const int* fst = P.first_step;
     if (P.tile > 0) {
         long long d_last = (blockIdx.x * (long long)blockDim.x + blockDim.x - 1) / nl;
         if (d_last > P.n - 1) d_last = P.n - 1;
         const long long cnt = (d_last - d_first + 1) * n_var;
         const double* src = P.designs + d_first * n_var;
         for (long long i = threadIdx.x; i < cnt; i += blockDim.x) dir_rows[i] = src[i];
+        int* s_tab = reinterpret_cast<int*>(dir_rows + (size_t)P.tile * (n_var + N * NQ));
+        const int n_ind = (NCTRL + NOBS) * N;
+        for (int i = threadIdx.x; i < n_ind; i += blockDim.x) s_tab[i] = P.indicators[i];
+        for (int i = threadIdx.x; i <= N; i += blockDim.x) s_tab[n_ind + i] = P.first_step[i];
+        ind = s_tab; fst = s_tab + n_ind;
         __syncthreads();
     }
 
@@ -608,25 +617,34 @@ __global__ void __launch_bounds__(32, 1) dir_eval_kernel(const EvalParams P) {
         }
 #pragma unroll
         for (int a = 0; a < NF; ++a) F[a] = T(0.0);
-        double* pq = P.traj + (size_t)g * N * NQ;
+        // per-interval quadratures of the base lane: shared memory next to the rows, else global scratch
+        double* pq = P.tile > 0 ? dir_rows + (size_t)P.tile * n_var + (size_t)(g - d_first) * N * NQ
+                                : P.traj + (size_t)g * N * NQ;
+        int s_cur = fst[0];
+        double t_next = __ldg(P.step_t + s_cur), h_next = __ldg(P.step_h + s_cur);
         for (int j = 0; j < N; ++j) {
             T u[NCU], c[M::NCONST];
             double w[NOBS];
 #pragma unroll
             for (int k = 0; k < NCTRL; ++k) {
-                const int idx = __ldg(P.indicators + k * N + j);
+                const int idx = ind[k * N + j];
                 u[k] = T(row[P.ctrl_off[k] + idx]);
                 u[k].d[0] = (k == dk && idx == didx) ? 1.0 : 0.0;
             }
 #pragma unroll
-            for (int i = 0; i < NOBS; ++i) w[i] = row[P.w_off[i] + __ldg(P.indicators + (NCTRL + i) * N + j)];
+            for (int i = 0; i < NOBS; ++i) w[i] = row[P.w_off[i] + ind[(NCTRL + i) * N + j]];
             M::template consts_t<T>(u, th, c);
             T Pq[NQ];
 #pragma unroll
             for (int a = 0; a < NQ; ++a) Pq[a] = T(0.0);
-            const int s0 = __ldg(P.first_step + j), s1 = __ldg(P.first_step + j + 1);
-            for (int s = s0; s < s1; ++s)
-                Stepper::template step<M, T>(__ldg(P.step_t + s), __ldg(P.step_h + s), z, Pq, u, th, c);
+            // one warp per SM sub-partition has nothing to hide a load behind: (t, h) of the NEXT step
+            // are fetched before the current step's arithmetic (the step tables are padded by one entry)
+            const int s1 = fst[j + 1];
+            for (; s_cur < s1; ++s_cur) {
+                const double t_now = t_next, h_now = h_next;
+                t_next = __ldg(P.step_t + s_cur + 1); h_next = __ldg(P.step_h + s_cur + 1);
+                Stepper::template step<M, T>(t_now, h_now, z, Pq, u, th, c);
+            }
 #pragma unroll
             for (int i = 0; i < NOBS; ++i)
 #pragma unroll
@@ -667,7 +685,7 @@ __global__ void __launch_bounds__(32, 1) dir_eval_kernel(const EvalParams P) {
             for (int j = 0; j < N; ++j) {
 #pragma unroll
                 for (int i = 0; i < NOBS; ++i) {
-                    const int idx = __ldg(P.indicators + (NCTRL + i) * N + j);
+                    const int idx = ind[(NCTRL + i) * N + j];
                     if (idx != wk[i]) {
                         if (wk[i] >= 0) grow[P.w_off[i] + wk[i]] = wb[i];
                         wb[i] = 0.0; wk[i] = idx;
