@@ -268,7 +268,8 @@ struct Slot {
 
 // memcpy split over a few host threads: one core moves ~10 GB/s, a PCIe Gen5 link wants ~50
 static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    if (bytes < (2u << 20)) { memcpy(dst, src, bytes); return; }
+    static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     const int nt = (int)std::min<size_t>(std::min<unsigned>(8u, std::max(1u, hw / 2)), bytes / (1u << 20));
     if (nt <= 1) { memcpy(dst, src, bytes); return; }
     std::vector<std::thread> th;
@@ -351,6 +352,7 @@ struct dynoed_ctx {
     Slot slots[kSlots];
     int64_t launches = 0;
     int64_t pdl_launches = 0;
+    cudaEvent_t ev_order = nullptr;    // host path: orders the slot streams after / before the ctx stream
     int64_t dir_launches = 0;
     size_t scratch_bytes = 0;
     // optional per-launch timing of the evaluation kernel (device-pointer path)
@@ -662,6 +664,7 @@ void dynoed_destroy(dynoed_ctx* ctx) {
     cudaFree(ctx->d_best); cudaFree(ctx->d_ring); cudaFree(ctx->d_ticket);
     cudaFree(ctx->hs.pert); cudaFree(ctx->hs.pcrit); cudaFree(ctx->hs.pgrad); cudaFree(ctx->hs.x); cudaFree(ctx->hs.c); cudaFree(ctx->hs.g); cudaFree(ctx->hs.H);
     if (ctx->ev_k0) { cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1); }
+    if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -691,10 +694,35 @@ int dynoed_own_stream(dynoed_ctx* ctx) {
     return DYNOED_OK;
 }
 
+// cudaPointerGetAttributes, memoised for the duration of ONE evaluation call (the same four caller
+// pointers are classified several times on the way down; a one-design call is all host overhead)
+struct AttrMemo {
+    bool active = false;
+    int n = 0;
+    const void* ptr[8];
+    cudaPointerAttributes attr[8];
+    bool ok[8];
+};
+static thread_local AttrMemo g_attr_memo;
+struct AttrMemoScope {
+    AttrMemoScope() { g_attr_memo.active = true; g_attr_memo.n = 0; }
+    ~AttrMemoScope() { g_attr_memo.active = false; g_attr_memo.n = 0; }
+};
+static bool pointer_attrs(const void* p, cudaPointerAttributes* out) {
+    AttrMemo& m = g_attr_memo;
+    if (m.active)
+        for (int i = 0; i < m.n; ++i)
+            if (m.ptr[i] == p) { *out = m.attr[i]; return m.ok[i]; }
+    const bool ok = cudaPointerGetAttributes(out, p) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    if (m.active && m.n < 8) { m.ptr[m.n] = p; m.attr[m.n] = *out; m.ok[m.n] = ok; ++m.n; }
+    return ok;
+}
+
 // 0 = host, 1 = device/managed
 static int ptr_kind(const void* p) {
     cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (!pointer_attrs(p, &a)) return 0;
     return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? 1 : 0;
 }
 
@@ -839,7 +867,7 @@ static int ensure_staging(dynoed_ctx* ctx, Slot& s, int64_t cap) {
 static bool is_pageable(const void* p) {
     if (!p) return false;
     cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    if (!pointer_attrs(p, &a)) return true;
     return a.type == cudaMemoryTypeUnregistered;
 }
 
@@ -892,7 +920,7 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
     auto mapped = [ctx](const void* p) -> double* {
         if (!p || !ctx->zero_copy) return nullptr;
         cudaPointerAttributes a;
-        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (!pointer_attrs(p, &a)) return nullptr;
         return a.type == cudaMemoryTypeHost ? static_cast<double*>(a.devicePointer) : nullptr;
     };
     double* crit_map = mapped(crit);
@@ -918,8 +946,8 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         if (fim) memcpy(fim + off * nF, s.h_fim, sizeof(double) * cnt * nF);
         return DYNOED_OK;
     };
-    cudaEvent_t ev;
-    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    if (!ctx->ev_order) CU(cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming));
+    cudaEvent_t ev = ctx->ev_order;   // re-recorded at every use: a wait captures the record that precedes it
     for (int q = 0; q < 2; ++q)
         if (!ctx->call_done[q]) CU(cudaEventCreateWithFlags(&ctx->call_done[q], cudaEventDisableTiming));
     if (pipelined && !ctx->stream_dirty && !staged) {
@@ -946,7 +974,7 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         Slot& s0 = ctx->slots[0];
         auto dev = [](const void* p) -> double* {
             cudaPointerAttributes a;
-            if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            if (!p || !pointer_attrs(p, &a)) return nullptr;
             return a.type == cudaMemoryTypeHost ? static_cast<double*>(a.devicePointer) : nullptr;
         };
         zc_in = dev(staged ? s0.h_designs : designs);
@@ -1002,7 +1030,6 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         CU(cudaEventRecord(ev, ctx->slots[k].stream));
         CU(cudaStreamWaitEvent(ctx->stream, ev, 0));
     }
-    CU(cudaEventDestroy(ev));
     CU(cudaEventRecord(ctx->call_done[par], ctx->stream));   // fires when every chunk of THIS call has landed
     ctx->host_seq++;
     ctx->call_of_parity[par] = ctx->host_seq;
@@ -1017,6 +1044,7 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
 static int eval_common(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad, double* fim,
                        bool allow_host, bool sync, uint32_t flags = 0, bool pipelined = false) {
     if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    AttrMemoScope memo;
     ctx->err.clear();
     if (n < 0) return fail(ctx, DYNOED_EINVAL, "n < 0");
     if (n == 0) { ctx->have_batch = false; return DYNOED_OK; }
