@@ -90,3 +90,79 @@ def gpu_evaluator(ctx):
             return crit, grad, ctx.argmin()
         return crit, grad, (-1, float("inf"))
     return evaluate
+
+
+# ---- device-side selection: ONE collective, ONE host synchronisation per sweep -------------------
+def pack_local_winner(values: torch.Tensor, indices: torch.Tensor, index_base: int, designs_local: torch.Tensor,
+                      grad_local: torch.Tensor) -> torch.Tensor:
+    """[value, global index, design row, gradient row] of this rank's best candidate, as one
+    float64 tensor on the tensors' device, without leaving the device.
+
+    values / indices: per-batch (min value, LOCAL row index within the shard, < 0 = none) records
+    of this rank (e.g. `Context.argmin_history_async` reinterpreted).  NaN never wins; ties go to
+    the smallest index.  An empty / all-NaN shard yields (inf, -1, zeros, zeros)."""
+    n_var = designs_local.shape[1]
+    vals = torch.where((indices >= 0) & (values == values), values, torch.full_like(values, float("inf")))
+    m = vals.min()
+    cand = torch.where(vals == m, indices, torch.full_like(indices, torch.iinfo(torch.int64).max))
+    li = cand.min()
+    valid = torch.isfinite(m) | (m == float("-inf"))
+    valid = valid & (li < torch.iinfo(torch.int64).max) & (li >= 0)
+    safe = torch.where(valid, li, torch.zeros_like(li)).clamp(0, max(designs_local.shape[0] - 1, 0))
+    out = torch.zeros(2 + 2 * n_var, dtype=torch.float64, device=designs_local.device)
+    out[0] = torch.where(valid, m, torch.full_like(m, float("inf")))
+    out[1] = torch.where(valid, (li + index_base).to(torch.float64), torch.full_like(m, -1.0))
+    if designs_local.shape[0] > 0:
+        keep = valid.to(torch.float64)
+        out[2:2 + n_var] = designs_local.index_select(0, safe.reshape(1))[0] * keep
+        out[2 + n_var:] = grad_local.index_select(0, safe.reshape(1))[0] * keep
+    return out
+
+
+def gather_winner(payload: torch.Tensor, group=None) -> torch.Tensor:
+    """all_gather of every rank's `pack_local_winner` payload, then the global winner's payload
+    (min value, ties -> smallest global index) with the owner rank appended — still on the device;
+    the caller reads it with ONE `.cpu()`."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world > 1:
+        flat = torch.empty(world * payload.numel(), dtype=payload.dtype, device=payload.device)
+        dist.all_gather_into_tensor(flat, payload.contiguous(), group=group)
+        allp = flat.view(world, payload.numel())
+    else:
+        allp = payload[None]
+    v, idx = allp[:, 0], allp[:, 1]
+    m = v.min()
+    cand = torch.where((v == m) & (idx >= 0), idx, torch.full_like(idx, float("inf")))
+    owner = torch.argmin(cand)
+    win = allp.index_select(0, owner.reshape(1))[0]
+    none = ~torch.isfinite(cand.min())
+    owner_f = torch.where(none, torch.full((), -1.0, dtype=torch.float64, device=payload.device),
+                          owner.to(torch.float64))
+    return torch.cat([win, owner_f.reshape(1)])
+
+
+def sweep_device(ctx, designs_local: torch.Tensor, crit: torch.Tensor, grad: torch.Tensor, index_base: int,
+                 chunk: int = 65536, group=None) -> dict:
+    """One multistart sweep of this rank's shard on the GPU: back-to-back launches of `chunk`
+    designs (their tails overlap), the per-batch records read on the device, one all_gather of the
+    local winners, one device->host read at the end."""
+    n_local, n_var = designs_local.shape
+    dev = designs_local.device
+    nch = (n_local + chunk - 1) // chunk
+    if nch > 64:
+        raise ValueError("history ring holds 64 batches: use a larger chunk")
+    for c in range(nch):
+        a, b = c * chunk, min((c + 1) * chunk, n_local)
+        ctx.eval_batch(designs_local[a:b], crit[a:b], grad[a:b], None, async_=True)
+    if nch > 0:
+        rec = torch.empty((nch, 2), dtype=torch.int64, device=dev)
+        ctx.argmin_history_async(nch, rec)
+        values = rec[:, 0].contiguous().view(torch.float64)
+        base = torch.arange(nch, dtype=torch.int64, device=dev) * chunk
+        indices = torch.where(rec[:, 1] >= 0, rec[:, 1] + base, rec[:, 1])
+    else:
+        values = torch.full((1,), float("inf"), dtype=torch.float64, device=dev)
+        indices = torch.full((1,), -1, dtype=torch.int64, device=dev)
+    win = gather_winner(pack_local_winner(values, indices, index_base, designs_local, grad), group).cpu()
+    return dict(value=float(win[0]), index=int(win[1]), owner=int(win[-1]), design=win[2:2 + n_var],
+                grad=win[2 + n_var:2 + 2 * n_var])

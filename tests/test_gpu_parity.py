@@ -968,3 +968,23 @@ def test_small_batch_kernel_device_pointers_and_nan(built_library):
     den = np.maximum(np.abs(cb[:32]), np.max(np.abs(Fb[:32]), axis=1))
     assert float(np.max(np.abs(c - cb[:32]) / den)) < 1e-11 and rel(F, Fb[:32]) < 1e-11
     assert rel_rows(g, gb[:32]) < RTOL
+
+
+def test_multistart_sweep_device_side_selection(built_library):
+    """Chunked back-to-back launches, per-batch records reduced on the device, one host read: the
+    winner equals the arg-min of all criterion values and carries its own design / gradient rows."""
+    import torch
+    from dynamicoed.jl_b200 import multistart
+    ctx = make_problem("lv_fishing", D.FisherDCriterion).context()
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    n = 3 * 65536 + 1234
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    des = torch.rand((n, 71), dtype=torch.float64, device="cuda", generator=g)
+    des[:, -1] = 1e-3 + 0.99 * des[:, -1]
+    des[17, 3] = float("nan")
+    crit = torch.empty(n, dtype=torch.float64, device="cuda"); grad = torch.empty_like(des)
+    out = multistart.sweep_device(ctx, des, crit, grad, 1000, chunk=65536)
+    k = int(torch.argmin(torch.nan_to_num(crit, nan=float("inf"))))
+    assert out["index"] == 1000 + k and out["value"] == float(crit[k]) and out["owner"] == 0
+    assert torch.equal(out["design"], des[k].cpu()) and torch.equal(out["grad"], grad[k].cpu())
+    ctx.own_stream()

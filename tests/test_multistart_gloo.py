@@ -50,6 +50,26 @@ def _worker(rank, world, port, q):
           np.array_equal(out["design"].numpy(), des[k]) and
           np.array_equal(out["grad"].numpy(), g_all[k]) and
           np.array_equal(out["crit_all"].numpy(), cr_all) and out["owner"] == (0 if k < hi - lo or rank == 0 and k < hi else out["owner"]))
+    # the device-side protocol (one all_gather of packed local winners, no host round trips): the
+    # shard's per-batch records, here two "batches" per rank, packed and reduced with the same code
+    from dynamicoed.jl_b200.multistart import gather_winner, pack_local_winner
+    cr_loc, g_loc = torch.from_numpy(cr_all[lo:hi].copy()), torch.from_numpy(g_all[lo:hi].copy())
+    half = (hi - lo) // 2
+    vals = torch.stack([cr_loc[:half].min(), cr_loc[half:].min()])
+    idxs = torch.stack([cr_loc[:half].argmin(), cr_loc[half:].argmin() + half])
+    win = gather_winner(pack_local_winner(vals, idxs, lo, torch.from_numpy(des[lo:hi]), g_loc))
+    ok = ok and (int(win[1]) == k and float(win[0]) == cr_all[k] and int(win[-1]) == out["owner"] and
+                 np.array_equal(win[2:73].numpy(), des[k]) and np.array_equal(win[73:144].numpy(), g_all[k]))
+    # a rank without any valid candidate (all NaN) never wins; if nobody has one: index -1, owner -1
+    nanp = pack_local_winner(torch.tensor([float("nan")], dtype=torch.float64), torch.tensor([5]), lo,
+                             torch.from_numpy(des[lo:hi]), g_loc)
+    win2 = gather_winner(nanp if rank == 0 else pack_local_winner(vals, idxs, lo, torch.from_numpy(des[lo:hi]), g_loc))
+    k1 = lo_hi_best = None
+    lo1, hi1 = shard_bounds(n, 1, world)
+    k1 = lo1 + int(np.argmin(cr_all[lo1:hi1]))
+    ok = ok and int(win2[1]) == k1 and int(win2[-1]) == 1
+    win3 = gather_winner(nanp)
+    ok = ok and int(win3[1]) == -1 and int(win3[-1]) == -1 and float(win3[0]) == float("inf")
     q.put((rank, bool(ok), out["index"], k))
     dist.barrier()
     dist.destroy_process_group()
