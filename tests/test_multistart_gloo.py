@@ -87,3 +87,27 @@ def test_world_size_2_sweep_matches_single_process():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok, _, _ in res), res
+
+
+def test_pack_and_gather_winner_single_process_edges():
+    from dynamicoed.jl_b200.multistart import gather_winner, pack_local_winner
+    rng = np.random.default_rng(3)
+    d = torch.from_numpy(rng.random((10, 5))); g = torch.from_numpy(rng.random((10, 5)))
+    # NaN never wins, ties go to the smallest index, indices < 0 mean "no candidate in that batch"
+    vals = torch.tensor([0.5, float("nan"), -1.0, -1.0, -7.0])
+    idx = torch.tensor([3, 4, 7, 2, -1])
+    p = pack_local_winner(vals, idx, 100, d, g)
+    assert float(p[0]) == -1.0 and int(p[1]) == 102
+    assert torch.equal(p[2:7], d[2]) and torch.equal(p[7:], g[2])
+    w = gather_winner(p)
+    assert float(w[0]) == -1.0 and int(w[1]) == 102 and int(w[-1]) == 0 and torch.equal(w[:-1], p)
+    # -inf is a legitimate value
+    p = pack_local_winner(torch.tensor([float("-inf"), 1.0]), torch.tensor([9, 0]), 0, d, g)
+    assert float(p[0]) == float("-inf") and int(p[1]) == 9 and torch.equal(p[2:7], d[9])
+    # no candidate at all / empty shard
+    for v, i, dd, gg in ((torch.tensor([float("nan")]), torch.tensor([5]), d, g),
+                         (torch.tensor([float("inf")]), torch.tensor([-1]), d[:0], g[:0])):
+        p = pack_local_winner(v, i, 100, dd, gg)
+        assert float(p[0]) == float("inf") and int(p[1]) == -1 and float(p[2:].abs().sum()) == 0.0
+        w = gather_winner(p)
+        assert int(w[1]) == -1 and int(w[-1]) == -1
