@@ -334,3 +334,41 @@ def test_stiff_golden_fixtures_match_the_cpp_oracle(name, method):
     o = Oracle(ctor(), int(z["criterion"]), method, list(D.graded_edges(10, 30, 1e-6, 6)))
     c, g, F = cpp_oracle.CppOracle(name, o).evaluate(z["designs"], grad=True)
     assert np.array_equal(c, z["crit"]) and np.array_equal(g, z["grad"]) and np.array_equal(F, z["F"])
+
+
+@pytest.mark.parametrize("crit", [1, 3, 4])
+def test_central_differences_of_the_exact_gradient_give_the_hessian(crit):
+    """The Hessian recipe of `dynoed_hessian_batch` (central differences of the exact gradient, step
+    cbrt(eps) * max(1, |x_i|), symmetrised) applied to the ORACLE's gradient: its (w, tau) block
+    must equal the closed form d^2 phi(F + tau I)[B_a, B_b] (F is linear in w, augment.jl:223-226),
+    which bounds the method's own error independently of the GPU."""
+    o = Oracle(models.lotka_volterra_fishing(), crit, "rk4", 4)
+    c = cpp_oracle.CppOracle("lv_fishing", o)
+    rng = np.random.default_rng(11)
+    x = rng.random(71); x[-1] = 0.3
+    nv = x.size
+    h = 6.0554544523933395e-06 * np.maximum(1.0, np.abs(x))
+    P = np.vstack([x + np.diag(h), x - np.diag(h)])
+    G = c.evaluate(P, grad=True)[1]
+    den = (P[np.arange(nv), np.arange(nv)] - P[nv + np.arange(nv), np.arange(nv)])[:, None]
+    A = (G[:nv] - G[nv:]) / den
+    H = 0.5 * (A + A.T)
+    units = np.tile(x, (60, 1)); units[:, 10:70] = np.eye(60)
+    Bp = c.evaluate(units, grad=False)[2]
+    _, g0, F0 = c.evaluate(x[None], grad=True)
+    sym = lambda p: np.array([[p[0], p[1]], [p[1], p[2]]])
+    dirs = [sym(b) for b in Bp] + [np.eye(2)]
+    M = sym(F0[0]) + x[-1] * np.eye(2)
+    Mi, d = np.linalg.inv(M), np.linalg.det(M)
+
+    def second(A_, B_):
+        tA, tB, tAB = np.trace(Mi @ A_), np.trace(Mi @ B_), np.trace(Mi @ A_ @ Mi @ B_)
+        if crit == 1:
+            return -d * (tA * tB - tAB)                      # -det M
+        if crit == 3:
+            return 2.0 * np.trace(Mi @ A_ @ Mi @ B_ @ Mi)    # tr M^-1
+        return (tA * tB + tAB) / d                           # 1 / det M
+    Hw = np.array([[second(a, b) for b in dirs] for a in dirs])
+    cols = list(range(10, 71))
+    scale = max(np.abs(Hw).max(), np.abs(g0).max())
+    assert np.abs(H[np.ix_(cols, cols)] - Hw).max() < 2e-8 * scale
