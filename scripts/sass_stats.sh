@@ -1,15 +1,19 @@
 #!/bin/bash
 # Compile the LV-fishing-only library and print SASS statistics of the RK4 gradient kernel.
 set -e
-cd /tmp/sass
+ROOT=$(cd "$(dirname "$0")/.." && pwd)
+W=$ROOT/gpurun_out/sass          # scratch (git-ignored)
+mkdir -p $W
+cd $W
+printf '#pragma once\n#include "%s/dynamicoed.jl_b200/csrc/generated/model_lv_fishing.cuh"\n#define DYNOED_FOR_EACH_MODEL(X) X(Model_lv_fishing)\n' "$ROOT" > models.cuh
 if [ -z "$NOBUILD" ]; then nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared -Xptxas -v \
-  '-DDYNOED_MODELS_HEADER="/tmp/sass/models.cuh"' -o lv.so /root/repo/dynamicoed.jl_b200/csrc/dynoed_api.cu 2> ptxas.log; fi
+  -I$ROOT/include "-DDYNOED_MODELS_HEADER=\"$W/models.cuh\"" $EXTRA_DEFINES -o lv.so $ROOT/dynamicoed.jl_b200/csrc/dynoed_api.cu 2> ptxas.log; fi
 grep -A1 "oed_eval_kernelI16Model_lv_fishingNS_6TabRK4ELb1ELb1" ptxas.log | grep -E "registers|spill" | head -4
 cuobjdump -sass -fun '_ZN6dynoed15oed_eval_kernelI16Model_lv_fishingNS_6TabRK4ELb1ELb1EEEvNS_10EvalParamsE' lv.so > k.sass
 python3 - <<'PY'
 import re,collections
 ins=[]
-for l in open('/tmp/sass/k.sass'):
+for l in open('k.sass'):
     m=re.search(r'/\*([0-9a-f]{4,})\*/\s+(.*?);',l)
     if m: ins.append((int(m.group(1),16),m.group(2).strip()))
 print('total instr',len(ins))
