@@ -43,13 +43,23 @@ def make_designs(n, n_var, seed):
     return d
 
 
+MULTISTART_N = 1 << 20      # BASELINE.json config 5: designs of the whole sweep, split over the GPUs
+
+
+def ref_sample():
+    """Designs per step of the reference (CPU) arm: a bounded sample of the 65,536-design batch."""
+    return int(os.environ.get("DYNOED_REF_SAMPLE", 2048 * max(1, (os.cpu_count() or 8) // 8)))
+
+
 def workload_config(n_gpus):
     return {"workload": "lv_fishing: 65,536 random relaxed designs per GPU, FisherD criterion + "
                         "full gradient (71 vars), RK4 m=4 x 30 intervals, arg-min",
             "designs_per_gpu": N_PER_GPU, "total_designs": N_PER_GPU * n_gpus, "n_var": 71,
             "integrator": "RK4 fixed step, 4 substeps/interval (120 steps)",
             "criterion": "FisherDCriterion", "parallelism": f"design-sharded x{n_gpus}",
-            "l2": f"{NBUF} rotating input/output buffer sets (>126 MB L2) + 327 MB trajectory scratch"}
+            "l2": f"{NBUF} rotating input/output buffer sets (>126 MB L2) + 420 MB checkpoint scratch",
+            "reference_arm_sample": f"{ref_sample()} designs of the same batch per step (CPU arm only; a rate)",
+            "multistart_designs": MULTISTART_N}
 
 
 class ClockSampler:
@@ -103,12 +113,19 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(pw)}
 
 
+CPU_ALGORITHM = ("forward-mode dual numbers through the fixed-step integrator, chunk 12 (as ForwardDiff), "
+                 "std::thread over designs")
+
+
 def cpu_oracle(method="rk4"):
+    """The TIMED CPU arm: the C++ restatement built for this host's ISA with FMA contraction
+    (-O3 -march=native -ffp-contract=fast; oracle/Makefile `native`).  The strict-FP build
+    (-ffp-contract=off) stays the parity oracle of the tests."""
     from dynamicoed.jl_b200 import models
-    from oracle.cpp_oracle import CppOracle, max_threads
+    from oracle.cpp_oracle import NATIVE_FLAGS, CppOracle, max_threads
     from oracle.oed_oracle import FISHER_D, Oracle
     o = Oracle(models.lotka_volterra_fishing(), FISHER_D, method, SUBSTEPS)
-    return CppOracle("lv_fishing", o), max_threads()
+    return CppOracle("lv_fishing", o, native=True), max_threads(), NATIVE_FLAGS
 
 
 def time_cpu(orc, threads, designs, seconds):
@@ -131,9 +148,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    orc, threads = cpu_oracle()
+    orc, threads, cflags = cpu_oracle()
     designs = make_designs(N_PER_GPU, 71, 20262)
-    sample = int(os.environ.get("DYNOED_REF_SAMPLE", 2048 * max(1, threads // 8)))
+    sample = ref_sample()
     for _ in range(min(args.warmup, 2)):
         orc.evaluate(designs[:sample], grad=True, threads=threads)
     t0 = time.perf_counter()
@@ -148,7 +165,8 @@ def run_reference(args):
             "data": "synthetic", "config": workload_config(args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{sample} designs per step x {args.steps} steps of the same "
-                                       "workload (criterion + full forward-mode gradient)"},
+                                       "workload (criterion + full forward-mode gradient)",
+                             "cpu_algorithm": CPU_ALGORITHM, "build_flags": cflags},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -213,27 +231,39 @@ def main():
     # multi-GPU: NCCL only gathers the per-rank (min, index) records.  GATHER batches share one
     # collective (records come from the library's history ring), so that the evaluation launches
     # in between stay back to back and overlap their tails exactly as at N=1.
+    # The gather runs on a SIDE stream, ordered after the evaluation launches by an event (an event
+    # record does not end the launches' overlap; a copy or kernel on the evaluation stream would).
     GATHER = 16
     rec = torch.empty((GATHER, 2), dtype=torch.int64, device=dev)          # {value bits, local index}
     gat = torch.empty((world, GATHER, 2), dtype=torch.int64, device=dev)
     best = torch.empty((GATHER, 3), dtype=torch.int64, device=dev)         # {value bits, global index, owner}
     pending = [0]
+    side = torch.cuda.Stream(device=dev)
+    ctx.set_aux_stream(side.cuda_stream)
 
     def flush():
         g = pending[0]
-        if world > 1 and g:
-            ctx.argmin_history_async(g, rec)
-            buf = gat if g == GATHER else torch.empty((world, g, 2), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(buf, rec[:g])
-            ctx.argmin_gathered(buf, world, n, best, groups=g)
+        if g:
+            with torch.cuda.stream(side):
+                ctx.argmin_history_async(g, rec)                            # waits for the launches so far
+                buf = gat if g == GATHER else torch.empty((world, g, 2), dtype=torch.int64, device=dev)
+                if world > 1:
+                    dist.all_gather_into_tensor(buf, rec[:g])
+                else:
+                    buf.copy_(rec[:g].view(1, g, 2))
+                ctx.argmin_gathered(buf, world, n, best, groups=g)
         pending[0] = 0
 
     def step(k):
         b = k % NBUF
-        ctx.eval_batch(d_in[b], d_crit[b], d_grad[b], d_fim[b], async_=True)
+        # static, disjoint buffer sets: consecutive launches may overlap (DYNOED_OVERLAP_OK)
+        ctx.eval_batch(d_in[b], d_crit[b], d_grad[b], d_fim[b], async_=True, flags=runtime.OVERLAP_OK)
         pending[0] += 1
         if pending[0] == GATHER:
             flush()
+
+    def join_side():
+        stream.wait_stream(side)
 
     def barrier():
         torch.cuda.synchronize()
@@ -245,6 +275,7 @@ def main():
     for k in range(args.warmup):
         step(k)
     flush()
+    join_side()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -258,9 +289,72 @@ def main():
     for k in range(args.steps):
         step(k)
     flush()
+    join_side()                      # the timed region ends when the last gather + reduction has finished
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
+
+    # ---- untimed check of the gathered arg-min at THIS world size: one batch per buffer set, one gather;
+    # every record must equal an all_reduce(MIN) over the ranks' criterion values, name the rank that
+    # holds it and that rank's row.  A wrong selection fails the run.
+    for b in range(NBUF):
+        step(b)
+    g_chk = pending[0]
+    flush()
+    join_side()
+    torch.cuda.synchronize()
+    rec_h = best[:g_chk].cpu()
+    for b in range(g_chk):
+        cb = torch.nan_to_num(d_crit[b], nan=float("inf"))
+        lmin = cb.min().reshape(1).clone()
+        gmin = lmin.clone()
+        if world > 1:
+            dist.all_reduce(gmin, op=dist.ReduceOp.MIN)
+        val = float(rec_h[b, :1].view(torch.float64)[0])
+        gidx, owner = int(rec_h[b, 1]), int(rec_h[b, 2])
+        if val != float(gmin) or not (0 <= owner < world) or gidx // n != owner:
+            raise SystemExit(f"arg-min check failed: batch {b}: record ({val}, {gidx}, {owner}) vs min {float(gmin)}")
+        if owner == rank and (float(d_crit[b][gidx - owner * n]) != val or int(torch.argmin(cb)) != gidx - owner * n):
+            raise SystemExit(f"arg-min check failed on the owner: batch {b}, row {gidx - owner * n}")
+    argmin_verified = True
+
+    # ---- BASELINE.json config 5: the whole 1,048,576-design multistart sweep, sharded over the GPUs:
+    # evaluation launches + dynoed_pack_winner + ONE all_gather + dynoed_select_winner + one host read.
+    from dynamicoed.jl_b200 import multistart
+    ctx.set_aux_stream(0)
+    lo, hi = multistart.shard_bounds(MULTISTART_N, rank, world)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(20264 + rank)
+    ms_des = torch.rand((hi - lo, n_var), dtype=torch.float64, device=dev, generator=gen)
+    ms_des[:, -1] = 1e-3 + (1 - 1e-3) * ms_des[:, -1]
+    ms_crit = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+    ms_grad = torch.empty_like(ms_des)
+    ms_times = []
+    for rep in range(9):                                   # 2 warm-up sweeps, 7 timed
+        barrier()
+        t0 = time.perf_counter()
+        ms_out = multistart.sweep_device(ctx, ms_des, ms_crit, ms_grad, lo, chunk=N_PER_GPU)
+        ms_times.append(time.perf_counter() - t0)
+    tt = torch.tensor(ms_times[2:], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)          # per repetition: the slowest rank
+    multistart_ms = float(tt.median()) * 1e3
+    mn = torch.nan_to_num(ms_crit, nan=float("inf")).min().reshape(1).clone()
+    if world > 1:
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+    ok = float(mn) == ms_out["value"] and multistart.shard_bounds(MULTISTART_N, ms_out["owner"], world)[0] <= ms_out["index"] < \
+        multistart.shard_bounds(MULTISTART_N, ms_out["owner"], world)[1]
+    if ms_out["owner"] == rank:
+        r = ms_out["index"] - lo
+        ok = ok and torch.equal(ms_out["design"], ms_des[r].cpu()) and torch.equal(ms_out["grad"], ms_grad[r].cpu()) \
+            and float(ms_crit[r]) == ms_out["value"]
+    okt = torch.tensor([1.0 if ok else 0.0], device=dev)
+    if world > 1:
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    if float(okt) != 1.0:
+        raise SystemExit("multistart winner check failed")
+    del ms_des, ms_grad, ms_crit
+    ctx.set_aux_stream(side.cuda_stream)
     ks1 = ctx.kernel_stats(True)
     launches = ks1["launches"] - launches0
     overlapped = ks1["overlapped_launches"] - over0
@@ -278,7 +372,7 @@ def main():
     for key, kw in (("criterion_only", dict(grad=False)), ("criterion_dw_dtau", dict(grad=True, flags=runtime.GRAD_NO_CONTROLS))):
         def one(k):
             ctx.eval_batch(d_in[k % NBUF], d_crit[k % NBUF], d_grad[k % NBUF] if kw["grad"] else None, d_fim[k % NBUF],
-                           async_=True, flags=kw.get("flags", 0))
+                           async_=True, flags=kw.get("flags", 0) | runtime.OVERLAP_OK)
         for k in range(3):
             one(k)
         torch.cuda.synchronize()
@@ -303,13 +397,15 @@ def main():
                                 alg=alg, device=local).context()
             ctxa.set_stream(stream.cuda_stream)
             for k in range(3):
-                ctxa.eval_batch(d_in[k % NBUF], d_crit[k % NBUF], d_grad[k % NBUF], d_fim[k % NBUF], async_=True)
+                ctxa.eval_batch(d_in[k % NBUF], d_crit[k % NBUF], d_grad[k % NBUF], d_fim[k % NBUF], async_=True,
+                                flags=runtime.OVERLAP_OK)
             torch.cuda.synchronize()
             s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = min(args.steps, 40)
             s0.record(stream)
             for k in range(reps):
-                ctxa.eval_batch(d_in[k % NBUF], d_crit[k % NBUF], d_grad[k % NBUF], d_fim[k % NBUF], async_=True)
+                ctxa.eval_batch(d_in[k % NBUF], d_crit[k % NBUF], d_grad[k % NBUF], d_fim[k % NBUF], async_=True,
+                                flags=runtime.OVERLAP_OK)
             s1.record(stream)
             torch.cuda.synchronize()
             msa = s0.elapsed_time(s1) / reps
@@ -343,7 +439,8 @@ def main():
     t_probe = time.perf_counter()
     k = 0
     while sampler and time.perf_counter() - t_probe < 1.0:   # rank 0 only: local launches, NO collectives
-        ctx.eval_batch(d_in[k % NBUF], d_crit[k % NBUF], d_grad[k % NBUF], d_fim[k % NBUF], async_=True)
+        ctx.eval_batch(d_in[k % NBUF], d_crit[k % NBUF], d_grad[k % NBUF], d_fim[k % NBUF], async_=True,
+                       flags=runtime.OVERLAP_OK)
         k += 1
         if k % 50 == 0:
             torch.cuda.synchronize()
@@ -382,14 +479,17 @@ def main():
         for _ in range(3):
             c_i.eval_batch(hp.numpy(), hc.numpy(), hg.numpy(), hf.numpy())
 
-    def e2e_run(nthreads):
+    def e2e_run(nthreads, with_grad=True):
         sink = [0.0] * nthreads
 
         def work(i):
             torch.cuda.set_device(local)
             c_i, hp, hc, hg, hf = sets[i]
             for _ in range(i, e2e_steps, nthreads):
-                c_i.eval_batch(hp.numpy(), hc.numpy(), hg.numpy(), hf.numpy())
+                if with_grad:
+                    c_i.eval_batch(hp.numpy(), hc.numpy(), hg.numpy(), hf.numpy())
+                else:                                         # what a multistart sweep needs over PCIe:
+                    c_i.eval_batch(hp.numpy(), hc.numpy(), None, None)   # 568 B in, 8 B back per design
                 sink[i] += float(hc[0])                       # host read of the step's result
         ths = [threading.Thread(target=work, args=(i,)) for i in range(nthreads)]
         barrier()
@@ -408,6 +508,35 @@ def main():
 
     e2e_single = e2e_run(1)
     e2e_value = e2e_run(E2E_THREADS)
+    e2e_objective_only = e2e_run(E2E_THREADS, with_grad=False)
+
+    # The ceiling the host-buffer path can reach on this box: the same bytes per step as plain pinned
+    # copies (H2D of the designs on one stream, D2H of objective + gradient + F on another, both
+    # directions busy, no kernel), all ranks at once.
+    def copy_ceiling():
+        _, hp, hc, hg, hf = sets[0]
+        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        dd, dc, dg, df = d_in[0], d_crit[0], d_grad[0], d_fim[0]
+
+        def once():
+            with torch.cuda.stream(s_in):
+                dd.copy_(hp, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                hc.copy_(dc, non_blocking=True); hg.copy_(dg, non_blocking=True); hf.copy_(df, non_blocking=True)
+        for _ in range(3):
+            once()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            once()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tmax = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dt = float(tmax)
+        return n * world * e2e_steps / dt, (n * n_var * 8 + n * (1 + n_var + 3) * 8) * world * e2e_steps / dt / 1e9
+    e2e_ceiling, e2e_ceiling_gbs = copy_ceiling()
 
     # one host thread, two calls in flight (dynoed_eval_batch_host_async / dynoed_wait)
     def e2e_pipelined():
@@ -473,24 +602,44 @@ def main():
                              "frac_isolated": flops / (kernel_ms_iso * 1e-3) / 1e12 / peak if kernel_ms_iso > 0 else None,
                              "flops_per_design": ks["flops_per_design_grad"],
                              "regs": ks["regs_per_thread"], "blocks_per_sm": ks["blocks_per_sm"],
-                             "hbm": {"achieved_gbs": ks["bytes_per_design"] * n / (kernel_ms * 1e-3) / 1e9
-                                     if kernel_ms > 0 else None,
-                                     "peak_gbs": hbm_peak, "peak_source": hbm_src,
-                                     "algorithmic_bytes_per_design": ks["bytes_per_design"]}},
+                             # HBM side of the same launches (I/O phases): algorithmic bytes / launch time
+                             "hbm_achieved_gbs": ks["bytes_per_design"] * n / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None,
+                             "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
+                             "hbm_frac": ks["bytes_per_design"] * n / (kernel_ms * 1e-3) / 1e9 / hbm_peak if kernel_ms > 0 else None,
+                             "hbm_algorithmic_bytes_per_design": ks["bytes_per_design"],
+                             "dram_traffic_over_algorithmic": traffic / (ks["bytes_per_design"] * n) if traffic else None},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * n_var * 8,
                         "d2h_bytes_per_step": n * (1 + n_var + 3) * 8, "steps": e2e_steps,
                         "host_memory": "pinned", "host_threads": E2E_THREADS,
                         "value_single_host_thread": e2e_single,
                         "value_single_host_thread_pipelined": e2e_piped,
+                        "value_objective_only": e2e_objective_only,
+                        "copy_ceiling": e2e_ceiling, "copy_ceiling_gbs": e2e_ceiling_gbs,
+                        "frac_of_copy_ceiling": e2e_value / e2e_ceiling,
                         "note": "blocking dynoed_eval_batch calls on host buffers, alternate steps on two "
                                 "host threads (one ctx each); PCIe-bound"},
-                "gpu_launches": int(launches), "clocks": clocks, "sub_metrics": sub}
+                "gpu_launches": int(launches), "clocks": clocks, "sub_metrics": sub,
+                "argmin_verified": argmin_verified,
+                # BASELINE config 5, strong scaling: the WHOLE 1,048,576-design sweep split over the GPUs,
+                # incl. selection and the one host read (median of 7 sweeps, slowest rank); winner verified
+                "multistart_1M_ms": multistart_ms, "multistart_1M_designs_per_s": MULTISTART_N / (multistart_ms * 1e-3),
+                "multistart_winner_verified": True}
+        for key, v in sub.items():                           # flat copies: nested objects do not survive the driver's parser
+            if "designs_per_s_per_gpu" in v:
+                line[f"sub_{key}_designs_per_s"] = v["designs_per_s_per_gpu"]
+                line[f"sub_{key}_frac_fp64"] = v["tflops"] / peak
+        if "single_design_host_call" in sub:
+            line["single_design_objective_gradient_us"] = sub["single_design_host_call"]["objective_gradient_us"]
+            line["single_design_hessian_us"] = sub["single_design_host_call"]["hessian_us"]
+        line["e2e_objective_only_designs_per_s"] = e2e_objective_only
+        line["e2e_frac_of_copy_ceiling"] = e2e_value / e2e_ceiling
         if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only
-            orc, threads = cpu_oracle()
+            orc, threads, cflags = cpu_oracle()
             v, ns, dt = time_cpu(orc, threads, make_designs(4 * N_PER_GPU, 71, 20262), 20.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{ns} designs of the same workload (same generator), "
-                                              f"criterion + full forward-mode gradient, {dt:.1f} s"}
+                                              f"criterion + full forward-mode gradient, {dt:.1f} s",
+                                    "cpu_algorithm": CPU_ALGORITHM, "build_flags": cflags}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

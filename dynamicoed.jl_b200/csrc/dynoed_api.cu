@@ -199,8 +199,9 @@ static ModelEntry make_entry() {
     i.n_theta = M::NTH; i.nz = M::NZ; i.nF = M::NF;
     for (int k = 0; k < M::NIC; ++k) i.ic_state[k] = M::ic_state(k);
     i.autonomous = M::AUTONOMOUS ? 1 : 0;
-    i.flops_primal = M::FLOPS_PRIMAL; i.flops_primal_z = M::FLOPS_PRIMAL_Z;
+    i.flops_primal_z = M::FLOPS_PRIMAL_Z;
     i.flops_adjoint = M::FLOPS_ADJOINT; i.flops_consts = M::FLOPS_CONSTS; i.flops_ros_f = M::FLOPS_ROS_F;
+    i.flops_primal = M::FLOPS_PRIMAL_Z + M::FLOPS_OBS;
     for (int k = 0; k < M::NX; ++k) i.x0[k] = M::default_x0()[k];
     for (int k = 0; k < M::NX * M::NP; ++k) i.G0[k] = M::default_G0()[k];
     for (int k = 0; k < M::NTH; ++k) i.theta[k] = M::default_theta()[k];
@@ -319,6 +320,14 @@ struct dynoed_ctx {
     long long* d_ring = nullptr;       // [kRing][2]: the same record for the last kRing batches
     int64_t batch_seq = 0;             // batches evaluated so far (ring slot = seq % kRing)
     unsigned int* d_ticket = nullptr;  // [2]
+    unsigned long long* d_guard = nullptr;   // [2][4]: scratch-set owner serial, waits, timed-out waits (scratch_acquire)
+    unsigned long long call_serial = 0;      // serial of the most recent evaluation call (> 0)
+    uint32_t call_flags = 0;                 // flags of the call being served
+    std::vector<int> h_first;                // host copy of first_step[N+1]
+    size_t l2_bytes = 0;
+    double l2_hot_frac = 0.5;                // share of L2 the top of the checkpoint stack may occupy
+    cudaStream_t aux_stream = nullptr;       // selection helpers run here when set (dynoed_set_aux_stream)
+    cudaEvent_t ev_aux = nullptr;
     struct HessScratch {               // dynoed_hessian_batch: perturbed batch + staging, grown on demand
         double *pert = nullptr, *pcrit = nullptr, *pgrad = nullptr, *x = nullptr, *c = nullptr, *g = nullptr, *H = nullptr;
         int64_t cap = 0;               // designs per chunk the buffers hold
@@ -417,7 +426,7 @@ static size_t traj_bytes_for(const dynoed_ctx* ctx, int grid, int kidx = 1) {
     const auto& mi = ctx->model->info;
     const size_t per_lane = (ctx->rosenbrock || kidx == 2)
                                 ? (size_t)ctx->n_intervals * mi.n_obs * mi.nF + ctx->base.n_ctrl_values
-                                : (size_t)ctx->n_steps * mi.nz;
+                                : (size_t)ctx->n_steps * mi.nz + (size_t)ctx->n_intervals * mi.n_obs * mi.nF;
     return (size_t)grid * per_lane * kMaxTile * sizeof(double);
 }
 
@@ -593,6 +602,11 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     CUC(cudaMemset(ctx->d_ring, 0xff, 2 * kRing * sizeof(long long)));
     CUC(cudaMalloc(&ctx->d_ticket, 2 * sizeof(unsigned int)));
     CUC(cudaMemset(ctx->d_ticket, 0, 2 * sizeof(unsigned int)));
+    CUC(cudaMalloc(&ctx->d_guard, 8 * sizeof(unsigned long long)));
+    CUC(cudaMemset(ctx->d_guard, 0, 8 * sizeof(unsigned long long)));
+    ctx->h_first = first;
+    ctx->l2_bytes = (size_t)prop.l2CacheSize;
+    if (const char* hf = getenv("DYNOED_L2_HOT_FRAC")) ctx->l2_hot_frac = std::min(4.0, std::max(0.0, atof(hf)));
     ctx->pdl_enabled = !getenv("DYNOED_NO_PDL");
     {   // direction-parallel small-batch kernel: its quadrature scratch must fit what a launch owns anyway
         int nvals = 0;
@@ -661,7 +675,8 @@ void dynoed_destroy(dynoed_ctx* ctx) {
     }
     cudaFree(ctx->d_first_step); cudaFree(ctx->d_step_t); cudaFree(ctx->d_step_h); cudaFree(ctx->d_indicators);
     for (int q = 0; q < 2; ++q) { cudaFree(ctx->traj[q]); cudaFree(ctx->part_val[q]); cudaFree(ctx->part_idx[q]); if (ctx->call_done[q]) cudaEventDestroy(ctx->call_done[q]); }
-    cudaFree(ctx->d_best); cudaFree(ctx->d_ring); cudaFree(ctx->d_ticket);
+    cudaFree(ctx->d_best); cudaFree(ctx->d_ring); cudaFree(ctx->d_ticket); cudaFree(ctx->d_guard);
+    if (ctx->ev_aux) cudaEventDestroy(ctx->ev_aux);
     cudaFree(ctx->hs.pert); cudaFree(ctx->hs.pcrit); cudaFree(ctx->hs.pgrad); cudaFree(ctx->hs.x); cudaFree(ctx->hs.c); cudaFree(ctx->hs.g); cudaFree(ctx->hs.H);
     if (ctx->ev_k0) { cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1); }
     if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
@@ -679,8 +694,10 @@ int dynoed_set_criterion(dynoed_ctx* ctx, int criterion) {
 
 int dynoed_set_stream(dynoed_ctx* ctx, void* s) {
     if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    if (ctx->stream == (cudaStream_t)s) return DYNOED_OK;   // unchanged: keeps the overlap bookkeeping
     // the ctx's scratch is ordered by its stream: drain the old one before work moves to another
-    if (ctx->stream != (cudaStream_t)s) { CU(cudaSetDevice(ctx->device)); CU(cudaStreamSynchronize(ctx->stream)); }
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
     ctx->stream = (cudaStream_t)s;   // NULL is the CUDA legacy default stream
     ctx->prev.valid = false;
     return DYNOED_OK;
@@ -730,6 +747,32 @@ static bool ranges_overlap(const char* a0, const char* a1, const char* b0, const
     return a0 && b0 && a0 < b1 && b0 < a1;
 }
 
+// How much of the checkpoint stack stays in L2 (see the CkptPolicy comment in dynoed_kernels.cuh):
+// the top `hot` steps of every resident lane, sized so that all resident lanes together use
+// l2_hot_frac of the L2.
+static void set_scratch_params(dynoed_ctx* ctx, EvalParams& P, int par, int kidx) {
+    const auto& mi = ctx->model->info;
+    P.guard = ctx->d_guard + 4 * par;
+    P.serial = ctx->call_serial;
+    const double lanes = (double)ctx->sm_count * std::max(ctx->bps[kidx], 1) * kMaxTile;
+    const double per_step = 8.0 * (mi.nz + (double)mi.n_obs * mi.nF * ctx->n_intervals / std::max(ctx->n_steps, 1));
+    int hot = (int)((double)ctx->l2_bytes * ctx->l2_hot_frac / (lanes * per_step));
+    hot = std::max(0, std::min(hot, ctx->n_steps));
+    P.hot_step = ctx->n_steps - hot;
+    P.hot_interval = ctx->n_intervals;
+    for (int j = 0; j < ctx->n_intervals; ++j)
+        if (ctx->h_first[j] >= P.hot_step) { P.hot_interval = j; break; }
+}
+
+// after a failed call the scratch set may be left acquired / the ticket partially counted: drain and clear
+static void reset_parity(dynoed_ctx* ctx, int par) {
+    cudaDeviceSynchronize();
+    cudaGetLastError();
+    cudaMemset(ctx->d_ticket + par, 0, sizeof(unsigned int));
+    cudaMemset(ctx->d_guard + 4 * par, 0, sizeof(unsigned long long));
+    ctx->prev.valid = false;
+}
+
 // launch on device-resident buffers
 static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad,
                          double* fim, double* xgrid, int par, int grid, cudaStream_t st) {
@@ -741,16 +784,20 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
     P.part_base = 0; P.n_parts = grid; P.ticket_target = (unsigned int)grid;
     P.ticket = ctx->d_ticket + par; P.best_val = reinterpret_cast<double*>(ctx->d_best + 2 * par); P.best_idx = ctx->d_best + 2 * par + 1;
     P.ring_rec = ctx->d_ring + 2 * (ctx->batch_seq % kRing);
+    set_scratch_params(ctx, P, par, grad ? ctx->kidx_req : 0);
     P.use_tma = ((reinterpret_cast<uintptr_t>(designs) % 16 == 0) &&
                  (grad == nullptr || reinterpret_cast<uintptr_t>(grad) % 16 == 0) &&
                  (((size_t)ctx->tile * ctx->n_var * 8) % 16 == 0)) ? 1 : 0;
-    // May this launch start while the previous one drains?  Only if both fill the whole GPU with
-    // the same kernel (then launch k+1 cannot start before launch k-1 has left the SMs, and two
-    // scratch sets suffice), on the same stream, and their buffers are disjoint.
+    // May this launch start while the previous one drains (programmatic dependent launch)?  Only if
+    // the caller opted in (DYNOED_OVERLAP_OK: no kernel enqueued after the previous launch produces
+    // this launch's inputs — the kernels do not execute griddepcontrol.wait), both launches are the
+    // same kernel of this context on the same stream, and their buffers are disjoint.  The two
+    // scratch sets alternate; the scratch-set guard (scratch_acquire) keeps launch k+2 off the set
+    // of launch k until k has finished, whatever the grid sizes.
     dynoed_ctx::Prev cur;
-    cur.valid = xgrid == nullptr;
     cur.kidx = grad ? ctx->kidx_req : 0;
     const bool dirpar = grad && !xgrid && dir_eligible(ctx, n, cur.kidx);
+    cur.valid = xgrid == nullptr && !dirpar;
     if (dirpar) P.use_tma = 0;
     cur.full = !dirpar && grid == ctx->sm_count * std::max(ctx->bps[cur.kidx], 1);
     cur.stream = st;
@@ -759,7 +806,7 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
     cur.out0[1] = (const char*)grad; cur.out1[1] = grad ? cur.out0[1] + sizeof(double) * n * ctx->n_var : nullptr;
     cur.out0[2] = (const char*)fim; cur.out1[2] = fim ? cur.out0[2] + sizeof(double) * n * mi.nF : nullptr;
     const dynoed_ctx::Prev& pv = ctx->prev;
-    bool pdl = ctx->pdl_enabled && !ctx->profiling && cur.valid && pv.valid && cur.full && pv.full &&
+    bool pdl = ctx->pdl_enabled && (ctx->call_flags & DYNOED_OVERLAP_OK) && !ctx->profiling && cur.valid && pv.valid &&
                cur.kidx == pv.kidx && cur.stream == pv.stream && stream_last_serial(st) == pv.serial;
     for (int a = 0; pdl && a < 3; ++a) {
         if (ranges_overlap(cur.in0, cur.in1, pv.out0[a], pv.out1[a])) pdl = false;      // RAW
@@ -809,8 +856,9 @@ static int eval_device(dynoed_ctx* ctx, const double* designs, int64_t n, double
     }
     int rc = ensure_partials(ctx, grid, par);
     if (rc) return rc;
+    ctx->call_serial++;
     rc = launch_device(ctx, designs, n, crit, grad, fim, xgrid, par, grid, ctx->stream);
-    if (rc) return rc;
+    if (rc) { reset_parity(ctx, par); return rc; }
     ctx->last_parity = par;
     ctx->parity = par ^ 1;
     ctx->batch_seq++;
@@ -983,53 +1031,62 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         zc_fim = fim ? dev(staged ? s0.h_fim : fim) : nullptr;
         small_zc = zc_in && zc_crit && zc_grad && (!fim || zc_fim);
     }
-    int part_base = 0;
-    for (int64_t c = 0; c < nchunks; ++c) {
-        Slot& s = ctx->slots[c % kSlots];
-        const int64_t off = bounds[c], cnt = bounds[c + 1] - bounds[c];
-        const double* h_src = designs + off * ctx->n_var;
-        if (staged) {
-            if (c >= kSlots) { rc = drain(c - kSlots); if (rc) return rc; }   // frees this slot's staging
-            if (small_zc) memcpy(s.h_designs, h_src, sizeof(double) * cnt * ctx->n_var);
-            else parallel_memcpy(s.h_designs, h_src, sizeof(double) * cnt * ctx->n_var);
-            h_src = s.h_designs;
+    ctx->call_serial++;
+    // everything that launches: a failure part-way leaves the ticket partially counted and the scratch set
+    // acquired, so the error path drains the device and clears both (reset_parity)
+    auto enqueue = [&]() -> int {
+        int part_base = 0;
+        for (int64_t c = 0; c < nchunks; ++c) {
+            Slot& s = ctx->slots[c % kSlots];
+            const int64_t off = bounds[c], cnt = bounds[c + 1] - bounds[c];
+            const double* h_src = designs + off * ctx->n_var;
+            if (staged) {
+                if (c >= kSlots) { rc = drain(c - kSlots); if (rc) return rc; }   // frees this slot's staging
+                if (small_zc) memcpy(s.h_designs, h_src, sizeof(double) * cnt * ctx->n_var);
+                else parallel_memcpy(s.h_designs, h_src, sizeof(double) * cnt * ctx->n_var);
+                h_src = s.h_designs;
+            }
+            if (!small_zc)
+                CU(cudaMemcpyAsync(s.d_designs, h_src, sizeof(double) * cnt * ctx->n_var, cudaMemcpyHostToDevice, s.stream));
+            EvalParams P = ctx->base;
+            const int grid = grid_for(ctx, cnt, kidx);
+            P.designs = s.d_designs; P.crit = crit_map ? crit_map + off : s.d_crit; P.grad = g ? s.d_grad : nullptr;
+            P.fim = !fim ? nullptr : fim_map ? fim_map + off * nF : s.d_fim;
+            if (small_zc) {   // the kernel reads the rows from, and stores every result into, page-locked host memory
+                P.designs = zc_in; P.crit = zc_crit; P.grad = zc_grad; P.fim = fim ? zc_fim : nullptr;
+            }
+            P.xgrid = nullptr; P.traj = s.traj; P.n = cnt;
+            P.part_val = ctx->part_val[par]; P.part_idx = ctx->part_idx[par];
+            P.part_base = part_base; P.n_parts = total_parts; P.ticket_target = (unsigned int)total_parts;
+            P.ticket = ctx->d_ticket + par; P.best_val = reinterpret_cast<double*>(ctx->d_best + 2 * par); P.best_idx = ctx->d_best + 2 * par + 1;
+            P.ring_rec = ctx->d_ring + 2 * (ctx->batch_seq % kRing);
+            set_scratch_params(ctx, P, par, kidx);
+            part_base += grid;
+            const bool dirpar = g && dir_eligible(ctx, cnt, kidx);
+            P.use_tma = (!dirpar && ((size_t)ctx->tile * ctx->n_var * 8) % 16 == 0) ? 1 : 0;
+            P.index_base = off;
+            CU(ctx->model->launch(method_code(ctx, kidx) | (dirpar ? kDirPar : 0), g, ctx->ucoef, false, P, grid, ctx->tile,
+                                  smem_bytes(ctx), s.stream));
+            ctx->launches++;
+            ctx->dir_launches += dirpar ? 1 : 0;
+            double* o_crit = staged ? s.h_crit : crit + off;
+            double* o_grad = staged ? s.h_grad : (g ? grad + off * ctx->n_var : nullptr);
+            double* o_fim = staged ? s.h_fim : (fim ? fim + off * nF : nullptr);
+            if (!crit_map && !small_zc) CU(cudaMemcpyAsync(o_crit, s.d_crit, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s.stream));
+            if (g && !small_zc) CU(cudaMemcpyAsync(o_grad, s.d_grad, sizeof(double) * cnt * ctx->n_var, cudaMemcpyDeviceToHost, s.stream));
+            if (fim && !fim_map && !small_zc) CU(cudaMemcpyAsync(o_fim, s.d_fim, sizeof(double) * cnt * nF, cudaMemcpyDeviceToHost, s.stream));
+            if (staged) CU(cudaEventRecord(s.done, s.stream));
         }
-        if (!small_zc)
-            CU(cudaMemcpyAsync(s.d_designs, h_src, sizeof(double) * cnt * ctx->n_var, cudaMemcpyHostToDevice, s.stream));
-        EvalParams P = ctx->base;
-        const int grid = grid_for(ctx, cnt, kidx);
-        P.designs = s.d_designs; P.crit = crit_map ? crit_map + off : s.d_crit; P.grad = g ? s.d_grad : nullptr;
-        P.fim = !fim ? nullptr : fim_map ? fim_map + off * nF : s.d_fim;
-        if (small_zc) {   // the kernel reads the rows from, and stores every result into, page-locked host memory
-            P.designs = zc_in; P.crit = zc_crit; P.grad = zc_grad; P.fim = fim ? zc_fim : nullptr;
+        if (staged)
+            for (int64_t c = std::max<int64_t>(0, nchunks - kSlots); c < nchunks; ++c) { rc = drain(c); if (rc) return rc; }
+        for (int k = 0; k < kSlots && k < nchunks; ++k) {
+            CU(cudaEventRecord(ev, ctx->slots[k].stream));
+            CU(cudaStreamWaitEvent(ctx->stream, ev, 0));
         }
-        P.xgrid = nullptr; P.traj = s.traj; P.n = cnt;
-        P.part_val = ctx->part_val[par]; P.part_idx = ctx->part_idx[par];
-        P.part_base = part_base; P.n_parts = total_parts; P.ticket_target = (unsigned int)total_parts;
-        P.ticket = ctx->d_ticket + par; P.best_val = reinterpret_cast<double*>(ctx->d_best + 2 * par); P.best_idx = ctx->d_best + 2 * par + 1;
-        P.ring_rec = ctx->d_ring + 2 * (ctx->batch_seq % kRing);
-        part_base += grid;
-        const bool dirpar = g && dir_eligible(ctx, cnt, kidx);
-        P.use_tma = (!dirpar && ((size_t)ctx->tile * ctx->n_var * 8) % 16 == 0) ? 1 : 0;
-        P.index_base = off;
-        CU(ctx->model->launch(method_code(ctx, kidx) | (dirpar ? kDirPar : 0), g, ctx->ucoef, false, P, grid, ctx->tile,
-                              smem_bytes(ctx), s.stream));
-        ctx->launches++;
-        ctx->dir_launches += dirpar ? 1 : 0;
-        double* o_crit = staged ? s.h_crit : crit + off;
-        double* o_grad = staged ? s.h_grad : (g ? grad + off * ctx->n_var : nullptr);
-        double* o_fim = staged ? s.h_fim : (fim ? fim + off * nF : nullptr);
-        if (!crit_map && !small_zc) CU(cudaMemcpyAsync(o_crit, s.d_crit, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s.stream));
-        if (g && !small_zc) CU(cudaMemcpyAsync(o_grad, s.d_grad, sizeof(double) * cnt * ctx->n_var, cudaMemcpyDeviceToHost, s.stream));
-        if (fim && !fim_map && !small_zc) CU(cudaMemcpyAsync(o_fim, s.d_fim, sizeof(double) * cnt * nF, cudaMemcpyDeviceToHost, s.stream));
-        if (staged) CU(cudaEventRecord(s.done, s.stream));
-    }
-    if (staged)
-        for (int64_t c = std::max<int64_t>(0, nchunks - kSlots); c < nchunks; ++c) { rc = drain(c); if (rc) return rc; }
-    for (int k = 0; k < kSlots && k < nchunks; ++k) {
-        CU(cudaEventRecord(ev, ctx->slots[k].stream));
-        CU(cudaStreamWaitEvent(ctx->stream, ev, 0));
-    }
+        return DYNOED_OK;
+    };
+    rc = enqueue();
+    if (rc) { reset_parity(ctx, par); return rc; }
     CU(cudaEventRecord(ctx->call_done[par], ctx->stream));   // fires when every chunk of THIS call has landed
     ctx->host_seq++;
     ctx->call_of_parity[par] = ctx->host_seq;
@@ -1050,6 +1107,7 @@ static int eval_common(dynoed_ctx* ctx, const double* designs, int64_t n, double
     if (n == 0) { ctx->have_batch = false; return DYNOED_OK; }
     if (!designs || !crit) return fail(ctx, DYNOED_EINVAL, "designs/crit is NULL");
     ctx->kidx_req = kernel_index(ctx, grad != nullptr, flags);
+    ctx->call_flags = flags;
     CU(cudaSetDevice(ctx->device));
     const int kd = ptr_kind(designs);
     if (ptr_kind(crit) != kd || (grad && ptr_kind(grad) != kd) || (fim && ptr_kind(fim) != kd))
@@ -1140,6 +1198,25 @@ int dynoed_argmin_record_async(dynoed_ctx* ctx, void* d_record) {
     return DYNOED_OK;
 }
 
+int dynoed_set_aux_stream(dynoed_ctx* ctx, void* s) {
+    if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    ctx->aux_stream = (cudaStream_t)s;
+    return DYNOED_OK;
+}
+
+// the stream the ring-reading selection helpers run on: the aux stream (ordered after every evaluation
+// enqueued so far by an event — an event record does not break the launches' overlap, a kernel or copy
+// on the evaluation stream would) or, without one, the ctx stream itself
+static int ring_reader_stream(dynoed_ctx* ctx, cudaStream_t* out) {
+    *out = ctx->stream;
+    if (!ctx->aux_stream || ctx->aux_stream == ctx->stream) return DYNOED_OK;
+    if (!ctx->ev_aux) CU(cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming));
+    CU(cudaEventRecord(ctx->ev_aux, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_aux, 0));
+    *out = ctx->aux_stream;
+    return DYNOED_OK;
+}
+
 int dynoed_argmin_history_async(dynoed_ctx* ctx, int count, void* d_records) {
     if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
     if (count < 1 || count > kRing || (int64_t)count > ctx->batch_seq)
@@ -1149,10 +1226,58 @@ int dynoed_argmin_history_async(dynoed_ctx* ctx, int count, void* d_records) {
     const int s0 = (int)(first % kRing);
     const int n0 = std::min(count, kRing - s0);            // up to the end of the ring, then wrap
     char* dst = reinterpret_cast<char*>(d_records);
-    CU(cudaMemcpyAsync(dst, ctx->d_ring + 2 * s0, (size_t)n0 * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+    cudaStream_t st;
+    int rc = ring_reader_stream(ctx, &st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(dst, ctx->d_ring + 2 * s0, (size_t)n0 * 16, cudaMemcpyDeviceToDevice, st));
     if (n0 < count)
-        CU(cudaMemcpyAsync(dst + (size_t)n0 * 16, ctx->d_ring, (size_t)(count - n0) * 16, cudaMemcpyDeviceToDevice,
-                           ctx->stream));
+        CU(cudaMemcpyAsync(dst + (size_t)n0 * 16, ctx->d_ring, (size_t)(count - n0) * 16, cudaMemcpyDeviceToDevice, st));
+    if (st == ctx->stream) ctx->prev.valid = false;
+    return DYNOED_OK;
+}
+
+int dynoed_pack_winner(dynoed_ctx* ctx, int nbatches, const double* designs, const double* grad, int64_t n_local,
+                       int64_t batch_stride, int64_t index_base, double* d_payload) {
+    if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    if (nbatches < 0 || nbatches > kRing || (int64_t)nbatches > ctx->batch_seq)
+        return fail(ctx, DYNOED_EINVAL, "nbatches must be 0..64 and not exceed the batches evaluated so far");
+    if (!d_payload || (nbatches > 0 && !designs) || n_local < 0 || batch_stride < 1)
+        return fail(ctx, DYNOED_EINVAL, "bad arguments");
+    if (ptr_kind(d_payload) != 1 || (designs && ptr_kind(designs) != 1) || (grad && ptr_kind(grad) != 1))
+        return fail(ctx, DYNOED_EINVAL, "dynoed_pack_winner needs device pointers");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st;
+    int rc = ring_reader_stream(ctx, &st);
+    if (rc) return rc;
+    const int s0 = (int)((ctx->batch_seq - nbatches) % kRing);
+    pack_winner_kernel<<<1, kSelThreads, 0, st>>>(ctx->d_ring, kRing, s0, nbatches, (long long)batch_stride,
+                                                  (long long)index_base, (long long)n_local, designs, grad, ctx->n_var, d_payload);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    if (st == ctx->stream) ctx->prev.valid = false;
+    return DYNOED_OK;
+}
+
+int dynoed_select_winner(dynoed_ctx* ctx, const double* d_gathered, int world, double* d_out) {
+    if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    if (!d_gathered || !d_out || world < 1 || world > 65536) return fail(ctx, DYNOED_EINVAL, "bad arguments");
+    if (ptr_kind(d_gathered) != 1 || ptr_kind(d_out) != 1) return fail(ctx, DYNOED_EINVAL, "dynoed_select_winner needs device pointers");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->aux_stream ? ctx->aux_stream : ctx->stream;
+    select_winner_kernel<<<1, kSelThreads, 0, st>>>(d_gathered, world, 2 + 2 * ctx->n_var, d_out);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    if (st == ctx->stream) ctx->prev.valid = false;
+    return DYNOED_OK;
+}
+
+int dynoed_guard_stats(dynoed_ctx* ctx, int64_t* waits, int64_t* timeouts) {
+    if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
+    CU(cudaSetDevice(ctx->device));
+    unsigned long long g[8];
+    CU(cudaMemcpy(g, ctx->d_guard, sizeof(g), cudaMemcpyDeviceToHost));   // synchronises with all prior work
+    if (waits) *waits = (int64_t)(g[1] + g[5]);
+    if (timeouts) *timeouts = (int64_t)(g[2] + g[6]);
     return DYNOED_OK;
 }
 
@@ -1162,10 +1287,12 @@ int dynoed_argmin_gathered(dynoed_ctx* ctx, const void* d_records, int world, in
     if (!d_records || !d_out || world < 1 || world > 1024 || groups < 1 || groups > 65535)
         return fail(ctx, DYNOED_EINVAL, "bad arguments");
     CU(cudaSetDevice(ctx->device));
-    argmin_records_kernel<<<groups, 32, 0, ctx->stream>>>(reinterpret_cast<const long long*>(d_records), world, groups,
-                                                          (long long)shard_size, reinterpret_cast<long long*>(d_out));
+    cudaStream_t st = ctx->aux_stream ? ctx->aux_stream : ctx->stream;
+    argmin_records_kernel<<<groups, 32, 0, st>>>(reinterpret_cast<const long long*>(d_records), world, groups,
+                                                 (long long)shard_size, reinterpret_cast<long long*>(d_out));
     CU(cudaGetLastError());
     ctx->launches++;
+    if (st == ctx->stream) ctx->prev.valid = false;
     return DYNOED_OK;
 }
 
@@ -1201,22 +1328,27 @@ int dynoed_trajectory(dynoed_ctx* ctx, const double* designs, int64_t n, double*
     const int kd = ptr_kind(designs);
     if (ptr_kind(X) != kd) return fail(ctx, DYNOED_EINVAL, "designs/X must both be host or both be device pointers");
     double *dd = nullptr, *dx = nullptr, *dc = nullptr;
-    CU(cudaMalloc(&dc, sizeof(double) * n));
+    auto cleanup = [&]() { cudaFree(dd); cudaFree(dx); cudaFree(dc); };
+#define CUT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); \
+        return fail(ctx, DYNOED_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+    ctx->call_flags = 0;
+    CUT(cudaMalloc(&dc, sizeof(double) * n));
     int rc;
     if (kd == 1) {
         rc = eval_device(ctx, designs, n, dc, nullptr, nullptr, X);
-        if (!rc) CU(cudaStreamSynchronize(ctx->stream));
+        if (!rc) CUT(cudaStreamSynchronize(ctx->stream));
     } else {
-        CU(cudaMalloc(&dd, sizeof(double) * n * ctx->n_var));
-        CU(cudaMalloc(&dx, sizeof(double) * n * row));
-        CU(cudaMemcpyAsync(dd, designs, sizeof(double) * n * ctx->n_var, cudaMemcpyHostToDevice, ctx->stream));
+        CUT(cudaMalloc(&dd, sizeof(double) * n * ctx->n_var));
+        CUT(cudaMalloc(&dx, sizeof(double) * n * row));
+        CUT(cudaMemcpyAsync(dd, designs, sizeof(double) * n * ctx->n_var, cudaMemcpyHostToDevice, ctx->stream));
         rc = eval_device(ctx, dd, n, dc, nullptr, nullptr, dx);
         if (!rc) {
-            CU(cudaMemcpyAsync(X, dx, sizeof(double) * n * row, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
+            CUT(cudaMemcpyAsync(X, dx, sizeof(double) * n * row, cudaMemcpyDeviceToHost, ctx->stream));
+            CUT(cudaStreamSynchronize(ctx->stream));
         }
     }
-    cudaFree(dd); cudaFree(dx); cudaFree(dc);
+#undef CUT
+    cleanup();
     return rc;
 }
 
@@ -1247,6 +1379,7 @@ int dynoed_information_gain(dynoed_ctx* ctx, const double* designs, int64_t n, d
         if (Pl) CUI(cudaMalloc(&dP, sizeof(double) * n * prow));
         if (Pi) CUI(cudaMalloc(&dPi, sizeof(double) * n * prow));
     } else { dP = Pl; dPi = Pi; }
+    ctx->call_flags = 0;
     rc = eval_device(ctx, ddes, n, dc, nullptr, dF, dx);     // trajectory at the grid points + F(t_f)
     if (rc) { cleanup(); return rc; }
     EvalParams P = ctx->base;
@@ -1297,6 +1430,7 @@ int dynoed_hessian_batch(dynoed_ctx* ctx, const double* designs, int64_t n, doub
     }
     cudaStream_t st = ctx->stream;
     ctx->kidx_req = 1;
+    ctx->call_flags = 0;
     ctx->prev.valid = false;
     for (int64_t o = 0; o < n; o += chunk) {
         const int64_t m = std::min(chunk, n - o);
@@ -1532,31 +1666,41 @@ int dynoed_kernel_stats_query(dynoed_ctx* ctx, int with_grad, dynoed_kernel_stat
     o->scratch_bytes = (int64_t)ctx->scratch_bytes;
     o->n_steps = ctx->n_steps;
     o->stages = ctx->stages;
-    // algorithmic flops of the straight-line code the emitter produced (FMA = 2):
-    //   forward step : S primal calls + stage states (2 NZ per non-zero a_ij) + accumulation
-    //                  (2 (NZ + NF) per stage) + h*a / h*b products
-    //   backward step: (S-1) primal_z + S adjoint calls + stage states + kb / lambda / w-bar updates
+    // algorithmic flops of the straight-line code the emitter produced plus the template's own
+    // arithmetic (FMA = 2, mul/add = 1):
+    //   forward step : S x (primal_z + obs) + stage states (2 NZ per non-zero a_ij) + z accumulation
+    //                  (2 NZ per stage) + unweighted quadrature accumulation (2 NOBS NF per stage, plus
+    //                  NOBS NP scalings for every stage with b_s != b_0)
+    //   per interval : P = (h b_0) acc, F += w P (3 NOBS NF), consts
+    //   backward step: (S-1) primal_z + S adjoint + stage states + kb' (2 NZ per a_ij each) +
+    //                  lambda / u-bar accumulation (2 per entry and stage)
+    //   per interval : cwL = 2 w L (NOBS (1 + NF)), d/dw = <Lambda, P> (2 NOBS NF), consts
     const int S = ctx->stages;
-    int nza = 0;
-    for (int i = 0; i < S; ++i)
+    int nza = 0, nscaled = 0;
+    for (int i = 0; i < S; ++i) {
+        const double bi = ctx->method == DYNOED_RK4 ? TabRK4::b(i) : TabTsit5::b(i);
+        const double b0 = ctx->method == DYNOED_RK4 ? TabRK4::b(0) : TabTsit5::b(0);
+        nscaled += (bi / b0 != 1.0);
         for (int j = 0; j < i; ++j)
             nza += (ctx->method == DYNOED_RK4 ? TabRK4::a(i, j) : TabTsit5::a(i, j)) != 0.0;
-    const double fwd = (double)S * mi.flops_primal + 2.0 * mi.nz * nza + 2.0 * (mi.nz + mi.nF) * S + nza + S;
-    //   backward step: (S-1) primal_z + S adjoint calls + stage states (2 NZ per a_ij) + kb'
-    //                  (2 NZ per a_ij) + lambda / u-bar / w-bar accumulation (2 per entry and stage)
-    const double bwd = (double)(S - 1) * mi.flops_primal_z + (double)S * mi.flops_adjoint + 2.0 * mi.nz * nza +
-                       2.0 * mi.nz * nza + 2.0 * S * (mi.nz + mi.n_obs + mi.n_ctrl) + 2.0 * nza + S;
+    }
+    const int nq = mi.n_obs * mi.nF;
+    const double fwd = (double)S * mi.flops_primal + 2.0 * mi.nz * nza + 2.0 * mi.nz * S + 2.0 * nq * S +
+                       (double)nscaled * mi.n_obs * mi.np + (ctx->ucoef ? 0.0 : 2.0 * nq);
+    const double fwd_iv = (ctx->ucoef ? 3.0 : 2.0) * nq + mi.flops_consts;
+    const double bwd = (double)(S - 1) * mi.flops_primal_z + (double)S * mi.flops_adjoint + 4.0 * mi.nz * nza +
+                       2.0 * S * (mi.nz + mi.n_ctrl);
+    const double bwd_iv = (double)mi.n_obs * (1 + mi.nF) + 2.0 * nq + mi.flops_consts;
     const double epi = 10.0 * mi.nF;
     if (ctx->rosenbrock) {   // no frozen flop count for the Rosenbrock kernels (not a roofline-reported path)
         o->flops_per_design_eval = o->flops_per_design_grad = 0.0;
         o->bytes_per_design = 8.0 * (ctx->n_var + 1 + (with_grad ? ctx->n_var : 0) + mi.nF);
         return DYNOED_OK;
     }
-    o->flops_per_design_eval = fwd * ctx->n_steps + (double)ctx->n_intervals * mi.flops_consts + epi;
-    o->flops_per_design_grad = (fwd + bwd) * ctx->n_steps + 2.0 * ctx->n_intervals * mi.flops_consts + epi;
+    o->flops_per_design_eval = fwd * ctx->n_steps + (double)ctx->n_intervals * fwd_iv + epi;
+    o->flops_per_design_grad = (fwd + bwd) * ctx->n_steps + (double)ctx->n_intervals * (fwd_iv + bwd_iv) + epi;
     if (g == 2) {   // forward-only gradient: unweighted per-observation quadratures, F += w P per interval,
                     // d/dw = <Lambda, P> in the epilogue
-        const int nq = mi.n_obs * mi.nF;
         const double f2 = (double)S * mi.flops_ros_f + 2.0 * mi.nz * nza + 2.0 * (mi.nz + nq) * S + nza + S;
         o->flops_per_design_grad = f2 * ctx->n_steps + (double)ctx->n_intervals * (mi.flops_consts + 4.0 * nq) + epi;
     }

@@ -86,6 +86,13 @@ struct EvalParams {
     double* __restrict__ best_val;
     long long* __restrict__ best_idx;
     long long* __restrict__ ring_rec;     // history slot of this batch: {value bits, index} (or nullptr)
+    // scratch-set guard: guard[0] = serial of the call that owns this scratch set (0 = free),
+    // guard[1] = CTAs that had to wait for it, guard[2] = waits that timed out (see scratch_acquire)
+    unsigned long long* __restrict__ guard;
+    unsigned long long serial;            // this call's serial (> 0)
+    // checkpoints of steps >= hot_step and quadratures of intervals >= hot_interval are kept in L2
+    int hot_step;
+    int hot_interval;
     // Runge-Kutta factors of the single step size of a uniform grid (UCOEF kernels)
     double coef[kCoefStride];
 };
@@ -207,6 +214,38 @@ __device__ __forceinline__ double ld_pinned(const double* p) {
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+// L2 residency control for the checkpoint stack.  The forward sweep pushes (x, G) of every step and
+// the backward sweep pops them in reverse order, so the LAST pushes are the FIRST pops; the whole
+// stack of all resident lanes (409 MB for LV) does not fit the 126 MB L2, and with the default
+// policy every line travels to HBM and back (measured: the checkpoint traffic costs ~35 % of the
+// launch's energy and the kernel runs at the 1 kW cap).  Hot entries (the top of the stack, sized by
+// the host to a fraction of L2) are stored evict_last and DISCARDED after their pop — they never
+// reach HBM; cold entries are stored / loaded evict_first so that they do not push hot lines out.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_hint(double* p, double v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+// not sinkable towards its use, like ld_pinned
+__device__ __forceinline__ double ld_hint(const double* p, uint64_t pol) {
+    double v;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+// the 128-byte line at p (128-byte aligned) is dead: drop it from L2 without write-back
+__device__ __forceinline__ void discard_l2(const void* p) {
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+}
+struct CkptPolicy { uint64_t hot, cold; };
+
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -387,13 +426,21 @@ __device__ __forceinline__ void criterion_eval(const double (&F)[N * (N + 1) / 2
 }
 
 // ----------------------------------------------------------------------------------------------
-// One explicit RK step of the augmented system (forward) and its discrete adjoint (backward)
+// One explicit RK step of the augmented system (forward) and its discrete adjoint (backward).
+//
+// The Fisher rows F' = sum_i w_i (Q_i^T Q_i)_triu (/root/reference/src/augment.jl:223-226) feed
+// nothing back, and w is constant on a merged interval, so the step does not carry F: it adds the
+// UNWEIGHTED stage integrands, scaled by b_s / b_0, to per-observation accumulators
+//     acc_i += sum_s (b_s / b_0) (Q_i(Z_s)^T Q_i(Z_s))_triu ,
+// and the caller folds  P_i = (h b_0) acc_i ,  F += w_i P_i  once per interval (uniform grid) or
+// once per step.  Same Runge-Kutta quadrature as integrating F as a state, 13 -> 8 FP64
+// instructions per stage for LV, and the P_i are exactly d F / d w_i.
 // ----------------------------------------------------------------------------------------------
 template <class M, class Tab>
 __device__ __forceinline__ void rk_forward_step(double t, const double* __restrict__ cf, double (&z)[M::NZ],
-                                                double (&F)[M::NF], const double* u, const double* w,
+                                                double (&acc)[M::NOBS * M::NF], const double* u,
                                                 const double* th, const double* c) {
-    constexpr int S = Tab::S, NZ = M::NZ, NF = M::NF;
+    constexpr int S = Tab::S, NZ = M::NZ, NF = M::NF, NP = M::NP, NOBS = M::NOBS;
     double k[S][NZ];
     double zacc[NZ];
 #pragma unroll
@@ -411,28 +458,38 @@ __device__ __forceinline__ void rk_forward_step(double t, const double* __restri
                 for (int a = 0; a < NZ; ++a) Z[a] = fma(ha, k[j][a], Z[a]);
             }
         }
-        double dF[NF];
-        M::primal(t + Tab::c(s) * cf[coef_h()], Z, u, w, th, c, k[s], dF);
+        const double ts = t + Tab::c(s) * cf[coef_h()];
+        M::primal_z(ts, Z, u, th, c, k[s]);
         const double hb = cf[coef_hb(s)];
 #pragma unroll
         for (int a = 0; a < NZ; ++a) zacc[a] = fma(hb, k[s][a], zacc[a]);
+        double Q[NOBS * NP];
+        M::obs(ts, Z, u, th, c, Q);
+        const double ratio = Tab::b(s) / Tab::b(0);   // folds: the stage loop is fully unrolled
 #pragma unroll
-        for (int a = 0; a < NF; ++a) F[a] = fma(hb, dF[a], F[a]);
+        for (int i = 0; i < NOBS; ++i)
+#pragma unroll
+            for (int a = 0; a < NP; ++a) {
+                const double sq = (ratio == 1.0) ? Q[i * NP + a] : ratio * Q[i * NP + a];
+#pragma unroll
+                for (int b = a; b < NP; ++b)
+                    acc[i * NF + tri(a, b)] = fma(sq, Q[i * NP + b], acc[i * NF + tri(a, b)]);
+            }
     }
 #pragma unroll
     for (int a = 0; a < NZ; ++a) z[a] = zacc[a];
 }
 
-// lam: adjoint of z_{n+1} on entry, of z_n on exit.  ub/wb accumulate d/du and d/dw of the
-// Lambda-weighted objective over this step.  The stage adjoints are carried UNSCALED
-// (zb'_s = zb_s / (h b_s)), which removes the h*b_s*lam products from the dependency chain:
+// lam: adjoint of z_{n+1} on entry, of z_n on exit.  ub accumulates d/du of the Lambda-weighted
+// objective over this step (d/dw comes from the stored interval quadratures, not from here).  The
+// stage adjoints are carried UNSCALED (zb'_s = zb_s / (h b_s)), which removes the h*b_s*lam
+// products from the dependency chain:
 //   kb'_s = lam + sum_{j>s} (h a_js b_j / b_s) zb'_j ,   zb'_s = g_z(Z_s)^T kb'_s + q_z(Z_s) ,
-//   lam_n = lam + sum_s h b_s zb'_s ,  ub += h b_s g_u^T kb'_s ,  wb_i += h b_s q_i(Z_s).
+//   lam_n = lam + sum_s h b_s zb'_s ,  ub += h b_s g_u^T kb'_s .
 template <class M, class Tab>
 __device__ __forceinline__ void rk_adjoint_step(double t, const double* __restrict__ cf, const double (&zn)[M::NZ],
-                                                double (&lam)[M::NZ], const double* u, const double* cw,
-                                                const double* th, const double* c, const double* L,
-                                                double* ub, double* wb) {
+                                                double (&lam)[M::NZ], const double* u, const double* cwL,
+                                                const double* th, const double* c, double* ub) {
     constexpr int S = Tab::S, NZ = M::NZ;
     constexpr int NCU = M::NCTRL > 0 ? M::NCTRL : 1;
     const double h = cf[coef_h()];
@@ -473,10 +530,8 @@ __device__ __forceinline__ void rk_adjoint_step(double t, const double* __restri
                 for (int a = 0; a < NZ; ++a) kb[a] = fma(r, Zb[j][a], kb[a]);
             }
         }
-        double qw[M::NOBS], us[NCU];
-        M::adjoint(t + Tab::c(s) * h, Z[s], u, cw, th, c, L, kb, Zb[s], us, qw);
-#pragma unroll
-        for (int i = 0; i < M::NOBS; ++i) wb[i] = fma(hb, qw[i], wb[i]);
+        double us[NCU];
+        M::adjoint(t + Tab::c(s) * h, Z[s], u, cwL, th, c, kb, Zb[s], us);
 #pragma unroll
         for (int k = 0; k < M::NCTRL; ++k) ub[k] = fma(hb, us[k], ub[k]);
 #pragma unroll
@@ -484,6 +539,40 @@ __device__ __forceinline__ void rk_adjoint_step(double t, const double* __restri
     }
 #pragma unroll
     for (int a = 0; a < NZ; ++a) lam[a] = lacc[a];
+}
+
+// ----------------------------------------------------------------------------------------------
+// Scratch-set guard.  Consecutive device-path launches alternate between two scratch sets
+// (checkpoints, arg-min partials, ticket, result slot) and may overlap through programmatic
+// dependent launch, so launch k+2 can become resident while launch k (same set) still runs when the
+// launches do not fill the GPU.  Every CTA therefore acquires its set before touching it: the
+// owner word is 0 (free) or the serial of the call that holds it; the last CTA of a call releases
+// it after its arg-min reduction.  This cannot deadlock: a dependent grid starts only after every
+// CTA of its predecessor has STARTED, so when CTAs of launch k+2 spin, all CTAs of launch k are
+// already resident or done.  A wait that exceeds 2 s (a lost release after a failed call) is
+// counted in guard[2] and abandoned instead of hanging the device.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void scratch_acquire(const EvalParams& P) {
+    if (threadIdx.x == 0 && P.guard) {
+        unsigned long long old = atomicCAS(P.guard, 0ULL, P.serial);
+        if (old != 0ULL && old != P.serial) {
+            atomicAdd(P.guard + 1, 1ULL);
+            const unsigned long long t0 = global_ns();
+            while (true) {
+                __nanosleep(200);
+                old = atomicCAS(P.guard, 0ULL, P.serial);
+                if (old == 0ULL || old == P.serial) break;
+                if (global_ns() - t0 > 2000000000ULL) { atomicAdd(P.guard + 2, 1ULL); break; }
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -549,33 +638,63 @@ __device__ __forceinline__ void argmin_tail(const EvalParams& P, double best_val
             *P.best_idx = bi;
             if (P.ring_rec) { P.ring_rec[0] = __double_as_longlong(bv); P.ring_rec[1] = bi; }
             *P.ticket = 0u;
+            if (P.guard) { __threadfence(); atomicExch(P.guard, 0ULL); }   // release the scratch set
         }
     }
 }
+
+// MEASUREMENT-ONLY build switch (scripts/build_variants.py): DYNOED_TRAJ_WRAP folds every checkpoint /
+// quadrature slot onto a 4-deep (2-deep) window, so the scratch stays L2-resident and the launch
+// moves no checkpoint bytes to HBM.  Results are WRONG; the timing bounds what any scheme that
+// trades checkpoint traffic for recomputation could gain.
+#ifdef DYNOED_TRAJ_WRAP
+#define DYNOED_CKPT(s) ((s) & 3)
+#define DYNOED_QSLOT(j) ((j) & 1)
+#else
+#define DYNOED_CKPT(s) (s)
+#define DYNOED_QSLOT(j) (j)
+#endif
 
 // ----------------------------------------------------------------------------------------------
 // The substeps of one merged interval.  UC: the grid has ONE step size and the Runge-Kutta factors
 // h*a, h*b are read from EvalParams::coef at compile-time addresses (constant-bank operands: a
 // DFMA with three vector-register sources issues at 2/3 rate on sm_100a, register * constant +
 // register at full rate); otherwise they are computed per step from step_h.
+// Pint[i*NF + k] receives the interval's unweighted quadratures  int (Q_i^T Q_i)_k dt.
 // ----------------------------------------------------------------------------------------------
 template <class M, class Tab, bool GRAD, bool UC>
-__device__ __forceinline__ void forward_interval(const EvalParams& P, int s0, int s1, double* __restrict__ tr,
-                                                 double (&z)[M::NZ], double (&F)[M::NF], const double* u,
-                                                 const double* w, const double* th, const double* c) {
-    constexpr int NZ = M::NZ;
+__device__ __forceinline__ void forward_interval(const EvalParams& P, const CkptPolicy& K, int s0, int s1,
+                                                 double* __restrict__ tr, double (&z)[M::NZ],
+                                                 double (&Pint)[M::NOBS * M::NF], const double* u,
+                                                 const double* th, const double* c) {
+    constexpr int NZ = M::NZ, NQ = M::NOBS * M::NF;
+    double acc[NQ];
+#pragma unroll
+    for (int a = 0; a < NQ; ++a) { acc[a] = 0.0; Pint[a] = 0.0; }
     for (int s = s0; s < s1; ++s) {
         if (GRAD) {
+#ifdef DYNOED_NO_L2_POLICY
 #pragma unroll
-            for (int a = 0; a < NZ; ++a) tr[((size_t)s * NZ + a) * kMaxTile] = z[a];
+            for (int a = 0; a < NZ; ++a) tr[((size_t)DYNOED_CKPT(s) * NZ + a) * kMaxTile] = z[a];
+#else
+            const uint64_t pol = s >= P.hot_step ? K.hot : K.cold;
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) st_hint(tr + ((size_t)DYNOED_CKPT(s) * NZ + a) * kMaxTile, z[a], pol);
+#endif
         }
         if (UC) {
-            rk_forward_step<M, Tab>(__ldg(P.step_t + s), P.coef, z, F, u, w, th, c);
+            rk_forward_step<M, Tab>(__ldg(P.step_t + s), P.coef, z, acc, u, th, c);
         } else {
             double cfl[kCoefStride];
             fill_coef<Tab>(__ldg(P.step_h + s), cfl);
-            rk_forward_step<M, Tab>(__ldg(P.step_t + s), cfl, z, F, u, w, th, c);
+            rk_forward_step<M, Tab>(__ldg(P.step_t + s), cfl, z, acc, u, th, c);
+#pragma unroll
+            for (int a = 0; a < NQ; ++a) { Pint[a] = fma(cfl[coef_hb(0)], acc[a], Pint[a]); acc[a] = 0.0; }
         }
+    }
+    if (UC) {
+#pragma unroll
+        for (int a = 0; a < NQ; ++a) Pint[a] = P.coef[coef_hb(0)] * acc[a];
     }
 }
 
@@ -583,31 +702,46 @@ __device__ __forceinline__ void forward_interval(const EvalParams& P, int s0, in
 // step's are requested at the top of the current step, and the checkpoint three steps ahead is
 // pulled from HBM into L2, so that neither latency is exposed.
 template <class M, class Tab, bool UC>
-__device__ __forceinline__ void backward_interval(const EvalParams& P, int s0, int s1, const double* __restrict__ tr,
+__device__ __forceinline__ void backward_interval(const EvalParams& P, const CkptPolicy& K, int s0, int s1,
+                                                  const double* __restrict__ tr,
                                                   double (&zn)[M::NZ], double& tcur, double& hcur,
-                                                  double (&lam)[M::NZ], const double* u, const double* cw,
-                                                  const double* th, const double* c, const double* L,
-                                                  double* ub, double* wb) {
+                                                  double (&lam)[M::NZ], const double* u, const double* cwL,
+                                                  const double* th, const double* c, double* ub) {
     constexpr int NZ = M::NZ;
     for (int s = s1 - 1; s >= s0; --s) {
         double znext[NZ];
         const int sp = s > 0 ? s - 1 : 0;
+#ifdef DYNOED_NO_L2_POLICY
 #pragma unroll
-        for (int a = 0; a < NZ; ++a) znext[a] = ld_pinned(tr + ((size_t)sp * NZ + a) * kMaxTile);
+        for (int a = 0; a < NZ; ++a) znext[a] = ld_pinned(tr + ((size_t)DYNOED_CKPT(sp) * NZ + a) * kMaxTile);
+#else
+        {
+            const uint64_t pol = sp >= P.hot_step ? K.hot : K.cold;
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) znext[a] = ld_hint(tr + ((size_t)DYNOED_CKPT(sp) * NZ + a) * kMaxTile, pol);
+        }
+#endif
         const double tnext = __ldg(P.step_t + sp), hnext = __ldg(P.step_h + sp);
 #ifndef DYNOED_NO_L2_PREFETCH
         if (s >= 3) {
 #pragma unroll
-            for (int a = 0; a < NZ; ++a) prefetch_l2(tr + ((size_t)(s - 3) * NZ + a) * kMaxTile);
+            for (int a = 0; a < NZ; ++a) prefetch_l2(tr + ((size_t)DYNOED_CKPT(s - 3) * NZ + a) * kMaxTile);
         }
 #endif
         if (UC) {
-            rk_adjoint_step<M, Tab>(tcur, P.coef, zn, lam, u, cw, th, c, L, ub, wb);
+            rk_adjoint_step<M, Tab>(tcur, P.coef, zn, lam, u, cwL, th, c, ub);
         } else {
             double cfl[kCoefStride];
             fill_coef<Tab>(hcur, cfl);
-            rk_adjoint_step<M, Tab>(tcur, cfl, zn, lam, u, cw, th, c, L, ub, wb);
+            rk_adjoint_step<M, Tab>(tcur, cfl, zn, lam, u, cwL, th, c, ub);
         }
+#ifndef DYNOED_NO_L2_POLICY
+        // checkpoint s has been consumed by every lane of this warp: a hot one never goes to HBM
+        if (s >= P.hot_step && (threadIdx.x & 15) == 0) {
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) discard_l2(tr + ((size_t)DYNOED_CKPT(s) * NZ + a) * kMaxTile);
+        }
+#endif
 #pragma unroll
         for (int a = 0; a < NZ; ++a) zn[a] = znext[a];
         tcur = tnext; hcur = hnext;
@@ -620,7 +754,7 @@ __device__ __forceinline__ void backward_interval(const EvalParams& P, int s0, i
 template <class M, class Tab, bool GRAD, bool UCOEF>
 __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) {
     constexpr int NX = M::NX, NP = M::NP, NZ = M::NZ, NF = M::NF, NOBS = M::NOBS, NCTRL = M::NCTRL;
-    constexpr int NCU = NCTRL > 0 ? NCTRL : 1;
+    constexpr int NCU = NCTRL > 0 ? NCTRL : 1, NQ = NOBS * NF;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     double* tile_buf = reinterpret_cast<double*>(smem_raw + 128);
@@ -636,7 +770,10 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
     // drain, which hides the partial last wave.  No-op when the next launch is an ordinary one.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0 && P.use_tma) mbar_init(bar, 1);
-    __syncthreads();
+    scratch_acquire(P);
+    CkptPolicy K;
+    K.hot = l2_policy_evict_last();
+    K.cold = l2_policy_evict_first();
     uint32_t phase = 0;
     double best_val = __longlong_as_double(0x7ff0000000000000LL);   // +inf
     long long best_idx = -1;
@@ -675,7 +812,9 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
             for (int a = 0; a < M::NIC; ++a) z[M::ic_state(a)] = row[P.ic_off + a];
 #pragma unroll
             for (int a = 0; a < NF; ++a) F[a] = 0.0;
-            double* tr = P.traj + ((size_t)blockIdx.x * P.n_steps * NZ) * kMaxTile + tid;
+            // per-CTA scratch: (x, G) checkpoints [n_steps][NZ][128], then interval quadratures [N][NQ][128]
+            double* tr = P.traj + ((size_t)blockIdx.x * ((size_t)P.n_steps * NZ + (size_t)N * NQ)) * kMaxTile + tid;
+            double* pq = tr + (size_t)P.n_steps * NZ * kMaxTile;
             double* xg = (P.xgrid && active) ? P.xgrid + (size_t)g * (N + 1) * (NZ + NF) : nullptr;
             if (xg) {
 #pragma unroll
@@ -693,9 +832,23 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
                 for (int i = 0; i < NOBS; ++i) w[i] = row[P.w_off[i] + __ldg(P.indicators + (NCTRL + i) * N + j)];
                 M::consts(u, th, c);
                 const int s0 = __ldg(P.first_step + j), s1 = __ldg(P.first_step + j + 1);
-                // one instantiation per coefficient row: the row offset is then a compile-time
-                // constant and every h*a / h*b factor is a constant-bank operand of its DFMA
-                forward_interval<M, Tab, GRAD, UCOEF>(P, s0, s1, tr, z, F, u, w, th, c);
+                double Pint[NQ];
+                forward_interval<M, Tab, GRAD, UCOEF>(P, K, s0, s1, tr, z, Pint, u, th, c);
+                // F is linear in the weights: F += w_i P_i ; the P_i are kept for d/dw
+#pragma unroll
+                for (int i = 0; i < NOBS; ++i)
+#pragma unroll
+                    for (int k = 0; k < NF; ++k) F[k] = fma(w[i], Pint[i * NF + k], F[k]);
+                if (GRAD) {
+#ifdef DYNOED_NO_L2_POLICY
+#pragma unroll
+                    for (int a = 0; a < NQ; ++a) pq[((size_t)DYNOED_QSLOT(j) * NQ + a) * kMaxTile] = Pint[a];
+#else
+                    const uint64_t pol = j >= P.hot_interval ? K.hot : K.cold;
+#pragma unroll
+                    for (int a = 0; a < NQ; ++a) st_hint(pq + ((size_t)DYNOED_QSLOT(j) * NQ + a) * kMaxTile, Pint[a], pol);
+#endif
+                }
                 if (xg) {
                     double* o = xg + (size_t)(j + 1) * (NZ + NF);
 #pragma unroll
@@ -728,15 +881,32 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
                 for (int k = 0; k < NCU; ++k) { ub[k] = 0.0; uk[k] = -1; }
 #pragma unroll
                 for (int i = 0; i < NOBS; ++i) { wb[i] = 0.0; wk[i] = -1; }
+                // <Lambda, .> with the symmetric pairing: off-diagonal entries count twice
+                double Ls[NF];
+#pragma unroll
+                for (int jj = 0; jj < NP; ++jj)
+#pragma unroll
+                    for (int ii = 0; ii <= jj; ++ii) Ls[tri(ii, jj)] = (ii == jj ? 1.0 : 2.0) * L[tri(ii, jj)];
                 // (x, G) checkpoint and (t, h) of the step about to be processed.  The next step's
                 // (s - 1) are requested at the top of the current step, and the checkpoint three
                 // steps ahead is pulled from HBM into L2, so that neither latency is exposed.
                 double zn[NZ];
 #pragma unroll
-                for (int a = 0; a < NZ; ++a) zn[a] = tr[((size_t)(P.n_steps - 1) * NZ + a) * kMaxTile];
+                for (int a = 0; a < NZ; ++a) zn[a] = ld_pinned(tr + ((size_t)DYNOED_CKPT(P.n_steps - 1) * NZ + a) * kMaxTile);
                 double tcur = __ldg(P.step_t + P.n_steps - 1), hcur = __ldg(P.step_h + P.n_steps - 1);
                 for (int j = N - 1; j >= 0; --j) {
-                    double u[NCU], cw[NOBS], c[M::NCONST];
+                    double u[NCU], cwL[NQ], c[M::NCONST], Pj[NQ];
+                    // this interval's quadratures (d F / d w_i): requested here, consumed after the steps
+#ifdef DYNOED_NO_L2_POLICY
+#pragma unroll
+                    for (int a = 0; a < NQ; ++a) Pj[a] = ld_pinned(pq + ((size_t)DYNOED_QSLOT(j) * NQ + a) * kMaxTile);
+#else
+                    {
+                        const uint64_t pol = j >= P.hot_interval ? K.hot : K.cold;
+#pragma unroll
+                        for (int a = 0; a < NQ; ++a) Pj[a] = ld_hint(pq + ((size_t)DYNOED_QSLOT(j) * NQ + a) * kMaxTile, pol);
+                    }
+#endif
 #pragma unroll
                     for (int k = 0; k < NCTRL; ++k) {
                         const int idx = __ldg(P.indicators + k * N + j);
@@ -753,11 +923,23 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
                             if (wk[i] >= 0) row[P.w_off[i] + wk[i]] = wb[i];
                             wb[i] = 0.0; wk[i] = idx;
                         }
-                        cw[i] = 2.0 * row[P.w_off[i] + idx];
+                        const double cw = 2.0 * row[P.w_off[i] + idx];
+#pragma unroll
+                        for (int k = 0; k < NF; ++k) cwL[i * NF + k] = cw * L[k];
                     }
                     M::consts(u, th, c);
                     const int s0 = __ldg(P.first_step + j), s1 = __ldg(P.first_step + j + 1);
-                    backward_interval<M, Tab, UCOEF>(P, s0, s1, tr, zn, tcur, hcur, lam, u, cw, th, c, L, ub, wb);
+                    backward_interval<M, Tab, UCOEF>(P, K, s0, s1, tr, zn, tcur, hcur, lam, u, cwL, th, c, ub);
+#pragma unroll
+                    for (int i = 0; i < NOBS; ++i)
+#pragma unroll
+                        for (int k = 0; k < NF; ++k) wb[i] = fma(Ls[k], Pj[i * NF + k], wb[i]);
+#ifndef DYNOED_NO_L2_POLICY
+                    if (j >= P.hot_interval && (tid & 15) == 0) {
+#pragma unroll
+                        for (int a = 0; a < NQ; ++a) discard_l2(pq + ((size_t)DYNOED_QSLOT(j) * NQ + a) * kMaxTile);
+                    }
+#endif
                 }
 #pragma unroll
                 for (int k = 0; k < NCTRL; ++k)
@@ -830,6 +1012,89 @@ __global__ void argmin_records_kernel(const long long* __restrict__ rec, int wor
 }
 
 // ----------------------------------------------------------------------------------------------
+// Multistart selection without leaving the device (BASELINE.json config 5).  A sweep evaluates a
+// rank's shard as `nbatches` back-to-back launches; each left its {min value, index within the
+// batch} record in the context's history ring.
+//   pack_winner_kernel  : reduces the ring records of the last `nbatches` batches to the rank's best
+//                         candidate and packs  payload = [value, global index, design row, gradient
+//                         row]  (2 + 2 n_var doubles; an empty / all-NaN shard packs [inf, -1, 0...]).
+//   select_winner_kernel: picks the global winner from the all-gathered payloads [world][len] and
+//                         writes  [winner payload, owner rank]  (len + 1 doubles).
+// NaN never wins; ties go to the smallest global index.  One CTA each; they replace ~30 eager
+// framework launches on the selection path.
+// ----------------------------------------------------------------------------------------------
+constexpr int kSelThreads = 128;
+
+__device__ __forceinline__ void block_argmin(double& v, long long& i) {
+    __shared__ double sv[kSelThreads / 32];
+    __shared__ long long si[kSelThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, v, o);
+        const long long oi = __shfl_down_sync(0xffffffffu, i, o);
+        if (oi >= 0 && (i < 0 || ov < v || (ov == v && oi < i))) { v = ov; i = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = v; si[threadIdx.x >> 5] = i; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kSelThreads / 32; ++w)
+            if (si[w] >= 0 && (i < 0 || sv[w] < v || (sv[w] == v && si[w] < i))) { v = sv[w]; i = si[w]; }
+        sv[0] = v; si[0] = i;
+    }
+    __syncthreads();
+    v = sv[0]; i = si[0];
+}
+
+__global__ void __launch_bounds__(kSelThreads) pack_winner_kernel(const long long* __restrict__ ring, int ring_len,
+                                                                  int first_slot, int nbatches, long long batch_stride,
+                                                                  long long index_base, long long n_local,
+                                                                  const double* __restrict__ designs,
+                                                                  const double* __restrict__ grad, int n_var,
+                                                                  double* __restrict__ payload) {
+    double v = __longlong_as_double(0x7ff0000000000000LL);
+    long long row = -1;
+    for (int b = threadIdx.x; b < nbatches; b += kSelThreads) {
+        const long long* q = ring + 2 * ((first_slot + b) % ring_len);
+        const double bv = __longlong_as_double(q[0]);
+        const long long bi = q[1];
+        const long long r = bi >= 0 ? (long long)b * batch_stride + bi : -1;
+        if (r >= 0 && r < n_local && bv == bv && (row < 0 || bv < v || (bv == v && r < row))) { v = bv; row = r; }
+    }
+    block_argmin(v, row);
+    if (threadIdx.x == 0) {
+        payload[0] = row >= 0 ? v : __longlong_as_double(0x7ff0000000000000LL);
+        payload[1] = row >= 0 ? (double)(index_base + row) : -1.0;
+    }
+    for (int k = threadIdx.x; k < n_var; k += kSelThreads) {
+        payload[2 + k] = row >= 0 ? designs[row * n_var + k] : 0.0;
+        payload[2 + n_var + k] = (row >= 0 && grad) ? grad[row * n_var + k] : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(kSelThreads) select_winner_kernel(const double* __restrict__ gathered, int world,
+                                                                    int len, double* __restrict__ out) {
+    double v = __longlong_as_double(0x7ff0000000000000LL);
+    long long gi = -1;
+    int owner = -1;
+    for (int r = threadIdx.x; r < world; r += kSelThreads) {
+        const double rv = gathered[(size_t)r * len];
+        const long long ri = (long long)gathered[(size_t)r * len + 1];
+        if (ri >= 0 && rv == rv && (gi < 0 || rv < v || (rv == v && ri < gi))) { v = rv; gi = ri; }
+    }
+    block_argmin(v, gi);
+    __shared__ int s_owner;
+    if (threadIdx.x == 0) s_owner = -1;
+    __syncthreads();
+    for (int r = threadIdx.x; r < world; r += kSelThreads)
+        if (gi >= 0 && (long long)gathered[(size_t)r * len + 1] == gi && gathered[(size_t)r * len] == v) atomicMax(&s_owner, r);
+    __syncthreads();
+    owner = s_owner;
+    for (int k = threadIdx.x; k < len; k += kSelThreads)
+        out[k] = owner >= 0 ? gathered[(size_t)owner * len + k] : (k == 0 ? __longlong_as_double(0x7ff0000000000000LL) : k == 1 ? -1.0 : 0.0);
+    if (threadIdx.x == 0) out[len] = (double)owner;
+}
+
+// ----------------------------------------------------------------------------------------------
 // Local information gain (/root/reference/src/utilities.jl:47-70): at every merged-grid point t_j
 // and for every observed function i,  P_i(t_j) = Q_i^T Q_i  with Q = h_x G  (np x np, rank one) and
 // Pi_i(t_j) = F^-1 P_i F^-1  with F = F(t_f) (no regularisation, as in the reference).
@@ -858,7 +1123,9 @@ __global__ void info_gain_kernel(const EvalParams P, const double* __restrict__ 
     for (int k = 0; k < NCTRL; ++k)
         u[k] = P.designs[g * P.n_var + P.ctrl_off[k] + __ldg(P.indicators + k * N + jj)];
     M::consts(u, P.theta, c);
-    const double t = j < N ? __ldg(P.step_t + __ldg(P.first_step + j)) : 0.0;
+    // t_j: start of interval j; the final grid point is the end of the last step
+    const double t = j < N ? __ldg(P.step_t + __ldg(P.first_step + j))
+                           : __ldg(P.step_t + P.n_steps - 1) + __ldg(P.step_h + P.n_steps - 1);
     M::obs(t, z, u, P.theta, c, Q);
     // F^-1
     double A[NP][NP], B[NP][NP];

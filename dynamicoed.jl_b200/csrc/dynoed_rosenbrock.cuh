@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams 
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see oed_eval_kernel / launch_device
     if (tid == 0 && P.use_tma) mbar_init(bar, 1);
-    __syncthreads();
+    scratch_acquire(P);
     uint32_t phase = 0;
     double best_val = __longlong_as_double(0x7ff0000000000000LL);
     long long best_idx = -1;
@@ -565,6 +565,7 @@ __global__ void __launch_bounds__(32, 1) dir_eval_kernel(const EvalParams P) {
     const double* th = P.theta;
     double best_val = __longlong_as_double(0x7ff0000000000000LL);
     long long best_idx = -1;
+    scratch_acquire(P);
 
     // P.tile > 0: the design rows of this CTA's lanes are staged in shared memory first (one
     // coalesced read — the rows may live in mapped host memory, see eval_host's small-call path)

@@ -63,6 +63,46 @@ class _Printer(C99CodePrinter):
         return f"({int(expr.p)}.0/{int(expr.q)}.0)"
 
 
+class _FmaPrinter(_Printer):
+    """Prints every sum of products as ONE explicit fma chain seeded with its plain addends
+    (``fma(z3, J01, fma(z2, J00, fp00))`` instead of ``z2*J00 + z3*J01 + fp00``): a C compiler may
+    contract a*b+c but must not reassociate, so the left-to-right sum costs a DMUL, a DFMA and a
+    DADD where the chain costs two DFMAs.  double blocks only (the dual-number templates keep
+    operator syntax)."""
+
+    def _factor(self, f):
+        s = self._print(f)
+        return f"({s})" if (f.is_Add or (f.is_Mul and len(f.args) > 1)) else s
+
+    def _print_Add(self, expr):
+        plain, prods = [], []
+        for t in expr.as_ordered_terms():
+            c, rest = t.as_coeff_Mul()
+            fac = [] if rest == 1 else list(sp.Mul.make_args(rest))
+            expanded = []
+            for f in fac:          # x**2 is two factors
+                if f.is_Pow and f.exp.is_Integer and 2 <= int(f.exp) <= 4:
+                    expanded += [f.base] * int(f.exp)
+                else:
+                    expanded.append(f)
+            nfac = len(expanded) + (0 if c in (1, -1) else 1)
+            (prods if nfac >= 2 else plain).append((c, expanded, t))
+        if plain:
+            acc = super()._print_Add(sp.Add(*[t for _, _, t in plain])) if len(plain) > 1 \
+                else self._print(plain[0][2])
+        else:
+            acc = self._print(prods.pop(0)[2])
+        for c, fac, _ in prods:
+            if c in (1, -1):
+                a = ("-" if c == -1 else "") + self._factor(fac[0])
+                rest = fac[1:]
+            else:
+                a, rest = self._print(c), fac
+            b = "*".join(self._factor(f) for f in rest)
+            acc = f"fma({a}, {b}, {acc})"
+        return acc
+
+
 def count_flops(expr) -> int:
     """mul/add = 1 (an FMA therefore counts 2), division / elementary function = 1."""
     expr = sp.sympify(expr)
@@ -233,44 +273,56 @@ def emit_model(name: str, s: SimplifiedOEDSystem) -> tuple[str, dict]:
     for k, v in enumerate(wsym):
         names[v] = f"w[{k}]"
     kb = [sp.Symbol(f"kb{a}", real=True) for a in range(nz)]
-    Ls = [sp.Symbol(f"L{k}", real=True) for k in range(nF)]
-    cws = [sp.Symbol(f"cw{i}", real=True) for i in range(n_obs)]   # cw_i = 2 w_i (caller)
+    # cwL[i*nF + k] = 2 w_i Lambda_k (packed symmetric; the caller forms it once per merged interval)
+    cwLs = [[sp.Symbol(f"cwL{i}_{k}", real=True) for k in range(nF)] for i in range(n_obs)]
     for a, v in enumerate(kb):
         names[v] = f"kb[{a}]"
-    for k, v in enumerate(Ls):
-        names[v] = f"L[{k}]"
-    for k, v in enumerate(cws):
-        names[v] = f"cw[{k}]"
-    Lfull = sp.zeros(np_, np_)
-    for k, (i, j) in enumerate(triu_pairs(np_)):
-        Lfull[i, j] = Ls[k]
-        Lfull[j, i] = Ls[k]
+    for i in range(n_obs):
+        for k, v in enumerate(cwLs[i]):
+            names[v] = f"cwL[{i * nF + k}]"
+    cwLfull = []
+    for i in range(n_obs):
+        m = sp.zeros(np_, np_)
+        for k, (a, b_) in enumerate(triu_pairs(np_)):
+            m[a, b_] = cwLs[i][k]
+            m[b_, a] = cwLs[i][k]
+        cwLfull.append(m)
 
     hoist = _Hoister(set(theta) | set(s.controls))
     wrt = x
     H = lambda e: hoist(_horner(e, wrt))
 
+    def H_best(e):
+        """Horner form or factored form, whichever is cheaper after hoisting (x' = x (a - c y) and
+        J_00 = a - c y then share one sub-expression)."""
+        import copy
+        cands = [_horner(e, wrt)]
+        try:
+            cands.append(sp.factor(e))
+        except Exception:
+            pass
+        best, cost = None, None
+        for cnd in cands:
+            trial = copy.deepcopy(hoist)
+            k = count_flops(trial(cnd))
+            if cost is None or k < cost:
+                best, cost = cnd, k
+        return hoist(best)
+
     # ---------------- primal ---------------------------------------------------------------------
-    def build_primal(with_F: bool):
+    def build_primal():
         b = _Block()
         Jt = sp.Matrix(nx, nx, lambda i, c: b.tmp(f"J{i}{c}", H(J[i, c])))
         fpt = sp.Matrix(nx, max(n_ord, 0), lambda i, j: b.tmp(f"fp{i}{j}", H(fp[i, j]))) \
             if n_ord else sp.zeros(nx, 0)
         for i in range(nx):
-            b.out(f"dz[{i}]", H(f[i]))
+            b.out(f"dz[{i}]", H_best(f[i]))
         for j in range(np_):
             for i in range(nx):
                 e = sum(Jt[i, c] * G[c, j] for c in range(nx))
                 if j < n_ord:
                     e = e + fpt[i, j]
                 b.out(f"dz[{nx + j * nx + i}]", e)
-        if with_F:
-            Hct = sp.Matrix(n_obs, nx, lambda i, c: b.tmp(f"h{i}{c}", H(Hc[i, c])))
-            Qt = sp.Matrix(n_obs, np_, lambda i, j: b.tmp(
-                f"Q{i}{j}", sum(Hct[i, c] * G[c, j] for c in range(nx)) + H(H0[i, j])))
-            wQ = sp.Matrix(n_obs, np_, lambda i, j: b.tmp(f"wQ{i}{j}", wsym[i] * Qt[i, j]))
-            for k, (i, j) in enumerate(triu_pairs(np_)):
-                b.out(f"dF[{k}]", sum(wQ[o, i] * Qt[o, j] for o in range(n_obs)))
         return b
 
     # ---------------- adjoint --------------------------------------------------------------------
@@ -279,22 +331,17 @@ def emit_model(name: str, s: SimplifiedOEDSystem) -> tuple[str, dict]:
         kx = kb[:nx]
         kG = sp.Matrix(nx, np_, lambda i, j: kb[nx + j * nx + i])
         Jt = sp.Matrix(nx, nx, lambda i, c: b.tmp(f"J{i}{c}", H(J[i, c])))
-        Hct = sp.Matrix(n_obs, nx, lambda i, c: b.tmp(f"h{i}{c}", H(Hc[i, c])))
-        Qt = sp.Matrix(n_obs, np_, lambda i, j: b.tmp(
-            f"Q{i}{j}", sum(Hct[i, c] * G[c, j] for c in range(nx)) + H(H0[i, j])))
-        # r_i = Lambda Q_i^T ; dq_i = Q_i r_i
-        r = sp.Matrix(n_obs, np_, lambda i, j: b.tmp(
-            f"r{i}{j}", sum(Lfull[j, k] * Qt[i, k] for k in range(np_))))
-        for i in range(n_obs):
-            b.out(f"qw[{i}]", sum(Qt[i, j] * r[i, j] for j in range(np_)))
-        cw = cws
-        # G-bar = J^T kG + sum_i cw_i Hc[i,:]^T r_i
+        Hct = sp.Matrix(n_obs, nx, lambda i, c: H(Hc[i, c]))
+        Qe = sp.Matrix(n_obs, np_, lambda i, j: sum(Hct[i, c] * G[c, j] for c in range(nx)) + H(H0[i, j]))
+        # rw_ij = (2 w_i Lambda Q_i^T)_j  — plain expressions: cse names the ones used more than once
+        rw = sp.Matrix(n_obs, np_, lambda i, j: sum(cwLfull[i][j, k] * Qe[i, k] for k in range(np_)))
+        # G-bar = J^T kG + sum_i Hc[i,:]^T rw_i
         for j in range(np_):
             for c in range(nx):
                 e = sum(Jt[i, c] * kG[i, j] for i in range(nx))
                 for i in range(n_obs):
                     if Hc[i, c] != 0:
-                        e = e + (cw[i] * Hct[i, c]) * r[i, j] if Hc[i, c] != 1 else e + cw[i] * r[i, j]
+                        e = e + Hct[i, c] * rw[i, j]
                 b.out(f"zb[{nx + j * nx + c}]", e)
         # scalar S = kx.f + <W, J> + <kG_ord, fp> + sum_ic m_ic Hc_ic + sum_ij n_ij H0_ij;
         # x-bar = dS/dx, u-bar = dS/du (W, m, n treated as constants)
@@ -317,10 +364,11 @@ def emit_model(name: str, s: SimplifiedOEDSystem) -> tuple[str, dict]:
         for i in range(n_obs):
             for c in range(nx):
                 if msym[i, c] in used:
-                    sub[msym[i, c]] = b.tmp(f"m{i}{c}", cw[i] * sum(G[c, j] * r[i, j] for j in range(np_)))
+                    sub[msym[i, c]] = b.tmp(f"m{i}{c}", sum(G[c, j] * rw[i, j] for j in range(np_)))
             for j in range(np_):
                 if nsym[i, j] in used:
-                    sub[nsym[i, j]] = b.tmp(f"n{i}{j}", cw[i] * r[i, j])
+                    sub[nsym[i, j]] = b.tmp(f"n{i}{j}", rw[i, j])
+        static = [v for v in theta] + list(hoist.table.values())
 
         def collect_lin(g):
             g = sp.expand(g)
@@ -332,11 +380,19 @@ def emit_model(name: str, s: SimplifiedOEDSystem) -> tuple[str, dict]:
                     out = out + v * H(co)
                     rest = sp.expand(rest - v * co)
             assert rest == 0, "adjoint scalar must be linear in the adjoint symbols"
+            out = out.xreplace(sub)
+            # -p3 x kx0 - p3 W00 - ...  ->  -p3 (x kx0 + W00) - ... when that is cheaper
+            try:
+                col = sp.collect(sp.expand(out), [v for v in static if out.has(v)])
+                if count_flops(col) < count_flops(out):
+                    out = col
+            except Exception:
+                pass
             return out
         for a in range(nx):
-            b.out(f"zb[{a}]", collect_lin(grads[a]).xreplace(sub))
+            b.out(f"zb[{a}]", collect_lin(grads[a]))
         for k in range(nc):
-            b.out(f"ub[{k}]", collect_lin(grads[nx + k]).xreplace(sub))
+            b.out(f"ub[{k}]", collect_lin(grads[nx + k]))
         return b
 
     def build_obs():
@@ -408,21 +464,25 @@ def emit_model(name: str, s: SimplifiedOEDSystem) -> tuple[str, dict]:
                 b.out(f"dPU[{o * nF + k}]", e)
         return b
 
-    blocks = OrderedDict(primal=build_primal(True), primal_z=build_primal(False),
+    blocks = OrderedDict(primal_z=build_primal(),
                          adjoint=build_adjoint(), obs=build_obs(), ros_f=build_ros_f(),
                          ros_jac=build_ros_jac(), ros_ling=build_ros_ling(),
                          ros_linp=build_ros_linp())
     for k, v in enumerate(hoist.table.values()):
         names[v] = f"c[{k}]"
     pr = _Printer(names)
+    prf = _FmaPrinter(names)       # double blocks: explicit fma chains
     inputs = set(names.keys())
     code, flops = {}, {}
     for key, blk in blocks.items():
-        code[key], flops[key] = blk.render(pr, inputs, scalar="T" if key.startswith("ros_") else "double")
+        tmpl = key.startswith("ros_")
+        code[key], flops[key] = blk.render(pr if tmpl else prf, inputs, scalar="T" if tmpl else "double")
+    # what one forward stage of the explicit integrators evaluates: (x, G) right-hand side + Q
+    flops["primal"] = flops["primal_z"] + flops["obs"]
     cb = _Block()
     for k, e in enumerate(hoist.table.keys()):
         cb.out(f"c[{k}]", e)
-    code["consts"], flops["consts"] = cb.render(pr, inputs)
+    code["consts"], flops["consts"] = cb.render(prf, inputs)
     code["consts_t"], _ = cb.render(pr, inputs, scalar="T")
     n_const = max(len(hoist.table), 1)
     autonomous = not any(sp.sympify(e).has(t) for e in list(f) + list(s.Qexpr))
@@ -452,6 +512,7 @@ struct {cname} {{
     static constexpr int NTH = {len(theta)}, NCONST = {n_const}, NZ = {nz}, NF = {nF};
     static constexpr int FLOPS_PRIMAL = {flops['primal']}, FLOPS_PRIMAL_Z = {flops['primal_z']};
     static constexpr int FLOPS_ADJOINT = {flops['adjoint']}, FLOPS_CONSTS = {flops['consts']};
+    static constexpr int FLOPS_OBS = {flops['obs']};
     static constexpr int FLOPS_ROS_F = {flops['ros_f']};
     static constexpr const char* NAME = "{name}";
     __host__ __device__ static constexpr int ic_state(int i) {{
@@ -467,26 +528,19 @@ struct {cname} {{
                                                   double* __restrict__ c) {{
 {code['consts']}
     }}
-    // x' = f, G' = J G + f_p, F'_triu = sum_i w_i (Q_i^T Q_i)_triu
-    __device__ __forceinline__ static void primal(double t, const double* __restrict__ z,
-            const double* __restrict__ u, const double* __restrict__ w,
-            const double* __restrict__ th, const double* __restrict__ c,
-            double* __restrict__ dz, double* __restrict__ dF) {{
-{code['primal']}
-    }}
-    // (x, G) part only — stage recomputation in the backward sweep
+    // x' = f, G' = J G + f_p  (the Fisher quadratures are formed from Q = obs() by the kernel template)
     __device__ __forceinline__ static void primal_z(double t, const double* __restrict__ z,
             const double* __restrict__ u, const double* __restrict__ th,
             const double* __restrict__ c, double* __restrict__ dz) {{
 {code['primal_z']}
     }}
-    // zb = (d g/d z)^T kb + sum_i (cw_i / 2) d(Q_i L Q_i^T)/dz   (caller passes cw_i = 2 w_i) ;
-    // ub = (d g/d u)^T kb ;  qw[i] = Q_i L Q_i^T  (L = packed symmetric d criterion / d F)
+    // zb = (d g/d z)^T kb + sum_i w_i d(Q_i L Q_i^T)/dz ;  ub = (d g/d u)^T kb
+    // cwL[i*NF + k] = 2 w_i L_k  (L = packed symmetric d criterion / d F; formed once per interval)
     __device__ __forceinline__ static void adjoint(double t, const double* __restrict__ z,
-            const double* __restrict__ u, const double* __restrict__ cw,
+            const double* __restrict__ u, const double* __restrict__ cwL,
             const double* __restrict__ th, const double* __restrict__ c,
-            const double* __restrict__ L, const double* __restrict__ kb,
-            double* __restrict__ zb, double* __restrict__ ub, double* __restrict__ qw) {{
+            const double* __restrict__ kb,
+            double* __restrict__ zb, double* __restrict__ ub) {{
 {code['adjoint']}
     }}
     // Q = h_x G, row-major [NOBS][NP]

@@ -80,7 +80,9 @@ def sweep(evaluate, designs_local: torch.Tensor, index_base: int, group=None, ga
 
 
 def gpu_evaluator(ctx):
-    """evaluate() closure over a `runtime.Context` for CUDA tensors (device-pointer path)."""
+    """evaluate() closure over a `runtime.Context` for CUDA tensors (device-pointer path).  The context is
+    bound to torch's current stream (`Context.eval_batch` does that for CUDA tensors), so tensors produced by
+    torch kernels before the call and consumed by torch kernels after it are ordered with the evaluation."""
     def evaluate(designs_local: torch.Tensor):
         n = designs_local.shape[0]
         crit = torch.empty(n, dtype=torch.float64, device=designs_local.device)
@@ -93,14 +95,16 @@ def gpu_evaluator(ctx):
 
 
 # ---- device-side selection: ONE collective, ONE host synchronisation per sweep -------------------
+# Host-logic mirror (plain torch ops, any device) of the library's pack_winner / select_winner kernels:
+# what the gloo CPU tests exercise, and the specification the GPU tests hold the kernels to.
 def pack_local_winner(values: torch.Tensor, indices: torch.Tensor, index_base: int, designs_local: torch.Tensor,
                       grad_local: torch.Tensor) -> torch.Tensor:
     """[value, global index, design row, gradient row] of this rank's best candidate, as one
-    float64 tensor on the tensors' device, without leaving the device.
+    float64 tensor on the tensors' device.
 
     values / indices: per-batch (min value, LOCAL row index within the shard, < 0 = none) records
-    of this rank (e.g. `Context.argmin_history_async` reinterpreted).  NaN never wins; ties go to
-    the smallest index.  An empty / all-NaN shard yields (inf, -1, zeros, zeros)."""
+    of this rank.  NaN never wins; ties go to the smallest index.  An empty / all-NaN shard yields
+    (inf, -1, zeros, zeros)."""
     n_var = designs_local.shape[1]
     vals = torch.where((indices >= 0) & (values == values), values, torch.full_like(values, float("inf")))
     m = vals.min()
@@ -120,9 +124,8 @@ def pack_local_winner(values: torch.Tensor, indices: torch.Tensor, index_base: i
 
 
 def gather_winner(payload: torch.Tensor, group=None) -> torch.Tensor:
-    """all_gather of every rank's `pack_local_winner` payload, then the global winner's payload
-    (min value, ties -> smallest global index) with the owner rank appended — still on the device;
-    the caller reads it with ONE `.cpu()`."""
+    """all_gather of every rank's payload, then the global winner's payload (min value, ties ->
+    smallest global index) with the owner rank appended."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world > 1:
         flat = torch.empty(world * payload.numel(), dtype=payload.dtype, device=payload.device)
@@ -141,28 +144,46 @@ def gather_winner(payload: torch.Tensor, group=None) -> torch.Tensor:
     return torch.cat([win, owner_f.reshape(1)])
 
 
+def _sweep_buffers(ctx, dev, world: int, length: int):
+    key = (str(dev), world, length)
+    cache = ctx.__dict__.setdefault("_sweep_buf", {})
+    if key not in cache:
+        cache[key] = (torch.empty(length, dtype=torch.float64, device=dev),
+                      torch.empty((world, length), dtype=torch.float64, device=dev),
+                      torch.empty(length + 1, dtype=torch.float64, device=dev),
+                      torch.empty(length + 1, dtype=torch.float64).pin_memory())
+    return cache[key]
+
+
 def sweep_device(ctx, designs_local: torch.Tensor, crit: torch.Tensor, grad: torch.Tensor, index_base: int,
                  chunk: int = 65536, group=None) -> dict:
-    """One multistart sweep of this rank's shard on the GPU: back-to-back launches of `chunk`
-    designs (their tails overlap), the per-batch records read on the device, one all_gather of the
-    local winners, one device->host read at the end."""
+    """One multistart sweep of this rank's shard on the GPU (BASELINE.json config 5): back-to-back
+    launches of `chunk` designs whose tails overlap, then THREE more enqueues and one host read —
+    `dynoed_pack_winner` (the rank's best candidate from the per-batch records the library keeps),
+    one `all_gather_into_tensor` of the 2 + 2 n_var doubles per rank, `dynoed_select_winner`, and a
+    pinned device->host copy of the winner.  Everything runs on torch's current stream."""
     n_local, n_var = designs_local.shape
     dev = designs_local.device
     nch = (n_local + chunk - 1) // chunk
     if nch > 64:
         raise ValueError("history ring holds 64 batches: use a larger chunk")
+    from .runtime import OVERLAP_OK
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    ctx.bind_torch_stream(dev)
     for c in range(nch):
         a, b = c * chunk, min((c + 1) * chunk, n_local)
-        ctx.eval_batch(designs_local[a:b], crit[a:b], grad[a:b], None, async_=True)
-    if nch > 0:
-        rec = torch.empty((nch, 2), dtype=torch.int64, device=dev)
-        ctx.argmin_history_async(nch, rec)
-        values = rec[:, 0].contiguous().view(torch.float64)
-        base = torch.arange(nch, dtype=torch.int64, device=dev) * chunk
-        indices = torch.where(rec[:, 1] >= 0, rec[:, 1] + base, rec[:, 1])
+        # launches after the first may start while their predecessor drains: nothing enqueued in between
+        # writes the design rows (the first one stays ordered after whatever produced `designs_local`)
+        ctx.eval_batch(designs_local[a:b], crit[a:b], grad[a:b], None, async_=True, flags=OVERLAP_OK if c else 0)
+    payload, gathered, out, host = _sweep_buffers(ctx, dev, world, 2 + 2 * n_var)
+    ctx.pack_winner(nch, designs_local, grad, chunk, index_base, payload, n_local=n_local)
+    if world > 1:
+        dist.all_gather_into_tensor(gathered.view(-1), payload, group=group)
+        ctx.select_winner(gathered, world, out)
     else:
-        values = torch.full((1,), float("inf"), dtype=torch.float64, device=dev)
-        indices = torch.full((1,), -1, dtype=torch.int64, device=dev)
-    win = gather_winner(pack_local_winner(values, indices, index_base, designs_local, grad), group).cpu()
+        ctx.select_winner(payload, 1, out)
+    host.copy_(out, non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    win = host.clone()
     return dict(value=float(win[0]), index=int(win[1]), owner=int(win[-1]), design=win[2:2 + n_var],
                 grad=win[2 + n_var:2 + 2 * n_var])

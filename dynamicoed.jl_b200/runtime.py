@@ -12,10 +12,12 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdynoed_cuda.so")
+# DYNOED_LIB: another build of the same library (measurement variants, scripts/build_variants.py)
+LIB_PATH = os.environ.get("DYNOED_LIB") or os.path.join(_HERE, "libdynoed_cuda.so")
 
 RK4, TSIT5, ROS2, ROS3P, RODAS3 = 0, 1, 2, 3, 4
 GRAD_NO_CONTROLS = 1    # eval flag: weights / tau / IC gradient only (forward sweep), control entries NaN
+OVERLAP_OK = 2          # eval flag: inputs are not produced by work enqueued after the previous launch (see dynoed.h)
 METHODS = {"rk4": RK4, "RK4": RK4, "tsit5": TSIT5, "Tsit5": TSIT5, "ros2": ROS2, "ROS2": ROS2,
            "ros3p": ROS3P, "ROS3P": ROS3P, "rodas3": RODAS3, "RODAS3": RODAS3}
 
@@ -61,7 +63,8 @@ EXPORTS = ["dynoed_abi_version", "dynoed_model_count", "dynoed_model_name", "dyn
            "dynoed_eval_batch", "dynoed_eval_batch_async", "dynoed_eval_batch_host_async", "dynoed_wait",
            "dynoed_sync", "dynoed_argmin",
            "dynoed_argmin_async", "dynoed_argmin_record_async", "dynoed_argmin_history_async",
-           "dynoed_argmin_gathered",
+           "dynoed_argmin_gathered", "dynoed_set_aux_stream", "dynoed_pack_winner", "dynoed_select_winner",
+           "dynoed_guard_stats",
            "dynoed_set_profiling", "dynoed_kernel_time",
            "dynoed_trajectory", "dynoed_information_gain", "dynoed_fim_basis", "dynoed_hessian_batch",
            "dynoed_eval_fixed_controls", "dynoed_criterion_batch", "dynoed_fp64_peak", "dynoed_fp64_microbench",
@@ -101,6 +104,10 @@ def lib(path: str | None = None):
         L.dynoed_argmin_record_async.argtypes = [vp, dp]
         L.dynoed_argmin_history_async.argtypes = [vp, C.c_int, dp]
         L.dynoed_argmin_gathered.argtypes = [vp, dp, C.c_int, C.c_int, i64, dp]
+        L.dynoed_set_aux_stream.argtypes = [vp, vp]
+        L.dynoed_pack_winner.argtypes = [vp, C.c_int, dp, dp, i64, i64, i64, dp]
+        L.dynoed_select_winner.argtypes = [vp, dp, C.c_int, dp]
+        L.dynoed_guard_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.dynoed_set_profiling.argtypes = [vp, C.c_int]
         L.dynoed_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         L.dynoed_trajectory.argtypes = [vp, dp, i64, dp]
@@ -220,16 +227,30 @@ class Context:
     def set_stream(self, stream_ptr: int):
         """Run on the given cudaStream_t (0 = legacy default stream, e.g. torch's default)."""
         _check(self._L.dynoed_set_stream(self._h, C.c_void_p(int(stream_ptr))), self._h, self._L)
+        self._bound_stream = int(stream_ptr)
 
     def own_stream(self):
         _check(self._L.dynoed_own_stream(self._h), self._h, self._L)
+        self._bound_stream = None
 
     def eval_batch(self, designs, crit, grad=None, fim=None, n=None, async_=False, flags=0):
         """designs [n, n_var], crit [n], grad [n, n_var] | None, fim [n, nF] | None — numpy arrays
         (host path) or torch CUDA tensors (device path), float64, contiguous."""
         n = int(designs.shape[0]) if n is None else int(n)
+        if getattr(designs, "is_cuda", False):
+            self.bind_torch_stream(designs.device)
         fn = self._L.dynoed_eval_batch_async if async_ else self._L.dynoed_eval_batch
         _check(fn(self._h, _ptr(designs), n, _ptr(crit), _ptr(grad), _ptr(fim), int(flags)), self._h, self._L)
+
+    def bind_torch_stream(self, device=None):
+        """Order this context with torch: run on torch's CURRENT stream of `device`.  CUDA tensors handed to
+        `eval_batch` were produced, and their results will be consumed, on that stream; a context left on its
+        own non-blocking stream would race with both.  (No-op when the stream is unchanged.)"""
+        import torch
+        ptr = torch.cuda.current_stream(device).cuda_stream
+        if ptr != getattr(self, "_bound_stream", None):
+            self.set_stream(ptr)
+
 
     def eval_batch_host_async(self, designs, crit, grad=None, fim=None, flags=0) -> int:
         """Pipelined host-buffer evaluation (page-locked numpy arrays): returns a call id for `wait`."""
@@ -266,6 +287,28 @@ class Context:
         ([groups, 3] int64: value bits, global index, owner rank), on the ctx stream."""
         _check(self._L.dynoed_argmin_gathered(self._h, d_records.data_ptr(), int(world), int(groups),
                                               int(shard_size), d_out.data_ptr()), self._h, self._L)
+
+    def set_aux_stream(self, stream_ptr: int):
+        """Selection helpers run on this cudaStream_t (0 = back to the ctx stream); see dynoed.h."""
+        _check(self._L.dynoed_set_aux_stream(self._h, C.c_void_p(int(stream_ptr)) if stream_ptr else None),
+               self._h, self._L)
+
+    def pack_winner(self, nbatches: int, designs, grad, batch_stride: int, index_base: int, d_payload, n_local=None):
+        """[value, global index, design row, gradient row] of the best candidate among the last
+        `nbatches` batches, written to the CUDA tensor d_payload (2 + 2 n_var float64)."""
+        n_local = int(designs.shape[0]) if n_local is None else int(n_local)
+        _check(self._L.dynoed_pack_winner(self._h, int(nbatches), _ptr(designs) if n_local else None,
+                                          _ptr(grad) if (grad is not None and n_local) else None, n_local,
+                                          int(batch_stride), int(index_base), _ptr(d_payload)), self._h, self._L)
+
+    def select_winner(self, d_gathered, world: int, d_out):
+        """Global winner of all-gathered payloads [world, 2 + 2 n_var] -> d_out [2 + 2 n_var + 1] (owner last)."""
+        _check(self._L.dynoed_select_winner(self._h, _ptr(d_gathered), int(world), _ptr(d_out)), self._h, self._L)
+
+    def guard_stats(self):
+        w, t = C.c_int64(), C.c_int64()
+        _check(self._L.dynoed_guard_stats(self._h, C.byref(w), C.byref(t)), self._h, self._L)
+        return int(w.value), int(t.value)
 
     def set_profiling(self, on: bool):
         _check(self._L.dynoed_set_profiling(self._h, int(bool(on))), self._h, self._L)

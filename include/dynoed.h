@@ -16,9 +16,10 @@
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
  *     DYNOED_ECUDA.
  *   - stream order is kept: whatever is enqueued on the ctx stream after an evaluation sees its
- *     results.  Two consecutive dynoed_eval_batch_async calls of one ctx on DISJOINT buffers may
- *     overlap on the device (the second starts while the first drains); calls that share a
- *     buffer, or that come from different contexts, never do.
+ *     results, and an evaluation sees whatever was enqueued before it.  The one exception is
+ *     opt-in: a dynoed_eval_batch_async call that carries DYNOED_OVERLAP_OK may start while the
+ *     previous evaluation launch of the same ctx (same stream, same kernel, disjoint buffers) still
+ *     drains.  Calls that share a buffer, or come from different contexts, never overlap.
  */
 #ifndef DYNOED_H
 #define DYNOED_H
@@ -63,6 +64,11 @@ extern "C" {
                                     * forward sweep with per-interval quadratures, no adjoint sweep
                                     * (explicit tableaus) / no control passes (Rosenbrock);
                                     * control entries of grad are NaN ("not computed") */
+#define DYNOED_OVERLAP_OK 2u       /* dynoed_eval_batch_async: this launch may start while the previous launch
+                                    * of the same ctx drains.  The caller asserts that NO work enqueued on the
+                                    * stream after that previous launch produces this launch's inputs (the
+                                    * kernels do not wait for the preceding grid's memory to be flushed).
+                                    * Without the flag every launch is fully ordered after its predecessor. */
 
 typedef struct dynoed_ctx dynoed_ctx;
 
@@ -169,6 +175,31 @@ int dynoed_argmin_history_async(dynoed_ctx* ctx, int count, void* d_records);
  * int64 owner rank}.  NaN never wins, ties go to the smallest global index.  (BASELINE config 5.) */
 int dynoed_argmin_gathered(dynoed_ctx* ctx, const void* d_records, int world, int groups,
                            int64_t shard_size, void* d_out);
+
+/* Selection helpers normally run on the ctx stream, where any node between two evaluation launches
+ * ends their overlap.  With an auxiliary stream set (cudaStream_t as void*, NULL = unset) they run
+ * there instead: the ring readers (dynoed_argmin_history_async, dynoed_pack_winner) are ordered after
+ * every evaluation enqueued so far by an event; the reducers over gathered data
+ * (dynoed_argmin_gathered, dynoed_select_winner) are simply enqueued on it — issue the collective
+ * that feeds them on the same stream.  The caller orders its own stream after the aux stream. */
+int dynoed_set_aux_stream(dynoed_ctx* ctx, void* cuda_stream);
+
+/* Multistart sweep selection on the device (BASELINE config 5; replaces N sequential calls of the
+ * objective closure /root/reference/src/problem.jl:112-121 plus a host-side arg-min).
+ * dynoed_pack_winner: the shard was evaluated as the last `nbatches` (<= 64) device-path batches of
+ * this ctx, batch b covering rows [b * batch_stride, ...) of designs / grad ([n_local][n_var], device).
+ * Writes d_payload[2 + 2 n_var] = {best value, index_base + best row, design row, gradient row}
+ * ({+inf, -1, 0...} for an empty or all-NaN shard; grad may be NULL -> zeros).
+ * dynoed_select_winner: d_gathered = the payloads of all ranks, [world][2 + 2 n_var] (e.g. from ONE
+ * all-gather); writes d_out[2 + 2 n_var + 1] = {winner's payload, owner rank} (owner -1 if none).
+ * NaN never wins, ties go to the smallest global index.  One small kernel each, no host sync. */
+int dynoed_pack_winner(dynoed_ctx* ctx, int nbatches, const double* designs, const double* grad,
+                       int64_t n_local, int64_t batch_stride, int64_t index_base, double* d_payload);
+int dynoed_select_winner(dynoed_ctx* ctx, const double* d_gathered, int world, double* d_out);
+
+/* scratch-set guard counters (synchronises the device): CTAs that had to wait for a scratch set still
+ * held by the launch two back, and waits abandoned after 2 s (must stay 0) */
+int dynoed_guard_stats(dynoed_ctx* ctx, int64_t* waits, int64_t* timeouts);
 
 /* the predictor p -> (X, t) of build_predictor (problem.jl:80-90) at the merged-grid points:
  * X[k] is [N+1][nz+nF] row-major (state order [x; vec(G); F_triu], augment.jl:240) */

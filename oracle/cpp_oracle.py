@@ -30,23 +30,54 @@ def build():
     return LIB
 
 
+NATIVE_FLAGS = "-O3 -march=native -ffp-contract=fast"   # the timing arm's build (oracle/Makefile)
+
+
+def _native_path():
+    """The timing-arm build (-O3 -march=native, FMA contraction on) for THIS host: built where it runs,
+    named after the host's ISA flags so that a copy built on another machine is never loaded."""
+    import hashlib
+    flags = ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                flags = line
+                break
+    except OSError:
+        pass
+    tag = hashlib.sha256(flags.encode()).hexdigest()[:10]
+    path = os.path.join(_HERE, "_build", f"liboed_oracle_native.{tag}.so")
+    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(os.path.join(_HERE, "oed_oracle.cpp")):
+        subprocess.run(["make", "-s", "-C", _HERE, "native", f"NATIVE_TAG={tag}"], check=True)
+    return path
+
+
 _lib = None
+_libs = {}
 
 
-def lib():
+def lib(native: bool = False):
+    """The strict-FP parity oracle (default) or, for the timed CPU arm only, the native-ISA build."""
     global _lib
+    if native:
+        if "native" not in _libs:
+            _libs["native"] = _configure(C.CDLL(_native_path()))
+        return _libs["native"]
     if _lib is None:
         if not os.path.exists(LIB):
             build()
-        L = C.CDLL(LIB)
-        L.oracle_eval_batch.argtypes = [C.POINTER(_Desc), C.c_void_p, C.c_int64, C.c_void_p,
-                                        C.c_void_p, C.c_void_p, C.c_int]
-        L.oracle_trajectory.argtypes = [C.POINTER(_Desc), C.c_void_p, C.c_void_p]
-        L.oracle_criterion.restype = C.c_double
-        L.oracle_criterion.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_void_p]
-        L.oracle_max_threads.restype = C.c_int
-        _lib = L
+        _lib = _configure(C.CDLL(LIB))
     return _lib
+
+
+def _configure(L):
+    L.oracle_eval_batch.argtypes = [C.POINTER(_Desc), C.c_void_p, C.c_int64, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_int]
+    L.oracle_trajectory.argtypes = [C.POINTER(_Desc), C.c_void_p, C.c_void_p]
+    L.oracle_criterion.restype = C.c_double
+    L.oracle_criterion.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_void_p]
+    L.oracle_max_threads.restype = C.c_int
+    return L
 
 
 def uniform_step(tgrid, substeps):
@@ -89,9 +120,10 @@ def step_table(tgrid, substeps=None, edges=None):
 
 
 class CppOracle:
-    def __init__(self, model: str, py_oracle):
+    def __init__(self, model: str, py_oracle, native: bool = False):
         o = py_oracle
         self.o = o
+        self._native = native
         self.model = MODEL_IDS[model]
         self.n_var, self.N = o.n_var, o.N
         self.nF = o.nF
@@ -128,7 +160,7 @@ class CppOracle:
         crit = np.empty(n)
         g = np.empty((n, self.n_var)) if grad else None
         f = np.empty((n, self.nF))
-        rc = lib().oracle_eval_batch(C.byref(self.d), designs.ctypes.data, n, crit.ctypes.data,
+        rc = lib(self._native).oracle_eval_batch(C.byref(self.d), designs.ctypes.data, n, crit.ctypes.data,
                                      g.ctypes.data if grad else None, f.ctypes.data, threads)
         assert rc == 0
         return crit, g, f

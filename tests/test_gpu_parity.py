@@ -279,11 +279,12 @@ def test_reference_lv_optimum_through_the_boundary(built_library):
 
 
 def test_overlapped_back_to_back_launches_match_isolated_ones(built_library):
-    """Consecutive full-GPU launches on disjoint buffers may overlap their tails (programmatic
-    dependent launch, two scratch sets).  Every batch must still equal its isolated evaluation
-    bit for bit, the arg-min must be the last batch's, and launches that reuse a buffer of their
-    predecessor must NOT be overlapped."""
+    """Consecutive launches on disjoint buffers that carry DYNOED_OVERLAP_OK may overlap their tails
+    (programmatic dependent launch, two scratch sets behind the scratch-set guard).  Every batch must
+    still equal its isolated evaluation bit for bit, the arg-min must be the last batch's; launches
+    WITHOUT the flag, and launches that reuse a buffer of their predecessor, must not be overlapped."""
     import torch
+    from dynamicoed.jl_b200.runtime import OVERLAP_OK
     ctx = make_problem("lv_fishing", D.FisherDCriterion).context()
     ks = ctx.kernel_stats(True)
     n = ks["grid"] * ks["block"] + 5000                  # 1.09 waves: a real partial last wave
@@ -298,9 +299,13 @@ def test_overlapped_back_to_back_launches_match_isolated_ones(built_library):
     over0 = ctx.kernel_stats(True)["overlapped_launches"]
     outs = [(torch.empty(n, dtype=torch.float64, device="cuda"), torch.empty_like(ins[k]),
              torch.empty((n, 3), dtype=torch.float64, device="cuda")) for k in range(K)]
+    for k in range(K):                                   # the default is full stream order
+        ctx.eval_batch(ins[k], *outs[k], async_=True)
+    ctx.sync()
+    assert ctx.kernel_stats(True)["overlapped_launches"] == over0
     for rep in range(3):
         for k in range(K):
-            ctx.eval_batch(ins[k], *outs[k], async_=True)
+            ctx.eval_batch(ins[k], *outs[k], async_=True, flags=OVERLAP_OK)
     ctx.sync()
     assert ctx.kernel_stats(True)["overlapped_launches"] - over0 == 3 * K
     for k in range(K):
@@ -309,12 +314,70 @@ def test_overlapped_back_to_back_launches_match_isolated_ones(built_library):
     assert ctx.argmin() == ref[K - 1][3]
     # same output buffers twice in a row: stream order must be kept, so no overlap
     over1 = ctx.kernel_stats(True)["overlapped_launches"]
-    ctx.eval_batch(ins[0], *outs[0], async_=True)
-    ctx.eval_batch(ins[1], *outs[0], async_=True)
+    ctx.eval_batch(ins[0], *outs[0], async_=True, flags=OVERLAP_OK)
+    ctx.eval_batch(ins[1], *outs[0], async_=True, flags=OVERLAP_OK)
     ctx.sync()
     assert ctx.kernel_stats(True)["overlapped_launches"] == over1 + 1   # only the first of the two
     for a, b in zip(outs[0], ref[1][:3]):
         assert torch.equal(a, b)
+    # inputs rewritten by a foreign kernel between two launches: without the flag the second launch sees them
+    mod = ins[2].clone()
+    ctx.eval_batch(ins[0], *outs[0], async_=True, flags=OVERLAP_OK)
+    mod.copy_(ins[3])                                    # torch kernel on the same stream
+    ctx.eval_batch(mod, *outs[1], async_=True)           # no flag: ordered after the copy
+    ctx.sync()
+    for a, b in zip(outs[1], ref[3][:3]):
+        assert torch.equal(a, b)
+    assert ctx.guard_stats()[1] == 0
+
+
+def test_subwave_launches_overlap_behind_the_scratch_guard(built_library):
+    """Batches smaller than one wave (what a branch-and-bound driver sends: 16-32 k designs) also run
+    back to back under programmatic dependent launch.  Launch k+2 shares its scratch set with launch k
+    and can become resident while k still runs; the scratch-set guard makes its CTAs wait.  Results
+    must be bit-identical to isolated launches, no guard wait may time out."""
+    import torch
+    from dynamicoed.jl_b200.runtime import OVERLAP_OK
+    ctx = make_problem("lv_fishing", D.FisherDCriterion).context()
+    ks = ctx.kernel_stats(True)
+    K = 6
+    for n in (ks["grid"] * ks["block"] // 2 + 77, 9000):
+        ins = [torch.from_numpy(random_designs("lv_fishing", 71, n, 300 + k)).cuda() for k in range(K)]
+        ref = []
+        for k in range(K):
+            c = torch.empty(n, dtype=torch.float64, device="cuda"); g = torch.empty_like(ins[k])
+            f = torch.empty((n, 3), dtype=torch.float64, device="cuda")
+            ctx.eval_batch(ins[k], c, g, f)
+            ref.append((c.clone(), g.clone(), f.clone(), ctx.argmin()))
+        outs = [(torch.empty(n, dtype=torch.float64, device="cuda"), torch.empty_like(ins[k]),
+                 torch.empty((n, 3), dtype=torch.float64, device="cuda")) for k in range(K)]
+        over0 = ctx.kernel_stats(True)["overlapped_launches"]
+        for rep in range(4):
+            for k in range(K):
+                ctx.eval_batch(ins[k], *outs[k], async_=True, flags=OVERLAP_OK)
+        ctx.sync()
+        assert ctx.kernel_stats(True)["overlapped_launches"] - over0 >= 4 * K - 1
+        for k in range(K):
+            for a, b in zip(outs[k], ref[k][:3]):
+                assert torch.equal(a, b)
+        assert ctx.argmin() == ref[K - 1][3]
+    waits, timeouts = ctx.guard_stats()
+    assert timeouts == 0
+    # objective-only launches take the same path
+    n = 20000
+    ins = [torch.from_numpy(random_designs("lv_fishing", 71, n, 400 + k)).cuda() for k in range(4)]
+    cs = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(4)]
+    iso = []
+    for k in range(4):
+        ctx.eval_batch(ins[k], cs[k], None, None)
+        iso.append(cs[k].clone())
+    for rep in range(3):
+        for k in range(4):
+            ctx.eval_batch(ins[k], cs[k], None, None, async_=True, flags=OVERLAP_OK)
+    ctx.sync()
+    for k in range(4):
+        assert torch.equal(cs[k], iso[k])
+    assert ctx.guard_stats()[1] == 0
 
 
 # ---------------------------------------------------------------------------------------------
@@ -971,20 +1034,86 @@ def test_small_batch_kernel_device_pointers_and_nan(built_library):
 
 
 def test_multistart_sweep_device_side_selection(built_library):
-    """Chunked back-to-back launches, per-batch records reduced on the device, one host read: the
-    winner equals the arg-min of all criterion values and carries its own design / gradient rows."""
+    """Chunked back-to-back launches, per-batch records reduced on the device by the library's
+    pack / select kernels, one host read: the winner equals the arg-min of all criterion values and
+    carries its own design / gradient rows."""
     import torch
     from dynamicoed.jl_b200 import multistart
     ctx = make_problem("lv_fishing", D.FisherDCriterion).context()
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     n = 3 * 65536 + 1234
     g = torch.Generator(device="cuda"); g.manual_seed(7)
     des = torch.rand((n, 71), dtype=torch.float64, device="cuda", generator=g)
     des[:, -1] = 1e-3 + 0.99 * des[:, -1]
     des[17, 3] = float("nan")
     crit = torch.empty(n, dtype=torch.float64, device="cuda"); grad = torch.empty_like(des)
+    l0 = ctx.kernel_stats(True)["launches"]
     out = multistart.sweep_device(ctx, des, crit, grad, 1000, chunk=65536)
+    assert ctx.kernel_stats(True)["launches"] - l0 == 4 + 2          # 4 evaluation launches + pack + select
     k = int(torch.argmin(torch.nan_to_num(crit, nan=float("inf"))))
     assert out["index"] == 1000 + k and out["value"] == float(crit[k]) and out["owner"] == 0
     assert torch.equal(out["design"], des[k].cpu()) and torch.equal(out["grad"], grad[k].cpu())
+    # a second sweep over designs that a torch kernel rewrote in place: ordered, not stale
+    des.mul_(0.5).add_(0.25)
+    out2 = multistart.sweep_device(ctx, des, crit, grad, 0, chunk=65536)
+    k2 = int(torch.argmin(torch.nan_to_num(crit, nan=float("inf"))))
+    assert out2["index"] == k2 and out2["value"] == float(crit[k2])
+    c_chk = torch.empty(64, dtype=torch.float64, device="cuda")
+    ctx.eval_batch(des[k2:k2 + 64].contiguous(), c_chk, None, None)
+    assert float(c_chk[0]) == out2["value"]
+    ctx.own_stream()
+
+
+def test_pack_and_select_winner_kernels_match_their_host_mirror(built_library):
+    """dynoed_pack_winner / dynoed_select_winner against multistart.pack_local_winner / gather_winner (the
+    plain-torch specification the gloo tests run): NaN never wins, ties go to the smallest global index,
+    empty and all-NaN shards, the ring's wrap-around, fabricated multi-rank gathers."""
+    import torch
+    from dynamicoed.jl_b200 import multistart
+    ctx = make_problem("lv_fishing", D.FisherDCriterion).context()
+    nv, chunk = 71, 512
+    L = 2 + 2 * nv
+    for nb in (1, 3, 64, 5):                                  # 64 + 5 batches wrap the 64-deep ring
+        n = nb * chunk - (37 if nb > 1 else 0)
+        des = torch.from_numpy(random_designs("lv_fishing", nv, n, 900 + nb)).cuda()
+        if nb == 3:
+            des[chunk + 5, 2] = float("nan")
+        crit = torch.empty(n, dtype=torch.float64, device="cuda"); grad = torch.empty_like(des)
+        for c in range(nb):
+            a, b = c * chunk, min((c + 1) * chunk, n)
+            ctx.eval_batch(des[a:b], crit[a:b], grad[a:b], None, async_=True)
+        pay = torch.empty(L, dtype=torch.float64, device="cuda")
+        ctx.pack_winner(nb, des, grad, chunk, 10_000, pay)
+        ctx.sync()
+        vals = torch.stack([torch.nan_to_num(crit[c * chunk:(c + 1) * chunk], nan=float("inf")).min() for c in range(nb)])
+        idxs = torch.stack([torch.argmin(torch.nan_to_num(crit[c * chunk:(c + 1) * chunk], nan=float("inf"))) + c * chunk
+                            for c in range(nb)])
+        want = multistart.pack_local_winner(vals, idxs, 10_000, des, grad)
+        assert torch.equal(pay, want)
+    # empty shard
+    pay0 = torch.empty(L, dtype=torch.float64, device="cuda")
+    ctx.pack_winner(0, des[:0], grad[:0], chunk, 5, pay0, n_local=0)
+    ctx.sync()
+    assert float(pay0[0]) == float("inf") and float(pay0[1]) == -1.0 and float(pay0[2:].abs().sum()) == 0.0
+    # fabricated gathers: world = 5 with a NaN rank, an empty rank and a tie
+    g = torch.zeros((5, L), dtype=torch.float64, device="cuda")
+    g[:, 2:] = torch.arange(5, dtype=torch.float64, device="cuda")[:, None] + 0.5
+    g[:, 0] = torch.tensor([0.5, -2.0, float("nan"), -2.0, float("inf")], dtype=torch.float64)
+    g[:, 1] = torch.tensor([7.0, 9000.0, 3.0, 4105.0, -1.0], dtype=torch.float64)
+    out = torch.empty(L + 1, dtype=torch.float64, device="cuda")
+    ctx.select_winner(g, 5, out)
+    ctx.sync()
+    assert float(out[-1]) == 3.0 and float(out[0]) == -2.0 and float(out[1]) == 4105.0   # tie -> smaller global index
+    assert torch.equal(out[2:-1], g[3, 2:])
+    g[:, 1] = -1.0
+    ctx.select_winner(g, 5, out)
+    ctx.sync()
+    assert float(out[-1]) == -1.0 and float(out[0]) == float("inf") and float(out[1]) == -1.0
+    # selection on an auxiliary stream: ordered after the evaluations by an event, results identical
+    side = torch.cuda.Stream()
+    ctx.set_aux_stream(side.cuda_stream)
+    pay2 = torch.empty(L, dtype=torch.float64, device="cuda")
+    ctx.pack_winner(5, des, grad, chunk, 10_000, pay2)
+    side.synchronize()
+    assert torch.equal(pay2, pay)
+    ctx.set_aux_stream(0)
     ctx.own_stream()
