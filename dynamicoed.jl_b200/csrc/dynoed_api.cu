@@ -45,6 +45,7 @@ struct ModelEntry {
     cudaError_t (*attrs)(int method, bool grad, bool ucoef, int block, size_t smem, cudaFuncAttributes* fa,
                          int* blocks_per_sm);
     cudaError_t (*info_gain)(const EvalParams& P, const double* X, double* Pout, double* Piout, cudaStream_t st);
+    int flops_ros_jac, flops_ros_ling, flops_ros_linp, flops_ros_hvp;   // emitted Rosenbrock pieces (FMA = 2)
 };
 
 template <class K>
@@ -85,15 +86,28 @@ static cudaError_t launch_tab(bool grad, bool uc, bool pdl, const EvalParams& P,
               : launch_one<M, Tab, false, false>(pdl, P, grid, block, smem, st);
 }
 
-// CG: differentiate with respect to control values too (one dual pass each; Rosenbrock steppers)
+// directions per integration pass of the forward-mode gradient kernels (DYNOED_ROS_NDIR at build time)
+#ifndef DYNOED_ROS_NDIR
+#define DYNOED_ROS_NDIR 2
+#endif
+// Up to DYNOED_ROS_NDIR directions share one pass (and its value computations); four-stage schemes keep
+// one direction per pass — with two the stage vectors of models of chem6's size spill so much that the
+// pass is slower than two single-direction passes (measured on B200: RODAS3 2.4e6 vs 2.8e6 designs/s).
+template <class M, bool CG, class Stepper>
+constexpr int ros_ndir() {
+    constexpr int cap = Stepper::STAGES >= 4 ? 1 : DYNOED_ROS_NDIR;
+    return (CG && M::NCTRL > 0) ? cap : (M::NIC > 0 && M::NIC < cap ? M::NIC : M::NIC > 0 ? cap : 1);
+}
+
+// CG: differentiate with respect to control values too (Rosenbrock steppers)
 template <class M, class Stepper, bool GRAD, bool CG = false>
 static cudaError_t launch_ros(bool pdl, const EvalParams& P, int grid, int block, size_t smem, cudaStream_t st) {
-    return launch_kernel(ros_eval_kernel<M, Stepper, GRAD, CG>, pdl, P, grid, block, smem, st);
+    return launch_kernel(ros_eval_kernel<M, Stepper, GRAD, CG, ros_ndir<M, CG, Stepper>()>, pdl, P, grid, block, smem, st);
 }
 
 template <class M, class Stepper, bool GRAD, bool CG = false>
 static cudaError_t attrs_ros(int block, size_t smem, cudaFuncAttributes* fa, int* bps) {
-    auto kern = ros_eval_kernel<M, Stepper, GRAD, CG>;
+    auto kern = ros_eval_kernel<M, Stepper, GRAD, CG, ros_ndir<M, CG, Stepper>()>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(fa, kern);
@@ -205,6 +219,9 @@ static ModelEntry make_entry() {
     for (int k = 0; k < M::NX; ++k) i.x0[k] = M::default_x0()[k];
     for (int k = 0; k < M::NX * M::NP; ++k) i.G0[k] = M::default_G0()[k];
     for (int k = 0; k < M::NTH; ++k) i.theta[k] = M::default_theta()[k];
+    e.flops_ros_jac = M::FLOPS_ROS_JAC; e.flops_ros_ling = M::FLOPS_ROS_LING;
+    e.flops_ros_linp = M::FLOPS_ROS_LINP; e.flops_ros_hvp = M::FLOPS_ROS_HVP;
+
     e.launch = &launch_model<M>;
     e.attrs = &attrs_model<M>;
     e.info_gain = &info_gain_model<M>;
@@ -325,7 +342,7 @@ struct dynoed_ctx {
     uint32_t call_flags = 0;                 // flags of the call being served
     std::vector<int> h_first;                // host copy of first_step[N+1]
     size_t l2_bytes = 0;
-    double l2_hot_frac = 0.5;                // share of L2 the top of the checkpoint stack may occupy
+    double l2_hot_frac = 1.0;                // share of L2 the top of the checkpoint stack may occupy
     cudaStream_t aux_stream = nullptr;       // selection helpers run here when set (dynoed_set_aux_stream)
     cudaEvent_t ev_aux = nullptr;
     struct HessScratch {               // dynoed_hessian_batch: perturbed batch + staging, grown on demand
@@ -1692,8 +1709,46 @@ int dynoed_kernel_stats_query(dynoed_ctx* ctx, int with_grad, dynoed_kernel_stat
                        2.0 * S * (mi.nz + mi.n_ctrl);
     const double bwd_iv = (double)mi.n_obs * (1 + mi.nF) + 2.0 * nq + mi.flops_consts;
     const double epi = 10.0 * mi.nF;
-    if (ctx->rosenbrock) {   // no frozen flop count for the Rosenbrock kernels (not a roofline-reported path)
-        o->flops_per_design_eval = o->flops_per_design_grad = 0.0;
+    if (ctx->rosenbrock) {
+        // Rosenbrock kernels (config 4), algorithmic flops per design, FMA = 2:
+        //   step   : f_x (ros_jac) + nx for W = c0 I - f_x + pivoted LU (1 + (n-1-k) + 2 (n-1-k)^2 per pivot)
+        //   stage  : stage state (2 NZ per a_ij) and g = ros_f unless the tableau reuses the previous stage
+        //            state; right-hand side (2 (NZ + NQ) per c_ij); 1 + np triangular solves (2 nx (nx-1) + nx
+        //            each) + ros_ling + nx np; quadrature rows ros_linp + 2 NQ
+        //   update : 2 (NZ + NQ) per stage with m_s != 0;   interval: F += w P (2 NQ)
+        //   every gradient DIRECTION adds the tangent of all of that except the factorisation: twice the
+        //   function / combination flops (dual-number product rule) + its own 1 + np solves with the value
+        //   factors + ros_hvp + nx per solve; a pass carries NDIR directions and recomputes the values.
+        const int nx = mi.nx, np_ = mi.np, nz = mi.nz, nqq = mi.n_obs * mi.nF;
+        int Sr = 0, na = 0, nc = 0, nm = 0, nf = 0;
+        auto tab = [&](auto RT) {
+            using R = decltype(RT);
+            Sr = R::S;
+            for (int i = 0; i < R::S; ++i) {
+                nm += R::m(i) != 0.0;
+                nf += !R::same_stage_state(i);
+                for (int j = 0; j < i; ++j) { na += (!R::same_stage_state(i)) && R::a(i, j) != 0.0; nc += R::c(i, j) != 0.0; }
+            }
+        };
+        if (ctx->method == DYNOED_ROS2) tab(TabROS2{}); else if (ctx->method == DYNOED_ROS3P) tab(TabROS3P{}); else tab(TabRODAS3{});
+        double lu = 0.0;
+        for (int k = 0; k < nx; ++k) lu += 1.0 + (nx - 1 - k) + 2.0 * (nx - 1 - k) * (nx - 1 - k);
+        const double solve = 2.0 * nx * (nx - 1) + nx;
+        const double fun = (double)nf * mi.flops_ros_f + (double)Sr * (ctx->model->flops_ros_ling + ctx->model->flops_ros_linp);
+        const double comb = 2.0 * nz * na + (2.0 * (nz + nqq) + 1.0) * nc + (double)Sr * (nx * np_ + 2.0 * nqq) + 2.0 * (nz + nqq) * nm;
+        const double solves = (double)Sr * (1 + np_) * solve;
+        const double val_step = ctx->model->flops_ros_jac + nx + lu + fun + comb + solves;
+        const double dir_step = 2.0 * (fun + comb) + solves + (double)Sr * (1 + np_) * (ctx->model->flops_ros_hvp + nx);
+        const double val = val_step * ctx->n_steps + (double)ctx->n_intervals * (2.0 * nqq + mi.flops_consts) + epi;
+        const bool cgrad = g == 1 && mi.n_ctrl > 0;
+        const int ndirs = mi.n_ic + (cgrad ? ctx->base.n_ctrl_values : 0);
+        const int cap = Sr >= 4 ? 1 : DYNOED_ROS_NDIR;   // ros_ndir()
+        const int per_pass = cgrad ? cap : std::max(1, std::min(cap, (int)mi.n_ic));
+        const int passes = ndirs > 0 ? (ndirs + per_pass - 1) / per_pass : 1;
+        o->flops_per_design_eval = val;
+        // d/dw, d/dtau from the stored quadratures: 2 NQ per interval
+        o->flops_per_design_grad = passes * val + ndirs * (dir_step * ctx->n_steps + 4.0 * nqq * ctx->n_intervals) +
+                                   2.0 * nqq * ctx->n_intervals;
         o->bytes_per_design = 8.0 * (ctx->n_var + 1 + (with_grad ? ctx->n_var : 0) + mi.nF);
         return DYNOED_OK;
     }

@@ -178,6 +178,86 @@ struct SmallLU {
 };
 
 // ----------------------------------------------------------------------------------------------
+// The linear systems of one step:  W U = b  with  W = 1/(h gamma) I - f_x(x_n).
+// Plain doubles: one pivoted LU.  Forward-mode duals (gradient directions): the factorisation is
+// still the VALUE factorisation W0; a direction's part follows from differentiating the system,
+//     W0 U1 = b1 - W1 U0 = b1 + (d f_x . direction) U0 ,
+// with the second-derivative product emitted sparsely (Model::ros_hvp).  A dual-number LU would
+// triple the factorisation work and double its registers (36 more doubles for nx = 6).
+// ----------------------------------------------------------------------------------------------
+template <class M, class T>
+struct StepSolver;
+
+template <class M>
+struct StepSolver<M, double> {
+    SmallLU<double, M::NX> lu;
+    __device__ __forceinline__ void init(double t, double c0, const double* z, const double* u, const double* th,
+                                         const double* c) {
+        constexpr int NX = M::NX;
+        double A[NX * NX];
+        M::template ros_jac<double>(t, z, u, th, c, A);
+#pragma unroll
+        for (int i = 0; i < NX; ++i)
+#pragma unroll
+            for (int j = 0; j < NX; ++j) lu.a[i][j] = (i == j ? c0 : 0.0) - A[i * NX + j];
+        lu.factor();
+    }
+    __device__ __forceinline__ void solve(double (&b)[M::NX]) const { lu.solve(b); }
+};
+
+template <class M, int K>
+struct StepSolver<M, Dual<K>> {
+    static constexpr int NX = M::NX, NCU = M::NCTRL > 0 ? M::NCTRL : 1;
+    SmallLU<double, NX> lu;
+    double xv[NX], xd[K][NX], uv[NCU], ud[K][NCU], cv[M::NCONST];
+    double t;
+    const double* th;
+    __device__ __forceinline__ void init(double t_, double c0, const Dual<K>* z, const Dual<K>* u, const double* th_,
+                                         const Dual<K>* c) {
+        t = t_; th = th_;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            xv[i] = z[i].v;
+#pragma unroll
+            for (int d = 0; d < K; ++d) xd[d][i] = z[i].d[d];
+        }
+#pragma unroll
+        for (int k = 0; k < M::NCTRL; ++k) {
+            uv[k] = u[k].v;
+#pragma unroll
+            for (int d = 0; d < K; ++d) ud[d][k] = u[k].d[d];
+        }
+#pragma unroll
+        for (int k = 0; k < M::NCONST; ++k) cv[k] = c[k].v;
+        double A[NX * NX];
+        M::template ros_jac<double>(t, xv, uv, th, cv, A);
+#pragma unroll
+        for (int i = 0; i < NX; ++i)
+#pragma unroll
+            for (int j = 0; j < NX; ++j) lu.a[i][j] = (i == j ? c0 : 0.0) - A[i * NX + j];
+        lu.factor();
+    }
+    __device__ __forceinline__ void solve(Dual<K> (&b)[NX]) const {
+        double b0[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) b0[i] = b[i].v;
+        lu.solve(b0);
+#pragma unroll
+        for (int d = 0; d < K; ++d) {
+            double hv[NX], b1[NX];
+            M::ros_hvp(t, xv, xd[d], uv, ud[d], th, cv, b0, hv);
+#pragma unroll
+            for (int i = 0; i < NX; ++i) b1[i] = b[i].d[d] + hv[i];
+            lu.solve(b1);
+#pragma unroll
+            for (int i = 0; i < NX; ++i) b[i].d[d] = b1[i];
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) b[i].v = b0[i];
+    }
+};
+
+// ----------------------------------------------------------------------------------------------
 // One Rosenbrock step on y = [z (x, G); Pq (unweighted quadratures)]
 // ----------------------------------------------------------------------------------------------
 template <class M, class RT, class T>
@@ -186,16 +266,8 @@ __device__ __forceinline__ void rosenbrock_step(double t, double h, T (&z)[M::NZ
     constexpr int S = RT::S, NX = M::NX, NP = M::NP, NZ = M::NZ, NQ = M::NOBS * M::NF;
     const double c0 = 1.0 / (h * RT::gamma);
     const double ih = 1.0 / h;
-    SmallLU<T, NX> lu;
-    {
-        T A[NX * NX];
-        M::template ros_jac<T>(t, z, u, th, c, A);
-#pragma unroll
-        for (int i = 0; i < NX; ++i)
-#pragma unroll
-            for (int j = 0; j < NX; ++j) lu.a[i][j] = (i == j ? c0 : 0.0) - A[i * NX + j];
-    }
-    lu.factor();
+    StepSolver<M, T> lu;
+    lu.init(t, c0, z, u, th, c);
     T Uz[S][NZ], Uq[S][NQ];
     T gz[NZ], gq[NQ];
 #pragma unroll
@@ -272,6 +344,7 @@ __device__ __forceinline__ void rosenbrock_step(double t, double h, T (&z)[M::NZ
 // ----------------------------------------------------------------------------------------------
 template <class RT>
 struct RosenbrockStepper {
+    static constexpr int STAGES = RT::S;
     template <class M, class T>
     __device__ __forceinline__ static void step(double t, double h, T (&z)[M::NZ], T (&Pq)[M::NOBS * M::NF],
                                                 const T* u, const double* th, const T* c) {
@@ -281,6 +354,7 @@ struct RosenbrockStepper {
 
 template <class Tab>
 struct ExplicitStepper {
+    static constexpr int STAGES = Tab::S;
     template <class M, class T>
     __device__ __forceinline__ static void step(double t, double h, T (&z)[M::NZ], T (&Pq)[M::NOBS * M::NF],
                                                 const T* u, const double* th, const T* c) {
@@ -320,18 +394,17 @@ struct ExplicitStepper {
 // comment for the gradient).  Control entries of the gradient are NaN ("not computed").
 // P.traj is used as the per-interval quadrature scratch [grid][N][NOBS*NF][kMaxTile].
 // ----------------------------------------------------------------------------------------------
-template <class M, class Stepper, bool GRAD, bool CTRLGRAD>
+template <class M, class Stepper, bool GRAD, bool CTRLGRAD, int NDIR>
 __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams P) {
     constexpr int NX = M::NX, NP = M::NP, NZ = M::NZ, NF = M::NF, NOBS = M::NOBS, NCTRL = M::NCTRL;
     constexpr int NCU = NCTRL > 0 ? NCTRL : 1, NQ = NOBS * NF;
-    // unknown initial conditions: ONE dual direction per integration pass (NIC passes).  Carrying all
-    // directions at once (Dual<NIC>) is 1 + NIC units of arithmetic instead of 2 NIC, but its register
-    // footprint spills 3.6-4.9 KB per lane for models of chem6's size (2.3-2.9 KB this way) and
-    // measured 1.1x (ROS2) to 1.4x (ROS3P) slower on B200.
-    // CTRLGRAD (Rosenbrock with controls): one more pass per control VALUE of the design vector.
+    // gradient directions (unknown initial conditions, and with CTRLGRAD every control VALUE of the design
+    // vector) are carried as forward-mode dual parts, NDIR directions per integration pass.  The linear
+    // systems of every direction are solved with the value factorisation (StepSolver): a pass costs about
+    // 1 + NDIR units of a plain integration.
     constexpr bool CG = GRAD && CTRLGRAD && M::NCTRL > 0;
     constexpr bool DUAL = GRAD && (M::NIC > 0 || CG);
-    using T = typename std::conditional<DUAL, Dual<1>, double>::type;
+    using T = typename std::conditional<DUAL, Dual<NDIR>, double>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     double* tile_buf = reinterpret_cast<double*>(smem_raw + 128);
@@ -377,15 +450,19 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams 
             double Ls[NF], L[NF], icg[M::NIC > 0 ? M::NIC : 1];
             const int ndir = DUAL ? M::NIC + (CG ? P.n_ctrl_values : 0) : 1;
             // direction -> (control k, entry idx) for dir >= NIC: controls are laid out block after block
-            for (int dir = 0; dir < (ndir > 0 ? ndir : 1); ++dir) {
-                int dk = -1, didx = -1;
-                if (CG && dir >= M::NIC) {
-                    int rest = dir - M::NIC;
+            for (int dir0 = 0; dir0 < (ndir > 0 ? ndir : 1); dir0 += NDIR) {
+                int dk[NDIR], didx[NDIR];
 #pragma unroll
-                    for (int k = 0; k < NCTRL; ++k) {
-                        if (dk < 0) {
-                            if (rest < P.ctrl_len[k]) { dk = k; didx = rest; }
-                            else rest -= P.ctrl_len[k];
+                for (int q = 0; q < NDIR; ++q) {
+                    dk[q] = -1; didx[q] = -1;
+                    if (CG && dir0 + q >= M::NIC && dir0 + q < ndir) {
+                        int rest = dir0 + q - M::NIC;
+#pragma unroll
+                        for (int k = 0; k < NCTRL; ++k) {
+                            if (dk[q] < 0) {
+                                if (rest < P.ctrl_len[k]) { dk[q] = k; didx[q] = rest; }
+                                else rest -= P.ctrl_len[k];
+                            }
                         }
                     }
                 }
@@ -398,13 +475,16 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams 
 #pragma unroll
                     for (int a = 0; a < M::NIC; ++a) {
                         T v(row[P.ic_off + a]);
-                        if constexpr (GRAD) v.d[0] = (a == dir) ? 1.0 : 0.0;
+                        if constexpr (GRAD) {
+#pragma unroll
+                            for (int q = 0; q < NDIR; ++q) v.d[q] = (a == dir0 + q) ? 1.0 : 0.0;
+                        }
                         z[M::ic_state(a)] = v;
                     }
                 }
 #pragma unroll
                 for (int a = 0; a < NF; ++a) F[a] = T(0.0);
-                double* xg = (P.xgrid && dir == 0) ? P.xgrid + (size_t)g * (N + 1) * (NZ + NF) : nullptr;
+                double* xg = (P.xgrid && dir0 == 0) ? P.xgrid + (size_t)g * (N + 1) * (NZ + NF) : nullptr;
                 if (xg) {
 #pragma unroll
                     for (int a = 0; a < NZ; ++a) xg[a] = value_of(z[a]);
@@ -418,7 +498,10 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams 
                     for (int k = 0; k < NCTRL; ++k) {
                         const int idx = __ldg(P.indicators + k * N + j);
                         u[k] = T(row[P.ctrl_off[k] + idx]);
-                        if constexpr (CG) u[k].d[0] = (k == dk && idx == didx) ? 1.0 : 0.0;
+                        if constexpr (CG) {
+#pragma unroll
+                            for (int q = 0; q < NDIR; ++q) u[k].d[q] = (k == dk[q] && idx == didx[q]) ? 1.0 : 0.0;
+                        }
                     }
 #pragma unroll
                     for (int i = 0; i < NOBS; ++i) w[i] = row[P.w_off[i] + __ldg(P.indicators + (NCTRL + i) * N + j)];
@@ -433,7 +516,7 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams 
                     for (int i = 0; i < NOBS; ++i)
 #pragma unroll
                         for (int k = 0; k < NF; ++k) F[k] = F[k] + w[i] * Pq[i * NF + k];
-                    if (GRAD && dir == 0) {
+                    if (GRAD && dir0 == 0) {
 #pragma unroll
                         for (int a = 0; a < NQ; ++a) pq[((size_t)j * NQ + a) * kMaxTile] = value_of(Pq[a]);
                     }
@@ -446,7 +529,7 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams 
                     }
                 }
 
-                if (dir == 0) {
+                if (dir0 == 0) {
                     // ---- criterion epilogue ----
                     const double tau = row[P.tau_off];
                     double Fv[NF], value;
@@ -466,13 +549,16 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams 
                         for (int ii = 0; ii <= jj; ++ii) Ls[tri(ii, jj)] = (ii == jj ? 1.0 : 2.0) * L[tri(ii, jj)];
                 }
                 if constexpr (DUAL) {   // <Lambda, dF/d(direction)> with the symmetric pairing
-                    double sd = 0.0;
 #pragma unroll
-                    for (int k = 0; k < NF; ++k) sd = fma(Ls[k], dual_part(F[k], 0), sd);
+                    for (int q = 0; q < NDIR; ++q) {
+                        double sd = 0.0;
 #pragma unroll
-                    for (int a = 0; a < M::NIC; ++a)
-                        if (a == dir) icg[a] = sd;          // static indexing keeps icg in registers
-                    if (CG && dir >= M::NIC) cg[(size_t)(dir - M::NIC) * kMaxTile] = sd;
+                        for (int k = 0; k < NF; ++k) sd = fma(Ls[k], dual_part(F[k], q), sd);
+#pragma unroll
+                        for (int a = 0; a < M::NIC; ++a)
+                            if (a == dir0 + q) icg[a] = sd;          // static indexing keeps icg in registers
+                        if (CG && dir0 + q >= M::NIC && dir0 + q < ndir) cg[(size_t)(dir0 + q - M::NIC) * kMaxTile] = sd;
+                    }
                 }
             }
 

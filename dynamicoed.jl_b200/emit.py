@@ -454,6 +454,28 @@ def emit_model(name: str, s: SimplifiedOEDSystem) -> tuple[str, dict]:
                 b.out(f"BU[{j * nx + i}]", e)
         return b
 
+    # ros_hvp: (d f_x / d eps) U for the direction (xd, ud) of (x, controls) — what a forward-mode
+    # direction needs to reuse the VALUE factorisation of  W = 1/(h gamma) I - f_x :
+    #   W0 U1 = r1 - W1 U0 = r1 + (d f_x . (xd, ud)) U0
+    xds = [sp.Symbol(f"xd{k}", real=True) for k in range(nx)]
+    uds = [sp.Symbol(f"ud{k}", real=True) for k in range(nc)]
+    for k, v in enumerate(xds):
+        names[v] = f"xd[{k}]"
+    for k, v in enumerate(uds):
+        names[v] = f"ud[{k}]"
+
+    def build_ros_hvp():
+        b = _Block()
+        for i in range(nx):
+            e = 0
+            for j in range(nx):
+                dA = sum(sp.diff(J[i, j], x[k]) * xds[k] for k in range(nx)) + \
+                    sum(sp.diff(J[i, j], s.controls[m]) * uds[m] for m in range(nc))
+                if dA != 0:
+                    e = e + H(sp.expand(dA)) * Usym[j]
+            b.out(f"out[{i}]", e)
+        return b
+
     def build_ros_linp():
         b = _Block()
         zs = x + [G[i, j] for j in range(np_) for i in range(nx)]
@@ -467,7 +489,7 @@ def emit_model(name: str, s: SimplifiedOEDSystem) -> tuple[str, dict]:
     blocks = OrderedDict(primal_z=build_primal(),
                          adjoint=build_adjoint(), obs=build_obs(), ros_f=build_ros_f(),
                          ros_jac=build_ros_jac(), ros_ling=build_ros_ling(),
-                         ros_linp=build_ros_linp())
+                         ros_linp=build_ros_linp(), ros_hvp=build_ros_hvp())
     for k, v in enumerate(hoist.table.values()):
         names[v] = f"c[{k}]"
     pr = _Printer(names)
@@ -475,7 +497,7 @@ def emit_model(name: str, s: SimplifiedOEDSystem) -> tuple[str, dict]:
     inputs = set(names.keys())
     code, flops = {}, {}
     for key, blk in blocks.items():
-        tmpl = key.startswith("ros_")
+        tmpl = key.startswith("ros_") and key != "ros_hvp"
         code[key], flops[key] = blk.render(pr if tmpl else prf, inputs, scalar="T" if tmpl else "double")
     # what one forward stage of the explicit integrators evaluates: (x, G) right-hand side + Q
     flops["primal"] = flops["primal_z"] + flops["obs"]
@@ -514,6 +536,8 @@ struct {cname} {{
     static constexpr int FLOPS_ADJOINT = {flops['adjoint']}, FLOPS_CONSTS = {flops['consts']};
     static constexpr int FLOPS_OBS = {flops['obs']};
     static constexpr int FLOPS_ROS_F = {flops['ros_f']};
+    static constexpr int FLOPS_ROS_JAC = {flops['ros_jac']}, FLOPS_ROS_LING = {flops['ros_ling']};
+    static constexpr int FLOPS_ROS_LINP = {flops['ros_linp']}, FLOPS_ROS_HVP = {flops['ros_hvp']};
     static constexpr const char* NAME = "{name}";
     __host__ __device__ static constexpr int ic_state(int i) {{
         constexpr int v[{max(n_ic, 1)}] = {{{arr(ic_state, '{}')}}};
@@ -585,6 +609,14 @@ struct {cname} {{
             const T* __restrict__ u, const double* __restrict__ th,
             const T* __restrict__ c, const T* __restrict__ U, T* __restrict__ dPU) {{
 {code['ros_linp']}
+    }}
+    // out = (d f_x / d eps) U  along the direction (xd, ud) of (states, controls): lets a forward-mode
+    // direction be solved with the VALUE factorisation of 1/(h gamma) I - f_x
+    __device__ __forceinline__ static void ros_hvp(double t, const double* __restrict__ z,
+            const double* __restrict__ xd, const double* __restrict__ u, const double* __restrict__ ud,
+            const double* __restrict__ th, const double* __restrict__ c,
+            const double* __restrict__ U, double* __restrict__ out) {{
+{code['ros_hvp']}
     }}
 }};
 """

@@ -395,6 +395,30 @@ def criterion_batch(criterion: int, F_packed, tau=None, with_gradient=False, dev
     return (val, dL) if with_gradient else val
 
 
+def gpu_numa_cpus(device: int = 0):
+    """(NUMA node, sorted CPU list) of the host CPUs closest to CUDA device `device`, from sysfs; (None, [])
+    when the box does not expose it.  A host thread that feeds the GPU from page-locked memory should run,
+    and allocate that memory, on these CPUs: `os.sched_setaffinity(0, cpus)` before the first allocation."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device), "pci_domain_id", 0)
+        devid = getattr(torch.cuda.get_device_properties(device), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devid:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None, []
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(c for c in cpus if c in allowed)
+        return node, cpus
+    except Exception:
+        return None, []
+
+
 def fp64_peak(device: int = 0, stream_ptr=None):
     t, ms = C.c_double(), C.c_double()
     _check(lib().dynoed_fp64_peak(device, C.c_void_p(stream_ptr) if stream_ptr else None,

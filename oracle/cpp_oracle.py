@@ -120,7 +120,9 @@ def step_table(tgrid, substeps=None, edges=None):
 
 
 class CppOracle:
-    def __init__(self, model: str, py_oracle, native: bool = False):
+    def __init__(self, model: str, py_oracle, native: bool = False, own_constants: bool = False):
+        """own_constants: use the model constants hard-coded in oed_oracle.cpp from the reference's test files
+        (lv_fishing, one_d) instead of the ones `py_oracle` took from the product's models.py."""
         o = py_oracle
         self.o = o
         self._native = native
@@ -149,6 +151,9 @@ class CppOracle:
         d.ind, d.ctrl_off, d.w_off = a["ind"].ctypes.data, a["ctrl"].ctypes.data, a["w"].ctypes.data
         d.ic_off, d.tau_off = lay.ic_offset, lay.tau_offset
         d.theta, d.x0, d.G0 = a["theta"].ctypes.data, a["x0"].ctypes.data, a["G0"].ctypes.data
+        if own_constants:
+            assert model in ("lv_fishing", "one_d")
+            d.theta = d.x0 = d.G0 = None
         self.d = d
 
     def set_criterion(self, crit: int):

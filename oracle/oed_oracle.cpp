@@ -515,12 +515,26 @@ struct oracle_desc {
     const double* theta; const double* x0; const double* G0;
 };
 
+// Model constants written down HERE from the reference's own test files, for callers that pass
+// theta / x0 / G0 = NULL: an oracle fed from the product's models.py would share a wrong constant with it.
+//   lv_fishing: /root/reference/test/references/LotkaVolterra.jl:11 (x = 0.5, y = 0.7), :13-17
+//               (p = [1.0; 1.0; 0.4; 0.6], c = [1.0; 1.0]); no unknown initial conditions => G0 = 0
+//   one_d     : /root/reference/test/references/1D.jl:15-16 (x = 1.0, p = -2.0)
+static bool own_constants(int model, const double** th, const double** x0, const double** G0) {
+    static const double lv_th[6] = {1.0, 1.0, 0.4, 0.6, 1.0, 1.0}, lv_x0[2] = {0.5, 0.7}, zeros[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    static const double od_th[1] = {-2.0}, od_x0[1] = {1.0};
+    if (model == 2) { *th = lv_th; *x0 = lv_x0; *G0 = zeros; return true; }
+    if (model == 0) { *th = od_th; *x0 = od_x0; *G0 = zeros; return true; }
+    return false;
+}
+
 static Grid to_grid(const oracle_desc* d) {
     Grid g;
     g.N = d->N; g.n_var = d->n_var; g.method = d->method; g.crit = d->crit; g.tgrid = d->tgrid;
     g.first_step = d->first_step; g.step_t = d->step_t; g.step_h = d->step_h; g.ind = d->ind;
     g.ctrl_off = d->ctrl_off; g.w_off = d->w_off; g.ic_off = d->ic_off; g.tau_off = d->tau_off;
     g.theta = d->theta; g.x0 = d->x0; g.G0 = d->G0;
+    if (!d->theta && !d->x0 && !d->G0) own_constants(d->model, &g.theta, &g.x0, &g.G0);
     return g;
 }
 
