@@ -118,51 +118,70 @@ struct TabRODAS3 {
 };
 
 // ----------------------------------------------------------------------------------------------
-// LU with partial pivoting of a small matrix held in registers.  Row exchanges are done with
-// compare-and-swap over statically indexed rows (no dynamic register indexing => no local memory);
-// the right-hand sides are permuted the same way at solve time.
+// LU with partial pivoting of a small matrix held in registers.  Row exchanges are SELECTS over
+// statically indexed rows (no dynamic register indexing: ptxas otherwise moves the whole matrix to local
+// memory and swaps rows through an address), and they are skipped altogether when no lane of the
+// converged warp needs one at this elimination step — the common case for W = 1/(h gamma) I - f_x,
+// which is close to column diagonally dominant.  The vote only decides whether the (always correct)
+// select code runs, so results do not depend on which lanes share a warp.
 // ----------------------------------------------------------------------------------------------
+template <class T>
+__device__ __forceinline__ void select_swap(bool sw, T& x, T& y) {
+    const T tx = x, ty = y;
+    x = sw ? ty : tx;
+    y = sw ? tx : ty;
+}
+
 template <class T, int N>
 struct SmallLU {
     T a[N][N];
-    int piv[N];   // piv[k] = row exchanged with row k at elimination step k
+    int piv[N];        // piv[k] = row exchanged with row k at elimination step k
+    unsigned swaps;    // bit k set: some lane of the warp exchanged rows at step k (warp-uniform)
 
-    __device__ __forceinline__ void factor() {
+    // one elimination step per template instantiation: a `#pragma unroll` loop over k is NOT fully
+    // unrolled once the warp vote is inside it, and a run-time k puts the matrix in local memory
+    template <int k>
+    __device__ __forceinline__ void factor_step() {
+        int p = k;
+        double best = fabs(value_of(a[k][k]));
 #pragma unroll
-        for (int k = 0; k < N; ++k) {
-            int p = k;
-            double best = fabs(value_of(a[k][k]));
-#pragma unroll
-            for (int i = k + 1; i < N; ++i) {
-                const double v = fabs(value_of(a[i][k]));
-                if (v > best) { best = v; p = i; }
-            }
-            piv[k] = p;
-#pragma unroll
-            for (int i = k + 1; i < N; ++i) {
-                if (p == i) {   // exchange the active part only: earlier multipliers stay put, which
-                                // is what the interleaved swap/eliminate order of solve() assumes
-#pragma unroll
-                    for (int j = k; j < N; ++j) { const T t = a[k][j]; a[k][j] = a[i][j]; a[i][j] = t; }
-                }
-            }
-            const T inv = 1.0 / a[k][k];
-            a[k][k] = inv;   // the diagonal keeps 1 / pivot
+        for (int i = k + 1; i < N; ++i) {
+            const double v = fabs(value_of(a[i][k]));
+            if (v > best) { best = v; p = i; }
+        }
+        piv[k] = p;
+        if (k + 1 < N && __any_sync(__activemask(), p != k)) {
+            swaps |= 1u << k;
+            // exchange the active part only: earlier multipliers stay put, which is what the
+            // interleaved swap/eliminate order of solve() assumes
 #pragma unroll
             for (int i = k + 1; i < N; ++i) {
-                const T l = a[i][k] * inv;
-                a[i][k] = l;
+                const bool sw = (p == i);
 #pragma unroll
-                for (int j = k + 1; j < N; ++j) a[i][j] = a[i][j] - l * a[k][j];
+                for (int j = k; j < N; ++j) select_swap(sw, a[k][j], a[i][j]);
             }
         }
+        const T inv = 1.0 / a[k][k];
+        a[k][k] = inv;   // the diagonal keeps 1 / pivot
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) {
+            const T l = a[i][k] * inv;
+            a[i][k] = l;
+#pragma unroll
+            for (int j = k + 1; j < N; ++j) a[i][j] = a[i][j] - l * a[k][j];
+        }
+        if constexpr (k + 1 < N) factor_step<k + 1>();
+    }
+    __device__ __forceinline__ void factor() {
+        swaps = 0u;
+        factor_step<0>();
     }
     __device__ __forceinline__ void solve(T (&b)[N]) const {
 #pragma unroll
         for (int k = 0; k < N; ++k) {
+            if (swaps & (1u << k)) {
 #pragma unroll
-            for (int i = k + 1; i < N; ++i) {
-                if (piv[k] == i) { const T t = b[k]; b[k] = b[i]; b[i] = t; }
+                for (int i = k + 1; i < N; ++i) select_swap(piv[k] == i, b[k], b[i]);
             }
 #pragma unroll
             for (int i = k + 1; i < N; ++i) b[i] = b[i] - a[i][k] * b[k];
@@ -619,6 +638,421 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams 
                 __syncthreads();
             }
         } else {
+            __syncthreads();
+        }
+    }
+    argmin_tail(P, best_val, best_idx);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Rosenbrock gradient kernel for UNKNOWN INITIAL CONDITIONS (BASELINE.json config 4: stiff kinetics,
+// ~6 states, 12 sensitivities, Fisher criteria).  d objective / d ic_a needs dF/d ic_a, i.e. the
+// second-order sensitivities H_(j,a) = dG_j/d ic_a.  Differentiating a Rosenbrock scheme that uses
+// the exact Jacobian gives the same scheme on the system extended by H and dP = dP/d ic (emit.py,
+// "second-order pieces"), whose Jacobian is still block lower triangular with diagonal block f_x:
+// every H column is one more right-hand side for the step's ONE value factorisation.  Compared
+// with forward-mode dual numbers through the whole step this (a) does not carry d x/d ic_a twice
+// (it IS a G column), (b) uses H_(j,a) = H_(a,j), (c) evaluates only the non-zero second derivatives.
+//
+// Registers cannot hold the extended state and its S stage increments (chem6: 54 + 54 S doubles), so
+// the step is ordered by COLUMN and only what later columns need is kept, in shared memory:
+//   phase 1  (x, G, P) stage by stage as in ros_eval_kernel; the increments U_s of (x, G) go to
+//            shared memory  [S][NZ][tile]
+//   phase 2  one H column at a time through all S stages: stage states of (x, G) are rebuilt from y_n
+//            (registers) and the stored increments; the column's own increments live in registers for
+//            the duration of the column; its share of the dP rows is accumulated (the stage recursion of
+//            the quadrature rows is linear, so each column applies it to its own contribution)
+//   phase 3  y_n <- y_n + sum_s m_s U_s
+// Shared memory per lane: (S + NH/NP... ) see Ic2Layout; each lane touches only its own slots, so the
+// phases need no barrier.
+// ----------------------------------------------------------------------------------------------
+template <class M, class RT>
+struct Ic2Layout {
+    static constexpr int S = RT::S;
+    static constexpr int U = 0;                          // [S][NZ] increments of (x, G)
+    static constexpr int HN = U + S * M::NZ;             // [NH][NX] second-order sensitivities at y_n
+    static constexpr int SLOTS = HN + M::NH * M::NX;     // doubles per lane
+};
+
+template <class RT, int NZ>
+struct StageZ {                       // Z_s[k] = y_n[k] + sum_j a_sj U_j[k]
+    const double (&z)[NZ];
+    const double* U;
+    int s;
+    __device__ __forceinline__ double operator[](int k) const {
+        double v = z[k];
+#pragma unroll
+        for (int j = 0; j < RT::S; ++j)
+            if (j < s && RT::a(s, j) != 0.0) v = fma(RT::a(s, j), U[(size_t)(j * NZ + k) * kMaxTile], v);
+        return v;
+    }
+};
+template <int NZ>
+struct StageU {
+    const double* U;
+    int s;
+    __device__ __forceinline__ double operator[](int k) const { return U[(size_t)(s * NZ + k) * kMaxTile]; }
+};
+
+template <class M, class RT, int Q>
+struct Ic2Column {
+    __device__ __forceinline__ static void run(double t, double ih, double ic0, const StepSolver<M, double>& lu,
+                                               const double (&z)[M::NZ], double (&dP)[M::NOBS * M::NF * M::NIC],
+                                               double* __restrict__ sm, const double* u, const double* th) {
+        constexpr int S = RT::S, NX = M::NX, NZ = M::NZ, NQ2 = M::NOBS * M::NF * M::NIC;
+        constexpr unsigned long long rows = M::ic2_qrows(Q);
+        using Lay = Ic2Layout<M, RT>;
+        const double* Us = sm + (size_t)Lay::U * kMaxTile;
+        double* Hs = sm + (size_t)(Lay::HN + Q * NX) * kMaxTile;
+        double Hn[NX], UH[S][NX], Ud[S][NQ2];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) Hn[i] = Hs[(size_t)i * kMaxTile];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const StageZ<RT, NZ> zs{z, Us, s};
+            const StageU<NZ> us{Us, s};
+            double ZH[NX], r[NX], b[NX];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) {
+                double v = Hn[i];
+#pragma unroll
+                for (int j = 0; j < s; ++j)
+                    if (RT::a(s, j) != 0.0) v = fma(RT::a(s, j), UH[j][i], v);
+                ZH[i] = v;
+            }
+            M::template ic2_rhs<Q>(t, zs, ZH, u, th, r);
+            M::template ic2_lin<Q>(t, z, Hn, us, u, th, b);
+#pragma unroll
+            for (int i = 0; i < NX; ++i) {
+                double v = r[i] + b[i];
+#pragma unroll
+                for (int j = 0; j < s; ++j)
+                    if (RT::c(s, j) != 0.0) v = fma(RT::c(s, j) * ih, UH[j][i], v);
+                r[i] = v;
+            }
+            lu.solve(r);
+#pragma unroll
+            for (int i = 0; i < NX; ++i) UH[s][i] = r[i];
+            if constexpr (rows != 0ull) {
+                double acc[NQ2];
+#pragma unroll
+                for (int a = 0; a < NQ2; ++a) acc[a] = 0.0;
+                M::template ic2_qcol<Q>(t, zs, ZH, z, Hn, us, UH[s], u, th, acc);
+#pragma unroll
+                for (int a = 0; a < NQ2; ++a) {
+                    if (rows >> a & 1ull) {
+                        double v = acc[a];
+#pragma unroll
+                        for (int j = 0; j < s; ++j)
+                            if (RT::c(s, j) != 0.0) v = fma(RT::c(s, j) * ih, Ud[j][a], v);
+                        Ud[s][a] = v * ic0;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            double v = Hn[i];
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+                if (RT::m(s) != 0.0) v = fma(RT::m(s), UH[s][i], v);
+            Hs[(size_t)i * kMaxTile] = v;
+        }
+#pragma unroll
+        for (int a = 0; a < NQ2; ++a) {
+            if (rows >> a & 1ull) {
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+                    if (RT::m(s) != 0.0) dP[a] = fma(RT::m(s), Ud[s][a], dP[a]);
+            }
+        }
+        if constexpr (Q + 1 < M::NH) Ic2Column<M, RT, Q + 1>::run(t, ih, ic0, lu, z, dP, sm, u, th);
+    }
+};
+
+template <class M, class RT>
+__device__ __forceinline__ void rosenbrock_ic_step(double t, double h, double (&z)[M::NZ], double (&Pq)[M::NOBS * M::NF],
+                                                   double (&dP)[M::NOBS * M::NF * M::NIC], double* __restrict__ sm,
+                                                   const double* u, const double* th, const double* c) {
+    constexpr int S = RT::S, NX = M::NX, NP = M::NP, NZ = M::NZ, NQ = M::NOBS * M::NF, NQ2 = NQ * M::NIC;
+    using Lay = Ic2Layout<M, RT>;
+    const double c0 = 1.0 / (h * RT::gamma);
+    const double ih = 1.0 / h;
+    const double ic0 = h * RT::gamma;
+    double* Us = sm + (size_t)Lay::U * kMaxTile;
+    StepSolver<M, double> lu;
+    lu.init(t, c0, z, u, th, c);
+    // ---- phase 1: (x, G, P) ----
+    double Uq[S][NQ];
+    double gz[NZ], gq[NQ];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        if (!RT::same_stage_state(s)) {
+            const StageZ<RT, NZ> zs{z, Us, s};
+            double Z[NZ];
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) Z[a] = zs[a];
+            M::template ros_f<double>(t, Z, u, th, c, gz, gq);
+        }
+        double rz[NZ], rq[NQ];
+#pragma unroll
+        for (int a = 0; a < NZ; ++a) rz[a] = gz[a];
+#pragma unroll
+        for (int a = 0; a < NQ; ++a) rq[a] = gq[a];
+#pragma unroll
+        for (int j = 0; j < s; ++j) {
+            if (RT::c(s, j) != 0.0) {
+                const double cj = RT::c(s, j) * ih;
+#pragma unroll
+                for (int a = 0; a < NZ; ++a) rz[a] = fma(cj, Us[(size_t)(j * NZ + a) * kMaxTile], rz[a]);
+#pragma unroll
+                for (int a = 0; a < NQ; ++a) rq[a] = fma(cj, Uq[j][a], rq[a]);
+            }
+        }
+        double Uc[NZ];
+        {
+            double bx[NX];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) bx[i] = rz[i];
+            lu.solve(bx);
+#pragma unroll
+            for (int i = 0; i < NX; ++i) Uc[i] = bx[i];
+        }
+        double BU[NX * NP];
+        M::template ros_ling<double>(t, z, u, th, c, Uc, BU);
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            double bg[NX];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) bg[i] = rz[NX + j * NX + i] + BU[j * NX + i];
+            lu.solve(bg);
+#pragma unroll
+            for (int i = 0; i < NX; ++i) Uc[NX + j * NX + i] = bg[i];
+        }
+        double dPU[NQ];
+        M::template ros_linp<double>(t, z, u, th, c, Uc, dPU);
+#pragma unroll
+        for (int a = 0; a < NQ; ++a) Uq[s][a] = (rq[a] + dPU[a]) * ic0;
+#pragma unroll
+        for (int a = 0; a < NZ; ++a) Us[(size_t)(s * NZ + a) * kMaxTile] = Uc[a];
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        if (RT::m(s) != 0.0) {
+#pragma unroll
+            for (int a = 0; a < NQ; ++a) Pq[a] = fma(RT::m(s), Uq[s][a], Pq[a]);
+        }
+    }
+    // ---- phase 2: dP rows that do not involve H, then the H columns ----
+    if constexpr (M::IC2_QBASE_ROWS != 0ull) {
+        double Ub[S][NQ2];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const StageZ<RT, NZ> zs{z, Us, s};
+            const StageU<NZ> us{Us, s};
+            double rb[NQ2];
+            M::ic2_qbase(t, zs, z, us, u, th, rb);
+#pragma unroll
+            for (int a = 0; a < NQ2; ++a) {
+                if (M::IC2_QBASE_ROWS >> a & 1ull) {
+                    double v = rb[a];
+#pragma unroll
+                    for (int j = 0; j < s; ++j)
+                        if (RT::c(s, j) != 0.0) v = fma(RT::c(s, j) * ih, Ub[j][a], v);
+                    Ub[s][a] = v * ic0;
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < NQ2; ++a) {
+            if (M::IC2_QBASE_ROWS >> a & 1ull) {
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+                    if (RT::m(s) != 0.0) dP[a] = fma(RT::m(s), Ub[s][a], dP[a]);
+            }
+        }
+    }
+    Ic2Column<M, RT, 0>::run(t, ih, ic0, lu, z, dP, sm, u, th);
+    // ---- phase 3 ----
+#pragma unroll
+    for (int a = 0; a < NZ; ++a) {
+        double v = z[a];
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+            if (RT::m(s) != 0.0) v = fma(RT::m(s), Us[(size_t)(s * NZ + a) * kMaxTile], v);
+        z[a] = v;
+    }
+}
+
+template <class M, class RT>
+__global__ void __launch_bounds__(kMaxTile, 1) ros_ic_kernel(const EvalParams P) {
+    constexpr int NX = M::NX, NP = M::NP, NZ = M::NZ, NF = M::NF, NOBS = M::NOBS, NCTRL = M::NCTRL, NIC = M::NIC;
+    constexpr int NCU = NCTRL > 0 ? NCTRL : 1, NQ = NOBS * NF, NQ2 = NQ * NIC;
+    using Lay = Ic2Layout<M, RT>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    double* tile_buf = reinterpret_cast<double*>(smem_raw + 128);
+    const int tid = threadIdx.x;
+    const int TILE = P.tile;
+    const int n_var = P.n_var;
+    const long long ntiles = (P.n + TILE - 1) / TILE;
+    const int N = P.n_intervals;
+    const double* th = P.theta;
+    // this lane's column of the stage / second-order storage, behind the design tile
+    double* sm = tile_buf + (((size_t)TILE * n_var + 15) & ~(size_t)15) + tid;
+
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see oed_eval_kernel / launch_device
+    if (tid == 0 && P.use_tma) mbar_init(bar, 1);
+    scratch_acquire(P);
+    uint32_t phase = 0;
+    double best_val = __longlong_as_double(0x7ff0000000000000LL);
+    long long best_idx = -1;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long g0 = tile * TILE;
+        const int count = (int)((P.n - g0 < TILE) ? (P.n - g0) : TILE);
+        const double* src = P.designs + g0 * n_var;
+        const uint32_t bytes = (uint32_t)count * n_var * 8u;
+        const bool tma_ok = P.use_tma && (bytes % 16u == 0);
+        if (tma_ok) {
+            if (tid == 0) {
+                mbar_expect_tx(bar, bytes);
+                tma_load_1d(tile_buf, src, bytes, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+        } else {
+            for (int i = tid; i < count * n_var; i += blockDim.x) tile_buf[i] = src[i];
+            __syncthreads();
+        }
+
+        if (tid < count) {
+            double* row = tile_buf + (size_t)tid * n_var;
+            const long long g = g0 + tid;
+            double* pq = P.traj + ((size_t)blockIdx.x * (N * NQ + P.n_ctrl_values)) * kMaxTile + tid;
+            double z[NZ], F[NF], Fd[NIC][NF];
+#pragma unroll
+            for (int a = 0; a < NX; ++a) z[a] = P.x0[a];
+#pragma unroll
+            for (int a = 0; a < NX * NP; ++a) z[NX + a] = P.G0[a];
+#pragma unroll
+            for (int a = 0; a < NIC; ++a) z[M::ic_state(a)] = row[P.ic_off + a];
+#pragma unroll
+            for (int a = 0; a < NF; ++a) F[a] = 0.0;
+#pragma unroll
+            for (int a = 0; a < NIC; ++a)
+#pragma unroll
+                for (int k = 0; k < NF; ++k) Fd[a][k] = 0.0;
+#pragma unroll
+            for (int a = 0; a < M::NH * NX; ++a) sm[(size_t)(Lay::HN + a) * kMaxTile] = 0.0;   // G0 is constant
+            double* xg = P.xgrid ? P.xgrid + (size_t)g * (N + 1) * (NZ + NF) : nullptr;
+            if (xg) {
+#pragma unroll
+                for (int a = 0; a < NZ; ++a) xg[a] = z[a];
+#pragma unroll
+                for (int a = 0; a < NF; ++a) xg[NZ + a] = 0.0;
+            }
+            for (int j = 0; j < N; ++j) {
+                double u[NCU], c[M::NCONST], w[NOBS];
+#pragma unroll
+                for (int k = 0; k < NCTRL; ++k) u[k] = row[P.ctrl_off[k] + __ldg(P.indicators + k * N + j)];
+#pragma unroll
+                for (int i = 0; i < NOBS; ++i) w[i] = row[P.w_off[i] + __ldg(P.indicators + (NCTRL + i) * N + j)];
+                M::consts(u, th, c);
+                double Pq[NQ], dP[NQ2];
+#pragma unroll
+                for (int a = 0; a < NQ; ++a) Pq[a] = 0.0;
+#pragma unroll
+                for (int a = 0; a < NQ2; ++a) dP[a] = 0.0;
+                const int s0 = __ldg(P.first_step + j), s1 = __ldg(P.first_step + j + 1);
+                for (int s = s0; s < s1; ++s)
+                    rosenbrock_ic_step<M, RT>(__ldg(P.step_t + s), __ldg(P.step_h + s), z, Pq, dP, sm, u, th, c);
+#pragma unroll
+                for (int i = 0; i < NOBS; ++i)
+#pragma unroll
+                    for (int k = 0; k < NF; ++k) {
+                        F[k] = fma(w[i], Pq[i * NF + k], F[k]);
+#pragma unroll
+                        for (int a = 0; a < NIC; ++a) Fd[a][k] = fma(w[i], dP[a * NQ + i * NF + k], Fd[a][k]);
+                    }
+#pragma unroll
+                for (int a = 0; a < NQ; ++a) pq[((size_t)j * NQ + a) * kMaxTile] = Pq[a];
+                if (xg) {
+                    double* o = xg + (size_t)(j + 1) * (NZ + NF);
+#pragma unroll
+                    for (int a = 0; a < NZ; ++a) o[a] = z[a];
+#pragma unroll
+                    for (int a = 0; a < NF; ++a) o[NZ + a] = F[a];
+                }
+            }
+
+            // ---- criterion epilogue ----
+            const double tau = row[P.tau_off];
+            double value, L[NF], Ls[NF];
+            criterion_eval<NP>(F, tau, P.criterion, value, L);
+            const double obj = value + tau;
+            P.crit[g] = obj;
+            if (P.fim) {
+#pragma unroll
+                for (int a = 0; a < NF; ++a) P.fim[g * NF + a] = F[a];
+            }
+            if (obj < best_val) { best_val = obj; best_idx = P.index_base + g; }
+#pragma unroll
+            for (int jj = 0; jj < NP; ++jj)
+#pragma unroll
+                for (int ii = 0; ii <= jj; ++ii) Ls[tri(ii, jj)] = (ii == jj ? 1.0 : 2.0) * L[tri(ii, jj)];
+
+            // ---- gradient: <Lambda, .> with the symmetric pairing (off-diagonals count twice) ----
+            double wb[NOBS];
+            int wk[NOBS];
+#pragma unroll
+            for (int i = 0; i < NOBS; ++i) { wb[i] = 0.0; wk[i] = -1; }
+            for (int j = 0; j < N; ++j) {
+#pragma unroll
+                for (int i = 0; i < NOBS; ++i) {
+                    const int idx = __ldg(P.indicators + (NCTRL + i) * N + j);
+                    if (idx != wk[i]) {
+                        if (wk[i] >= 0) row[P.w_off[i] + wk[i]] = wb[i];
+                        wb[i] = 0.0; wk[i] = idx;
+                    }
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NF; ++k) s = fma(Ls[k], pq[((size_t)j * NQ + i * NF + k) * kMaxTile], s);
+                    wb[i] += s;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NOBS; ++i)
+                if (wk[i] >= 0) row[P.w_off[i] + wk[i]] = wb[i];
+#pragma unroll
+            for (int a = 0; a < NIC; ++a) {
+                double sd = 0.0;
+#pragma unroll
+                for (int k = 0; k < NF; ++k) sd = fma(Ls[k], Fd[a][k], sd);
+                row[P.ic_off + a] = sd;
+            }
+#pragma unroll
+            for (int k = 0; k < NCTRL; ++k)       // controls: "not computed" (the CTRLGRAD kernels do them)
+                for (int idx = 0; idx < P.ctrl_len[k]; ++idx)
+                    row[P.ctrl_off[k] + idx] = __longlong_as_double(0x7ff8000000000000LL);
+            double trL = 1.0;
+#pragma unroll
+            for (int i = 0; i < NP; ++i) trL += L[tri(i, i)];
+            row[P.tau_off] = trL;
+        }
+
+        double* dst = P.grad + g0 * n_var;
+        if (tma_ok) {
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {
+                tma_store_1d(dst, tile_buf, bytes);
+                tma_store_wait_read();
+            }
+            __syncthreads();
+        } else {
+            __syncthreads();
+            for (int i = tid; i < count * n_var; i += blockDim.x) dst[i] = tile_buf[i];
             __syncthreads();
         }
     }

@@ -486,6 +486,125 @@ def emit_model(name: str, s: SimplifiedOEDSystem) -> tuple[str, dict]:
                 b.out(f"dPU[{o * nF + k}]", e)
         return b
 
+    # ---------------- second-order pieces: gradient with respect to unknown initial conditions ----
+    # d/d(ic_a) of the Rosenbrock scheme on (x, G, P) IS the same scheme on the system extended by
+    #   H_(j,a) = d G_j / d ic_a   (d x / d ic_a is the G column of that initial condition itself)
+    #   dP_a    = d P   / d ic_a
+    # because the scheme uses the exact Jacobian.  The extended Jacobian stays block lower triangular
+    # with diagonal block f_x, so every H column is one more right-hand side for the step's LU.
+    # Emitted per unique column q = (j, a) (H_(j,a) = H_(a',j') when both are initial conditions):
+    #   ic2_rhs<q>  : g = J(Z) ZH + d(J G_j + f_p,j)/dx . G_a        at the stage state
+    #   ic2_lin<q>  : b = dg/d(x, G) . U                              at y_n (off-diagonal blocks)
+    #   ic2_qbase   : rows of dP that do not involve H:  rhs(Z) + lin(y_n; U)
+    #   ic2_qcol<q> : the part of the dP rows that is linear in (H_q, U_Hq)
+    ga = [n_ord + a for a in range(n_ic)]
+    hcols, hidx = [], {}
+    for a in range(n_ic):
+        for j in range(np_):
+            key = (j, a)
+            if j >= n_ord and (j - n_ord) < a:
+                key = (n_ord + a, j - n_ord)
+            if key not in hidx:
+                hidx[key] = len(hcols)
+                hcols.append(key)
+            hidx[(j, a)] = hidx[key]
+    nh = len(hcols)
+    nQ = n_obs * nF
+    ic2_code, ic2_flops = {}, {}
+    if n_ic:
+        names2 = dict(names)
+        for i, v in enumerate(x):
+            names2[v] = f"Z[{i}]"
+        for j in range(np_):
+            for i in range(nx):
+                names2[G[i, j]] = f"Z[{nx + j * nx + i}]"
+        xn = [sp.Symbol(f"xn{i}", real=True) for i in range(nx)]
+        Gn = sp.Matrix(nx, np_, lambda i, j: sp.Symbol(f"Gn{i}_{j}", real=True))
+        for i, v in enumerate(xn):
+            names2[v] = f"zn[{i}]"
+        for j in range(np_):
+            for i in range(nx):
+                names2[Gn[i, j]] = f"zn[{nx + j * nx + i}]"
+        ZH = [[sp.Symbol(f"ZH{q}_{i}", real=True) for i in range(nx)] for q in range(nh)]
+        HN = [[sp.Symbol(f"HN{q}_{i}", real=True) for i in range(nx)] for q in range(nh)]
+        UH = [[sp.Symbol(f"UH{q}_{i}", real=True) for i in range(nx)] for q in range(nh)]
+        for q in range(nh):
+            for i in range(nx):
+                names2[ZH[q][i]] = f"ZH[{i}]"
+                names2[HN[q][i]] = f"Hn[{i}]"
+                names2[UH[q][i]] = f"UH[{i}]"
+        to_n = {x[i]: xn[i] for i in range(nx)}
+        to_n.update({G[i, j]: Gn[i, j] for i in range(nx) for j in range(np_)})
+        to_n.update({ZH[q][i]: HN[q][i] for q in range(nh) for i in range(nx)})
+        zsyms = x + [G[i, j] for j in range(np_) for i in range(nx)]
+        g1 = [[sum(J[i, c] * G[c, j] for c in range(nx)) + (fp[i, j] if j < n_ord else 0)
+               for i in range(nx)] for j in range(np_)]
+        g2 = [[sum(J[i, c] * ZH[q][c] for c in range(nx)) +
+               sum(sp.diff(g1[j][i], x[c]) * G[c, ga[a]] for c in range(nx))
+               for i in range(nx)] for q, (j, a) in enumerate(hcols)]
+        q2 = []          # rows a*nQ + o*nF + k
+        for a in range(n_ic):
+            for o in range(n_obs):
+                for k, (i, j) in enumerate(triu_pairs(np_)):
+                    q1 = s.Qexpr[o, i] * s.Qexpr[o, j]
+                    e = sum(sp.diff(q1, x[c]) * G[c, ga[a]] for c in range(nx))
+                    e += sum(sp.diff(q1, G[c, jj]) * ZH[hidx[(jj, a)]][c]
+                             for c in range(nx) for jj in range(np_))
+                    q2.append(sp.expand(e))
+        allZH = [v for col in ZH for v in col]
+        allHN = [v for col in HN for v in col]
+        allUH = [v for col in UH for v in col]
+        hz = lambda e: _horner(sp.expand(e), x + xn)
+        pr2 = _FmaPrinter(names2)
+        inputs2 = set(names2.keys())
+
+        def chain(blocks_q, signature):
+            body, fl = [], []
+            for q, b in enumerate(blocks_q):
+                code_q, f_q = b.render(pr2, inputs2, indent="            ")
+                kw = "if" if q == 0 else "else if"
+                body.append(f"        {kw} constexpr (Q == {q}) {{\n{code_q}\n        }}")
+                fl.append(f_q)
+            return "\n".join(body), fl
+
+        rhs_b, lin_b, qcol_b = [], [], []
+        for q in range(nh):
+            b = _Block()
+            for i in range(nx):
+                b.out(f"g[{i}]", hz(g2[q][i]))
+            rhs_b.append(b)
+            b = _Block()
+            for i in range(nx):
+                e = sum(sp.diff(g2[q][i], v) * Usym[k] for k, v in enumerate(zsyms))
+                b.out(f"b[{i}]", hz(sp.expand(e).xreplace(to_n)))
+            lin_b.append(b)
+        # quadrature-derivative rows: stage-state part and the coupling at y_n
+        qlin = []
+        for e in q2:
+            l = sum(sp.diff(e, v) * Usym[k] for k, v in enumerate(zsyms))
+            l += sum(sp.diff(e, ZH[q][i]) * UH[q][i] for q in range(nh) for i in range(nx))
+            qlin.append(sp.expand(sp.expand(l).xreplace(to_n)))
+        zeroH = {v: 0 for v in allZH + allHN + allUH}
+        b = _Block()
+        for r, e in enumerate(q2):
+            b.out(f"rb[{r}]", hz(e.xreplace(zeroH)) + hz(qlin[r].xreplace(zeroH)))
+        ic2_code["qbase"], ic2_flops["qbase"] = b.render(pr2, inputs2, indent="        ")
+        for q in range(nh):
+            b = _Block()
+            for r, e in enumerate(q2):
+                part = sum(sp.diff(e, v) * v for v in ZH[q])
+                part += sum(sp.diff(qlin[r], v) * v for v in HN[q] + UH[q])
+                part = sp.expand(part)
+                if part != 0:
+                    b.out(f"acc[{r}]", hz(part), accumulate=True)
+            qcol_b.append(b)
+        ic2_rows = [sum(1 << int(lv[4:-1]) for lv, _, _ in b.outs) for b in qcol_b]
+        ic2_base_rows = sum(1 << r for r, e in enumerate(q2)
+                            if (e.xreplace(zeroH) != 0 or qlin[r].xreplace(zeroH) != 0))
+        ic2_code["rhs"], ic2_flops["rhs"] = chain(rhs_b, None)
+        ic2_code["lin"], ic2_flops["lin"] = chain(lin_b, None)
+        ic2_code["qcol"], ic2_flops["qcol"] = chain(qcol_b, None)
+
     blocks = OrderedDict(primal_z=build_primal(),
                          adjoint=build_adjoint(), obs=build_obs(), ros_f=build_ros_f(),
                          ros_jac=build_ros_jac(), ros_ling=build_ros_ling(),
@@ -501,6 +620,11 @@ def emit_model(name: str, s: SimplifiedOEDSystem) -> tuple[str, dict]:
         code[key], flops[key] = blk.render(pr if tmpl else prf, inputs, scalar="T" if tmpl else "double")
     # what one forward stage of the explicit integrators evaluates: (x, G) right-hand side + Q
     flops["primal"] = flops["primal_z"] + flops["obs"]
+    if n_ic:
+        flops["ic2_col"] = sum(ic2_flops["rhs"]) + sum(ic2_flops["lin"])
+        flops["ic2_q"] = ic2_flops["qbase"] + sum(ic2_flops["qcol"])
+    else:
+        flops["ic2_col"] = flops["ic2_q"] = 0
     cb = _Block()
     for k, e in enumerate(hoist.table.keys()):
         cb.out(f"c[{k}]", e)
@@ -514,7 +638,7 @@ def emit_model(name: str, s: SimplifiedOEDSystem) -> tuple[str, dict]:
     G0 = [float(v) for v in s.u0[nx:nz]]
     th0 = [float(s.defaults.get(p, getdefault(p, 0.0))) for p in theta]
     info = dict(name=name, nx=nx, np=np_, n_obs=n_obs, n_ctrl=nc, n_ic=n_ic, n_theta=len(theta),
-                n_const=len(hoist.table), nz=nz, nF=nF, ic_state=ic_state, x0=x0, G0=G0,
+                n_const=len(hoist.table), nz=nz, nF=nF, nh=nh, ic_state=ic_state, x0=x0, G0=G0,
                 theta=th0, theta_names=[p.name for p in theta],
                 control_names=[c.name for c in s.controls], w_names=[w.name for w in s.w],
                 ic_names=[p.name for p in s.x_ic], tunable_names=[p.name for p in s.p_tunable],
@@ -524,6 +648,40 @@ def emit_model(name: str, s: SimplifiedOEDSystem) -> tuple[str, dict]:
         return ", ".join(fmt.format(v) for v in vals) if vals else "0"
 
     cname = "Model_" + name
+    ic2_src = ""
+    if n_ic:
+        ic2_src = f"""    // ---- second-order sensitivities for the unknown-initial-condition gradient (see emit.py) ----
+    // unique H columns q -> (parameter column j, initial condition a): {', '.join(f'{q}:({j},{a})' for q, (j, a) in enumerate(hcols))}
+    // Z: stage state (x, G), zn: (x, G) at the step start, U: this stage's increments of (x, G) — arrays or
+    // accessors with operator[]; ZH / Hn / UH: the column's own 6-vectors; dP rows: a*NOBS*NF + o*NF + k
+    static constexpr unsigned long long IC2_QBASE_ROWS = {ic2_base_rows}ull;   // dP rows with an H-free part
+    __host__ __device__ static constexpr unsigned long long ic2_qrows(int q) {{   // dP rows column q feeds
+        constexpr unsigned long long v[{max(nh, 1)}] = {{{', '.join(f'{r}ull' for r in ic2_rows)}}};
+        return v[q];
+    }}
+    template <int Q, class ZA>
+    __device__ __forceinline__ static void ic2_rhs(double t, const ZA& Z, const double* __restrict__ ZH,
+            const double* __restrict__ u, const double* __restrict__ th, double* __restrict__ g) {{
+{ic2_code['rhs']}
+    }}
+    template <int Q, class NA, class UA>
+    __device__ __forceinline__ static void ic2_lin(double t, const NA& zn, const double* __restrict__ Hn,
+            const UA& U, const double* __restrict__ u, const double* __restrict__ th,
+            double* __restrict__ b) {{
+{ic2_code['lin']}
+    }}
+    template <class ZA, class NA, class UA>
+    __device__ __forceinline__ static void ic2_qbase(double t, const ZA& Z, const NA& zn, const UA& U,
+            const double* __restrict__ u, const double* __restrict__ th, double* __restrict__ rb) {{
+{ic2_code['qbase']}
+    }}
+    template <int Q, class ZA, class NA, class UA>
+    __device__ __forceinline__ static void ic2_qcol(double t, const ZA& Z, const double* __restrict__ ZH,
+            const NA& zn, const double* __restrict__ Hn, const UA& U, const double* __restrict__ UH,
+            const double* __restrict__ u, const double* __restrict__ th, double* __restrict__ acc) {{
+{ic2_code['qcol']}
+    }}
+"""
     src = f"""// GENERATED by dynamicoed.jl_b200/emit.py — do not edit.  Model "{name}".
 // states  : {', '.join(info['state_names'])}
 // tunables: {', '.join(info['tunable_names'])}   controls: {', '.join(info['control_names']) or '-'}
@@ -538,6 +696,8 @@ struct {cname} {{
     static constexpr int FLOPS_ROS_F = {flops['ros_f']};
     static constexpr int FLOPS_ROS_JAC = {flops['ros_jac']}, FLOPS_ROS_LING = {flops['ros_ling']};
     static constexpr int FLOPS_ROS_LINP = {flops['ros_linp']}, FLOPS_ROS_HVP = {flops['ros_hvp']};
+    static constexpr int NH = {nh}, FLOPS_IC2_COL = {flops['ic2_col']}, FLOPS_IC2_Q = {flops['ic2_q']};
+    static constexpr bool IC2_OK = {'true' if (n_ic and n_obs * nF * n_ic <= 64) else 'false'};
     static constexpr const char* NAME = "{name}";
     __host__ __device__ static constexpr int ic_state(int i) {{
         constexpr int v[{max(n_ic, 1)}] = {{{arr(ic_state, '{}')}}};
@@ -618,7 +778,7 @@ struct {cname} {{
             const double* __restrict__ U, double* __restrict__ out) {{
 {code['ros_hvp']}
     }}
-}};
+{ic2_src}}};
 """
     info["sha"] = hashlib.sha256(src.encode()).hexdigest()[:16]
     return src, info

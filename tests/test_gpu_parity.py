@@ -1117,3 +1117,51 @@ def test_pack_and_select_winner_kernels_match_their_host_mirror(built_library):
     assert torch.equal(pay2, pay)
     ctx.set_aux_stream(0)
     ctx.own_stream()
+
+
+def test_repeated_smallest_eigenvalue_gives_a_valid_subgradient(built_library):
+    """FisherE / E at a REPEATED lambda_min (SURVEY.md section 7 hard part): the criterion is not
+    differentiable there, the value is still exact and the kernel must return one valid element of the
+    generalised gradient, -v v^T (FisherE) or -v v^T / lambda^2 (E) with v a unit vector of the smallest
+    eigenvalue's eigenspace (closed 2x2 form: v = e_1; register Jacobi: the first minimal column)."""
+    from oracle.oed_oracle import criterion, criterion_matrix_gradient
+    rng = np.random.default_rng(11)
+    mats = [np.diag([2.0, 2.0]), 3.5 * np.eye(2), np.diag([2.0, 2.0, 5.0]), np.diag([7.0, 1.5, 1.5]),
+            np.diag([4.0, 4.0, 4.0, 9.0]), 0.75 * np.eye(4)]
+    for n, k in ((3, 2), (4, 2), (4, 3), (6, 2)):            # rotated: eigenspace not axis-aligned
+        Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+        lam = np.concatenate([np.full(k, 1.25), 1.25 + 1.0 + rng.random(n - k)])
+        mats.append((Q * lam) @ Q.T)
+    for Mx in mats:
+        n = Mx.shape[0]
+        Mx = 0.5 * (Mx + Mx.T)
+        lmin = float(np.linalg.eigvalsh(Mx)[0])
+        for cls, crit in ((D.FisherECriterion, 2), (D.ECriterion, 5)):
+            v = cls()(Mx, 0.0)
+            assert np.isclose(v, criterion(crit, Mx, 0.0), rtol=1e-12)
+            L = cls().gradient(Mx, 0.0)
+            scale = 1.0 if crit == 2 else 1.0 / lmin ** 2
+            assert np.allclose(L, L.T, atol=1e-14)
+            P = -L / scale                                    # should be v v^T, |v| = 1, M v = lmin v
+            assert abs(np.trace(P) - 1.0) < 1e-9
+            assert np.linalg.norm(P @ P - P) < 1e-8           # a rank-one projector
+            assert np.linalg.norm(Mx @ P - lmin * P) < 1e-8 * max(1.0, abs(lmin))
+            if np.count_nonzero(Mx - np.diag(np.diag(Mx))) == 0:
+                # axis-aligned eigenspace: the documented convention coincides with LAPACK's (first column)
+                assert np.allclose(L, criterion_matrix_gradient(crit, Mx, 0.0), atol=1e-13)
+
+
+def test_lv_against_the_oracle_with_its_own_constants(built_library):
+    """The C++ oracle evaluated with the Lotka-Volterra / 1D constants it carries itself (written down in
+    oracle/oed_oracle.cpp from /root/reference/test/references/LotkaVolterra.jl:11-17 and 1D.jl:15-16),
+    not the ones the product's models.py feeds it: a wrong constant in models.py can no longer cancel."""
+    from oracle.cpp_oracle import CppOracle
+    from oracle.oed_oracle import Oracle
+    for name, crit_cls, crit in (("lv_fishing", D.FisherDCriterion, 1), ("one_d", D.FisherACriterion, 0)):
+        ctx = make_problem(name, crit_cls).context()
+        des = random_designs(name, ctx.n_var, 777, 91)
+        c, g, F = ctx.evaluate(des)
+        orc = CppOracle(name, Oracle(CASES[name](), crit, "rk4", 4), own_constants=True)
+        orc.set_criterion(crit)
+        oc, og, oF = orc.evaluate(des, grad=True)
+        assert rel(c, oc) < RTOL and rel(F, oF) < RTOL and rel_rows(g, og) < RTOL

@@ -223,6 +223,19 @@ def test_cpp_oracle_matches_numpy_oracle(name, ctor, method):
     assert np.allclose(X, Y, rtol=1e-12, atol=1e-14)
 
 
+@pytest.mark.parametrize("name,ctor", [("lv_fishing", models.lotka_volterra_fishing), ("one_d", models.one_d)])
+def test_models_py_constants_equal_the_constants_the_oracle_carries_itself(name, ctor):
+    """oracle/oed_oracle.cpp holds its own copy of the LV / 1D constants, written from
+    /root/reference/test/references/LotkaVolterra.jl:11-17 and 1D.jl:15-16.  Feeding the oracle the product's
+    models.py values must change nothing, bit for bit: otherwise one of the two copies is wrong."""
+    rng = np.random.default_rng(17)
+    o = Oracle(ctor(), 1, "rk4", 4)
+    fed, own = cpp_oracle.CppOracle(name, o), cpp_oracle.CppOracle(name, o, own_constants=True)
+    des = rng.random((9, o.n_var))
+    for x, y in zip(fed.evaluate(des, grad=True), own.evaluate(des, grad=True)):
+        assert np.array_equal(x, y)
+
+
 def test_forward_mode_gradient_vs_finite_differences():
     rng = np.random.default_rng(11)
     o = Oracle(models.lotka_volterra_fishing(), CRIT_A, "rk4", 2)
