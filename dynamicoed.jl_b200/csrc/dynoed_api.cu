@@ -33,6 +33,8 @@ constexpr int kFwdOnly = 16;
 constexpr int kCtrlGrad = 32;
 // method | kDirPar: direction-parallel gradient kernel for small batches (dir_eval_kernel)
 constexpr int kDirPar = 64;
+// method | kIc2: Rosenbrock gradient with second-order sensitivities for unknown initial conditions (ros_ic_kernel)
+constexpr int kIc2 = 128;
 constexpr int kDirBlock = 32;
 // host calls of at most this many designs let the kernel read / write page-locked host memory directly
 constexpr int64_t kSmallZeroCopy = 16;
@@ -46,6 +48,9 @@ struct ModelEntry {
                          int* blocks_per_sm);
     cudaError_t (*info_gain)(const EvalParams& P, const double* X, double* Pout, double* Piout, cudaStream_t st);
     int flops_ros_jac, flops_ros_ling, flops_ros_linp, flops_ros_hvp;   // emitted Rosenbrock pieces (FMA = 2)
+    int nh, flops_ic2_col, flops_ic2_q;   // unique second-order columns and their emitted pieces (all columns, one stage)
+    bool ic2_ok;
+    int ic2_gcol[kMaxIC];                 // G column that is d x / d ic_a
 };
 
 template <class K>
@@ -115,6 +120,26 @@ static cudaError_t attrs_ros(int block, size_t smem, cudaFuncAttributes* fa, int
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, block, smem);
 }
 
+// Rosenbrock gradient of a model with unknown initial conditions and no controls: ros_ic_kernel
+template <class M, class RT>
+static cudaError_t launch_ic(bool pdl, const EvalParams& P, int grid, int block, size_t smem, cudaStream_t st) {
+    if constexpr (M::IC2_OK) return launch_kernel(ros_ic_kernel<M, RT>, pdl, P, grid, block, smem, st);
+    else return cudaErrorInvalidDeviceFunction;
+}
+template <class M, class RT>
+static cudaError_t attrs_ic(int block, size_t smem, cudaFuncAttributes* fa, int* bps) {
+    if constexpr (M::IC2_OK) {
+        auto kern = ros_ic_kernel<M, RT>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncGetAttributes(fa, kern);
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, block, smem);
+    } else {
+        return cudaErrorInvalidDeviceFunction;
+    }
+}
+
 template <class M, class Stepper>
 static cudaError_t launch_dir(const EvalParams& P0, int grid, cudaStream_t st) {
     // the design rows of one CTA's lanes are staged in shared memory when they fit the default 48 KB
@@ -139,6 +164,13 @@ static cudaError_t launch_model(int method, bool grad, bool uc, bool pdl, const 
             case DYNOED_ROS2: return launch_dir<M, RosenbrockStepper<TabROS2>>(P, grid, st);
             case DYNOED_ROS3P: return launch_dir<M, RosenbrockStepper<TabROS3P>>(P, grid, st);
             default: return launch_dir<M, RosenbrockStepper<TabRODAS3>>(P, grid, st);
+        }
+    }
+    if (method & kIc2) {
+        switch (method & 15) {
+            case DYNOED_ROS2: return launch_ic<M, TabROS2>(pdl, P, grid, block, smem, st);
+            case DYNOED_ROS3P: return launch_ic<M, TabROS3P>(pdl, P, grid, block, smem, st);
+            default: return launch_ic<M, TabRODAS3>(pdl, P, grid, block, smem, st);
         }
     }
     const bool cg = (method & kCtrlGrad) != 0;
@@ -173,6 +205,13 @@ static cudaError_t attrs_tab(bool grad, bool uc, int block, size_t smem, cudaFun
 template <class M>
 static cudaError_t attrs_model(int method, bool grad, bool uc, int block, size_t smem, cudaFuncAttributes* fa,
                                int* bps) {
+    if (method & kIc2) {
+        switch (method & 15) {
+            case DYNOED_ROS2: return attrs_ic<M, TabROS2>(block, smem, fa, bps);
+            case DYNOED_ROS3P: return attrs_ic<M, TabROS3P>(block, smem, fa, bps);
+            default: return attrs_ic<M, TabRODAS3>(block, smem, fa, bps);
+        }
+    }
     const bool cg = (method & kCtrlGrad) != 0;
     method &= ~kCtrlGrad;
     if (method == DYNOED_RK4) return attrs_tab<M, TabRK4>(grad, uc, block, smem, fa, bps);
@@ -221,6 +260,8 @@ static ModelEntry make_entry() {
     for (int k = 0; k < M::NTH; ++k) i.theta[k] = M::default_theta()[k];
     e.flops_ros_jac = M::FLOPS_ROS_JAC; e.flops_ros_ling = M::FLOPS_ROS_LING;
     e.flops_ros_linp = M::FLOPS_ROS_LINP; e.flops_ros_hvp = M::FLOPS_ROS_HVP;
+    e.nh = M::NH; e.flops_ic2_col = M::FLOPS_IC2_COL; e.flops_ic2_q = M::FLOPS_IC2_Q; e.ic2_ok = M::IC2_OK;
+    for (int k = 0; k < M::NIC; ++k) e.ic2_gcol[k] = M::ic2_gcol(k);
 
     e.launch = &launch_model<M>;
     e.attrs = &attrs_model<M>;
@@ -315,6 +356,7 @@ struct dynoed_ctx {
     int w_len[kMaxObs] = {0};   // length of each measurement-weight block of the design vector
     bool ucoef = false;    // step coefficients served from the constant bank (uniform registers)
     bool rosenbrock = false;
+    bool ic2 = false;      // gradient kernel = ros_ic_kernel (Rosenbrock, unknown initial conditions, no controls)
     int bps[3] = {0, 0, 0};   // blocks per SM: objective only / gradient / forward-only gradient (explicit RK)
     size_t smem_floor = 0; // dynamic shared memory padding that caps the resident CTAs per SM
     cudaFuncAttributes fa[3];
@@ -456,12 +498,21 @@ static int kernel_index(const dynoed_ctx* ctx, bool grad, uint32_t flags) {
 
 // the method code the model's launch / attrs dispatch understands, per kernel index
 static int method_code(const dynoed_ctx* ctx, int kidx) {
+    if (ctx->rosenbrock && kidx == 1 && ctx->ic2) return ctx->method | kIc2;
     if (ctx->rosenbrock) return (kidx == 1 && ctx->model->info.n_ctrl > 0) ? (ctx->method | kCtrlGrad) : ctx->method;
     return kidx == 2 ? kFwdOnly + ctx->method : ctx->method;
 }
 
-static size_t smem_bytes(const dynoed_ctx* ctx) {
-    return std::max(ctx->smem_floor, 128 + (size_t)ctx->tile * ctx->n_var * sizeof(double));
+// kidx 1 of an ic2 context: behind the design tile every lane owns Ic2Layout::SLOTS doubles (stage
+// increments of (x, G) and the second-order sensitivity columns), strided by kMaxTile
+static size_t smem_bytes(const dynoed_ctx* ctx, int kidx = 0) {
+    size_t need = 128 + (size_t)ctx->tile * ctx->n_var * sizeof(double);
+    if (kidx == 1 && ctx->ic2) {
+        const auto& mi = ctx->model->info;
+        const size_t slots = (size_t)ctx->stages * mi.nz + (size_t)ctx->model->nh * mi.nx;
+        need = 128 + ((((size_t)ctx->tile * ctx->n_var + 15) & ~(size_t)15) + slots * kMaxTile) * sizeof(double);
+    }
+    return std::max(ctx->smem_floor, need);
 }
 
 // Small gradient batches (the optimiser callback, finite-difference Hessians) are bound by the
@@ -667,10 +718,19 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
         if (k > 0) ctx->smem_floor = ((size_t)prop.sharedMemPerMultiprocessor / k - 1024) & ~(size_t)127;
         if (ctx->smem_floor > (size_t)prop.sharedMemPerBlockOptin - 2048) ctx->smem_floor = prop.sharedMemPerBlockOptin - 2048;
     }
-    const size_t smem = smem_bytes(ctx);
-    if (smem > (size_t)prop.sharedMemPerBlockOptin)
+    // Rosenbrock gradient with unknown initial conditions and no controls: second-order sensitivity kernel,
+    // unless its per-lane shared-memory columns do not fit (then: forward-mode duals, ros_eval_kernel)
+    ctx->ic2 = rosenbrock && mi.n_ic > 0 && mi.n_ctrl == 0 && m->ic2_ok && !getenv("DYNOED_NO_IC2");
+    if (ctx->ic2 && smem_bytes(ctx, 1) > (size_t)prop.sharedMemPerBlockOptin) ctx->ic2 = false;
+    // the kernel takes d x / d ic_a from G column ic2_gcol(a): only valid while that column starts as the
+    // unit vector of the state (a caller-supplied G0 may say otherwise)
+    for (int a = 0; ctx->ic2 && a < mi.n_ic; ++a)
+        for (int i = 0; i < mi.nx; ++i)
+            if (P.G0[m->ic2_gcol[a] * mi.nx + i] != (i == mi.ic_state[a] ? 1.0 : 0.0)) ctx->ic2 = false;
+    if (smem_bytes(ctx) > (size_t)prop.sharedMemPerBlockOptin)
         return bail(DYNOED_EINVAL, "tile * n_var does not fit in shared memory; use a smaller tile");
     for (int g = 0; g < 3; ++g) {
+        const size_t smem = smem_bytes(ctx, g);
         CUC(m->attrs(method_code(ctx, g), g >= 1, ctx->ucoef, tile, smem, &ctx->fa[g], &ctx->bps[g]));
         if (ctx->bps[g] < 1) return bail(DYNOED_ECUDA, "kernel cannot be resident with this tile size");
     }
@@ -842,7 +902,7 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
         CU(cudaEventRecord(ctx->ev_k0, st));
     }
     CU(ctx->model->launch(method_code(ctx, cur.kidx) | (dirpar ? kDirPar : 0), grad != nullptr, ctx->ucoef, pdl, P, grid,
-                          ctx->tile, smem_bytes(ctx), st));
+                          ctx->tile, smem_bytes(ctx, cur.kidx), st));
     if (ctx->profiling) { CU(cudaEventRecord(ctx->ev_k1, st)); ctx->ev_pending = true; }
     cur.serial = stream_new_serial(st);
     ctx->prev = cur;
@@ -1083,7 +1143,7 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
             P.use_tma = (!dirpar && ((size_t)ctx->tile * ctx->n_var * 8) % 16 == 0) ? 1 : 0;
             P.index_base = off;
             CU(ctx->model->launch(method_code(ctx, kidx) | (dirpar ? kDirPar : 0), g, ctx->ucoef, false, P, grid, ctx->tile,
-                                  smem_bytes(ctx), s.stream));
+                                  smem_bytes(ctx, kidx), s.stream));
             ctx->launches++;
             ctx->dir_launches += dirpar ? 1 : 0;
             double* o_crit = staged ? s.h_crit : crit + off;
@@ -1670,7 +1730,7 @@ int dynoed_kernel_stats_query(dynoed_ctx* ctx, int with_grad, dynoed_kernel_stat
     memset(o, 0, sizeof(*o));
     o->regs_per_thread = ctx->fa[g].numRegs;
     o->static_smem = (int)ctx->fa[g].sharedSizeBytes;
-    o->dynamic_smem = (int)smem_bytes(ctx);
+    o->dynamic_smem = (int)smem_bytes(ctx, g);
     o->blocks_per_sm = ctx->bps[g];
     o->grid = ctx->sm_count * ctx->bps[g];
     o->block = ctx->tile;
@@ -1749,6 +1809,20 @@ int dynoed_kernel_stats_query(dynoed_ctx* ctx, int with_grad, dynoed_kernel_stat
         // d/dw, d/dtau from the stored quadratures: 2 NQ per interval
         o->flops_per_design_grad = passes * val + ndirs * (dir_step * ctx->n_steps + 4.0 * nqq * ctx->n_intervals) +
                                    2.0 * nqq * ctx->n_intervals;
+        if (g == 1 && ctx->ic2) {
+            // ros_ic_kernel: ONE value pass + the second-order columns.  Per stage: the emitted right-hand
+            // sides / couplings of all NH columns and of the dP rows, NH solves with the value factors
+            // (+ nx for r + b); per step: column stage states, c_ij and m_s combinations (2 nx each) and the
+            // stage recursion of the NQ NIC quadrature-derivative rows.
+            int na_all = 0;
+            auto cnt = [&](auto RT) { using R = decltype(RT); for (int i = 0; i < R::S; ++i) for (int j = 0; j < i; ++j) na_all += R::a(i, j) != 0.0; };
+            if (ctx->method == DYNOED_ROS2) cnt(TabROS2{}); else if (ctx->method == DYNOED_ROS3P) cnt(TabROS3P{}); else cnt(TabRODAS3{});
+            const int nh = ctx->model->nh, nq2 = nqq * mi.n_ic;
+            const double h_step = (double)Sr * (ctx->model->flops_ic2_col + ctx->model->flops_ic2_q + nh * (solve + nx)) +
+                                  2.0 * nh * nx * (na_all + nc + nm) + (double)nq2 * (2.0 * nc + Sr + 2.0 * nm);
+            o->flops_per_design_grad = val + h_step * ctx->n_steps +
+                                       (double)ctx->n_intervals * (2.0 * nq2 + 2.0 * nqq) + 2.0 * mi.nF * mi.n_ic;
+        }
         o->bytes_per_design = 8.0 * (ctx->n_var + 1 + (with_grad ? ctx->n_var : 0) + mi.nF);
         return DYNOED_OK;
     }

@@ -674,10 +674,13 @@ struct Ic2Layout {
     static constexpr int SLOTS = HN + M::NH * M::NX;     // doubles per lane
 };
 
+// Shared-memory reads of the stage storage are VOLATILE: otherwise the compiler forwards the values it has
+// just stored from registers, keeps every increment live and spills them to local memory — the opposite
+// of what the shared-memory staging is for.
 template <class RT, int NZ>
 struct StageZ {                       // Z_s[k] = y_n[k] + sum_j a_sj U_j[k]
     const double (&z)[NZ];
-    const double* U;
+    const volatile double* U;
     int s;
     __device__ __forceinline__ double operator[](int k) const {
         double v = z[k];
@@ -689,7 +692,7 @@ struct StageZ {                       // Z_s[k] = y_n[k] + sum_j a_sj U_j[k]
 };
 template <int NZ>
 struct StageU {
-    const double* U;
+    const volatile double* U;
     int s;
     __device__ __forceinline__ double operator[](int k) const { return U[(size_t)(s * NZ + k) * kMaxTile]; }
 };
@@ -702,8 +705,8 @@ struct Ic2Column {
         constexpr int S = RT::S, NX = M::NX, NZ = M::NZ, NQ2 = M::NOBS * M::NF * M::NIC;
         constexpr unsigned long long rows = M::ic2_qrows(Q);
         using Lay = Ic2Layout<M, RT>;
-        const double* Us = sm + (size_t)Lay::U * kMaxTile;
-        double* Hs = sm + (size_t)(Lay::HN + Q * NX) * kMaxTile;
+        const volatile double* Us = sm + (size_t)Lay::U * kMaxTile;
+        volatile double* Hs = sm + (size_t)(Lay::HN + Q * NX) * kMaxTile;
         double Hn[NX], UH[S][NX], Ud[S][NQ2];
 #pragma unroll
         for (int i = 0; i < NX; ++i) Hn[i] = Hs[(size_t)i * kMaxTile];
@@ -779,7 +782,7 @@ __device__ __forceinline__ void rosenbrock_ic_step(double t, double h, double (&
     const double c0 = 1.0 / (h * RT::gamma);
     const double ih = 1.0 / h;
     const double ic0 = h * RT::gamma;
-    double* Us = sm + (size_t)Lay::U * kMaxTile;
+    volatile double* Us = sm + (size_t)Lay::U * kMaxTile;
     StepSolver<M, double> lu;
     lu.init(t, c0, z, u, th, c);
     // ---- phase 1: (x, G, P) ----

@@ -497,13 +497,26 @@ def emit_model(name: str, s: SimplifiedOEDSystem) -> tuple[str, dict]:
     #   ic2_lin<q>  : b = dg/d(x, G) . U                              at y_n (off-diagonal blocks)
     #   ic2_qbase   : rows of dP that do not involve H:  rhs(Z) + lin(y_n; U)
     #   ic2_qcol<q> : the part of the dP rows that is linear in (H_q, U_Hq)
-    ga = [n_ord + a for a in range(n_ic)]
+    # G column that IS d x / d ic_a: the one whose initial value is the unit vector of that state (the
+    # reference assigns them in its own order, quirk Q3 of /root/reference/src/augment.jl:186); -1 if the
+    # default G0 has no such column (then the second-order kernel is not offered)
+    ic_state_ = [s.x.index(s.aug.x[i - 1]) for i in s.aug.unknown_initial_conditions]
+    G0m = [[float(s.u0[nx + j * nx + i]) for j in range(np_)] for i in range(nx)]
+    ga = []
+    for a in range(n_ic):
+        cols = [j for j in range(n_ord, np_)
+                if all(G0m[i][j] == (1.0 if i == ic_state_[a] else 0.0) for i in range(nx))]
+        ga.append(cols[0] if cols else -1)
+    ic2_possible = n_ic > 0 and all(c >= 0 for c in ga) and len(set(ga)) == n_ic
+    if not ic2_possible:
+        ga = [n_ord + a for a in range(n_ic)]
+    col_ic = {c: a for a, c in enumerate(ga)}
     hcols, hidx = [], {}
     for a in range(n_ic):
         for j in range(np_):
             key = (j, a)
-            if j >= n_ord and (j - n_ord) < a:
-                key = (n_ord + a, j - n_ord)
+            if j in col_ic and col_ic[j] < a:        # H_(ga[a'], a) = d2 x / d ic_a' d ic_a = H_(ga[a], a')
+                key = (ga[a], col_ic[j])
             if key not in hidx:
                 hidx[key] = len(hcols)
                 hcols.append(key)
@@ -697,7 +710,12 @@ struct {cname} {{
     static constexpr int FLOPS_ROS_JAC = {flops['ros_jac']}, FLOPS_ROS_LING = {flops['ros_ling']};
     static constexpr int FLOPS_ROS_LINP = {flops['ros_linp']}, FLOPS_ROS_HVP = {flops['ros_hvp']};
     static constexpr int NH = {nh}, FLOPS_IC2_COL = {flops['ic2_col']}, FLOPS_IC2_Q = {flops['ic2_q']};
-    static constexpr bool IC2_OK = {'true' if (n_ic and n_obs * nF * n_ic <= 64) else 'false'};
+    static constexpr bool IC2_OK = {'true' if (ic2_possible and n_obs * nF * n_ic <= 64) else 'false'};
+    // G column that is d x / d ic_a (its initial value must be the unit vector of state ic_state(a))
+    __host__ __device__ static constexpr int ic2_gcol(int a) {{
+        constexpr int v[{max(n_ic, 1)}] = {{{arr(ga, '{}')}}};
+        return v[a];
+    }}
     static constexpr const char* NAME = "{name}";
     __host__ __device__ static constexpr int ic_state(int i) {{
         constexpr int v[{max(n_ic, 1)}] = {{{arr(ic_state, '{}')}}};

@@ -14,7 +14,7 @@ log = open('ptxas.log').read()
 ents = re.findall(r"Compiling entry function '(\S+)' for 'sm_100a'\n.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\nptxas info\s+: Used (\d+) registers", log)
 for name, stack, ss, sl, regs in ents:
     dem = subprocess.run(['c++filt', name], capture_output=True, text=True).stdout.strip()
-    if 'ros_eval_kernel' not in dem and 'ros_cols_kernel' not in dem: continue
+    if 'ros_eval_kernel' not in dem and 'ros_ic_kernel' not in dem: continue
     sass = subprocess.run(['cuobjdump', '-sass', '-fun', name, 'c6.so'], capture_output=True, text=True).stdout
     c = collections.Counter()
     for l in sass.splitlines():

@@ -427,6 +427,43 @@ def test_rosenbrock_kernels_vs_cpp_oracle(name, method, built_library):
     assert rel(X.T, orc.trajectory(des[5])) < RTOL
 
 
+@pytest.mark.parametrize("method", ["ros2", "ros3p", "rodas3"])
+def test_second_order_sensitivity_kernel_and_dual_number_kernels_agree(method, monkeypatch, built_library):
+    """Unknown initial conditions under a Rosenbrock scheme: the large-batch gradient kernel (ros_ic_kernel:
+    emitted second-order sensitivities, columns staged in shared memory), the forward-mode dual-number
+    kernel it replaced (DYNOED_NO_IC2=1) and the direction-parallel small-batch kernel are three
+    implementations of the same discrete derivative; each is checked against the C++ oracle, for the stiff
+    6-state model and for Lotka-Volterra with an unknown initial condition AND an ordinary parameter
+    (mixed second-order columns)."""
+    from oracle.cpp_oracle import CppOracle
+    from oracle.oed_oracle import Oracle
+    for name, ctor, crit_cls, crit_id, sub in (("chem6", models.chem6, D.FisherECriterion, 2, D.graded_edges(10, 24, 1e-6, 5)),
+                                               ("lv_ic", models.lotka_volterra_ic, D.ACriterion, 3, 8)):
+        alg = ROS[method](edges=sub) if not isinstance(sub, int) else ROS[method](sub)
+        out = {}
+        for variant, env in (("ic2", {"DYNOED_NO_DIRPAR": "1"}), ("dual", {"DYNOED_NO_DIRPAR": "1", "DYNOED_NO_IC2": "1"}),
+                             ("dirpar", {})):
+            for k in ("DYNOED_NO_DIRPAR", "DYNOED_NO_IC2"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            ctx = D.OEDProblem(D.OEDSystem(ctor()), crit_cls(), alg=alg).context()
+            des = (stiff_designs if name == "chem6" else random_designs)(name, ctx.n_var, 333, 5)
+            st0 = ctx.kernel_stats(True)
+            out[variant] = ctx.evaluate(des) + (st0["dynamic_smem"], ctx.kernel_stats(True)["small_batch_launches"])
+            ctx.close()
+        for k in ("DYNOED_NO_DIRPAR", "DYNOED_NO_IC2"):
+            monkeypatch.delenv(k, raising=False)
+        assert out["ic2"][3] > out["dual"][3]                # the second-order kernel stages columns in shared memory
+        assert out["ic2"][4] == 0 and out["dual"][4] == 0 and out["dirpar"][4] > 0
+        orc = CppOracle(name, Oracle(ctor(), crit_id, method, list(sub) if not isinstance(sub, int) else sub))
+        oc, og, oF = orc.evaluate(des, grad=True)
+        den = np.maximum(np.abs(oc), np.max(np.abs(oF), axis=1))
+        for variant, (c, g, F, _, _) in out.items():
+            assert rel(F, oF) < RTOL and float(np.max(np.abs(c - oc) / den)) < RTOL, (name, method, variant)
+            assert rel_rows(g, og) < RTOL, (name, method, variant, rel_rows(g, og))
+
+
 def test_robertson_reference_golden_through_the_boundary(built_library):
     """test/references/Rober.jl:50-66 — DCriterion, measurements on the last 3 of 10 intervals:
     objective 0 +- 1e-2 (here 1/(F + tau) + tau with F = 740.6)."""
