@@ -413,6 +413,46 @@ def main():
             sub[key] = {"designs_per_s_per_gpu": n / msa * 1e3, "ms_per_step": msa,
                         "flops_per_design": fla, "tflops": fla * n / msa / 1e9}
             ctxa.close()
+    # BASELINE config 4: stiff kinetics with unknown initial conditions (chem6: 6 states, 12 sensitivities,
+    # FisherE), ROS3P on a graded 130-step grid, 65,536 designs: objective only (ros_eval_kernel) and
+    # objective + full gradient (second-order sensitivity kernel ros_ic_kernel); flops as counted by
+    # dynoed_kernel_stats_query (emitted pieces + one nx x nx LU per step + the solves)
+    if rank == 0:
+        ctxs = D.OEDProblem(D.OEDSystem(models.chem6()), D.FisherECriterion(),
+                            alg=D.ROS3P(edges=D.graded_edges(10, 40, 1e-6, 10)), device=local).context()
+        ctxs.set_stream(stream.cuda_stream)
+        gens = torch.Generator(device=dev)
+        gens.manual_seed(20263)
+        s_in = []
+        for b in range(3):
+            dsn = torch.rand((n, ctxs.n_var), dtype=torch.float64, device=dev, generator=gens)
+            dsn[:, -1] = 1e-3 + 0.9 * dsn[:, -1]
+            dsn[:, 0] = 0.5 + dsn[:, 0]
+            dsn[:, 1] = 0.1 + 0.9 * dsn[:, 1]
+            s_in.append(dsn)
+        s_c = torch.empty(n, dtype=torch.float64, device=dev)
+        s_g = torch.empty_like(s_in[0])
+        for key, g_on in (("stiff_chem6_objective", False), ("stiff_chem6_grad", True)):
+            for k in range(2):
+                ctxs.eval_batch(s_in[k % 3], s_c, s_g if g_on else None, None, async_=True)
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 9
+            s0.record(stream)
+            for k in range(reps):
+                ctxs.eval_batch(s_in[k % 3], s_c, s_g if g_on else None, None, async_=True)
+            s1.record(stream)
+            torch.cuda.synchronize()
+            mss = s0.elapsed_time(s1) / reps
+            kss = ctxs.kernel_stats(g_on)
+            fls = kss["flops_per_design_grad" if g_on else "flops_per_design_eval"]
+            sub[key] = {"designs_per_s_per_gpu": n / mss * 1e3, "ms_per_step": mss, "flops_per_design": fls,
+                        "tflops": fls * n / mss / 1e9, "regs": kss["regs_per_thread"], "method": "ROS3P",
+                        "steps": 130, "n_var": ctxs.n_var}
+        sub["stiff_chem6_grad"]["grad_over_objective_cost"] = \
+            sub["stiff_chem6_grad"]["ms_per_step"] / sub["stiff_chem6_objective"]["ms_per_step"]
+        ctxs.close()
+        del s_in, s_c, s_g
     # BASELINE config 2: ONE design, objective + gradient (+ Hessian) through the blocking host call —
     # the optimiser callback (wall clock per call; numpy arrays, i.e. pageable memory)
     if rank == 0:
@@ -628,6 +668,11 @@ def main():
             if "designs_per_s_per_gpu" in v:
                 line[f"sub_{key}_designs_per_s"] = v["designs_per_s_per_gpu"]
                 line[f"sub_{key}_frac_fp64"] = v["tflops"] / peak
+        if "stiff_chem6_grad" in sub:
+            line["stiff_chem6_grad_designs_per_s"] = sub["stiff_chem6_grad"]["designs_per_s_per_gpu"]
+            line["stiff_chem6_frac_fp64"] = sub["stiff_chem6_grad"]["tflops"] / peak
+            line["stiff_chem6_objective_designs_per_s"] = sub["stiff_chem6_objective"]["designs_per_s_per_gpu"]
+            line["stiff_chem6_grad_over_objective_cost"] = sub["stiff_chem6_grad"]["grad_over_objective_cost"]
         if "single_design_host_call" in sub:
             line["single_design_objective_gradient_us"] = sub["single_design_host_call"]["objective_gradient_us"]
             line["single_design_hessian_us"] = sub["single_design_host_call"]["hessian_us"]

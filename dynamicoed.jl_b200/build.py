@@ -9,9 +9,11 @@ import hashlib
 import os
 import shutil
 import subprocess
+import time
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
+LAST_BUILD: dict = {}      # library path -> "compiled by nvcc in N s" | "reused (...)", for build()'s report
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -39,15 +41,24 @@ def build_library(out_path: str, models_dir: str | None = None, force: bool = Fa
     srcs += [os.path.join(_HERE, "..", "include", "dynoed.h")]
     srcs += [os.path.join(models_dir, f) for f in sorted(os.listdir(models_dir)) if f.endswith(".cuh")]
     if not force and _newer(out_path, srcs):
+        LAST_BUILD[os.path.abspath(out_path)] = "reused (up to date with its sources)"
         return out_path
     cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
     cmd += [f"-D{d}" for d in os.environ.get("DYNOED_NVCC_DEFINES", "").split() if d]
     if os.path.abspath(models_dir) != os.path.abspath(os.path.join(CSRC, "generated")):
         cmd += [f'-DDYNOED_MODELS_HEADER="{os.path.join(os.path.abspath(models_dir), "models.cuh")}"']
-    cmd += ["-o", out_path, srcs[0]]
+    # nvcc writes to a private temporary next to the target; os.replace() publishes it atomically, so
+    # concurrent ranks (torchrun) never dlopen a half-written library nor write the same file
+    tmp_path = f"{out_path}.{os.getpid()}.tmp"
+    cmd += ["-o", tmp_path, srcs[0]]
+    t0 = time.perf_counter()
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
+        if os.path.exists(tmp_path):
+            os.unlink(tmp_path)
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    os.replace(tmp_path, out_path)
+    LAST_BUILD[os.path.abspath(out_path)] = f"compiled by nvcc in {time.perf_counter() - t0:.0f} s"
     if verbose:
         print(r.stderr)
     return out_path
@@ -80,10 +91,12 @@ def build_user_model(src: str, info: dict, cache_dir: str | None = None) -> str:
         if f.endswith((".cu", ".cuh")):
             h.update(open(os.path.join(CSRC, f), "rb").read())
     h.update(open(os.path.join(_HERE, "..", "include", "dynoed.h"), "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(os.environ.get("DYNOED_NVCC_DEFINES", "").encode())
     key = h.hexdigest()[:16]
     d = os.path.join(cache_dir, key)
     out = os.path.join(d, f"libdynoed_{key}.so")
-    if os.path.exists(out):
+    if os.path.exists(out):             # published atomically by build_library: complete if present
         return out
     os.makedirs(d, exist_ok=True)
     name = info["name"]

@@ -6,7 +6,8 @@ summaries under profiles/:
   profiles/<tag>_summary.md        launch shares, key raw metrics, instruction mix, stall reasons
   profiles/ncu_summary.json        {"dram_bytes_per_launch": ...} read by bench.py for `traffic`
 
-usage: python scripts/summarize_ncu.py <tag>     (expects prof_<tag>.ncu-rep, launches_<tag>.csv)
+usage: python scripts/summarize_ncu.py <tag> [aux]    (expects prof_<tag>.ncu-rep, launches_<tag>.csv;
+       `aux`: a secondary kernel, summary json goes to profiles/<tag>_ncu.json)
 """
 import collections
 import csv
@@ -99,36 +100,49 @@ def main():
                    "regs": vals.get("launch__registers_per_thread")}
         md += ["", f"DRAM traffic per launch: {dr/1e6:.1f} MB read + {dw/1e6:.1f} MB written = "
                f"{(dr+dw)/1e6:.1f} MB.", ""]
-    # ---- source page: instruction mix and stall reasons ----
+    # ---- source page: instruction mix and stall reasons (one section per captured launch; the last
+    # capture of every distinct kernel is summarised) ----
     src = list(csv.reader(open(export(tag, "source"))))
-    hdr = src[1]
-    ix = {h: i for i, h in enumerate(hdr)}
-    st = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
-    mix, stall = collections.Counter(), collections.Counter()
-    tot_inst = 0
-    for r in src[2:]:
-        toks = [t for t in r[ix["Source"]].split() if not t.startswith("@")]
-        op = toks[0].split(".")[0] if toks else "?"
-        n = int(r[ix["Instructions Executed"]] or 0)
-        mix[op] += n
-        tot_inst += n
-        for h in st:
-            stall[h] += int(r[ix[h]] or 0)
-    md += ["## Instruction mix (warp-level instructions executed, source page)", "",
-           "| opcode | executed | share |", "|---|---|---|"]
-    for k, v in mix.most_common(12):
-        md.append(f"| {k} | {v} | {100*v/tot_inst:.1f} % |")
-    fp = sum(v for k, v in mix.items() if k in ("DFMA", "DMUL", "DADD"))
-    md += ["", f"FP64 arithmetic = {100*fp/tot_inst:.1f} % of all issued warp instructions.", "",
-           "## Warp stall sampling (all samples)", "", "| reason | samples | share |", "|---|---|---|"]
-    s = sum(stall.values())
-    for k, v in stall.most_common(8):
-        md.append(f"| {k} | {v} | {100*v/s:.1f} % |")
-    summary["inst_mix"] = dict(mix.most_common(8))
-    summary["stalls"] = dict(stall.most_common(6))
+    sections, cur = collections.OrderedDict(), None
+    for r in src:
+        if r and r[0] == "Kernel Name":
+            cur = r[1]
+            sections[cur] = []
+        elif cur is not None:
+            sections[cur].append(r)
+    for kname, rows in sections.items():
+        hdr = rows[0]
+        ix = {h: i for i, h in enumerate(hdr)}
+        st = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+        mix, stall = collections.Counter(), collections.Counter()
+        tot_inst = 0
+        for r in rows[1:]:
+            if len(r) < len(hdr):
+                continue
+            toks = [t for t in r[ix["Source"]].split() if not t.startswith("@")]
+            op = toks[0].split(".")[0] if toks else "?"
+            n = int(r[ix["Instructions Executed"]] or 0)
+            mix[op] += n
+            tot_inst += n
+            for h in st:
+                stall[h] += int(r[ix[h]] or 0)
+        md += [f"## Instruction mix — `{kname[:110]}` (warp-level instructions executed, source page)", "",
+               "| opcode | executed | share |", "|---|---|---|"]
+        for k, v in mix.most_common(12):
+            md.append(f"| {k} | {v} | {100*v/max(tot_inst, 1):.1f} % |")
+        fp = sum(v for k, v in mix.items() if k in ("DFMA", "DMUL", "DADD"))
+        md += ["", f"FP64 arithmetic = {100*fp/max(tot_inst, 1):.1f} % of all issued warp instructions.", "",
+               "## Warp stall sampling (all samples)", "", "| reason | samples | share |", "|---|---|---|"]
+        sm_ = max(sum(stall.values()), 1)
+        for k, v in stall.most_common(8):
+            md.append(f"| {k} | {v} | {100*v/sm_:.1f} % |")
+        md.append("")
+        summary["inst_mix"] = dict(mix.most_common(8))
+        summary["stalls"] = dict(stall.most_common(6))
     with open(os.path.join(P, f"{tag}_summary.md"), "w") as fh:
         fh.write("\n".join(md) + "\n")
-    with open(os.path.join(P, "ncu_summary.json"), "w") as fh:
+    # a second argument marks a capture of a SECONDARY kernel: its json does not feed bench.py's `traffic`
+    with open(os.path.join(P, "ncu_summary.json" if len(sys.argv) < 3 else f"{tag}_ncu.json"), "w") as fh:
         json.dump(summary, fh, indent=1)
     print("\n".join(md))
 
