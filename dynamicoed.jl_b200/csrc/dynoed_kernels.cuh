@@ -643,6 +643,10 @@ __device__ __forceinline__ void argmin_tail(const EvalParams& P, double best_val
     }
 }
 
+#ifndef DYNOED_PF_DIST
+#define DYNOED_PF_DIST 3      // backward sweep: checkpoints are pulled from HBM into L2 this many steps ahead
+#endif
+
 // MEASUREMENT-ONLY build switch (scripts/build_variants.py): DYNOED_TRAJ_WRAP folds every checkpoint /
 // quadrature slot onto a 4-deep (2-deep) window, so the scratch stays L2-resident and the launch
 // moves no checkpoint bytes to HBM.  Results are WRONG; the timing bounds what any scheme that
@@ -723,9 +727,9 @@ __device__ __forceinline__ void backward_interval(const EvalParams& P, const Ckp
 #endif
         const double tnext = __ldg(P.step_t + sp), hnext = __ldg(P.step_h + sp);
 #ifndef DYNOED_NO_L2_PREFETCH
-        if (s >= 3) {
+        if (s >= DYNOED_PF_DIST) {
 #pragma unroll
-            for (int a = 0; a < NZ; ++a) prefetch_l2(tr + ((size_t)DYNOED_CKPT(s - 3) * NZ + a) * kMaxTile);
+            for (int a = 0; a < NZ; ++a) prefetch_l2(tr + ((size_t)DYNOED_CKPT(s - DYNOED_PF_DIST) * NZ + a) * kMaxTile);
         }
 #endif
         if (UC) {
@@ -824,14 +828,32 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
             }
 
             // ---------------- forward sweep ----------------
+            // The interval tables (indicator rows, first_step) are read ONE INTERVAL AHEAD into
+            // registers: a table load followed at once by its use exposed a full L1/L2 round trip per
+            // interval (11 % of the stall samples of round 2's first capture sat on those compares).
+            int nci[NCU], nwi[NOBS];
+#pragma unroll
+            for (int k = 0; k < NCTRL; ++k) nci[k] = __ldg(P.indicators + k * N);
+#pragma unroll
+            for (int i = 0; i < NOBS; ++i) nwi[i] = __ldg(P.indicators + (NCTRL + i) * N);
+            int s_cur = __ldg(P.first_step), s_nxt = __ldg(P.first_step + 1);
             for (int j = 0; j < N; ++j) {
                 double u[NCU], w[NOBS], c[M::NCONST];
 #pragma unroll
-                for (int k = 0; k < NCTRL; ++k) u[k] = row[P.ctrl_off[k] + __ldg(P.indicators + k * N + j)];
+                for (int k = 0; k < NCTRL; ++k) u[k] = row[P.ctrl_off[k] + nci[k]];
 #pragma unroll
-                for (int i = 0; i < NOBS; ++i) w[i] = row[P.w_off[i] + __ldg(P.indicators + (NCTRL + i) * N + j)];
+                for (int i = 0; i < NOBS; ++i) w[i] = row[P.w_off[i] + nwi[i]];
+                const int s0 = s_cur, s1 = s_nxt;
+                {
+                    const int jn = j + 1 < N ? j + 1 : j;
+#pragma unroll
+                    for (int k = 0; k < NCTRL; ++k) nci[k] = __ldg(P.indicators + k * N + jn);
+#pragma unroll
+                    for (int i = 0; i < NOBS; ++i) nwi[i] = __ldg(P.indicators + (NCTRL + i) * N + jn);
+                    s_cur = s1;
+                    s_nxt = __ldg(P.first_step + jn + 1);
+                }
                 M::consts(u, th, c);
-                const int s0 = __ldg(P.first_step + j), s1 = __ldg(P.first_step + j + 1);
                 double Pint[NQ];
                 forward_interval<M, Tab, GRAD, UCOEF>(P, K, s0, s1, tr, z, Pint, u, th, c);
                 // F is linear in the weights: F += w_i P_i ; the P_i are kept for d/dw
@@ -894,6 +916,13 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
 #pragma unroll
                 for (int a = 0; a < NZ; ++a) zn[a] = ld_pinned(tr + ((size_t)DYNOED_CKPT(P.n_steps - 1) * NZ + a) * kMaxTile);
                 double tcur = __ldg(P.step_t + P.n_steps - 1), hcur = __ldg(P.step_h + P.n_steps - 1);
+                // interval tables one interval ahead, as in the forward sweep
+                int bci[NCU], bwi[NOBS];
+#pragma unroll
+                for (int k = 0; k < NCTRL; ++k) bci[k] = __ldg(P.indicators + k * N + N - 1);
+#pragma unroll
+                for (int i = 0; i < NOBS; ++i) bwi[i] = __ldg(P.indicators + (NCTRL + i) * N + N - 1);
+                int b_lo = __ldg(P.first_step + N - 1), b_hi = __ldg(P.first_step + N);
                 for (int j = N - 1; j >= 0; --j) {
                     double u[NCU], cwL[NQ], c[M::NCONST], Pj[NQ];
                     // this interval's quadratures (d F / d w_i): requested here, consumed after the steps
@@ -907,9 +936,24 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
                         for (int a = 0; a < NQ; ++a) Pj[a] = ld_hint(pq + ((size_t)DYNOED_QSLOT(j) * NQ + a) * kMaxTile, pol);
                     }
 #endif
+                    const int s0 = b_lo, s1 = b_hi;
+                    int cci[NCU], cwi[NOBS];
+#pragma unroll
+                    for (int k = 0; k < NCTRL; ++k) cci[k] = bci[k];
+#pragma unroll
+                    for (int i = 0; i < NOBS; ++i) cwi[i] = bwi[i];
+                    {
+                        const int jn = j > 0 ? j - 1 : 0;
+#pragma unroll
+                        for (int k = 0; k < NCTRL; ++k) bci[k] = __ldg(P.indicators + k * N + jn);
+#pragma unroll
+                        for (int i = 0; i < NOBS; ++i) bwi[i] = __ldg(P.indicators + (NCTRL + i) * N + jn);
+                        b_hi = s0;
+                        b_lo = __ldg(P.first_step + jn);
+                    }
 #pragma unroll
                     for (int k = 0; k < NCTRL; ++k) {
-                        const int idx = __ldg(P.indicators + k * N + j);
+                        const int idx = cci[k];
                         if (idx != uk[k]) {
                             if (uk[k] >= 0) row[P.ctrl_off[k] + uk[k]] = ub[k];
                             ub[k] = 0.0; uk[k] = idx;
@@ -918,7 +962,7 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
                     }
 #pragma unroll
                     for (int i = 0; i < NOBS; ++i) {
-                        const int idx = __ldg(P.indicators + (NCTRL + i) * N + j);
+                        const int idx = cwi[i];
                         if (idx != wk[i]) {
                             if (wk[i] >= 0) row[P.w_off[i] + wk[i]] = wb[i];
                             wb[i] = 0.0; wk[i] = idx;
@@ -928,7 +972,6 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
                         for (int k = 0; k < NF; ++k) cwL[i * NF + k] = cw * L[k];
                     }
                     M::consts(u, th, c);
-                    const int s0 = __ldg(P.first_step + j), s1 = __ldg(P.first_step + j + 1);
                     backward_interval<M, Tab, UCOEF>(P, K, s0, s1, tr, zn, tcur, hcur, lam, u, cwL, th, c, ub);
 #pragma unroll
                     for (int i = 0; i < NOBS; ++i)

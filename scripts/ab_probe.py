@@ -49,5 +49,8 @@ out["power_w_max"] = max(pw) if pw else None
 ctx.set_profiling(True); run(0, 30); torch.cuda.synchronize()
 out["isolated_ms"] = ctx.kernel_time()[0]; ctx.set_profiling(False)
 out["crit0"] = float(bufs[0][1][0])
+# order-independent fingerprints of buffer set 0 (bit-identical between builds that do the same arithmetic)
+out["crit_xor"] = int(torch.bitwise_xor(bufs[0][1].view(torch.int64)[::2], bufs[0][1].view(torch.int64)[1::2]).sum())
+out["grad_sum"] = float(bufs[0][2].sum())
 out["fp64_peak"] = runtime.fp64_peak()[0]
 print(json.dumps(out))
