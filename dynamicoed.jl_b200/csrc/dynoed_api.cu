@@ -379,7 +379,8 @@ struct dynoed_ctx {
     long long* d_ring = nullptr;       // [kRing][2]: the same record for the last kRing batches
     int64_t batch_seq = 0;             // batches evaluated so far (ring slot = seq % kRing)
     unsigned int* d_ticket = nullptr;  // [2]
-    unsigned long long* d_guard = nullptr;   // [2][4]: scratch-set owner serial, waits, timed-out waits (scratch_acquire)
+    unsigned long long* d_guard = nullptr;   // [2][4]: calls finished with the set, waits, timed-out waits (scratch_acquire)
+    unsigned long long set_calls[2] = {0, 0};   // calls handed each scratch set so far (incl. the current one)
     unsigned long long call_serial = 0;      // serial of the most recent evaluation call (> 0)
     uint32_t call_flags = 0;                 // flags of the call being served
     std::vector<int> h_first;                // host copy of first_step[N+1]
@@ -830,7 +831,7 @@ static bool ranges_overlap(const char* a0, const char* a1, const char* b0, const
 static void set_scratch_params(dynoed_ctx* ctx, EvalParams& P, int par, int kidx) {
     const auto& mi = ctx->model->info;
     P.guard = ctx->d_guard + 4 * par;
-    P.serial = ctx->call_serial;
+    P.serial = ctx->set_calls[par] - 1;      // the calls that used this set before the current one must be done
     const double lanes = (double)ctx->sm_count * std::max(ctx->bps[kidx], 1) * kMaxTile;
     const double per_step = 8.0 * (mi.nz + (double)mi.n_obs * mi.nF * ctx->n_intervals / std::max(ctx->n_steps, 1));
     int hot = (int)((double)ctx->l2_bytes * ctx->l2_hot_frac / (lanes * per_step));
@@ -846,7 +847,7 @@ static void reset_parity(dynoed_ctx* ctx, int par) {
     cudaDeviceSynchronize();
     cudaGetLastError();
     cudaMemset(ctx->d_ticket + par, 0, sizeof(unsigned int));
-    cudaMemset(ctx->d_guard + 4 * par, 0, sizeof(unsigned long long));
+    cudaMemcpy(ctx->d_guard + 4 * par, &ctx->set_calls[par], sizeof(unsigned long long), cudaMemcpyHostToDevice);   // all done
     ctx->prev.valid = false;
 }
 
@@ -934,6 +935,7 @@ static int eval_device(dynoed_ctx* ctx, const double* designs, int64_t n, double
     int rc = ensure_partials(ctx, grid, par);
     if (rc) return rc;
     ctx->call_serial++;
+    ctx->set_calls[par]++;
     rc = launch_device(ctx, designs, n, crit, grad, fim, xgrid, par, grid, ctx->stream);
     if (rc) { reset_parity(ctx, par); return rc; }
     ctx->last_parity = par;
@@ -1109,6 +1111,7 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         small_zc = zc_in && zc_crit && zc_grad && (!fim || zc_fim);
     }
     ctx->call_serial++;
+    ctx->set_calls[par]++;
     // everything that launches: a failure part-way leaves the ticket partially counted and the scratch set
     // acquired, so the error path drains the device and clears both (reset_parity)
     auto enqueue = [&]() -> int {

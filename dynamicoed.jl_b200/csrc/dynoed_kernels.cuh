@@ -86,10 +86,10 @@ struct EvalParams {
     double* __restrict__ best_val;
     long long* __restrict__ best_idx;
     long long* __restrict__ ring_rec;     // history slot of this batch: {value bits, index} (or nullptr)
-    // scratch-set guard: guard[0] = serial of the call that owns this scratch set (0 = free),
-    // guard[1] = CTAs that had to wait for it, guard[2] = waits that timed out (see scratch_acquire)
+    // scratch-set guard: guard[0] = number of calls that have finished with this scratch set,
+    // guard[1] = CTAs that had to wait for their turn, guard[2] = waits that timed out (see scratch_acquire)
     unsigned long long* __restrict__ guard;
-    unsigned long long serial;            // this call's serial (> 0)
+    unsigned long long serial;            // calls handed this scratch set before this one (its turn: guard[0] >= serial)
     // checkpoints of steps >= hot_step and quadratures of intervals >= hot_interval are kept in L2
     int hot_step;
     int hot_interval;
@@ -545,28 +545,35 @@ __device__ __forceinline__ void rk_adjoint_step(double t, const double* __restri
 // Scratch-set guard.  Consecutive device-path launches alternate between two scratch sets
 // (checkpoints, arg-min partials, ticket, result slot) and may overlap through programmatic
 // dependent launch, so launch k+2 can become resident while launch k (same set) still runs when the
-// launches do not fill the GPU.  Every CTA therefore acquires its set before touching it: the
-// owner word is 0 (free) or the serial of the call that holds it; the last CTA of a call releases
-// it after its arg-min reduction.  This cannot deadlock: a dependent grid starts only after every
-// CTA of its predecessor has STARTED, so when CTAs of launch k+2 spin, all CTAs of launch k are
-// already resident or done.  A wait that exceeds 2 s (a lost release after a failed call) is
-// counted in guard[2] and abandoned instead of hanging the device.
+// launches do not fill the GPU.  Every CTA therefore waits for its TURN on the set before touching it:
+// guard[0] counts the calls that have finished with the set (the last CTA of a call adds one after its
+// arg-min reduction), P.serial is the number of calls that were handed the set before this one, and a
+// CTA proceeds once guard[0] >= P.serial.  Turns — not a free/owned flag — because waiters must be
+// served in launch order: with a plain lock, CTAs of launch k+4 spinning next to CTAs of launch k+2 can
+// win the set first; every launch's own results would still be right, but the set's result slot
+// (dynoed_argmin) would finally hold the older batch.  This cannot deadlock: a dependent grid starts
+// only after every CTA of its predecessor has STARTED, so when CTAs of launch k+2 spin, all CTAs of
+// launch k are already resident or done.  A wait that exceeds 2 s (a lost release after a failed call)
+// is counted in guard[2] and abandoned instead of hanging the device.
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void scratch_acquire(const EvalParams& P) {
     if (threadIdx.x == 0 && P.guard) {
-        unsigned long long old = atomicCAS(P.guard, 0ULL, P.serial);
-        if (old != 0ULL && old != P.serial) {
+        if (ld_acquire_u64(P.guard) < P.serial) {
             atomicAdd(P.guard + 1, 1ULL);
             const unsigned long long t0 = global_ns();
             while (true) {
                 __nanosleep(200);
-                old = atomicCAS(P.guard, 0ULL, P.serial);
-                if (old == 0ULL || old == P.serial) break;
+                if (ld_acquire_u64(P.guard) >= P.serial) break;
                 if (global_ns() - t0 > 2000000000ULL) { atomicAdd(P.guard + 2, 1ULL); break; }
             }
         }
@@ -638,7 +645,7 @@ __device__ __forceinline__ void argmin_tail(const EvalParams& P, double best_val
             *P.best_idx = bi;
             if (P.ring_rec) { P.ring_rec[0] = __double_as_longlong(bv); P.ring_rec[1] = bi; }
             *P.ticket = 0u;
-            if (P.guard) { __threadfence(); atomicExch(P.guard, 0ULL); }   // release the scratch set
+            if (P.guard) { __threadfence(); atomicAdd(P.guard, 1ULL); }   // this call is done with the scratch set
         }
     }
 }

@@ -118,12 +118,23 @@ struct TabRODAS3 {
 };
 
 // ----------------------------------------------------------------------------------------------
-// LU with partial pivoting of a small matrix held in registers.  Row exchanges are SELECTS over
-// statically indexed rows (no dynamic register indexing: ptxas otherwise moves the whole matrix to local
-// memory and swaps rows through an address), and they are skipped altogether when no lane of the
-// converged warp needs one at this elimination step — the common case for W = 1/(h gamma) I - f_x,
-// which is close to column diagonally dominant.  The vote only decides whether the (always correct)
-// select code runs, so results do not depend on which lanes share a warp.
+// LU with partial pivoting of a small matrix held in registers.
+//
+// The COMMON case needs no row exchange at all: W = 1/(h gamma) I - f_x is column diagonally dominant
+// for small steps and for kinetics of any step (f_x has non-positive column sums), and partial pivoting
+// never exchanges rows of such a matrix.  So the factorisation runs SPECULATIVELY without exchanges and
+// only records, per lane, whether partial pivoting would have picked another row at some elimination
+// step (the column maxima it needs are by-products of the elimination).  If no lane of the warp needed
+// one — one vote per factorisation — the result IS the pivoted factorisation and every solve is plain
+// straight-line substitution.  Otherwise the warp rebuilds the matrix and takes the pivoted path:
+// row exchanges as SELECTS over statically indexed rows (dynamic register indexing would move the whole
+// matrix to local memory), whole rows as in LAPACK's getrf, so that a solve applies the exchanges to its
+// right-hand side first (laswp) and then runs the same substitution code.  The vote only decides which
+// (equivalent) code runs: results do not depend on which lanes share a warp.
+//
+// (Round 2's first version voted at every elimination step and guarded the exchanges of every solve
+// step: ptxas paid for those ~50 warp-uniform branches per Rosenbrock step with phi copies of the matrix
+// at every join — 470 IMAD.MOV + 160 FSEL of 1,780 executed instructions per chem6 ROS3P step.)
 // ----------------------------------------------------------------------------------------------
 template <class T>
 __device__ __forceinline__ void select_swap(bool sw, T& x, T& y) {
@@ -134,14 +145,41 @@ __device__ __forceinline__ void select_swap(bool sw, T& x, T& y) {
 
 template <class T, int N>
 struct SmallLU {
-    T a[N][N];
-    int piv[N];        // piv[k] = row exchanged with row k at elimination step k
-    unsigned swaps;    // bit k set: some lane of the warp exchanged rows at step k (warp-uniform)
+    T a[N][N];         // L (unit diagonal, multipliers below) and U; the diagonal keeps 1 / pivot
+    int piv[N];        // pivoted path: row exchanged with row k at elimination step k
+    bool pivoted;      // warp-uniform: a[][] factorises the row-exchanged matrix
 
-    // one elimination step per template instantiation: a `#pragma unroll` loop over k is NOT fully
-    // unrolled once the warp vote is inside it, and a run-time k puts the matrix in local memory
+    // elimination step k on rows k+1.. (shared by both paths)
     template <int k>
-    __device__ __forceinline__ void factor_step() {
+    __device__ __forceinline__ void eliminate() {
+        const T inv = 1.0 / a[k][k];
+        a[k][k] = inv;
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) {
+            const T l = a[i][k] * inv;
+            a[i][k] = l;
+#pragma unroll
+            for (int j = k + 1; j < N; ++j) a[i][j] = a[i][j] - l * a[k][j];
+        }
+    }
+    // no exchanges; returns whether partial pivoting would have exchanged rows at some step (then a[][] is
+    // not to be used: the caller rebuilds the matrix and calls factor_pivoted)
+    template <int k>
+    __device__ __forceinline__ bool plain_step() {
+        bool need = false;
+        const double d = fabs(value_of(a[k][k]));
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) need = need || (fabs(value_of(a[i][k])) > d);
+        eliminate<k>();
+        if constexpr (k + 1 < N) need = plain_step<k + 1>() || need;
+        return need;
+    }
+    __device__ __forceinline__ bool factor_plain() {
+        pivoted = false;
+        return plain_step<0>();
+    }
+    template <int k>
+    __device__ __forceinline__ void pivoted_step() {
         int p = k;
         double best = fabs(value_of(a[k][k]));
 #pragma unroll
@@ -150,42 +188,30 @@ struct SmallLU {
             if (v > best) { best = v; p = i; }
         }
         piv[k] = p;
-        if (k + 1 < N && __any_sync(__activemask(), p != k)) {
-            swaps |= 1u << k;
-            // exchange the active part only: earlier multipliers stay put, which is what the
-            // interleaved swap/eliminate order of solve() assumes
-#pragma unroll
-            for (int i = k + 1; i < N; ++i) {
-                const bool sw = (p == i);
-#pragma unroll
-                for (int j = k; j < N; ++j) select_swap(sw, a[k][j], a[i][j]);
-            }
-        }
-        const T inv = 1.0 / a[k][k];
-        a[k][k] = inv;   // the diagonal keeps 1 / pivot
 #pragma unroll
         for (int i = k + 1; i < N; ++i) {
-            const T l = a[i][k] * inv;
-            a[i][k] = l;
+            const bool sw = (p == i);
 #pragma unroll
-            for (int j = k + 1; j < N; ++j) a[i][j] = a[i][j] - l * a[k][j];
+            for (int j = 0; j < N; ++j) select_swap(sw, a[k][j], a[i][j]);   // whole rows (getrf)
         }
-        if constexpr (k + 1 < N) factor_step<k + 1>();
+        eliminate<k>();
+        if constexpr (k + 1 < N) pivoted_step<k + 1>();
     }
-    __device__ __forceinline__ void factor() {
-        swaps = 0u;
-        factor_step<0>();
+    __device__ __forceinline__ void factor_pivoted() {
+        pivoted = true;
+        pivoted_step<0>();
     }
     __device__ __forceinline__ void solve(T (&b)[N]) const {
+        if (pivoted) {   // warp-uniform, rare
 #pragma unroll
-        for (int k = 0; k < N; ++k) {
-            if (swaps & (1u << k)) {
+            for (int k = 0; k + 1 < N; ++k)
 #pragma unroll
                 for (int i = k + 1; i < N; ++i) select_swap(piv[k] == i, b[k], b[i]);
-            }
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k)
 #pragma unroll
             for (int i = k + 1; i < N; ++i) b[i] = b[i] - a[i][k] * b[k];
-        }
 #pragma unroll
         for (int k = N - 1; k >= 0; --k) {
             T s = b[k];
@@ -195,6 +221,31 @@ struct SmallLU {
         }
     }
 };
+
+// W = c0 I - A  ->  lu: speculative plain factorisation, pivoted redo when some lane of the warp needs it.
+// `jac(A)` fills A = f_x row-major; it is evaluated AGAIN on the rare path instead of keeping NX^2 more
+// doubles alive across the elimination.
+template <int NX, class Jac>
+__device__ __forceinline__ void factor_shifted(SmallLU<double, NX>& lu, double c0, Jac jac) {
+    {
+        double A[NX * NX];
+        jac(A);
+#pragma unroll
+        for (int i = 0; i < NX; ++i)
+#pragma unroll
+            for (int j = 0; j < NX; ++j) lu.a[i][j] = (i == j ? c0 : 0.0) - A[i * NX + j];
+    }
+    const bool need = lu.factor_plain();
+    if (__any_sync(__activemask(), need)) {
+        double A[NX * NX];
+        jac(A);
+#pragma unroll
+        for (int i = 0; i < NX; ++i)
+#pragma unroll
+            for (int j = 0; j < NX; ++j) lu.a[i][j] = (i == j ? c0 : 0.0) - A[i * NX + j];
+        lu.factor_pivoted();
+    }
+}
 
 // ----------------------------------------------------------------------------------------------
 // The linear systems of one step:  W U = b  with  W = 1/(h gamma) I - f_x(x_n).
@@ -213,13 +264,7 @@ struct StepSolver<M, double> {
     __device__ __forceinline__ void init(double t, double c0, const double* z, const double* u, const double* th,
                                          const double* c) {
         constexpr int NX = M::NX;
-        double A[NX * NX];
-        M::template ros_jac<double>(t, z, u, th, c, A);
-#pragma unroll
-        for (int i = 0; i < NX; ++i)
-#pragma unroll
-            for (int j = 0; j < NX; ++j) lu.a[i][j] = (i == j ? c0 : 0.0) - A[i * NX + j];
-        lu.factor();
+        factor_shifted<NX>(lu, c0, [&](double (&A)[NX * NX]) { M::template ros_jac<double>(t, z, u, th, c, A); });
     }
     __device__ __forceinline__ void solve(double (&b)[M::NX]) const { lu.solve(b); }
 };
@@ -248,13 +293,7 @@ struct StepSolver<M, Dual<K>> {
         }
 #pragma unroll
         for (int k = 0; k < M::NCONST; ++k) cv[k] = c[k].v;
-        double A[NX * NX];
-        M::template ros_jac<double>(t, xv, uv, th, cv, A);
-#pragma unroll
-        for (int i = 0; i < NX; ++i)
-#pragma unroll
-            for (int j = 0; j < NX; ++j) lu.a[i][j] = (i == j ? c0 : 0.0) - A[i * NX + j];
-        lu.factor();
+        factor_shifted<NX>(lu, c0, [&](double (&A)[NX * NX]) { M::template ros_jac<double>(t, xv, uv, th, cv, A); });
     }
     __device__ __forceinline__ void solve(Dual<K> (&b)[NX]) const {
         double b0[NX];

@@ -427,6 +427,52 @@ def test_rosenbrock_kernels_vs_cpp_oracle(name, method, built_library):
     assert rel(X.T, orc.trajectory(des[5])) < RTOL
 
 
+def _pivoting_system():
+    """A linear 3-state system dominated by rotation: W = 1/(h gamma) I - f_x has off-diagonal entries
+    (40, 25) far above its diagonal (~5) at the step sizes used below, so partial pivoting MUST exchange
+    rows at elimination steps 0 and 1."""
+    from dynamicoed.jl_b200.symbolic import (Differential, Eq, ODESystem, independent_variable,
+                                             observed_variables, parameters, variables)
+    t = independent_variable("t")
+    x1, x2, x3 = variables("x1 x2 x3", [1.0, 0.5, -0.5])
+    k = parameters("k[1] k[2]", [0.7, 1.3], tunable=True)
+    obs = observed_variables("o[1] o[2]", measurement_rate=0.25)
+    Dt = Differential(t)
+    return ODESystem([Eq(Dt(x1), -k[0] * x1 + 40.0 * x2), Eq(Dt(x2), -40.0 * x1 - k[1] * x2 + 25.0 * x3),
+                      Eq(Dt(x3), -25.0 * x2 - 0.5 * x3)],
+                     t, tspan=(0.0, 1.0), observed=[Eq(obs[0], x1), Eq(obs[1], x3)], name="piv3")
+
+
+@pytest.mark.parametrize("method", ["ros2", "ros3p"])
+def test_rosenbrock_lu_takes_the_row_exchange_path_when_it_must(method, built_library):
+    """The Rosenbrock kernels factorise W speculatively without row exchanges and redo the factorisation
+    with partial pivoting when some lane of the warp needs an exchange (SmallLU, factor_shifted).  This
+    system needs exchanges at every step; F and the objective against the numpy oracle (LAPACK solves of
+    the flat dense system), the weight gradient against central differences of the GPU objective."""
+    from oracle.oed_oracle import Oracle
+    sysm = _pivoting_system()
+    gamma = {"ros2": 1.0 + 1.0 / np.sqrt(2.0), "ros3p": 0.7886751345948129}[method]
+    W = np.eye(3) / (0.125 * gamma) - np.array([[-0.7, 40.0, 0.0], [-40.0, -1.3, 25.0], [0.0, -25.0, -0.5]])
+    assert abs(W[1, 0]) > abs(W[0, 0])                   # partial pivoting exchanges rows 0 and 1
+    prob = D.OEDProblem(D.OEDSystem(sysm), D.ACriterion(), alg=ROS[method](2))
+    ctx = prob.context()
+    rng = np.random.Generator(np.random.Philox(31))
+    des = 0.1 + 0.9 * rng.random((70, ctx.n_var))
+    c, g, F = ctx.evaluate(des)
+    oc, _, oF = Oracle(sysm, D.ACriterion().id, method, 2).evaluate(des, grad=False)
+    assert rel(F, oF) < RTOL and rel(c, oc) < RTOL
+    big = np.tile(des, (30, 1))                          # 2,100 designs: the large-batch kernel
+    cb, gb, Fb = ctx.evaluate(big)
+    assert rel(Fb[:70], oF) < RTOL and rel(cb[:70], oc) < RTOL and rel_rows(gb[:70], g) < 1e-11
+    eps = 1e-6
+    for kk in (0, 3, ctx.n_var - 2, ctx.n_var - 1):
+        dp, dm = des[:8].copy(), des[:8].copy()
+        dp[:, kk] += eps
+        dm[:, kk] -= eps
+        fd = (ctx.evaluate(dp, grad=False, fim=False)[0] - ctx.evaluate(dm, grad=False, fim=False)[0]) / (2 * eps)
+        assert np.max(np.abs(fd - g[:8, kk]) / np.maximum(np.abs(g[:8, kk]), 1e-3)) < 1e-5, kk
+
+
 @pytest.mark.parametrize("method", ["ros2", "ros3p", "rodas3"])
 def test_second_order_sensitivity_kernel_and_dual_number_kernels_agree(method, monkeypatch, built_library):
     """Unknown initial conditions under a Rosenbrock scheme: the large-batch gradient kernel (ros_ic_kernel:
