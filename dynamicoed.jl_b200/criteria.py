@@ -82,5 +82,11 @@ class ECriterion(AbstractInformationCriterion):
     id = 5
 
 
+class LogDCriterion(AbstractInformationCriterion):
+    """-log(det(F)): the log form of the D criterion.  NOT in the reference (fisher.jl has -det F and
+    1/det F); BASELINE.json's north_star names "FisherD logdet F", so it is offered as an extension."""
+    id = 6
+
+
 ALL_CRITERIA = [FisherACriterion, FisherDCriterion, FisherECriterion, ACriterion, DCriterion,
-                ECriterion]
+                ECriterion]          # the reference's six; LogDCriterion is an extension

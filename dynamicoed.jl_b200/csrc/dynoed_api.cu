@@ -547,7 +547,7 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     const ModelEntry* m = find_model(d->model);
     if (!m) return fail(nullptr, DYNOED_ENOMODEL, std::string("unknown model: ") + (d->model ? d->model : "(null)"));
     const dynoed_model_info& mi = m->info;
-    if (d->criterion < 0 || d->criterion > 5) return fail(nullptr, DYNOED_EINVAL, "criterion out of range");
+    if (d->criterion < 0 || d->criterion >= kNumCriteria) return fail(nullptr, DYNOED_EINVAL, "criterion out of range");
     if (d->method < DYNOED_RK4 || d->method > DYNOED_RODAS3)
         return fail(nullptr, DYNOED_EUNSUPPORTED, "unsupported integration method");
     const bool rosenbrock = d->method == DYNOED_ROS2 || d->method == DYNOED_ROS3P || d->method == DYNOED_RODAS3;
@@ -764,7 +764,7 @@ void dynoed_destroy(dynoed_ctx* ctx) {
 
 int dynoed_set_criterion(dynoed_ctx* ctx, int criterion) {
     if (!ctx) return fail(nullptr, DYNOED_EINVAL, "ctx is NULL");
-    if (criterion < 0 || criterion > 5) return fail(ctx, DYNOED_EINVAL, "criterion out of range");
+    if (criterion < 0 || criterion >= kNumCriteria) return fail(ctx, DYNOED_EINVAL, "criterion out of range");
     ctx->criterion = criterion;
     ctx->base.criterion = criterion;
     return DYNOED_OK;
@@ -1626,7 +1626,7 @@ int dynoed_eval_fixed_controls(dynoed_ctx* ctx, const double* basis, const doubl
 int dynoed_criterion_batch(int device, int criterion, int np, const double* F, const double* tau, int64_t batch,
                            double* value, double* dcdF) {
     dynoed_ctx* ctx = nullptr;
-    if (criterion < 0 || criterion > 5) return fail(nullptr, DYNOED_EINVAL, "criterion out of range");
+    if (criterion < 0 || criterion >= kNumCriteria) return fail(nullptr, DYNOED_EINVAL, "criterion out of range");
     if (np < 1 || np > kMaxCritN) return fail(nullptr, DYNOED_EINVAL, "np must be 1..24");
     if (!F || !value || batch <= 0) return fail(nullptr, DYNOED_EINVAL, "bad arguments");
     CU(cudaSetDevice(device));

@@ -40,7 +40,10 @@ __host__ __device__ constexpr int coef_hb(int s) { return 1 + s; }
 __host__ __device__ constexpr int coef_ha(int s, int j) { return 1 + kCoefS + s * kCoefS + j; }
 __host__ __device__ constexpr int coef_hr(int j, int s) { return 1 + kCoefS + kCoefS * kCoefS + j * kCoefS + s; }
 
-enum Criterion : int { kFisherA = 0, kFisherD = 1, kFisherE = 2, kA = 3, kD = 4, kE = 5 };
+// kLogD = -log det(F + tau I): the log form of the D criterion that BASELINE.json's north_star names
+// ("FisherD logdet F"); NOT in the reference (its FisherD is -det F, fisher.jl:33-45) — an extension.
+enum Criterion : int { kFisherA = 0, kFisherD = 1, kFisherE = 2, kA = 3, kD = 4, kE = 5, kLogD = 6 };
+constexpr int kNumCriteria = 7;
 
 // Everything the kernel needs besides the design batch; passed by value (constant bank).
 struct EvalParams {
@@ -316,6 +319,7 @@ __device__ __forceinline__ void criterion_eval(const double (&F)[N * (N + 1) / 2
         const double m = F[0] + tau;
         switch (crit) {
             case kFisherA: case kFisherD: case kFisherE: value = -m; L[0] = -1.0; break;
+            case kLogD: value = -log(m); L[0] = -1.0 / m; break;
             default: value = 1.0 / m; L[0] = -1.0 / (m * m); break;
         }
         return;
@@ -325,6 +329,10 @@ __device__ __forceinline__ void criterion_eval(const double (&F)[N * (N + 1) / 2
         const double tr = a + d;
         if (crit == kFisherA) { value = -tr; L[0] = -1.0; L[1] = 0.0; L[2] = -1.0; return; }
         if (crit == kFisherD) { value = -det; L[0] = -d; L[1] = b; L[2] = -a; return; }
+        if (crit == kLogD) {   // d(-log det M)/dM = -M^-1 = -adj(M) / det
+            const double id = 1.0 / det;
+            value = -log(det); L[0] = -d * id; L[1] = b * id; L[2] = -a * id; return;
+        }
         if (crit == kD) {
             const double id = 1.0 / det, s = -id * id;
             value = id; L[0] = s * d; L[1] = -s * b; L[2] = s * a; return;
@@ -399,6 +407,10 @@ __device__ __forceinline__ void criterion_eval(const double (&F)[N * (N + 1) / 2
             case kD: value = 1.0 / det;
 #pragma unroll
                 for (int i = 0; i < N; ++i) g[i] = -1.0 / (det * lam[i]);
+                break;
+            case kLogD: value = -log(det);
+#pragma unroll
+                for (int i = 0; i < N; ++i) g[i] = -1.0 / lam[i];
                 break;
             case kA: value = sinv;
 #pragma unroll
@@ -1460,6 +1472,7 @@ __global__ void criterion_batch_kernel(const double* __restrict__ Fp, const doub
         case kFisherE: val = -A[kmin * n + kmin]; break;
         case kA: val = sinv; break;
         case kD: val = 1.0 / det; break;
+        case kLogD: val = -log(det); break;
         default: val = 1.0 / A[kinv * n + kinv]; break;
     }
     value[g] = val;
@@ -1476,6 +1489,7 @@ __global__ void criterion_batch_kernel(const double* __restrict__ Fp, const doub
                         case kFisherE: gk = (k == kmin) ? -1.0 : 0.0; break;
                         case kA: gk = -1.0 / (l * l); break;
                         case kD: gk = -1.0 / (det * l); break;
+                        case kLogD: gk = -1.0 / l; break;
                         default: gk = (k == kinv) ? -1.0 / (l * l) : 0.0; break;
                     }
                     s += V[i * n + k] * gk * V[j * n + k];

@@ -46,6 +46,8 @@ extern "C" {
 #define DYNOED_A 3        /* tr F^-1        fisher.jl:73-76  */
 #define DYNOED_D 4        /* 1/det F        fisher.jl:89-91  */
 #define DYNOED_E 5        /* max 1/lambda   fisher.jl:104-107 */
+#define DYNOED_LOG_D 6    /* -log det F: the log form of the D criterion (BASELINE north_star's "FisherD logdet F");
+                           * an EXTENSION, not in the reference (its FisherD is -det F) */
 
 /* fixed-step integrators (the reference passes `alg` to OrdinaryDiffEq.solve,
  * /root/reference/src/problem.jl:25, /root/reference/src/discretize.jl:314-317) */

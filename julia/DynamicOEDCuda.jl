@@ -24,6 +24,7 @@ using ComponentArrays
 using ModelingToolkit
 using Optimization
 using SciMLBase
+using LinearAlgebra: logdet
 
 export CudaBackend, DynoedContext, eval_batch!, hessian!, eval_batch_async!, wait_call, argmin_design, dynoed_library,
        pinned_matrix
@@ -42,6 +43,10 @@ criterion_id(::FisherECriterion) = Cint(2)
 criterion_id(::ACriterion) = Cint(3)
 criterion_id(::DCriterion) = Cint(4)
 criterion_id(::ECriterion) = Cint(5)
+# extension (not in DynamicOED.jl): -log det(F + tau I), DYNOED_LOG_D
+struct LogDCriterion <: DynamicOED.AbstractInformationCriterion end
+(c::LogDCriterion)(F::AbstractArray{T, 2}) where {T} = -logdet(F)
+criterion_id(::LogDCriterion) = Cint(6)
 
 # struct dynoed_problem_desc (include/dynoed.h) — field order and types must match exactly
 struct ProblemDesc

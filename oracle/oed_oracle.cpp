@@ -422,6 +422,7 @@ double criterion(int crit, int n, const double* Fp, double tau, double* L) {
         case 2: val = -lam[kmin]; for (int i = 0; i < n; ++i) gk[i] = i == kmin ? -1.0 : 0.0; break;
         case 3: val = sinv; for (int i = 0; i < n; ++i) gk[i] = -1.0 / (lam[i] * lam[i]); break;
         case 4: val = 1.0 / det; for (int i = 0; i < n; ++i) gk[i] = -1.0 / (det * lam[i]); break;
+        case 6: val = -std::log(det); for (int i = 0; i < n; ++i) gk[i] = -1.0 / lam[i]; break;   // log form of D (extension)
         default: val = 1.0 / lam[kinv]; for (int i = 0; i < n; ++i) gk[i] = i == kinv ? -1.0 / (lam[i] * lam[i]) : 0.0; break;
     }
     for (int j = 0; j < n; ++j) for (int i = 0; i <= j; ++i) { double s = 0; for (int k = 0; k < n; ++k) s += V[i][k] * gk[k] * V[j][k]; L[tri(i, j)] = s; }

@@ -43,6 +43,7 @@ import dynamicoed.jl_b200.symbolic as S            # noqa: E402  (metadata vocab
 from dynamicoed.jl_b200.discretize import Timegrid, design_layout  # noqa: E402  (golden-pinned)
 
 FISHER_A, FISHER_D, FISHER_E, CRIT_A, CRIT_D, CRIT_E = range(6)
+LOG_D = 6      # -log det(F + tau I): extension (BASELINE north_star), not one of the reference's six
 CRITERIA = {"FisherACriterion": 0, "FisherDCriterion": 1, "FisherECriterion": 2,
             "ACriterion": 3, "DCriterion": 4, "ECriterion": 5}
 
@@ -216,6 +217,8 @@ def criterion(crit: int, F, tau=0.0):
         return 1.0 / np.linalg.det(M)
     if crit == CRIT_E:
         return np.max(1.0 / np.linalg.eigvalsh(M), axis=-1)
+    if crit == LOG_D:
+        return -np.linalg.slogdet(M)[1]
     raise ValueError(crit)
 
 
@@ -234,6 +237,8 @@ def criterion_matrix_gradient(crit: int, F, tau=0.0):
         return -Mi @ Mi
     if crit == CRIT_D:
         return -np.linalg.inv(M) / np.linalg.det(M)[..., None, None]
+    if crit == LOG_D:
+        return -np.linalg.inv(M)
     lam, V = np.linalg.eigh(M)
     v = V[..., :, 0]
     vv = v[..., :, None] * v[..., None, :]

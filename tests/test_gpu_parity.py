@@ -89,6 +89,27 @@ def test_random_designs_vs_cpp_oracle(name, method, m, oracles, built_library):
         assert i == int(np.argmin(c)) and v == c[i]
 
 
+@pytest.mark.parametrize("name", ["readme", "lv_fishing", "lv_ic"])
+def test_log_det_criterion_extension(name, oracles, built_library):
+    """-log det(F + tau I) (criterion id 6; BASELINE north_star's "FisherD logdet F" — not one of the
+    reference's six): objective, F and the full gradient against the C++ oracle (np = 1 and np = 2 closed
+    forms), the host-side criterion call against numpy, and consistency with the reference's D criterion
+    on the same designs: LogD + tau-part == log(DCriterion) where both are defined."""
+    ctx = make_problem(name, D.LogDCriterion, "rk4", 4).context()
+    des = random_designs(name, ctx.n_var, 600, 77)
+    c, g, F = ctx.evaluate(des)
+    oc, og, oF = oracles(name, 6, "rk4", 4).evaluate(des, grad=True)
+    assert rel(c, oc) < RTOL and rel(F, oF) < RTOL and rel_rows(g, og) < RTOL
+    cd = make_problem(name, D.DCriterion, "rk4", 4).context().evaluate(des, grad=False)[0]
+    tau = des[:, -1]
+    ok = cd - tau > 0
+    assert ok.sum() > 500 and np.allclose((c - tau)[ok], np.log((cd - tau)[ok]), rtol=1e-9, atol=1e-12)
+    A = np.random.default_rng(5).standard_normal((4, 7))
+    M = A @ A.T
+    assert np.isclose(D.LogDCriterion()(M, 0.5), -np.linalg.slogdet(M + 0.5 * np.eye(4))[1], rtol=1e-12)
+    assert np.allclose(D.LogDCriterion().gradient(M, 0.5), -np.linalg.inv(M + 0.5 * np.eye(4)), rtol=1e-10)
+
+
 def test_ragged_and_empty_batches(oracles, built_library):
     ctx = make_problem("lv_fishing", D.DCriterion).context()
     orc = oracles("lv_fishing", 4, "rk4", 4)

@@ -143,7 +143,7 @@ def test_integer_codes_match_the_defines():
     crit = dict(re.findall(r"criterion_id\(::(\w+)Criterion\) = Cint\((\d+)\)", SHIM))
     assert {k: int(v) for k, v in crit.items()} == {
         "FisherA": defs["DYNOED_FISHER_A"], "FisherD": defs["DYNOED_FISHER_D"], "FisherE": defs["DYNOED_FISHER_E"],
-        "A": defs["DYNOED_A"], "D": defs["DYNOED_D"], "E": defs["DYNOED_E"]}
+        "A": defs["DYNOED_A"], "D": defs["DYNOED_D"], "E": defs["DYNOED_E"], "LogD": defs["DYNOED_LOG_D"]}
     assert int(re.search(r"const DYNOED_OK = Cint\((\d+)\)", SHIM).group(1)) == defs["DYNOED_OK"]
     # the Python host uses the same numbers
     assert (runtime.RK4, runtime.TSIT5, runtime.ROS2, runtime.ROS3P, runtime.RODAS3) == (0, 1, 2, 3, 4)

@@ -45,7 +45,22 @@ def test_criteria_kat(crit, res):   # test/criteria.jl:26-29, isapprox default r
     assert np.isclose(v, res, rtol=1.5e-8, atol=0)
 
 
-@pytest.mark.parametrize("crit", range(6))
+def test_log_det_extension_against_the_reference_d_criteria():
+    """-log det(F + tau I) (DYNOED_LOG_D, an extension: BASELINE's north_star names "FisherD logdet F",
+    the reference has -det F and 1/det F): consistent with the reference's own D values on the KAT matrix of
+    test/criteria.jl, in both oracles."""
+    from oracle.oed_oracle import LOG_D
+    fisher_d, crit_d = dict(KAT)[1], dict(KAT)[4]
+    v = criterion(LOG_D, F_KAT)
+    assert np.isclose(v, -np.log(-fisher_d), rtol=1e-9) and np.isclose(v, np.log(crit_d), rtol=1e-9)
+    vc = cpp_oracle.lib().oracle_criterion(LOG_D, 5, vector_from_symmetric(F_KAT).ctypes.data, 0.0, None)
+    assert np.isclose(vc, v, rtol=1e-12)
+    Lc = np.empty(15)
+    cpp_oracle.lib().oracle_criterion(LOG_D, 5, vector_from_symmetric(F_KAT).ctypes.data, 0.25, Lc.ctypes.data)
+    assert np.allclose(symmetric_from_vector(Lc), criterion_matrix_gradient(LOG_D, F_KAT, 0.25), rtol=1e-10, atol=0)
+
+
+@pytest.mark.parametrize("crit", range(7))
 def test_criterion_gradient_vs_finite_differences(crit):
     rng = np.random.default_rng(crit)
     for n in (1, 2, 3, 5):
