@@ -120,6 +120,34 @@ static cudaError_t attrs_ros(int block, size_t smem, cudaFuncAttributes* fa, int
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, block, smem);
 }
 
+// forward-only gradient mode of an explicit tableau (DYNOED_GRAD_NO_CONTROLS): models without unknown initial
+// conditions run the evaluation kernel's own forward sweep with the quadratures kept (oed_wgrad_kernel); the
+// others the generic forward-only kernel, which carries dual parts for the initial conditions
+template <class M, class Tab>
+static cudaError_t launch_fwdonly(bool uc, bool pdl, const EvalParams& P, int grid, int block, size_t smem, cudaStream_t st) {
+    if constexpr (M::NIC == 0)
+        return uc ? launch_kernel(oed_wgrad_kernel<M, Tab, true>, pdl, P, grid, block, smem, st)
+                  : launch_kernel(oed_wgrad_kernel<M, Tab, false>, pdl, P, grid, block, smem, st);
+    else
+        return launch_ros<M, ExplicitStepper<Tab>, true>(pdl, P, grid, block, smem, st);
+}
+template <class M, class Tab, bool UC>
+static cudaError_t attrs_wgrad(int block, size_t smem, cudaFuncAttributes* fa, int* bps) {
+    auto kern = oed_wgrad_kernel<M, Tab, UC>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(fa, kern);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, block, smem);
+}
+template <class M, class Tab>
+static cudaError_t attrs_fwdonly(bool uc, int block, size_t smem, cudaFuncAttributes* fa, int* bps) {
+    if constexpr (M::NIC == 0)
+        return uc ? attrs_wgrad<M, Tab, true>(block, smem, fa, bps) : attrs_wgrad<M, Tab, false>(block, smem, fa, bps);
+    else
+        return attrs_ros<M, ExplicitStepper<Tab>, true>(block, smem, fa, bps);
+}
+
 // Rosenbrock gradient of a model with unknown initial conditions and no controls: ros_ic_kernel
 template <class M, class RT>
 static cudaError_t launch_ic(bool pdl, const EvalParams& P, int grid, int block, size_t smem, cudaStream_t st) {
@@ -190,8 +218,8 @@ static cudaError_t launch_model(int method, bool grad, bool uc, bool pdl, const 
                : cg ? launch_ros<M, RosenbrockStepper<TabRODAS3>, true, (M::NCTRL > 0)>(pdl, P, grid, block, smem, st)
                     : launch_ros<M, RosenbrockStepper<TabRODAS3>, true>(pdl, P, grid, block, smem, st);
     // forward-only gradient mode of the explicit tableaus (kFwdOnly + method)
-    if (method == kFwdOnly + DYNOED_RK4) return launch_ros<M, ExplicitStepper<TabRK4>, true>(pdl, P, grid, block, smem, st);
-    return launch_ros<M, ExplicitStepper<TabTsit5>, true>(pdl, P, grid, block, smem, st);
+    if (method == kFwdOnly + DYNOED_RK4) return launch_fwdonly<M, TabRK4>(uc, pdl, P, grid, block, smem, st);
+    return launch_fwdonly<M, TabTsit5>(uc, pdl, P, grid, block, smem, st);
 }
 
 template <class M, class Tab>
@@ -228,8 +256,8 @@ static cudaError_t attrs_model(int method, bool grad, bool uc, int block, size_t
         return !grad ? attrs_ros<M, RosenbrockStepper<TabRODAS3>, false>(block, smem, fa, bps)
                : cg ? attrs_ros<M, RosenbrockStepper<TabRODAS3>, true, (M::NCTRL > 0)>(block, smem, fa, bps)
                     : attrs_ros<M, RosenbrockStepper<TabRODAS3>, true>(block, smem, fa, bps);
-    if (method == kFwdOnly + DYNOED_RK4) return attrs_ros<M, ExplicitStepper<TabRK4>, true>(block, smem, fa, bps);
-    return attrs_ros<M, ExplicitStepper<TabTsit5>, true>(block, smem, fa, bps);
+    if (method == kFwdOnly + DYNOED_RK4) return attrs_fwdonly<M, TabRK4>(uc, block, smem, fa, bps);
+    return attrs_fwdonly<M, TabTsit5>(uc, block, smem, fa, bps);
 }
 
 template <class M>
@@ -1833,8 +1861,12 @@ int dynoed_kernel_stats_query(dynoed_ctx* ctx, int with_grad, dynoed_kernel_stat
     o->flops_per_design_grad = (fwd + bwd) * ctx->n_steps + (double)ctx->n_intervals * (fwd_iv + bwd_iv) + epi;
     if (g == 2) {   // forward-only gradient: unweighted per-observation quadratures, F += w P per interval,
                     // d/dw = <Lambda, P> in the epilogue
-        const double f2 = (double)S * mi.flops_ros_f + 2.0 * mi.nz * nza + 2.0 * (mi.nz + nq) * S + nza + S;
-        o->flops_per_design_grad = f2 * ctx->n_steps + (double)ctx->n_intervals * (mi.flops_consts + 4.0 * nq) + epi;
+        if (mi.n_ic == 0) {   // oed_wgrad_kernel: the objective kernel's sweep + <Lambda, P_ij> per interval
+            o->flops_per_design_grad = o->flops_per_design_eval + (double)ctx->n_intervals * 2.0 * nq + mi.np;
+        } else {
+            const double f2 = (double)S * mi.flops_ros_f + 2.0 * mi.nz * nza + 2.0 * (mi.nz + nq) * S + nza + S;
+            o->flops_per_design_grad = f2 * ctx->n_steps + (double)ctx->n_intervals * (mi.flops_consts + 4.0 * nq) + epi;
+        }
     }
     o->bytes_per_design = 8.0 * (ctx->n_var + 1 + (with_grad ? ctx->n_var : 0) + mi.nF);
     return DYNOED_OK;

@@ -774,8 +774,13 @@ __device__ __forceinline__ void backward_interval(const EvalParams& P, const Ckp
 // ----------------------------------------------------------------------------------------------
 // The evaluation kernel
 // ----------------------------------------------------------------------------------------------
-template <class M, class Tab, bool GRAD, bool UCOEF>
-__global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) {
+// MODE 0: objective (+ F, trajectory) only.  MODE 1: + full gradient by the discrete adjoint sweep.
+// MODE 2: + d/dw and d/dtau only (DYNOED_GRAD_NO_CONTROLS for models without unknown initial conditions):
+// the forward sweep keeps the per-interval quadratures, no checkpoints, no backward sweep; control entries
+// of the gradient are NaN ("not computed").
+template <class M, class Tab, int MODE, bool UCOEF>
+__device__ __forceinline__ void oed_eval_body(const EvalParams& P) {
+    constexpr bool GRAD = MODE != 0, ADJ = MODE == 1;
     constexpr int NX = M::NX, NP = M::NP, NZ = M::NZ, NF = M::NF, NOBS = M::NOBS, NCTRL = M::NCTRL;
     constexpr int NCU = NCTRL > 0 ? NCTRL : 1, NQ = NOBS * NF;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -836,8 +841,10 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
 #pragma unroll
             for (int a = 0; a < NF; ++a) F[a] = 0.0;
             // per-CTA scratch: (x, G) checkpoints [n_steps][NZ][128], then interval quadratures [N][NQ][128]
-            double* tr = P.traj + ((size_t)blockIdx.x * ((size_t)P.n_steps * NZ + (size_t)N * NQ)) * kMaxTile + tid;
-            double* pq = tr + (size_t)P.n_steps * NZ * kMaxTile;
+            // (MODE 2: quadratures only, in the forward-only kernels' layout [grid][N * NQ + n_ctrl_values][128])
+            double* tr = P.traj + ((size_t)blockIdx.x * (ADJ ? (size_t)P.n_steps * NZ + (size_t)N * NQ
+                                                             : (size_t)N * NQ + P.n_ctrl_values)) * kMaxTile + tid;
+            double* pq = ADJ ? tr + (size_t)P.n_steps * NZ * kMaxTile : tr;
             double* xg = (P.xgrid && active) ? P.xgrid + (size_t)g * (N + 1) * (NZ + NF) : nullptr;
             if (xg) {
 #pragma unroll
@@ -874,7 +881,7 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
                 }
                 M::consts(u, th, c);
                 double Pint[NQ];
-                forward_interval<M, Tab, GRAD, UCOEF>(P, K, s0, s1, tr, z, Pint, u, th, c);
+                forward_interval<M, Tab, ADJ, UCOEF>(P, K, s0, s1, tr, z, Pint, u, th, c);
                 // F is linear in the weights: F += w_i P_i ; the P_i are kept for d/dw
 #pragma unroll
                 for (int i = 0; i < NOBS; ++i)
@@ -885,7 +892,7 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
 #pragma unroll
                     for (int a = 0; a < NQ; ++a) pq[((size_t)DYNOED_QSLOT(j) * NQ + a) * kMaxTile] = Pint[a];
 #else
-                    const uint64_t pol = j >= P.hot_interval ? K.hot : K.cold;
+                    const uint64_t pol = (!ADJ || j >= P.hot_interval) ? K.hot : K.cold;   // MODE 2: all of it fits L2
 #pragma unroll
                     for (int a = 0; a < NQ; ++a) st_hint(pq + ((size_t)DYNOED_QSLOT(j) * NQ + a) * kMaxTile, Pint[a], pol);
 #endif
@@ -911,8 +918,48 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
             }
             if (active && obj < best_val) { best_val = obj; best_idx = P.index_base + g; }   // NaN never wins
 
+            // ---------------- d/dw, d/dtau from the stored quadratures (MODE 2) ----------------
+            if (MODE == 2) {
+                static_assert(MODE != 2 || M::NIC == 0, "MODE 2 does not differentiate initial conditions");
+                double Ls[NF];
+#pragma unroll
+                for (int jj = 0; jj < NP; ++jj)
+#pragma unroll
+                    for (int ii = 0; ii <= jj; ++ii) Ls[tri(ii, jj)] = (ii == jj ? 1.0 : 2.0) * L[tri(ii, jj)];
+                double wb[NOBS];
+                int wk[NOBS];
+#pragma unroll
+                for (int i = 0; i < NOBS; ++i) { wb[i] = 0.0; wk[i] = -1; }
+                for (int j = 0; j < N; ++j) {
+                    double Pj[NQ];
+#pragma unroll
+                    for (int a = 0; a < NQ; ++a) Pj[a] = ld_pinned(pq + ((size_t)DYNOED_QSLOT(j) * NQ + a) * kMaxTile);
+#pragma unroll
+                    for (int i = 0; i < NOBS; ++i) {
+                        const int idx = __ldg(P.indicators + (NCTRL + i) * N + j);
+                        if (idx != wk[i]) {
+                            if (wk[i] >= 0) row[P.w_off[i] + wk[i]] = wb[i];
+                            wb[i] = 0.0; wk[i] = idx;
+                        }
+#pragma unroll
+                        for (int k = 0; k < NF; ++k) wb[i] = fma(Ls[k], Pj[i * NF + k], wb[i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NOBS; ++i)
+                    if (wk[i] >= 0) row[P.w_off[i] + wk[i]] = wb[i];
+#pragma unroll
+                for (int k = 0; k < NCTRL; ++k)
+                    for (int idx = 0; idx < P.ctrl_len[k]; ++idx)
+                        row[P.ctrl_off[k] + idx] = __longlong_as_double(0x7ff8000000000000LL);   // not computed
+                double trL = 1.0;
+#pragma unroll
+                for (int i = 0; i < NP; ++i) trL += L[tri(i, i)];
+                row[P.tau_off] = trL;
+            }
+
             // ---------------- backward (discrete adjoint) sweep ----------------
-            if (GRAD) {
+            if (ADJ) {
                 double lam[NZ];
 #pragma unroll
                 for (int a = 0; a < NZ; ++a) lam[a] = 0.0;
@@ -1039,6 +1086,18 @@ __global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) 
     }
 
     argmin_tail(P, best_val, best_idx);
+}
+
+template <class M, class Tab, bool GRAD, bool UCOEF>
+__global__ void __launch_bounds__(kMaxTile) oed_eval_kernel(const EvalParams P) {
+    oed_eval_body<M, Tab, GRAD ? 1 : 0, UCOEF>(P);
+}
+
+// objective + d/dw + d/dtau (SURVEY.md 8d's sub-metric; DYNOED_GRAD_NO_CONTROLS) for models without unknown
+// initial conditions: the evaluation kernel's forward sweep with the quadratures kept, no backward sweep
+template <class M, class Tab, bool UCOEF>
+__global__ void __launch_bounds__(kMaxTile) oed_wgrad_kernel(const EvalParams P) {
+    if constexpr (M::NIC == 0) oed_eval_body<M, Tab, 2, UCOEF>(P);
 }
 
 // ----------------------------------------------------------------------------------------------
