@@ -130,6 +130,86 @@ def system_from_ir(ir: dict) -> ODESystem:
                      name=ir.get("name", "sys"))
 
 
+# ----------------------------------------------------------------------------------------------
+# Optional section "augmented": the explicit right-hand sides of the REFERENCE-built system,
+# `full_equations(structural_simplify(OEDSystem(sys)))`, one entry per differential state, written by
+# julia/export_ir.jl with canonical identifiers that depend only on positions the reference fixes
+# (/root/reference/src/augment.jl:233-243: states = [x; vec(G); F[triu]; vec(Q)], parameters =
+# [p; unknown initial conditions; w]):
+#     x<k>      k-th state of the user system (0-based, as in "states")
+#     G_<i>_<j> sensitivity of state i w.r.t. tunable j (1-based, the reference's G[i,j])
+#     F_<i>_<j> Fisher entry (i <= j, 1-based)
+#     p<k>      k-th parameter of the user system (0-based, as in "parameters")
+#     ic<i>     unknown initial condition of state i (1-based)          w<i>  measurement weight i (1-based)
+# When the section is present, `build_from_ir` refuses to emit a kernel unless the host's own augmentation
+# (augment.py) reproduces every one of those right-hand sides: the reference's simplified system is the
+# authority for the equations that reach the kernel template, the Python derivation only adds the
+# structure (Jacobian blocks, adjoint) the emitter needs.
+# ----------------------------------------------------------------------------------------------
+def _canonical_symbols(simp, user_ir=None):
+    """{our symbol: canonical identifier} for a SimplifiedOEDSystem."""
+    aug = simp.aug
+    names = {}
+    for k, v in enumerate(aug.x):
+        names[v] = sp.Symbol(f"x{k}")
+    nx, np_ = aug.G.shape
+    for i in range(nx):
+        for j in range(np_):
+            names[aug.G[i, j]] = sp.Symbol(f"G_{i + 1}_{j + 1}")
+    for i in range(np_):
+        for j in range(i, np_):
+            names[aug.F[i, j]] = sp.Symbol(f"F_{i + 1}_{j + 1}")
+    for k, v in enumerate(aug.base.parameters()):
+        names[v] = sp.Symbol(f"p{k}")
+    for v, i in zip(aug.x_ic, aug.unknown_initial_conditions):
+        names[v] = sp.Symbol(f"ic{i}")
+    for i, v in enumerate(aug.w, start=1):
+        names[v] = sp.Symbol(f"w{i}")
+    names[aug.iv] = sp.Symbol("t")
+    return names
+
+
+def augmented_to_ir(simp) -> dict:
+    """The "augmented" section as THIS host derives it (what export_ir.jl writes from the reference's
+    own `structural_simplify(OEDSystem(sys))`)."""
+    names = _canonical_symbols(simp)
+    eqs = []
+    for v, r in zip(simp.x, simp.f):
+        eqs.append(dict(state=names[v].name, rhs=_expr_str(r, names)))
+    for j in range(simp.np_):
+        for i in range(simp.nx):
+            eqs.append(dict(state=names[simp.G[i, j]].name, rhs=_expr_str(simp.dG[i, j], names)))
+    for v, r in zip(simp.F_triu, simp.dF):
+        eqs.append(dict(state=names[v].name, rhs=_expr_str(r, names)))
+    return dict(equations=eqs)
+
+
+def check_augmented(section: dict, simp, rtol: float = 1e-10, points: int = 4) -> int:
+    """Compare the reference-exported right-hand sides with this host's, numerically at random points (the two
+    sides differ in expression form, not in value).  Raises ValueError naming the first disagreement."""
+    import random
+    ours = {e["state"]: sp.sympify(e["rhs"]) for e in augmented_to_ir(simp)["equations"]}
+    theirs = {}
+    for e in section["equations"]:
+        theirs[e["state"]] = sp.sympify(e["rhs"].replace("^", "**"))
+    missing = sorted(set(ours) - set(theirs))
+    extra = sorted(set(theirs) - set(ours))
+    if missing or extra:
+        raise ValueError(f"augmented systems differ in their differential states: the reference's system lacks "
+                         f"{missing}, this host's lacks {extra}")
+    rng = random.Random(20262)
+    syms = sorted(set().union(*[e.free_symbols for e in ours.values()], *[e.free_symbols for e in theirs.values()]),
+                  key=lambda v: v.name)
+    for _ in range(points):
+        at = {v: rng.uniform(0.5, 1.5) for v in syms}
+        for st in ours:
+            a, b = float(ours[st].evalf(30, subs=at)), float(theirs[st].evalf(30, subs=at))
+            if abs(a - b) > rtol * max(1.0, abs(a), abs(b)):
+                raise ValueError(f"augmented right-hand side of {st} differs from the reference's: "
+                                 f"{ours[st]}  vs  {theirs[st]}")
+    return len(ours)
+
+
 def build_from_ir(path: str) -> dict:
     """IR file -> emitted model -> compiled library.  Returns {library, model, n_var, ...}."""
     from .augment import OEDSystem, structural_simplify
@@ -137,11 +217,13 @@ def build_from_ir(path: str) -> dict:
     with open(path) as fh:
         ir = json.load(fh)
     simp = structural_simplify(OEDSystem(system_from_ir(ir)))
+    checked = check_augmented(ir["augmented"], simp) if ir.get("augmented") else 0
     lib, name, info = _resolve_model(simp)
     from . import runtime
     return dict(library=lib or runtime.LIB_PATH, model=name, nx=info["nx"], np=info["np"],
                 n_obs=info["n_obs"], n_ctrl=info["n_ctrl"], n_ic=info["n_ic"],
-                theta_names=info["theta_names"], state_names=info["state_names"])
+                theta_names=info["theta_names"], state_names=info["state_names"],
+                augmented_equations_checked=checked)
 
 
 if __name__ == "__main__":
@@ -149,6 +231,10 @@ if __name__ == "__main__":
         print(json.dumps(build_from_ir(sys.argv[2]), ensure_ascii=False))
     elif len(sys.argv) == 3 and sys.argv[1] == "export":
         from . import models
-        print(json.dumps(system_to_ir(models.BUILTIN[sys.argv[2]]()), indent=1, ensure_ascii=False))
+        from .augment import OEDSystem, structural_simplify
+        sys0 = models.BUILTIN[sys.argv[2]]()
+        out = system_to_ir(sys0)
+        out["augmented"] = augmented_to_ir(structural_simplify(OEDSystem(sys0)))
+        print(json.dumps(out, indent=1, ensure_ascii=False))
     else:
         print("usage: python -m dynamicoed.jl_b200.ir build <model.json> | export <builtin name>")

@@ -6,19 +6,26 @@
 # tests/test_ir.py (Python round trip of every built-in model).
 #
 # The file describes the UN-augmented system exactly as the user declares it for DynamicOED.jl
-# (e.g. /root/reference/test/references/LotkaVolterra.jl:10-36): the augmentation
-# (`OEDSystem`, src/augment.jl:128-244) and `structural_simplify` are re-done by the Python host
-# with the same equations, so nothing MTK-internal has to cross the boundary.
+# (e.g. /root/reference/test/references/LotkaVolterra.jl:10-36) AND, in its "augmented" section, the
+# explicit right-hand sides of the reference's own `structural_simplify(OEDSystem(sys))`
+# (`full_equations`: MTK's tearing result with the observed equations substituted back).  The Python
+# host derives the structure the kernel emitter needs (Jacobian blocks, adjoint) from the user system
+# and REFUSES to emit a kernel unless its augmented right-hand sides equal the exported ones
+# (dynamicoed.jl_b200/ir.py::check_augmented): the MTK-simplified system is the authority for the
+# equations that reach the kernel template.
 #
 #   include("export_ir.jl")
 #   export_ir(lotka_volterra, "lv.json")                       # the plain ODESystem, before OEDSystem()
-#   run(`python -m dynamicoed.jl_b200.ir build lv.json`)       # -> {"library": ..., "model": ...}
+#   run(`python -m dynamicoed.jl_b200.ir build lv.json`)       # -> {"library": ..., "model": ..., "augmented_equations_checked": 9}
+#   export_ir(sys, path; augmented = false)                    # user system only (no cross-check)
 module DynoedIR
 
 using ModelingToolkit
 using ModelingToolkit: getdefault, hasdefault, istunable, isinput, getbounds, hasbounds
 using Symbolics
-using DynamicOED: is_measured, get_measurement_rate
+using DynamicOED: is_measured, get_measurement_rate, OEDSystem, is_initial_condition, get_initial_condition_id,
+                  is_measurement_function
+using LinearAlgebra: triu
 
 export export_ir
 
@@ -35,8 +42,65 @@ function expr_text(ex, alias::Dict)
     replace(s, "^" => "**")
 end
 
+# Canonical identifiers of the augmented system, from POSITIONS the reference fixes
+# (/root/reference/src/augment.jl:233-243): states(OEDSystem(sys)) = [x; vec(G); F[triu]; vec(Q)],
+# parameters = [union(p, p_tunable); w].  No name parsing.
+function augmented_alias(sys, oed)
+    x, p = states(sys), parameters(sys)
+    nx = length(x)
+    ps = parameters(oed)
+    ic = filter(is_initial_condition, ps)
+    w = filter(is_measurement_function, ps)
+    np_ = count(v -> ModelingToolkit.istunable(v, false) && !ModelingToolkit.isinput(v), p) + length(ic)
+    st = states(oed)
+    alias = Dict{Any, Any}()
+    sym(s) = Symbolics.unwrap(Symbolics.variable(Symbol(s)))
+    for k in 1:nx
+        alias[Symbolics.unwrap(st[k])] = sym("x$(k-1)")
+    end
+    for j in 1:np_, i in 1:nx                              # vec(G): column-major
+        alias[Symbolics.unwrap(st[nx + (j - 1) * nx + i])] = sym("G_$(i)_$(j)")
+    end
+    k = nx + nx * np_
+    for j in 1:np_, i in 1:j                               # F[triu(trues(np, np))]: column-major upper triangle
+        k += 1
+        alias[Symbolics.unwrap(st[k])] = sym("F_$(i)_$(j)")
+    end
+    for (k, v) in enumerate(p)
+        alias[Symbolics.unwrap(v)] = sym("p$(k-1)")
+    end
+    for v in ic
+        alias[Symbolics.unwrap(v)] = sym("ic$(get_initial_condition_id(v))")
+    end
+    for (i, v) in enumerate(w)
+        alias[Symbolics.unwrap(v)] = sym("w$(i)")
+    end
+    alias
+end
+
+# "augmented": one entry per differential state of the reference's simplified augmented system
+function augmented_section(sys)
+    oed = OEDSystem(sys)
+    alias = augmented_alias(sys, oed)
+    simp = structural_simplify(oed)
+    io = IOBuffer()
+    print(io, "{\"equations\": [")
+    first = true
+    for eq in ModelingToolkit.full_equations(simp)
+        lhs = Symbolics.unwrap(eq.lhs)
+        (Symbolics.istree(lhs) && Symbolics.operation(lhs) isa Differential) || continue
+        v = only(Symbolics.arguments(lhs))
+        haskey(alias, v) || continue                       # Q rows are observed, not states
+        first || print(io, ", ")
+        first = false
+        print(io, "{\"state\": ", json_str(string(alias[v])), ", \"rhs\": ", json_str(expr_text(eq.rhs, alias)), "}")
+    end
+    print(io, "]}")
+    String(take!(io))
+end
+
 function export_ir(sys::ModelingToolkit.AbstractODESystem, path::AbstractString;
-        tspan = ModelingToolkit.get_tspan(sys))
+        tspan = ModelingToolkit.get_tspan(sys), augmented::Bool = true)
     t = ModelingToolkit.get_iv(sys)
     sts = states(sys)
     ps = parameters(sys)
@@ -92,7 +156,9 @@ function export_ir(sys::ModelingToolkit.AbstractODESystem, path::AbstractString;
             ", \"rhs\": ", json_str(expr_text(eq.rhs, alias)),
             ", \"measurement_rate\": ", json_num(r), ", \"rate_is_count\": ", json_num(r isa Integer), "}")
     end
-    print(io, "]}\n")
+    print(io, "]")
+    augmented && print(io, ",\n\"augmented\": ", augmented_section(sys))
+    print(io, "}\n")
     write(path, String(take!(io)))
     path
 end

@@ -53,3 +53,40 @@ def test_build_from_ir_resolves_builtin_models_without_recompiling(tmp_path, bui
     out = ir.build_from_ir(str(path))
     assert out["model"] == "lv_fishing" and out["library"] == runtime.LIB_PATH
     assert (out["nx"], out["np"], out["n_obs"], out["n_ctrl"], out["n_ic"]) == (2, 2, 2, 1, 0)
+
+
+@pytest.mark.parametrize("name", list(models.BUILTIN))
+def test_augmented_section_is_checked_against_the_hosts_own_augmentation(name):
+    """The "augmented" section carries the reference's own `full_equations(structural_simplify(OEDSystem(sys)))`
+    (julia/export_ir.jl); `build_from_ir` emits a kernel only if this host's augmentation reproduces every
+    right-hand side.  Here the section is produced by the host itself, re-ordered and re-written in another
+    expression form (expanded / factored, `^` for powers as Julia prints them), and then tampered with."""
+    import sympy as sp
+    simp = D.structural_simplify(D.OEDSystem(models.BUILTIN[name]()))
+    sec = ir.augmented_to_ir(simp)
+    assert len(sec["equations"]) == len(simp.states)
+    other = {"equations": [dict(state=e["state"], rhs=str(sp.factor(sp.sympify(e["rhs"]))).replace("**", "^"))
+                           for e in reversed(sec["equations"])]}
+    assert ir.check_augmented(json.loads(json.dumps(other)), simp) == len(simp.states)
+    bad = json.loads(json.dumps(sec))
+    bad["equations"][-1]["rhs"] = "1.0000001*(" + bad["equations"][-1]["rhs"] + ")"
+    with pytest.raises(ValueError, match="differs from the reference"):
+        ir.check_augmented(bad, simp)
+    short = {"equations": sec["equations"][:-1]}
+    with pytest.raises(ValueError, match="differential states"):
+        ir.check_augmented(short, simp)
+
+
+def test_build_from_ir_runs_the_cross_check(tmp_path, built_library):
+    from dynamicoed.jl_b200 import runtime
+    sys0 = models.lotka_volterra_fishing()
+    d = ir.system_to_ir(sys0)
+    d["augmented"] = ir.augmented_to_ir(D.structural_simplify(D.OEDSystem(sys0)))
+    path = tmp_path / "lv_aug.json"
+    path.write_text(json.dumps(d, ensure_ascii=False))
+    out = ir.build_from_ir(str(path))
+    assert out["model"] == "lv_fishing" and out["augmented_equations_checked"] == 9
+    d["augmented"]["equations"][2]["rhs"] += " + 1e-6*x0"
+    path.write_text(json.dumps(d, ensure_ascii=False))
+    with pytest.raises(ValueError):
+        ir.build_from_ir(str(path))

@@ -167,15 +167,29 @@ def test_shim_keeps_the_reference_signature():
             assert piece in rs, piece
 
 
+def D_simplified():
+    import dynamicoed.jl_b200 as D
+    return D.structural_simplify(D.OEDSystem(models.lotka_volterra_fishing()))
+
+
 def test_export_ir_writes_the_keys_ir_py_reads():
     keys = lambda section: set(re.findall(r'\\"(\w+)\\": ', section))
-    top = keys(EXPORT)
+    MAIN = EXPORT[EXPORT.index("function export_ir("):]          # the user-system part of the file
+    top = keys(MAIN)
     want = ir.system_to_ir(models.lotka_volterra_fishing())
     assert set(want) <= top, set(want) - top
-    st = EXPORT[EXPORT.index('\\"states\\": ['):EXPORT.index('\\"parameters\\": [')]
-    pa = EXPORT[EXPORT.index('\\"parameters\\": ['):EXPORT.index('\\"equations\\": [')]
-    eq = EXPORT[EXPORT.index('\\"equations\\": ['):EXPORT.index('\\"observed\\": [')]
-    ob = EXPORT[EXPORT.index('\\"observed\\": ['):]
+    st = MAIN[MAIN.index('\\"states\\": ['):MAIN.index('\\"parameters\\": [')]
+    pa = MAIN[MAIN.index('\\"parameters\\": ['):MAIN.index('\\"equations\\": [')]
+    eq = MAIN[MAIN.index('\\"equations\\": ['):MAIN.index('\\"observed\\": [')]
+    ob = MAIN[MAIN.index('\\"observed\\": ['):MAIN.index('augmented &&')]
+    # the "augmented" section (reference-built simplified system) and its canonical identifiers
+    AUG = EXPORT[EXPORT.index("function augmented_alias("):EXPORT.index("function export_ir(")]
+    sec = ir.augmented_to_ir(D_simplified())
+    assert keys(AUG) == {"equations"} | set(sec["equations"][0])
+    assert "augmented" in top
+    for ident in ('"x$(k-1)"', '"G_$(i)_$(j)"', '"F_$(i)_$(j)"', '"p$(k-1)"', '"ic$(get_initial_condition_id(v))"', '"w$(i)"'):
+        assert ident in AUG, ident
+    assert {e["state"] for e in sec["equations"]} == {"x0", "x1", "G_1_1", "G_2_1", "G_1_2", "G_2_2", "F_1_1", "F_1_2", "F_2_2"}
     assert keys(st) - {"states"} == set(want["states"][0])
     assert keys(pa) - {"parameters"} == set(want["parameters"][0])
     assert keys(eq) - {"equations"} == set(want["equations"][0])
