@@ -662,6 +662,10 @@ __device__ __forceinline__ void argmin_tail(const EvalParams& P, double best_val
     }
 }
 
+#ifndef DYNOED_BWD_UNROLL
+#define DYNOED_BWD_UNROLL 1   // unroll factor of the backward step loop (measurement switch)
+#endif
+constexpr int kBwdUnroll = DYNOED_BWD_UNROLL;
 #ifndef DYNOED_PF_DIST
 #define DYNOED_PF_DIST 3      // backward sweep: checkpoints are pulled from HBM into L2 this many steps ahead
 #endif
@@ -731,6 +735,7 @@ __device__ __forceinline__ void backward_interval(const EvalParams& P, const Ckp
                                                   double (&lam)[M::NZ], const double* u, const double* cwL,
                                                   const double* th, const double* c, double* ub) {
     constexpr int NZ = M::NZ;
+#pragma unroll kBwdUnroll
     for (int s = s1 - 1; s >= s0; --s) {
         double znext[NZ];
         const int sp = s > 0 ? s - 1 : 0;
