@@ -1793,9 +1793,13 @@ int dynoed_kernel_stats_query(dynoed_ctx* ctx, int with_grad, dynoed_kernel_stat
             nza += (ctx->method == DYNOED_RK4 ? TabRK4::a(i, j) : TabTsit5::a(i, j)) != 0.0;
     }
     const int nq = mi.n_obs * mi.nF;
+    // stages with equal weights share an accumulator set (QuadClasses): no scalings, one more fold per set
+    const int nsets = ctx->method == DYNOED_RK4 ? QuadClasses<TabRK4>::N : QuadClasses<TabTsit5>::N;
+    if (nsets > 1) nscaled = 0;
+    const double fold = 2.0 * nq * (nsets - 1);
     const double fwd = (double)S * mi.flops_primal + 2.0 * mi.nz * nza + 2.0 * mi.nz * S + 2.0 * nq * S +
-                       (double)nscaled * mi.n_obs * mi.np + (ctx->ucoef ? 0.0 : 2.0 * nq);
-    const double fwd_iv = (ctx->ucoef ? 3.0 : 2.0) * nq + mi.flops_consts;
+                       (double)nscaled * mi.n_obs * mi.np + (ctx->ucoef ? 0.0 : 2.0 * nq + fold);
+    const double fwd_iv = (ctx->ucoef ? 3.0 * nq + fold : 2.0 * nq) + mi.flops_consts;
     const double bwd = (double)(S - 1) * mi.flops_primal_z + (double)S * mi.flops_adjoint + 4.0 * mi.nz * nza +
                        2.0 * S * (mi.nz + mi.n_ctrl);
     const double bwd_iv = (double)mi.n_obs * (1 + mi.nF) + 2.0 * nq + mi.flops_consts;
