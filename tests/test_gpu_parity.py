@@ -373,15 +373,23 @@ def test_subwave_launches_overlap_behind_the_scratch_guard(built_library):
         outs = [(torch.empty(n, dtype=torch.float64, device="cuda"), torch.empty_like(ins[k]),
                  torch.empty((n, 3), dtype=torch.float64, device="cuda")) for k in range(K)]
         over0 = ctx.kernel_stats(True)["overlapped_launches"]
-        for rep in range(4):
+        REPS = 16
+        for rep in range(REPS):
             for k in range(K):
                 ctx.eval_batch(ins[k], *outs[k], async_=True, flags=OVERLAP_OK)
         ctx.sync()
-        assert ctx.kernel_stats(True)["overlapped_launches"] - over0 >= 4 * K - 1
+        assert ctx.kernel_stats(True)["overlapped_launches"] - over0 >= REPS * K - 1
         for k in range(K):
             for a, b in zip(outs[k], ref[k][:3]):
                 assert torch.equal(a, b)
+        # the scratch set's result slot must hold the LAST launch's batch: waiters on a set are served in
+        # launch order (a plain lock let a later launch overtake an earlier one here, about one run in four)
         assert ctx.argmin() == ref[K - 1][3]
+        for last in (2, 3):                       # ... also when the last launch uses the other scratch set
+            for k in range(last + 1):
+                ctx.eval_batch(ins[k], *outs[k], async_=True, flags=OVERLAP_OK)
+            ctx.sync()
+            assert ctx.argmin() == ref[last][3]
     waits, timeouts = ctx.guard_stats()
     assert timeouts == 0
     # objective-only launches take the same path
