@@ -182,6 +182,63 @@ def build_predictor(prob: OEDProblem):
     return predictor
 
 
+@dataclass
+class IntervalSolution:
+    """One merged-grid interval of `continuous_predict`: the stand-in for the `ODESolution` the reference
+    returns per interval (/root/reference/src/utilities.jl:11-15).  ``t`` [k+1] are the integrator's own
+    step points of the interval (both ends included, like `sol.t`), ``u`` [n_aug, k+1] the augmented state
+    ``[x; vec(G); F_triu]`` there (like `sol[:, :]`)."""
+    t: np.ndarray
+    u: np.ndarray
+
+    def __getitem__(self, key):
+        return self.u[key]
+
+    def __len__(self):
+        return len(self.t)
+
+
+def _dense_context(prob: OEDProblem):
+    """A second evaluator whose OUTPUT grid is the integrator's step grid: every step of the original
+    problem becomes a merged interval of its own (one step each, same step sizes, each variable keeps the
+    value of the interval the step came from), so `dynoed_trajectory` returns the state after every step.
+    With equal substeps the step size is the same single constant as in the original problem and the
+    integration is bit-identical."""
+    if getattr(prob, "_dense", None) is None:
+        tp = np.asarray(prob.timegrid.tpoints, dtype=np.float64)
+        N = len(tp) - 1
+        edges = getattr(prob.alg, "edges", None)
+        rel = [np.asarray(e, dtype=np.float64) for e in edges] if edges is not None else \
+            [np.arange(prob.alg.substeps + 1, dtype=np.float64) / prob.alg.substeps] * N
+        t_dense, owner = [tp[0]], []
+        for j in range(N):
+            L = tp[j + 1] - tp[j]
+            for k in range(1, len(rel[j])):
+                t_dense.append(tp[j + 1] if k == len(rel[j]) - 1 else tp[j] + rel[j][k] * L)
+                owner.append(j)
+        ind = np.asarray(prob.timegrid.indicators - 1)[:, owner]
+        libpath, name, info = _resolve_model(prob.system)
+        lay = prob.layout
+        ctx = runtime.Context(
+            name, criterion=prob.objective.id, method=prob.alg.method, tgrid=np.asarray(t_dense),
+            indicators=ind, ctrl_offsets=lay.control_offsets, w_offsets=lay.w_offsets,
+            ic_offset=lay.ic_offset, tau_offset=lay.tau_offset, n_var=lay.n_var, substeps=1,
+            theta=info["theta"], x0=info["x0"], G0=info["G0"], device=prob.device, library_path=libpath)
+        counts = [len(r) - 1 for r in rel]
+        prob._dense = (ctx, np.asarray(t_dense), np.concatenate([[0], np.cumsum(counts)]))
+    return prob._dense
+
+
+def continuous_predict(prob: OEDProblem, result) -> list:
+    """utilities.jl:1-17: the solution on every merged interval, restarted from the end of the previous one
+    — here: the state after every integrator step of the GPU evaluation, one `IntervalSolution` per merged
+    interval (its first column is the previous interval's last)."""
+    ctx, t_dense, first = _dense_context(prob)
+    X = ctx.trajectory(np.asarray(getattr(result, "data", result), dtype=np.float64))[0].T   # [n_aug, n_steps+1]
+    return [IntervalSolution(t_dense[first[j]:first[j + 1] + 1].copy(), X[:, first[j]:first[j + 1] + 1].copy())
+            for j in range(len(first) - 1)]
+
+
 # --- constraints (ModelingToolkit.ConstraintsSystem stand-in) -----------------------------------
 @dataclass
 class Constraint:

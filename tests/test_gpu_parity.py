@@ -110,6 +110,40 @@ def test_log_det_criterion_extension(name, oracles, built_library):
     assert np.allclose(D.LogDCriterion().gradient(M, 0.5), -np.linalg.inv(M + 0.5 * np.eye(4)), rtol=1e-10)
 
 
+def test_continuous_predict_returns_the_state_after_every_step(built_library):
+    """utilities.jl:1-17 (`continuous_predict`): one solution per merged interval.  Here: the state after
+    every integrator step.  At the grid points it must be BIT-identical to `build_predictor` (same single
+    step size), between them it is the same scheme's intermediate state: checked against the closed form of
+    the 1-D system (x = exp(p t), G = t exp(p t), test/references/1D.jl:14-24) and, for a graded Rosenbrock
+    grid, against the grid-point trajectory to rounding."""
+    prob = D.OEDProblem(D.OEDSystem(models.lotka_volterra_fishing()), D.FisherDCriterion(), alg=D.RK4(4))
+    des = random_designs("lv_fishing", 71, 1, 3)[0]
+    sols = D.continuous_predict(prob, des)
+    X, t = D.build_predictor(prob)(des)
+    assert len(sols) == 30 and all(len(s_) == 5 and s_.u.shape == (9, 5) for s_ in sols)
+    for j, s_ in enumerate(sols):
+        assert s_.t[0] == t[j] and s_.t[-1] == t[j + 1] and np.all(np.diff(s_.t) > 0)
+        assert np.array_equal(s_.u[:, 0], X[:, j]) and np.array_equal(s_.u[:, -1], X[:, j + 1])
+        if j:
+            assert np.array_equal(s_.u[:, 0], sols[j - 1].u[:, -1])
+    p1 = D.OEDProblem(D.OEDSystem(models.one_d()), D.FisherACriterion(), alg=D.Tsit5(8))
+    w = np.array([0, 0, 0, 1, 1, 1, 1, 0, 0, 0, 1.0])
+    th = p1.context().info
+    for s_ in D.continuous_predict(p1, w):
+        lam = np.log(s_.u[0, -1] / s_.u[0, 0]) / (s_.t[-1] - s_.t[0])          # x' = p x: recover p from the data
+        assert np.allclose(s_.u[0], s_.u[0, 0] * np.exp(lam * (s_.t - s_.t[0])), rtol=1e-9)
+        assert np.allclose(s_.u[1], s_.t * s_.u[0], rtol=1e-8, atol=1e-12)      # G = t x
+        assert np.all(np.diff(s_.u[2]) >= 0)                                    # F' = w G^2 >= 0
+    edges = D.graded_edges(10, 12, 1e-6, 3)
+    pr = D.OEDProblem(D.OEDSystem(models.robertson()), D.DCriterion(), alg=D.ROS3P(edges=edges))
+    dr = stiff_designs("robertson", pr.context().n_var, 1, 5)[0]
+    sr = D.continuous_predict(pr, dr)
+    Xr, tr_ = D.build_predictor(pr)(dr)
+    assert [len(s_) - 1 for s_ in sr] == [len(e) - 1 for e in edges]
+    for j, s_ in enumerate(sr):
+        assert rel(s_.u[:, -1], Xr[:, j + 1]) < 1e-11
+
+
 def test_ragged_and_empty_batches(oracles, built_library):
     ctx = make_problem("lv_fishing", D.DCriterion).context()
     orc = oracles("lv_fishing", 4, "rk4", 4)
