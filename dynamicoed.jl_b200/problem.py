@@ -202,8 +202,8 @@ def _dense_context(prob: OEDProblem):
     """A second evaluator whose OUTPUT grid is the integrator's step grid: every step of the original
     problem becomes a merged interval of its own (one step each, same step sizes, each variable keeps the
     value of the interval the step came from), so `dynoed_trajectory` returns the state after every step.
-    With equal substeps the step size is the same single constant as in the original problem and the
-    integration is bit-identical."""
+    With equal substeps the step size is the same single constant as in the original problem: x and G are
+    bit-identical at the grid points, F agrees to rounding (its quadrature is folded once per interval)."""
     if getattr(prob, "_dense", None) is None:
         tp = np.asarray(prob.timegrid.tpoints, dtype=np.float64)
         N = len(tp) - 1

@@ -112,8 +112,8 @@ def test_log_det_criterion_extension(name, oracles, built_library):
 
 def test_continuous_predict_returns_the_state_after_every_step(built_library):
     """utilities.jl:1-17 (`continuous_predict`): one solution per merged interval.  Here: the state after
-    every integrator step.  At the grid points it must be BIT-identical to `build_predictor` (same single
-    step size), between them it is the same scheme's intermediate state: checked against the closed form of
+    every integrator step.  At the grid points x and G must be BIT-identical to `build_predictor` (same single
+    step size; F agrees to rounding), between them it is the same scheme's intermediate state: checked against the closed form of
     the 1-D system (x = exp(p t), G = t exp(p t), test/references/1D.jl:14-24) and, for a graded Rosenbrock
     grid, against the grid-point trajectory to rounding."""
     prob = D.OEDProblem(D.OEDSystem(models.lotka_volterra_fishing()), D.FisherDCriterion(), alg=D.RK4(4))
@@ -123,7 +123,10 @@ def test_continuous_predict_returns_the_state_after_every_step(built_library):
     assert len(sols) == 30 and all(len(s_) == 5 and s_.u.shape == (9, 5) for s_ in sols)
     for j, s_ in enumerate(sols):
         assert s_.t[0] == t[j] and s_.t[-1] == t[j + 1] and np.all(np.diff(s_.t) > 0)
-        assert np.array_equal(s_.u[:, 0], X[:, j]) and np.array_equal(s_.u[:, -1], X[:, j + 1])
+        # x and G: the same steps with the same single step size -> bit-identical; F: the quadrature is folded
+        # once per (now shorter) interval -> equal to rounding
+        assert np.array_equal(s_.u[:6, 0], X[:6, j]) and np.array_equal(s_.u[:6, -1], X[:6, j + 1])
+        assert np.allclose(s_.u[6:, -1], X[6:, j + 1], rtol=1e-13, atol=1e-300)
         if j:
             assert np.array_equal(s_.u[:, 0], sols[j - 1].u[:, -1])
     p1 = D.OEDProblem(D.OEDSystem(models.one_d()), D.FisherACriterion(), alg=D.Tsit5(8))
