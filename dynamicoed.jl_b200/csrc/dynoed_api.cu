@@ -392,6 +392,7 @@ struct dynoed_ctx {
     int* d_first_step = nullptr;
     double* d_step_t = nullptr;
     double* d_step_h = nullptr;
+    double* d_step_ih = nullptr;
     int* d_indicators = nullptr;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -689,10 +690,17 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     CUC(cudaMalloc(&ctx->d_step_h, sizeof(double) * (st.size() + 1)));
     CUC(cudaMemset(ctx->d_step_t, 0, sizeof(double) * (st.size() + 1)));
     CUC(cudaMemset(ctx->d_step_h, 0, sizeof(double) * (st.size() + 1)));
+    CUC(cudaMalloc(&ctx->d_step_ih, sizeof(double) * (st.size() + 1)));
+    CUC(cudaMemset(ctx->d_step_ih, 0, sizeof(double) * (st.size() + 1)));
     CUC(cudaMalloc(&ctx->d_indicators, sizeof(int) * nvars * N));
     CUC(cudaMemcpy(ctx->d_first_step, first.data(), sizeof(int) * (N + 1), cudaMemcpyHostToDevice));
     CUC(cudaMemcpy(ctx->d_step_t, st.data(), sizeof(double) * st.size(), cudaMemcpyHostToDevice));
     CUC(cudaMemcpy(ctx->d_step_h, sh.data(), sizeof(double) * st.size(), cudaMemcpyHostToDevice));
+    {
+        std::vector<double> sih(sh.size());
+        for (size_t k = 0; k < sh.size(); ++k) sih[k] = 1.0 / sh[k];
+        CUC(cudaMemcpy(ctx->d_step_ih, sih.data(), sizeof(double) * sih.size(), cudaMemcpyHostToDevice));
+    }
     CUC(cudaMemcpy(ctx->d_indicators, d->indicators, sizeof(int) * nvars * N, cudaMemcpyHostToDevice));
     CUC(cudaMalloc(&ctx->d_best, 4 * sizeof(long long)));
     CUC(cudaMalloc(&ctx->d_ring, 2 * kRing * sizeof(long long)));
@@ -728,6 +736,7 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     P.first_step = ctx->d_first_step;
     P.step_t = ctx->d_step_t;
     P.step_h = ctx->d_step_h;
+    P.step_ih = ctx->d_step_ih;
     P.indicators = ctx->d_indicators;
     for (int k = 0; k < mi.n_ctrl; ++k) { P.ctrl_off[k] = d->ctrl_offsets[k]; P.ctrl_len[k] = len[k]; P.n_ctrl_values += len[k]; }
     for (int k = 0; k < mi.n_obs; ++k) P.w_off[k] = d->w_offsets[k];
@@ -779,7 +788,7 @@ void dynoed_destroy(dynoed_ctx* ctx) {
         cudaFreeHost(s.h_designs); cudaFreeHost(s.h_crit); cudaFreeHost(s.h_grad); cudaFreeHost(s.h_fim);
         if (s.done) cudaEventDestroy(s.done);
     }
-    cudaFree(ctx->d_first_step); cudaFree(ctx->d_step_t); cudaFree(ctx->d_step_h); cudaFree(ctx->d_indicators);
+    cudaFree(ctx->d_first_step); cudaFree(ctx->d_step_t); cudaFree(ctx->d_step_h); cudaFree(ctx->d_step_ih); cudaFree(ctx->d_indicators);
     for (int q = 0; q < 2; ++q) { cudaFree(ctx->traj[q]); cudaFree(ctx->part_val[q]); cudaFree(ctx->part_idx[q]); if (ctx->call_done[q]) cudaEventDestroy(ctx->call_done[q]); }
     cudaFree(ctx->d_best); cudaFree(ctx->d_ring); cudaFree(ctx->d_ticket); cudaFree(ctx->d_guard);
     if (ctx->ev_aux) cudaEventDestroy(ctx->ev_aux);

@@ -65,6 +65,7 @@ struct EvalParams {
     const int* __restrict__ first_step;   // [N+1]
     const double* __restrict__ step_t;    // [n_steps]
     const double* __restrict__ step_h;    // [n_steps]
+    const double* __restrict__ step_ih;   // [n_steps] 1 / h (Rosenbrock steps: no per-step divisions on the device)
     const int* __restrict__ indicators;   // [NCTRL+NOBS][N], 0-based index into the variable's own grid
     // layout
     int ctrl_off[kMaxCtrl];

@@ -319,11 +319,12 @@ struct StepSolver<M, Dual<K>> {
 // One Rosenbrock step on y = [z (x, G); Pq (unweighted quadratures)]
 // ----------------------------------------------------------------------------------------------
 template <class M, class RT, class T>
-__device__ __forceinline__ void rosenbrock_step(double t, double h, T (&z)[M::NZ], T (&Pq)[M::NOBS * M::NF],
+__device__ __forceinline__ void rosenbrock_step(double t, double h, double ih, T (&z)[M::NZ], T (&Pq)[M::NOBS * M::NF],
                                                 const T* u, const double* th, const T* c) {
     constexpr int S = RT::S, NX = M::NX, NP = M::NP, NZ = M::NZ, NQ = M::NOBS * M::NF;
-    const double c0 = 1.0 / (h * RT::gamma);
-    const double ih = 1.0 / h;
+    // ih = 1 / h comes from the host's step table: two FP64 divisions per step less (for a 2-state model like
+    // Robertson they were ~15 % of the step's instructions)
+    const double c0 = ih * (1.0 / RT::gamma);
     StepSolver<M, T> lu;
     lu.init(t, c0, z, u, th, c);
     T Uz[S][NZ], Uq[S][NQ];
@@ -404,9 +405,9 @@ template <class RT>
 struct RosenbrockStepper {
     static constexpr int STAGES = RT::S;
     template <class M, class T>
-    __device__ __forceinline__ static void step(double t, double h, T (&z)[M::NZ], T (&Pq)[M::NOBS * M::NF],
+    __device__ __forceinline__ static void step(double t, double h, double ih, T (&z)[M::NZ], T (&Pq)[M::NOBS * M::NF],
                                                 const T* u, const double* th, const T* c) {
-        rosenbrock_step<M, RT, T>(t, h, z, Pq, u, th, c);
+        rosenbrock_step<M, RT, T>(t, h, ih, z, Pq, u, th, c);
     }
 };
 
@@ -414,7 +415,7 @@ template <class Tab>
 struct ExplicitStepper {
     static constexpr int STAGES = Tab::S;
     template <class M, class T>
-    __device__ __forceinline__ static void step(double t, double h, T (&z)[M::NZ], T (&Pq)[M::NOBS * M::NF],
+    __device__ __forceinline__ static void step(double t, double h, double /*ih*/, T (&z)[M::NZ], T (&Pq)[M::NOBS * M::NF],
                                                 const T* u, const double* th, const T* c) {
         constexpr int S = Tab::S, NZ = M::NZ, NQ = M::NOBS * M::NF;
         T k[S][NZ], zacc[NZ];
@@ -569,7 +570,7 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams 
                     for (int a = 0; a < NQ; ++a) Pq[a] = T(0.0);
                     const int s0 = __ldg(P.first_step + j), s1 = __ldg(P.first_step + j + 1);
                     for (int s = s0; s < s1; ++s)
-                        Stepper::template step<M, T>(__ldg(P.step_t + s), __ldg(P.step_h + s), z, Pq, u, th, c);
+                        Stepper::template step<M, T>(__ldg(P.step_t + s), __ldg(P.step_h + s), __ldg(P.step_ih + s), z, Pq, u, th, c);
 #pragma unroll
                     for (int i = 0; i < NOBS; ++i)
 #pragma unroll
@@ -813,13 +814,12 @@ struct Ic2Column {
 };
 
 template <class M, class RT>
-__device__ __forceinline__ void rosenbrock_ic_step(double t, double h, double (&z)[M::NZ], double (&Pq)[M::NOBS * M::NF],
+__device__ __forceinline__ void rosenbrock_ic_step(double t, double h, double ih, double (&z)[M::NZ], double (&Pq)[M::NOBS * M::NF],
                                                    double (&dP)[M::NOBS * M::NF * M::NIC], double* __restrict__ sm,
                                                    const double* u, const double* th, const double* c) {
     constexpr int S = RT::S, NX = M::NX, NP = M::NP, NZ = M::NZ, NQ = M::NOBS * M::NF, NQ2 = NQ * M::NIC;
     using Lay = Ic2Layout<M, RT>;
-    const double c0 = 1.0 / (h * RT::gamma);
-    const double ih = 1.0 / h;
+    const double c0 = ih * (1.0 / RT::gamma);
     const double ic0 = h * RT::gamma;
     volatile double* Us = sm + (size_t)Lay::U * kMaxTile;
     StepSolver<M, double> lu;
@@ -1008,7 +1008,7 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_ic_kernel(const EvalParams P)
                 for (int a = 0; a < NQ2; ++a) dP[a] = 0.0;
                 const int s0 = __ldg(P.first_step + j), s1 = __ldg(P.first_step + j + 1);
                 for (int s = s0; s < s1; ++s)
-                    rosenbrock_ic_step<M, RT>(__ldg(P.step_t + s), __ldg(P.step_h + s), z, Pq, dP, sm, u, th, c);
+                    rosenbrock_ic_step<M, RT>(__ldg(P.step_t + s), __ldg(P.step_h + s), __ldg(P.step_ih + s), z, Pq, dP, sm, u, th, c);
 #pragma unroll
                 for (int i = 0; i < NOBS; ++i)
 #pragma unroll
@@ -1184,7 +1184,7 @@ __global__ void __launch_bounds__(32, 1) dir_eval_kernel(const EvalParams P) {
         double* pq = P.tile > 0 ? dir_rows + (size_t)P.tile * n_var + (size_t)(g - d_first) * N * NQ
                                 : P.traj + (size_t)g * N * NQ;
         int s_cur = fst[0];
-        double t_next = __ldg(P.step_t + s_cur), h_next = __ldg(P.step_h + s_cur);
+        double t_next = __ldg(P.step_t + s_cur), h_next = __ldg(P.step_h + s_cur), ih_next = __ldg(P.step_ih + s_cur);
         for (int j = 0; j < N; ++j) {
             T u[NCU], c[M::NCONST];
             double w[NOBS];
@@ -1204,9 +1204,10 @@ __global__ void __launch_bounds__(32, 1) dir_eval_kernel(const EvalParams P) {
             // are fetched before the current step's arithmetic (the step tables are padded by one entry)
             const int s1 = fst[j + 1];
             for (; s_cur < s1; ++s_cur) {
-                const double t_now = t_next, h_now = h_next;
+                const double t_now = t_next, h_now = h_next, ih_now = ih_next;
                 t_next = __ldg(P.step_t + s_cur + 1); h_next = __ldg(P.step_h + s_cur + 1);
-                Stepper::template step<M, T>(t_now, h_now, z, Pq, u, th, c);
+                ih_next = __ldg(P.step_ih + s_cur + 1);
+                Stepper::template step<M, T>(t_now, h_now, ih_now, z, Pq, u, th, c);
             }
 #pragma unroll
             for (int i = 0; i < NOBS; ++i)
