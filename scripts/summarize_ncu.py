@@ -40,6 +40,10 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 def export(tag, page):
     rep = os.path.join(G, f"prof_{tag}.ncu-rep")
     out = os.path.join(G, f"prof_{tag}_{page}.csv")
+    # the CSV pages may have been exported on the GPU box already (reports of several captures exceed gpurun's
+    # 64 MiB return limit): then the .ncu-rep is not needed here
+    if os.path.exists(out) and not os.path.exists(rep):
+        return out
     if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(rep):
         with open(out, "w") as fh:
             subprocess.run(["ncu", "-i", rep, "--page", page, "--csv"], stdout=fh,
