@@ -1089,13 +1089,17 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
     };
     double* crit_map = mapped(crit);
     double* fim_map = mapped(fim);
+    // gradient tiles stored by the kernel's TMA bulk store straight into page-locked host memory (no D2H copy
+    // stage in the pipeline): opt-in, DYNOED_ZC_GRAD=1 (measurement switch)
+    static const bool zc_grad_on = getenv("DYNOED_ZC_GRAD") && atoi(getenv("DYNOED_ZC_GRAD")) != 0;
+    double* grad_map = (g && zc_grad_on) ? mapped(grad) : nullptr;
     // Pageable caller arrays: the driver would stage them through a small bounce buffer at a few
     // GB/s.  Instead every chunk goes through page-locked staging owned by its slot, filled and
     // drained by multi-threaded memcpy while the other slots' copies and kernels are in flight.
     const bool staged = ctx->host_staging &&
                         (is_pageable(designs) || is_pageable(crit) || is_pageable(grad) || is_pageable(fim));
     if (staged) {
-        crit_map = fim_map = nullptr;
+        crit_map = fim_map = grad_map = nullptr;
         for (int k = 0; k < kSlots && k < nchunks; ++k) {
             rc = ensure_staging(ctx, ctx->slots[k], chunk);
             if (rc) return rc;
@@ -1167,7 +1171,7 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
                 CU(cudaMemcpyAsync(s.d_designs, h_src, sizeof(double) * cnt * ctx->n_var, cudaMemcpyHostToDevice, s.stream));
             EvalParams P = ctx->base;
             const int grid = grid_for(ctx, cnt, kidx);
-            P.designs = s.d_designs; P.crit = crit_map ? crit_map + off : s.d_crit; P.grad = g ? s.d_grad : nullptr;
+            P.designs = s.d_designs; P.crit = crit_map ? crit_map + off : s.d_crit; P.grad = !g ? nullptr : grad_map ? grad_map + off * ctx->n_var : s.d_grad;
             P.fim = !fim ? nullptr : fim_map ? fim_map + off * nF : s.d_fim;
             if (small_zc) {   // the kernel reads the rows from, and stores every result into, page-locked host memory
                 P.designs = zc_in; P.crit = zc_crit; P.grad = zc_grad; P.fim = fim ? zc_fim : nullptr;
@@ -1190,7 +1194,7 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
             double* o_grad = staged ? s.h_grad : (g ? grad + off * ctx->n_var : nullptr);
             double* o_fim = staged ? s.h_fim : (fim ? fim + off * nF : nullptr);
             if (!crit_map && !small_zc) CU(cudaMemcpyAsync(o_crit, s.d_crit, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s.stream));
-            if (g && !small_zc) CU(cudaMemcpyAsync(o_grad, s.d_grad, sizeof(double) * cnt * ctx->n_var, cudaMemcpyDeviceToHost, s.stream));
+            if (g && !small_zc && !grad_map) CU(cudaMemcpyAsync(o_grad, s.d_grad, sizeof(double) * cnt * ctx->n_var, cudaMemcpyDeviceToHost, s.stream));
             if (fim && !fim_map && !small_zc) CU(cudaMemcpyAsync(o_fim, s.d_fim, sizeof(double) * cnt * nF, cudaMemcpyDeviceToHost, s.stream));
             if (staged) CU(cudaEventRecord(s.done, s.stream));
         }
