@@ -382,12 +382,21 @@ def emit_model(name: str, s: SimplifiedOEDSystem) -> tuple[str, dict]:
             assert rest == 0, "adjoint scalar must be linear in the adjoint symbols"
             out = out.xreplace(sub)
             # -p3 x kx0 - p3 W00 - ...  ->  -p3 (x kx0 + W00) - ... when that is cheaper
+            cands = []
             try:
-                col = sp.collect(sp.expand(out), [v for v in static if out.has(v)])
-                if count_flops(col) < count_flops(out):
-                    out = col
+                cands.append(sp.collect(sp.expand(out), [v for v in static if out.has(v)]))
             except Exception:
                 pass
+            try:
+                # (kb5 - kb2) z1 instead of kb5 z1 - kb2 z1: common STATE factors of the adjoint symbols
+                cands.append(sp.collect(sp.expand(out), [v for v in x if out.has(v)]))
+                cands.append(sp.collect(sp.collect(sp.expand(out), [v for v in x if out.has(v)]),
+                                        [v for v in static if out.has(v)]))
+            except Exception:
+                pass
+            for col in cands:
+                if count_flops(col) < count_flops(out):
+                    out = col
             return out
         for a in range(nx):
             b.out(f"zb[{a}]", collect_lin(grads[a]))

@@ -248,6 +248,31 @@ def test_full_size_properties(oracles, built_library):
     assert rel(c[idx], oc) < RTOL and rel(F[idx], oF) < RTOL and rel_rows(g[idx], og) < RTOL
 
 
+def test_one_call_at_multistart_size(built_library):
+    """BASELINE.json config 5 size in ONE device-path call (1,048,576 + 77 designs, a ragged last tile):
+    every row is the value the same design gets in a small batch (bit for bit: one design per lane, nothing
+    depends on its position in the batch), the arg-min is the global one (index beyond 2^20), NaN rows lose."""
+    import torch
+    n = (1 << 20) + 77
+    ctx = make_problem("lv_fishing", D.FisherDCriterion).context()
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(5)
+    d = torch.rand((n, 71), dtype=torch.float64, device="cuda", generator=gen)
+    d[:, -1] = 1e-3 + 0.99 * d[:, -1]
+    d[12345, 3] = float("nan")
+    c = torch.empty(n, dtype=torch.float64, device="cuda")
+    g = torch.empty_like(d)
+    F = torch.empty((n, 3), dtype=torch.float64, device="cuda")
+    ctx.eval_batch(d, c, g, F)
+    cc = torch.nan_to_num(c, nan=float("inf"))
+    i, v = ctx.argmin()
+    assert i == int(torch.argmin(cc)) and v == float(cc.min()) and bool(torch.isnan(c[12345]))
+    for lo, hi in ((0, 4096), (524288 - 2048, 524288 + 2048), (n - 4096 - 77, n)):     # large enough for the same kernel
+        cs, gs, Fs = ctx.evaluate(d[lo:hi].cpu().numpy())
+        assert np.array_equal(cs, c[lo:hi].cpu().numpy()) and np.array_equal(gs, g[lo:hi].cpu().numpy())
+        assert np.array_equal(Fs, F[lo:hi].cpu().numpy())
+
+
 def test_set_criterion_and_predictor(oracles, built_library):
     prob = make_problem("lv_fishing", D.FisherACriterion)
     ctx = prob.context()
