@@ -239,6 +239,36 @@ def continuous_predict(prob: OEDProblem, result) -> list:
             for j in range(len(first) - 1)]
 
 
+def extract_fisher(prob: OEDProblem, result) -> np.ndarray:
+    """utilities.jl:37-45: F(t_f) as a symmetric np x np matrix."""
+    from .criteria import _symmetric_from_vector
+    ctx = prob.context()
+    X = ctx.trajectory(np.asarray(getattr(result, "data", result), dtype=np.float64))[0]
+    return _symmetric_from_vector(X[-1, ctx.info.nz:])
+
+
+def compute_local_information_gain(Qs):
+    """utilities.jl:47-54: P_i(t_k) = Q_i(t_k)^T Q_i(t_k) for a list of n_obs x np matrices Q(t_k)."""
+    n_h = np.asarray(Qs[0]).shape[0]
+    return [[np.outer(np.asarray(Q)[i], np.asarray(Q)[i]) for Q in Qs] for i in range(n_h)]
+
+
+def compute_information_gain(prob: OEDProblem, result, dense: bool = False):
+    """utilities.jl:56-70: ``(F, Ps, Πs, np, sols)`` with ``Ps[i][k] = Q_i(t_k)^T Q_i(t_k)`` and
+    ``Πs[i][k] = F^-1 Ps[i][k] F^-1`` (local / global information gain of observable i).  The time points are
+    the merged-grid points, or with ``dense=True`` the integrator's step points (what the reference's saved
+    solution points are for a fixed-step run); all of it computed by `dynoed_information_gain` on the GPU."""
+    from .criteria import _symmetric_from_vector
+    des = np.asarray(getattr(result, "data", result), dtype=np.float64)
+    ctx = _dense_context(prob)[0] if dense else prob.context()
+    F, P, Pi = ctx.information_gain(des)
+    n_obs = ctx.info.n_obs
+    Ps = [[P[0, k, i] for k in range(P.shape[1])] for i in range(n_obs)]
+    Pis = [[Pi[0, k, i] for k in range(Pi.shape[1])] for i in range(n_obs)]
+    sols = continuous_predict(prob, des) if dense else None
+    return _symmetric_from_vector(F[0]), Ps, Pis, ctx.info.np, sols
+
+
 # --- constraints (ModelingToolkit.ConstraintsSystem stand-in) -----------------------------------
 @dataclass
 class Constraint:

@@ -707,6 +707,29 @@ def test_information_gain_matches_oracle(name, oracles, built_library):
                 assert np.max(np.abs(Pi[d, j, i] - Piref)) <= 1e-8 * max(np.max(np.abs(Piref)), 1e-300)
 
 
+def test_information_gain_host_mirrors(built_library):
+    """The reference's names for the analysis helpers (/root/reference/src/utilities.jl:37-70) on top of the GPU
+    calls: `extract_fisher`, `compute_local_information_gain`, `compute_information_gain` at the grid points and
+    at every integrator step (`dense=True`); the dense result contains the grid-point result."""
+    prob = D.OEDProblem(D.OEDSystem(models.lotka_volterra_fishing()), D.FisherACriterion(), alg=D.RK4(4))
+    des = random_designs("lv_fishing", 71, 1, 41)[0]
+    F, Ps, Pis, np_, sols = D.compute_information_gain(prob, des)
+    assert np_ == 2 and sols is None and len(Ps) == 2 and len(Ps[0]) == 31 and Ps[0][0].shape == (2, 2)
+    assert np.array_equal(F, D.extract_fisher(prob, des)) and np.allclose(F, F.T)
+    Fi = np.linalg.inv(F)
+    for i in range(2):
+        for k in (0, 7, 30):
+            assert np.allclose(Pis[i][k], Fi @ Ps[i][k] @ Fi, rtol=1e-9, atol=1e-300)
+            assert np.linalg.matrix_rank(Ps[i][k], tol=1e-12 * max(np.abs(Ps[i][k]).max(), 1e-300)) <= 1   # Q_i^T Q_i
+    X, _ = D.build_predictor(prob)(des)
+    Q = [np.array([[X[2, k], X[4, k]], [X[3, k], X[5, k]]]) for k in range(31)]      # h = (x, y): Q = G
+    loc = D.compute_local_information_gain(Q)
+    assert all(np.allclose(loc[i][k], Ps[i][k], rtol=1e-12, atol=1e-300) for i in range(2) for k in range(31))
+    Fd, Pd, Pid, _, sd = D.compute_information_gain(prob, des, dense=True)
+    assert len(Pd[0]) == 121 and len(sd) == 30 and np.allclose(Fd, F, rtol=1e-13)
+    assert all(np.allclose(Pd[i][4 * k], Ps[i][k], rtol=1e-12, atol=1e-300) for i in range(2) for k in range(31))
+
+
 def test_fixed_controls_shortcut_matches_full_evaluation(oracles, built_library):
     """Integer / branch-and-bound batch mode (problem.jl:137-146): with the controls frozen, F is
     linear in the weights, so F = designs x basis.  The shortcut must reproduce the full
