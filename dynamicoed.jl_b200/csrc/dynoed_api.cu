@@ -540,7 +540,8 @@ static size_t smem_bytes(const dynoed_ctx* ctx, int kidx = 0) {
     if (kidx == 1 && ctx->ic2) {
         const auto& mi = ctx->model->info;
         const size_t slots = (size_t)ctx->stages * mi.nz + (size_t)ctx->model->nh * mi.nx;
-        need = 128 + ((((size_t)ctx->tile * ctx->n_var + 15) & ~(size_t)15) + slots * kMaxTile) * sizeof(double);
+        const size_t stride = ctx->stages >= 4 ? 64 : kMaxTile;      // ic_stride<RT>()
+        need = 128 + ((((size_t)ctx->tile * ctx->n_var + 15) & ~(size_t)15) + slots * stride) * sizeof(double);
     }
     return std::max(ctx->smem_floor, need);
 }
@@ -594,6 +595,10 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     int tile = d->tile ? d->tile : 128;
     if (!d->tile)
         while (tile > 32 && 128 + (size_t)tile * d->n_var * sizeof(double) > (size_t)227 * 1024) tile -= 32;
+    // four-stage Rosenbrock gradient with unknown initial conditions: 64-lane CTAs (ic_stride, dynoed_rosenbrock.cuh)
+    const bool ic2_four_stage = d->method == DYNOED_RODAS3 && mi.n_ic > 0 && mi.n_ctrl == 0 && m->ic2_ok &&
+                                !getenv("DYNOED_NO_IC2");
+    if (!d->tile && ic2_four_stage) tile = std::min(tile, 64);
     if (tile % 32 != 0 || tile < 32 || tile > kMaxTile) return fail(nullptr, DYNOED_EINVAL, "tile must be 32..128, multiple of 32");
     const int nvars = mi.n_ctrl + mi.n_obs;
     // per-variable block lengths from the indicators; all indices must be valid
@@ -759,6 +764,7 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
     // Rosenbrock gradient with unknown initial conditions and no controls: second-order sensitivity kernel,
     // unless its per-lane shared-memory columns do not fit (then: forward-mode duals, ros_eval_kernel)
     ctx->ic2 = rosenbrock && mi.n_ic > 0 && mi.n_ctrl == 0 && m->ic2_ok && !getenv("DYNOED_NO_IC2");
+    if (ctx->ic2 && ctx->stages >= 4 && ctx->tile > 64) ctx->ic2 = false;     // caller-forced tile above the slot stride
     if (ctx->ic2 && smem_bytes(ctx, 1) > (size_t)prop.sharedMemPerBlockOptin) ctx->ic2 = false;
     // the kernel takes d x / d ic_a from G column ic2_gcol(a): only valid while that column starts as the
     // unit vector of the state (a caller-supplied G0 may say otherwise)

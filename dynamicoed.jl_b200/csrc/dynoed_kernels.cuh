@@ -600,8 +600,9 @@ __device__ __forceinline__ void rk_adjoint_step(double t, const double* __restri
 // win the set first; every launch's own results would still be right, but the set's result slot
 // (dynoed_argmin) would finally hold the older batch.  This cannot deadlock: a dependent grid starts
 // only after every CTA of its predecessor has STARTED, so when CTAs of launch k+2 spin, all CTAs of
-// launch k are already resident or done.  A wait that exceeds 2 s (a lost release after a failed call)
-// is counted in guard[2] and abandoned instead of hanging the device.
+// launch k are already resident or done.  A wait that exceeds 20 s (far beyond any launch: 1 M LV designs
+// take 4 ms; a lost release after a failed call) is counted in guard[2] and abandoned instead of hanging
+// the device.
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
@@ -621,7 +622,7 @@ __device__ __forceinline__ void scratch_acquire(const EvalParams& P) {
             while (true) {
                 __nanosleep(200);
                 if (ld_acquire_u64(P.guard) >= P.serial) break;
-                if (global_ns() - t0 > 2000000000ULL) { atomicAdd(P.guard + 2, 1ULL); break; }
+                if (global_ns() - t0 > 20000000000ULL) { atomicAdd(P.guard + 2, 1ULL); break; }
             }
         }
         __threadfence();

@@ -706,6 +706,12 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams 
 // Shared memory per lane: (S + NH/NP... ) see Ic2Layout; each lane touches only its own slots, so the
 // phases need no barrier.
 // ----------------------------------------------------------------------------------------------
+// Lane stride of the shared-memory slots = lanes per CTA of this kernel.  Four-stage tableaus (RODAS3) need
+// S NZ + NH NX slots per lane (chem6: 90 doubles = 92 KB at 128 lanes, one CTA per SM); with 64-lane CTAs
+// three or four fit.  The host picks the matching tile (dynoed_create).
+template <class RT>
+__host__ __device__ constexpr int ic_stride() { return RT::S >= 4 ? 64 : kMaxTile; }
+
 template <class M, class RT>
 struct Ic2Layout {
     static constexpr int S = RT::S;
@@ -726,15 +732,15 @@ struct StageZ {                       // Z_s[k] = y_n[k] + sum_j a_sj U_j[k]
         double v = z[k];
 #pragma unroll
         for (int j = 0; j < RT::S; ++j)
-            if (j < s && RT::a(s, j) != 0.0) v = fma(RT::a(s, j), U[(size_t)(j * NZ + k) * kMaxTile], v);
+            if (j < s && RT::a(s, j) != 0.0) v = fma(RT::a(s, j), U[(size_t)(j * NZ + k) * ic_stride<RT>()], v);
         return v;
     }
 };
-template <int NZ>
+template <class RT, int NZ>
 struct StageU {
     const volatile double* U;
     int s;
-    __device__ __forceinline__ double operator[](int k) const { return U[(size_t)(s * NZ + k) * kMaxTile]; }
+    __device__ __forceinline__ double operator[](int k) const { return U[(size_t)(s * NZ + k) * ic_stride<RT>()]; }
 };
 
 template <class M, class RT, int Q>
@@ -745,15 +751,15 @@ struct Ic2Column {
         constexpr int S = RT::S, NX = M::NX, NZ = M::NZ, NQ2 = M::NOBS * M::NF * M::NIC;
         constexpr unsigned long long rows = M::ic2_qrows(Q);
         using Lay = Ic2Layout<M, RT>;
-        const volatile double* Us = sm + (size_t)Lay::U * kMaxTile;
-        volatile double* Hs = sm + (size_t)(Lay::HN + Q * NX) * kMaxTile;
+        const volatile double* Us = sm + (size_t)Lay::U * ic_stride<RT>();
+        volatile double* Hs = sm + (size_t)(Lay::HN + Q * NX) * ic_stride<RT>();
         double Hn[NX], UH[S][NX], Ud[S][NQ2];
 #pragma unroll
-        for (int i = 0; i < NX; ++i) Hn[i] = Hs[(size_t)i * kMaxTile];
+        for (int i = 0; i < NX; ++i) Hn[i] = Hs[(size_t)i * ic_stride<RT>()];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             const StageZ<RT, NZ> zs{z, Us, s};
-            const StageU<NZ> us{Us, s};
+            const StageU<RT, NZ> us{Us, s};
             double ZH[NX], r[NX], b[NX];
 #pragma unroll
             for (int i = 0; i < NX; ++i) {
@@ -799,7 +805,7 @@ struct Ic2Column {
 #pragma unroll
             for (int s = 0; s < S; ++s)
                 if (RT::m(s) != 0.0) v = fma(RT::m(s), UH[s][i], v);
-            Hs[(size_t)i * kMaxTile] = v;
+            Hs[(size_t)i * ic_stride<RT>()] = v;
         }
 #pragma unroll
         for (int a = 0; a < NQ2; ++a) {
@@ -821,7 +827,7 @@ __device__ __forceinline__ void rosenbrock_ic_step(double t, double h, double ih
     using Lay = Ic2Layout<M, RT>;
     const double c0 = ih * (1.0 / RT::gamma);
     const double ic0 = h * RT::gamma;
-    volatile double* Us = sm + (size_t)Lay::U * kMaxTile;
+    volatile double* Us = sm + (size_t)Lay::U * ic_stride<RT>();
     StepSolver<M, double> lu;
     lu.init(t, c0, z, u, th, c);
     // ---- phase 1: (x, G, P) ----
@@ -846,7 +852,7 @@ __device__ __forceinline__ void rosenbrock_ic_step(double t, double h, double ih
             if (RT::c(s, j) != 0.0) {
                 const double cj = RT::c(s, j) * ih;
 #pragma unroll
-                for (int a = 0; a < NZ; ++a) rz[a] = fma(cj, Us[(size_t)(j * NZ + a) * kMaxTile], rz[a]);
+                for (int a = 0; a < NZ; ++a) rz[a] = fma(cj, Us[(size_t)(j * NZ + a) * ic_stride<RT>()], rz[a]);
 #pragma unroll
                 for (int a = 0; a < NQ; ++a) rq[a] = fma(cj, Uq[j][a], rq[a]);
             }
@@ -876,7 +882,7 @@ __device__ __forceinline__ void rosenbrock_ic_step(double t, double h, double ih
 #pragma unroll
         for (int a = 0; a < NQ; ++a) Uq[s][a] = (rq[a] + dPU[a]) * ic0;
 #pragma unroll
-        for (int a = 0; a < NZ; ++a) Us[(size_t)(s * NZ + a) * kMaxTile] = Uc[a];
+        for (int a = 0; a < NZ; ++a) Us[(size_t)(s * NZ + a) * ic_stride<RT>()] = Uc[a];
     }
 #pragma unroll
     for (int s = 0; s < S; ++s) {
@@ -891,7 +897,7 @@ __device__ __forceinline__ void rosenbrock_ic_step(double t, double h, double ih
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             const StageZ<RT, NZ> zs{z, Us, s};
-            const StageU<NZ> us{Us, s};
+            const StageU<RT, NZ> us{Us, s};
             double rb[NQ2];
             M::ic2_qbase(t, zs, z, us, u, th, rb);
 #pragma unroll
@@ -921,7 +927,7 @@ __device__ __forceinline__ void rosenbrock_ic_step(double t, double h, double ih
         double v = z[a];
 #pragma unroll
         for (int s = 0; s < S; ++s)
-            if (RT::m(s) != 0.0) v = fma(RT::m(s), Us[(size_t)(s * NZ + a) * kMaxTile], v);
+            if (RT::m(s) != 0.0) v = fma(RT::m(s), Us[(size_t)(s * NZ + a) * ic_stride<RT>()], v);
         z[a] = v;
     }
 }
@@ -986,7 +992,7 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_ic_kernel(const EvalParams P)
 #pragma unroll
                 for (int k = 0; k < NF; ++k) Fd[a][k] = 0.0;
 #pragma unroll
-            for (int a = 0; a < M::NH * NX; ++a) sm[(size_t)(Lay::HN + a) * kMaxTile] = 0.0;   // G0 is constant
+            for (int a = 0; a < M::NH * NX; ++a) sm[(size_t)(Lay::HN + a) * ic_stride<RT>()] = 0.0;   // G0 is constant
             double* xg = P.xgrid ? P.xgrid + (size_t)g * (N + 1) * (NZ + NF) : nullptr;
             if (xg) {
 #pragma unroll

@@ -200,7 +200,7 @@ int dynoed_pack_winner(dynoed_ctx* ctx, int nbatches, const double* designs, con
 int dynoed_select_winner(dynoed_ctx* ctx, const double* d_gathered, int world, double* d_out);
 
 /* scratch-set guard counters (synchronises the device): CTAs that had to wait for a scratch set still
- * held by the launch two back, and waits abandoned after 2 s (must stay 0) */
+ * held by the launch two back, and waits abandoned after 20 s (must stay 0) */
 int dynoed_guard_stats(dynoed_ctx* ctx, int64_t* waits, int64_t* timeouts);
 
 /* the predictor p -> (X, t) of build_predictor (problem.jl:80-90) at the merged-grid points:
