@@ -233,7 +233,7 @@ def main():
     # in between stay back to back and overlap their tails exactly as at N=1.
     # The gather runs on a SIDE stream, ordered after the evaluation launches by an event (an event
     # record does not end the launches' overlap; a copy or kernel on the evaluation stream would).
-    GATHER = 16
+    GATHER = 32      # <= 64 (the library ring): one collective per 32 steps
     rec = torch.empty((GATHER, 2), dtype=torch.int64, device=dev)          # {value bits, local index}
     gat = torch.empty((world, GATHER, 2), dtype=torch.int64, device=dev)
     best = torch.empty((GATHER, 3), dtype=torch.int64, device=dev)         # {value bits, global index, owner}
@@ -296,6 +296,8 @@ def main():
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
+    ks_t = ctx.kernel_stats(True)                  # evaluation launches of the timed region only
+    launches, overlapped = ks_t["launches"] - launches0, ks_t["overlapped_launches"] - over0
 
     # ---- untimed check of the gathered arg-min at THIS world size: one batch per buffer set, one gather;
     # every record must equal an all_reduce(MIN) over the ranks' criterion values, name the rank that
@@ -358,9 +360,6 @@ def main():
         raise SystemExit("multistart winner check failed")
     del ms_des, ms_grad, ms_crit
     ctx.set_aux_stream(side.cuda_stream)
-    ks1 = ctx.kernel_stats(True)
-    launches = ks1["launches"] - launches0
-    overlapped = ks1["overlapped_launches"] - over0
     # the same launches once more with an event pair around EACH launch (this serialises them: a
     # launch can no longer start while its predecessor drains) -> isolated kernel duration
     ctx.set_profiling(True)
@@ -626,7 +625,7 @@ def main():
         # The evaluation kernel is the only launch of the timed region at N = 1, so its average launch
         # duration over the region IS region time / launches (consecutive launches overlap their tails,
         # see "overlapped_launches").  At N > 1 the region also holds one NCCL record gather and one
-        # reduction kernel per 16 steps; region time / steps is then a slightly pessimistic kernel time.
+        # reduction kernel per 32 steps; region time / steps is then a slightly pessimistic kernel time.
         kernel_ms = ms_total / args.steps
         achieved = flops / (kernel_ms * 1e-3) / 1e12 if kernel_ms > 0 else None
         peak = max(peak_burst, peak_after)
