@@ -960,6 +960,7 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
 static int eval_device(dynoed_ctx* ctx, const double* designs, int64_t n, double* crit, double* grad, double* fim,
                        double* xgrid) {
     const bool g = grad != nullptr;
+    if (g && xgrid) return fail(ctx, DYNOED_EUNSUPPORTED, "the trajectory is written by the objective-only kernels");
     const int kidx = g ? ctx->kidx_req : 0;
     ctx->call_n = n;
     const int grid = grid_for(ctx, n, kidx);

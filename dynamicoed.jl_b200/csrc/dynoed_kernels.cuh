@@ -897,7 +897,9 @@ __device__ __forceinline__ void oed_eval_body(const EvalParams& P) {
             double* tr = P.traj + ((size_t)blockIdx.x * (ADJ ? (size_t)P.n_steps * NZ + (size_t)N * NQ
                                                              : (size_t)N * NQ + P.n_ctrl_values)) * kMaxTile + tid;
             double* pq = ADJ ? tr + (size_t)P.n_steps * NZ * kMaxTile : tr;
-            double* xg = (P.xgrid && active) ? P.xgrid + (size_t)g * (N + 1) * (NZ + NF) : nullptr;
+            // the trajectory is only ever requested without a gradient (dynoed_trajectory, dynoed_information_gain):
+            // gradient kernels carry no trajectory code
+            double* xg = (!GRAD && P.xgrid && active) ? P.xgrid + (size_t)g * (N + 1) * (NZ + NF) : nullptr;
             if (xg) {
 #pragma unroll
                 for (int a = 0; a < NZ; ++a) xg[a] = z[a];

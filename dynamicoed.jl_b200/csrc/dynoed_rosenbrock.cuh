@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_eval_kernel(const EvalParams 
                 }
 #pragma unroll
                 for (int a = 0; a < NF; ++a) F[a] = T(0.0);
-                double* xg = (P.xgrid && dir0 == 0) ? P.xgrid + (size_t)g * (N + 1) * (NZ + NF) : nullptr;
+                double* xg = (!GRAD && P.xgrid && dir0 == 0) ? P.xgrid + (size_t)g * (N + 1) * (NZ + NF) : nullptr;
                 if (xg) {
 #pragma unroll
                     for (int a = 0; a < NZ; ++a) xg[a] = value_of(z[a]);
@@ -993,7 +993,7 @@ __global__ void __launch_bounds__(kMaxTile, 1) ros_ic_kernel(const EvalParams P)
                 for (int k = 0; k < NF; ++k) Fd[a][k] = 0.0;
 #pragma unroll
             for (int a = 0; a < M::NH * NX; ++a) sm[(size_t)(Lay::HN + a) * ic_stride<RT>()] = 0.0;   // G0 is constant
-            double* xg = P.xgrid ? P.xgrid + (size_t)g * (N + 1) * (NZ + NF) : nullptr;
+            double* const xg = nullptr;      // gradient kernel: the trajectory comes from the objective-only kernels
             if (xg) {
 #pragma unroll
                 for (int a = 0; a < NZ; ++a) xg[a] = z[a];
