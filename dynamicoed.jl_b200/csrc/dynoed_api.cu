@@ -35,6 +35,8 @@ constexpr int kCtrlGrad = 32;
 constexpr int kDirPar = 64;
 // method | kIc2: Rosenbrock gradient with second-order sensitivities for unknown initial conditions (ros_ic_kernel)
 constexpr int kIc2 = 128;
+// method | kTimePar: time-parallel gradient kernel for the smallest batches (tp_eval_kernel, one CTA per design)
+constexpr int kTimePar = 256;
 constexpr int kDirBlock = 32;
 // host calls of at most this many designs let the kernel read / write page-locked host memory directly
 constexpr int64_t kSmallZeroCopy = 16;
@@ -51,6 +53,8 @@ struct ModelEntry {
     int nh, flops_ic2_col, flops_ic2_q;   // unique second-order columns and their emitted pieces (all columns, one stage)
     bool ic2_ok;
     int ic2_gcol[kMaxIC];                 // G column that is d x / d ic_a
+    int tp_nd;                            // tp_eval_kernel: adjoint lanes (nz + n_ctrl), 0 = kernel not built
+    size_t (*tp_smem)(int n_var, int n_intervals, int n_steps, int n_ctrl_values);
 };
 
 template <class K>
@@ -183,8 +187,42 @@ static cudaError_t launch_dir(const EvalParams& P0, int grid, cudaStream_t st) {
 }
 
 template <class M>
+constexpr bool tp_built() { return M::NZ + 1 <= 32; }
+
+template <class M>
+static size_t tp_smem_model(int n_var, int N, int n_steps, int ncv) { return tp_smem_bytes<M>(n_var, N, n_steps, ncv); }
+
+template <class M, class Stepper>
+static cudaError_t launch_tp(const EvalParams& P, int grid, cudaStream_t st) {
+    if constexpr (tp_built<M>()) {
+        const size_t smem = tp_smem_bytes<M>(P.n_var, P.n_intervals, P.n_steps, P.n_ctrl_values);
+        static size_t smem_set[64] = {0};      // opt-in dynamic shared memory, raised once per device and size
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (smem > smem_set[dev & 63]) {
+            cudaError_t e = cudaFuncSetAttribute(tp_eval_kernel<M, Stepper>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            smem_set[dev & 63] = smem;
+        }
+        tp_eval_kernel<M, Stepper><<<grid, kTpBlock, smem, st>>>(P);
+        return cudaGetLastError();
+    } else {
+        return cudaErrorInvalidDeviceFunction;
+    }
+}
+
+template <class M>
 static cudaError_t launch_model(int method, bool grad, bool uc, bool pdl, const EvalParams& P, int grid, int block,
                                 size_t smem, cudaStream_t st) {
+    if (method & kTimePar) {
+        switch (method & 15) {
+            case DYNOED_RK4: return launch_tp<M, ExplicitStepper<TabRK4>>(P, grid, st);
+            case DYNOED_TSIT5: return launch_tp<M, ExplicitStepper<TabTsit5>>(P, grid, st);
+            case DYNOED_ROS2: return launch_tp<M, RosenbrockStepper<TabROS2>>(P, grid, st);
+            case DYNOED_ROS3P: return launch_tp<M, RosenbrockStepper<TabROS3P>>(P, grid, st);
+            default: return launch_tp<M, RosenbrockStepper<TabRODAS3>>(P, grid, st);
+        }
+    }
     if (method & kDirPar) {
         switch (method & 15) {
             case DYNOED_RK4: return launch_dir<M, ExplicitStepper<TabRK4>>(P, grid, st);
@@ -291,6 +329,8 @@ static ModelEntry make_entry() {
     e.nh = M::NH; e.flops_ic2_col = M::FLOPS_IC2_COL; e.flops_ic2_q = M::FLOPS_IC2_Q; e.ic2_ok = M::IC2_OK;
     for (int k = 0; k < M::NIC; ++k) e.ic2_gcol[k] = M::ic2_gcol(k);
 
+    e.tp_nd = tp_built<M>() ? M::NZ + M::NCTRL : 0;
+    e.tp_smem = &tp_smem_model<M>;
     e.launch = &launch_model<M>;
     e.attrs = &attrs_model<M>;
     e.info_gain = &info_gain_model<M>;
@@ -424,6 +464,8 @@ struct dynoed_ctx {
     bool dir_ok = false;               // direction-parallel kernel usable for small gradient batches
     int dir_nl = 1;                    // its lanes per design: 1 + unknown ICs + control values
     int64_t dir_max_lanes = 0;
+    bool tp_ok = false;                // time-parallel kernel usable for the smallest gradient batches
+    int64_t tp_max_n = 0;
     int64_t call_n = 0;                // designs of the call being served
     int kidx_req = 1;                  // gradient kernel requested by the current call (1 adjoint/Rosenbrock, 2 forward-only)
     int parity = 0;                    // scratch set of the NEXT device-path launch
@@ -452,6 +494,7 @@ struct dynoed_ctx {
     int64_t pdl_launches = 0;
     cudaEvent_t ev_order = nullptr;    // host path: orders the slot streams after / before the ctx stream
     int64_t dir_launches = 0;
+    int64_t tp_launches = 0;
     size_t scratch_bytes = 0;
     // optional per-launch timing of the evaluation kernel (device-pointer path)
     bool profiling = false;
@@ -554,7 +597,14 @@ static bool dir_eligible(const dynoed_ctx* ctx, int64_t n, int kidx) {
     return kidx == 1 && ctx->dir_ok && n > 0 && std::max(n, ctx->call_n) * ctx->dir_nl <= ctx->dir_max_lanes;
 }
 
+// The smallest of them (one optimiser callback, the 2 n_var + 1 designs of a finite-difference Hessian)
+// run on the time-parallel kernel: one CTA per design, see tp_eval_kernel.
+static bool tp_eligible(const dynoed_ctx* ctx, int64_t n, int kidx) {
+    return ctx->tp_ok && dir_eligible(ctx, n, kidx) && std::max(n, ctx->call_n) <= ctx->tp_max_n;
+}
+
 static int grid_for(const dynoed_ctx* ctx, int64_t n, int kidx) {
+    if (tp_eligible(ctx, n, kidx)) return (int)n;
     if (dir_eligible(ctx, n, kidx)) return (int)((n * ctx->dir_nl + kDirBlock - 1) / kDirBlock);
     const int64_t ntiles = (n + ctx->tile - 1) / ctx->tile;
     const int64_t resident = (int64_t)ctx->sm_count * std::max(ctx->bps[kidx], 1);
@@ -563,6 +613,7 @@ static int grid_for(const dynoed_ctx* ctx, int64_t n, int kidx) {
 
 // scratch of one gradient launch of n designs
 static size_t traj_need(const dynoed_ctx* ctx, int64_t n, int kidx) {
+    if (tp_eligible(ctx, n, kidx)) return 0;      // everything lives in shared memory
     if (dir_eligible(ctx, n, kidx))
         return sizeof(double) * (size_t)n * ctx->n_intervals * ctx->model->info.n_obs * ctx->model->info.nF;
     return traj_bytes_for(ctx, grid_for(ctx, n, kidx), kidx);
@@ -727,6 +778,11 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
         if (const char* dl = getenv("DYNOED_DIRPAR_MAX_LANES")) ctx->dir_max_lanes = std::max(0, atoi(dl));
         ctx->dir_ok = !getenv("DYNOED_NO_DIRPAR") && ctx->dir_nl > 1 &&
                       (rosenbrock || (size_t)N * mi.n_obs * mi.nF <= (size_t)ctx->n_steps * mi.nz);
+        // time-parallel kernel: one CTA per design, all of its tables in (opt-in) shared memory
+        ctx->tp_max_n = 2 * (int64_t)prop.multiProcessorCount;
+        if (const char* tn = getenv("DYNOED_TIMEPAR_MAX_N")) ctx->tp_max_n = std::max(0, atoi(tn));
+        ctx->tp_ok = ctx->dir_ok && !getenv("DYNOED_NO_TIMEPAR") && m->tp_nd > 0 &&
+                     m->tp_smem(d->n_var, N, ctx->n_steps, nvals) + 2048 <= (size_t)prop.sharedMemPerBlockOptin;
     }
     ctx->zero_copy = !getenv("DYNOED_NO_ZEROCOPY");
     ctx->host_staging = !getenv("DYNOED_NO_STAGING");
@@ -918,6 +974,7 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
     dynoed_ctx::Prev cur;
     cur.kidx = grad ? ctx->kidx_req : 0;
     const bool dirpar = grad && !xgrid && dir_eligible(ctx, n, cur.kidx);
+    const bool timepar = dirpar && tp_eligible(ctx, n, cur.kidx);
     cur.valid = xgrid == nullptr && !dirpar;
     if (dirpar) P.use_tma = 0;
     cur.full = !dirpar && grid == ctx->sm_count * std::max(ctx->bps[cur.kidx], 1);
@@ -945,8 +1002,8 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
         }
         CU(cudaEventRecord(ctx->ev_k0, st));
     }
-    CU(ctx->model->launch(method_code(ctx, cur.kidx) | (dirpar ? kDirPar : 0), grad != nullptr, ctx->ucoef, pdl, P, grid,
-                          ctx->tile, smem_bytes(ctx, cur.kidx), st));
+    CU(ctx->model->launch(method_code(ctx, cur.kidx) | (timepar ? kTimePar : dirpar ? kDirPar : 0), grad != nullptr,
+                          ctx->ucoef, pdl, P, grid, ctx->tile, smem_bytes(ctx, cur.kidx), st));
     if (ctx->profiling) { CU(cudaEventRecord(ctx->ev_k1, st)); ctx->ev_pending = true; }
     cur.serial = stream_new_serial(st);
     ctx->prev = cur;
@@ -954,6 +1011,7 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
     ctx->launches++;
     ctx->pdl_launches += pdl ? 1 : 0;
     ctx->dir_launches += dirpar ? 1 : 0;
+    ctx->tp_launches += timepar ? 1 : 0;
     return DYNOED_OK;
 }
 
@@ -1143,9 +1201,9 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
     bool small_zc = false;
     double *zc_in = nullptr, *zc_crit = nullptr, *zc_grad = nullptr, *zc_fim = nullptr;
     if (g && nchunks == 1 && n <= kSmallZeroCopy && ctx->zero_copy && !pipelined && dir_eligible(ctx, n, kidx) &&
-        ((size_t)(kDirBlock + ctx->dir_nl - 1) / ctx->dir_nl + 1) *
+        (tp_eligible(ctx, n, kidx) || ((size_t)(kDirBlock + ctx->dir_nl - 1) / ctx->dir_nl + 1) *
                 (ctx->n_var + (size_t)ctx->n_intervals * ctx->model->info.n_obs * ctx->model->info.nF) * sizeof(double) +
-                sizeof(int) * ((size_t)(ctx->model->info.n_ctrl + ctx->model->info.n_obs + 1) * ctx->n_intervals + 1) <= 48 * 1024) {
+                sizeof(int) * ((size_t)(ctx->model->info.n_ctrl + ctx->model->info.n_obs + 1) * ctx->n_intervals + 1) <= 48 * 1024)) {
         Slot& s0 = ctx->slots[0];
         auto dev = [](const void* p) -> double* {
             cudaPointerAttributes a;
@@ -1191,12 +1249,14 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
             set_scratch_params(ctx, P, par, kidx);
             part_base += grid;
             const bool dirpar = g && dir_eligible(ctx, cnt, kidx);
+            const bool timepar = dirpar && tp_eligible(ctx, cnt, kidx);
             P.use_tma = (!dirpar && ((size_t)ctx->tile * ctx->n_var * 8) % 16 == 0) ? 1 : 0;
             P.index_base = off;
-            CU(ctx->model->launch(method_code(ctx, kidx) | (dirpar ? kDirPar : 0), g, ctx->ucoef, false, P, grid, ctx->tile,
-                                  smem_bytes(ctx, kidx), s.stream));
+            CU(ctx->model->launch(method_code(ctx, kidx) | (timepar ? kTimePar : dirpar ? kDirPar : 0), g, ctx->ucoef, false, P,
+                                  grid, ctx->tile, smem_bytes(ctx, kidx), s.stream));
             ctx->launches++;
             ctx->dir_launches += dirpar ? 1 : 0;
+            ctx->tp_launches += timepar ? 1 : 0;
             double* o_crit = staged ? s.h_crit : crit + off;
             double* o_grad = staged ? s.h_grad : (g ? grad + off * ctx->n_var : nullptr);
             double* o_fim = staged ? s.h_fim : (fim ? fim + off * nF : nullptr);
@@ -1790,7 +1850,7 @@ int dynoed_kernel_stats_query(dynoed_ctx* ctx, int with_grad, dynoed_kernel_stat
     o->overlapped_launches = ctx->pdl_launches;
     o->small_batch_launches = ctx->dir_launches;
     o->small_batch_max = ctx->dir_ok ? (int32_t)(ctx->dir_max_lanes / ctx->dir_nl) : 0;
-    o->reserved_ = 0;
+    o->time_parallel_max = ctx->tp_ok ? (int32_t)std::min<int64_t>(ctx->tp_max_n, o->small_batch_max) : 0;
     o->scratch_bytes = (int64_t)ctx->scratch_bytes;
     o->n_steps = ctx->n_steps;
     o->stages = ctx->stages;

@@ -1278,4 +1278,508 @@ __global__ void __launch_bounds__(32, 1) dir_eval_kernel(const EvalParams P) {
     argmin_tail(P, best_val, best_idx);
 }
 
+// ----------------------------------------------------------------------------------------------
+// Time-parallel gradient kernel for the SMALLEST batches — one CTA per design.
+//
+// dir_eval_kernel above spreads the gradient DIRECTIONS of one design over lanes; every lane still
+// walks all n_steps steps with a dual number, so one call costs n_steps x (a dual-number step).
+// Here the sequential part is cut down to what is sequential by nature:
+//   phase 1 (one lane)        the plain forward sweep x_0 .. x_n of the STATES only (doubles); nothing
+//                             else is nonlinear in time;
+//   phase 1b                  the sensitivities G: given x_k a step maps G affinely, so task (k, q) gets
+//                             column q of that map from one dual-number step, and the chain of small affine
+//                             maps is evaluated in chunks of steps (compose per chunk, chain the chunks,
+//                             replay) — z_k = (x_k, G_k) at every step start ends up in shared memory;
+//   phase 2 (all warps)       the steps are now INDEPENDENT: task (k, m) pushes one dual number through
+//                             step k alone, seeded in state component m (or in the control value active
+//                             on step k), which yields column m of the step Jacobian d z_{k+1} / d (z_k, u),
+//                             the quadrature increment of step k and its derivative;
+//   phase 2b                  interval quadratures, F (lanes over intervals + butterfly), the criterion and
+//                             Lambda = d criterion / d F; then every task contracts its quadrature
+//                             derivative with Lambda and the measurement weights (s_k);
+//   phase 3                   the discrete adjoint recursion lambda_k = s_k + J_k^T lambda_{k+1} over these
+//                             small matrices, itself cut into <= 16 chunks of steps (one lane alone needs
+//                             ~200 cycles per step):  (1) every chunk composes its steps into one affine map
+//                             lambda_lo = b_c + A_c lambda_hi — one lane per column of [A_c | b_c], no
+//                             communication;  (2) one warp chains the chunk maps (<= 16 small mat-vecs) and
+//                             gets lambda at every chunk boundary, lambda_0 = d/d(initial conditions);
+//                             (3) models with controls: one lane per chunk replays its steps from the known
+//                             boundary value and adds lambda_{k+1} . d z_{k+1}/d u + s_k,u into its own
+//                             partial of d/d(control value); partials are summed in a fixed order.
+//                             Warp 1 writes d/dw and d/dtau meanwhile.
+// The adjoint of the step map is exact for the discrete scheme (same derivative as the dual sweep of
+// dir_eval_kernel / the reference's ForwardDiff gradient, /root/reference/src/problem.jl:154), for
+// explicit and Rosenbrock steppers alike — the step is differentiated as a black box.
+// Shared memory: row | step tables | z_k | step and interval quadratures | J columns | quadrature
+// derivatives | s | Lambda | int tables.
+// ----------------------------------------------------------------------------------------------
+#ifndef DYNOED_TP_BLOCK
+#define DYNOED_TP_BLOCK 256
+#endif
+constexpr int kTpBlock = DYNOED_TP_BLOCK;
+// MEASUREMENT-ONLY build switch DYNOED_TP_TIMING: thread 0 overwrites the first gradient entries of its
+// design with the SM-cycle counts of the phases (scripts/tp_phase_probe.py); results are WRONG.
+#ifdef DYNOED_TP_TIMING
+#define DYNOED_TP_MARK(i) { if (threadIdx.x == 0) tp_clk[i] = clock64(); __syncwarp(); }
+// BAR.SYNC.DEFER_BLOCKING lets the clock read that follows it issue before the warp blocks: a barrier
+// whose result is consumed does block
+#define DYNOED_TP_SYNC() { tp_sink += __syncthreads_count(1); }
+#else
+#define DYNOED_TP_MARK(i)
+#define DYNOED_TP_SYNC() __syncthreads();
+#endif
+constexpr int kTpMaxChunks = 16;
+
+template <class M>
+__host__ __device__ inline size_t tp_smem_bytes(int n_var, int N, int n_steps, int n_ctrl_values) {
+    constexpr int NZ = M::NZ, NQ = M::NOBS * M::NF, ND = M::NZ + M::NCTRL;
+    size_t dbl = (size_t)n_var + 3 * (size_t)n_steps + (size_t)(n_steps + 1) * NZ + (size_t)n_steps * NQ +
+                 (size_t)N * NQ + (size_t)n_steps * ND * (NZ + NQ + 1) + M::NF + 2 +
+                 (size_t)kTpMaxChunks * (NZ + 1) * NZ + (size_t)(kTpMaxChunks + 1) * NZ +
+                 (size_t)kTpMaxChunks * (n_ctrl_values > 0 ? n_ctrl_values : 1);
+    size_t ints = (size_t)(M::NCTRL + M::NOBS) * N + (N + 1) + n_steps;
+    return dbl * sizeof(double) + ints * sizeof(int) + 16;
+}
+
+template <class M, class Stepper>
+__global__ void __launch_bounds__(kTpBlock, 1) tp_eval_kernel(const EvalParams P) {
+    constexpr int NX = M::NX, NP = M::NP, NZ = M::NZ, NF = M::NF, NOBS = M::NOBS, NCTRL = M::NCTRL;
+    constexpr int NCU = NCTRL > 0 ? NCTRL : 1, NQ = NOBS * NF, ND = NZ + NCTRL;
+    using T = Dual<1>;
+    const int n_var = P.n_var, N = P.n_intervals, n_steps = P.n_steps;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long g = blockIdx.x;
+    const double* th = P.theta;
+#ifdef DYNOED_TP_TIMING
+    long long tp_clk[7];
+    int tp_sink = 0;
+#endif
+    DYNOED_TP_MARK(0)
+    scratch_acquire(P);
+
+    extern __shared__ __align__(16) double tp_sm[];
+    double* row = tp_sm;
+    double* s_t = row + n_var;
+    double* s_h = s_t + n_steps;
+    double* s_ih = s_h + n_steps;
+    double* zs = s_ih + n_steps;                         // [n_steps + 1][NZ] state at every step start
+    double* pqs = zs + (size_t)(n_steps + 1) * NZ;       // [n_steps][NQ]     quadrature increment of every step
+    double* pq = pqs + (size_t)n_steps * NQ;             // [N][NQ]           interval quadratures
+    double* jc = pq + (size_t)N * NQ;                    // [n_steps][ND][NZ] step Jacobian columns
+    double* dpq = jc + (size_t)n_steps * ND * NZ;        // [n_steps][ND][NQ] derivative of the step's quadrature increment
+    double* sc = dpq + (size_t)n_steps * ND * NQ;        // [n_steps][ND]     ... contracted with Lambda and the weights
+    double* ls = sc + (size_t)n_steps * ND;              // [NF] (+ trace term)
+    double* comp = ls + NF + 2;                          // [chunks][NZ + 1][NZ] columns of [A_c | b_c]
+    double* lamb = comp + (size_t)kTpMaxChunks * (NZ + 1) * NZ;          // [chunks + 1][NZ] lambda at chunk boundaries
+    double* part = lamb + (size_t)(kTpMaxChunks + 1) * NZ;               // [chunks][n_ctrl_values] partial d/d(control value)
+    const int ncv = P.n_ctrl_values > 0 ? P.n_ctrl_values : 1;
+    int* ind = reinterpret_cast<int*>(part + (size_t)kTpMaxChunks * ncv);   // [(NCTRL + NOBS)][N]
+    int* fst = ind + (NCTRL + NOBS) * N;                 // [N + 1]
+    int* siv = fst + (N + 1);                            // [n_steps] interval of every step
+
+    double* grow = P.grad + g * n_var;
+    {
+        const double* src = P.designs + g * n_var;
+        for (int i = tid; i < n_var; i += blockDim.x) row[i] = src[i];
+        for (int i = tid; i < n_steps; i += blockDim.x) {
+            s_t[i] = P.step_t[i]; s_h[i] = P.step_h[i]; s_ih[i] = P.step_ih[i];
+        }
+        for (int i = tid; i < (NCTRL + NOBS) * N; i += blockDim.x) ind[i] = P.indicators[i];
+        for (int i = tid; i <= N; i += blockDim.x) fst[i] = P.first_step[i];
+        for (int j = warp; j < N; j += (int)(blockDim.x >> 5)) {
+            const int a = P.first_step[j], b = P.first_step[j + 1];
+            for (int s = a + lane; s < b; s += 32) siv[s] = j;
+        }
+    }
+    DYNOED_TP_SYNC()
+    DYNOED_TP_MARK(1)
+
+    // ---- phase 1: plain forward sweep of the STATES x, one lane.  The stepper runs on the whole z, but only
+    //      x is stored: the sensitivities and quadratures feed nothing that is read, so their arithmetic is
+    //      dead code here (the compiler removes it) ----
+    constexpr int NG = NX * NP;                                  // sensitivities
+    if (tid == 0) {
+        double z[NZ];
+#pragma unroll
+        for (int a = 0; a < NX; ++a) z[a] = P.x0[a];
+#pragma unroll
+        for (int a = 0; a < NG; ++a) z[NX + a] = P.G0[a];
+        if constexpr (M::NIC > 0) {
+#pragma unroll
+            for (int a = 0; a < M::NIC; ++a) z[M::ic_state(a)] = row[P.ic_off + a];
+        }
+        int s_cur = fst[0];
+        for (int j = 0; j < N; ++j) {
+            double u[NCU], c[M::NCONST];
+#pragma unroll
+            for (int k = 0; k < NCTRL; ++k) u[k] = row[P.ctrl_off[k] + ind[k * N + j]];
+            M::template consts_t<double>(u, th, c);
+            const int s1 = fst[j + 1];
+            for (; s_cur < s1; ++s_cur) {
+#pragma unroll
+                for (int a = 0; a < NX; ++a) zs[(size_t)s_cur * NZ + a] = z[a];
+                double Pq[NQ];
+#pragma unroll
+                for (int a = 0; a < NQ; ++a) Pq[a] = 0.0;
+                Stepper::template step<M, double>(s_t[s_cur], s_h[s_cur], s_ih[s_cur], z, Pq, u, th, c);
+            }
+        }
+    }
+    DYNOED_TP_MARK(2)
+    DYNOED_TP_SYNC()
+
+    // ---- phase 1b: the sensitivities.  Given x_k, one step maps G affinely: G_{k+1} = psi_k + Phi_k G_k
+    //      (G' = f_x G + f_p, /root/reference/src/augment.jl:200-216; true for the explicit and the
+    //      Rosenbrock steps alike).  Task (k, q) takes the step from (x_k, G = 0) with a dual seed in
+    //      sensitivity q: the dual part is column q of Phi_k (exact: the map is affine), the value part is
+    //      psi_k.  The chain of these small affine maps is then evaluated in chunks like phase 3, forward. ----
+    constexpr int NCG = NG + 1;                                   // columns of [Phi | psi]
+    constexpr int LGG = NCG <= 8 ? 8 : NCG <= 16 ? 16 : 32;
+    constexpr int CPWG = 32 / LGG;
+    static_assert(NCG <= 32, "one lane per column of a chunk map");
+    double* phi = jc;                                            // [n_steps][NG + 1][NG]  (jc is written in phase 2)
+    double* compg = comp;                                        // [chunks][NG + 1][NG]
+    double* gb = lamb;                                           // [chunks + 1][NG] G at the chunk boundaries
+    for (int task = tid; task < n_steps * NCG; task += blockDim.x) {
+        const int k = task / NCG, q = task - k * NCG;
+        const int j = siv[k];
+        T z[NZ], u[NCU], c[M::NCONST], Pq[NQ];
+#pragma unroll
+        for (int a = 0; a < NX; ++a) z[a] = T(zs[(size_t)k * NZ + a]);
+#pragma unroll
+        for (int a = 0; a < NG; ++a) { z[NX + a].v = 0.0; z[NX + a].d[0] = (a == q) ? 1.0 : 0.0; }
+#pragma unroll
+        for (int kk = 0; kk < NCTRL; ++kk) u[kk] = T(row[P.ctrl_off[kk] + ind[kk * N + j]]);
+        M::template consts_t<T>(u, th, c);
+#pragma unroll
+        for (int a = 0; a < NQ; ++a) Pq[a] = T(0.0);
+        Stepper::template step<M, T>(s_t[k], s_h[k], s_ih[k], z, Pq, u, th, c);
+#pragma unroll
+        for (int a = 0; a < NG; ++a) phi[(size_t)task * NG + a] = (q < NG) ? z[NX + a].d[0] : z[NX + a].v;
+    }
+    DYNOED_TP_SYNC()
+    const int nchunk_g = min(min(kTpMaxChunks, CPWG * (int)(blockDim.x >> 5)), n_steps);
+    {   // compose the steps of every chunk, forward in time
+        const int c = warp * CPWG + lane / LGG, q = lane % LGG;
+        if (c < nchunk_g && q < NCG) {
+            double v[NG];
+#pragma unroll
+            for (int a = 0; a < NG; ++a) v[a] = (a == q) ? 1.0 : 0.0;
+            const int lo = (int)((long long)c * n_steps / nchunk_g), hi = (int)((long long)(c + 1) * n_steps / nchunk_g);
+            const double sw = (q == NG) ? 1.0 : 0.0;
+            for (int k = lo; k < hi; ++k) {
+                const double* ph = phi + (size_t)k * NCG * NG;
+                double nv[NG];
+#pragma unroll
+                for (int a = 0; a < NG; ++a) nv[a] = sw * ph[NG * NG + a];
+#pragma unroll
+                for (int r = 0; r < NG; ++r)
+#pragma unroll
+                    for (int a = 0; a < NG; ++a) nv[a] = fma(ph[r * NG + a], v[r], nv[a]);
+#pragma unroll
+                for (int a = 0; a < NG; ++a) v[a] = nv[a];
+            }
+#pragma unroll
+            for (int a = 0; a < NG; ++a) compg[((size_t)c * NCG + q) * NG + a] = v[a];
+        }
+    }
+    DYNOED_TP_SYNC()
+    if (warp == 0) {   // chain the chunk maps from G_0: gb[c] = G at the lower end of chunk c
+        double g_a = lane < NG ? P.G0[lane] : 0.0;
+        for (int c = 0; c < nchunk_g; ++c) {
+            if (lane < NG) gb[(size_t)c * NG + lane] = g_a;
+            __syncwarp();
+            if (lane < NG) {
+                double acc = compg[((size_t)c * NCG + NG) * NG + lane];
+#pragma unroll
+                for (int r = 0; r < NG; ++r) acc = fma(compg[((size_t)c * NCG + r) * NG + lane], gb[(size_t)c * NG + r], acc);
+                g_a = acc;
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+        if (lane < nchunk_g) {   // replay every chunk from its boundary value: G_k at every step start
+            const int c = lane;
+            double G[NG];
+#pragma unroll
+            for (int a = 0; a < NG; ++a) G[a] = gb[(size_t)c * NG + a];
+            const int lo = (int)((long long)c * n_steps / nchunk_g), hi = (int)((long long)(c + 1) * n_steps / nchunk_g);
+            for (int k = lo; k < hi; ++k) {
+                const double* ph = phi + (size_t)k * NCG * NG;
+                double nv[NG];
+#pragma unroll
+                for (int a = 0; a < NG; ++a) { zs[(size_t)k * NZ + NX + a] = G[a]; nv[a] = ph[NG * NG + a]; }
+#pragma unroll
+                for (int r = 0; r < NG; ++r)
+#pragma unroll
+                    for (int a = 0; a < NG; ++a) nv[a] = fma(ph[r * NG + a], G[r], nv[a]);
+#pragma unroll
+                for (int a = 0; a < NG; ++a) G[a] = nv[a];
+            }
+        }
+    }
+    DYNOED_TP_SYNC()
+    DYNOED_TP_MARK(3)
+
+    // ---- phase 2: every step on its own, one dual direction per task ----
+    {
+        for (int task = tid; task < n_steps * ND; task += blockDim.x) {
+            const int k = task / ND, m = task - k * ND;
+            const int j = siv[k];
+            T z[NZ], u[NCU], c[M::NCONST], Pq[NQ];
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) {
+                z[a].v = zs[(size_t)k * NZ + a];
+                z[a].d[0] = (a == m) ? 1.0 : 0.0;
+            }
+#pragma unroll
+            for (int kk = 0; kk < NCTRL; ++kk) {
+                u[kk].v = row[P.ctrl_off[kk] + ind[kk * N + j]];
+                u[kk].d[0] = (NZ + kk == m) ? 1.0 : 0.0;
+            }
+            M::template consts_t<T>(u, th, c);
+#pragma unroll
+            for (int a = 0; a < NQ; ++a) Pq[a] = T(0.0);
+            Stepper::template step<M, T>(s_t[k], s_h[k], s_ih[k], z, Pq, u, th, c);
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) jc[(size_t)task * NZ + a] = z[a].d[0];
+#pragma unroll
+            for (int a = 0; a < NQ; ++a) dpq[(size_t)task * NQ + a] = Pq[a].d[0];
+            if (m == 0) {
+#pragma unroll
+                for (int a = 0; a < NQ; ++a) pqs[(size_t)k * NQ + a] = Pq[a].v;
+            }
+        }
+    }
+    DYNOED_TP_SYNC()
+    DYNOED_TP_MARK(4)
+
+    // ---- phase 2b: interval quadratures (steps summed in order), F, criterion, Lambda ----
+    double best_val = __longlong_as_double(0x7ff0000000000000LL);
+    long long best_idx = -1;
+    for (int i = tid; i < N * NQ; i += blockDim.x) {
+        const int j = i / NQ, a = i - j * NQ;
+        double acc = 0.0;
+        for (int k = fst[j]; k < fst[j + 1]; ++k) acc += pqs[(size_t)k * NQ + a];
+        pq[i] = acc;
+    }
+    for (int i = tid; i < kTpMaxChunks * ncv; i += blockDim.x) part[i] = 0.0;
+    DYNOED_TP_SYNC()
+    if (warp == 0) {
+        double F[NF];
+#pragma unroll
+        for (int a = 0; a < NF; ++a) F[a] = 0.0;
+        for (int j = lane; j < N; j += 32) {
+#pragma unroll
+            for (int i = 0; i < NOBS; ++i) {
+                const double w = row[P.w_off[i] + ind[(NCTRL + i) * N + j]];
+#pragma unroll
+                for (int k = 0; k < NF; ++k) F[k] = fma(w, pq[(size_t)j * NQ + i * NF + k], F[k]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int a = 0; a < NF; ++a) F[a] += __shfl_xor_sync(0xffffffffu, F[a], o);
+        }
+        if (lane == 0) {
+            const double tau = row[P.tau_off];
+            double L[NF], value;
+            criterion_eval<NP>(F, tau, P.criterion, value, L);
+#pragma unroll
+            for (int jj = 0; jj < NP; ++jj)
+#pragma unroll
+                for (int ii = 0; ii <= jj; ++ii) ls[tri(ii, jj)] = (ii == jj ? 1.0 : 2.0) * L[tri(ii, jj)];
+            double trL = 1.0;
+#pragma unroll
+            for (int i = 0; i < NP; ++i) trL += L[tri(i, i)];
+            ls[NF] = trL;
+            const double obj = value + tau;
+            P.crit[g] = obj;
+            if (P.fim) {
+#pragma unroll
+                for (int a = 0; a < NF; ++a) P.fim[g * NF + a] = F[a];
+            }
+            if (obj < best_val) { best_val = obj; best_idx = P.index_base + g; }   // NaN never wins
+        }
+    }
+    DYNOED_TP_SYNC()
+    for (int task = tid; task < n_steps * ND; task += blockDim.x) {
+        const int j = siv[task / ND];
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < NOBS; ++i) {
+            const double w = row[P.w_off[i] + ind[(NCTRL + i) * N + j]];
+            double si = 0.0;
+#pragma unroll
+            for (int f = 0; f < NF; ++f) si = fma(ls[f], dpq[(size_t)task * NQ + i * NF + f], si);
+            s = fma(w, si, s);
+        }
+        sc[task] = s;
+    }
+    DYNOED_TP_SYNC()
+    DYNOED_TP_MARK(5)
+
+    // ---- phase 3: adjoint recursion over the step Jacobians, cut into chunks of steps ----
+    constexpr int NC = NZ + 1;                                   // columns of [A_c | b_c]
+    constexpr int LG = NC <= 8 ? 8 : NC <= 16 ? 16 : 32;         // lanes per chunk
+    constexpr int CPW = 32 / LG;                                 // chunks per warp
+    static_assert(NC <= 32, "one lane per column of a chunk map");
+    const int nchunk = min(min(kTpMaxChunks, CPW * (int)(blockDim.x >> 5)), n_steps);
+    {   // (1) compose the steps of every chunk: column q of A_c is the chain applied to e_q, b_c starts from 0
+        const int c = warp * CPW + lane / LG, q = lane % LG;
+        if (c < nchunk && q < NC) {
+            double v[NZ];
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) v[a] = (a == q) ? 1.0 : 0.0;
+            const int lo = (int)((long long)c * n_steps / nchunk), hi = (int)((long long)(c + 1) * n_steps / nchunk);
+            const double sw = (q == NZ) ? 1.0 : 0.0;
+            for (int k = hi - 1; k >= lo; --k) {
+                const double* col = jc + (size_t)k * ND * NZ;
+                const double* sk = sc + (size_t)k * ND;
+                double nv[NZ];
+#pragma unroll
+                for (int m = 0; m < NZ; ++m) nv[m] = sw * sk[m];
+#pragma unroll
+                for (int r = 0; r < NZ; ++r)
+#pragma unroll
+                    for (int m = 0; m < NZ; ++m) nv[m] = fma(v[r], col[m * NZ + r], nv[m]);
+#pragma unroll
+                for (int m = 0; m < NZ; ++m) v[m] = nv[m];
+            }
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) comp[((size_t)c * NC + q) * NZ + a] = v[a];
+        }
+    }
+    DYNOED_TP_SYNC()
+    if (warp == 0) {   // (2) chain the chunk maps from the end: lamb[c + 1] = lambda at the upper end of chunk c
+        double lam_m = 0.0;
+        for (int c = nchunk - 1; c >= 0; --c) {
+            if (lane < NZ) lamb[(size_t)(c + 1) * NZ + lane] = lam_m;
+            __syncwarp();
+            if (lane < NZ) {
+                double acc = comp[((size_t)c * NC + NZ) * NZ + lane];
+#pragma unroll
+                for (int r = 0; r < NZ; ++r) acc = fma(comp[((size_t)c * NC + r) * NZ + lane], lamb[(size_t)(c + 1) * NZ + r], acc);
+                lam_m = acc;
+            }
+            __syncwarp();
+        }
+        if (lane < NZ) lamb[lane] = lam_m;
+        __syncwarp();
+        if constexpr (M::NIC > 0) {
+            if (lane < M::NIC) grow[P.ic_off + lane] = lamb[M::ic_state(lane)];
+        }
+    } else if (warp == 1) {   // d/dw from the interval quadratures, d/dtau
+        if (lane < NOBS) {
+            const int i = lane;
+            double wb = 0.0;
+            int wk = -1;
+            for (int j = 0; j < N; ++j) {
+                const int idx = ind[(NCTRL + i) * N + j];
+                if (idx != wk) {
+                    if (wk >= 0) grow[P.w_off[i] + wk] = wb;
+                    wb = 0.0; wk = idx;
+                }
+                double sacc = 0.0;
+#pragma unroll
+                for (int k = 0; k < NF; ++k) sacc = fma(ls[k], pq[(size_t)j * NQ + i * NF + k], sacc);
+                wb += sacc;
+            }
+            if (wk >= 0) grow[P.w_off[i] + wk] = wb;
+        } else if (lane == NOBS) {
+            grow[P.tau_off] = ls[NF];
+        }
+    }
+    if constexpr (NCTRL > 0) {
+        DYNOED_TP_SYNC()
+        if (warp == 0 && lane < nchunk) {   // (3) replay every chunk from its boundary value: control columns
+            const int c = lane;
+            double lam[NZ];
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) lam[a] = lamb[(size_t)(c + 1) * NZ + a];
+            const int lo = (int)((long long)c * n_steps / nchunk), hi = (int)((long long)(c + 1) * n_steps / nchunk);
+            for (int k = hi - 1; k >= lo; --k) {
+                const double* col = jc + (size_t)k * ND * NZ;
+                const double* sk = sc + (size_t)k * ND;
+                const int j = siv[k];
+                int cbase = 0;
+#pragma unroll
+                for (int kc = 0; kc < NCTRL; ++kc) {
+                    double mu = sk[NZ + kc];
+#pragma unroll
+                    for (int r = 0; r < NZ; ++r) mu = fma(lam[r], col[(NZ + kc) * NZ + r], mu);
+                    part[(size_t)c * ncv + cbase + ind[kc * N + j]] += mu;
+                    cbase += P.ctrl_len[kc];
+                }
+                double nl[NZ];
+#pragma unroll
+                for (int m = 0; m < NZ; ++m) nl[m] = sk[m];
+#pragma unroll
+                for (int r = 0; r < NZ; ++r)
+#pragma unroll
+                    for (int m = 0; m < NZ; ++m) nl[m] = fma(lam[r], col[m * NZ + r], nl[m]);
+#pragma unroll
+                for (int m = 0; m < NZ; ++m) lam[m] = nl[m];
+            }
+        }
+        DYNOED_TP_SYNC()
+        for (int i = tid; i < P.n_ctrl_values; i += blockDim.x) {   // later chunks first, as the recursion runs
+            double acc = 0.0;
+            for (int c = nchunk - 1; c >= 0; --c) acc += part[(size_t)c * ncv + i];
+            int rest = i, off = -1;
+#pragma unroll
+            for (int kc = 0; kc < NCTRL; ++kc) {
+                if (off < 0) {
+                    if (rest < P.ctrl_len[kc]) off = P.ctrl_off[kc] + rest;
+                    else rest -= P.ctrl_len[kc];
+                }
+            }
+            if (off >= 0) grow[off] = acc;
+        }
+    }
+    DYNOED_TP_MARK(6)
+    DYNOED_TP_SYNC()
+#ifdef DYNOED_TP_TIMING
+    if (tid == 0) {
+        for (int i = 0; i < 6; ++i) grow[i] = (double)(tp_clk[i + 1] - tp_clk[i]);
+        if (tp_sink == -12345) grow[6] = 0.0;
+    }
+#endif
+
+    // ---- arg-min record of this CTA (= this design); the last CTA reduces the batch ----
+    __shared__ int tp_last;
+    if (tid == 0) {
+        P.part_val[P.part_base + blockIdx.x] = best_val;
+        P.part_idx[P.part_base + blockIdx.x] = best_idx;
+        __threadfence();
+        const unsigned int t = atomicAdd(P.ticket, 1u);
+        tp_last = (t == P.ticket_target - 1u);
+    }
+    __syncthreads();
+    if (tp_last && warp == 0) {
+        __threadfence();
+        double bv = __longlong_as_double(0x7ff0000000000000LL);
+        long long bi = -1;
+        for (int i = lane; i < P.n_parts; i += 32) {
+            const double v = __ldcg(P.part_val + i);
+            const long long k = __ldcg(P.part_idx + i);
+            if (k >= 0 && (v < bv || (v == bv && (bi < 0 || k < bi)))) { bv = v; bi = k; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, bv, o);
+            const long long oi = __shfl_down_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (ov < bv || (ov == bv && (bi < 0 || oi < bi)))) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) {
+            *P.best_val = bv;
+            *P.best_idx = bi;
+            if (P.ring_rec) { P.ring_rec[0] = __double_as_longlong(bv); P.ring_rec[1] = bi; }
+            *P.ticket = 0u;
+            if (P.guard) { __threadfence(); atomicAdd(P.guard, 1ULL); }   // this call is done with the scratch set
+        }
+    }
+}
+
 }  // namespace dynoed

@@ -54,7 +54,7 @@ class KernelStats(C.Structure):
                 ("scratch_bytes", C.c_int64), ("n_steps", C.c_int32), ("stages", C.c_int32),
                 ("flops_per_design_eval", C.c_double), ("flops_per_design_grad", C.c_double),
                 ("bytes_per_design", C.c_double), ("overlapped_launches", C.c_int64),
-                ("small_batch_launches", C.c_int64), ("small_batch_max", C.c_int32), ("reserved_", C.c_int32)]
+                ("small_batch_launches", C.c_int64), ("small_batch_max", C.c_int32), ("time_parallel_max", C.c_int32)]
 
 
 EXPORTS = ["dynoed_abi_version", "dynoed_model_count", "dynoed_model_name", "dynoed_model_query",
