@@ -779,7 +779,9 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
         ctx->dir_ok = !getenv("DYNOED_NO_DIRPAR") && ctx->dir_nl > 1 &&
                       (rosenbrock || (size_t)N * mi.n_obs * mi.nF <= (size_t)ctx->n_steps * mi.nz);
         // time-parallel kernel: one CTA per design, all of its tables in (opt-in) shared memory
-        ctx->tp_max_n = 2 * (int64_t)prop.multiProcessorCount;
+        // measured on B200 (scripts/tp_probe.py): ahead of the direction-parallel kernel for every model while
+        // each design has an SM of its own; at two CTAs per SM the cheap models lose
+        ctx->tp_max_n = (int64_t)prop.multiProcessorCount;
         if (const char* tn = getenv("DYNOED_TIMEPAR_MAX_N")) ctx->tp_max_n = std::max(0, atoi(tn));
         ctx->tp_ok = ctx->dir_ok && !getenv("DYNOED_NO_TIMEPAR") && m->tp_nd > 0 &&
                      m->tp_smem(d->n_var, N, ctx->n_steps, nvals) + 2048 <= (size_t)prop.sharedMemPerBlockOptin;
@@ -1183,21 +1185,10 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
     cudaEvent_t ev = ctx->ev_order;   // re-recorded at every use: a wait captures the record that precedes it
     for (int q = 0; q < 2; ++q)
         if (!ctx->call_done[q]) CU(cudaEventCreateWithFlags(&ctx->call_done[q], cudaEventDisableTiming));
-    if (pipelined && !ctx->stream_dirty && !staged) {
-        // Pipelined host call: do NOT order after the previous host call (its D2H should overlap this
-        // call's H2D; chunk c of both calls shares slot c % kSlots, whose stream keeps them in order).
-        // Only the call that used the same scratch parity (two calls back) must have finished.
-        if (ctx->call_of_parity[par] >= 0)
-            for (int k = 0; k < kSlots && k < nchunks; ++k)
-                CU(cudaStreamWaitEvent(ctx->slots[k].stream, ctx->call_done[par], 0));
-    } else {
-        // order after whatever the ctx stream was doing
-        CU(cudaEventRecord(ev, ctx->stream));
-        for (int k = 0; k < kSlots && k < nchunks; ++k) CU(cudaStreamWaitEvent(ctx->slots[k].stream, ev, 0));
-    }
     // A call of a handful of designs (the optimiser callback) is all latency: skip the three or four
-    // small DMA transfers — the direction-parallel kernel stages the rows from page-locked host
-    // memory itself (one coalesced read) and stores its results there (posted writes).
+    // small DMA transfers — the small-batch kernels stage the rows from page-locked host
+    // memory themselves (one coalesced read) and store their results there (posted writes).  Such a call
+    // runs on the ctx stream itself: no slot stream, no cross-stream events (four driver calls less).
     bool small_zc = false;
     double *zc_in = nullptr, *zc_crit = nullptr, *zc_grad = nullptr, *zc_fim = nullptr;
     if (g && nchunks == 1 && n <= kSmallZeroCopy && ctx->zero_copy && !pipelined && dir_eligible(ctx, n, kidx) &&
@@ -1215,6 +1206,18 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
         zc_grad = dev(staged ? s0.h_grad : grad);
         zc_fim = fim ? dev(staged ? s0.h_fim : fim) : nullptr;
         small_zc = zc_in && zc_crit && zc_grad && (!fim || zc_fim);
+    }
+    if (pipelined && !ctx->stream_dirty && !staged) {
+        // Pipelined host call: do NOT order after the previous host call (its D2H should overlap this
+        // call's H2D; chunk c of both calls shares slot c % kSlots, whose stream keeps them in order).
+        // Only the call that used the same scratch parity (two calls back) must have finished.
+        if (ctx->call_of_parity[par] >= 0)
+            for (int k = 0; k < kSlots && k < nchunks; ++k)
+                CU(cudaStreamWaitEvent(ctx->slots[k].stream, ctx->call_done[par], 0));
+    } else if (!small_zc) {
+        // order after whatever the ctx stream was doing
+        CU(cudaEventRecord(ev, ctx->stream));
+        for (int k = 0; k < kSlots && k < nchunks; ++k) CU(cudaStreamWaitEvent(ctx->slots[k].stream, ev, 0));
     }
     ctx->call_serial++;
     ctx->set_calls[par]++;
@@ -1252,8 +1255,9 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
             const bool timepar = dirpar && tp_eligible(ctx, cnt, kidx);
             P.use_tma = (!dirpar && ((size_t)ctx->tile * ctx->n_var * 8) % 16 == 0) ? 1 : 0;
             P.index_base = off;
+            cudaStream_t run_stream = small_zc ? ctx->stream : s.stream;
             CU(ctx->model->launch(method_code(ctx, kidx) | (timepar ? kTimePar : dirpar ? kDirPar : 0), g, ctx->ucoef, false, P,
-                                  grid, ctx->tile, smem_bytes(ctx, kidx), s.stream));
+                                  grid, ctx->tile, smem_bytes(ctx, kidx), run_stream));
             ctx->launches++;
             ctx->dir_launches += dirpar ? 1 : 0;
             ctx->tp_launches += timepar ? 1 : 0;
@@ -1263,11 +1267,11 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
             if (!crit_map && !small_zc) CU(cudaMemcpyAsync(o_crit, s.d_crit, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s.stream));
             if (g && !small_zc && !grad_map) CU(cudaMemcpyAsync(o_grad, s.d_grad, sizeof(double) * cnt * ctx->n_var, cudaMemcpyDeviceToHost, s.stream));
             if (fim && !fim_map && !small_zc) CU(cudaMemcpyAsync(o_fim, s.d_fim, sizeof(double) * cnt * nF, cudaMemcpyDeviceToHost, s.stream));
-            if (staged) CU(cudaEventRecord(s.done, s.stream));
+            if (staged) CU(cudaEventRecord(s.done, run_stream));
         }
         if (staged)
             for (int64_t c = std::max<int64_t>(0, nchunks - kSlots); c < nchunks; ++c) { rc = drain(c); if (rc) return rc; }
-        for (int k = 0; k < kSlots && k < nchunks; ++k) {
+        for (int k = 0; k < kSlots && k < nchunks && !small_zc; ++k) {
             CU(cudaEventRecord(ev, ctx->slots[k].stream));
             CU(cudaStreamWaitEvent(ctx->stream, ev, 0));
         }

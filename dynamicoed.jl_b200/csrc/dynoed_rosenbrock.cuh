@@ -1353,9 +1353,11 @@ __global__ void __launch_bounds__(kTpBlock, 1) tp_eval_kernel(const EvalParams P
 #ifdef DYNOED_TP_TIMING
     long long tp_clk[7];
     int tp_sink = 0;
+    const unsigned long long tp_ns0 = global_ns();
 #endif
     DYNOED_TP_MARK(0)
-    scratch_acquire(P);
+    __shared__ int tp_prog;            // steps whose start state x_k is in shared memory (phase 1 -> phase 1b)
+    if (threadIdx.x == 0) tp_prog = 0;
 
     extern __shared__ __align__(16) double tp_sm[];
     double* row = tp_sm;
@@ -1423,13 +1425,14 @@ __global__ void __launch_bounds__(kTpBlock, 1) tp_eval_kernel(const EvalParams P
                 for (int a = 0; a < NQ; ++a) Pq[a] = 0.0;
                 Stepper::template step<M, double>(s_t[s_cur], s_h[s_cur], s_ih[s_cur], z, Pq, u, th, c);
             }
+            __threadfence_block();
+            *(volatile int*)&tp_prog = s1;      // the tasks of phase 1b start on these steps while the sweep goes on
         }
     }
     DYNOED_TP_MARK(2)
-    DYNOED_TP_SYNC()
 
     // ---- phase 1b: the sensitivities.  Given x_k, one step maps G affinely: G_{k+1} = psi_k + Phi_k G_k
-    //      (G' = f_x G + f_p, /root/reference/src/augment.jl:200-216; true for the explicit and the
+    //      (G' = f_x G + f_p, /root/reference/src/augment.jl:231; true for the explicit and the
     //      Rosenbrock steps alike).  Task (k, q) takes the step from (x_k, G = 0) with a dual seed in
     //      sensitivity q: the dual part is column q of Phi_k (exact: the map is affine), the value part is
     //      psi_k.  The chain of these small affine maps is then evaluated in chunks like phase 3, forward. ----
@@ -1440,8 +1443,17 @@ __global__ void __launch_bounds__(kTpBlock, 1) tp_eval_kernel(const EvalParams P
     double* phi = jc;                                            // [n_steps][NG + 1][NG]  (jc is written in phase 2)
     double* compg = comp;                                        // [chunks][NG + 1][NG]
     double* gb = lamb;                                           // [chunks + 1][NG] G at the chunk boundaries
-    for (int task = tid; task < n_steps * NCG; task += blockDim.x) {
+    // The tasks run WHILE lane 0 is still sweeping (they only need x_k): every warp except warp 0 and the one
+    // that shares its scheduler (warp 4) takes tasks in step order and waits for the sweep's progress counter.
+    const int nwork = ((int)(blockDim.x >> 5) - (blockDim.x > 128 ? 2 : 1)) * 32;
+    const int wtid = warp == 0 || (warp == 4 && blockDim.x > 128) ? -1 : (warp - 1 - (warp > 4 ? 1 : 0)) * 32 + lane;
+    for (int task = wtid; wtid >= 0 && task < n_steps * NCG; task += nwork) {
         const int k = task / NCG, q = task - k * NCG;
+        {
+            const int klast = min((task - lane + 31) / NCG, n_steps - 1);     // warp-uniform
+            while (*(volatile int*)&tp_prog <= klast) __nanosleep(64);
+            __threadfence_block();
+        }
         const int j = siv[k];
         T z[NZ], u[NCU], c[M::NCONST], Pq[NQ];
 #pragma unroll
@@ -1743,11 +1755,14 @@ __global__ void __launch_bounds__(kTpBlock, 1) tp_eval_kernel(const EvalParams P
 #ifdef DYNOED_TP_TIMING
     if (tid == 0) {
         for (int i = 0; i < 6; ++i) grow[i] = (double)(tp_clk[i + 1] - tp_clk[i]);
-        if (tp_sink == -12345) grow[6] = 0.0;
+        grow[6] = (double)(global_ns() - tp_ns0);      // wall time of the same span, ns
+        if (tp_sink == -12345) grow[7] = 0.0;
     }
 #endif
 
-    // ---- arg-min record of this CTA (= this design); the last CTA reduces the batch ----
+    // ---- arg-min record of this CTA (= this design); the last CTA reduces the batch.  Only these record
+    //      slots belong to the scratch set, so its guard is taken here, after the work ----
+    scratch_acquire(P);
     __shared__ int tp_last;
     if (tid == 0) {
         P.part_val[P.part_base + blockIdx.x] = best_val;

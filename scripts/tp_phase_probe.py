@@ -15,7 +15,7 @@ for alg in (D.RK4(4), D.Tsit5(4)):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(S); ctx.eval_batch(d, c, g, None, async_=True); e1.record(S); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e3)
-        cyc = g.cpu().numpy()[:, :6]
-        print(os.environ.get("DYNOED_LIB", "default").split("/")[-1], type(alg).__name__, f"n={n} device {np.median(ts):.1f} us; cycles setup/phase1/phase1b/phase2/phase2b/phase3 (median over designs):",
+        cyc = g.cpu().numpy()[:, :7]
+        print(os.environ.get("DYNOED_LIB", "default").split("/")[-1], type(alg).__name__, f"n={n} device {np.median(ts):.1f} us; cycles setup/phase1/phase1b/phase2/phase2b/phase3, ns start-to-end (median over designs):",
               np.median(cyc, axis=0).astype(int).tolist(), flush=True)
     ctx.close()

@@ -152,10 +152,18 @@ def test_ragged_and_empty_batches(oracles, built_library):
     orc = oracles("lv_fishing", 4, "rk4", 4)
     des = random_designs("lv_fishing", 71, 1000, 5)
     full = ctx.evaluate(des)
+    # batches up to time_parallel_max run on the time-parallel kernel, larger ones on the direction-parallel
+    # kernel: bitwise equal within a kernel whatever the batch size, equal to rounding between the two
+    tpmax = ctx.kernel_stats(True)["time_parallel_max"]
+    assert 128 <= tpmax < 257
+    tp_full = ctx.evaluate(des[:tpmax])
+    for a, b in zip(tp_full, full):
+        assert rel_rows(a.reshape(tpmax, -1), b[:tpmax].reshape(tpmax, -1)) < 1e-12
     for n in (1, 2, 31, 127, 128, 129, 257, 1000):
         c, g, F = ctx.evaluate(des[:n])
-        assert np.array_equal(c, full[0][:n]) and np.array_equal(g, full[1][:n])
-        assert np.array_equal(F, full[2][:n])
+        ref = tp_full if n <= tpmax else full
+        assert np.array_equal(c, ref[0][:n]) and np.array_equal(g, ref[1][:n])
+        assert np.array_equal(F, ref[2][:n])
     oc, og, oF = orc.evaluate(des[:129], grad=True)
     assert rel(full[0][:129], oc) < RTOL and rel_rows(full[1][:129], og) < RTOL
     # empty batch: OK, nothing written
@@ -1197,6 +1205,59 @@ def test_small_batches_use_the_direction_parallel_kernel_and_match(name, method,
         oc, og, oF = oracles(name, crit, method, m).evaluate(big[:64], grad=True)
         c, g, F = ctx.evaluate(big[:64])
         assert rel(c, oc) < RTOL and rel(F, oF) < RTOL and rel_rows(g, og) < RTOL
+
+
+@pytest.mark.parametrize("name,method,sub", [("lv_fishing", "rk4", 4), ("lv_fishing", "tsit5", 2), ("lv_ic", "rk4", 4),
+                                             ("lv_ic", "ros3p", 8), ("lv_fishing", "ros2", 4),
+                                             ("chem6", "rodas3", D.graded_edges(10, 8, 1e-6, 3))])
+def test_time_parallel_kernel_matches_the_other_gradient_kernels_and_the_oracle(name, method, sub, built_library, monkeypatch):
+    """The smallest gradient batches run one CTA per design (tp_eval_kernel: x-only sweep, per-step affine
+    maps, chunked chains).  Same numbers as the direction-parallel kernel (DYNOED_NO_TIMEPAR), the large-batch
+    kernels and the C++ oracle; arg-min and NaN handling included."""
+    from oracle.cpp_oracle import CppOracle
+    from oracle.oed_oracle import Oracle
+    ctor = {"lv_fishing": models.lotka_volterra_fishing, "lv_ic": models.lotka_volterra_ic, "chem6": models.chem6}[name]
+    algs = dict(ALGS, **ROS)
+    alg = algs[method](edges=sub) if not isinstance(sub, int) else algs[method](sub)
+    crit_cls, crit_id = (D.FisherECriterion, 2) if name == "chem6" else (D.ACriterion, 3)
+    out = {}
+    for variant, env in (("tp", {}), ("dir", {"DYNOED_NO_TIMEPAR": "1"}), ("large", {"DYNOED_NO_DIRPAR": "1"})):
+        for k in ("DYNOED_NO_TIMEPAR", "DYNOED_NO_DIRPAR"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ctx = D.OEDProblem(D.OEDSystem(ctor()), crit_cls(), alg=alg).context()
+        ks = ctx.kernel_stats(True)
+        assert (ks["time_parallel_max"] > 0) == (variant == "tp"), (variant, ks)
+        des = (stiff_designs if name == "chem6" else random_designs)(name, ctx.n_var, 40, 21)
+        res = []
+        for n in (1, 5, 40):
+            c, g, F = ctx.evaluate(des[:n])
+            i, v = ctx.argmin()
+            assert i == int(np.argmin(c)) and v == c[i]
+            res.append((c, g, F))
+        small = ctx.kernel_stats(True)["small_batch_launches"]
+        assert (small == 0) == (variant == "large")
+        if variant == "tp":                       # a NaN design poisons its own row only and never wins
+            bad = des[:5].copy(); bad[2, 3] = np.nan
+            c, g, F = ctx.evaluate(bad)
+            ok = np.array([0, 1, 3, 4])
+            assert np.isnan(c[2]) and np.array_equal(c[ok], res[1][0][ok]) and np.array_equal(g[ok], res[1][1][ok])
+            assert ctx.argmin()[0] == int(ok[np.argmin(c[ok])])
+        out[variant] = res
+        ctx.close()
+    for k in ("DYNOED_NO_TIMEPAR", "DYNOED_NO_DIRPAR"):
+        monkeypatch.delenv(k, raising=False)
+    orc = CppOracle(name, Oracle(ctor(), crit_id, method, list(sub) if not isinstance(sub, int) else sub))
+    oc, og, oF = orc.evaluate(des, grad=True)
+    den = np.maximum(np.abs(oc), np.max(np.abs(oF), axis=1))
+    for variant, res in out.items():
+        for (c, g, F), n in zip(res, (1, 5, 40)):
+            assert rel(F, oF[:n]) < RTOL and float(np.max(np.abs(c - oc[:n]) / den[:n])) < RTOL, (variant, n)
+            if not (variant == "large" and name == "lv_fishing" and method == "ros2"):   # large Rosenbrock batches: controls need DYNOED_GRAD controls mode
+                assert rel_rows(g, og[:n]) < RTOL, (variant, n)
+    for (c, g, F), (c2, g2, F2) in zip(out["tp"], out["dir"]):
+        assert rel(F, F2) < 1e-11 and rel_rows(g, g2) < 1e-10
 
 
 def test_small_batch_kernel_device_pointers_and_nan(built_library):
