@@ -389,6 +389,7 @@ struct Slot {
     int64_t cap = 0;   // designs
     // page-locked staging for PAGEABLE caller arrays (ordinary malloc / numpy / Julia arrays)
     double *h_designs = nullptr, *h_crit = nullptr, *h_grad = nullptr, *h_fim = nullptr;
+    double *hd_designs = nullptr, *hd_crit = nullptr, *hd_grad = nullptr, *hd_fim = nullptr;   // their device addresses
     int64_t hcap = 0;
     cudaEvent_t done = nullptr;
 };
@@ -1089,6 +1090,12 @@ static int ensure_staging(dynoed_ctx* ctx, Slot& s, int64_t cap) {
         CU(cudaMallocHost(&s.h_crit, sizeof(double) * cap));
         CU(cudaMallocHost(&s.h_grad, sizeof(double) * cap * ctx->n_var));
         CU(cudaMallocHost(&s.h_fim, sizeof(double) * cap * nF));
+        // device addresses of the staging, looked up once (the small zero-copy calls would pay four driver
+        // calls per evaluation otherwise)
+        CU(cudaHostGetDevicePointer((void**)&s.hd_designs, s.h_designs, 0));
+        CU(cudaHostGetDevicePointer((void**)&s.hd_crit, s.h_crit, 0));
+        CU(cudaHostGetDevicePointer((void**)&s.hd_grad, s.h_grad, 0));
+        CU(cudaHostGetDevicePointer((void**)&s.hd_fim, s.h_fim, 0));
         s.hcap = cap;
     }
     return DYNOED_OK;
@@ -1201,10 +1208,10 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
             if (!p || !pointer_attrs(p, &a)) return nullptr;
             return a.type == cudaMemoryTypeHost ? static_cast<double*>(a.devicePointer) : nullptr;
         };
-        zc_in = dev(staged ? s0.h_designs : designs);
-        zc_crit = dev(staged ? s0.h_crit : crit);
-        zc_grad = dev(staged ? s0.h_grad : grad);
-        zc_fim = fim ? dev(staged ? s0.h_fim : fim) : nullptr;
+        zc_in = staged ? s0.hd_designs : dev(designs);
+        zc_crit = staged ? s0.hd_crit : dev(crit);
+        zc_grad = staged ? s0.hd_grad : dev(grad);
+        zc_fim = !fim ? nullptr : staged ? s0.hd_fim : dev(fim);
         small_zc = zc_in && zc_crit && zc_grad && (!fim || zc_fim);
     }
     if (pipelined && !ctx->stream_dirty && !staged) {
