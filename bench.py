@@ -453,6 +453,16 @@ def main():
                         "steps": 130, "n_var": ctxs.n_var}
         sub["stiff_chem6_grad"]["grad_over_objective_cost"] = \
             sub["stiff_chem6_grad"]["ms_per_step"] / sub["stiff_chem6_objective"]["ms_per_step"]
+        # ... and ONE chem6 design through the blocking host call (the optimiser callback of the stiff
+        # configuration; time-parallel kernel with its per-step tables in global scratch)
+        us1 = np.ascontiguousarray(s_in[0][:1].cpu().numpy())
+        cs1, gs1 = np.empty(1), np.empty((1, ctxs.n_var))
+        for _ in range(5):
+            ctxs.eval_batch(us1, cs1, gs1, None)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            ctxs.eval_batch(us1, cs1, gs1, None)
+        sub["stiff_chem6_grad"]["single_design_host_call_us"] = (time.perf_counter() - t0) / 50 * 1e6
         ctxs.close()
         del s_in, s_c, s_g
     # BASELINE config 2: ONE design, objective + gradient (+ Hessian) through the blocking host call —
@@ -692,6 +702,7 @@ def main():
             line["stiff_chem6_frac_fp64"] = sub["stiff_chem6_grad"]["tflops"] / peak
             line["stiff_chem6_objective_designs_per_s"] = sub["stiff_chem6_objective"]["designs_per_s_per_gpu"]
             line["stiff_chem6_grad_over_objective_cost"] = sub["stiff_chem6_grad"]["grad_over_objective_cost"]
+            line["stiff_chem6_single_design_us"] = sub["stiff_chem6_grad"]["single_design_host_call_us"]
         if "single_design_host_call" in sub:
             line["single_design_objective_gradient_us"] = sub["single_design_host_call"]["objective_gradient_us"]
             line["single_design_hessian_us"] = sub["single_design_host_call"]["hessian_us"]

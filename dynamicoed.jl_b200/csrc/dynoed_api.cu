@@ -37,6 +37,8 @@ constexpr int kDirPar = 64;
 constexpr int kIc2 = 128;
 // method | kTimePar: time-parallel gradient kernel for the smallest batches (tp_eval_kernel, one CTA per design)
 constexpr int kTimePar = 256;
+// ... | kTpSpill: with its per-step tables in global scratch instead of shared memory
+constexpr int kTpSpill = 512;
 constexpr int kDirBlock = 32;
 // host calls of at most this many designs let the kernel read / write page-locked host memory directly
 constexpr int64_t kSmallZeroCopy = 16;
@@ -54,7 +56,8 @@ struct ModelEntry {
     bool ic2_ok;
     int ic2_gcol[kMaxIC];                 // G column that is d x / d ic_a
     int tp_nd;                            // tp_eval_kernel: adjoint lanes (nz + n_ctrl), 0 = kernel not built
-    size_t (*tp_smem)(int n_var, int n_intervals, int n_steps, int n_ctrl_values);
+    size_t (*tp_smem)(int n_var, int n_intervals, int n_steps, int n_ctrl_values, bool spill);
+    size_t (*tp_spill_bytes)(int n_steps);   // global scratch per design in spill mode
 };
 
 template <class K>
@@ -190,22 +193,28 @@ template <class M>
 constexpr bool tp_built() { return M::NZ + 1 <= 32; }
 
 template <class M>
-static size_t tp_smem_model(int n_var, int N, int n_steps, int ncv) { return tp_smem_bytes<M>(n_var, N, n_steps, ncv); }
+static size_t tp_smem_model(int n_var, int N, int n_steps, int ncv, bool spill) { return tp_smem_bytes<M>(n_var, N, n_steps, ncv, spill); }
+template <class M>
+static size_t tp_spill_model(int n_steps) { return sizeof(double) * tp_spill_doubles<M>(n_steps); }
 
+template <class M, class Stepper, bool SPILL>
+static cudaError_t launch_tp_one(const EvalParams& P, int grid, cudaStream_t st) {
+    const size_t smem = tp_smem_bytes<M>(P.n_var, P.n_intervals, P.n_steps, P.n_ctrl_values, SPILL);
+    static size_t smem_set[64] = {0};      // opt-in dynamic shared memory, raised once per device and size
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > smem_set[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(tp_eval_kernel<M, Stepper, SPILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        smem_set[dev & 63] = smem;
+    }
+    tp_eval_kernel<M, Stepper, SPILL><<<grid, kTpBlock, smem, st>>>(P);
+    return cudaGetLastError();
+}
 template <class M, class Stepper>
-static cudaError_t launch_tp(const EvalParams& P, int grid, cudaStream_t st) {
+static cudaError_t launch_tp(bool spill, const EvalParams& P, int grid, cudaStream_t st) {
     if constexpr (tp_built<M>()) {
-        const size_t smem = tp_smem_bytes<M>(P.n_var, P.n_intervals, P.n_steps, P.n_ctrl_values);
-        static size_t smem_set[64] = {0};      // opt-in dynamic shared memory, raised once per device and size
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (smem > smem_set[dev & 63]) {
-            cudaError_t e = cudaFuncSetAttribute(tp_eval_kernel<M, Stepper>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            smem_set[dev & 63] = smem;
-        }
-        tp_eval_kernel<M, Stepper><<<grid, kTpBlock, smem, st>>>(P);
-        return cudaGetLastError();
+        return spill ? launch_tp_one<M, Stepper, true>(P, grid, st) : launch_tp_one<M, Stepper, false>(P, grid, st);
     } else {
         return cudaErrorInvalidDeviceFunction;
     }
@@ -215,12 +224,13 @@ template <class M>
 static cudaError_t launch_model(int method, bool grad, bool uc, bool pdl, const EvalParams& P, int grid, int block,
                                 size_t smem, cudaStream_t st) {
     if (method & kTimePar) {
+        const bool sp = (method & kTpSpill) != 0;
         switch (method & 15) {
-            case DYNOED_RK4: return launch_tp<M, ExplicitStepper<TabRK4>>(P, grid, st);
-            case DYNOED_TSIT5: return launch_tp<M, ExplicitStepper<TabTsit5>>(P, grid, st);
-            case DYNOED_ROS2: return launch_tp<M, RosenbrockStepper<TabROS2>>(P, grid, st);
-            case DYNOED_ROS3P: return launch_tp<M, RosenbrockStepper<TabROS3P>>(P, grid, st);
-            default: return launch_tp<M, RosenbrockStepper<TabRODAS3>>(P, grid, st);
+            case DYNOED_RK4: return launch_tp<M, ExplicitStepper<TabRK4>>(sp, P, grid, st);
+            case DYNOED_TSIT5: return launch_tp<M, ExplicitStepper<TabTsit5>>(sp, P, grid, st);
+            case DYNOED_ROS2: return launch_tp<M, RosenbrockStepper<TabROS2>>(sp, P, grid, st);
+            case DYNOED_ROS3P: return launch_tp<M, RosenbrockStepper<TabROS3P>>(sp, P, grid, st);
+            default: return launch_tp<M, RosenbrockStepper<TabRODAS3>>(sp, P, grid, st);
         }
     }
     if (method & kDirPar) {
@@ -331,6 +341,7 @@ static ModelEntry make_entry() {
 
     e.tp_nd = tp_built<M>() ? M::NZ + M::NCTRL : 0;
     e.tp_smem = &tp_smem_model<M>;
+    e.tp_spill_bytes = &tp_spill_model<M>;
     e.launch = &launch_model<M>;
     e.attrs = &attrs_model<M>;
     e.info_gain = &info_gain_model<M>;
@@ -466,6 +477,7 @@ struct dynoed_ctx {
     int dir_nl = 1;                    // its lanes per design: 1 + unknown ICs + control values
     int64_t dir_max_lanes = 0;
     bool tp_ok = false;                // time-parallel kernel usable for the smallest gradient batches
+    bool tp_spill = false;             // ... with its per-step tables in global scratch (they exceed shared memory)
     int64_t tp_max_n = 0;
     int64_t call_n = 0;                // designs of the call being served
     int kidx_req = 1;                  // gradient kernel requested by the current call (1 adjoint/Rosenbrock, 2 forward-only)
@@ -614,7 +626,8 @@ static int grid_for(const dynoed_ctx* ctx, int64_t n, int kidx) {
 
 // scratch of one gradient launch of n designs
 static size_t traj_need(const dynoed_ctx* ctx, int64_t n, int kidx) {
-    if (tp_eligible(ctx, n, kidx)) return 0;      // everything lives in shared memory
+    if (tp_eligible(ctx, n, kidx))                // everything lives in shared memory unless the tables spill
+        return ctx->tp_spill ? (size_t)n * ctx->model->tp_spill_bytes(ctx->n_steps) : 0;
     if (dir_eligible(ctx, n, kidx))
         return sizeof(double) * (size_t)n * ctx->n_intervals * ctx->model->info.n_obs * ctx->model->info.nF;
     return traj_bytes_for(ctx, grid_for(ctx, n, kidx), kidx);
@@ -784,8 +797,10 @@ int dynoed_create(const dynoed_problem_desc* d, int device, dynoed_ctx** out) {
         // each design has an SM of its own; at two CTAs per SM the cheap models lose
         ctx->tp_max_n = (int64_t)prop.multiProcessorCount;
         if (const char* tn = getenv("DYNOED_TIMEPAR_MAX_N")) ctx->tp_max_n = std::max(0, atoi(tn));
+        const bool fits = m->tp_smem(d->n_var, N, ctx->n_steps, nvals, false) + 2048 <= (size_t)prop.sharedMemPerBlockOptin;
+        ctx->tp_spill = !fits || getenv("DYNOED_TIMEPAR_SPILL");
         ctx->tp_ok = ctx->dir_ok && !getenv("DYNOED_NO_TIMEPAR") && m->tp_nd > 0 &&
-                     m->tp_smem(d->n_var, N, ctx->n_steps, nvals) + 2048 <= (size_t)prop.sharedMemPerBlockOptin;
+                     (fits || m->tp_smem(d->n_var, N, ctx->n_steps, nvals, true) + 2048 <= (size_t)prop.sharedMemPerBlockOptin);
     }
     ctx->zero_copy = !getenv("DYNOED_NO_ZEROCOPY");
     ctx->host_staging = !getenv("DYNOED_NO_STAGING");
@@ -1005,7 +1020,7 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
         }
         CU(cudaEventRecord(ctx->ev_k0, st));
     }
-    CU(ctx->model->launch(method_code(ctx, cur.kidx) | (timepar ? kTimePar : dirpar ? kDirPar : 0), grad != nullptr,
+    CU(ctx->model->launch(method_code(ctx, cur.kidx) | (timepar ? (ctx->tp_spill ? kTimePar | kTpSpill : kTimePar) : dirpar ? kDirPar : 0), grad != nullptr,
                           ctx->ucoef, pdl, P, grid, ctx->tile, smem_bytes(ctx, cur.kidx), st));
     if (ctx->profiling) { CU(cudaEventRecord(ctx->ev_k1, st)); ctx->ev_pending = true; }
     cur.serial = stream_new_serial(st);
@@ -1263,7 +1278,7 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
             P.use_tma = (!dirpar && ((size_t)ctx->tile * ctx->n_var * 8) % 16 == 0) ? 1 : 0;
             P.index_base = off;
             cudaStream_t run_stream = small_zc ? ctx->stream : s.stream;
-            CU(ctx->model->launch(method_code(ctx, kidx) | (timepar ? kTimePar : dirpar ? kDirPar : 0), g, ctx->ucoef, false, P,
+            CU(ctx->model->launch(method_code(ctx, kidx) | (timepar ? (ctx->tp_spill ? kTimePar | kTpSpill : kTimePar) : dirpar ? kDirPar : 0), g, ctx->ucoef, false, P,
                                   grid, ctx->tile, smem_bytes(ctx, kidx), run_stream));
             ctx->launches++;
             ctx->dir_launches += dirpar ? 1 : 0;

@@ -1330,18 +1330,25 @@ constexpr int kTpBlock = DYNOED_TP_BLOCK;
 #endif
 constexpr int kTpMaxChunks = 16;
 
+// SPILL: the two large per-step tables (Jacobian columns, quadrature derivatives) live in the launch's global
+// scratch (L2) instead of shared memory — models / grids whose tables exceed one SM's shared memory
+// (chem6 on a 130-step grid: 18 x 18 columns per step; LV with 16 substeps per interval).
 template <class M>
-__host__ __device__ inline size_t tp_smem_bytes(int n_var, int N, int n_steps, int n_ctrl_values) {
+__host__ __device__ inline size_t tp_spill_doubles(int n_steps) {
+    return (size_t)n_steps * (M::NZ + M::NCTRL) * (M::NZ + M::NOBS * M::NF);
+}
+template <class M>
+__host__ __device__ inline size_t tp_smem_bytes(int n_var, int N, int n_steps, int n_ctrl_values, bool spill) {
     constexpr int NZ = M::NZ, NQ = M::NOBS * M::NF, ND = M::NZ + M::NCTRL;
     size_t dbl = (size_t)n_var + 3 * (size_t)n_steps + (size_t)(n_steps + 1) * NZ + (size_t)n_steps * NQ +
-                 (size_t)N * NQ + (size_t)n_steps * ND * (NZ + NQ + 1) + M::NF + 2 +
+                 (size_t)N * NQ + (spill ? 0 : tp_spill_doubles<M>(n_steps)) + (size_t)n_steps * ND + M::NF + 2 +
                  (size_t)kTpMaxChunks * (NZ + 1) * NZ + (size_t)(kTpMaxChunks + 1) * NZ +
                  (size_t)kTpMaxChunks * (n_ctrl_values > 0 ? n_ctrl_values : 1);
     size_t ints = (size_t)(M::NCTRL + M::NOBS) * N + (N + 1) + n_steps;
     return dbl * sizeof(double) + ints * sizeof(int) + 16;
 }
 
-template <class M, class Stepper>
+template <class M, class Stepper, bool SPILL>
 __global__ void __launch_bounds__(kTpBlock, 1) tp_eval_kernel(const EvalParams P) {
     constexpr int NX = M::NX, NP = M::NP, NZ = M::NZ, NF = M::NF, NOBS = M::NOBS, NCTRL = M::NCTRL;
     constexpr int NCU = NCTRL > 0 ? NCTRL : 1, NQ = NOBS * NF, ND = NZ + NCTRL;
@@ -1358,6 +1365,7 @@ __global__ void __launch_bounds__(kTpBlock, 1) tp_eval_kernel(const EvalParams P
     DYNOED_TP_MARK(0)
     __shared__ int tp_prog;            // steps whose start state x_k is in shared memory (phase 1 -> phase 1b)
     if (threadIdx.x == 0) tp_prog = 0;
+    if constexpr (SPILL) scratch_acquire(P);      // the spilled tables belong to the scratch set
 
     extern __shared__ __align__(16) double tp_sm[];
     double* row = tp_sm;
@@ -1367,9 +1375,10 @@ __global__ void __launch_bounds__(kTpBlock, 1) tp_eval_kernel(const EvalParams P
     double* zs = s_ih + n_steps;                         // [n_steps + 1][NZ] state at every step start
     double* pqs = zs + (size_t)(n_steps + 1) * NZ;       // [n_steps][NQ]     quadrature increment of every step
     double* pq = pqs + (size_t)n_steps * NQ;             // [N][NQ]           interval quadratures
-    double* jc = pq + (size_t)N * NQ;                    // [n_steps][ND][NZ] step Jacobian columns
+    double* big = SPILL ? P.traj + (size_t)blockIdx.x * tp_spill_doubles<M>(n_steps) : pq + (size_t)N * NQ;
+    double* jc = big;                                    // [n_steps][ND][NZ] step Jacobian columns
     double* dpq = jc + (size_t)n_steps * ND * NZ;        // [n_steps][ND][NQ] derivative of the step's quadrature increment
-    double* sc = dpq + (size_t)n_steps * ND * NQ;        // [n_steps][ND]     ... contracted with Lambda and the weights
+    double* sc = SPILL ? pq + (size_t)N * NQ : dpq + (size_t)n_steps * ND * NQ;   // [n_steps][ND] ... contracted with Lambda and the weights
     double* ls = sc + (size_t)n_steps * ND;              // [NF] (+ trace term)
     double* comp = ls + NF + 2;                          // [chunks][NZ + 1][NZ] columns of [A_c | b_c]
     double* lamb = comp + (size_t)kTpMaxChunks * (NZ + 1) * NZ;          // [chunks + 1][NZ] lambda at chunk boundaries
@@ -1761,8 +1770,8 @@ __global__ void __launch_bounds__(kTpBlock, 1) tp_eval_kernel(const EvalParams P
 #endif
 
     // ---- arg-min record of this CTA (= this design); the last CTA reduces the batch.  Only these record
-    //      slots belong to the scratch set, so its guard is taken here, after the work ----
-    scratch_acquire(P);
+    //      slots belong to the scratch set (unless tables are spilled), so its guard is taken here, after the work ----
+    if constexpr (!SPILL) scratch_acquire(P);
     __shared__ int tp_last;
     if (tid == 0) {
         P.part_val[P.part_base + blockIdx.x] = best_val;

@@ -8,7 +8,9 @@ from dynamicoed.jl_b200 import models
 CASES = (("lv_fishing", models.lotka_volterra_fishing, D.FisherDCriterion, D.RK4(4)),
          ("lv_fishing", models.lotka_volterra_fishing, D.FisherDCriterion, D.Tsit5(4)),
          ("lv_ic", models.lotka_volterra_ic, D.FisherDCriterion, D.RK4(4)),
-         ("lv_ic", models.lotka_volterra_ic, D.ACriterion, D.ROS3P(8)))
+         ("lv_ic", models.lotka_volterra_ic, D.ACriterion, D.ROS3P(8)),
+         ("lv_fishing", models.lotka_volterra_fishing, D.FisherDCriterion, D.RK4(16)),          # tables spill to global scratch
+         ("chem6", models.chem6, D.FisherECriterion, D.ROS3P(edges=D.graded_edges(10, 30, 1e-6, 6))))
 for name, ctor, crit, alg in CASES:
     ctxs = {}
     for mode in ("tp", "dir"):
@@ -18,7 +20,7 @@ for name, ctor, crit, alg in CASES:
     nv = ctxs["tp"].n_var
     print(name, type(alg).__name__, "time_parallel_max", ctxs["tp"].kernel_stats(True)["time_parallel_max"],
           ctxs["dir"].kernel_stats(True)["time_parallel_max"], flush=True)
-    for n in (1, 143, 296):
+    for n in (1, 143):
         rng = np.random.default_rng(1)
         des = rng.random((n, nv)); des[:, -1] = 0.5
         if name == "chem6": des[:, :] = 0.3 + 0.4 * rng.random((n, nv))

@@ -1209,7 +1209,8 @@ def test_small_batches_use_the_direction_parallel_kernel_and_match(name, method,
 
 @pytest.mark.parametrize("name,method,sub", [("lv_fishing", "rk4", 4), ("lv_fishing", "tsit5", 2), ("lv_ic", "rk4", 4),
                                              ("lv_ic", "ros3p", 8), ("lv_fishing", "ros2", 4),
-                                             ("chem6", "rodas3", D.graded_edges(10, 8, 1e-6, 3))])
+                                             ("chem6", "rodas3", D.graded_edges(10, 8, 1e-6, 3)),
+                                             ("chem6", "ros3p", D.graded_edges(10, 30, 1e-6, 6))])   # tables spill to global scratch
 def test_time_parallel_kernel_matches_the_other_gradient_kernels_and_the_oracle(name, method, sub, built_library, monkeypatch):
     """The smallest gradient batches run one CTA per design (tp_eval_kernel: x-only sweep, per-step affine
     maps, chunked chains).  Same numbers as the direction-parallel kernel (DYNOED_NO_TIMEPAR), the large-batch
@@ -1221,14 +1222,15 @@ def test_time_parallel_kernel_matches_the_other_gradient_kernels_and_the_oracle(
     alg = algs[method](edges=sub) if not isinstance(sub, int) else algs[method](sub)
     crit_cls, crit_id = (D.FisherECriterion, 2) if name == "chem6" else (D.ACriterion, 3)
     out = {}
-    for variant, env in (("tp", {}), ("dir", {"DYNOED_NO_TIMEPAR": "1"}), ("large", {"DYNOED_NO_DIRPAR": "1"})):
-        for k in ("DYNOED_NO_TIMEPAR", "DYNOED_NO_DIRPAR"):
+    for variant, env in (("tp", {}), ("tp_spill", {"DYNOED_TIMEPAR_SPILL": "1"}), ("dir", {"DYNOED_NO_TIMEPAR": "1"}),
+                         ("large", {"DYNOED_NO_DIRPAR": "1"})):
+        for k in ("DYNOED_NO_TIMEPAR", "DYNOED_NO_DIRPAR", "DYNOED_TIMEPAR_SPILL"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         ctx = D.OEDProblem(D.OEDSystem(ctor()), crit_cls(), alg=alg).context()
         ks = ctx.kernel_stats(True)
-        assert (ks["time_parallel_max"] > 0) == (variant == "tp"), (variant, ks)
+        assert (ks["time_parallel_max"] > 0) == variant.startswith("tp"), (variant, ks)
         des = (stiff_designs if name == "chem6" else random_designs)(name, ctx.n_var, 40, 21)
         res = []
         for n in (1, 5, 40):
@@ -1246,8 +1248,10 @@ def test_time_parallel_kernel_matches_the_other_gradient_kernels_and_the_oracle(
             assert ctx.argmin()[0] == int(ok[np.argmin(c[ok])])
         out[variant] = res
         ctx.close()
-    for k in ("DYNOED_NO_TIMEPAR", "DYNOED_NO_DIRPAR"):
+    for k in ("DYNOED_NO_TIMEPAR", "DYNOED_NO_DIRPAR", "DYNOED_TIMEPAR_SPILL"):
         monkeypatch.delenv(k, raising=False)
+    for (c, g, F), (c2, g2, F2) in zip(out["tp"], out["tp_spill"]):   # same algorithm, tables in global scratch (another
+        assert rel(c, c2) < 1e-12 and rel(F, F2) < 1e-12 and rel_rows(g, g2) < 1e-11   # instantiation: FMA contraction may differ)
     orc = CppOracle(name, Oracle(ctor(), crit_id, method, list(sub) if not isinstance(sub, int) else sub))
     oc, og, oF = orc.evaluate(des, grad=True)
     den = np.maximum(np.abs(oc), np.max(np.abs(oF), axis=1))
