@@ -480,6 +480,7 @@ struct dynoed_ctx {
     bool tp_spill = false;             // ... with its per-step tables in global scratch (they exceed shared memory)
     int64_t tp_max_n = 0;
     int64_t call_n = 0;                // designs of the call being served
+    bool call_xgrid = false;           // ... and it writes the trajectory (objective-only kernels of the large-batch path)
     int kidx_req = 1;                  // gradient kernel requested by the current call (1 adjoint/Rosenbrock, 2 forward-only)
     int parity = 0;                    // scratch set of the NEXT device-path launch
     int last_parity = 0;               // scratch set that holds the most recent batch's arg-min
@@ -616,8 +617,16 @@ static bool tp_eligible(const dynoed_ctx* ctx, int64_t n, int kidx) {
     return ctx->tp_ok && dir_eligible(ctx, n, kidx) && std::max(n, ctx->call_n) <= ctx->tp_max_n;
 }
 
+// ... and the smallest OBJECTIVE-ONLY calls too (the line-search evaluations of an optimiser): same kernel
+// without its dual / adjoint phases, reading and writing page-locked host memory directly for host calls
+// instead of three small DMA transfers.  Not with spilled tables (no scratch is sized for objective calls).
+static bool tp_obj_eligible(const dynoed_ctx* ctx, int64_t n, int kidx) {
+    return kidx == 0 && ctx->tp_ok && !ctx->tp_spill && !ctx->call_xgrid && n > 0 &&
+           std::max(n, ctx->call_n) <= ctx->tp_max_n;
+}
+
 static int grid_for(const dynoed_ctx* ctx, int64_t n, int kidx) {
-    if (tp_eligible(ctx, n, kidx)) return (int)n;
+    if (tp_eligible(ctx, n, kidx) || tp_obj_eligible(ctx, n, kidx)) return (int)n;
     if (dir_eligible(ctx, n, kidx)) return (int)((n * ctx->dir_nl + kDirBlock - 1) / kDirBlock);
     const int64_t ntiles = (n + ctx->tile - 1) / ctx->tile;
     const int64_t resident = (int64_t)ctx->sm_count * std::max(ctx->bps[kidx], 1);
@@ -992,10 +1001,11 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
     dynoed_ctx::Prev cur;
     cur.kidx = grad ? ctx->kidx_req : 0;
     const bool dirpar = grad && !xgrid && dir_eligible(ctx, n, cur.kidx);
-    const bool timepar = dirpar && tp_eligible(ctx, n, cur.kidx);
-    cur.valid = xgrid == nullptr && !dirpar;
-    if (dirpar) P.use_tma = 0;
-    cur.full = !dirpar && grid == ctx->sm_count * std::max(ctx->bps[cur.kidx], 1);
+    const bool tpobj = !grad && !xgrid && tp_obj_eligible(ctx, n, cur.kidx);
+    const bool timepar = (dirpar && tp_eligible(ctx, n, cur.kidx)) || tpobj;
+    cur.valid = xgrid == nullptr && !dirpar && !tpobj;
+    if (dirpar || tpobj) P.use_tma = 0;
+    cur.full = !dirpar && !tpobj && grid == ctx->sm_count * std::max(ctx->bps[cur.kidx], 1);
     cur.stream = st;
     cur.in0 = (const char*)designs; cur.in1 = cur.in0 + sizeof(double) * n * ctx->n_var;
     cur.out0[0] = (const char*)crit; cur.out1[0] = cur.out0[0] + sizeof(double) * n;
@@ -1028,7 +1038,7 @@ static int launch_device(dynoed_ctx* ctx, const double* designs, int64_t n, doub
     ctx->stream_dirty = true;
     ctx->launches++;
     ctx->pdl_launches += pdl ? 1 : 0;
-    ctx->dir_launches += dirpar ? 1 : 0;
+    ctx->dir_launches += (dirpar || tpobj) ? 1 : 0;
     ctx->tp_launches += timepar ? 1 : 0;
     return DYNOED_OK;
 }
@@ -1039,6 +1049,7 @@ static int eval_device(dynoed_ctx* ctx, const double* designs, int64_t n, double
     if (g && xgrid) return fail(ctx, DYNOED_EUNSUPPORTED, "the trajectory is written by the objective-only kernels");
     const int kidx = g ? ctx->kidx_req : 0;
     ctx->call_n = n;
+    ctx->call_xgrid = xgrid != nullptr;
     const int grid = grid_for(ctx, n, kidx);
     const int par = ctx->parity;
     if (g) {
@@ -1131,6 +1142,7 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
     const int nF = ctx->model->info.nF;
     const bool g = grad != nullptr;
     ctx->call_n = n;
+    ctx->call_xgrid = false;
     // Chunk schedule: host_chunks equal chunks (default 8).  Measured on B200 / PCIe Gen5: 4..16 equal
     // chunks and a ramped schedule (small chunks at both ends: 1,1,2,4,8,8,4,2,1,1 thirty-seconds,
     // DYNOED_HOST_CHUNKS=0) all land within 5 % of each other at 71-75 % of the rate of two
@@ -1213,6 +1225,18 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
     // runs on the ctx stream itself: no slot stream, no cross-stream events (four driver calls less).
     bool small_zc = false;
     double *zc_in = nullptr, *zc_crit = nullptr, *zc_grad = nullptr, *zc_fim = nullptr;
+    if (!g && nchunks == 1 && n <= kSmallZeroCopy && ctx->zero_copy && !pipelined && tp_obj_eligible(ctx, n, kidx)) {
+        Slot& s0 = ctx->slots[0];
+        auto dev = [](const void* p) -> double* {
+            cudaPointerAttributes a;
+            if (!p || !pointer_attrs(p, &a)) return nullptr;
+            return a.type == cudaMemoryTypeHost ? static_cast<double*>(a.devicePointer) : nullptr;
+        };
+        zc_in = staged ? s0.hd_designs : dev(designs);
+        zc_crit = staged ? s0.hd_crit : dev(crit);
+        zc_fim = !fim ? nullptr : staged ? s0.hd_fim : dev(fim);
+        small_zc = zc_in && zc_crit && (!fim || zc_fim);
+    }
     if (g && nchunks == 1 && n <= kSmallZeroCopy && ctx->zero_copy && !pipelined && dir_eligible(ctx, n, kidx) &&
         (tp_eligible(ctx, n, kidx) || ((size_t)(kDirBlock + ctx->dir_nl - 1) / ctx->dir_nl + 1) *
                 (ctx->n_var + (size_t)ctx->n_intervals * ctx->model->info.n_obs * ctx->model->info.nF) * sizeof(double) +
@@ -1264,7 +1288,7 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
             P.designs = s.d_designs; P.crit = crit_map ? crit_map + off : s.d_crit; P.grad = !g ? nullptr : grad_map ? grad_map + off * ctx->n_var : s.d_grad;
             P.fim = !fim ? nullptr : fim_map ? fim_map + off * nF : s.d_fim;
             if (small_zc) {   // the kernel reads the rows from, and stores every result into, page-locked host memory
-                P.designs = zc_in; P.crit = zc_crit; P.grad = zc_grad; P.fim = fim ? zc_fim : nullptr;
+                P.designs = zc_in; P.crit = zc_crit; P.grad = g ? zc_grad : nullptr; P.fim = fim ? zc_fim : nullptr;
             }
             P.xgrid = nullptr; P.traj = s.traj; P.n = cnt;
             P.part_val = ctx->part_val[par]; P.part_idx = ctx->part_idx[par];
@@ -1274,14 +1298,15 @@ static int eval_host(dynoed_ctx* ctx, const double* designs, int64_t n, double* 
             set_scratch_params(ctx, P, par, kidx);
             part_base += grid;
             const bool dirpar = g && dir_eligible(ctx, cnt, kidx);
-            const bool timepar = dirpar && tp_eligible(ctx, cnt, kidx);
-            P.use_tma = (!dirpar && ((size_t)ctx->tile * ctx->n_var * 8) % 16 == 0) ? 1 : 0;
+            const bool tpobj = !g && tp_obj_eligible(ctx, cnt, kidx);
+            const bool timepar = (dirpar && tp_eligible(ctx, cnt, kidx)) || tpobj;
+            P.use_tma = (!dirpar && !tpobj && ((size_t)ctx->tile * ctx->n_var * 8) % 16 == 0) ? 1 : 0;
             P.index_base = off;
             cudaStream_t run_stream = small_zc ? ctx->stream : s.stream;
             CU(ctx->model->launch(method_code(ctx, kidx) | (timepar ? (ctx->tp_spill ? kTimePar | kTpSpill : kTimePar) : dirpar ? kDirPar : 0), g, ctx->ucoef, false, P,
                                   grid, ctx->tile, smem_bytes(ctx, kidx), run_stream));
             ctx->launches++;
-            ctx->dir_launches += dirpar ? 1 : 0;
+            ctx->dir_launches += (dirpar || tpobj) ? 1 : 0;
             ctx->tp_launches += timepar ? 1 : 0;
             double* o_crit = staged ? s.h_crit : crit + off;
             double* o_grad = staged ? s.h_grad : (g ? grad + off * ctx->n_var : nullptr);

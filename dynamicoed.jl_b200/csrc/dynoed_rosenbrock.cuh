@@ -1543,9 +1543,12 @@ __global__ void __launch_bounds__(kTpBlock, 1) tp_eval_kernel(const EvalParams P
     DYNOED_TP_MARK(3)
 
     // ---- phase 2: every step on its own, one dual direction per task ----
+    // (objective-only call: one unseeded task per step, for its quadrature increment alone)
+    const bool want_grad = P.grad != nullptr;
+    const int nd_run = want_grad ? ND : 1;
     {
-        for (int task = tid; task < n_steps * ND; task += blockDim.x) {
-            const int k = task / ND, m = task - k * ND;
+        for (int task = tid; task < n_steps * nd_run; task += blockDim.x) {
+            const int k = task / nd_run, m = want_grad ? task - k * nd_run : -1;
             const int j = siv[k];
             T z[NZ], u[NCU], c[M::NCONST], Pq[NQ];
 #pragma unroll
@@ -1562,11 +1565,13 @@ __global__ void __launch_bounds__(kTpBlock, 1) tp_eval_kernel(const EvalParams P
 #pragma unroll
             for (int a = 0; a < NQ; ++a) Pq[a] = T(0.0);
             Stepper::template step<M, T>(s_t[k], s_h[k], s_ih[k], z, Pq, u, th, c);
+            if (want_grad) {
 #pragma unroll
-            for (int a = 0; a < NZ; ++a) jc[(size_t)task * NZ + a] = z[a].d[0];
+                for (int a = 0; a < NZ; ++a) jc[(size_t)task * NZ + a] = z[a].d[0];
 #pragma unroll
-            for (int a = 0; a < NQ; ++a) dpq[(size_t)task * NQ + a] = Pq[a].d[0];
-            if (m == 0) {
+                for (int a = 0; a < NQ; ++a) dpq[(size_t)task * NQ + a] = Pq[a].d[0];
+            }
+            if (m <= 0) {
 #pragma unroll
                 for (int a = 0; a < NQ; ++a) pqs[(size_t)k * NQ + a] = Pq[a].v;
             }
@@ -1625,7 +1630,7 @@ __global__ void __launch_bounds__(kTpBlock, 1) tp_eval_kernel(const EvalParams P
         }
     }
     DYNOED_TP_SYNC()
-    for (int task = tid; task < n_steps * ND; task += blockDim.x) {
+    for (int task = tid; want_grad && task < n_steps * ND; task += blockDim.x) {
         const int j = siv[task / ND];
         double s = 0.0;
 #pragma unroll
@@ -1646,7 +1651,7 @@ __global__ void __launch_bounds__(kTpBlock, 1) tp_eval_kernel(const EvalParams P
     constexpr int LG = NC <= 8 ? 8 : NC <= 16 ? 16 : 32;         // lanes per chunk
     constexpr int CPW = 32 / LG;                                 // chunks per warp
     static_assert(NC <= 32, "one lane per column of a chunk map");
-    const int nchunk = min(min(kTpMaxChunks, CPW * (int)(blockDim.x >> 5)), n_steps);
+    const int nchunk = want_grad ? min(min(kTpMaxChunks, CPW * (int)(blockDim.x >> 5)), n_steps) : 0;   // 0: nothing to do
     {   // (1) compose the steps of every chunk: column q of A_c is the chain applied to e_q, b_c starts from 0
         const int c = warp * CPW + lane / LG, q = lane % LG;
         if (c < nchunk && q < NC) {
@@ -1673,7 +1678,7 @@ __global__ void __launch_bounds__(kTpBlock, 1) tp_eval_kernel(const EvalParams P
         }
     }
     DYNOED_TP_SYNC()
-    if (warp == 0) {   // (2) chain the chunk maps from the end: lamb[c + 1] = lambda at the upper end of chunk c
+    if (warp == 0 && want_grad) {   // (2) chain the chunk maps from the end: lamb[c + 1] = lambda at the upper end of chunk c
         double lam_m = 0.0;
         for (int c = nchunk - 1; c >= 0; --c) {
             if (lane < NZ) lamb[(size_t)(c + 1) * NZ + lane] = lam_m;
@@ -1691,7 +1696,7 @@ __global__ void __launch_bounds__(kTpBlock, 1) tp_eval_kernel(const EvalParams P
         if constexpr (M::NIC > 0) {
             if (lane < M::NIC) grow[P.ic_off + lane] = lamb[M::ic_state(lane)];
         }
-    } else if (warp == 1) {   // d/dw from the interval quadratures, d/dtau
+    } else if (warp == 1 && want_grad) {   // d/dw from the interval quadratures, d/dtau
         if (lane < NOBS) {
             const int i = lane;
             double wb = 0.0;
@@ -1745,7 +1750,7 @@ __global__ void __launch_bounds__(kTpBlock, 1) tp_eval_kernel(const EvalParams P
             }
         }
         DYNOED_TP_SYNC()
-        for (int i = tid; i < P.n_ctrl_values; i += blockDim.x) {   // later chunks first, as the recursion runs
+        for (int i = tid; want_grad && i < P.n_ctrl_values; i += blockDim.x) {   // later chunks first, as the recursion runs
             double acc = 0.0;
             for (int c = nchunk - 1; c >= 0; --c) acc += part[(size_t)c * ncv + i];
             int rest = i, off = -1;

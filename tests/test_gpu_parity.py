@@ -1240,6 +1240,14 @@ def test_time_parallel_kernel_matches_the_other_gradient_kernels_and_the_oracle(
             res.append((c, g, F))
         small = ctx.kernel_stats(True)["small_batch_launches"]
         assert (small == 0) == (variant == "large")
+        if variant.startswith("tp"):              # objective-only calls of this size: same kernel without its gradient phases
+            c0, g0, F0 = ctx.evaluate(des[:5], grad=False)
+            assert g0 is None and rel(c0, res[1][0]) < 1e-12 and rel(F0, res[1][2]) < 1e-12
+            i0, v0 = ctx.argmin()
+            assert i0 == int(np.argmin(c0)) and v0 == c0[i0]
+            if variant == "tp" and not (name == "chem6" and method == "ros3p"):     # (not with spilled tables)
+                assert ctx.kernel_stats(True)["small_batch_launches"] == small + 1
+                assert np.array_equal(c0, res[1][0]) and np.array_equal(F0, res[1][2])
         if variant == "tp":                       # a NaN design poisons its own row only and never wins
             bad = des[:5].copy(); bad[2, 3] = np.nan
             c, g, F = ctx.evaluate(bad)
