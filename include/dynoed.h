@@ -122,7 +122,8 @@ typedef struct dynoed_kernel_stats {
     int64_t overlapped_launches; /* launches allowed to start while their predecessor drained */
     int64_t small_batch_launches; /* gradient launches served by the small-batch kernels (direction- or time-parallel) */
     int32_t small_batch_max;   /* largest call (designs) that kernel takes; 0 = never */
-    int32_t time_parallel_max; /* largest call (designs) that runs one CTA per design (tp_eval_kernel); 0 = never */
+    int32_t time_parallel_max; /* largest call (designs) that runs one CTA per design (tp_eval_kernel; gradient
+                                  calls, and objective-only calls unless its tables spill); 0 = never */
 } dynoed_kernel_stats;
 
 int dynoed_abi_version(void);

@@ -1329,7 +1329,7 @@ def test_multistart_sweep_device_side_selection(built_library):
     assert out2["index"] == k2 and out2["value"] == float(crit[k2])
     c_chk = torch.empty(64, dtype=torch.float64, device="cuda")
     ctx.eval_batch(des[k2:k2 + 64].contiguous(), c_chk, None, None)
-    assert float(c_chk[0]) == out2["value"]
+    assert abs(float(c_chk[0]) - out2["value"]) <= 1e-12 * max(1.0, abs(out2["value"]))   # (64 designs: the time-parallel kernel)
     ctx.own_stream()
 
 
