@@ -40,3 +40,18 @@ def test_chunking_does_not_change_the_result_beyond_rounding():
         got = tp_restatement.evaluate(orc, des, n_chunks=nch)
         assert abs(got[0] - ref[0]) <= 1e-13 * abs(ref[0]) and np.max(np.abs(got[2] - ref[2])) <= 1e-13 * np.max(np.abs(ref[2]))
         assert np.max(np.abs(got[1] - ref[1])) <= 1e-12 * np.max(np.abs(ref[1]))
+
+
+def test_time_parallel_algorithm_on_a_graded_grid():
+    """Per-interval substep edges (step sizes differ from step to step): the per-step (t, h) travel along the
+    batch axis of the oracle's step function."""
+    N = 10
+    edges = [np.array([0.0, 0.1, 0.35, 1.0])] + [np.array([0.0, 0.5, 1.0])] * (N - 1)
+    orc = Oracle(models.lotka_volterra_ic(), 0, "rk4", edges)
+    assert orc.N == N and orc.uniform is None
+    des = np.random.Generator(np.random.Philox(11)).random((1, orc.n_var))
+    oc, og, oF = orc.evaluate(des, grad=True)
+    obj, g, F, diag = tp_restatement.evaluate(orc, des[0], n_chunks=4)
+    assert diag["G_chain_vs_sweep"] < 1e-12 and abs(obj - oc[0]) <= 1e-11 * max(1.0, abs(oc[0]))
+    assert np.max(np.abs(g - og[0])) <= 1e-10 * np.max(np.abs(og[0]))
+
