@@ -189,8 +189,10 @@ static cudaError_t launch_dir(const EvalParams& P0, int grid, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// only models that have something besides w and tau to differentiate ever run the kernel (see dir_ok):
+// the others do not instantiate it
 template <class M>
-constexpr bool tp_built() { return M::NZ + 1 <= 32; }
+constexpr bool tp_built() { return M::NZ + 1 <= 32 && M::NIC + M::NCTRL > 0; }
 
 template <class M>
 static size_t tp_smem_model(int n_var, int N, int n_steps, int ncv, bool spill) { return tp_smem_bytes<M>(n_var, N, n_steps, ncv, spill); }
