@@ -120,8 +120,9 @@ typedef struct dynoed_kernel_stats {
     double flops_per_design_eval, flops_per_design_grad; /* algorithmic, FMA = 2 */
     double bytes_per_design;   /* algorithmic HBM bytes: n_var in + (1 + n_var + nF) out */
     int64_t overlapped_launches; /* launches allowed to start while their predecessor drained */
-    int64_t small_batch_launches; /* gradient launches served by the small-batch kernels (direction- or time-parallel) */
-    int32_t small_batch_max;   /* largest call (designs) that kernel takes; 0 = never */
+    int64_t small_batch_launches; /* launches served by the small-batch kernels (direction- or time-parallel;
+                                     objective-only calls of the time-parallel kernel included) */
+    int32_t small_batch_max;   /* largest gradient call (designs) the small-batch kernels take; 0 = never */
     int32_t time_parallel_max; /* largest call (designs) that runs one CTA per design (tp_eval_kernel; gradient
                                   calls, and objective-only calls unless its tables spill); 0 = never */
 } dynoed_kernel_stats;
